@@ -1,0 +1,75 @@
+"""Synthetic "Alexandria-shaped" crystals.
+
+Statistics come from the reference's own dataset probes: mean density 0.0554 atoms/A^3
+(exploration/find_avg_density_of_dataset.py:40) -> 18.05 A^3 per atom; largest cell 236 atoms
+(exploration/largest_system_in_dataset.py:34).  Deterministic in (seed, config); numpy only so
+the oracle, the tests and bench.py all see the same inputs.
+"""
+from __future__ import annotations
+
+from dataclasses import dataclass
+
+import numpy as np
+
+VOLUME_PER_ATOM = 18.05
+NUM_ELEMENT_STATES = 89  # real elements; state 89 is the D3PM mask
+
+
+@dataclass
+class Crystals:
+    frac: np.ndarray       # [N,3] float64 in [0,1)
+    types: np.ndarray      # [N] int64 in [0, 89)
+    lengths: np.ndarray    # [G,3] float64, Angstrom
+    angles: np.ndarray     # [G,3] float64, radians
+    num_atoms: np.ndarray  # [G] int64
+
+    @property
+    def num_crystals(self) -> int:
+        return int(self.num_atoms.shape[0])
+
+    @property
+    def total_atoms(self) -> int:
+        return int(self.num_atoms.sum())
+
+
+def make_crystals(num_crystals: int, atoms_lo: int, atoms_hi: int | None = None, seed: int = 0) -> Crystals:
+    """`atoms_hi=None` -> every crystal has exactly `atoms_lo` atoms, else n ~ U{lo..hi}."""
+    rng = np.random.default_rng(seed)
+    if atoms_hi is None:
+        n = np.full(num_crystals, atoms_lo, dtype=np.int64)
+    else:
+        n = rng.integers(atoms_lo, atoms_hi + 1, size=num_crystals).astype(np.int64)
+    a = np.cbrt(VOLUME_PER_ATOM * n.astype(np.float64))
+    lengths = a[:, None] * (1.0 + 0.1 * rng.standard_normal((num_crystals, 3)))
+    angles = np.pi / 2 + 0.1 * rng.standard_normal((num_crystals, 3))
+    N = int(n.sum())
+    frac = rng.random((N, 3))
+    types = rng.integers(0, NUM_ELEMENT_STATES, size=N).astype(np.int64)
+    return Crystals(frac, types, lengths, angles, n)
+
+
+# BASELINE.json configs: name -> (G, n_lo, n_hi, radius, steps)
+CONFIGS = {
+    "C1": dict(num_crystals=16, atoms_lo=2, atoms_hi=20, radius=5.0, T=11),
+    "C2": dict(num_crystals=1024, atoms_lo=40, atoms_hi=None, radius=5.0, T=1000),
+    "C3": dict(num_crystals=256, atoms_lo=200, atoms_hi=None, radius=7.0, T=1000),
+}
+
+
+def calibrate_length_readout(state: dict, atoms_per_crystal: int, num_layers: int = 5, first_row: int = 91) -> dict:
+    """Quirk B7: with random-init weights the predicted lengths explode and
+    the graph empties within a few steps.  For throughput/trajectory runs scale the three
+    length read-out rows by 1e-3 and set their bias to a_target / n^2 so that
+    x0_hat = len0 * n ~= a_target = (18.05 n)^(1/3); cost and architecture are unchanged.
+    Works on any mapping name -> array (numpy or torch); returns a shallow copy."""
+    out = dict(state)
+    a_target = float(np.cbrt(VOLUME_PER_ATOM * atoms_per_crystal))
+    for l in range(num_layers):
+        w = out[f"read_out_layers.{l}.weight"].copy() if hasattr(out[f"read_out_layers.{l}.weight"], "copy") \
+            else out[f"read_out_layers.{l}.weight"].clone()
+        b = out[f"read_out_layers.{l}.bias"].copy() if hasattr(out[f"read_out_layers.{l}.bias"], "copy") \
+            else out[f"read_out_layers.{l}.bias"].clone()
+        w[first_row:first_row + 3] = w[first_row:first_row + 3] * 1e-3
+        b[first_row:first_row + 3] = a_target / atoms_per_crystal ** 2
+        out[f"read_out_layers.{l}.weight"], out[f"read_out_layers.{l}.bias"] = w, b
+    return out
