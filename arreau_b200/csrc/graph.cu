@@ -1,0 +1,331 @@
+// K1 -- periodic radius graph over the 27 lattice images (sm_100a).
+//
+// Replaces diffusion/diffusion_helpers.py:328-564 (radius_graph_pbc).  The reference materialises
+// ~10 tensors of 27*sum(n_g^2) rows; here one warp owns one receiver atom, walks its 27*n_g
+// candidates in (j, cell) order with lanes striding the candidate index, filters them with a
+// ballot, and (under the neighbour cap) keeps the `cap` nearest through a small shared-memory
+// selection buffer.  No candidate list ever reaches HBM: the only traffic is pos/lattice in
+// (L1/L2 resident per crystal) and the surviving edges out.
+//
+// Arithmetic is fp64 with explicit round-to-nearest adds/muls (no FMA contraction) in the
+// reference's operation order, so thresholds and the cap order are decided on the same bits as
+// the reference:   off_k = (c0*a + c1*b) + c2*c ;  dir = (pos_j + off_k) - pos_i ;
+//                  d2 = (dx*dx + dy*dy) + dz*dz          (helpers:390-409)
+// The image loop is only +-1 cells on unwrapped positions (quirk B3), so there is nothing to bin:
+// with n_g <= 236 atoms a cell list would cost more than the 27*n_g distance tests it saves
+// (C3: 276 M candidates = 5.5 GDFLOP, ~0.2 ms of fp64 on B200).
+#include "common.cuh"
+
+namespace {
+
+constexpr int kWarpsPerBlock = 8;
+constexpr int kSelBuf = 256;      // selection buffer entries per warp
+constexpr int kMaxCap = kSelBuf - 32;
+
+struct WarpCtx {
+  double off[27][3];
+};
+
+__device__ __forceinline__ void cell_of(int k, int& c0, int& c1, int& c2) {
+  // k-th element of itertools.product((-1,0,1), repeat=3)   (helpers:10)
+  c0 = k / 9 - 1;
+  c1 = (k / 3) % 3 - 1;
+  c2 = k % 3 - 1;
+}
+
+__device__ __forceinline__ void load_offsets(WarpCtx& ctx, const double* __restrict__ lat, int lane) {
+  if (lane < 27) {
+    int c0, c1, c2;
+    cell_of(lane, c0, c1, c2);
+#pragma unroll
+    for (int a = 0; a < 3; ++a) {
+      // bmm(lattice^T, cells): sum over lattice rows m = 0,1,2 in order (helpers:390-393)
+      double t0 = __dmul_rn((double)c0, lat[0 * 3 + a]);
+      double t1 = __dmul_rn((double)c1, lat[1 * 3 + a]);
+      double t2 = __dmul_rn((double)c2, lat[2 * 3 + a]);
+      ctx.off[lane][a] = __dadd_rn(__dadd_rn(t0, t1), t2);
+    }
+  }
+  __syncwarp();
+}
+
+__device__ __forceinline__ double cand_d2(const WarpCtx& ctx, const double* __restrict__ pos, int start,
+                                          int c, double pix, double piy, double piz, double& dx,
+                                          double& dy, double& dz) {
+  const int j = c / 27, k = c - j * 27;
+  const double* pj = pos + 3 * (size_t)(start + j);
+  dx = __dadd_rn(__dadd_rn(pj[0], ctx.off[k][0]), -pix);
+  dy = __dadd_rn(__dadd_rn(pj[1], ctx.off[k][1]), -piy);
+  dz = __dadd_rn(__dadd_rn(pj[2], ctx.off[k][2]), -piz);
+  return __dadd_rn(__dadd_rn(__dmul_rn(dx, dx), __dmul_rn(dy, dy)), __dmul_rn(dz, dz));
+}
+
+__device__ __forceinline__ bool cand_pass(double d2, double r2, int remove_self) {
+  return (d2 <= r2) && (!remove_self || d2 > 0.0001);   // helpers:432-436
+}
+
+__global__ void __launch_bounds__(kWarpsPerBlock * 32)
+graph_count_kernel(const double* __restrict__ pos, const double* __restrict__ lattice,
+                   const int32_t* __restrict__ atom_offset, const int32_t* __restrict__ crystal_of_atom,
+                   int N, double r2, int cap, int remove_self, int32_t* __restrict__ raw_count,
+                   int32_t* __restrict__ deg, unsigned long long* __restrict__ nimg) {
+  __shared__ WarpCtx ctxs[kWarpsPerBlock];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int i = blockIdx.x * kWarpsPerBlock + warp;
+  if (i >= N) return;
+  WarpCtx& ctx = ctxs[warp];
+  const int g = crystal_of_atom[i];
+  const int start = atom_offset[g], n = atom_offset[g + 1] - start;
+  load_offsets(ctx, lattice + 9 * (size_t)g, lane);
+  const double pix = pos[3 * (size_t)i], piy = pos[3 * (size_t)i + 1], piz = pos[3 * (size_t)i + 2];
+  int cnt = 0;
+  const int total = 27 * n;
+  for (int c = lane; c < total; c += 32) {
+    double dx, dy, dz;
+    const double d2 = cand_d2(ctx, pos, start, c, pix, piy, piz, dx, dy, dz);
+    cnt += cand_pass(d2, r2, remove_self) ? 1 : 0;
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) cnt += __shfl_xor_sync(0xffffffffu, cnt, o);
+  if (lane == 0) {
+    raw_count[i] = cnt;
+    deg[i] = (cap > 0 && cnt > cap) ? cap : cnt;
+    // helpers:456-465: _max_neighbors[_max_neighbors > threshold] = threshold, summed per crystal
+    // (for cap <= 0 this is the reference's own quirk: zeros / negative numbers)
+    const long long clipped = (cnt > cap) ? (long long)cap : (long long)cnt;
+    atomicAdd(nimg + g, (unsigned long long)clipped);   // integer atomics: order independent
+  }
+}
+
+// Single-CTA exclusive scan (N is at most a few 100k atoms per micro-batch).
+__global__ void __launch_bounds__(1024) scan_kernel(const int32_t* __restrict__ in, int32_t* __restrict__ out, int n) {
+  __shared__ int warp_tot[32];
+  __shared__ int carry_s;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int per = (n + 1023) / 1024;
+  const int lo = min(n, tid * per), hi = min(n, lo + per);
+  int s = 0;
+  for (int k = lo; k < hi; ++k) s += in[k];
+  int incl = s;
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1) {
+    int v = __shfl_up_sync(0xffffffffu, incl, o);
+    if (lane >= o) incl += v;
+  }
+  if (lane == 31) warp_tot[warp] = incl;
+  __syncthreads();
+  if (warp == 0) {
+    int w = warp_tot[lane], wi = w;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      int v = __shfl_up_sync(0xffffffffu, wi, o);
+      if (lane >= o) wi += v;
+    }
+    warp_tot[lane] = wi - w;
+    if (lane == 31) carry_s = wi;
+  }
+  __syncthreads();
+  int run = warp_tot[warp] + incl - s;
+  for (int k = lo; k < hi; ++k) {
+    out[k] = run;
+    run += in[k];
+  }
+  if (tid == 0) out[n] = carry_s;
+}
+
+struct SelEntry {
+  double d2;
+  int c;
+};
+
+// Keep the `cap` smallest entries by (d2, c) ascending, preserving buffer (= candidate) order.
+__device__ __forceinline__ int select_topk(double* sd2, int* sc, unsigned* smask, int m, int cap, int lane) {
+  const int chunks = (m + 31) >> 5;
+  for (int t = 0; t < chunks; ++t) {
+    const int a = t * 32 + lane;
+    bool keep = false;
+    if (a < m) {
+      const double da = sd2[a];
+      const int ca = sc[a];
+      int rank = 0;
+      for (int b = 0; b < m; ++b) {
+        const double db = sd2[b];
+        rank += (db < da || (db == da && sc[b] < ca)) ? 1 : 0;
+      }
+      keep = rank < cap;
+    }
+    const unsigned bal = __ballot_sync(0xffffffffu, keep);
+    if (lane == 0) smask[t] = bal;
+  }
+  __syncwarp();
+  int out = 0;
+  for (int t = 0; t < chunks; ++t) {
+    const int a = t * 32 + lane;
+    const unsigned bal = smask[t];
+    const bool keep = (bal >> lane) & 1u;
+    double da = 0.0;
+    int ca = 0;
+    if (a < m) {
+      da = sd2[a];
+      ca = sc[a];
+    }
+    __syncwarp();
+    if (keep) {
+      const int p = out + __popc(bal & ((1u << lane) - 1u));
+      sd2[p] = da;
+      sc[p] = ca;
+    }
+    out += __popc(bal);
+    __syncwarp();
+  }
+  return out;
+}
+
+__global__ void __launch_bounds__(kWarpsPerBlock * 32)
+graph_fill_kernel(const double* __restrict__ pos, const double* __restrict__ lattice,
+                  const int32_t* __restrict__ atom_offset, const int32_t* __restrict__ crystal_of_atom, int N,
+                  double r2, int cap, int remove_self, const int32_t* __restrict__ raw_count,
+                  const int32_t* __restrict__ row_ptr, long long edge_capacity, int32_t* __restrict__ src,
+                  int32_t* __restrict__ dst, int8_t* __restrict__ cell, double* __restrict__ dist,
+                  double* __restrict__ dir, long long* __restrict__ ei64, double* __restrict__ cell_offsets,
+                  int32_t* __restrict__ overflow_flag) {
+  __shared__ WarpCtx ctxs[kWarpsPerBlock];
+  __shared__ double s_d2[kWarpsPerBlock][kSelBuf];
+  __shared__ int s_c[kWarpsPerBlock][kSelBuf];
+  __shared__ unsigned s_mask[kWarpsPerBlock][kSelBuf / 32];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int i = blockIdx.x * kWarpsPerBlock + warp;
+  if (i >= N) return;
+  WarpCtx& ctx = ctxs[warp];
+  const int g = crystal_of_atom[i];
+  const int start = atom_offset[g], n = atom_offset[g + 1] - start;
+  load_offsets(ctx, lattice + 9 * (size_t)g, lane);
+  const double pix = pos[3 * (size_t)i], piy = pos[3 * (size_t)i + 1], piz = pos[3 * (size_t)i + 2];
+  const long long base = row_ptr[i];
+  const int total = 27 * n;
+  const bool select = cap > 0 && raw_count[i] > cap;
+
+  auto emit = [&](long long e, int c, double d2, double dx, double dy, double dz) {
+    if (e >= edge_capacity) {
+      if (overflow_flag) *overflow_flag = 1;
+      return;
+    }
+    const int j = c / 27, k = c - j * 27;
+    src[e] = start + j;
+    dst[e] = i;
+    cell[e] = (int8_t)k;
+    dist[e] = sqrt(d2);                     // helpers:544 (IEEE correctly rounded)
+    dir[3 * e] = dx;
+    dir[3 * e + 1] = dy;
+    dir[3 * e + 2] = dz;
+    if (ei64) {
+      ei64[e] = start + j;
+      ei64[edge_capacity + e] = i;
+    }
+    if (cell_offsets) {
+      int c0, c1, c2;
+      cell_of(k, c0, c1, c2);
+      cell_offsets[3 * e] = -(double)c0;    // helpers:549 returns -unit_cell
+      cell_offsets[3 * e + 1] = -(double)c1;
+      cell_offsets[3 * e + 2] = -(double)c2;
+    }
+  };
+
+  if (!select) {
+    int written = 0;
+    for (int c0 = 0; c0 < total; c0 += 32) {
+      const int c = c0 + lane;
+      double dx = 0, dy = 0, dz = 0, d2 = 0;
+      bool ok = false;
+      if (c < total) {
+        d2 = cand_d2(ctx, pos, start, c, pix, piy, piz, dx, dy, dz);
+        ok = cand_pass(d2, r2, remove_self);
+      }
+      const unsigned bal = __ballot_sync(0xffffffffu, ok);
+      if (ok) emit(base + written + __popc(bal & ((1u << lane) - 1u)), c, d2, dx, dy, dz);
+      written += __popc(bal);
+    }
+    return;
+  }
+
+  double* sd2 = s_d2[warp];
+  int* sc = s_c[warp];
+  int m = 0;
+  for (int c0 = 0; c0 < total; c0 += 32) {
+    if (m + 32 > kSelBuf) m = select_topk(sd2, sc, s_mask[warp], m, cap, lane);
+    const int c = c0 + lane;
+    double dx, dy, dz, d2 = 0;
+    bool ok = false;
+    if (c < total) {
+      d2 = cand_d2(ctx, pos, start, c, pix, piy, piz, dx, dy, dz);
+      ok = cand_pass(d2, r2, remove_self);
+    }
+    const unsigned bal = __ballot_sync(0xffffffffu, ok);
+    if (ok) {
+      const int p = m + __popc(bal & ((1u << lane) - 1u));
+      sd2[p] = d2;
+      sc[p] = c;
+    }
+    m += __popc(bal);
+    __syncwarp();
+  }
+  if (m > cap) m = select_topk(sd2, sc, s_mask[warp], m, cap, lane);
+  for (int a = lane; a < m; a += 32) {
+    double dx, dy, dz;
+    const int c = sc[a];
+    const double d2 = cand_d2(ctx, pos, start, c, pix, piy, piz, dx, dy, dz);
+    emit(base + a, c, d2, dx, dy, dz);
+  }
+}
+
+}  // namespace
+
+extern "C" int arreau_graph_count(const double* pos, const double* lattice, const int32_t* atom_offset,
+                                  const int32_t* crystal_of_atom, int32_t N, int32_t G, double radius_sq,
+                                  int32_t cap, int32_t remove_self_edges, int32_t* raw_count, int32_t* deg,
+                                  int64_t* num_neighbors_image, void* stream) {
+  if (!pos || !lattice || !atom_offset || !crystal_of_atom || !raw_count || !deg || !num_neighbors_image)
+    return ARREAU_ERR_NULL;
+  if (N < 0 || G < 0) return ARREAU_ERR_BAD_SHAPE;
+  if (cap > kMaxCap) return ARREAU_ERR_UNSUPPORTED;
+  cudaStream_t s = (cudaStream_t)stream;
+  if (G > 0) {
+    cudaError_t e = cudaMemsetAsync(num_neighbors_image, 0, sizeof(int64_t) * (size_t)G, s);
+    if (e != cudaSuccess) return (int)e;
+  }
+  if (N == 0) return ARREAU_OK;
+  const int blocks = (N + kWarpsPerBlock - 1) / kWarpsPerBlock;
+  graph_count_kernel<<<blocks, kWarpsPerBlock * 32, 0, s>>>(pos, lattice, atom_offset, crystal_of_atom, N,
+                                                             radius_sq, cap, remove_self_edges, raw_count, deg,
+                                                             (unsigned long long*)num_neighbors_image);
+  CUDA_LAUNCH_CHECK();
+  return ARREAU_OK;
+}
+
+extern "C" int arreau_graph_scan(const int32_t* deg, int32_t* row_ptr, int32_t n, void* stream) {
+  if (!row_ptr || (n > 0 && !deg)) return ARREAU_ERR_NULL;
+  if (n < 0) return ARREAU_ERR_BAD_SHAPE;
+  scan_kernel<<<1, 1024, 0, (cudaStream_t)stream>>>(deg, row_ptr, n);
+  CUDA_LAUNCH_CHECK();
+  return ARREAU_OK;
+}
+
+extern "C" int arreau_graph_fill(const double* pos, const double* lattice, const int32_t* atom_offset,
+                                 const int32_t* crystal_of_atom, int32_t N, int32_t G, double radius_sq,
+                                 int32_t cap, int32_t remove_self_edges, const int32_t* raw_count,
+                                 const int32_t* row_ptr, int64_t edge_capacity, int32_t* src, int32_t* dst,
+                                 int8_t* cell, double* dist, double* dir, int64_t* edge_index_i64,
+                                 double* cell_offsets, int32_t* overflow_flag, void* stream) {
+  if (N == 0) return ARREAU_OK;
+  if (!pos || !lattice || !atom_offset || !crystal_of_atom || !raw_count || !row_ptr) return ARREAU_ERR_NULL;
+  if (edge_capacity > 0 && (!src || !dst || !cell || !dist || !dir)) return ARREAU_ERR_NULL;
+  if (N < 0 || G < 0 || edge_capacity < 0) return ARREAU_ERR_BAD_SHAPE;
+  if (cap > kMaxCap) return ARREAU_ERR_UNSUPPORTED;
+  const int blocks = (N + kWarpsPerBlock - 1) / kWarpsPerBlock;
+  graph_fill_kernel<<<blocks, kWarpsPerBlock * 32, 0, (cudaStream_t)stream>>>(
+      pos, lattice, atom_offset, crystal_of_atom, N, radius_sq, cap, remove_self_edges, raw_count, row_ptr,
+      (long long)edge_capacity, src, dst, cell, dist, dir, (long long*)edge_index_i64, cell_offsets,
+      overflow_flag);
+  CUDA_LAUNCH_CHECK();
+  return ARREAU_OK;
+}

@@ -1,0 +1,657 @@
+// K2-K7 of the Ponita fiber-bundle forward in fp32 (sm_100a, FFMA2 SIMT path).
+//
+// This is the fp32-grade path (parity within 1e-4 of the fp64 reference).  The dense contractions
+// run as shared-memory tiled SIMT GEMMs on packed FFMA2; the tcgen05 bf16 variants of the two
+// GEMM-shaped kernels live in model_tc.cu and share every other kernel in this file.
+//
+//   node_embed_kernel          K2   position_orientation_graph.py:84-86 + ponita.py:98
+//   fiber_kernel_kernel        K3'  geometry/invariants.py:23, ponita.py:66,95, conv.py:113
+//   edge_kernels_simt_kernel   K3+K4a  invariants -> monomials -> basis MLP -> window -> 5 kernel projections
+//   message_fiber_norm_kernel  K4b+K5 + LayerNorm   conv.py:115,126-133, convnext.py:25
+//   convnext_mlp_simt_kernel   K6   convnext.py:26-32
+//   readout_*_kernel           K7   ponita.py:105-117,152, to_from_sphere.py:10-14
+#include <cuda_bf16.h>
+
+#include "common.cuh"
+
+namespace {
+
+// ------------------------------------------------------------------------------------------------
+// shared SIMT GEMM pass:  acc[128 x 128] += A^T(smem [K][kPitch]) * B(global [K][ldb], 128 columns)
+// 256 threads, thread (ty, tx) owns rows {ty*4..+3, 64+ty*4..+3} x cols {tx*4..+3, 64+tx*4..+3}.
+// B is streamed through a cp.async double buffer in chunks of kKC rows.
+// ------------------------------------------------------------------------------------------------
+constexpr int kTM = 128;
+constexpr int kPitch = 132;
+constexpr int kKC = 16;
+constexpr int kNT = 128;
+constexpr int kGemmThreads = 256;
+
+__device__ __forceinline__ void zero_acc(float2 (&acc)[8][4]) {
+#pragma unroll
+  for (int i = 0; i < 8; ++i)
+#pragma unroll
+    for (int j = 0; j < 4; ++j) acc[i][j] = make_float2(0.f, 0.f);
+}
+
+__device__ __forceinline__ int acc_row(int ty, int i) { return (i < 4) ? (ty * 4 + i) : (64 + ty * 4 + i - 4); }
+__device__ __forceinline__ int acc_col(int tx, int j2) {  // j2 in 0..7
+  return (j2 < 4) ? (tx * 4 + j2) : (64 + tx * 4 + j2 - 4);
+}
+
+template <int K>
+__device__ __forceinline__ void gemm_pass(float2 (&acc)[8][4], const float* __restrict__ As,
+                                          const float* __restrict__ Bg, int ldb, float* __restrict__ Bs, int tid) {
+  static_assert(K % kKC == 0, "K must be a multiple of the chunk");
+  const int ty = tid >> 4, tx = tid & 15;
+  auto load_chunk = [&](int chunk, int buf) {
+#pragma unroll
+    for (int v = tid; v < kKC * kNT / 4; v += kGemmThreads) {
+      const int r = v >> 5, c4 = v & 31;
+      cp_async16(Bs + buf * kKC * kNT + r * kNT + c4 * 4, Bg + (size_t)(chunk * kKC + r) * ldb + c4 * 4);
+    }
+    cp_async_commit();
+  };
+  load_chunk(0, 0);
+  constexpr int kChunks = K / kKC;
+  for (int ch = 0; ch < kChunks; ++ch) {
+    if (ch + 1 < kChunks) {
+      load_chunk(ch + 1, (ch + 1) & 1);
+      cp_async_wait<1>();
+    } else {
+      cp_async_wait<0>();
+    }
+    __syncthreads();
+    const float* b = Bs + (ch & 1) * kKC * kNT;
+    const float* a = As + ch * kKC * kPitch;
+#pragma unroll
+    for (int k = 0; k < kKC; ++k) {
+      const float4 a0 = *reinterpret_cast<const float4*>(a + k * kPitch + ty * 4);
+      const float4 a1 = *reinterpret_cast<const float4*>(a + k * kPitch + 64 + ty * 4);
+      const float4 b0 = *reinterpret_cast<const float4*>(b + k * kNT + tx * 4);
+      const float4 b1 = *reinterpret_cast<const float4*>(b + k * kNT + 64 + tx * 4);
+      const float av[8] = {a0.x, a0.y, a0.z, a0.w, a1.x, a1.y, a1.z, a1.w};
+      const float2 bv[4] = {make_float2(b0.x, b0.y), make_float2(b0.z, b0.w), make_float2(b1.x, b1.y),
+                            make_float2(b1.z, b1.w)};
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        const float2 aa = make_float2(av[i], av[i]);
+#pragma unroll
+        for (int j = 0; j < 4; ++j) acc[i][j] = __ffma2_rn(aa, bv[j], acc[i][j]);
+      }
+    }
+    __syncthreads();
+  }
+}
+
+// acc element (i, j2) with j2 in 0..7
+__device__ __forceinline__ float acc_get(const float2 (&acc)[8][4], int i, int j2) {
+  return (j2 & 1) ? acc[i][j2 >> 1].y : acc[i][j2 >> 1].x;
+}
+
+// ------------------------------------------------------------------------------------------------
+// K2  node embedding
+// ------------------------------------------------------------------------------------------------
+constexpr int kEmbedNodes = 8;
+constexpr int kMaxVec = 8;
+
+__global__ void __launch_bounds__(kC)
+node_embed_kernel(const float* __restrict__ x, const float* __restrict__ vec, const float* __restrict__ w_t,
+                  const float* __restrict__ ori, int N, int F, int V, float* __restrict__ h) {
+  extern __shared__ float sm[];
+  float* xs = sm;                                   // [kEmbedNodes][F]
+  float* dots = sm + kEmbedNodes * F;               // [kEmbedNodes][V][kO]
+  const int c = threadIdx.x;
+  const int b0 = blockIdx.x * kEmbedNodes;
+  const int nb = min(kEmbedNodes, N - b0);
+  for (int idx = c; idx < nb * F; idx += kC) xs[idx] = x[(size_t)b0 * F + idx];
+  for (int idx = c; idx < nb * V * kO; idx += kC) {
+    const int o = idx % kO, v = (idx / kO) % V, b = idx / (kO * V);
+    const float* p = vec + ((size_t)(b0 + b) * V + v) * 3;
+    dots[idx] = p[0] * ori[3 * o] + p[1] * ori[3 * o + 1] + p[2] * ori[3 * o + 2];   // to_from_sphere.py:7-8
+  }
+  __syncthreads();
+  float s[kEmbedNodes];
+#pragma unroll
+  for (int b = 0; b < kEmbedNodes; ++b) s[b] = 0.f;
+  for (int f = 0; f < F; ++f) {
+    const float w = w_t[(size_t)f * kC + c];
+#pragma unroll
+    for (int b = 0; b < kEmbedNodes; ++b) s[b] = fmaf(xs[b * F + f], w, s[b]);   // rows >= nb read stale smem, unused
+  }
+  float wv[kMaxVec];
+#pragma unroll
+  for (int v = 0; v < kMaxVec; ++v) wv[v] = v < V ? w_t[(size_t)(F + v) * kC + c] : 0.f;
+  for (int b = 0; b < nb; ++b) {
+#pragma unroll
+    for (int o = 0; o < kO; ++o) {
+      float r = s[b];
+#pragma unroll
+      for (int v = 0; v < kMaxVec; ++v)
+        if (v < V) r = fmaf(dots[(b * V + v) * kO + o], wv[v], r);
+      h[((size_t)(b0 + b) * kO + o) * kC + c] = r;
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// K3'  fiber kernels (input independent; evaluated in fp64, stored fp32)
+// ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ double gelu_erf_d(double x) { return 0.5 * x * (1.0 + erf(x * 0.70710678118654752440)); }
+
+__global__ void __launch_bounds__(kD)
+fiber_kernel_kernel(const float* __restrict__ ori, const float* __restrict__ w1, const float* __restrict__ b1,
+                    const float* __restrict__ w2, const float* __restrict__ b2, const float* __restrict__ wf,
+                    float* __restrict__ fk) {
+  __shared__ double h1[kC];
+  __shared__ double fkb[kD];
+  const int o = blockIdx.x / kO, p = blockIdx.x % kO, t = threadIdx.x;
+  const double fa = (double)ori[3 * o] * ori[3 * p] + (double)ori[3 * o + 1] * ori[3 * p + 1] +
+                    (double)ori[3 * o + 2] * ori[3 * p + 2];
+  if (t < kC) h1[t] = gelu_erf_d(w1[3 * t] * fa + w1[3 * t + 1] * (fa * fa) + w1[3 * t + 2] * (fa * fa * fa) + b1[t]);
+  __syncthreads();
+  {
+    double s = b2[t];
+    for (int c = 0; c < kC; ++c) s += (double)w2[(size_t)t * kC + c] * h1[c];
+    fkb[t] = gelu_erf_d(s);
+  }
+  __syncthreads();
+  for (int idx = t; idx < kL * kC; idx += kD) {
+    const int l = idx / kC, c = idx % kC;
+    const float* w = wf + ((size_t)l * kC + c) * kD;
+    double s = 0.0;
+    for (int d = 0; d < kD; ++d) s += (double)w[d] * fkb[d];
+    fk[(((size_t)l * kO + o) * kO + p) * kC + c] = (float)s;
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// K3 + K4a  edge pipeline (fp32 SIMT)
+// ------------------------------------------------------------------------------------------------
+constexpr int kEdgesPerTile = kTM / kO;   // 8
+constexpr size_t kEdgeSmemFloats = (size_t)kD * kPitch + (size_t)kC * kPitch + 2 * kKC * kNT;
+
+__global__ void __launch_bounds__(kGemmThreads, 1)
+edge_kernels_simt_kernel(const double* __restrict__ dir, const double* __restrict__ dist,
+                         const double* __restrict__ lattice, const int32_t* __restrict__ crystal_of_atom,
+                         const int32_t* __restrict__ src, const int32_t* __restrict__ num_edges_ptr,
+                         long long edge_capacity, const float* __restrict__ ori, const float* __restrict__ w1m_t,
+                         const float* __restrict__ w2_t, const float* __restrict__ b2,
+                         const float* __restrict__ wk_t, double radius, float* __restrict__ kernels) {
+  extern __shared__ __align__(16) float smem[];
+  float* Xs = smem;                      // [kD][kPitch]: monomials (rows 0..95), later the kernel basis
+  float* Ys = Xs + kD * kPitch;          // [kC][kPitch]: hidden layer of the basis MLP
+  float* Bs = Ys + kC * kPitch;          // [2][kKC][kNT]
+  __shared__ float s_win[kEdgesPerTile];
+  const int tid = threadIdx.x, ty = tid >> 4, tx = tid & 15;
+  long long E = *num_edges_ptr;
+  if (E > edge_capacity) E = edge_capacity;
+  const long long tiles = (E + kEdgesPerTile - 1) / kEdgesPerTile;
+  float2 acc[8][4];
+  for (long long tile = blockIdx.x; tile < tiles; tile += gridDim.x) {
+    // ---- invariants -> 83 monomials + constant 1 (bias row) + zero padding to 96 ----
+    if (tid < kTM) {
+      const int row = tid, o = row & (kO - 1);
+      const long long e = tile * kEdgesPerTile + (row >> 4);
+      float attr[6] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+      float one = 0.f;
+      if (e < E) {
+        const int g = crystal_of_atom[src[e]];
+        edge_invariants(dir + 3 * e, dist[e], lattice + 9 * (size_t)g, ori + 3 * o, attr);
+        one = 1.f;
+        if (o == 0) s_win[row >> 4] = cutoff_window(dist[e], radius);
+      } else if (o == 0) {
+        s_win[row >> 4] = 0.f;
+      }
+      monomials83(attr, Xs + row, kPitch);
+      Xs[kMono * kPitch + row] = one;
+#pragma unroll
+      for (int k = kMono + 1; k < kMonoPad; ++k) Xs[k * kPitch + row] = 0.f;
+    }
+    __syncthreads();
+    // ---- hidden = GELU(W1m . monomials)   (bias folded into the constant row) ----
+    zero_acc(acc);
+    gemm_pass<kMonoPad>(acc, Xs, w1m_t, kC, Bs, tid);
+#pragma unroll
+    for (int j2 = 0; j2 < 8; ++j2) {
+      const int n = acc_col(tx, j2);
+      float4 lo = make_float4(gelu_erf(acc_get(acc, 0, j2)), gelu_erf(acc_get(acc, 1, j2)),
+                              gelu_erf(acc_get(acc, 2, j2)), gelu_erf(acc_get(acc, 3, j2)));
+      float4 hi = make_float4(gelu_erf(acc_get(acc, 4, j2)), gelu_erf(acc_get(acc, 5, j2)),
+                              gelu_erf(acc_get(acc, 6, j2)), gelu_erf(acc_get(acc, 7, j2)));
+      *reinterpret_cast<float4*>(Ys + n * kPitch + ty * 4) = lo;
+      *reinterpret_cast<float4*>(Ys + n * kPitch + 64 + ty * 4) = hi;
+    }
+    // ---- kernel basis = GELU(W2 . hidden + b2) * window ----
+    for (int p = 0; p < kD / kNT; ++p) {
+      zero_acc(acc);
+      gemm_pass<kC>(acc, Ys, w2_t + p * kNT, kD, Bs, tid);
+      float wl[4], wh[4];
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        wl[i] = s_win[(ty * 4 + i) >> 4];
+        wh[i] = s_win[(64 + ty * 4 + i) >> 4];
+      }
+#pragma unroll
+      for (int j2 = 0; j2 < 8; ++j2) {
+        const int n = p * kNT + acc_col(tx, j2);
+        const float bb = b2[n];
+        float4 lo = make_float4(gelu_erf(acc_get(acc, 0, j2) + bb) * wl[0], gelu_erf(acc_get(acc, 1, j2) + bb) * wl[1],
+                                gelu_erf(acc_get(acc, 2, j2) + bb) * wl[2], gelu_erf(acc_get(acc, 3, j2) + bb) * wl[3]);
+        float4 hi = make_float4(gelu_erf(acc_get(acc, 4, j2) + bb) * wh[0], gelu_erf(acc_get(acc, 5, j2) + bb) * wh[1],
+                                gelu_erf(acc_get(acc, 6, j2) + bb) * wh[2], gelu_erf(acc_get(acc, 7, j2) + bb) * wh[3]);
+        *reinterpret_cast<float4*>(Xs + n * kPitch + ty * 4) = lo;
+        *reinterpret_cast<float4*>(Xs + n * kPitch + 64 + ty * 4) = hi;
+      }
+    }
+    // ---- per-layer spatial kernels = Wk_l . kernel basis  -> kernels[l][e][o][c] ----
+    for (int l = 0; l < kL; ++l) {
+      zero_acc(acc);
+      gemm_pass<kD>(acc, Xs, wk_t + l * kNT, kL * kC, Bs, tid);
+      float* out = kernels + (size_t)l * edge_capacity * kO * kC + (size_t)tile * kTM * kC;
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        const int row = acc_row(ty, i);
+        if (tile * kEdgesPerTile + (row >> 4) < E) {
+          *reinterpret_cast<float4*>(out + (size_t)row * kC + tx * 4) =
+              make_float4(acc[i][0].x, acc[i][0].y, acc[i][1].x, acc[i][1].y);
+          *reinterpret_cast<float4*>(out + (size_t)row * kC + 64 + tx * 4) =
+              make_float4(acc[i][2].x, acc[i][2].y, acc[i][3].x, acc[i][3].y);
+        }
+      }
+    }
+    __syncthreads();
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// K4b + K5 + LayerNorm: receiver-sorted CSR reduction, fiber conv, norm.  Deterministic.
+// 128 threads: warp og owns orientations og*4..+3, lane cg owns channels cg*4..+3.
+// ------------------------------------------------------------------------------------------------
+constexpr int kMsgNodes = 4;
+
+__device__ __forceinline__ float4 load_kernel4(const float* p) { return *reinterpret_cast<const float4*>(p); }
+__device__ __forceinline__ float4 load_kernel4(const __nv_bfloat16* p) {
+  const uint2 raw = *reinterpret_cast<const uint2*>(p);
+  const __nv_bfloat162 a = *reinterpret_cast<const __nv_bfloat162*>(&raw.x);
+  const __nv_bfloat162 b = *reinterpret_cast<const __nv_bfloat162*>(&raw.y);
+  const float2 fa = __bfloat1622float2(a), fb = __bfloat1622float2(b);
+  return make_float4(fa.x, fa.y, fb.x, fb.y);
+}
+
+template <typename KT, typename YT>
+__global__ void __launch_bounds__(128)
+message_fiber_norm_kernel(const KT* __restrict__ kern, const float* __restrict__ h, const int32_t* __restrict__ row_ptr,
+                          const int32_t* __restrict__ src, const float* __restrict__ fk,
+                          const float* __restrict__ bias, const float* __restrict__ ln_w,
+                          const float* __restrict__ ln_b, int N, YT* __restrict__ y, float* __restrict__ x1_dbg,
+                          float* __restrict__ x2_dbg) {
+  __shared__ __align__(16) float x1s[kMsgNodes][kO][kC];
+  const int tid = threadIdx.x, og = tid >> 5, cg = tid & 31;
+  const int node0 = blockIdx.x * kMsgNodes;
+#pragma unroll 1
+  for (int nb = 0; nb < kMsgNodes; ++nb) {
+    const int node = node0 + nb;
+    float4 a[4];
+#pragma unroll
+    for (int oo = 0; oo < 4; ++oo) a[oo] = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (node < N) {
+      const int e0 = row_ptr[node], e1 = row_ptr[node + 1];
+      for (int e = e0; e < e1; ++e) {
+        const int s = src[e];
+        const KT* kp = kern + ((size_t)e * kO + og * 4) * kC + cg * 4;
+        const float* hp = h + ((size_t)s * kO + og * 4) * kC + cg * 4;
+        float4 kv[4], hv[4];
+#pragma unroll
+        for (int oo = 0; oo < 4; ++oo) {
+          kv[oo] = load_kernel4(kp + oo * kC);
+          hv[oo] = *reinterpret_cast<const float4*>(hp + oo * kC);
+        }
+#pragma unroll
+        for (int oo = 0; oo < 4; ++oo) {
+          a[oo].x = fmaf(kv[oo].x, hv[oo].x, a[oo].x);
+          a[oo].y = fmaf(kv[oo].y, hv[oo].y, a[oo].y);
+          a[oo].z = fmaf(kv[oo].z, hv[oo].z, a[oo].z);
+          a[oo].w = fmaf(kv[oo].w, hv[oo].w, a[oo].w);
+        }
+      }
+    }
+#pragma unroll
+    for (int oo = 0; oo < 4; ++oo) {
+      *reinterpret_cast<float4*>(&x1s[nb][og * 4 + oo][cg * 4]) = a[oo];
+      if (x1_dbg && node < N)
+        *reinterpret_cast<float4*>(x1_dbg + ((size_t)node * kO + og * 4 + oo) * kC + cg * 4) = a[oo];
+    }
+  }
+  __syncthreads();
+  // fiber conv: x2[nb][p = og*4+pp][c = cg*4..+3] = (1/O) sum_o x1[nb][o][c] * fk[o][p][c] + bias[c]
+  float4 x2[kMsgNodes][4];
+#pragma unroll
+  for (int nb = 0; nb < kMsgNodes; ++nb)
+#pragma unroll
+    for (int pp = 0; pp < 4; ++pp) x2[nb][pp] = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll 4
+  for (int o = 0; o < kO; ++o) {
+    float4 xv[kMsgNodes];
+#pragma unroll
+    for (int nb = 0; nb < kMsgNodes; ++nb) xv[nb] = *reinterpret_cast<const float4*>(&x1s[nb][o][cg * 4]);
+#pragma unroll
+    for (int pp = 0; pp < 4; ++pp) {
+      const float4 f = __ldg(reinterpret_cast<const float4*>(fk + ((size_t)(o * kO + og * 4 + pp)) * kC + cg * 4));
+#pragma unroll
+      for (int nb = 0; nb < kMsgNodes; ++nb) {
+        x2[nb][pp].x = fmaf(xv[nb].x, f.x, x2[nb][pp].x);
+        x2[nb][pp].y = fmaf(xv[nb].y, f.y, x2[nb][pp].y);
+        x2[nb][pp].z = fmaf(xv[nb].z, f.z, x2[nb][pp].z);
+        x2[nb][pp].w = fmaf(xv[nb].w, f.w, x2[nb][pp].w);
+      }
+    }
+  }
+  const float4 bv = *reinterpret_cast<const float4*>(bias + cg * 4);
+  const float4 gw = *reinterpret_cast<const float4*>(ln_w + cg * 4);
+  const float4 gb = *reinterpret_cast<const float4*>(ln_b + cg * 4);
+  constexpr float inv_o = 1.0f / kO;
+#pragma unroll
+  for (int nb = 0; nb < kMsgNodes; ++nb) {
+    const int node = node0 + nb;
+#pragma unroll
+    for (int pp = 0; pp < 4; ++pp) {
+      float4 v = x2[nb][pp];
+      v.x = v.x * inv_o + bv.x;
+      v.y = v.y * inv_o + bv.y;
+      v.z = v.z * inv_o + bv.z;
+      v.w = v.w * inv_o + bv.w;
+      if (x2_dbg && node < N)
+        *reinterpret_cast<float4*>(x2_dbg + ((size_t)node * kO + og * 4 + pp) * kC + cg * 4) = v;
+      // LayerNorm over the 128 channels held by this warp (biased variance, eps 1e-5)
+      const float mean = warp_sum((v.x + v.y) + (v.z + v.w)) * (1.0f / kC);
+      const float dx = v.x - mean, dy = v.y - mean, dz = v.z - mean, dw = v.w - mean;
+      const float var = warp_sum((dx * dx + dy * dy) + (dz * dz + dw * dw)) * (1.0f / kC);
+      const float rstd = 1.0f / sqrtf(var + 1e-5f);
+      float4 r = make_float4(dx * rstd * gw.x + gb.x, dy * rstd * gw.y + gb.y, dz * rstd * gw.z + gb.z,
+                             dw * rstd * gw.w + gb.w);
+      if (node < N) {
+        YT* yp = y + ((size_t)node * kO + og * 4 + pp) * kC + cg * 4;
+        if constexpr (sizeof(YT) == 4) {
+          *reinterpret_cast<float4*>(yp) = r;
+        } else {
+          __nv_bfloat162 p0 = __floats2bfloat162_rn(r.x, r.y), p1 = __floats2bfloat162_rn(r.z, r.w);
+          uint2 raw;
+          raw.x = *reinterpret_cast<unsigned*>(&p0);
+          raw.y = *reinterpret_cast<unsigned*>(&p1);
+          *reinterpret_cast<uint2*>(yp) = raw;
+        }
+      }
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// K6  ConvNext channel MLP (fp32 SIMT): h += layer_scale * (W2 gelu(W1 y + b1) + b2)
+// ------------------------------------------------------------------------------------------------
+constexpr size_t kMlpSmemFloats = 2 * (size_t)kC * kPitch + 2 * kKC * kNT;
+
+__global__ void __launch_bounds__(kGemmThreads, 1)
+convnext_mlp_simt_kernel(const float* __restrict__ y, const float* __restrict__ w1_t, const float* __restrict__ b1,
+                         const float* __restrict__ w2_t, const float* __restrict__ b2,
+                         const float* __restrict__ layer_scale, long long rows, float* __restrict__ h) {
+  extern __shared__ __align__(16) float smem[];
+  float* Ys = smem;                 // [kC][kPitch]  y tile, transposed
+  float* Hs = Ys + kC * kPitch;     // [kC][kPitch]  one 128-wide slice of the hidden layer, transposed
+  float* Bs = Hs + kC * kPitch;
+  const int tid = threadIdx.x, ty = tid >> 4, tx = tid & 15;
+  const long long tiles = (rows + kTM - 1) / kTM;
+  float2 acc1[8][4], acc2[8][4];
+  for (long long tile = blockIdx.x; tile < tiles; tile += gridDim.x) {
+    const long long r0 = tile * kTM;
+    for (int v = tid; v < kTM * kC / 4; v += kGemmThreads) {
+      const int r = v >> 5, k4 = v & 31;
+      float4 val = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (r0 + r < rows) val = *reinterpret_cast<const float4*>(y + (size_t)(r0 + r) * kC + k4 * 4);
+      Ys[(k4 * 4 + 0) * kPitch + r] = val.x;
+      Ys[(k4 * 4 + 1) * kPitch + r] = val.y;
+      Ys[(k4 * 4 + 2) * kPitch + r] = val.z;
+      Ys[(k4 * 4 + 3) * kPitch + r] = val.w;
+    }
+    __syncthreads();
+    zero_acc(acc2);
+    for (int j = 0; j < kW / kNT; ++j) {
+      zero_acc(acc1);
+      gemm_pass<kC>(acc1, Ys, w1_t + j * kNT, kW, Bs, tid);
+#pragma unroll
+      for (int j2 = 0; j2 < 8; ++j2) {
+        const int n = acc_col(tx, j2);
+        const float bb = b1[j * kNT + n];
+        *reinterpret_cast<float4*>(Hs + n * kPitch + ty * 4) =
+            make_float4(gelu_erf(acc_get(acc1, 0, j2) + bb), gelu_erf(acc_get(acc1, 1, j2) + bb),
+                        gelu_erf(acc_get(acc1, 2, j2) + bb), gelu_erf(acc_get(acc1, 3, j2) + bb));
+        *reinterpret_cast<float4*>(Hs + n * kPitch + 64 + ty * 4) =
+            make_float4(gelu_erf(acc_get(acc1, 4, j2) + bb), gelu_erf(acc_get(acc1, 5, j2) + bb),
+                        gelu_erf(acc_get(acc1, 6, j2) + bb), gelu_erf(acc_get(acc1, 7, j2) + bb));
+      }
+      gemm_pass<kNT>(acc2, Hs, w2_t + (size_t)j * kNT * kC, kC, Bs, tid);
+    }
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      const long long row = r0 + acc_row(ty, i);
+      if (row < rows) {
+#pragma unroll
+        for (int half = 0; half < 2; ++half) {
+          const int c0 = half * 64 + tx * 4;
+          float* hp = h + (size_t)row * kC + c0;
+          float4 hv = *reinterpret_cast<float4*>(hp);
+          const float4 bb = *reinterpret_cast<const float4*>(b2 + c0);
+          const float4 ls = *reinterpret_cast<const float4*>(layer_scale + c0);
+          const float2 p0 = acc2[i][half * 2], p1 = acc2[i][half * 2 + 1];
+          hv.x = fmaf(ls.x, p0.x + bb.x, hv.x);
+          hv.y = fmaf(ls.y, p0.y + bb.y, hv.y);
+          hv.z = fmaf(ls.z, p1.x + bb.z, hv.z);
+          hv.w = fmaf(ls.w, p1.y + bb.w, hv.w);
+          *reinterpret_cast<float4*>(hp) = hv;
+        }
+      }
+    }
+    __syncthreads();
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// K7  read-outs.  By linearity the orientation pooling is applied before the Linear:
+//   mean_o (Wr h[b,o] + br) = Wr (mean_o h[b,o]) + br.
+// acc[N][Z+6] = [logits (Z) | score vector (3) | length channels (3)], summed over layers.
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(kC)
+readout_accumulate_kernel(const float* __restrict__ h, const float* __restrict__ wr_t, const float* __restrict__ br,
+                          const float* __restrict__ ori, int N, int Z, int first_layer, float* __restrict__ acc) {
+  __shared__ float hbar[kC];
+  __shared__ float part[4][kO];
+  __shared__ float s_o[kO];
+  const int b = blockIdx.x, c = threadIdx.x, lane = c & 31, warp = c >> 5;
+  const int R = Z + 4;   // read-out rows: Z scalars, 1 vector channel, 3 global scalars (ponita.py:111)
+  const float* hp = h + (size_t)b * kO * kC + c;
+  const float wv = wr_t[(size_t)c * R + Z];
+  float sum = 0.f;
+  float p[kO];
+#pragma unroll
+  for (int o = 0; o < kO; ++o) {
+    const float v = hp[o * kC];
+    sum += v;
+    p[o] = v * wv;
+  }
+  hbar[c] = sum * (1.0f / kO);
+#pragma unroll
+  for (int o = 0; o < kO; ++o) {
+    const float r = warp_sum(p[o]);
+    if (lane == 0) part[warp][o] = r;
+  }
+  __syncthreads();
+  if (c < kO) s_o[c] = ((part[0][c] + part[1][c]) + (part[2][c] + part[3][c])) + br[Z];
+  __syncthreads();
+  float* ab = acc + (size_t)b * (Z + 6);
+  for (int z = c; z < R; z += kC) {
+    if (z == Z) continue;
+    float s = br[z];
+    for (int k = 0; k < kC; ++k) s = fmaf(wr_t[(size_t)k * R + z], hbar[k], s);
+    const int slot = z < Z ? z : (Z + 3 + (z - Z - 1));
+    ab[slot] = first_layer ? s : ab[slot] + s;
+  }
+  if (c < 3) {
+    float s = 0.f;
+#pragma unroll
+    for (int o = 0; o < kO; ++o) s = fmaf(s_o[o], ori[3 * o + c], s);   // to_from_sphere.py:10-11
+    s *= (1.0f / kO);
+    ab[Z + c] = first_layer ? s : ab[Z + c] + s;
+  }
+}
+
+__global__ void readout_finalize_kernel(const float* __restrict__ acc, const int32_t* __restrict__ atom_offset, int N,
+                                        int G, int Z, float inv_layers, float* __restrict__ logits,
+                                        float* __restrict__ score, float* __restrict__ len0) {
+  const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  const long long n_node = (long long)N * (Z + 3);
+  if (idx < n_node) {
+    const int b = (int)(idx / (Z + 3)), k = (int)(idx % (Z + 3));
+    const float v = acc[(size_t)b * (Z + 6) + k] * inv_layers;
+    if (k < Z) logits[(size_t)b * Z + k] = v;
+    else score[(size_t)b * 3 + (k - Z)] = v;
+  } else if (idx < n_node + 3LL * G) {
+    const int g = (int)((idx - n_node) / 3), d = (int)((idx - n_node) % 3);
+    float s = 0.f;   // global_add_pool (ponita.py:152): fixed atom order
+    for (int b = atom_offset[g]; b < atom_offset[g + 1]; ++b) s += acc[(size_t)b * (Z + 6) + Z + 3 + d] * inv_layers;
+    len0[3 * g + d] = s;
+  }
+}
+
+int num_sms() {
+  static int sms = 0;
+  if (!sms) {
+    int dev = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    if (sms <= 0) sms = 148;
+  }
+  return sms;
+}
+
+}  // namespace
+
+// ================================================================================================
+// C ABI
+// ================================================================================================
+extern "C" int arreau_node_embed(const float* x, const float* vec, const float* w_embed_t, const float* ori,
+                                 int32_t N, int32_t F, int32_t V, float* h, void* stream) {
+  if (N == 0) return ARREAU_OK;
+  if (!x || !vec || !w_embed_t || !ori || !h) return ARREAU_ERR_NULL;
+  if (N < 0 || F <= 0 || V < 0 || V > kMaxVec) return ARREAU_ERR_BAD_SHAPE;
+  const size_t smem = sizeof(float) * (size_t)kEmbedNodes * (F + V * kO);
+  if (smem > 48 * 1024) return ARREAU_ERR_UNSUPPORTED;
+  node_embed_kernel<<<(N + kEmbedNodes - 1) / kEmbedNodes, kC, smem, (cudaStream_t)stream>>>(x, vec, w_embed_t, ori,
+                                                                                            N, F, V, h);
+  CUDA_LAUNCH_CHECK();
+  return ARREAU_OK;
+}
+
+extern "C" int arreau_fiber_kernel_precompute(const float* ori, const float* w1, const float* b1, const float* w2,
+                                              const float* b2, const float* wf, float* fiber_kernel, void* stream) {
+  if (!ori || !w1 || !b1 || !w2 || !b2 || !wf || !fiber_kernel) return ARREAU_ERR_NULL;
+  fiber_kernel_kernel<<<kO * kO, kD, 0, (cudaStream_t)stream>>>(ori, w1, b1, w2, b2, wf, fiber_kernel);
+  CUDA_LAUNCH_CHECK();
+  return ARREAU_OK;
+}
+
+extern "C" int arreau_edge_kernels_f32(const double* dir, const double* dist, const double* lattice,
+                                       const int32_t* crystal_of_atom, const int32_t* src,
+                                       const int32_t* num_edges_ptr, int64_t edge_capacity, const float* ori,
+                                       const float* w1m_t, const float* w2_t, const float* b2, const float* wk_t,
+                                       double radius, float* kernels, void* stream) {
+  if (edge_capacity == 0) return ARREAU_OK;
+  if (!dir || !dist || !lattice || !crystal_of_atom || !src || !num_edges_ptr || !ori || !w1m_t || !w2_t || !b2 ||
+      !wk_t || !kernels)
+    return ARREAU_ERR_NULL;
+  if (edge_capacity < 0) return ARREAU_ERR_BAD_SHAPE;
+  static bool attr_set = false;
+  const size_t smem = kEdgeSmemFloats * sizeof(float);
+  if (!attr_set) {
+    cudaError_t e = cudaFuncSetAttribute(edge_kernels_simt_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return (int)e;
+    attr_set = true;
+  }
+  const long long tiles = (edge_capacity + kEdgesPerTile - 1) / kEdgesPerTile;
+  const int grid = (int)(tiles < (long long)num_sms() ? tiles : (long long)num_sms());
+  edge_kernels_simt_kernel<<<grid, kGemmThreads, smem, (cudaStream_t)stream>>>(
+      dir, dist, lattice, crystal_of_atom, src, num_edges_ptr, (long long)edge_capacity, ori, w1m_t, w2_t, b2, wk_t,
+      radius, kernels);
+  CUDA_LAUNCH_CHECK();
+  return ARREAU_OK;
+}
+
+extern "C" int arreau_message_fiber_norm(const void* kernels, int32_t kernels_bf16, const float* h,
+                                         const int32_t* row_ptr, const int32_t* src, const float* fiber_kernel,
+                                         const float* conv_bias, const float* ln_w, const float* ln_b, int32_t N,
+                                         void* y, int32_t y_bf16, float* x1_debug, float* x2_debug, void* stream) {
+  if (N == 0) return ARREAU_OK;
+  if (!h || !row_ptr || !fiber_kernel || !conv_bias || !ln_w || !ln_b || !y) return ARREAU_ERR_NULL;
+  if (N < 0) return ARREAU_ERR_BAD_SHAPE;
+  const int grid = (N + kMsgNodes - 1) / kMsgNodes;
+  cudaStream_t s = (cudaStream_t)stream;
+  if (!kernels_bf16 && !y_bf16)
+    message_fiber_norm_kernel<float, float><<<grid, 128, 0, s>>>((const float*)kernels, h, row_ptr, src, fiber_kernel,
+                                                                 conv_bias, ln_w, ln_b, N, (float*)y, x1_debug, x2_debug);
+  else if (kernels_bf16 && y_bf16)
+    message_fiber_norm_kernel<__nv_bfloat16, __nv_bfloat16><<<grid, 128, 0, s>>>(
+        (const __nv_bfloat16*)kernels, h, row_ptr, src, fiber_kernel, conv_bias, ln_w, ln_b, N, (__nv_bfloat16*)y,
+        x1_debug, x2_debug);
+  else if (kernels_bf16)
+    message_fiber_norm_kernel<__nv_bfloat16, float><<<grid, 128, 0, s>>>((const __nv_bfloat16*)kernels, h, row_ptr, src,
+                                                                         fiber_kernel, conv_bias, ln_w, ln_b, N,
+                                                                         (float*)y, x1_debug, x2_debug);
+  else
+    message_fiber_norm_kernel<float, __nv_bfloat16><<<grid, 128, 0, s>>>((const float*)kernels, h, row_ptr, src,
+                                                                         fiber_kernel, conv_bias, ln_w, ln_b, N,
+                                                                         (__nv_bfloat16*)y, x1_debug, x2_debug);
+  CUDA_LAUNCH_CHECK();
+  return ARREAU_OK;
+}
+
+extern "C" int arreau_convnext_mlp_f32(const float* y, const float* w1_t, const float* b1, const float* w2_t,
+                                       const float* b2, const float* layer_scale, int64_t num_rows, float* h,
+                                       void* stream) {
+  if (num_rows == 0) return ARREAU_OK;
+  if (!y || !w1_t || !b1 || !w2_t || !b2 || !layer_scale || !h) return ARREAU_ERR_NULL;
+  if (num_rows < 0) return ARREAU_ERR_BAD_SHAPE;
+  static bool attr_set = false;
+  const size_t smem = kMlpSmemFloats * sizeof(float);
+  if (!attr_set) {
+    cudaError_t e = cudaFuncSetAttribute(convnext_mlp_simt_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return (int)e;
+    attr_set = true;
+  }
+  const long long tiles = (num_rows + kTM - 1) / kTM;
+  const int grid = (int)(tiles < (long long)num_sms() ? tiles : (long long)num_sms());
+  convnext_mlp_simt_kernel<<<grid, kGemmThreads, smem, (cudaStream_t)stream>>>(y, w1_t, b1, w2_t, b2, layer_scale,
+                                                                                (long long)num_rows, h);
+  CUDA_LAUNCH_CHECK();
+  return ARREAU_OK;
+}
+
+extern "C" int arreau_readout_accumulate(const float* h, const float* wr_t, const float* br, const float* ori,
+                                         int32_t N, int32_t Z, int32_t first_layer, float* acc, void* stream) {
+  if (N == 0) return ARREAU_OK;
+  if (!h || !wr_t || !br || !ori || !acc) return ARREAU_ERR_NULL;
+  if (N < 0 || Z <= 0) return ARREAU_ERR_BAD_SHAPE;
+  readout_accumulate_kernel<<<N, kC, 0, (cudaStream_t)stream>>>(h, wr_t, br, ori, N, Z, first_layer, acc);
+  CUDA_LAUNCH_CHECK();
+  return ARREAU_OK;
+}
+
+extern "C" int arreau_readout_finalize(const float* acc, const int32_t* atom_offset, int32_t N, int32_t G, int32_t Z,
+                                       int32_t num_layers, float* logits, float* score, float* len0, void* stream) {
+  if (N == 0 && G == 0) return ARREAU_OK;
+  if (!acc || !atom_offset || !logits || !score || !len0) return ARREAU_ERR_NULL;
+  if (N < 0 || G < 0 || Z <= 0 || num_layers <= 0) return ARREAU_ERR_BAD_SHAPE;
+  const long long total = (long long)N * (Z + 3) + 3LL * G;
+  readout_finalize_kernel<<<(unsigned)((total + 255) / 256), 256, 0, (cudaStream_t)stream>>>(
+      acc, atom_offset, N, G, Z, 1.0f / (float)num_layers, logits, score, len0);
+  CUDA_LAUNCH_CHECK();
+  return ARREAU_OK;
+}

@@ -1,0 +1,183 @@
+// Host-side orchestration of the step behind the C ABI: the Ponita forward (K2..K7) and the whole
+// denoise step (K9 + K1 + forward + K8) as a fixed sequence of launches on one stream.  No host
+// synchronisation: the edge count stays on the device (row_ptr[N]) and every kernel bounds itself by it.
+#include "common.cuh"
+
+long long g_arreau_launches = 0;
+
+namespace {
+
+// ---- Philox4x32-10 counter-based generator (Salmon et al., SC'11) for throughput-run noise ----
+__device__ __forceinline__ void philox_round(uint32_t (&c)[4], uint32_t k0, uint32_t k1) {
+  const uint32_t hi0 = __umulhi(0xD2511F53u, c[0]), lo0 = 0xD2511F53u * c[0];
+  const uint32_t hi1 = __umulhi(0xCD9E8D57u, c[2]), lo1 = 0xCD9E8D57u * c[2];
+  const uint32_t n0 = hi1 ^ c[1] ^ k0, n1 = lo1, n2 = hi0 ^ c[3] ^ k1, n3 = lo0;
+  c[0] = n0; c[1] = n1; c[2] = n2; c[3] = n3;
+}
+__device__ __forceinline__ void philox4x32_10(uint64_t seed, uint64_t ctr_lo, uint32_t ctr_hi, uint32_t stream_id,
+                                              uint32_t (&out)[4]) {
+  uint32_t c[4] = {(uint32_t)ctr_lo, (uint32_t)(ctr_lo >> 32), ctr_hi, stream_id};
+  uint32_t k0 = (uint32_t)seed, k1 = (uint32_t)(seed >> 32);
+#pragma unroll
+  for (int r = 0; r < 10; ++r) {
+    philox_round(c, k0, k1);
+    k0 += 0x9E3779B9u;
+    k1 += 0xBB67AE85u;
+  }
+#pragma unroll
+  for (int i = 0; i < 4; ++i) out[i] = c[i];
+}
+__device__ __forceinline__ double u01(uint32_t a, uint32_t b) {   // 53-bit uniform in [0,1)
+  const uint64_t v = ((uint64_t)a << 21) ^ (uint64_t)(b >> 11);
+  return (double)(v & ((1ull << 53) - 1)) * (1.0 / 9007199254740992.0);
+}
+
+__global__ void step_noise_kernel(uint64_t seed, int step, long long n_normal, long long n_uniform,
+                                  double* __restrict__ z_len, long long n_len, double* __restrict__ z_frac,
+                                  double* __restrict__ u) {
+  const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  uint32_t r[4];
+  if (idx < (n_normal + 1) / 2) {   // Box-Muller: two normals per counter
+    philox4x32_10(seed, (uint64_t)idx, (uint32_t)step, 0u, r);
+    const double u1 = 1.0 - u01(r[0], r[1]), u2 = u01(r[2], r[3]);   // u1 in (0,1]
+    const double rad = sqrt(-2.0 * log(u1));
+    double s, c;
+    sincospi(2.0 * u2, &s, &c);
+    const long long k0 = 2 * idx, k1 = 2 * idx + 1;
+    const double v0 = rad * c, v1 = rad * s;
+    if (k0 < n_len) z_len[k0] = v0; else z_frac[k0 - n_len] = v0;
+    if (k1 < n_normal) {
+      if (k1 < n_len) z_len[k1] = v1; else z_frac[k1 - n_len] = v1;
+    }
+  }
+  if (idx < (n_uniform + 1) / 2) {
+    philox4x32_10(seed, (uint64_t)idx, (uint32_t)step, 1u, r);
+    u[2 * idx] = u01(r[0], r[1]);
+    if (2 * idx + 1 < n_uniform) u[2 * idx + 1] = u01(r[2], r[3]);
+  }
+}
+
+}  // namespace
+
+extern "C" int arreau_abi_version(void) { return 1; }
+
+extern "C" int arreau_model_dims(int* num_ori, int* hidden, int* basis, int* widening, int* layers) {
+  if (num_ori) *num_ori = kO;
+  if (hidden) *hidden = kC;
+  if (basis) *basis = kD;
+  if (widening) *widening = kW / kC;
+  if (layers) *layers = kL;
+  return ARREAU_OK;
+}
+
+extern "C" int64_t arreau_launch_count(void) { return (int64_t)g_arreau_launches; }
+
+extern "C" int arreau_step_noise(uint64_t seed, int32_t step, int32_t G, int32_t N, int32_t Z, double* z_len,
+                                 double* z_frac, double* u, void* stream) {
+  if (!z_len || !z_frac || !u) return ARREAU_ERR_NULL;
+  if (G < 0 || N < 0 || Z <= 0) return ARREAU_ERR_BAD_SHAPE;
+  const long long n_len = 3LL * G, n_normal = n_len + 3LL * N, n_uniform = (long long)N * Z;
+  const long long work = ((n_normal > n_uniform ? n_normal : n_uniform) + 1) / 2;
+  if (work == 0) return ARREAU_OK;
+  step_noise_kernel<<<(unsigned)((work + 255) / 256), 256, 0, (cudaStream_t)stream>>>(seed, step, n_normal, n_uniform,
+                                                                                     z_len, n_len, z_frac, u);
+  CUDA_LAUNCH_CHECK();
+  return ARREAU_OK;
+}
+
+#define ARREAU_TRY(call)        \
+  do {                          \
+    const int rc__ = (call);    \
+    if (rc__ != ARREAU_OK) return rc__; \
+  } while (0)
+
+extern "C" int arreau_ponita_forward(const arreau_weights* w, const arreau_workspace* ws, int32_t precision,
+                                     const float* x, const float* vec, const int32_t* row_ptr, const int32_t* src,
+                                     const double* dist, const double* dir, const double* lattice,
+                                     const int32_t* atom_offset, const int32_t* crystal_of_atom, int32_t N, int32_t G,
+                                     double radius, float* logits, float* score, float* len0, void* stream) {
+  if (!w || !ws) return ARREAU_ERR_NULL;
+  if (N < 0 || G < 0) return ARREAU_ERR_BAD_SHAPE;
+  if (N == 0) return ARREAU_OK;
+  if (!row_ptr || !ws->h || !ws->y || !ws->acc || (ws->edge_capacity > 0 && !ws->kernels)) return ARREAU_ERR_NULL;
+  if (precision != ARREAU_PRECISION_FP32 && precision != ARREAU_PRECISION_BF16) return ARREAU_ERR_UNSUPPORTED;
+  const bool bf16 = precision == ARREAU_PRECISION_BF16;
+  const int Z = w->num_states;
+  const size_t node_elems = (size_t)N * kO * kC;
+  cudaStream_t s = (cudaStream_t)stream;
+  ARREAU_TRY(arreau_node_embed(x, vec, w->w_embed_t, w->ori, N, w->num_scalar, w->num_vec, ws->h, stream));
+  if (ws->h_debug) {
+    cudaError_t e = cudaMemcpyAsync(ws->h_debug, ws->h, node_elems * sizeof(float), cudaMemcpyDeviceToDevice, s);
+    if (e != cudaSuccess) return (int)e;
+  }
+  const int32_t* num_edges_ptr = row_ptr + N;
+  if (bf16)
+    ARREAU_TRY(arreau_edge_kernels_bf16(dir, dist, lattice, crystal_of_atom, src, num_edges_ptr, ws->edge_capacity,
+                                        w->ori, w->w1m_bf16, w->w2_bf16, w->b2, w->wk_bf16, radius, ws->kernels,
+                                        stream));
+  else
+    ARREAU_TRY(arreau_edge_kernels_f32(dir, dist, lattice, crystal_of_atom, src, num_edges_ptr, ws->edge_capacity,
+                                       w->ori, w->w1m_t, w->w2_t, w->b2, w->wk_t, radius, (float*)ws->kernels,
+                                       stream));
+  const size_t layer_elems = (size_t)ws->edge_capacity * kO * kC;
+  for (int l = 0; l < kL; ++l) {
+    const void* kern = bf16 ? (const void*)((const uint16_t*)ws->kernels + (size_t)l * layer_elems)
+                            : (const void*)((const float*)ws->kernels + (size_t)l * layer_elems);
+    ARREAU_TRY(arreau_message_fiber_norm(kern, bf16, ws->h, row_ptr, src, w->fiber_kernel + (size_t)l * kO * kO * kC,
+                                         w->conv_bias + l * kC, w->ln_w + l * kC, w->ln_b + l * kC, N, ws->y, bf16,
+                                         ws->x1_debug ? ws->x1_debug + l * node_elems : nullptr,
+                                         ws->x2_debug ? ws->x2_debug + l * node_elems : nullptr, stream));
+    if (bf16)
+      ARREAU_TRY(arreau_convnext_mlp_bf16(ws->y, (const uint16_t*)w->mlp_w1_bf16 + (size_t)l * kW * kC,
+                                          w->mlp_b1 + l * kW, (const uint16_t*)w->mlp_w2_bf16 + (size_t)l * kC * kW,
+                                          w->mlp_b2 + l * kC, w->layer_scale + l * kC, (int64_t)N * kO, ws->h,
+                                          stream));
+    else
+      ARREAU_TRY(arreau_convnext_mlp_f32((const float*)ws->y, w->mlp_w1_t + (size_t)l * kC * kW, w->mlp_b1 + l * kW,
+                                         w->mlp_w2_t + (size_t)l * kW * kC, w->mlp_b2 + l * kC,
+                                         w->layer_scale + l * kC, (int64_t)N * kO, ws->h, stream));
+    if (ws->h_debug) {
+      cudaError_t e = cudaMemcpyAsync(ws->h_debug + (size_t)(l + 1) * node_elems, ws->h, node_elems * sizeof(float),
+                                      cudaMemcpyDeviceToDevice, s);
+      if (e != cudaSuccess) return (int)e;
+    }
+    ARREAU_TRY(arreau_readout_accumulate(ws->h, w->wr_t + (size_t)l * kC * (Z + 4), w->br + l * (Z + 4), w->ori, N, Z,
+                                         l == 0, ws->acc, stream));
+  }
+  ARREAU_TRY(arreau_readout_finalize(ws->acc, atom_offset, N, G, Z, kL, logits, score, len0, stream));
+  return ARREAU_OK;
+}
+
+extern "C" int arreau_denoise_step(const arreau_weights* w, const arreau_workspace* ws, const arreau_step_args* a,
+                                   void* stream) {
+  if (!w || !ws || !a) return ARREAU_ERR_NULL;
+  const int N = a->num_atoms_total, G = a->num_crystals, Z = w->num_states;
+  if (N < 0 || G < 0) return ARREAU_ERR_BAD_SHAPE;
+  if (N == 0 || G == 0) return ARREAU_OK;
+  if (w->num_scalar != Z + 2 * a->emb + 10 || w->num_vec != 4) return ARREAU_ERR_BAD_SHAPE;
+  // predict_scores: lattice, features, cartesian positions, graph, network   (diffusion_loss.py:112-197)
+  ARREAU_TRY(arreau_lattice_from_params(a->lengths, a->angles, G, a->lattice, stream));
+  ARREAU_TRY(arreau_assemble_features(a->frac, a->types, a->lengths, a->angles, a->lattice, a->atom_offset,
+                                      a->crystal_of_atom, nullptr, a->t, a->vp_betas, a->fourier_w, a->emb, N, G, Z,
+                                      a->x, a->vec, stream));
+  ARREAU_TRY(arreau_frac_to_cart(a->frac, a->lattice, a->crystal_of_atom, N, a->pos, stream));
+  const double r2 = a->radius * a->radius;
+  ARREAU_TRY(arreau_graph_count(a->pos, a->lattice, a->atom_offset, a->crystal_of_atom, N, G, r2, a->cap, 1,
+                                a->raw_count, a->deg, a->num_neighbors_image, stream));
+  ARREAU_TRY(arreau_graph_scan(a->deg, a->row_ptr, N, stream));
+  ARREAU_TRY(arreau_graph_fill(a->pos, a->lattice, a->atom_offset, a->crystal_of_atom, N, G, r2, a->cap, 1,
+                               a->raw_count, a->row_ptr, ws->edge_capacity, a->src, a->dst, a->cell, a->dist, a->dir,
+                               nullptr, nullptr, a->overflow_flag, stream));
+  ARREAU_TRY(arreau_ponita_forward(w, ws, a->precision, a->x, a->vec, a->row_ptr, a->src, a->dist, a->dir, a->lattice,
+                                   a->atom_offset, a->crystal_of_atom, N, G, a->radius, a->logits, a->score, a->len0,
+                                   stream));
+  // update: lengths, lattice, fractional coordinates, atom types   (diffusion_loss.py:338-349)
+  ARREAU_TRY(arreau_vp_lattice_reverse(a->lengths, a->len0, a->atom_offset, a->z_len, a->t, a->vp_cx0, a->vp_cxt,
+                                       a->vp_denom, a->vp_var, G, a->lengths, stream));
+  ARREAU_TRY(arreau_lattice_from_params(a->lengths, a->angles, G, a->lattice, stream));
+  ARREAU_TRY(arreau_ve_pbc_reverse(a->frac, a->score, a->z_frac, nullptr, a->t, a->ve_sigmas, N, a->frac, stream));
+  if (a->update_types)
+    ARREAU_TRY(arreau_d3pm_reverse(a->types, a->logits, a->u_type, nullptr, a->t, a->q_keep, a->q_to_mask,
+                                   a->onestep_keep, a->onestep_to_mask, a->num_steps, N, Z, a->types, stream));
+  return ARREAU_OK;
+}

@@ -1,0 +1,239 @@
+"""DenoiseEngine: device buffers + launch sequences of the denoising step.
+
+Host logic only (buffer ownership, argument structs, the sampler loop); every computation is a kernel
+of libarreau_b200.so reached through arreau_b200._lib.  One engine = one batch topology (num_atoms per
+crystal) on one GPU.  Mirrors the loop body of DiffusionLoss.sample (diffusion/diffusion_loss.py:318-349).
+"""
+from __future__ import annotations
+
+import ctypes as C
+from typing import Optional, Sequence, Tuple
+
+import numpy as np
+import torch
+
+from . import _lib
+from .tables import DiffusionTables
+from .weights import HIDDEN, LAYERS, NUM_ORI, PonitaWeights
+
+PRECISIONS = {"fp32": _lib.PRECISION_FP32, "bf16": _lib.PRECISION_BF16}
+
+
+def _i32(a, device):
+    return torch.as_tensor(np.asarray(a), dtype=torch.int32).to(device)
+
+
+class DenoiseEngine:
+    def __init__(self, weights: PonitaWeights, tables: DiffusionTables, fourier_w, num_atoms: Sequence[int],
+                 radius: float, max_neighbors: int, precision: str = "fp32", edge_capacity: Optional[int] = None,
+                 debug: bool = False, device="cuda"):
+        if precision not in PRECISIONS:
+            raise ValueError(f"precision must be one of {sorted(PRECISIONS)}")
+        _lib.load()
+        self.w, self.tabs = weights, tables
+        self.device = torch.device(device)
+        self.precision, self.debug = precision, debug
+        self.radius, self.cap = float(radius), int(max_neighbors)
+        na = np.asarray(num_atoms, dtype=np.int64).reshape(-1)
+        self.G, self.N = int(na.shape[0]), int(na.sum())
+        self.Z = weights.num_states
+        if tables.Z != self.Z:
+            raise ValueError(f"tables built for {tables.Z} atom states, weights have {self.Z}")
+        dev = self.device
+        off = np.zeros(self.G + 1, dtype=np.int64)
+        np.cumsum(na, out=off[1:])
+        self.num_atoms = torch.as_tensor(na).to(dev)
+        self.atom_offset = _i32(off, dev)
+        self.crystal_of_atom = _i32(np.repeat(np.arange(self.G), na), dev)
+        f64 = lambda *s: torch.zeros(*s, dtype=torch.float64, device=dev)  # noqa: E731
+        f32 = lambda *s: torch.zeros(*s, dtype=torch.float32, device=dev)  # noqa: E731
+        i32 = lambda *s: torch.zeros(*s, dtype=torch.int32, device=dev)  # noqa: E731
+        N, G, Z = self.N, self.G, self.Z
+        # diffusion state (fp64 / i64, like the reference)
+        self.frac, self.types = f64(N, 3), torch.zeros(N, dtype=torch.int64, device=dev)
+        self.lengths, self.angles, self.lattice = f64(G, 3), f64(G, 3), f64(G, 3, 3)
+        # graph scratch
+        self.pos, self.raw_count, self.deg, self.row_ptr = f64(N, 3), i32(N), i32(N), i32(N + 1)
+        self.num_neighbors_image = torch.zeros(G, dtype=torch.int64, device=dev)
+        self.overflow_flag = i32(1)
+        # network io
+        self.F = weights.num_scalar
+        self.emb = (self.F - Z - 10) // 2
+        self.x, self.vec = f32(N, self.F), f32(N, 4, 3)
+        self.logits, self.score, self.len0 = f32(N, Z), f32(N, 3), f32(G, 3)
+        self.h, self.acc = f32(N, NUM_ORI, HIDDEN), f32(N, Z + 6)
+        self.y = torch.zeros(N, NUM_ORI, HIDDEN, device=dev,
+                             dtype=torch.bfloat16 if precision == "bf16" else torch.float32)
+        self.t_of_atom = i32(N)
+        # noise
+        self.z_len, self.z_frac, self.u_type = f64(G, 3), f64(N, 3), f64(N, Z)
+        # tables
+        self.d_vp_betas = tables.vp_betas.to(torch.float64).to(dev)
+        self.d_ve_sigmas = tables.ve_sigmas.to(torch.float64).to(dev)
+        self.d_q_keep, self.d_q_to_mask = tables.q_keep.to(dev), tables.q_to_mask.to(dev)
+        self.d_fourier_w = torch.as_tensor(np.asarray(fourier_w.detach().cpu() if isinstance(fourier_w, torch.Tensor)
+                                                      else fourier_w), dtype=torch.float64).to(dev)
+        if self.d_fourier_w.numel() != self.emb:
+            raise ValueError(f"time embedding has {self.d_fourier_w.numel()} frequencies, the model expects {self.emb}")
+        self.edge_capacity = -1
+        self._alloc_edges(int(edge_capacity) if edge_capacity is not None else
+                          (N * self.cap if self.cap > 0 else max(1, 32 * N)))
+
+    # ------------------------------------------------------------------ buffers
+    def _alloc_edges(self, capacity: int) -> None:
+        dev, N = self.device, self.N
+        capacity = max(int(capacity), 1)
+        self.edge_capacity = capacity
+        self.src = torch.zeros(capacity, dtype=torch.int32, device=dev)
+        self.dst = torch.zeros(capacity, dtype=torch.int32, device=dev)
+        self.cell = torch.zeros(capacity, dtype=torch.int8, device=dev)
+        self.dist = torch.zeros(capacity, dtype=torch.float64, device=dev)
+        self.dir = torch.zeros(capacity, 3, dtype=torch.float64, device=dev)
+        kdt = torch.bfloat16 if self.precision == "bf16" else torch.float32
+        self.kernels = torch.empty(LAYERS, capacity, NUM_ORI, HIDDEN, dtype=kdt, device=dev)
+        node = (N, NUM_ORI, HIDDEN)
+        if self.debug:
+            self.x1_debug = torch.zeros(LAYERS, *node, dtype=torch.float32, device=dev)
+            self.x2_debug = torch.zeros(LAYERS, *node, dtype=torch.float32, device=dev)
+            self.h_debug = torch.zeros(LAYERS + 1, *node, dtype=torch.float32, device=dev)
+        else:
+            self.x1_debug = self.x2_debug = self.h_debug = None
+        ws = _lib.Workspace()
+        ws.h, ws.y, ws.kernels, ws.acc = self.h.data_ptr(), self.y.data_ptr(), self.kernels.data_ptr(), self.acc.data_ptr()
+        ws.x1_debug, ws.x2_debug, ws.h_debug = _lib.ptr(self.x1_debug), _lib.ptr(self.x2_debug), _lib.ptr(self.h_debug)
+        ws.edge_capacity = capacity
+        self.ws = ws
+        a = _lib.StepArgs()
+        p = _lib.ptr
+        a.frac, a.types, a.lengths, a.angles, a.lattice = p(self.frac), p(self.types), p(self.lengths), p(self.angles), p(self.lattice)
+        a.atom_offset, a.crystal_of_atom = p(self.atom_offset), p(self.crystal_of_atom)
+        a.num_atoms_total, a.num_crystals = self.N, self.G
+        a.pos, a.raw_count, a.deg, a.row_ptr = p(self.pos), p(self.raw_count), p(self.deg), p(self.row_ptr)
+        a.num_neighbors_image = p(self.num_neighbors_image)
+        a.src, a.dst, a.cell, a.dist, a.dir = p(self.src), p(self.dst), p(self.cell), p(self.dist), p(self.dir)
+        a.overflow_flag = p(self.overflow_flag)
+        a.x, a.vec, a.logits, a.score, a.len0 = p(self.x), p(self.vec), p(self.logits), p(self.score), p(self.len0)
+        a.z_len, a.z_frac, a.u_type = p(self.z_len), p(self.z_frac), p(self.u_type)
+        a.vp_betas, a.fourier_w, a.ve_sigmas = p(self.d_vp_betas), p(self.d_fourier_w), p(self.d_ve_sigmas)
+        a.q_keep, a.q_to_mask = p(self.d_q_keep), p(self.d_q_to_mask)
+        a.onestep_keep, a.onestep_to_mask = self.tabs.onestep_keep, self.tabs.onestep_to_mask
+        a.emb, a.num_steps, a.cap, a.radius = self.emb, self.tabs.T, self.cap, self.radius
+        a.precision, a.update_types = PRECISIONS[self.precision], 1
+        self.args = a
+
+    @property
+    def stream(self) -> int:
+        return torch.cuda.current_stream(self.device).cuda_stream
+
+    # ------------------------------------------------------------------ state
+    def set_state(self, frac, types, lengths, angles) -> None:
+        """Copies the diffusion state (any float dtype / host or device) into the engine's fp64 buffers."""
+        self.frac.copy_(torch.as_tensor(frac).reshape(self.N, 3), non_blocking=True)
+        self.types.copy_(torch.as_tensor(types).reshape(self.N), non_blocking=True)
+        self.lengths.copy_(torch.as_tensor(lengths).reshape(self.G, 3), non_blocking=True)
+        self.angles.copy_(torch.as_tensor(angles).reshape(self.G, 3), non_blocking=True)
+
+    def set_noise(self, z_len, z_frac, u_type) -> None:
+        self.z_len.copy_(torch.as_tensor(z_len).reshape(self.G, 3), non_blocking=True)
+        self.z_frac.copy_(torch.as_tensor(z_frac).reshape(self.N, 3), non_blocking=True)
+        self.u_type.copy_(torch.as_tensor(u_type).reshape(self.N, self.Z), non_blocking=True)
+
+    def draw_noise(self, seed: int, step: int) -> None:
+        """Philox noise on the device for throughput runs (the reference draws torch CPU noise)."""
+        _lib.call("arreau_step_noise", C.c_uint64(seed), step, self.G, self.N, self.Z, self.z_len.data_ptr(),
+                  self.z_frac.data_ptr(), self.u_type.data_ptr(), self.stream)
+
+    # ------------------------------------------------------------------ graph
+    def _count(self) -> None:
+        s = self.stream
+        _lib.call("arreau_graph_count", self.pos.data_ptr(), self.lattice.data_ptr(), self.atom_offset.data_ptr(),
+                  self.crystal_of_atom.data_ptr(), self.N, self.G, self.radius * self.radius, self.cap, 1,
+                  self.raw_count.data_ptr(), self.deg.data_ptr(), self.num_neighbors_image.data_ptr(), s)
+        _lib.call("arreau_graph_scan", self.deg.data_ptr(), self.row_ptr.data_ptr(), self.N, s)
+
+    def _ensure_capacity(self) -> None:
+        """Uncapped graphs only: the edge count is data dependent, so size the buffers from the count
+        (one host synchronisation; with a positive cap E <= N*cap and nothing is read back)."""
+        if self.cap > 0:
+            return
+        self._count()
+        E = int(self.row_ptr[self.N].item())
+        if E > self.edge_capacity:
+            self._alloc_edges(int(E * 1.25) + 1024)
+
+    def build_graph(self, edge_index_i64: Optional[torch.Tensor] = None, cell_offsets: Optional[torch.Tensor] = None):
+        """lattice/pos must be current.  count -> scan -> fill."""
+        s = self.stream
+        self._count()
+        self.overflow_flag.zero_()
+        _lib.call("arreau_graph_fill", self.pos.data_ptr(), self.lattice.data_ptr(), self.atom_offset.data_ptr(),
+                  self.crystal_of_atom.data_ptr(), self.N, self.G, self.radius * self.radius, self.cap, 1,
+                  self.raw_count.data_ptr(), self.row_ptr.data_ptr(), self.edge_capacity, self.src.data_ptr(),
+                  self.dst.data_ptr(), self.cell.data_ptr(), self.dist.data_ptr(), self.dir.data_ptr(),
+                  _lib.ptr(edge_index_i64), _lib.ptr(cell_offsets), self.overflow_flag.data_ptr(), s)
+
+    def num_edges(self) -> int:
+        return int(self.row_ptr[self.N].item())
+
+    # ------------------------------------------------------------------ predict_scores
+    def prepare_inputs(self, t) -> None:
+        """lattice_from_params, feature assembly, frac -> cart (diffusion_loss.py:124-158)."""
+        s = self.stream
+        if isinstance(t, int):
+            t_ptr, t_scalar = None, t
+        else:
+            self.t_of_atom.copy_(torch.as_tensor(t).reshape(self.N).to(torch.int32), non_blocking=True)
+            t_ptr, t_scalar = self.t_of_atom.data_ptr(), 0
+        _lib.call("arreau_lattice_from_params", self.lengths.data_ptr(), self.angles.data_ptr(), self.G,
+                  self.lattice.data_ptr(), s)
+        _lib.call("arreau_assemble_features", self.frac.data_ptr(), self.types.data_ptr(), self.lengths.data_ptr(),
+                  self.angles.data_ptr(), self.lattice.data_ptr(), self.atom_offset.data_ptr(),
+                  self.crystal_of_atom.data_ptr(), t_ptr, t_scalar, self.d_vp_betas.data_ptr(),
+                  self.d_fourier_w.data_ptr(), self.emb, self.N, self.G, self.Z, self.x.data_ptr(),
+                  self.vec.data_ptr(), s)
+        _lib.call("arreau_frac_to_cart", self.frac.data_ptr(), self.lattice.data_ptr(), self.crystal_of_atom.data_ptr(),
+                  self.N, self.pos.data_ptr(), s)
+
+    def forward(self, x=None, vec=None) -> Tuple[torch.Tensor, torch.Tensor, torch.Tensor]:
+        """PonitaFiberBundle.forward on the engine's current graph; returns (logits, score, len0) f32."""
+        x = self.x if x is None else x
+        vec = self.vec if vec is None else vec
+        _lib.call("arreau_ponita_forward", self.w.ref(), C.byref(self.ws), PRECISIONS[self.precision], x.data_ptr(),
+                  vec.data_ptr(), self.row_ptr.data_ptr(), self.src.data_ptr(), self.dist.data_ptr(),
+                  self.dir.data_ptr(), self.lattice.data_ptr(), self.atom_offset.data_ptr(),
+                  self.crystal_of_atom.data_ptr(), self.N, self.G, self.radius, self.logits.data_ptr(),
+                  self.score.data_ptr(), self.len0.data_ptr(), self.stream)
+        return self.logits, self.score, self.len0
+
+    def predict_scores(self, t) -> Tuple[torch.Tensor, torch.Tensor, torch.Tensor]:
+        """DiffusionLoss.predict_scores (diffusion_loss.py:112-197) on the engine state.
+        Returns (score[N,3], logits[N,Z], len0[G,3]) as fp32 device tensors (views of engine buffers)."""
+        self.prepare_inputs(t)
+        self._ensure_capacity()
+        self.build_graph()
+        self.forward()
+        return self.score, self.logits, self.len0
+
+    # ------------------------------------------------------------------ step
+    def step(self, t: int, update_types: bool = True) -> None:
+        """One iteration of the sampler loop (diffusion_loss.py:319-349), in place, using the noise
+        currently in z_len / z_frac / u_type.  A single C call, no host synchronisation when cap > 0."""
+        tb = self.tabs
+        if not (1 <= t <= tb.T):
+            raise ValueError(f"timestep {t} outside 1..{tb.T}")
+        if self.cap <= 0:
+            self.prepare_inputs(t)
+            self._ensure_capacity()
+        a = self.args
+        a.t = int(t)
+        a.vp_cx0, a.vp_cxt = float(tb.vp_cx0[t]), float(tb.vp_cxt[t])
+        a.vp_denom, a.vp_var = float(tb.vp_denom[t]), float(tb.vp_var[t])
+        a.update_types = 1 if update_types else 0
+        _lib.call("arreau_denoise_step", self.w.ref(), C.byref(self.ws), C.byref(a), self.stream)
+
+    def edges(self):
+        """Current edge list as (src, dst, cell, dist, dir) trimmed to E (host synchronisation)."""
+        E = self.num_edges()
+        if int(self.overflow_flag.item()):
+            raise RuntimeError("edge capacity overflow")
+        return self.src[:E], self.dst[:E], self.cell[:E], self.dist[:E], self.dir[:E]

@@ -1,0 +1,122 @@
+"""Reference state_dict -> device weight layouts of the kernels.
+
+Parameter names are the reference's: basis_fn.{1,3}.*, fiber_basis_fn.{1,3}.*, x_embedder.weight,
+interaction_layers.{l}.{layer_scale, conv.bias, conv.kernel.weight, conv.fiber_kernel.weight, linear_1.*,
+linear_2.*, norm.*}, read_out_layers.{l}.*.  The orientation grid is not part of the state_dict (quirk B2)
+and is passed explicitly.
+"""
+from __future__ import annotations
+
+import ctypes as C
+from typing import Dict, Mapping
+
+import numpy as np
+import torch
+
+from . import _lib
+
+NUM_ORI, HIDDEN, BASIS, WIDEN, LAYERS = 16, 128, 256, 4, 5
+NUM_MONO, MONO_PAD = 83, 96
+
+
+def monomial_fold_table(num_in: int = 6, degree: int = 3) -> np.ndarray:
+    """Index of the distinct monomial each PolynomialFeatures(3) output equals
+    (ponita/nn/embedding.py:10-14: [x, x(x)x, (x(x)x)(x)x], index = previous*6 + j).
+    Monomial order = csrc/common.cuh monomials83(): all i, all i<=j, all i<=j<=k."""
+    assert num_in == 6 and degree == 3
+    ids: Dict[tuple, int] = {}
+    for i in range(6):
+        ids[(i,)] = len(ids)
+    for i in range(6):
+        for j in range(i, 6):
+            ids[(i, j)] = len(ids)
+    for i in range(6):
+        for j in range(i, 6):
+            for k in range(j, 6):
+                ids[(i, j, k)] = len(ids)
+    assert len(ids) == NUM_MONO
+    table = []
+    for i in range(6):
+        table.append(ids[(i,)])
+    for i in range(6):
+        for j in range(6):
+            table.append(ids[tuple(sorted((i, j)))])
+    for i in range(6):
+        for j in range(6):
+            for k in range(6):
+                table.append(ids[tuple(sorted((i, j, k)))])
+    return np.asarray(table, dtype=np.int64)   # [258]
+
+
+def _np(v) -> np.ndarray:
+    if isinstance(v, torch.Tensor):
+        return v.detach().cpu().double().numpy()
+    return np.asarray(v, dtype=np.float64)
+
+
+class PonitaWeights:
+    """Device copies of one PonitaFiberBundle's parameters in kernel layouts."""
+
+    def __init__(self, state: Mapping[str, object], ori_grid, device="cuda", with_bf16: bool = True):
+        sd = {k: _np(v) for k, v in state.items() if hasattr(v, "shape") and np.prod(np.shape(v)) > 0
+              and not k.endswith("callibrated") and not k.startswith("windowing_fn")}
+        self.device = torch.device(device)
+        ori = _np(ori_grid)
+        if ori.shape != (NUM_ORI, 3):
+            raise ValueError(f"unsupported orientation grid {ori.shape}: kernels are specialised on {NUM_ORI}")
+        w1 = sd["basis_fn.1.weight"]
+        if w1.shape != (HIDDEN, 258) or sd["basis_fn.3.weight"].shape != (BASIS, HIDDEN):
+            raise ValueError("unsupported model dims: kernels are specialised on hidden 128 / basis 256 / degree 3")
+        L = LAYERS
+        for l in range(L):
+            if f"interaction_layers.{l}.conv.kernel.weight" not in sd:
+                raise ValueError(f"expected {L} interaction layers")
+        if f"interaction_layers.{L}.conv.kernel.weight" in sd:
+            raise ValueError(f"unsupported number of layers (kernels are specialised on {L})")
+        fold = monomial_fold_table()
+        w1m = np.zeros((HIDDEN, NUM_MONO))
+        np.add.at(w1m, (slice(None), fold), w1)           # sum the columns of equal monomials (fp64)
+        w1m_t = np.zeros((MONO_PAD, HIDDEN))
+        w1m_t[:NUM_MONO] = w1m.T
+        w1m_t[NUM_MONO] = sd["basis_fn.1.bias"]            # constant-1 monomial carries the bias
+        lay = lambda name: np.stack([sd[f"interaction_layers.{l}.{name}"] for l in range(L)])  # noqa: E731
+        wk = lay("conv.kernel.weight")                     # [L,C,D]
+        wemb = sd["x_embedder.weight"]                     # [C, F+V]
+        wr = np.stack([sd[f"read_out_layers.{l}.weight"] for l in range(L)])   # [L,R,C]
+        br = np.stack([sd[f"read_out_layers.{l}.bias"] for l in range(L)])
+        self.num_readout = wr.shape[1]
+        self.num_states = self.num_readout - 4             # scalars | 1 vector | 0 global vec | 3 global scalars
+        self.num_vec = 4
+        self.num_scalar = wemb.shape[1] - self.num_vec
+        f32 = lambda a: torch.as_tensor(np.ascontiguousarray(a), dtype=torch.float32).to(self.device)  # noqa: E731
+        self.t: Dict[str, torch.Tensor] = dict(
+            ori=f32(ori), w_embed_t=f32(wemb.T), w1m_t=f32(w1m_t), w2_t=f32(sd["basis_fn.3.weight"].T),
+            b2=f32(sd["basis_fn.3.bias"]), wk_t=f32(wk.transpose(2, 0, 1).reshape(BASIS, L * HIDDEN)),
+            conv_bias=f32(lay("conv.bias")), ln_w=f32(lay("norm.weight")), ln_b=f32(lay("norm.bias")),
+            mlp_w1_t=f32(lay("linear_1.weight").transpose(0, 2, 1)), mlp_b1=f32(lay("linear_1.bias")),
+            mlp_w2_t=f32(lay("linear_2.weight").transpose(0, 2, 1)), mlp_b2=f32(lay("linear_2.bias")),
+            layer_scale=f32(lay("layer_scale")), wr_t=f32(wr.transpose(0, 2, 1)), br=f32(br),
+            fiber_kernel=torch.empty(L, NUM_ORI, NUM_ORI, HIDDEN, dtype=torch.float32, device=self.device))
+        # K3': input-independent fiber kernels, evaluated once on the device
+        fw1, fb1 = f32(sd["fiber_basis_fn.1.weight"]), f32(sd["fiber_basis_fn.1.bias"])
+        fw2, fb2 = f32(sd["fiber_basis_fn.3.weight"]), f32(sd["fiber_basis_fn.3.bias"])
+        fwf = f32(lay("conv.fiber_kernel.weight"))
+        if fw1.shape != (HIDDEN, 3):
+            raise ValueError("unsupported fiber basis input width")
+        stream = torch.cuda.current_stream(self.device).cuda_stream
+        _lib.call("arreau_fiber_kernel_precompute", self.t["ori"].data_ptr(), fw1.data_ptr(), fb1.data_ptr(),
+                  fw2.data_ptr(), fb2.data_ptr(), fwf.data_ptr(), self.t["fiber_kernel"].data_ptr(), stream)
+        torch.cuda.current_stream(self.device).synchronize()
+        if with_bf16:
+            bf = lambda a: torch.as_tensor(np.ascontiguousarray(a), dtype=torch.float32).to(self.device).to(torch.bfloat16)  # noqa: E731
+            self.t.update(w1m_bf16=bf(w1m_t.T), w2_bf16=bf(sd["basis_fn.3.weight"]),
+                          wk_bf16=bf(wk.reshape(L * HIDDEN, BASIS)), mlp_w1_bf16=bf(lay("linear_1.weight")),
+                          mlp_w2_bf16=bf(lay("linear_2.weight")))
+        self.c = _lib.Weights()
+        for name, _ in _lib.Weights._fields_:
+            if name in self.t:
+                setattr(self.c, name, self.t[name].data_ptr())
+        self.c.num_scalar, self.c.num_vec, self.c.num_states = self.num_scalar, self.num_vec, self.num_states
+
+    def ref(self):
+        return C.byref(self.c)

@@ -1,0 +1,317 @@
+/*
+ * arreau_b200 -- C ABI of the B200-native denoising step of the Arreau crystal diffusion model.
+ *
+ * The reference (curtischong/arreau) is pure Python/PyTorch and has no FFI layer: the drop-in
+ * boundary is its Python module API, mirrored by the Python package
+ * arreau_b200/.  Those Python mirrors reach the GPU ONLY through the entry points below
+ * (ctypes, see arreau_b200/_lib.py and INTEGRATION.md).  Each entry point cites the reference
+ * function it replaces (paths relative to the reference root).
+ *
+ * Conventions
+ *  - every pointer is a DEVICE pointer into caller-owned memory (torch tensors) unless it is one of
+ *    the two plain-C argument structs (host memory, read during the call only); nothing is allocated
+ *    or freed here; the caller sizes outputs and workspaces;
+ *  - asynchronous on `stream` (a cudaStream_t passed as void*), no host synchronisation inside;
+ *    the number of edges stays on the device (row_ptr[N]);
+ *  - return 0 on success, a negative ARREAU_ERR_* for bad arguments, or the positive
+ *    cudaError_t of a failed launch.  No exceptions, no aborts, no CPU fallback;
+ *  - fp64 for geometry and diffusion state (the reference runs fp64), fp32 for the network
+ *    (bf16 tensor-core operands with fp32 accumulation on the ARREAU_PRECISION_BF16 path);
+ *  - the network kernels are specialised at compile time on the reference's default sizes
+ *    (arreau_model_dims); any other size is ARREAU_ERR_UNSUPPORTED.
+ */
+#ifndef ARREAU_B200_H
+#define ARREAU_B200_H
+#include <stddef.h>
+#include <stdint.h>
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define ARREAU_OK 0
+#define ARREAU_ERR_BAD_SHAPE (-1)
+#define ARREAU_ERR_UNSUPPORTED (-2)
+#define ARREAU_ERR_WORKSPACE (-3)
+#define ARREAU_ERR_NULL (-4)
+
+#define ARREAU_PRECISION_FP32 0 /* FFMA2 SIMT GEMMs, parity <= 1e-4 of the fp64 reference          */
+#define ARREAU_PRECISION_BF16 1 /* tcgen05 bf16 operands, fp32 accumulate; tolerance stated in tests */
+
+/* Library/ABI version and the compile-time model dimensions (O=16, C=128, D=256, W=4, L=5). */
+int arreau_abi_version(void);
+int arreau_model_dims(int* num_ori, int* hidden, int* basis, int* widening, int* layers);
+/* Number of kernels this library has launched since load (bench.py's gpu_launches). */
+int64_t arreau_launch_count(void);
+
+/* ---------------------------------------------------------------------------------------------
+ * K1  periodic radius graph            replaces diffusion/diffusion_helpers.py:328-564
+ *     (radius_graph_pbc, with SUPERCELLS :10).  Three launches so the caller can size E:
+ *       count -> scan -> fill.   Edges come out receiver-major (i, then j, then cell 0..26),
+ *       i.e. already CSR-by-receiver with row_ptr.
+ * ------------------------------------------------------------------------------------------- */
+
+/* Pass 1.  pos[N,3] f64 cartesian, lattice[G,3,3] f64 rows a,b,c, atom_offset[G+1] i32 (prefix
+ * sum of num_atoms), crystal_of_atom[N] i32.  radius_sq = radius*radius evaluated by the caller
+ * in double (helpers:432).  cap = max_num_neighbors_threshold (<= 0 disables, helpers:469-472).
+ * Outputs: raw_count[N] i32 (candidates with 1e-4 < d2 <= r2), deg[N] i32 (= min(raw, cap) when
+ * cap > 0), num_neighbors_image[G] i64 (helpers:456-465, incl. its cap<=0 quirk). */
+int arreau_graph_count(const double* pos, const double* lattice, const int32_t* atom_offset,
+                       const int32_t* crystal_of_atom, int32_t num_atoms_total, int32_t num_crystals,
+                       double radius_sq, int32_t cap, int32_t remove_self_edges, int32_t* raw_count,
+                       int32_t* deg, int64_t* num_neighbors_image, void* stream);
+
+/* Exclusive scan deg[N] -> row_ptr[N+1] (row_ptr[N] = E stays on the device). */
+int arreau_graph_scan(const int32_t* deg, int32_t* row_ptr, int32_t n, void* stream);
+
+/* Pass 2.  Writes, for e in [row_ptr[i], row_ptr[i+1]): src[e] (sender j), dst[e] (= i),
+ * cell[e] (index 0..26 into product((-1,0,1),repeat=3)), dist[e] f64, dir[e,3] f64
+ * (= (pos_j + cell @ lattice) - pos_i, helpers:404-409,544).  Optional (may be NULL):
+ * edge_index_i64[2,edge_capacity] (row 0 sender, row 1 receiver, row stride = edge_capacity)
+ * and cell_offsets[E,3] f64 (= -cell, helpers:549).  Exact d2 ties under the cap are broken by
+ * ascending (j, cell) -- torch.sort(stable=True) order.  Rows beyond edge_capacity are not
+ * written and *overflow_flag (i32, may be NULL) is set to 1. */
+int arreau_graph_fill(const double* pos, const double* lattice, const int32_t* atom_offset,
+                      const int32_t* crystal_of_atom, int32_t num_atoms_total, int32_t num_crystals,
+                      double radius_sq, int32_t cap, int32_t remove_self_edges, const int32_t* raw_count,
+                      const int32_t* row_ptr, int64_t edge_capacity, int32_t* src, int32_t* dst,
+                      int8_t* cell, double* dist, double* dir, int64_t* edge_index_i64,
+                      double* cell_offsets, int32_t* overflow_flag, void* stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * K9  feature assembly                 replaces diffusion/diffusion_loss.py:124-158,
+ *     diffusion/lattice_helpers.py:55-105 (lattice_from_params),
+ *     diffusion/diffusion_helpers.py:23-25 (GaussianFourierProjection), :223-230 (frac_to_cart).
+ * ------------------------------------------------------------------------------------------- */
+
+/* lattice[G,3,3] f64 from lengths[G,3], angles[G,3] (radians as consumed by the reference). */
+int arreau_lattice_from_params(const double* lengths, const double* angles, int32_t num_crystals,
+                               double* lattice, void* stream);
+
+/* pos[N,3] = frac[N,3] @ lattice[crystal_of_atom] (f64). */
+int arreau_frac_to_cart(const double* frac, const double* lattice, const int32_t* crystal_of_atom,
+                        int32_t num_atoms_total, double* pos, void* stream);
+
+/* Assemble the network inputs of predict_scores: x[N,F] f32 with F = Z + 2*emb + 10 laid out as
+ * [onehot(types) | sin,cos(2 pi beta_t w) | n | lengths | angles | |lengths/n|] and
+ * vec[N,4,3] f32 = [frac ; lattice rows].  The timestep of atom b is t_of_atom[b] (i32, may be
+ * NULL -> every atom uses t); it indexes vp_betas[T+1] f64 (diffusion_loss.py:126).
+ * fourier_w[emb] f64. */
+int arreau_assemble_features(const double* frac, const int64_t* types, const double* lengths,
+                             const double* angles, const double* lattice, const int32_t* atom_offset,
+                             const int32_t* crystal_of_atom, const int32_t* t_of_atom, int32_t t,
+                             const double* vp_betas, const double* fourier_w, int32_t emb,
+                             int32_t num_atoms_total, int32_t num_crystals, int32_t num_states,
+                             float* x, float* vec, void* stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * K2-K7  Ponita fiber-bundle forward   replaces ponita/models/ponita.py:88-155 and what it calls
+ *     (ponita/nn/{conv,convnext,embedding}.py, ponita/transforms/*, ponita/geometry/invariants.py,
+ *      ponita/utils/{to_from_sphere,windowing}.py, PyG add-aggregation and global_add_pool).
+ *     Weight layouts are prepared by arreau_b200/weights.py.
+ * ------------------------------------------------------------------------------------------- */
+
+/* K3' (input independent): fiber_kernel[L,O,O,C] = fiber_kernel.weight_l @ fiber_basis_fn(ori.ori)
+ * (ponita.py:66,95; conv.py:113).  w1[C,3] b1[C] w2[D,C] b2[D] wf[L,C,D], ori[O,3]. */
+int arreau_fiber_kernel_precompute(const float* ori, const float* w1, const float* b1, const float* w2,
+                                   const float* b2, const float* wf, float* fiber_kernel, void* stream);
+
+/* K2: h0[N,O,C] = x_embedder([x | vec . ori_o]) (position_orientation_graph.py:84-86, ponita.py:98).
+ * x[N,F] f32, vec[N,V,3] f32, w_embed_t[(F+V),C] f32 (transposed weight), ori[O,3]. */
+int arreau_node_embed(const float* x, const float* vec, const float* w_embed_t, const float* ori,
+                      int32_t num_atoms_total, int32_t num_scalar, int32_t num_vec, float* h, void* stream);
+
+/* K3+K4a: per (edge, orientation) invariants -> 83 monomials -> Linear+GELU -> Linear+GELU -> *window
+ * -> all L per-layer spatial kernels  kernels[L, edge_capacity, O, C] (ponita/geometry/invariants.py:17-22,
+ * transforms/invariants.py:81-87, embedding.py:10-14, ponita.py:65,94, windowing.py:21-29,
+ * conv.py:110).  dir[E,3]/dist[E] f64 from the graph; lattice[G,3,3] f64; crystal_of_atom[N];
+ * src[E]; num_edges_ptr = &row_ptr[N] (device).  w1m_t[96,C]: rows 0..82 the monomial-folded first
+ * layer, row 83 its bias, rows 84..95 zero; w2_t[C,D]; b2[D]; wk_t[D,L*C].
+ * _f32: FFMA2 SIMT, fp32 kernels out.  _bf16: tcgen05, bf16 operands (weights *_bf16 as documented
+ * in arreau_b200/weights.py), fp32 accumulation, bf16 kernels out. */
+int arreau_edge_kernels_f32(const double* dir, const double* dist, const double* lattice,
+                            const int32_t* crystal_of_atom, const int32_t* src, const int32_t* num_edges_ptr,
+                            int64_t edge_capacity, const float* ori, const float* w1m_t, const float* w2_t,
+                            const float* b2, const float* wk_t, double radius, float* kernels, void* stream);
+int arreau_edge_kernels_bf16(const double* dir, const double* dist, const double* lattice,
+                             const int32_t* crystal_of_atom, const int32_t* src, const int32_t* num_edges_ptr,
+                             int64_t edge_capacity, const float* ori, const void* w1m_bf16, const void* w2_bf16,
+                             const float* b2, const void* wk_bf16, double radius, void* kernels_bf16,
+                             void* stream);
+
+/* K4b+K5: x1[i,o,c] = sum_{e in row i} kernels[e,o,c] * h[src_e,o,c]   (conv.py:131-133 + PyG add)
+ *         x2[i,p,c] = (1/O) sum_o x1[i,o,c] fiber_kernel[o,p,c] + bias[c]  (conv.py:115,126)
+ *         y = LayerNorm_C(x2) * ln_w + ln_b                              (convnext.py:25)
+ * `kernels` is ONE layer's [edge_capacity,O,C] slab (f32, or bf16 when kernels_bf16 != 0);
+ * fiber_kernel is that layer's [O,O,C].  y[N,O,C] is f32 or bf16 (y_bf16).  x1_debug/x2_debug
+ * (f32 [N,O,C], may be NULL) receive the intermediates for the parity tests.
+ * Deterministic receiver-sorted CSR reduction (fixed order, no atomics). */
+int arreau_message_fiber_norm(const void* kernels, int32_t kernels_bf16, const float* h, const int32_t* row_ptr,
+                              const int32_t* src, const float* fiber_kernel, const float* conv_bias,
+                              const float* ln_w, const float* ln_b, int32_t num_atoms_total, void* y,
+                              int32_t y_bf16, float* x1_debug, float* x2_debug, void* stream);
+
+/* K6: h <- h + layer_scale * (W2 gelu(W1 y + b1) + b2)   (convnext.py:26-32); rows = N*O.
+ * _f32: w1_t[C,4C], w2_t[4C,C] f32.  _bf16: y bf16, w1/w2 bf16 in the reference's [out,in] layout. */
+int arreau_convnext_mlp_f32(const float* y, const float* w1_t, const float* b1, const float* w2_t,
+                            const float* b2, const float* layer_scale, int64_t num_rows, float* h, void* stream);
+int arreau_convnext_mlp_bf16(const void* y_bf16, const void* w1_bf16, const float* b1, const void* w2_bf16,
+                             const float* b2, const float* layer_scale, int64_t num_rows, float* h, void* stream);
+
+/* K7a: acc[N,Z+6] (+)= read-out of one layer pooled over orientations (ponita.py:105):
+ *   acc[b, 0:Z]      mean_o (Wr h[b,o] + br)[0:Z]                (to_from_sphere.py:13-14)
+ *   acc[b, Z:Z+3]    (1/O) sum_o (Wr h[b,o] + br)[Z] * ori_o      (to_from_sphere.py:10-11)
+ *   acc[b, Z+3:Z+6]  mean_o (Wr h[b,o] + br)[Z+1:Z+4]
+ * wr_t[C, Z+4] (transposed read-out weight), br[Z+4].  first_layer != 0 overwrites acc. */
+int arreau_readout_accumulate(const float* h, const float* wr_t, const float* br, const float* ori,
+                              int32_t num_atoms_total, int32_t num_states, int32_t first_layer, float* acc,
+                              void* stream);
+
+/* K7b: logits[N,Z], score[N,3] = acc / L; len0[G,3] = sum over atoms of crystal g of acc[.., Z+3:Z+6] / L
+ * (ponita.py:108-117,152).  Fixed-order segment sum per crystal (deterministic). */
+int arreau_readout_finalize(const float* acc, const int32_t* atom_offset, int32_t num_atoms_total,
+                            int32_t num_crystals, int32_t num_states, int32_t num_layers, float* logits,
+                            float* score, float* len0, void* stream);
+
+/* All device weight pointers of one model (filled by arreau_b200/weights.py). */
+typedef struct arreau_weights {
+  const float* ori;          /* [O,3]                                                       */
+  const float* w_embed_t;    /* [F+V, C]                                                    */
+  const float* w1m_t;        /* [96, C]                                                     */
+  const float* w2_t;         /* [C, D]                                                      */
+  const float* b2;           /* [D]                                                         */
+  const float* wk_t;         /* [D, L*C]                                                    */
+  const float* fiber_kernel; /* [L,O,O,C]                                                   */
+  const float* conv_bias;    /* [L,C]                                                       */
+  const float* ln_w;         /* [L,C]                                                       */
+  const float* ln_b;         /* [L,C]                                                       */
+  const float* mlp_w1_t;     /* [L,C,4C]                                                    */
+  const float* mlp_b1;       /* [L,4C]                                                      */
+  const float* mlp_w2_t;     /* [L,4C,C]                                                    */
+  const float* mlp_b2;       /* [L,C]                                                       */
+  const float* layer_scale;  /* [L,C]                                                       */
+  const float* wr_t;         /* [L,C,Z+4]                                                   */
+  const float* br;           /* [L,Z+4]                                                     */
+  /* bf16 operands of the tcgen05 path (NULL when only the fp32 path is used) */
+  const void* w1m_bf16;      /* [C, 96]      (out, in)                                      */
+  const void* w2_bf16;       /* [D, C]                                                      */
+  const void* wk_bf16;       /* [L*C, D]                                                    */
+  const void* mlp_w1_bf16;   /* [L,4C,C]                                                    */
+  const void* mlp_w2_bf16;   /* [L,C,4C]                                                    */
+  int32_t num_scalar;        /* F                                                           */
+  int32_t num_vec;           /* V                                                           */
+  int32_t num_states;        /* Z                                                           */
+  int32_t reserved;
+} arreau_weights;
+
+/* Scratch of one forward pass, sized for num_atoms_total N and edge_capacity. */
+typedef struct arreau_workspace {
+  float* h;         /* [N,O,C] f32                                                           */
+  void* y;          /* [N,O,C] f32 (fp32 path) or bf16 (bf16 path)                           */
+  void* kernels;    /* [L,edge_capacity,O,C] f32 or bf16                                     */
+  float* acc;       /* [N,Z+6] f32                                                           */
+  float* x1_debug;  /* NULL, or [L,N,O,C] f32                                                */
+  float* x2_debug;  /* NULL, or [L,N,O,C] f32                                                */
+  float* h_debug;   /* NULL, or [L+1,N,O,C] f32 (h after the embedding and after each layer) */
+  int64_t edge_capacity;
+} arreau_workspace;
+
+/* PonitaFiberBundle.forward (ponita/models/ponita.py:88-123) on a prebuilt graph: x[N,F], vec[N,V,3] f32;
+ * row_ptr[N+1], src[E] (receiver-sorted CSR), dist[E], dir[E,3] f64, lattice[G,3,3] f64.
+ * Outputs logits[N,Z], score[N,3], len0[G,3] f32. */
+int arreau_ponita_forward(const arreau_weights* w, const arreau_workspace* ws, int32_t precision, const float* x,
+                          const float* vec, const int32_t* row_ptr, const int32_t* src, const double* dist,
+                          const double* dir, const double* lattice, const int32_t* atom_offset,
+                          const int32_t* crystal_of_atom, int32_t num_atoms_total, int32_t num_crystals,
+                          double radius, float* logits, float* score, float* len0, void* stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * K8  per-step update                  replaces diffusion/diffusion_loss.py:338-349 with
+ *     diffusion/diffusion_helpers.py:185-199 (VP_lattice.reverse_given_x0), :65-81 (VE_pbc.reverse),
+ *     diffusion/d3pm.py:74-110,198-215 (D3PM.q_posterior_logits / reverse, mask chain).
+ * ------------------------------------------------------------------------------------------- */
+
+/* lengths'[G,3] = (cx0 * pred + cxt * lengths) / denom + var * z * [t>1]; the four coefficients are
+ * evaluated by the caller with the reference's mixed fp32/fp64 arithmetic (quirk B1).
+ * pred = len0[G,3] f32 * num_atoms (diffusion_loss.py:338). */
+int arreau_vp_lattice_reverse(const double* lengths, const float* len0, const int32_t* atom_offset,
+                              const double* z, int32_t t, double cx0, double cxt, double denom, double var,
+                              int32_t num_crystals, double* lengths_out, void* stream);
+
+/* frac'[N,3] = (frac - score*(s_t^2 - s_{t-1}^2) + sqrt(s_{t-1}^2 (s_t^2 - s_{t-1}^2)/s_t^2) z) mod 1
+ * with torch.remainder semantics; t_of_atom may be NULL (then every atom uses t). */
+int arreau_ve_pbc_reverse(const double* frac, const float* score, const double* z, const int32_t* t_of_atom,
+                          int32_t t, const double* ve_sigmas, int32_t num_atoms_total, double* frac_out,
+                          void* stream);
+
+/* types'[N] = argmax(log(f1+eps) + log(f2+eps) + gumbel(u) * (0.2 + 0.8 [t != 1])), or logits if t == 1.
+ * Mask-absorbing chain only (forward_type="mask", diffusion_loss.py:81): onestep_keep = 0.98,
+ * onestep_to_mask = 0.02, q_keep[T], q_to_mask[T] = Qbar_t[0,0], Qbar_t[0,Z-1] (index t-1).
+ * u[N,Z] f64 uniform noise. */
+int arreau_d3pm_reverse(const int64_t* types, const float* logits, const double* u, const int32_t* t_of_atom,
+                        int32_t t, const double* q_keep, const double* q_to_mask, double onestep_keep,
+                        double onestep_to_mask, int32_t num_steps, int32_t num_atoms_total, int32_t num_states,
+                        int64_t* types_out, void* stream);
+
+/* Counter-based noise for throughput runs (the reference draws torch CPU noise): fills
+ * z_len[G,3], z_frac[N,3] with N(0,1) and u[N,Z] with U[0,1) from Philox4x32-10 keyed by (seed, step). */
+int arreau_step_noise(uint64_t seed, int32_t step, int32_t num_crystals, int32_t num_atoms_total,
+                      int32_t num_states, double* z_len, double* z_frac, double* u, void* stream);
+
+/* One whole denoise step (the body of the sampler loop, diffusion_loss.py:319-349), every kernel
+ * above on one stream with no host synchronisation.  State is updated in place. */
+typedef struct arreau_step_args {
+  /* state, fp64 / i64, updated in place */
+  double* frac;            /* [N,3]   */
+  int64_t* types;          /* [N]     */
+  double* lengths;         /* [G,3]   */
+  const double* angles;    /* [G,3]   */
+  double* lattice;         /* [G,3,3] out: lattice_from_params(lengths', angles) */
+  /* topology */
+  const int32_t* atom_offset;      /* [G+1] */
+  const int32_t* crystal_of_atom;  /* [N]   */
+  int32_t num_atoms_total, num_crystals;
+  /* graph scratch */
+  double* pos;             /* [N,3]   */
+  int32_t* raw_count;      /* [N]     */
+  int32_t* deg;            /* [N]     */
+  int32_t* row_ptr;        /* [N+1]   */
+  int64_t* num_neighbors_image; /* [G] */
+  int32_t* src;            /* [edge_capacity] */
+  int32_t* dst;
+  int8_t* cell;
+  double* dist;
+  double* dir;             /* [edge_capacity,3] */
+  int32_t* overflow_flag;  /* [1] */
+  /* network io */
+  float* x;                /* [N,F]   */
+  float* vec;              /* [N,4,3] */
+  float* logits;           /* [N,Z]   */
+  float* score;            /* [N,3]   */
+  float* len0;             /* [G,3]   */
+  /* noise (injected for parity runs, or filled by arreau_step_noise) */
+  const double* z_len;     /* [G,3]   */
+  const double* z_frac;    /* [N,3]   */
+  const double* u_type;    /* [N,Z]   */
+  /* tables */
+  const double* vp_betas;  /* [T+1]   */
+  const double* fourier_w; /* [emb]   */
+  const double* ve_sigmas; /* [T+1]   */
+  const double* q_keep;    /* [T]     */
+  const double* q_to_mask; /* [T]     */
+  double onestep_keep, onestep_to_mask;
+  double vp_cx0, vp_cxt, vp_denom, vp_var;   /* coefficients of THIS timestep */
+  int32_t emb, num_steps;  /* time-embedding half width (32), T */
+  int32_t t;               /* timestep of this step (1..T-1) */
+  int32_t cap;             /* max_neighbors */
+  double radius;
+  int32_t precision;
+  int32_t update_types;    /* 0: keep types (constant_atoms mode, diffusion_loss.py:348-349) */
+} arreau_step_args;
+
+int arreau_denoise_step(const arreau_weights* w, const arreau_workspace* ws, const arreau_step_args* a,
+                        void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* ARREAU_B200_H */

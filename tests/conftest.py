@@ -1,0 +1,59 @@
+import os
+import sys
+
+import numpy as np
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+GOLD = os.path.join(ROOT, "tests", "golden")
+
+
+def pytest_configure(config):
+    config.addinivalue_line("markers", "gpu: needs a CUDA device (run on the B200 box)")
+
+
+@pytest.fixture(scope="session")
+def gold():
+    def load(name):
+        return np.load(os.path.join(GOLD, name), allow_pickle=False)
+    return load
+
+
+@pytest.fixture(scope="session")
+def graph_cases(gold):
+    z = gold("graph_cases.npz")
+    cases = {}
+    for k in z.files:
+        idx, name = k.split("/", 1)
+        cases.setdefault(idx, {})[name] = z[k]
+    return [cases[i] for i in sorted(cases)]
+
+
+def rel_err(a, b):
+    """max |a-b| / max |b| -- the tolerance north_star states is measured like this."""
+    a, b = np.asarray(a, dtype=np.float64), np.asarray(b, dtype=np.float64)
+    return float(np.abs(a - b).max() / max(np.abs(b).max(), 1e-30)) if a.size else 0.0
+
+
+@pytest.fixture(scope="session")
+def device():
+    import torch
+    if not torch.cuda.is_available():
+        pytest.skip("no CUDA device")
+    from arreau_b200 import _lib
+    _lib.load()   # fail loudly if the extension is missing on a GPU box
+    return torch.device("cuda:0")
+
+
+@pytest.fixture(scope="session")
+def weights_npz(gold):
+    return gold("weights_seed0.npz")
+
+
+@pytest.fixture(scope="session")
+def packed_weights(device, weights_npz):
+    from arreau_b200.weights import PonitaWeights
+    sd = {k: weights_npz[k] for k in weights_npz.files if k not in ("ori_grid", "fourier_w")}
+    return PonitaWeights(sd, weights_npz["ori_grid"], device=device)

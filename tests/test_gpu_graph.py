@@ -1,0 +1,84 @@
+"""K1 parity: the CUDA radius graph against the reference's golden edge lists (bit exact) and against the
+oracle on seeded inputs up to the C2/C3 shapes (size-independent properties at full size)."""
+import numpy as np
+import pytest
+import torch
+
+from arreau_b200.synthetic import make_crystals
+
+pytestmark = pytest.mark.gpu
+
+
+def _run(device, cart, lattice, num_atoms, radius, cap):
+    from arreau_b200.diffusion.diffusion_helpers import radius_graph_pbc
+    out = radius_graph_pbc(torch.as_tensor(cart, dtype=torch.float64, device=device),
+                           torch.as_tensor(lattice, dtype=torch.float64, device=device),
+                           torch.as_tensor(num_atoms, device=device), radius, cap, device=device)
+    torch.cuda.synchronize()
+    return [o.cpu().numpy() for o in out]
+
+
+def test_golden_graph_cases_bit_exact(device, graph_cases):
+    assert len(graph_cases) >= 15
+    for c in graph_cases:
+        ei, off, nimg, dist, direction = _run(device, c["cart"], c["lattice"], c["num_atoms"], float(c["radius"]), int(c["cap"]))
+        name = str(c["name"])
+        assert ei.shape == c["edge_index"].shape, name
+        assert np.array_equal(ei, c["edge_index"]), name
+        assert np.array_equal(off, c["cell_offsets"]), name
+        assert np.array_equal(nimg, c["num_neighbors_image"]), name
+        assert np.array_equal(dist, c["dist"]), name            # fp64, same operation order: bit exact
+        assert np.array_equal(direction, c["direction"]), name
+
+
+def test_empty_and_single_atom(device):
+    ei, off, nimg, dist, direction = _run(device, np.zeros((1, 3)), 30.0 * np.eye(3)[None], [1], 5.0, 8)
+    assert ei.shape == (2, 0) and dist.shape == (0,) and nimg.tolist() == [0]
+
+
+@pytest.mark.parametrize("G,n,radius,cap,seed", [(64, 40, 5.0, 8, 11), (8, 200, 7.0, 0, 12), (32, 40, 5.0, 0, 13),
+                                                  (4, 236, 7.0, 12, 14)])
+def test_against_oracle_seeded(device, G, n, radius, cap, seed):
+    from oracle import restatement as R
+    cr = make_crystals(G, n, None, seed=seed)
+    T64 = lambda a: torch.as_tensor(a, dtype=torch.float64)  # noqa: E731
+    lat = R.lattice_from_params(T64(cr.lengths), T64(cr.angles))
+    cart = R.frac_to_cart_coords(T64(cr.frac), lat, torch.as_tensor(cr.num_atoms))
+    ref = R.radius_graph_pbc(cart, lat, torch.as_tensor(cr.num_atoms), radius, cap)
+    got = _run(device, cart.numpy(), lat.numpy(), cr.num_atoms, radius, cap)
+    assert np.array_equal(got[0], ref[0].numpy())
+    assert np.array_equal(got[1], ref[1].numpy())
+    assert np.array_equal(got[2], ref[2].numpy())
+    assert np.array_equal(got[3], ref[3].numpy())
+    assert np.array_equal(got[4], ref[4].numpy())
+
+
+def test_full_size_properties_c2(device):
+    """C2 shape (1024 x 40, 5 A, cap 8): sortedness, cap, symmetric uncapped graph, determinism."""
+    cr = make_crystals(1024, 40, None, seed=0)
+    from arreau_b200.diffusion.diffusion_helpers import frac_to_cart_coords
+    from arreau_b200.diffusion.lattice_helpers import lattice_from_params
+    lat = lattice_from_params(torch.as_tensor(cr.lengths, device=device), torch.as_tensor(cr.angles, device=device))
+    na = torch.as_tensor(cr.num_atoms, device=device)
+    cart = frac_to_cart_coords(torch.as_tensor(cr.frac, device=device), lat, na)
+    a = _run(device, cart, lat, na, 5.0, 8)
+    b = _run(device, cart, lat, na, 5.0, 8)
+    for x, y in zip(a, b):
+        assert np.array_equal(x, y)                       # deterministic
+    ei, off, nimg, dist, direction = a
+    N = cr.total_atoms
+    deg = np.bincount(ei[1], minlength=N)
+    assert deg.max() <= 8 and ei.shape[1] == deg.sum()
+    assert np.all(np.diff(ei[1]) >= 0)                    # receiver-major
+    assert np.all(dist <= 5.0) and np.all(dist * dist > 1e-4 * (1 - 1e-12))
+    assert np.allclose(np.linalg.norm(direction, axis=1), dist, rtol=1e-14, atol=0)
+    assert np.all(ei[0] // 40 == ei[1] // 40)             # edges never cross crystals
+    assert nimg.sum() == ei.shape[1]
+    # uncapped graph is symmetric: (j -> i, cell c) has the partner (i -> j, -c)
+    ei_u, off_u, _, dist_u, _ = _run(device, cart, lat, na, 5.0, 0)
+    key = lambda s, d, o: set(zip(s.tolist(), d.tolist(), map(tuple, o.astype(int).tolist())))  # noqa: E731
+    sel = ei_u[1] < 400
+    fwd = key(ei_u[0][sel], ei_u[1][sel], off_u[sel])
+    sel2 = ei_u[0] < 400
+    bwd = key(ei_u[1][sel2], ei_u[0][sel2], -off_u[sel2])
+    assert fwd == bwd
