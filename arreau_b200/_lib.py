@@ -38,7 +38,7 @@ class Workspace(C.Structure):
 
 class StepArgs(C.Structure):
     _fields_ = [
-        ("frac", vp), ("types", vp), ("lengths", vp), ("angles", vp), ("lattice", vp),
+        ("frac", vp), ("types", vp), ("lengths", vp), ("angles", vp), ("angle_trig", vp), ("lattice", vp),
         ("atom_offset", vp), ("crystal_of_atom", vp), ("num_atoms_total", i32), ("num_crystals", i32),
         ("pos", vp), ("raw_count", vp), ("deg", vp), ("row_ptr", vp), ("num_neighbors_image", vp),
         ("src", vp), ("dst", vp), ("cell", vp), ("dist", vp), ("dir", vp), ("overflow_flag", vp),
@@ -60,6 +60,7 @@ SIGNATURES = {
     "arreau_graph_scan": [vp, vp, i32, vp],
     "arreau_graph_fill": [vp, vp, vp, vp, i32, i32, f64, i32, i32, vp, vp, i64, vp, vp, vp, vp, vp, vp, vp, vp, vp],
     "arreau_lattice_from_params": [vp, vp, i32, vp, vp],
+    "arreau_lattice_from_trig": [vp, vp, i32, vp, vp],
     "arreau_frac_to_cart": [vp, vp, vp, i32, vp, vp],
     "arreau_assemble_features": [vp, vp, vp, vp, vp, vp, vp, vp, i32, vp, vp, i32, i32, i32, i32, vp, vp, vp],
     "arreau_fiber_kernel_precompute": [vp] * 8,

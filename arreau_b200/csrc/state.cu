@@ -34,6 +34,25 @@ __global__ void lattice_from_params_kernel(const double* __restrict__ lengths, c
   L[8] = c;
 }
 
+// lattice_helpers.py:85-96 with the angle factors [sin b, cos b, sin a, cos g*, sin g*, cos a] given
+__global__ void lattice_from_trig_kernel(const double* __restrict__ lengths, const double* __restrict__ trig, int G,
+                                         double* __restrict__ lattice) {
+  const int g = blockIdx.x * blockDim.x + threadIdx.x;
+  if (g >= G) return;
+  const double a = lengths[3 * g], b = lengths[3 * g + 1], c = lengths[3 * g + 2];
+  const double* f = trig + 6 * (size_t)g;
+  double* L = lattice + 9 * (size_t)g;
+  L[0] = __dmul_rn(a, f[0]);
+  L[1] = 0.0;
+  L[2] = __dmul_rn(a, f[1]);
+  L[3] = __dmul_rn(__dmul_rn(-b, f[2]), f[3]);
+  L[4] = __dmul_rn(__dmul_rn(b, f[2]), f[4]);
+  L[5] = __dmul_rn(b, f[5]);
+  L[6] = 0.0;
+  L[7] = 0.0;
+  L[8] = c;
+}
+
 // diffusion/diffusion_helpers.py:223-230: pos_j = sum_i frac_i * L[i][j]  (einsum "bi,bij->bj")
 __global__ void frac_to_cart_kernel(const double* __restrict__ frac, const double* __restrict__ lattice,
                                     const int32_t* __restrict__ crystal_of_atom, int N, double* __restrict__ pos) {
@@ -225,6 +244,16 @@ extern "C" int arreau_lattice_from_params(const double* lengths, const double* a
   if (!lengths || !angles || !lattice) return ARREAU_ERR_NULL;
   if (G < 0) return ARREAU_ERR_BAD_SHAPE;
   lattice_from_params_kernel<<<(G + 127) / 128, 128, 0, (cudaStream_t)stream>>>(lengths, angles, G, lattice);
+  CUDA_LAUNCH_CHECK();
+  return ARREAU_OK;
+}
+
+extern "C" int arreau_lattice_from_trig(const double* lengths, const double* trig, int32_t G, double* lattice,
+                                        void* stream) {
+  if (G == 0) return ARREAU_OK;
+  if (!lengths || !trig || !lattice) return ARREAU_ERR_NULL;
+  if (G < 0) return ARREAU_ERR_BAD_SHAPE;
+  lattice_from_trig_kernel<<<(G + 127) / 128, 128, 0, (cudaStream_t)stream>>>(lengths, trig, G, lattice);
   CUDA_LAUNCH_CHECK();
   return ARREAU_OK;
 }

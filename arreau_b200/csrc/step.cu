@@ -156,7 +156,10 @@ extern "C" int arreau_denoise_step(const arreau_weights* w, const arreau_workspa
   if (N == 0 || G == 0) return ARREAU_OK;
   if (w->num_scalar != Z + 2 * a->emb + 10 || w->num_vec != 4) return ARREAU_ERR_BAD_SHAPE;
   // predict_scores: lattice, features, cartesian positions, graph, network   (diffusion_loss.py:112-197)
-  ARREAU_TRY(arreau_lattice_from_params(a->lengths, a->angles, G, a->lattice, stream));
+  if (a->angle_trig)
+    ARREAU_TRY(arreau_lattice_from_trig(a->lengths, a->angle_trig, G, a->lattice, stream));
+  else
+    ARREAU_TRY(arreau_lattice_from_params(a->lengths, a->angles, G, a->lattice, stream));
   ARREAU_TRY(arreau_assemble_features(a->frac, a->types, a->lengths, a->angles, a->lattice, a->atom_offset,
                                       a->crystal_of_atom, nullptr, a->t, a->vp_betas, a->fourier_w, a->emb, N, G, Z,
                                       a->x, a->vec, stream));
@@ -174,7 +177,10 @@ extern "C" int arreau_denoise_step(const arreau_weights* w, const arreau_workspa
   // update: lengths, lattice, fractional coordinates, atom types   (diffusion_loss.py:338-349)
   ARREAU_TRY(arreau_vp_lattice_reverse(a->lengths, a->len0, a->atom_offset, a->z_len, a->t, a->vp_cx0, a->vp_cxt,
                                        a->vp_denom, a->vp_var, G, a->lengths, stream));
-  ARREAU_TRY(arreau_lattice_from_params(a->lengths, a->angles, G, a->lattice, stream));
+  if (a->angle_trig)
+    ARREAU_TRY(arreau_lattice_from_trig(a->lengths, a->angle_trig, G, a->lattice, stream));
+  else
+    ARREAU_TRY(arreau_lattice_from_params(a->lengths, a->angles, G, a->lattice, stream));
   ARREAU_TRY(arreau_ve_pbc_reverse(a->frac, a->score, a->z_frac, nullptr, a->t, a->ve_sigmas, N, a->frac, stream));
   if (a->update_types)
     ARREAU_TRY(arreau_d3pm_reverse(a->types, a->logits, a->u_type, nullptr, a->t, a->q_keep, a->q_to_mask,

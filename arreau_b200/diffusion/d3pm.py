@@ -34,7 +34,8 @@ class D3PM(nn.Module):
         tt = t.reshape(-1).to(dev, torch.int32).contiguous()
         out = torch.empty_like(types)
         tb = self.tables
+        q_keep, q_to_mask = self.q_keep.to(dev), self.q_to_mask.to(dev)   # keep the device copies alive over the call
         _lib.call("arreau_d3pm_reverse", types.data_ptr(), logits.data_ptr(), u.data_ptr(), tt.data_ptr(), 0,
-                  self.q_keep.to(dev).data_ptr(), self.q_to_mask.to(dev).data_ptr(), tb.onestep_keep,
+                  q_keep.data_ptr(), q_to_mask.data_ptr(), tb.onestep_keep,
                   tb.onestep_to_mask, self.n_T, N, Z, out.data_ptr(), torch.cuda.current_stream(dev).cuda_stream)
         return out

@@ -109,8 +109,9 @@ class VE_pbc(nn.Module):
         score = _cuda(epx_x, torch.float32)
         tt = _cuda(t.reshape(-1), torch.int32)
         out = torch.empty_like(frac)
+        sigmas = self.sigmas.to(dev)                  # keep the device copy alive over the call
         _lib.call("arreau_ve_pbc_reverse", frac.data_ptr(), score.data_ptr(), z.data_ptr(), tt.data_ptr(), 0,
-                  self.sigmas.to(dev).data_ptr(), frac.shape[0], out.data_ptr(), _stream(dev))
+                  sigmas.data_ptr(), frac.shape[0], out.data_ptr(), _stream(dev))
         return out
 
 

@@ -19,6 +19,20 @@ from .weights import HIDDEN, LAYERS, NUM_ORI, PonitaWeights
 PRECISIONS = {"fp32": _lib.PRECISION_FP32, "bf16": _lib.PRECISION_BF16}
 
 
+def angle_factors(angles: torch.Tensor) -> torch.Tensor:
+    """[sin b, cos b, sin a, cos g*, sin g*, cos a] per crystal with the reference's own torch expressions
+    (diffusion/lattice_helpers.py:76-82).  The angles are constants of a sampling trajectory
+    (diffusion_loss.py:294-296), so this runs once per set_state on the host like the schedule tables; the
+    per-step lattice is then pure fp64 products on the device (arreau_lattice_from_trig) and bit-identical to
+    the reference's, which keeps exact-tie neighbour selection in degenerate cells identical too."""
+    alpha, beta, gamma = angles.unbind(-1)
+    cos_a, cos_b, cos_g = torch.cos(alpha), torch.cos(beta), torch.cos(gamma)
+    sin_a, sin_b = torch.sin(alpha), torch.sin(beta)
+    val = torch.clamp((cos_a * cos_b - cos_g) / (sin_a * sin_b), -1.0, 1.0)
+    gs = torch.arccos(val)
+    return torch.stack([sin_b, cos_b, sin_a, torch.cos(gs), torch.sin(gs), cos_a], dim=1)
+
+
 def _i32(a, device):
     return torch.as_tensor(np.asarray(a), dtype=torch.int32).to(device)
 
@@ -52,6 +66,7 @@ class DenoiseEngine:
         # diffusion state (fp64 / i64, like the reference)
         self.frac, self.types = f64(N, 3), torch.zeros(N, dtype=torch.int64, device=dev)
         self.lengths, self.angles, self.lattice = f64(G, 3), f64(G, 3), f64(G, 3, 3)
+        self.angle_trig = f64(G, 6)
         # graph scratch
         self.pos, self.raw_count, self.deg, self.row_ptr = f64(N, 3), i32(N), i32(N), i32(N + 1)
         self.num_neighbors_image = torch.zeros(G, dtype=torch.int64, device=dev)
@@ -106,6 +121,7 @@ class DenoiseEngine:
         a = _lib.StepArgs()
         p = _lib.ptr
         a.frac, a.types, a.lengths, a.angles, a.lattice = p(self.frac), p(self.types), p(self.lengths), p(self.angles), p(self.lattice)
+        a.angle_trig = p(self.angle_trig)
         a.atom_offset, a.crystal_of_atom = p(self.atom_offset), p(self.crystal_of_atom)
         a.num_atoms_total, a.num_crystals = self.N, self.G
         a.pos, a.raw_count, a.deg, a.row_ptr = p(self.pos), p(self.raw_count), p(self.deg), p(self.row_ptr)
@@ -131,7 +147,9 @@ class DenoiseEngine:
         self.frac.copy_(torch.as_tensor(frac).reshape(self.N, 3), non_blocking=True)
         self.types.copy_(torch.as_tensor(types).reshape(self.N), non_blocking=True)
         self.lengths.copy_(torch.as_tensor(lengths).reshape(self.G, 3), non_blocking=True)
-        self.angles.copy_(torch.as_tensor(angles).reshape(self.G, 3), non_blocking=True)
+        ang = torch.as_tensor(angles).reshape(self.G, 3)
+        self.angles.copy_(ang, non_blocking=True)
+        self.angle_trig.copy_(angle_factors(ang.detach().to("cpu", torch.float64)), non_blocking=True)
 
     def set_noise(self, z_len, z_frac, u_type) -> None:
         self.z_len.copy_(torch.as_tensor(z_len).reshape(self.G, 3), non_blocking=True)
@@ -184,7 +202,7 @@ class DenoiseEngine:
         else:
             self.t_of_atom.copy_(torch.as_tensor(t).reshape(self.N).to(torch.int32), non_blocking=True)
             t_ptr, t_scalar = self.t_of_atom.data_ptr(), 0
-        _lib.call("arreau_lattice_from_params", self.lengths.data_ptr(), self.angles.data_ptr(), self.G,
+        _lib.call("arreau_lattice_from_trig", self.lengths.data_ptr(), self.angle_trig.data_ptr(), self.G,
                   self.lattice.data_ptr(), s)
         _lib.call("arreau_assemble_features", self.frac.data_ptr(), self.types.data_ptr(), self.lengths.data_ptr(),
                   self.angles.data_ptr(), self.lattice.data_ptr(), self.atom_offset.data_ptr(),
@@ -237,3 +255,88 @@ class DenoiseEngine:
         if int(self.overflow_flag.item()):
             raise RuntimeError("edge capacity overflow")
         return self.src[:E], self.dst[:E], self.cell[:E], self.dist[:E], self.dir[:E]
+
+    # ------------------------------------------------------------------ measurement
+    def timed_breakdown(self, t: int, iters: int = 3):
+        """Per-kernel device times (ms, averaged over `iters`) of one predict_scores + update, launched one
+        entry point at a time with CUDA events on the current stream.  Leaves the state untouched (the update
+        kernels write to scratch).  Used by bench.py for the roofline of the dominant kernel."""
+        w, s, Z = self.w.t, None, self.Z
+        bf16 = self.precision == "bf16"
+        names, fns = [], []
+
+        def add(name, fn):
+            names.append(name)
+            fns.append(fn)
+
+        add("features", lambda: self.prepare_inputs(t))
+        add("graph", lambda: self.build_graph())
+        add("node_embed", lambda: _lib.call("arreau_node_embed", self.x.data_ptr(), self.vec.data_ptr(),
+                                            w["w_embed_t"].data_ptr(), w["ori"].data_ptr(), self.N, self.F, 4,
+                                            self.h.data_ptr(), self.stream))
+        nep = self.row_ptr.data_ptr() + 4 * self.N
+        if bf16:
+            add("edge_kernels", lambda: _lib.call(
+                "arreau_edge_kernels_bf16", self.dir.data_ptr(), self.dist.data_ptr(), self.lattice.data_ptr(),
+                self.crystal_of_atom.data_ptr(), self.src.data_ptr(), nep, self.edge_capacity, w["ori"].data_ptr(),
+                w["w1m_bf16"].data_ptr(), w["w2_bf16"].data_ptr(), w["b2"].data_ptr(), w["wk_bf16"].data_ptr(),
+                self.radius, self.kernels.data_ptr(), self.stream))
+        else:
+            add("edge_kernels", lambda: _lib.call(
+                "arreau_edge_kernels_f32", self.dir.data_ptr(), self.dist.data_ptr(), self.lattice.data_ptr(),
+                self.crystal_of_atom.data_ptr(), self.src.data_ptr(), nep, self.edge_capacity, w["ori"].data_ptr(),
+                w["w1m_t"].data_ptr(), w["w2_t"].data_ptr(), w["b2"].data_ptr(), w["wk_t"].data_ptr(),
+                self.radius, self.kernels.data_ptr(), self.stream))
+        for l in range(LAYERS):
+            add("message_fiber_norm", lambda l=l: _lib.call(
+                "arreau_message_fiber_norm", self.kernels[l].data_ptr(), int(bf16), self.h.data_ptr(),
+                self.row_ptr.data_ptr(), self.src.data_ptr(), w["fiber_kernel"][l].data_ptr(),
+                w["conv_bias"][l].data_ptr(), w["ln_w"][l].data_ptr(), w["ln_b"][l].data_ptr(), self.N,
+                self.y.data_ptr(), int(bf16), None, None, self.stream))
+            if bf16:
+                add("convnext_mlp", lambda l=l: _lib.call(
+                    "arreau_convnext_mlp_bf16", self.y.data_ptr(), w["mlp_w1_bf16"][l].data_ptr(),
+                    w["mlp_b1"][l].data_ptr(), w["mlp_w2_bf16"][l].data_ptr(), w["mlp_b2"][l].data_ptr(),
+                    w["layer_scale"][l].data_ptr(), self.N * NUM_ORI, self.h.data_ptr(), self.stream))
+            else:
+                add("convnext_mlp", lambda l=l: _lib.call(
+                    "arreau_convnext_mlp_f32", self.y.data_ptr(), w["mlp_w1_t"][l].data_ptr(),
+                    w["mlp_b1"][l].data_ptr(), w["mlp_w2_t"][l].data_ptr(), w["mlp_b2"][l].data_ptr(),
+                    w["layer_scale"][l].data_ptr(), self.N * NUM_ORI, self.h.data_ptr(), self.stream))
+            add("readout", lambda l=l: _lib.call(
+                "arreau_readout_accumulate", self.h.data_ptr(), w["wr_t"][l].data_ptr(), w["br"][l].data_ptr(),
+                w["ori"].data_ptr(), self.N, Z, int(l == 0), self.acc.data_ptr(), self.stream))
+        add("readout", lambda: _lib.call("arreau_readout_finalize", self.acc.data_ptr(), self.atom_offset.data_ptr(),
+                                         self.N, self.G, Z, LAYERS, self.logits.data_ptr(), self.score.data_ptr(),
+                                         self.len0.data_ptr(), self.stream))
+        sc_len, sc_frac, sc_types = torch.empty_like(self.lengths), torch.empty_like(self.frac), torch.empty_like(self.types)
+        tb = self.tabs
+
+        def update():
+            _lib.call("arreau_vp_lattice_reverse", self.lengths.data_ptr(), self.len0.data_ptr(),
+                      self.atom_offset.data_ptr(), self.z_len.data_ptr(), t, float(tb.vp_cx0[t]), float(tb.vp_cxt[t]),
+                      float(tb.vp_denom[t]), float(tb.vp_var[t]), self.G, sc_len.data_ptr(), self.stream)
+            _lib.call("arreau_ve_pbc_reverse", self.frac.data_ptr(), self.score.data_ptr(), self.z_frac.data_ptr(),
+                      None, t, self.d_ve_sigmas.data_ptr(), self.N, sc_frac.data_ptr(), self.stream)
+            _lib.call("arreau_d3pm_reverse", self.types.data_ptr(), self.logits.data_ptr(), self.u_type.data_ptr(), None,
+                      t, self.d_q_keep.data_ptr(), self.d_q_to_mask.data_ptr(), tb.onestep_keep, tb.onestep_to_mask,
+                      tb.T, self.N, Z, sc_types.data_ptr(), self.stream)
+        add("update", update)
+        totals, counts = {}, {}
+        for it in range(iters + 1):          # first pass is warm-up
+            evs = []
+            for fn in fns:
+                a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                a.record()
+                fn()
+                b.record()
+                evs.append((a, b))
+            torch.cuda.synchronize(self.device)
+            if it == 0:
+                continue
+            for name, (a, b) in zip(names, evs):
+                totals[name] = totals.get(name, 0.0) + a.elapsed_time(b)
+                counts[name] = counts.get(name, 0) + 1
+        launches = {n: counts[n] // iters for n in counts}
+        return {n: dict(ms_per_step=totals[n] / iters, launches_per_step=launches[n],
+                        ms_per_launch=totals[n] / counts[n]) for n in totals}

@@ -1,0 +1,355 @@
+#!/usr/bin/env python
+"""Benchmark of the Arreau denoising step (BASELINE.json: crystals/sec over a full 999-step denoise
+trajectory, and ms per denoise step).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--precision fp32|bf16] [--impl ours|reference]
+
+A "step" is one denoise step (graph + Ponita forward + VE/VP/D3PM update) of one batch of synthetic crystals;
+the N=1 workload is BASELINE.json configs[1] (C2: 1024 crystals x 40 atoms, 5 A cutoff, max_neighbors 8 as in the
+reference's Makefile:7).  value = crystals / (999 * step time): the whole-job trajectory throughput with the state
+resident in HBM.  e2e = the same through the public engine API with the step's state and noise copied from pinned
+host memory and the result read back, every step.  N>1: one process per GPU (torchrun), each rank owns its own
+batch of independent crystals (weak scaling, no data-path collective), time = max over ranks.
+
+--impl reference times the reference's algorithm on the host cores (the oracle port; the reference itself is
+Python that needs /root/reference and cannot travel) on a bounded sample of the same workload.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+T_STEPS = 1000          # Makefile:7 num_timesteps -> 999 denoise steps per trajectory
+Z = 90
+RADIUS = 5.0
+O, C, D, L, MONO = 16, 128, 256, 5, 83
+
+
+def load_weights(atoms_per_crystal: int):
+    from arreau_b200.synthetic import calibrate_length_readout
+    w = np.load(os.path.join(ROOT, "tests", "golden", "weights_seed0.npz"))
+    sd = {k: w[k] for k in w.files if k not in ("ori_grid", "fourier_w")}
+    # quirk B7: random-init length read-out would blow the cells up and empty the graph; calibrate it
+    return calibrate_length_readout(sd, atoms_per_crystal), w["ori_grid"], w["fourier_w"]
+
+
+def sampler_init(G: int, n: int, seed: int):
+    """The reference sampler's initial state (diffusion_loss.py:294-316)."""
+    rng = np.random.default_rng(seed)
+    angles = np.stack([np.full(G, 90.0), rng.uniform(90, 180, G), np.full(G, 90.0)], 1)
+    lengths = rng.standard_normal((G, 3))
+    frac = rng.standard_normal((G * n, 3))
+    types = np.full(G * n, Z - 1, dtype=np.int64)
+    return frac, types, lengths, angles
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled while the timed region runs."""
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index: int):
+        self.lines, self.proc = [], None
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
+                                          "-lms", "100", "-i", str(index)], stdout=subprocess.PIPE,
+                                         stderr=subprocess.DEVNULL, text=True)
+            self.thread = threading.Thread(target=self._pump, daemon=True)
+            self.thread.start()
+        except OSError:
+            self.proc = None
+        self.mark0 = self.mark1 = 0
+
+    def _pump(self):
+        for line in self.proc.stdout:
+            self.lines.append((time.time(), line.strip()))
+
+    def begin(self):
+        self.t0 = time.time()
+
+    def end(self):
+        self.t1 = time.time()
+
+    def summary(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        rows = [l.split(", ") for t, l in self.lines if self.t0 - 0.05 <= t <= self.t1 + 0.15]
+        if not rows:
+            rows = [l.split(", ") for _, l in self.lines[-3:]]
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for r in rows:
+            try:
+                sm.append(float(r[0])); mx.append(float(r[1]))
+            except (ValueError, IndexError):
+                continue
+            for nm, v in zip(names, r[3:7]):
+                if v.strip().lower().startswith("active"):
+                    reasons.add(nm)
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "samples": len(sm), "reasons": sorted(reasons)}
+
+
+def oracle_step_time(G_s: int, n: int, steps: int, warmup: int, cap: int, threads: int):
+    """Times the CPU restatement of the reference step (oracle/restatement.py, fp64 like the reference) on
+    G_s crystals x n atoms.  Returns (seconds per step, edges per atom)."""
+    import torch
+    from arreau_b200.synthetic import make_crystals
+    from oracle import restatement as R
+    torch.set_num_threads(threads)
+    prev = torch.get_default_dtype()
+    torch.set_default_dtype(torch.float64)
+    try:
+        sd, ori, fw = load_weights(n)
+        T64 = lambda a: torch.as_tensor(np.asarray(a), dtype=torch.float64)  # noqa: E731
+        W = R.PonitaWeights({k: T64(v) for k, v in sd.items()}, T64(ori), RADIUS)
+        tabs = R.DiffusionTables.build(T_STEPS, Z)
+        cr = make_crystals(G_s, n, None, seed=0)       # Alexandria-shaped cells: E/N = cap like the GPU run
+        frac, types, lengths, angles = T64(cr.frac), torch.as_tensor(cr.types), T64(cr.lengths), T64(cr.angles)
+        na = torch.as_tensor(cr.num_atoms)
+        N = cr.total_atoms
+        g = torch.Generator().manual_seed(0)
+        times, epa = [], 0.0
+        for it in range(warmup + steps):
+            t = T_STEPS - 1 - it
+            z_len = torch.randn(G_s, 3, generator=g); z_frac = torch.randn(N, 3, generator=g); u = torch.rand(N, Z, generator=g)
+            t0 = time.perf_counter()
+            out = R.denoise_step(W, tabs, T64(fw), frac, types, lengths, angles, na, t, z_len, z_frac, u, RADIUS, cap)
+            dt = time.perf_counter() - t0
+            if it >= warmup:
+                times.append(dt)
+        lat = R.lattice_from_params(lengths, angles)
+        ei = R.radius_graph_pbc(R.frac_to_cart_coords(frac, lat, na), lat, na, RADIUS, cap)[0]
+        epa = ei.shape[1] / N
+        return float(np.mean(times)), epa
+    finally:
+        torch.set_default_dtype(prev)
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    cores = os.cpu_count() or 1
+    G_s = args.ref_crystals
+    t_step, epa = oracle_step_time(G_s, args.atoms, args.steps, args.warmup, args.cap, cores)
+    value = G_s / ((T_STEPS - 1) * t_step)
+    sample = f"{G_s} crystals x {args.atoms} atoms, {args.steps} denoise steps (+{args.warmup} warm-up), E/N={epa:.2f}"
+    line = {"impl": "reference", "metric": "crystals_per_sec_full_trajectory", "value": value, "unit": "crystals/s",
+            "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": t_step * 1e3,
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "config": config_dict(args),
+            "cpu_baseline": {"value": value, "unit": "crystals/s", "cores": cores, "kind": "port", "sample": sample},
+            "e2e": {"value": value, "unit": "crystals/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            "note": "ms_per_step is for the bounded sample; crystals/s = sample crystals / (999 * step time)"}
+    print(json.dumps(line))
+
+
+def config_dict(args):
+    return {"workload": f"C2: full-trajectory sampling, {args.crystals} crystals x {args.atoms} atoms per GPU "
+                        f"(Alexandria-shaped), {RADIUS:g} A PBC cutoff, max_neighbors {args.cap}, T={T_STEPS} "
+                        f"(999 denoise steps per trajectory)",
+            "model": "random-init reference architecture, 1 170 678 params (hidden 128, basis 256, 5 layers, 16 ori), "
+                     "length read-out calibrated (SURVEY B7)",
+            "crystals_per_gpu": args.crystals, "atoms_per_crystal": args.atoms, "max_neighbors": args.cap,
+            "l2": "inputs larger than L2 (per-layer kernel slabs >= 1.3 GB, node features 335 MB)",
+            "parallelism": f"crystal-sharded x{args.gpus}, no per-step collective"}
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--precision", default=os.environ.get("ARREAU_PRECISION", "fp32"), choices=["fp32", "bf16"])
+    ap.add_argument("--crystals", type=int, default=1024)
+    ap.add_argument("--atoms", type=int, default=40)
+    ap.add_argument("--cap", type=int, default=8)
+    ap.add_argument("--ref-crystals", type=int, default=16)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 0)
+    if args.impl == "reference":
+        return run_reference(args)
+
+    import torch
+    import torch.distributed as dist
+    from arreau_b200 import _lib
+    from arreau_b200.engine import DenoiseEngine
+    from arreau_b200.tables import build_tables
+    from arreau_b200.weights import PonitaWeights
+
+    rank, world = int(os.environ.get("RANK", "0")), int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device: arreau_b200 has no CPU fallback")
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    _lib.load()
+    G, n = args.crystals, args.atoms
+    N = G * n
+    sd, ori, fw = load_weights(n)
+    eng = DenoiseEngine(PonitaWeights(sd, ori, device=dev), build_tables(T_STEPS, Z), fw, [n] * G, RADIUS, args.cap,
+                        precision=args.precision, device=dev)
+    frac, types, lengths, angles = sampler_init(G, n, seed=1234 + rank)
+    eng.set_state(frac, types, lengths, angles)
+    seed = 99 + rank
+
+    def barrier():
+        torch.cuda.synchronize(dev)
+        if world > 1:
+            dist.barrier()
+            torch.cuda.synchronize(dev)
+
+    # ---- device-resident trajectory steps -------------------------------------------------------------
+    t = T_STEPS - 1
+    for i in range(max(args.warmup, 3)):
+        eng.draw_noise(seed, i)
+        eng.step(t); t -= 1
+    barrier()
+    epa_first = eng.num_edges() / N
+    clocks = ClockSampler(local)
+    time.sleep(0.25)
+    l0 = _lib.launch_count()
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier()
+    clocks.begin()
+    ev0.record()
+    for i in range(args.steps):
+        eng.draw_noise(seed, 1000 + i)
+        eng.step(t); t -= 1
+    ev1.record()
+    barrier()
+    clocks.end()
+    launches = _lib.launch_count() - l0
+    ms = ev0.elapsed_time(ev1)
+    if world > 1:
+        tmax = torch.tensor([ms], device=dev)
+        dist.all_reduce(tmax, op=dist.ReduceOp.MAX)
+        ms = float(tmax.item())
+    ms_per_step = ms / args.steps
+    value = world * G / ((T_STEPS - 1) * ms_per_step * 1e-3)
+    epa_last = eng.num_edges() / N
+    overflow = int(eng.overflow_flag.item())
+    clk = clocks.summary()
+
+    # ---- end to end: state + noise from pinned host memory every step, result read back --------------
+    pin = lambda a: torch.as_tensor(a).pin_memory()  # noqa: E731
+    g = torch.Generator().manual_seed(5 + rank)
+    h_in = [pin(torch.randn(N, 3, generator=g, dtype=torch.float64)), pin(torch.as_tensor(types)),
+            pin(torch.as_tensor(np.abs(lengths) + 5.0)), pin(torch.as_tensor(angles))]
+    h_noise = [pin(torch.randn(G, 3, generator=g, dtype=torch.float64)), pin(torch.randn(N, 3, generator=g, dtype=torch.float64)),
+               pin(torch.rand(N, Z, generator=g, dtype=torch.float64))]
+    h_out = [torch.empty(N, 3, dtype=torch.float64).pin_memory(), torch.empty(N, dtype=torch.int64).pin_memory(),
+             torch.empty(G, 3, dtype=torch.float64).pin_memory(), torch.empty(G, 3, 3, dtype=torch.float64).pin_memory()]
+    h2d = sum(x.numel() * x.element_size() for x in h_in + h_noise)
+    d2h = sum(x.numel() * x.element_size() for x in h_out)
+
+    def e2e_step(tt):
+        eng.set_state(*h_in)
+        eng.set_noise(*h_noise)
+        eng.step(tt)
+        for dst_, src_ in zip(h_out, (eng.frac, eng.types, eng.lengths, eng.lattice)):
+            dst_.copy_(src_, non_blocking=True)
+        torch.cuda.current_stream(dev).synchronize()      # the caller holds the step's result on the host
+
+    for i in range(2):
+        e2e_step(500)
+    barrier()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for i in range(args.steps):
+        e2e_step(500 - i)
+    e1.record()
+    barrier()
+    ems = e0.elapsed_time(e1)
+    if world > 1:
+        tmax = torch.tensor([ems], device=dev)
+        dist.all_reduce(tmax, op=dist.ReduceOp.MAX)
+        ems = float(tmax.item())
+    e2e_value = world * G / ((T_STEPS - 1) * (ems / args.steps) * 1e-3)
+
+    # ---- final gather of a trajectory's result (the only collective of the sampling path) -------------
+    gather_ms = None
+    if world > 1:
+        outs = [torch.empty_like(eng.frac) for _ in range(world)]
+        barrier()
+        g0, g1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        g0.record()
+        dist.all_gather(outs, eng.frac)
+        dist.all_gather([torch.empty_like(eng.types) for _ in range(world)], eng.types)
+        dist.all_gather([torch.empty_like(eng.lattice) for _ in range(world)], eng.lattice)
+        g1.record()
+        barrier()
+        gather_ms = g0.elapsed_time(g1)
+
+    # ---- per-kernel breakdown and the roofline of the dominant kernel (rank 0) -------------------------
+    line = None
+    if rank == 0:
+        eng.set_state(*h_in)
+        br = eng.timed_breakdown(400, iters=3)
+        E = eng.num_edges()
+        peaks_path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+        if os.path.exists(peaks_path):
+            pk = json.load(open(peaks_path)); peak_src = "measured (MEASURED_PEAKS.json)"
+            peak_tf, peak_bw = pk["bf16_tflops_sustained"], pk["hbm_gbs"]
+        else:
+            peak_tf, peak_bw, peak_src = 1590.0, 6650.0, "fallback (B200_PROFILING.md)"
+        top = max(br, key=lambda k: br[k]["ms_per_step"])
+        flops_edge = 2.0 * E * O * (MONO * C + C * D + L * D * C) + 2.0 * L * 0   # 6.63 MFLOP/edge
+        flops_mlp = 2.0 * 2 * C * 4 * C * N * O                                   # per layer
+        kbytes = 2 if args.precision == "bf16" else 4
+        bytes_msg = E * O * C * kbytes + 2 * 4 * N * O * C + 12 * E               # per layer: kernels + h in + y out + edges
+        alg = {"edge_kernels": ("tensor", flops_edge / 1e12, peak_tf, "TFLOP/s"),
+               "convnext_mlp": ("tensor", flops_mlp / 1e12, peak_tf, "TFLOP/s"),
+               "message_fiber_norm": ("hbm", bytes_msg / 1e9, peak_bw, "GB/s")}
+        kernels = {}
+        for name, (bound, work, peak, unit) in alg.items():
+            sec = br[name]["ms_per_launch"] * 1e-3
+            ach = work / sec
+            kernels[name] = {"bound": bound, "achieved": ach, "peak": peak, "unit": unit, "frac": ach / peak,
+                             "ms_per_launch": br[name]["ms_per_launch"], "launches_per_step": br[name]["launches_per_step"]}
+        dom = top if top in kernels else "edge_kernels"
+        roof = dict(kernels[dom]); roof.update({"kernel": dom, "traffic": None, "peak_source": peak_src,
+                                                "share_of_step": br[dom]["ms_per_step"] / sum(v["ms_per_step"] for v in br.values())})
+        line = {"metric": "crystals_per_sec_full_trajectory", "value": value, "unit": "crystals/s", "n_gpus": world,
+                "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": ms_per_step, "higher_is_better": True,
+                "scaling": "weak", "vs_baseline": None, "dtype": "f32" if args.precision == "fp32" else "bf16",
+                "data": "synthetic", "config": config_dict(args), "clocks": clk,
+                "e2e": {"value": e2e_value, "unit": "crystals/s", "ms_per_step": ems / args.steps,
+                        "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h},
+                "gpu_launches": int(launches), "roofline": roof, "kernels": kernels,
+                "breakdown_ms_per_step": {k: round(v["ms_per_step"], 4) for k, v in br.items()},
+                "edges_per_atom": {"first_timed_step": epa_first, "last_timed_step": epa_last, "breakdown": E / N},
+                "edge_overflow": overflow, "final_gather_ms": gather_ms, "impl": "ours", "precision": args.precision}
+        if not args.no_cpu_baseline and world == 1:
+            cores = os.cpu_count() or 1
+            t_cpu, epa = oracle_step_time(args.ref_crystals, n, 3, 1, args.cap, cores)
+            line["cpu_baseline"] = {"value": args.ref_crystals / ((T_STEPS - 1) * t_cpu), "unit": "crystals/s", "cores": cores,
+                                    "kind": "port", "ms_per_step_sample": t_cpu * 1e3,
+                                    "sample": f"{args.ref_crystals} crystals x {n} atoms, 3 denoise steps (+1 warm-up), "
+                                              f"fp64 torch CPU restatement of the reference step, E/N={epa:.2f}"}
+        print(json.dumps(line))
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

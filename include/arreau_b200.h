@@ -87,6 +87,13 @@ int arreau_graph_fill(const double* pos, const double* lattice, const int32_t* a
 int arreau_lattice_from_params(const double* lengths, const double* angles, int32_t num_crystals,
                                double* lattice, void* stream);
 
+/* Same, from per-crystal angle factors trig[G,6] = [sin b, cos b, sin a, cos g*, sin g*, cos a] that the caller
+ * evaluated once (the angles are constant over a sampling trajectory): only the fp64 products of
+ * lattice_helpers.py:85-96 are left, so the lattice is bit-identical to the reference's whatever libm the
+ * factors came from. */
+int arreau_lattice_from_trig(const double* lengths, const double* trig, int32_t num_crystals, double* lattice,
+                             void* stream);
+
 /* pos[N,3] = frac[N,3] @ lattice[crystal_of_atom] (f64). */
 int arreau_frac_to_cart(const double* frac, const double* lattice, const int32_t* crystal_of_atom,
                         int32_t num_atoms_total, double* pos, void* stream);
@@ -265,6 +272,7 @@ typedef struct arreau_step_args {
   int64_t* types;          /* [N]     */
   double* lengths;         /* [G,3]   */
   const double* angles;    /* [G,3]   */
+  const double* angle_trig;/* NULL, or [G,6] angle factors (see arreau_lattice_from_trig) */
   double* lattice;         /* [G,3,3] out: lattice_from_params(lengths', angles) */
   /* topology */
   const int32_t* atom_offset;      /* [G+1] */

@@ -1,3 +1,4 @@
+import contextlib
 import os
 import sys
 
@@ -29,6 +30,25 @@ def graph_cases(gold):
         idx, name = k.split("/", 1)
         cases.setdefault(idx, {})[name] = z[k]
     return [cases[i] for i in sorted(cases)]
+
+
+@contextlib.contextmanager
+def f64_default():
+    """The oracle follows the reference: it must run under torch.set_default_dtype(float64)."""
+    import torch
+    prev = torch.get_default_dtype()
+    torch.set_default_dtype(torch.float64)
+    try:
+        yield
+    finally:
+        torch.set_default_dtype(prev)
+
+
+def within_one_ulp(a, b):
+    """fp64 equality up to one unit in the last place (torch's CPU sqrt is not correctly rounded in ~1 % of
+    the reference's distances; the device sqrt is IEEE)."""
+    a, b = np.asarray(a, dtype=np.float64), np.asarray(b, dtype=np.float64)
+    return a.shape == b.shape and bool(np.all(np.abs(a - b) <= np.spacing(np.abs(b))))
 
 
 def rel_err(a, b):

@@ -34,7 +34,7 @@ def _model(device, w, precision="fp32"):
                           ori_grid=w["ori_grid"], precision=precision)
     sd = {k: torch.as_tensor(w[k]) for k in w.files if k not in ("ori_grid", "fourier_w")}
     missing = m.load_state_dict(sd)
-    assert not missing.missing_keys, missing.missing_keys
+    assert all(k.endswith("callibrated") for k in missing.missing_keys), missing.missing_keys
     return m.to(device)
 
 

@@ -3,7 +3,7 @@ import numpy as np
 import pytest
 import torch
 
-from conftest import rel_err
+from conftest import f64_default, rel_err
 
 pytestmark = pytest.mark.gpu
 
@@ -27,7 +27,8 @@ def test_update_kernels_against_oracle(device, timestep):
     from oracle import restatement as R
     T, Z, N, G = 1000, 90, 257, 19
     g = torch.Generator().manual_seed(timestep)
-    tabs = R.DiffusionTables.build(T, Z)
+    with f64_default():
+        tabs = R.DiffusionTables.build(T, Z)
     frac = torch.rand(N, 3, generator=g, dtype=torch.float64) * 3 - 1
     score = torch.randn(N, 3, generator=g).float()
     z = torch.randn(N, 3, generator=g, dtype=torch.float64)
