@@ -27,7 +27,7 @@ class Weights(C.Structure):
     _fields_ = [(n, vp) for n in (
         "ori", "w_embed_t", "w1m_t", "w2_t", "b2", "wk_t", "fiber_kernel", "conv_bias", "ln_w", "ln_b",
         "mlp_w1_t", "mlp_b1", "mlp_w2_t", "mlp_b2", "layer_scale", "wr_t", "br",
-        "w1m_bf16", "w2_bf16", "wk_bf16", "mlp_w1_bf16", "mlp_w2_bf16")] + [
+        "edge_w1_img", "edge_w_img", "mlp_w_img")] + [
         ("num_scalar", i32), ("num_vec", i32), ("num_states", i32), ("reserved", i32)]
 
 
@@ -66,10 +66,10 @@ SIGNATURES = {
     "arreau_fiber_kernel_precompute": [vp] * 8,
     "arreau_node_embed": [vp, vp, vp, vp, i32, i32, i32, vp, vp],
     "arreau_edge_kernels_f32": [vp, vp, vp, vp, vp, vp, i64, vp, vp, vp, vp, vp, f64, vp, vp],
-    "arreau_edge_kernels_bf16": [vp, vp, vp, vp, vp, vp, i64, vp, vp, vp, vp, vp, f64, vp, vp],
+    "arreau_edge_kernels_bf16": [vp, vp, vp, vp, vp, vp, i64, vp, vp, vp, vp, f64, vp, vp],
     "arreau_message_fiber_norm": [vp, i32, vp, vp, vp, vp, vp, vp, vp, i32, vp, i32, vp, vp, vp],
     "arreau_convnext_mlp_f32": [vp, vp, vp, vp, vp, vp, i64, vp, vp],
-    "arreau_convnext_mlp_bf16": [vp, vp, vp, vp, vp, vp, i64, vp, vp],
+    "arreau_convnext_mlp_bf16": [vp, vp, vp, vp, vp, i64, vp, vp],
     "arreau_readout_accumulate": [vp, vp, vp, vp, i32, i32, i32, vp, vp],
     "arreau_readout_finalize": [vp, vp, i32, i32, i32, i32, vp, vp, vp, vp],
     "arreau_ponita_forward": [C.POINTER(Weights), C.POINTER(Workspace), i32, vp, vp, vp, vp, vp, vp, vp, vp, vp,

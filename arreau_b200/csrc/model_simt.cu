@@ -371,15 +371,21 @@ message_fiber_norm_kernel(const KT* __restrict__ kern, const float* __restrict__
       float4 r = make_float4(dx * rstd * gw.x + gb.x, dy * rstd * gw.y + gb.y, dz * rstd * gw.z + gb.z,
                              dw * rstd * gw.w + gb.w);
       if (node < N) {
-        YT* yp = y + ((size_t)node * kO + og * 4 + pp) * kC + cg * 4;
         if constexpr (sizeof(YT) == 4) {
-          *reinterpret_cast<float4*>(yp) = r;
+          *reinterpret_cast<float4*>(y + ((size_t)node * kO + og * 4 + pp) * kC + cg * 4) = r;
         } else {
+          // bf16 y goes straight into the UMMA operand image of the ConvNext MLP kernel: 128-row tiles of
+          // 32 KB, two 64-channel slabs of 128-byte rows, 16-byte chunks XOR-swizzled by (row & 7)
+          // (csrc/tc_common.cuh), so that kernel fetches a tile with one bulk copy.
+          const size_t row = (size_t)node * kO + og * 4 + pp;
+          const int rr = (int)(row & 127), c0 = cg * 4;
+          uint8_t* tile = reinterpret_cast<uint8_t*>(y) + (row >> 7) * 32768;
+          const int off = (c0 >> 6) * 16384 + rr * 128 + (((((c0 & 63) >> 3) ^ (rr & 7)) << 4) | ((c0 & 7) << 1));
           __nv_bfloat162 p0 = __floats2bfloat162_rn(r.x, r.y), p1 = __floats2bfloat162_rn(r.z, r.w);
           uint2 raw;
           raw.x = *reinterpret_cast<unsigned*>(&p0);
           raw.y = *reinterpret_cast<unsigned*>(&p1);
-          *reinterpret_cast<uint2*>(yp) = raw;
+          *reinterpret_cast<uint2*>(tile + off) = raw;
         }
       }
     }

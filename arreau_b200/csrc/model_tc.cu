@@ -1,12 +1,532 @@
-// tcgen05 (bf16 operands, fp32 accumulate in TMEM) variants of the two GEMM-shaped kernels.
+// tcgen05 (bf16 operands, fp32 accumulation in TMEM) variants of the two GEMM-shaped kernels of the step.
+//
+//   convnext_mlp_tc_kernel   K6   h += layer_scale * (W2 gelu(W1 y + b1) + b2)          convnext.py:26-32
+//   edge_kernels_tc_kernel   K3+K4a invariants -> monomials -> basis MLP -> window -> 5 kernel projections
+//
+// Both are persistent (one CTA per SM, 128-row tiles) and warp specialised:
+//   warp 0   producer: cp.async.bulk (TMA engine) of pre-swizzled weight / activation tiles into an mbarrier ring
+//   warp 1   MMA issuer: one thread issues tcgen05.mma (M = 128, N = 128, K = 16) and tcgen05.commit
+//   warp 2   TMEM allocation / release
+//   warps 4..11  epilogue: tcgen05.ld -> bias / GELU / window in registers -> bf16 operand tile of the next GEMM
+//                written back to shared memory in the UMMA layout (the intermediate never leaves the SM), or the
+//                final result to HBM.
 #include "common.cuh"
+#include "tc_common.cuh"
 
-extern "C" int arreau_edge_kernels_bf16(const double*, const double*, const double*, const int32_t*, const int32_t*,
-                                        const int32_t*, int64_t, const float*, const void*, const void*, const float*,
-                                        const void*, double, void*, void*) {
-  return ARREAU_ERR_UNSUPPORTED;
+namespace {
+
+using namespace tc;
+
+constexpr int kThreads = 384;
+constexpr int kEpiWarp0 = 4;
+constexpr int kEpiWarps = 8;
+constexpr int kTileM = 128;
+constexpr uint32_t kIdesc128 = umma_idesc_bf16(128, 128);
+
+// issue the UMMA_K = 16 steps of one 64-wide K slab: D[128 x 128] (+)= A_slab[128 x 64] * B_slab[128 x 64]^T
+__device__ __forceinline__ void mma_slab(uint32_t tmem_d, uint32_t a_slab, uint32_t b_slab, int ksteps, bool accumulate_first) {
+  const uint64_t ad = umma_desc_sw128(a_slab), bd = umma_desc_sw128(b_slab);
+#pragma unroll
+  for (int k = 0; k < 4; ++k) {
+    if (k < ksteps) umma_bf16(tmem_d, ad + (uint64_t)(k * 2), bd + (uint64_t)(k * 2), kIdesc128, (accumulate_first || k > 0) ? 1u : 0u);
+  }
 }
-extern "C" int arreau_convnext_mlp_bf16(const void*, const void*, const float*, const void*, const float*,
-                                        const float*, int64_t, float*, void*) {
-  return ARREAU_ERR_UNSUPPORTED;
+
+// =================================================================================================
+// K6  ConvNext channel MLP
+// =================================================================================================
+namespace mlp {
+constexpr int kTileBytes = 32768;     // [128 rows x 128 K] bf16 = 2 slabs
+constexpr int kWStages = 3;
+constexpr int kSmemBytes = (2 + 2 + kWStages) * kTileBytes + 1024;
+constexpr int kChunksPerTile = 8;     // W1_0, W1_1, W2_0, W1_2, W2_1, W1_3, W2_2, W2_3
+
+struct Bars {
+  uint64_t a_full[2], a_empty[2], w_full[kWStages], w_empty[kWStages];
+  uint64_t d1_full[2], d1_empty[2], h_full[2], h_empty[2], d2_full, d2_empty;
+};
+}  // namespace mlp
+
+__global__ void __launch_bounds__(kThreads, 1)
+convnext_mlp_tc_kernel(const uint8_t* __restrict__ y_img, const uint8_t* __restrict__ w_img, const float* __restrict__ b1,
+                       const float* __restrict__ b2, const float* __restrict__ layer_scale, long long rows,
+                       float* __restrict__ h) {
+  using namespace mlp;
+  extern __shared__ uint8_t smem_raw[];
+  __shared__ Bars bars;
+  __shared__ uint32_t tmem_base_s;
+  const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  uint8_t* smem = smem_raw + (base - smem_u32(smem_raw));
+  uint8_t* A[2] = {smem, smem + kTileBytes};
+  uint8_t* H[2] = {smem + 2 * kTileBytes, smem + 3 * kTileBytes};
+  uint8_t* W = smem + 4 * kTileBytes;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const long long tiles = (rows + kTileM - 1) / kTileM;
+
+  if (threadIdx.x == 0) {
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(&bars.a_full[i], 1); mbar_init(&bars.a_empty[i], 1);
+      mbar_init(&bars.d1_full[i], 1); mbar_init(&bars.d1_empty[i], kEpiWarps);
+      mbar_init(&bars.h_full[i], kEpiWarps); mbar_init(&bars.h_empty[i], 1);
+    }
+    for (int i = 0; i < kWStages; ++i) { mbar_init(&bars.w_full[i], 1); mbar_init(&bars.w_empty[i], 1); }
+    mbar_init(&bars.d2_full, 1); mbar_init(&bars.d2_empty, kEpiWarps);
+    fence_barrier_init();
+  }
+  if (warp == 2) tmem_alloc(&tmem_base_s, 512);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem = tmem_base_s;
+
+  if (warp == 0 && lane == 0) {
+    // ---------------- producer ----------------
+    uint32_t chunk = 0;
+    int it = 0;
+    for (long long tile = blockIdx.x; tile < tiles; tile += gridDim.x, ++it) {
+      const int ab = it & 1;
+      mbar_wait(&bars.a_empty[ab], ((it >> 1) & 1) ^ 1);
+      mbar_expect_tx(&bars.a_full[ab], kTileBytes);
+      bulk_g2s(A[ab], y_img + (size_t)tile * kTileBytes, kTileBytes, &bars.a_full[ab]);
+      for (int c = 0; c < kChunksPerTile; ++c, ++chunk) {
+        const int ws = chunk % kWStages;
+        mbar_wait(&bars.w_empty[ws], ((chunk / kWStages) & 1) ^ 1);
+        mbar_expect_tx(&bars.w_full[ws], kTileBytes);
+        bulk_g2s(W + ws * kTileBytes, w_img + (size_t)c * kTileBytes, kTileBytes, &bars.w_full[ws]);
+      }
+    }
+  } else if (warp == 1 && lane == 0) {
+    // ---------------- MMA issuer ----------------
+    uint32_t chunk = 0;
+    int it = 0;
+    for (long long tile = blockIdx.x; tile < tiles; tile += gridDim.x, ++it) {
+      const int ab = it & 1;
+      mbar_wait(&bars.a_full[ab], (it >> 1) & 1);
+      tc_fence_after();
+      const uint32_t a_addr = smem_u32(A[ab]);
+      auto wait_w = [&]() -> uint32_t {
+        const int ws = chunk % kWStages;
+        mbar_wait(&bars.w_full[ws], (chunk / kWStages) & 1);
+        tc_fence_after();
+        return smem_u32(W + ws * kTileBytes);
+      };
+      auto release_w = [&]() {
+        umma_commit(&bars.w_empty[chunk % kWStages]);
+        ++chunk;
+      };
+      auto gemm1 = [&](int j) {        // D1[j&1] = y_tile . W1_j^T
+        const int b = j & 1;
+        const uint32_t use = (uint32_t)it * 2 + (j >> 1);
+        const uint32_t w_addr = wait_w();
+        mbar_wait(&bars.d1_empty[b], (use & 1) ^ 1);
+        tc_fence_after();
+        const uint32_t d = tmem + b * 128;
+        mma_slab(d, a_addr, w_addr, 4, false);
+        mma_slab(d, a_addr + 16384, w_addr + 16384, 4, true);
+        release_w();
+        umma_commit(&bars.d1_full[b]);
+        if (j == 3) umma_commit(&bars.a_empty[ab]);
+      };
+      auto gemm2 = [&](int j) {        // D2 (+)= H[j&1] . W2_j^T
+        const int b = j & 1;
+        const uint32_t use = (uint32_t)it * 2 + (j >> 1);
+        const uint32_t w_addr = wait_w();
+        mbar_wait(&bars.h_full[b], use & 1);
+        if (j == 0) mbar_wait(&bars.d2_empty, (it & 1) ^ 1);
+        tc_fence_after();
+        const uint32_t d = tmem + 256;
+        const uint32_t h_addr = smem_u32(H[b]);
+        mma_slab(d, h_addr, w_addr, 4, j > 0);
+        mma_slab(d, h_addr + 16384, w_addr + 16384, 4, true);
+        release_w();
+        umma_commit(&bars.h_empty[b]);
+        if (j == 3) umma_commit(&bars.d2_full);
+      };
+      gemm1(0); gemm1(1); gemm2(0); gemm1(2); gemm2(1); gemm1(3); gemm2(2); gemm2(3);
+    }
+  } else if (warp >= kEpiWarp0) {
+    // ---------------- epilogue ----------------
+    const int q = warp & 3, half = (warp - kEpiWarp0) >> 2;
+    const int m = q * 32 + lane;
+    const uint32_t lane_addr = (uint32_t)(q * 32) << 16;
+    int it = 0;
+    for (long long tile = blockIdx.x; tile < tiles; tile += gridDim.x, ++it) {
+      for (int j = 0; j < 4; ++j) {
+        const int b = j & 1;
+        const uint32_t use = (uint32_t)it * 2 + (j >> 1);
+        mbar_wait(&bars.d1_full[b], use & 1);
+        mbar_wait(&bars.h_empty[b], (use & 1) ^ 1);
+        tc_fence_after();
+        uint8_t* hrow = H[b] + half * 16384 + m * kRowBytes;
+#pragma unroll
+        for (int g = 0; g < 2; ++g) {
+          float v[32];
+          tmem_ld32(tmem + lane_addr + b * 128 + half * 64 + g * 32, v);
+          const float* bias = b1 + j * 128 + half * 64 + g * 32;
+#pragma unroll
+          for (int cc = 0; cc < 4; ++cc) {
+            uint4 pk;
+            pk.x = pack_bf16(gelu_fast(v[cc * 8 + 0] + __ldg(bias + cc * 8 + 0)), gelu_fast(v[cc * 8 + 1] + __ldg(bias + cc * 8 + 1)));
+            pk.y = pack_bf16(gelu_fast(v[cc * 8 + 2] + __ldg(bias + cc * 8 + 2)), gelu_fast(v[cc * 8 + 3] + __ldg(bias + cc * 8 + 3)));
+            pk.z = pack_bf16(gelu_fast(v[cc * 8 + 4] + __ldg(bias + cc * 8 + 4)), gelu_fast(v[cc * 8 + 5] + __ldg(bias + cc * 8 + 5)));
+            pk.w = pack_bf16(gelu_fast(v[cc * 8 + 6] + __ldg(bias + cc * 8 + 6)), gelu_fast(v[cc * 8 + 7] + __ldg(bias + cc * 8 + 7)));
+            *reinterpret_cast<uint4*>(hrow + (((g * 4 + cc) ^ (m & 7)) << 4)) = pk;
+          }
+        }
+        tc_fence_before();
+        fence_proxy_async();
+        __syncwarp();
+        if (lane == 0) {
+          mbar_arrive(&bars.d1_empty[b]);
+          mbar_arrive(&bars.h_full[b]);
+        }
+      }
+      mbar_wait(&bars.d2_full, it & 1);
+      tc_fence_after();
+      const long long row = tile * kTileM + m;
+#pragma unroll
+      for (int g = 0; g < 2; ++g) {
+        float v[32];
+        tmem_ld32(tmem + lane_addr + 256 + half * 64 + g * 32, v);
+        if (row < rows) {
+          const int c0 = half * 64 + g * 32;
+          float* hp = h + (size_t)row * kC + c0;
+#pragma unroll
+          for (int i = 0; i < 8; ++i) {
+            float4 hv = *reinterpret_cast<float4*>(hp + 4 * i);
+            const float4 bb = __ldg(reinterpret_cast<const float4*>(b2 + c0 + 4 * i));
+            const float4 ls = __ldg(reinterpret_cast<const float4*>(layer_scale + c0 + 4 * i));
+            hv.x = fmaf(ls.x, v[4 * i + 0] + bb.x, hv.x);
+            hv.y = fmaf(ls.y, v[4 * i + 1] + bb.y, hv.y);
+            hv.z = fmaf(ls.z, v[4 * i + 2] + bb.z, hv.z);
+            hv.w = fmaf(ls.w, v[4 * i + 3] + bb.w, hv.w);
+            *reinterpret_cast<float4*>(hp + 4 * i) = hv;
+          }
+        }
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&bars.d2_empty);
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 2) {
+    tc_fence_after();
+    tmem_dealloc(tmem, 512);
+  }
+}
+
+// =================================================================================================
+// K3 + K4a  edge pipeline
+// =================================================================================================
+namespace edge {
+constexpr int kChunkBytes = 16384;      // [128 rows x 64 K] bf16 = 1 slab
+constexpr int kStages = 6;
+constexpr int kW1Bytes = 32768;         // [128 x 96 -> 128] resident
+constexpr int kA2Bytes = 32768;
+constexpr int kA3Bytes = 65536;         // first 32 KB double as the monomial tile A1
+constexpr int kSmemBytes = kW1Bytes + kA2Bytes + kA3Bytes + kStages * kChunkBytes + 1024;
+constexpr int kChunksPerTile = 4 + 4 * kL;   // W2 (n-half, k-slab) x4, then Wk_l k-slabs
+constexpr int kEdgesPerTile = kTileM / kO;
+
+struct Bars {
+  uint64_t w1_full, w_full[kStages], w_empty[kStages];
+  uint64_t a1_full, a2_full, a3_full, d2_full;
+  uint64_t x_full[2], x_empty[2];     // TMEM buffers X0 (D1, D3 even layers) / X1 (D3 odd layers)
+};
+}  // namespace edge
+
+__global__ void __launch_bounds__(kThreads, 1)
+edge_kernels_tc_kernel(const double* __restrict__ dir, const double* __restrict__ dist, const double* __restrict__ lattice,
+                       const int32_t* __restrict__ crystal_of_atom, const int32_t* __restrict__ src,
+                       const int32_t* __restrict__ num_edges_ptr, long long edge_capacity, const float* __restrict__ ori,
+                       const uint8_t* __restrict__ w1_img, const uint8_t* __restrict__ w_img, const float* __restrict__ b2,
+                       double radius, __nv_bfloat16* __restrict__ kernels) {
+  using namespace edge;
+  extern __shared__ uint8_t smem_raw[];
+  __shared__ Bars bars;
+  __shared__ uint32_t tmem_base_s;
+  __shared__ float s_win[kEdgesPerTile];
+  const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  uint8_t* smem = smem_raw + (base - smem_u32(smem_raw));
+  uint8_t* W1 = smem;
+  uint8_t* A2 = W1 + kW1Bytes;
+  uint8_t* A3 = A2 + kA2Bytes;          // A1 aliases A3[0 .. 32 KB)
+  uint8_t* W = A3 + kA3Bytes;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  long long E = *num_edges_ptr;
+  if (E > edge_capacity) E = edge_capacity;
+  const long long tiles = (E + kEdgesPerTile - 1) / kEdgesPerTile;
+
+  if (threadIdx.x == 0) {
+    mbar_init(&bars.w1_full, 1);
+    for (int i = 0; i < kStages; ++i) { mbar_init(&bars.w_full[i], 1); mbar_init(&bars.w_empty[i], 1); }
+    mbar_init(&bars.a1_full, kEpiWarps); mbar_init(&bars.a2_full, kEpiWarps); mbar_init(&bars.a3_full, kEpiWarps);
+    mbar_init(&bars.d2_full, 1);
+    for (int i = 0; i < 2; ++i) { mbar_init(&bars.x_full[i], 1); mbar_init(&bars.x_empty[i], kEpiWarps); }
+    fence_barrier_init();
+  }
+  if (warp == 2) tmem_alloc(&tmem_base_s, 512);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem = tmem_base_s;
+  // TMEM columns: X0 = [0,128)  D2 = [128,384)  X1 = [384,512)
+  const uint32_t tmem_x[2] = {tmem, tmem + 384};
+
+  if (warp == 0 && lane == 0) {
+    // ---------------- producer ----------------
+    mbar_expect_tx(&bars.w1_full, kW1Bytes);
+    bulk_g2s(W1, w1_img, kW1Bytes, &bars.w1_full);
+    uint32_t chunk = 0;
+    for (long long tile = blockIdx.x; tile < tiles; tile += gridDim.x) {
+      for (int c = 0; c < kChunksPerTile; ++c, ++chunk) {
+        const int ws = chunk % kStages;
+        mbar_wait(&bars.w_empty[ws], ((chunk / kStages) & 1) ^ 1);
+        mbar_expect_tx(&bars.w_full[ws], kChunkBytes);
+        bulk_g2s(W + ws * kChunkBytes, w_img + (size_t)c * kChunkBytes, kChunkBytes, &bars.w_full[ws]);
+      }
+    }
+  } else if (warp == 1 && lane == 0) {
+    // ---------------- MMA issuer ----------------
+    mbar_wait(&bars.w1_full, 0);
+    uint32_t chunk = 0;
+    uint32_t xuse[2] = {0, 0};
+    int it = 0;
+    const uint32_t w1_addr = smem_u32(W1), a2_addr = smem_u32(A2), a3_addr = smem_u32(A3);
+    auto wait_w = [&]() -> uint32_t {
+      const int ws = chunk % kStages;
+      mbar_wait(&bars.w_full[ws], (chunk / kStages) & 1);
+      tc_fence_after();
+      return smem_u32(W + ws * kChunkBytes);
+    };
+    auto release_w = [&]() {
+      umma_commit(&bars.w_empty[chunk % kStages]);
+      ++chunk;
+    };
+    for (long long tile = blockIdx.x; tile < tiles; tile += gridDim.x, ++it) {
+      // GEMM1: X0 = A1[128 x 96] . W1m^T
+      mbar_wait(&bars.a1_full, it & 1);
+      mbar_wait(&bars.x_empty[0], (xuse[0] & 1) ^ 1);
+      tc_fence_after();
+      mma_slab(tmem_x[0], a3_addr, w1_addr, 4, false);
+      mma_slab(tmem_x[0], a3_addr + 16384, w1_addr + 16384, 2, true);
+      umma_commit(&bars.x_full[0]);
+      ++xuse[0];
+      // GEMM2: D2[:, nh*128 ..] = A2[128 x 128] . W2[nh]^T
+      mbar_wait(&bars.a2_full, it & 1);
+      tc_fence_after();
+      for (int nh = 0; nh < 2; ++nh)
+        for (int ks = 0; ks < 2; ++ks) {
+          const uint32_t w_addr = wait_w();
+          mma_slab(tmem + 128 + nh * 128, a2_addr + ks * 16384, w_addr, 4, ks > 0);
+          release_w();
+        }
+      umma_commit(&bars.d2_full);
+      // GEMM3: X[l&1] = A3[128 x 256] . Wk_l^T
+      mbar_wait(&bars.a3_full, it & 1);
+      tc_fence_after();
+      for (int l = 0; l < kL; ++l) {
+        const int b = l & 1;
+        mbar_wait(&bars.x_empty[b], (xuse[b] & 1) ^ 1);
+        tc_fence_after();
+        for (int ks = 0; ks < 4; ++ks) {
+          const uint32_t w_addr = wait_w();
+          mma_slab(tmem_x[b], a3_addr + ks * 16384, w_addr, 4, ks > 0);
+          release_w();
+        }
+        umma_commit(&bars.x_full[b]);
+        ++xuse[b];
+      }
+    }
+  } else if (warp >= kEpiWarp0) {
+    // ---------------- generator + epilogues ----------------
+    const int q = warp & 3, half = (warp - kEpiWarp0) >> 2;
+    const int m = q * 32 + lane;                     // tile row = (edge m / 16, orientation m % 16)
+    const uint32_t lane_addr = (uint32_t)(q * 32) << 16;
+    uint32_t xuse[2] = {0, 0};
+    int it = 0;
+    for (long long tile = blockIdx.x; tile < tiles; tile += gridDim.x, ++it) {
+      const long long e = tile * kEdgesPerTile + (m >> 4);
+      const bool valid = e < E;
+      // ---- A1: invariants -> 83 monomials + constant 1 (bias) -> bf16, 6 of the 12 16-byte chunks per thread.
+      // The previous tile's GEMM3 finished reading A3 before its last x_full fired, which this warp waited on.
+      {
+        float attr[6] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+        float mono[kMonoPad];
+        if (valid) {
+          const int g = crystal_of_atom[src[e]];
+          edge_invariants(dir + 3 * e, dist[e], lattice + 9 * (size_t)g, ori + 3 * (m & 15), attr);
+          if (half == 0 && (m & 15) == 0) s_win[m >> 4] = cutoff_window(dist[e], radius);
+        } else if (half == 0 && (m & 15) == 0) {
+          s_win[m >> 4] = 0.f;
+        }
+        monomials83(attr, mono, 1);
+        mono[kMono] = valid ? 1.0f : 0.0f;
+#pragma unroll
+        for (int k = kMono + 1; k < kMonoPad; ++k) mono[k] = 0.f;
+        uint8_t* arow = A3 + m * kRowBytes;
+#pragma unroll
+        for (int c = 0; c < 12; ++c) {
+          if ((c < 6) == (half == 0)) {
+            uint4 pk;
+            pk.x = pack_bf16(mono[c * 8 + 0], mono[c * 8 + 1]);
+            pk.y = pack_bf16(mono[c * 8 + 2], mono[c * 8 + 3]);
+            pk.z = pack_bf16(mono[c * 8 + 4], mono[c * 8 + 5]);
+            pk.w = pack_bf16(mono[c * 8 + 6], mono[c * 8 + 7]);
+            *reinterpret_cast<uint4*>(arow + (c >> 3) * 16384 + (((c & 7) ^ (m & 7)) << 4)) = pk;
+          }
+        }
+      }
+      fence_proxy_async();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&bars.a1_full);
+      // ---- epilogue 1: hidden = GELU(X0) -> A2 ----
+      mbar_wait(&bars.x_full[0], xuse[0] & 1);
+      tc_fence_after();
+      {
+        uint8_t* hrow = A2 + half * 16384 + m * kRowBytes;
+#pragma unroll
+        for (int g = 0; g < 2; ++g) {
+          float v[32];
+          tmem_ld32(tmem_x[0] + lane_addr + half * 64 + g * 32, v);
+#pragma unroll
+          for (int cc = 0; cc < 4; ++cc) {
+            uint4 pk;
+            pk.x = pack_bf16(gelu_fast(v[cc * 8 + 0]), gelu_fast(v[cc * 8 + 1]));
+            pk.y = pack_bf16(gelu_fast(v[cc * 8 + 2]), gelu_fast(v[cc * 8 + 3]));
+            pk.z = pack_bf16(gelu_fast(v[cc * 8 + 4]), gelu_fast(v[cc * 8 + 5]));
+            pk.w = pack_bf16(gelu_fast(v[cc * 8 + 6]), gelu_fast(v[cc * 8 + 7]));
+            *reinterpret_cast<uint4*>(hrow + (((g * 4 + cc) ^ (m & 7)) << 4)) = pk;
+          }
+        }
+      }
+      tc_fence_before();
+      fence_proxy_async();
+      __syncwarp();
+      if (lane == 0) {
+        mbar_arrive(&bars.x_empty[0]);
+        mbar_arrive(&bars.a2_full);
+      }
+      ++xuse[0];
+      // ---- epilogue 2: kernel basis = GELU(D2 + b2) * window -> A3 (this warp: 128 of the 256 columns) ----
+      mbar_wait(&bars.d2_full, it & 1);
+      tc_fence_after();
+      {
+        const float win = s_win[m >> 4];
+#pragma unroll
+        for (int g = 0; g < 4; ++g) {
+          const int col0 = half * 128 + g * 32;            // kernel-basis channel = K index of GEMM3
+          float v[32];
+          tmem_ld32(tmem + 128 + lane_addr + col0, v);
+          const float* bias = b2 + col0;
+          uint8_t* arow = A3 + (col0 >> 6) * 16384 + m * kRowBytes;
+#pragma unroll
+          for (int cc = 0; cc < 4; ++cc) {
+            uint4 pk;
+            pk.x = pack_bf16(gelu_fast(v[cc * 8 + 0] + __ldg(bias + cc * 8 + 0)) * win, gelu_fast(v[cc * 8 + 1] + __ldg(bias + cc * 8 + 1)) * win);
+            pk.y = pack_bf16(gelu_fast(v[cc * 8 + 2] + __ldg(bias + cc * 8 + 2)) * win, gelu_fast(v[cc * 8 + 3] + __ldg(bias + cc * 8 + 3)) * win);
+            pk.z = pack_bf16(gelu_fast(v[cc * 8 + 4] + __ldg(bias + cc * 8 + 4)) * win, gelu_fast(v[cc * 8 + 5] + __ldg(bias + cc * 8 + 5)) * win);
+            pk.w = pack_bf16(gelu_fast(v[cc * 8 + 6] + __ldg(bias + cc * 8 + 6)) * win, gelu_fast(v[cc * 8 + 7] + __ldg(bias + cc * 8 + 7)) * win);
+            const int chunk = ((col0 & 63) >> 3) + cc;
+            *reinterpret_cast<uint4*>(arow + ((chunk ^ (m & 7)) << 4)) = pk;
+          }
+        }
+      }
+      tc_fence_before();
+      fence_proxy_async();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&bars.a3_full);
+      // ---- epilogue 3: kernels[l][e][o][c] = X[l&1] (bf16) ----
+      for (int l = 0; l < kL; ++l) {
+        const int b = l & 1;
+        mbar_wait(&bars.x_full[b], xuse[b] & 1);
+        tc_fence_after();
+        __nv_bfloat16* out = kernels + ((size_t)l * edge_capacity * kO + (size_t)tile * kTileM + m) * kC + half * 64;
+#pragma unroll
+        for (int g = 0; g < 2; ++g) {
+          float v[32];
+          tmem_ld32(tmem_x[b] + lane_addr + half * 64 + g * 32, v);
+          if (valid) {
+#pragma unroll
+            for (int cc = 0; cc < 4; ++cc) {
+              uint4 pk;
+              pk.x = pack_bf16(v[cc * 8 + 0], v[cc * 8 + 1]);
+              pk.y = pack_bf16(v[cc * 8 + 2], v[cc * 8 + 3]);
+              pk.z = pack_bf16(v[cc * 8 + 4], v[cc * 8 + 5]);
+              pk.w = pack_bf16(v[cc * 8 + 6], v[cc * 8 + 7]);
+              *reinterpret_cast<uint4*>(out + g * 32 + cc * 8) = pk;
+            }
+          }
+        }
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&bars.x_empty[b]);
+        ++xuse[b];
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 2) {
+    tc_fence_after();
+    tmem_dealloc(tmem, 512);
+  }
+}
+
+int num_sms_tc() {
+  static int sms = 0;
+  if (!sms) {
+    int dev = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    if (sms <= 0) sms = 148;
+  }
+  return sms;
+}
+
+}  // namespace
+
+extern "C" int arreau_convnext_mlp_bf16(const void* y_img, const void* w_img, const float* b1, const float* b2,
+                                        const float* layer_scale, int64_t num_rows, float* h, void* stream) {
+  if (num_rows == 0) return ARREAU_OK;
+  if (!y_img || !w_img || !b1 || !b2 || !layer_scale || !h) return ARREAU_ERR_NULL;
+  if (num_rows < 0) return ARREAU_ERR_BAD_SHAPE;
+  static bool attr_set = false;
+  if (!attr_set) {
+    cudaError_t e = cudaFuncSetAttribute(convnext_mlp_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, mlp::kSmemBytes);
+    if (e != cudaSuccess) return (int)e;
+    attr_set = true;
+  }
+  const long long tiles = (num_rows + kTileM - 1) / kTileM;
+  const int grid = (int)(tiles < (long long)num_sms_tc() ? tiles : (long long)num_sms_tc());
+  convnext_mlp_tc_kernel<<<grid, kThreads, mlp::kSmemBytes, (cudaStream_t)stream>>>(
+      (const uint8_t*)y_img, (const uint8_t*)w_img, b1, b2, layer_scale, (long long)num_rows, h);
+  CUDA_LAUNCH_CHECK();
+  return ARREAU_OK;
+}
+
+extern "C" int arreau_edge_kernels_bf16(const double* dir, const double* dist, const double* lattice,
+                                        const int32_t* crystal_of_atom, const int32_t* src, const int32_t* num_edges_ptr,
+                                        int64_t edge_capacity, const float* ori, const void* w1_img, const void* w_img,
+                                        const float* b2, double radius, void* kernels_bf16, void* stream) {
+  if (edge_capacity == 0) return ARREAU_OK;
+  if (!dir || !dist || !lattice || !crystal_of_atom || !src || !num_edges_ptr || !ori || !w1_img || !w_img || !b2 ||
+      !kernels_bf16)
+    return ARREAU_ERR_NULL;
+  if (edge_capacity < 0) return ARREAU_ERR_BAD_SHAPE;
+  static bool attr_set = false;
+  if (!attr_set) {
+    cudaError_t e = cudaFuncSetAttribute(edge_kernels_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, edge::kSmemBytes);
+    if (e != cudaSuccess) return (int)e;
+    attr_set = true;
+  }
+  const long long tiles = (edge_capacity + edge::kEdgesPerTile - 1) / edge::kEdgesPerTile;
+  const int grid = (int)(tiles < (long long)num_sms_tc() ? tiles : (long long)num_sms_tc());
+  edge_kernels_tc_kernel<<<grid, kThreads, edge::kSmemBytes, (cudaStream_t)stream>>>(
+      dir, dist, lattice, crystal_of_atom, src, num_edges_ptr, (long long)edge_capacity, ori, (const uint8_t*)w1_img,
+      (const uint8_t*)w_img, b2, radius, (__nv_bfloat16*)kernels_bf16);
+  CUDA_LAUNCH_CHECK();
+  return ARREAU_OK;
 }

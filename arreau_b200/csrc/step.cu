@@ -113,8 +113,7 @@ extern "C" int arreau_ponita_forward(const arreau_weights* w, const arreau_works
   const int32_t* num_edges_ptr = row_ptr + N;
   if (bf16)
     ARREAU_TRY(arreau_edge_kernels_bf16(dir, dist, lattice, crystal_of_atom, src, num_edges_ptr, ws->edge_capacity,
-                                        w->ori, w->w1m_bf16, w->w2_bf16, w->b2, w->wk_bf16, radius, ws->kernels,
-                                        stream));
+                                        w->ori, w->edge_w1_img, w->edge_w_img, w->b2, radius, ws->kernels, stream));
   else
     ARREAU_TRY(arreau_edge_kernels_f32(dir, dist, lattice, crystal_of_atom, src, num_edges_ptr, ws->edge_capacity,
                                        w->ori, w->w1m_t, w->w2_t, w->b2, w->wk_t, radius, (float*)ws->kernels,
@@ -128,10 +127,9 @@ extern "C" int arreau_ponita_forward(const arreau_weights* w, const arreau_works
                                          ws->x1_debug ? ws->x1_debug + l * node_elems : nullptr,
                                          ws->x2_debug ? ws->x2_debug + l * node_elems : nullptr, stream));
     if (bf16)
-      ARREAU_TRY(arreau_convnext_mlp_bf16(ws->y, (const uint16_t*)w->mlp_w1_bf16 + (size_t)l * kW * kC,
-                                          w->mlp_b1 + l * kW, (const uint16_t*)w->mlp_w2_bf16 + (size_t)l * kC * kW,
-                                          w->mlp_b2 + l * kC, w->layer_scale + l * kC, (int64_t)N * kO, ws->h,
-                                          stream));
+      ARREAU_TRY(arreau_convnext_mlp_bf16(ws->y, (const uint8_t*)w->mlp_w_img + (size_t)l * 8 * 32768,
+                                          w->mlp_b1 + l * kW, w->mlp_b2 + l * kC, w->layer_scale + l * kC,
+                                          (int64_t)N * kO, ws->h, stream));
     else
       ARREAU_TRY(arreau_convnext_mlp_f32((const float*)ws->y, w->mlp_w1_t + (size_t)l * kC * kW, w->mlp_b1 + l * kW,
                                          w->mlp_w2_t + (size_t)l * kW * kC, w->mlp_b2 + l * kC,

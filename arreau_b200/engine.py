@@ -77,8 +77,10 @@ class DenoiseEngine:
         self.x, self.vec = f32(N, self.F), f32(N, 4, 3)
         self.logits, self.score, self.len0 = f32(N, Z), f32(N, 3), f32(G, 3)
         self.h, self.acc = f32(N, NUM_ORI, HIDDEN), f32(N, Z + 6)
-        self.y = torch.zeros(N, NUM_ORI, HIDDEN, device=dev,
-                             dtype=torch.bfloat16 if precision == "bf16" else torch.float32)
+        if precision == "bf16":     # 128-row UMMA tile images (32 KB each), see arreau_message_fiber_norm
+            self.y = torch.zeros(((N * NUM_ORI + 127) // 128) * 128 * HIDDEN, device=dev, dtype=torch.bfloat16)
+        else:
+            self.y = torch.zeros(N, NUM_ORI, HIDDEN, device=dev, dtype=torch.float32)
         self.t_of_atom = i32(N)
         # noise
         self.z_len, self.z_frac, self.u_type = f64(G, 3), f64(N, 3), f64(N, Z)
@@ -279,7 +281,7 @@ class DenoiseEngine:
             add("edge_kernels", lambda: _lib.call(
                 "arreau_edge_kernels_bf16", self.dir.data_ptr(), self.dist.data_ptr(), self.lattice.data_ptr(),
                 self.crystal_of_atom.data_ptr(), self.src.data_ptr(), nep, self.edge_capacity, w["ori"].data_ptr(),
-                w["w1m_bf16"].data_ptr(), w["w2_bf16"].data_ptr(), w["b2"].data_ptr(), w["wk_bf16"].data_ptr(),
+                w["edge_w1_img"].data_ptr(), w["edge_w_img"].data_ptr(), w["b2"].data_ptr(),
                 self.radius, self.kernels.data_ptr(), self.stream))
         else:
             add("edge_kernels", lambda: _lib.call(
@@ -295,8 +297,8 @@ class DenoiseEngine:
                 self.y.data_ptr(), int(bf16), None, None, self.stream))
             if bf16:
                 add("convnext_mlp", lambda l=l: _lib.call(
-                    "arreau_convnext_mlp_bf16", self.y.data_ptr(), w["mlp_w1_bf16"][l].data_ptr(),
-                    w["mlp_b1"][l].data_ptr(), w["mlp_w2_bf16"][l].data_ptr(), w["mlp_b2"][l].data_ptr(),
+                    "arreau_convnext_mlp_bf16", self.y.data_ptr(), w["mlp_w_img"].data_ptr() + l * 8 * 32768,
+                    w["mlp_b1"][l].data_ptr(), w["mlp_b2"][l].data_ptr(),
                     w["layer_scale"][l].data_ptr(), self.N * NUM_ORI, self.h.data_ptr(), self.stream))
             else:
                 add("convnext_mlp", lambda l=l: _lib.call(

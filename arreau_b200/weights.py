@@ -48,6 +48,19 @@ def monomial_fold_table(num_in: int = 6, degree: int = 3) -> np.ndarray:
     return np.asarray(table, dtype=np.int64)   # [258]
 
 
+def umma_tile_image(w: np.ndarray) -> torch.Tensor:
+    """[rows, K] fp weights (rows = the UMMA N index, K a multiple of 64) -> the bf16 shared-memory image the
+    tcgen05 kernels expect (csrc/tc_common.cuh): K slabs of 64 back to back, each `rows` rows of 128 bytes with
+    the 16-byte chunk c of row r stored at chunk position c ^ (r & 7).  Returned as a flat int16 CPU tensor."""
+    rows, K = w.shape
+    assert K % 64 == 0 and rows % 8 == 0
+    bits = torch.as_tensor(np.ascontiguousarray(w), dtype=torch.float32).to(torch.bfloat16).view(torch.int16).numpy()
+    t = bits.reshape(rows, K // 64, 8, 8).transpose(1, 0, 2, 3)          # [slab, row, chunk, 8]
+    pos = np.arange(8)[None, :] ^ (np.arange(rows)[:, None] & 7)          # out[.., r, p] = in[.., r, p ^ (r & 7)]
+    out = np.take_along_axis(t, pos[None, :, :, None], axis=2)
+    return torch.as_tensor(np.ascontiguousarray(out).reshape(-1))
+
+
 def _np(v) -> np.ndarray:
     if isinstance(v, torch.Tensor):
         return v.detach().cpu().double().numpy()
@@ -108,10 +121,21 @@ class PonitaWeights:
                   fw2.data_ptr(), fb2.data_ptr(), fwf.data_ptr(), self.t["fiber_kernel"].data_ptr(), stream)
         torch.cuda.current_stream(self.device).synchronize()
         if with_bf16:
-            bf = lambda a: torch.as_tensor(np.ascontiguousarray(a), dtype=torch.float32).to(self.device).to(torch.bfloat16)  # noqa: E731
-            self.t.update(w1m_bf16=bf(w1m_t.T), w2_bf16=bf(sd["basis_fn.3.weight"]),
-                          wk_bf16=bf(wk.reshape(L * HIDDEN, BASIS)), mlp_w1_bf16=bf(lay("linear_1.weight")),
-                          mlp_w2_bf16=bf(lay("linear_2.weight")))
+            # tcgen05 path: every weight tile as a ready-to-copy UMMA shared-memory image
+            w1pad = np.zeros((HIDDEN, 128))
+            w1pad[:, :MONO_PAD] = w1m_t.T                                  # [N = hidden, K = 96 -> 128]
+            w2 = sd["basis_fn.3.weight"]                                   # [D, C]
+            chunks = [umma_tile_image(w2[nh * 128:(nh + 1) * 128, ks * 64:(ks + 1) * 64])
+                      for nh in range(2) for ks in range(2)]
+            chunks += [umma_tile_image(wk[l][:, ks * 64:(ks + 1) * 64]) for l in range(L) for ks in range(4)]
+            m1, m2 = lay("linear_1.weight"), lay("linear_2.weight")        # [L,4C,C], [L,C,4C]
+            mlp = []
+            for l in range(L):
+                g1 = [umma_tile_image(m1[l][j * 128:(j + 1) * 128, :]) for j in range(4)]
+                g2 = [umma_tile_image(m2[l][:, j * 128:(j + 1) * 128]) for j in range(4)]
+                mlp += [g1[0], g1[1], g2[0], g1[2], g2[1], g1[3], g2[2], g2[3]]   # MMA issue order
+            self.t.update(edge_w1_img=umma_tile_image(w1pad).to(self.device),
+                          edge_w_img=torch.cat(chunks).to(self.device), mlp_w_img=torch.cat(mlp).to(self.device))
         self.c = _lib.Weights()
         for name, _ in _lib.Weights._fields_:
             if name in self.t:
