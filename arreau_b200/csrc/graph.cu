@@ -251,14 +251,35 @@ graph_fill_kernel(const double* __restrict__ pos, const double* __restrict__ lat
   double* sd2 = s_d2[warp];
   int* sc = s_c[warp];
   int m = 0;
+  // Once the buffer has been cut down to the `cap` nearest seen so far, anything not strictly before the
+  // current cap-th entry in (d2, candidate) order can never be selected: reject it before it is buffered.
+  // In dense cells (sampler start: ~1 A cells, ~1000 in-range candidates per atom) this keeps the number of
+  // O(m^2) selection passes at O(log) instead of one per 224 candidates.
+  double thr_d2 = INFINITY;
+  int thr_c = 0x7fffffff;
   for (int c0 = 0; c0 < total; c0 += 32) {
-    if (m + 32 > kSelBuf) m = select_topk(sd2, sc, s_mask[warp], m, cap, lane);
+    if (m + 32 > kSelBuf) {
+      m = select_topk(sd2, sc, s_mask[warp], m, cap, lane);
+      // threshold = the largest kept key
+      double kd = -INFINITY;
+      int kc = -1;
+      for (int a = lane; a < m; a += 32)
+        if (sd2[a] > kd || (sd2[a] == kd && sc[a] > kc)) { kd = sd2[a]; kc = sc[a]; }
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) {
+        const double od = __shfl_xor_sync(0xffffffffu, kd, o);
+        const int oc = __shfl_xor_sync(0xffffffffu, kc, o);
+        if (od > kd || (od == kd && oc > kc)) { kd = od; kc = oc; }
+      }
+      thr_d2 = kd;
+      thr_c = kc;
+    }
     const int c = c0 + lane;
     double dx, dy, dz, d2 = 0;
     bool ok = false;
     if (c < total) {
       d2 = cand_d2(ctx, pos, start, c, pix, piy, piz, dx, dy, dz);
-      ok = cand_pass(d2, r2, remove_self);
+      ok = cand_pass(d2, r2, remove_self) && (d2 < thr_d2 || (d2 == thr_d2 && c < thr_c));
     }
     const unsigned bal = __ballot_sync(0xffffffffu, ok);
     if (ok) {

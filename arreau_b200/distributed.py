@@ -1,0 +1,50 @@
+"""Box-level sharding of independent crystals: one process per GPU, contiguous blocks of crystals
+per rank, whole trajectories per GPU, and ONE collective at the end (gather of the sampled crystals).  There is
+no per-step communication: graph edges never cross crystals (diffusion_helpers.py:350-383)."""
+from __future__ import annotations
+
+from typing import List, Optional, Tuple
+
+import numpy as np
+import torch
+import torch.distributed as dist
+
+from .diffusion.diffusion_loss import SampleResult
+
+
+def shard_range(num_crystals: int, rank: int, world: int) -> Tuple[int, int]:
+    """Contiguous [lo, hi) block of crystals owned by `rank`; sizes differ by at most one."""
+    base, rem = divmod(num_crystals, world)
+    lo = rank * base + min(rank, rem)
+    return lo, lo + base + (1 if rank < rem else 0)
+
+
+def gather_sample_results(local: SampleResult, group=None, device: Optional[torch.device] = None) -> SampleResult:
+    """All-gather the per-rank SampleResult (ragged in atoms) into the global one, rank-major = crystal order.
+    Uses the group's backend (NCCL on the GPUs, gloo in the CPU tests); counts first, then padded payloads."""
+    if not dist.is_initialized() or dist.get_world_size(group) == 1:
+        return local
+    world = dist.get_world_size(group)
+    dev = device if device is not None else torch.device("cpu")
+    n_atoms = torch.tensor([local.frac_x.shape[0], local.num_atoms.shape[0]], dtype=torch.int64, device=dev)
+    counts = [torch.zeros_like(n_atoms) for _ in range(world)]
+    dist.all_gather(counts, n_atoms, group=group)
+    counts = torch.stack(counts).cpu().numpy()
+    max_n, max_g = int(counts[:, 0].max()), int(counts[:, 1].max())
+
+    def gather(arr: np.ndarray, rows: int, dtype) -> List[np.ndarray]:
+        t = torch.zeros((rows,) + arr.shape[1:], dtype=dtype, device=dev)
+        t[: arr.shape[0]] = torch.as_tensor(arr, dtype=dtype)
+        outs = [torch.empty_like(t) for _ in range(world)]
+        dist.all_gather(outs, t, group=group)
+        return [o.cpu().numpy() for o in outs]
+
+    frac = gather(local.frac_x, max_n, torch.float64)
+    zs = gather(local.atomic_numbers, max_n, torch.int64)
+    lat = gather(local.lattice, max_g, torch.float64)
+    na = gather(local.num_atoms, max_g, torch.int64)
+    cat = lambda parts, col: np.concatenate([p[: int(counts[r, col])] for r, p in enumerate(parts)])  # noqa: E731
+    num_atoms = cat(na, 1)
+    idx_start = np.concatenate([[0], np.cumsum(num_atoms)[:-1]]) if num_atoms.size else num_atoms
+    return SampleResult(frac_x=cat(frac, 0), atomic_numbers=cat(zs, 0), lattice=cat(lat, 1), idx_start=idx_start,
+                        num_atoms=num_atoms)

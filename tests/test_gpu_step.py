@@ -59,7 +59,7 @@ def test_reference_sample_T11_teacher_forced(device, gold, weights_npz):
     from arreau_b200.weights import PonitaWeights
     s = gold("sample_T11.npz")
     n_per, G = int(s["n_per"]), int(s["num_crystals"])
-    sd = {k: weights_npz[k] for k in weights_npz.files if k not in ("ori_grid", "fourier_w")}
+    sd = {k: weights_npz[k].astype(np.float64) for k in weights_npz.files if k not in ("ori_grid", "fourier_w")}
     w = PonitaWeights(calibrate_length_readout(sd, n_per), weights_npz["ori_grid"], device=device)
     eng = DenoiseEngine(w, build_tables(11, 90), weights_npz["fourier_w"], [n_per] * G, 5.0, 8, device=device)
     steps = s["step_frac"].shape[0]

@@ -1,0 +1,154 @@
+"""Host-side logic and the C-ABI boundary, without a GPU: the library loads and exports every symbol the
+public header declares, argument validation returns the documented error codes, and the host tables / weight
+packing agree with the oracle."""
+import ctypes as C
+import os
+import re
+
+import numpy as np
+import pytest
+import torch
+
+from conftest import ROOT, f64_default
+
+HEADER = os.path.join(ROOT, "include", "arreau_b200.h")
+
+
+def _declared_symbols():
+    text = open(HEADER).read()
+    text = re.sub(r"/\*.*?\*/", "", text, flags=re.S)
+    return sorted(set(re.findall(r"\b(?:int|int64_t)\s+(arreau_\w+)\s*\(", text)))
+
+
+def test_library_exports_every_declared_symbol():
+    from arreau_b200 import _lib
+    lib = _lib.load()
+    names = _declared_symbols()
+    assert len(names) >= 24
+    for n in names:
+        assert hasattr(lib, n), n
+        assert n in _lib.SIGNATURES, f"{n} has no ctypes signature"
+    assert sorted(_lib.SIGNATURES) == names            # and nothing undeclared is bound
+    assert lib.arreau_abi_version() == 1
+    dims = [C.c_int() for _ in range(5)]
+    assert lib.arreau_model_dims(*[C.byref(d) for d in dims]) == 0
+    assert [d.value for d in dims] == [16, 128, 256, 4, 5]
+
+
+def test_argument_validation_error_codes():
+    """Bad arguments are rejected before anything is launched (no GPU needed): negative codes, no exceptions."""
+    from arreau_b200 import _lib
+    lib = _lib.load()
+    assert lib.arreau_graph_scan(None, None, 4, None) == -4                       # ARREAU_ERR_NULL
+    assert lib.arreau_lattice_from_params(None, None, 3, None, None) == -4
+    assert lib.arreau_lattice_from_params(None, None, 0, None, None) == 0          # empty input is a no-op
+    assert lib.arreau_frac_to_cart(None, None, None, 0, None, None) == 0
+    buf = (C.c_double * 16)()
+    p = C.cast(buf, C.c_void_p)
+    assert lib.arreau_lattice_from_params(p, p, -1, p, None) == -1                # ARREAU_ERR_BAD_SHAPE
+    assert lib.arreau_graph_count(p, p, p, p, 4, 1, 25.0, 100000, 1, p, p, p, None) == -2   # cap unsupported
+    assert lib.arreau_d3pm_reverse(p, p, p, None, 5, p, p, 0.98, 0.02, 1000, 4, 500, p, None) == -1   # Z > 128
+    with pytest.raises(RuntimeError, match="ARREAU_ERR_NULL"):
+        _lib.call("arreau_graph_scan", None, None, 4, None)
+    assert lib.arreau_ponita_forward(None, None, 0, *([None] * 9), 4, 1, 5.0, None, None, None, None) == -4
+
+
+def test_struct_layouts_match_header():
+    """ctypes mirrors of the three argument structs have the field order of the header."""
+    from arreau_b200 import _lib
+    text = open(HEADER).read()
+    for cname, cls in (("arreau_weights", _lib.Weights), ("arreau_workspace", _lib.Workspace), ("arreau_step_args", _lib.StepArgs)):
+        body = text[text.index("typedef struct " + cname):]
+        body = body[:body.index("} " + cname)]
+        body = re.sub(r"/\*.*?\*/", "", body, flags=re.S)
+        fields = []
+        for decl in body.split("{", 1)[1].split(";"):
+            decl = decl.strip()
+            if not decl:
+                continue
+            parts = decl.split(",")
+            fields.append(re.findall(r"(\w+)\s*$", parts[0])[0])
+            fields += [re.findall(r"(\w+)\s*$", p)[0] for p in parts[1:]]
+        assert fields == [f[0] for f in cls._fields_], cname
+
+
+def test_tables_match_golden(gold):
+    from arreau_b200.tables import build_tables
+    k = gold("kat.npz")
+    t = build_tables(1000, 90)
+    assert np.array_equal(t.ve_sigmas.numpy(), k["ve_sigmas"]) and np.array_equal(t.vp_betas.numpy(), k["vp_betas"])
+    assert np.array_equal(t.vp_alpha_bars.numpy(), k["vp_alpha_bars"]) and np.array_equal(t.vp_sigmas.numpy(), k["vp_sigmas"])
+    assert np.array_equal(t.q_keep.numpy(), k["d3pm_keep"]) and np.array_equal(t.q_to_mask.numpy(), k["d3pm_to_mask"])
+    assert (t.onestep_keep, t.onestep_to_mask) == (0.98, 0.02)
+    assert torch.get_default_dtype() == torch.float32          # the builder restores the caller's default dtype
+    # reverse_given_x0 coefficients against the oracle's formula at a few timesteps
+    from oracle import restatement as R
+    with f64_default():
+        tabs = R.DiffusionTables.build(1000, 90)
+        xt, x0, z = torch.rand(4, 3) + 5, torch.rand(4, 3) + 5, torch.randn(4, 3)
+        for ts in (999, 500, 2, 1):
+            ref = R.vp_lattice_reverse_given_x0(tabs, xt, x0, torch.tensor([ts]), z)
+            mine = (t.vp_cx0[ts] * x0 + t.vp_cxt[ts] * xt) / t.vp_denom[ts] + t.vp_var[ts] * (z if ts > 1 else 0 * z)
+            assert torch.equal(ref, mine), ts
+
+
+def test_monomial_fold_is_exact():
+    """W1 . PolynomialFeatures(3)(v) == W1m . monomials83(v): the fold only merges equal monomials."""
+    from arreau_b200.weights import monomial_fold_table
+    from oracle import restatement as R
+    fold = monomial_fold_table()
+    assert fold.shape == (258,) and fold.max() == 82 and len(set(fold.tolist())) == 83
+    g = torch.Generator().manual_seed(0)
+    with f64_default():
+        v = torch.randn(7, 6, generator=g, dtype=torch.float64)
+        W = torch.randn(11, 258, generator=g, dtype=torch.float64)
+        poly = R.polynomial_features(v, 3)
+        mono = torch.zeros(7, 83, dtype=torch.float64)
+        mono[:, torch.as_tensor(fold)] = poly                  # equal monomials carry equal values
+        Wm = torch.zeros(11, 83, dtype=torch.float64).index_add_(1, torch.as_tensor(fold), W)
+        assert torch.allclose(poly @ W.T, mono @ Wm.T, rtol=1e-12, atol=1e-12)
+    # order used by the kernels: singles, pairs i<=j, triples i<=j<=k
+    assert fold[:6].tolist() == list(range(6)) and fold[6] == 6 and fold[6 + 1] == 7 and fold[6 + 6] == 7
+
+
+def test_umma_tile_image_layout():
+    """16-byte chunk c of row r lands at chunk c ^ (r & 7) of the row's 128 bytes, K slabs back to back."""
+    from arreau_b200.weights import umma_tile_image
+    rows, K = 16, 128
+    w = np.arange(rows * K, dtype=np.float32).reshape(rows, K) % 251        # bf16-exact small integers
+    img = umma_tile_image(w).view(torch.bfloat16).float().numpy().reshape(K // 64, rows, 8, 8)
+    for r in (0, 1, 7, 9, 15):
+        for k in (0, 8, 63, 64, 127):
+            slab, c, e = k // 64, (k % 64) // 8, k % 8
+            assert img[slab, r, c ^ (r & 7), e] == w[r, k]
+
+
+def test_angle_factors_reproduce_reference_lattice(gold):
+    from arreau_b200.engine import angle_factors
+    k = gold("kat.npz")
+    f = angle_factors(torch.as_tensor(k["lat_angles"]))
+    a, b, c = torch.as_tensor(k["lat_lengths"]).unbind(-1)
+    lat = torch.zeros(3, 3, 3, dtype=torch.float64)
+    lat[:, 0, 0], lat[:, 0, 2] = a * f[:, 0], a * f[:, 1]
+    lat[:, 1, 0], lat[:, 1, 1], lat[:, 1, 2] = -b * f[:, 2] * f[:, 3], b * f[:, 2] * f[:, 4], b * f[:, 5]
+    lat[:, 2, 2] = c
+    assert np.array_equal(lat.numpy(), k["lat_matrix"])       # bit identical: same torch ops, same order
+
+
+def test_synthetic_crystals_are_deterministic():
+    from arreau_b200.synthetic import CONFIGS, make_crystals
+    a, b = make_crystals(16, 2, 20, seed=0), make_crystals(16, 2, 20, seed=0)
+    assert np.array_equal(a.frac, b.frac) and np.array_equal(a.num_atoms, b.num_atoms)
+    assert 2 <= a.num_atoms.min() and a.num_atoms.max() <= 20 and a.total_atoms == a.frac.shape[0]
+    vol = np.abs(np.linalg.det(np.stack([np.diag(l) for l in a.lengths])))
+    assert 10 < (vol / a.num_atoms).mean() < 30               # ~18 A^3 per atom (Alexandria density)
+    assert set(CONFIGS) >= {"C1", "C2", "C3"}
+
+
+def test_product_does_not_import_the_oracle():
+    """The oracle is test infrastructure: nothing under arreau_b200/ may import it."""
+    for dirpath, _, files in os.walk(os.path.join(ROOT, "arreau_b200")):
+        for f in files:
+            if f.endswith(".py"):
+                src = open(os.path.join(dirpath, f)).read()
+                assert not re.search(r"^\s*(from|import)\s+oracle\b", src, flags=re.M), f
