@@ -280,7 +280,7 @@ __device__ __forceinline__ float4 load_kernel4(const __nv_bfloat16* p) {
 }
 
 template <typename KT, typename YT>
-__global__ void __launch_bounds__(128)
+__global__ void __launch_bounds__(128, 6)
 message_fiber_norm_kernel(const KT* __restrict__ kern, const float* __restrict__ h, const int32_t* __restrict__ row_ptr,
                           const int32_t* __restrict__ src, const float* __restrict__ fk,
                           const float* __restrict__ bias, const float* __restrict__ ln_w,
@@ -289,6 +289,7 @@ message_fiber_norm_kernel(const KT* __restrict__ kern, const float* __restrict__
   __shared__ __align__(16) float x1s[kMsgNodes][kO][kC];
   const int tid = threadIdx.x, og = tid >> 5, cg = tid & 31;
   const int node0 = blockIdx.x * kMsgNodes;
+  // ---- phase 1: x1[node][o][c] = sum over the node's edges (fixed CSR order) of kernel * h[src] ----
 #pragma unroll 1
   for (int nb = 0; nb < kMsgNodes; ++nb) {
     const int node = node0 + nb;
@@ -297,22 +298,45 @@ message_fiber_norm_kernel(const KT* __restrict__ kern, const float* __restrict__
     for (int oo = 0; oo < 4; ++oo) a[oo] = make_float4(0.f, 0.f, 0.f, 0.f);
     if (node < N) {
       const int e0 = row_ptr[node], e1 = row_ptr[node + 1];
-      for (int e = e0; e < e1; ++e) {
-        const int s = src[e];
-        const KT* kp = kern + ((size_t)e * kO + og * 4) * kC + cg * 4;
-        const float* hp = h + ((size_t)s * kO + og * 4) * kC + cg * 4;
-        float4 kv[4], hv[4];
+      int e = e0;
+      for (; e + 1 < e1; e += 2) {       // two edges in flight: 16 independent 16-byte loads per thread
+        const int s0 = src[e], s1 = src[e + 1];
+        const KT* kp0 = kern + ((size_t)e * kO + og * 4) * kC + cg * 4;
+        const KT* kp1 = kp0 + kO * kC;
+        const float* hp0 = h + ((size_t)s0 * kO + og * 4) * kC + cg * 4;
+        const float* hp1 = h + ((size_t)s1 * kO + og * 4) * kC + cg * 4;
+        float4 k0[4], k1[4], h0[4], h1[4];
 #pragma unroll
         for (int oo = 0; oo < 4; ++oo) {
-          kv[oo] = load_kernel4(kp + oo * kC);
-          hv[oo] = *reinterpret_cast<const float4*>(hp + oo * kC);
+          k0[oo] = load_kernel4(kp0 + oo * kC);
+          k1[oo] = load_kernel4(kp1 + oo * kC);
+          h0[oo] = *reinterpret_cast<const float4*>(hp0 + oo * kC);
+          h1[oo] = *reinterpret_cast<const float4*>(hp1 + oo * kC);
         }
 #pragma unroll
+        for (int oo = 0; oo < 4; ++oo) {   // edge e then e+1: the reference order of the sum
+          a[oo].x = fmaf(k0[oo].x, h0[oo].x, a[oo].x);
+          a[oo].y = fmaf(k0[oo].y, h0[oo].y, a[oo].y);
+          a[oo].z = fmaf(k0[oo].z, h0[oo].z, a[oo].z);
+          a[oo].w = fmaf(k0[oo].w, h0[oo].w, a[oo].w);
+          a[oo].x = fmaf(k1[oo].x, h1[oo].x, a[oo].x);
+          a[oo].y = fmaf(k1[oo].y, h1[oo].y, a[oo].y);
+          a[oo].z = fmaf(k1[oo].z, h1[oo].z, a[oo].z);
+          a[oo].w = fmaf(k1[oo].w, h1[oo].w, a[oo].w);
+        }
+      }
+      if (e < e1) {
+        const int s0 = src[e];
+        const KT* kp0 = kern + ((size_t)e * kO + og * 4) * kC + cg * 4;
+        const float* hp0 = h + ((size_t)s0 * kO + og * 4) * kC + cg * 4;
+#pragma unroll
         for (int oo = 0; oo < 4; ++oo) {
-          a[oo].x = fmaf(kv[oo].x, hv[oo].x, a[oo].x);
-          a[oo].y = fmaf(kv[oo].y, hv[oo].y, a[oo].y);
-          a[oo].z = fmaf(kv[oo].z, hv[oo].z, a[oo].z);
-          a[oo].w = fmaf(kv[oo].w, hv[oo].w, a[oo].w);
+          const float4 kv = load_kernel4(kp0 + oo * kC);
+          const float4 hv = *reinterpret_cast<const float4*>(hp0 + oo * kC);
+          a[oo].x = fmaf(kv.x, hv.x, a[oo].x);
+          a[oo].y = fmaf(kv.y, hv.y, a[oo].y);
+          a[oo].z = fmaf(kv.z, hv.z, a[oo].z);
+          a[oo].w = fmaf(kv.w, hv.w, a[oo].w);
         }
       }
     }
@@ -324,60 +348,55 @@ message_fiber_norm_kernel(const KT* __restrict__ kern, const float* __restrict__
     }
   }
   __syncthreads();
-  // fiber conv: x2[nb][p = og*4+pp][c = cg*4..+3] = (1/O) sum_o x1[nb][o][c] * fk[o][p][c] + bias[c]
-  float4 x2[kMsgNodes][4];
-#pragma unroll
-  for (int nb = 0; nb < kMsgNodes; ++nb)
-#pragma unroll
-    for (int pp = 0; pp < 4; ++pp) x2[nb][pp] = make_float4(0.f, 0.f, 0.f, 0.f);
-#pragma unroll 4
-  for (int o = 0; o < kO; ++o) {
-    float4 xv[kMsgNodes];
-#pragma unroll
-    for (int nb = 0; nb < kMsgNodes; ++nb) xv[nb] = *reinterpret_cast<const float4*>(&x1s[nb][o][cg * 4]);
-#pragma unroll
-    for (int pp = 0; pp < 4; ++pp) {
-      const float4 f = __ldg(reinterpret_cast<const float4*>(fk + ((size_t)(o * kO + og * 4 + pp)) * kC + cg * 4));
-#pragma unroll
-      for (int nb = 0; nb < kMsgNodes; ++nb) {
-        x2[nb][pp].x = fmaf(xv[nb].x, f.x, x2[nb][pp].x);
-        x2[nb][pp].y = fmaf(xv[nb].y, f.y, x2[nb][pp].y);
-        x2[nb][pp].z = fmaf(xv[nb].z, f.z, x2[nb][pp].z);
-        x2[nb][pp].w = fmaf(xv[nb].w, f.w, x2[nb][pp].w);
-      }
-    }
-  }
+  // ---- phase 2: x2[nb][p][c] = (1/O) sum_o x1[nb][o][c] * fk[o][p][c] + bias[c]; LayerNorm; one output
+  // orientation p at a time so only 4 float4 accumulators are live (occupancy) ----
   const float4 bv = *reinterpret_cast<const float4*>(bias + cg * 4);
   const float4 gw = *reinterpret_cast<const float4*>(ln_w + cg * 4);
   const float4 gb = *reinterpret_cast<const float4*>(ln_b + cg * 4);
   constexpr float inv_o = 1.0f / kO;
+#pragma unroll 1
+  for (int pp = 0; pp < 4; ++pp) {
+    const int p = og * 4 + pp;
+    float4 x2[kMsgNodes];
 #pragma unroll
-  for (int nb = 0; nb < kMsgNodes; ++nb) {
-    const int node = node0 + nb;
+    for (int nb = 0; nb < kMsgNodes; ++nb) x2[nb] = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll 4
+    for (int o = 0; o < kO; ++o) {
+      const float4 f = __ldg(reinterpret_cast<const float4*>(fk + ((size_t)(o * kO + p)) * kC + cg * 4));
 #pragma unroll
-    for (int pp = 0; pp < 4; ++pp) {
-      float4 v = x2[nb][pp];
+      for (int nb = 0; nb < kMsgNodes; ++nb) {
+        const float4 xv = *reinterpret_cast<const float4*>(&x1s[nb][o][cg * 4]);
+        x2[nb].x = fmaf(xv.x, f.x, x2[nb].x);
+        x2[nb].y = fmaf(xv.y, f.y, x2[nb].y);
+        x2[nb].z = fmaf(xv.z, f.z, x2[nb].z);
+        x2[nb].w = fmaf(xv.w, f.w, x2[nb].w);
+      }
+    }
+#pragma unroll
+    for (int nb = 0; nb < kMsgNodes; ++nb) {
+      const int node = node0 + nb;
+      float4 v = x2[nb];
       v.x = v.x * inv_o + bv.x;
       v.y = v.y * inv_o + bv.y;
       v.z = v.z * inv_o + bv.z;
       v.w = v.w * inv_o + bv.w;
       if (x2_dbg && node < N)
-        *reinterpret_cast<float4*>(x2_dbg + ((size_t)node * kO + og * 4 + pp) * kC + cg * 4) = v;
+        *reinterpret_cast<float4*>(x2_dbg + ((size_t)node * kO + p) * kC + cg * 4) = v;
       // LayerNorm over the 128 channels held by this warp (biased variance, eps 1e-5)
       const float mean = warp_sum((v.x + v.y) + (v.z + v.w)) * (1.0f / kC);
       const float dx = v.x - mean, dy = v.y - mean, dz = v.z - mean, dw = v.w - mean;
       const float var = warp_sum((dx * dx + dy * dy) + (dz * dz + dw * dw)) * (1.0f / kC);
       const float rstd = 1.0f / sqrtf(var + 1e-5f);
-      float4 r = make_float4(dx * rstd * gw.x + gb.x, dy * rstd * gw.y + gb.y, dz * rstd * gw.z + gb.z,
-                             dw * rstd * gw.w + gb.w);
+      const float4 r = make_float4(dx * rstd * gw.x + gb.x, dy * rstd * gw.y + gb.y, dz * rstd * gw.z + gb.z,
+                                   dw * rstd * gw.w + gb.w);
       if (node < N) {
         if constexpr (sizeof(YT) == 4) {
-          *reinterpret_cast<float4*>(y + ((size_t)node * kO + og * 4 + pp) * kC + cg * 4) = r;
+          *reinterpret_cast<float4*>(y + ((size_t)node * kO + p) * kC + cg * 4) = r;
         } else {
           // bf16 y goes straight into the UMMA operand image of the ConvNext MLP kernel: 128-row tiles of
           // 32 KB, two 64-channel slabs of 128-byte rows, 16-byte chunks XOR-swizzled by (row & 7)
           // (csrc/tc_common.cuh), so that kernel fetches a tile with one bulk copy.
-          const size_t row = (size_t)node * kO + og * 4 + pp;
+          const size_t row = (size_t)node * kO + p;
           const int rr = (int)(row & 127), c0 = cg * 4;
           uint8_t* tile = reinterpret_cast<uint8_t*>(y) + (row >> 7) * 32768;
           const int off = (c0 >> 6) * 16384 + rr * 128 + (((((c0 & 63) >> 3) ^ (rr & 7)) << 4) | ((c0 & 7) << 1));
@@ -466,47 +485,72 @@ convnext_mlp_simt_kernel(const float* __restrict__ y, const float* __restrict__ 
 //   mean_o (Wr h[b,o] + br) = Wr (mean_o h[b,o]) + br.
 // acc[N][Z+6] = [logits (Z) | score vector (3) | length channels (3)], summed over layers.
 // ------------------------------------------------------------------------------------------------
+constexpr int kReadoutNodes = 8;
+
 __global__ void __launch_bounds__(kC)
 readout_accumulate_kernel(const float* __restrict__ h, const float* __restrict__ wr_t, const float* __restrict__ br,
                           const float* __restrict__ ori, int N, int Z, int first_layer, float* __restrict__ acc) {
-  __shared__ float hbar[kC];
-  __shared__ float part[4][kO];
-  __shared__ float s_o[kO];
-  const int b = blockIdx.x, c = threadIdx.x, lane = c & 31, warp = c >> 5;
+  __shared__ __align__(16) float hbar[kReadoutNodes][kC];   // mean over orientations
+  __shared__ float s_o[kReadoutNodes][kO];                  // vector-channel read-out per orientation
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int R = Z + 4;   // read-out rows: Z scalars, 1 vector channel, 3 global scalars (ponita.py:111)
-  const float* hp = h + (size_t)b * kO * kC + c;
-  const float wv = wr_t[(size_t)c * R + Z];
-  float sum = 0.f;
-  float p[kO];
+  const int b0 = blockIdx.x * kReadoutNodes;
+  // phase A: one warp per atom (two atoms per warp), lane = 4 channels
+  float4 wv;
+  wv.x = wr_t[(size_t)(lane * 4 + 0) * R + Z];
+  wv.y = wr_t[(size_t)(lane * 4 + 1) * R + Z];
+  wv.z = wr_t[(size_t)(lane * 4 + 2) * R + Z];
+  wv.w = wr_t[(size_t)(lane * 4 + 3) * R + Z];
+  const float bz = br[Z];
 #pragma unroll
-  for (int o = 0; o < kO; ++o) {
-    const float v = hp[o * kC];
-    sum += v;
-    p[o] = v * wv;
-  }
-  hbar[c] = sum * (1.0f / kO);
+  for (int rep = 0; rep < kReadoutNodes / 4; ++rep) {
+    const int a = warp + 4 * rep, b = b0 + a;
+    float4 sum = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (b < N) {
+      const float* hp = h + (size_t)b * kO * kC + lane * 4;
+      float4 hv[kO];
 #pragma unroll
-  for (int o = 0; o < kO; ++o) {
-    const float r = warp_sum(p[o]);
-    if (lane == 0) part[warp][o] = r;
+      for (int o = 0; o < kO; ++o) hv[o] = *reinterpret_cast<const float4*>(hp + o * kC);
+#pragma unroll
+      for (int o = 0; o < kO; ++o) {
+        sum.x += hv[o].x; sum.y += hv[o].y; sum.z += hv[o].z; sum.w += hv[o].w;
+        const float d = warp_sum((hv[o].x * wv.x + hv[o].y * wv.y) + (hv[o].z * wv.z + hv[o].w * wv.w));
+        if (lane == o) s_o[a][o] = d + bz;
+      }
+    }
+    constexpr float inv = 1.0f / kO;
+    *reinterpret_cast<float4*>(&hbar[a][lane * 4]) = make_float4(sum.x * inv, sum.y * inv, sum.z * inv, sum.w * inv);
   }
   __syncthreads();
-  if (c < kO) s_o[c] = ((part[0][c] + part[1][c]) + (part[2][c] + part[3][c])) + br[Z];
-  __syncthreads();
-  float* ab = acc + (size_t)b * (Z + 6);
-  for (int z = c; z < R; z += kC) {
-    if (z == Z) continue;
-    float s = br[z];
-    for (int k = 0; k < kC; ++k) s = fmaf(wr_t[(size_t)k * R + z], hbar[k], s);
+  // phase B: thread z owns read-out row z for the CTA's atoms (each weight load is reused for all of them)
+  if (tid < R && tid != Z) {
+    const int z = tid;
+    float r[kReadoutNodes];
+    const float bb = br[z];
+#pragma unroll
+    for (int a = 0; a < kReadoutNodes; ++a) r[a] = bb;
+    for (int k = 0; k < kC; ++k) {
+      const float w = wr_t[(size_t)k * R + z];
+#pragma unroll
+      for (int a = 0; a < kReadoutNodes; ++a) r[a] = fmaf(w, hbar[a][k], r[a]);
+    }
     const int slot = z < Z ? z : (Z + 3 + (z - Z - 1));
-    ab[slot] = first_layer ? s : ab[slot] + s;
-  }
-  if (c < 3) {
-    float s = 0.f;
 #pragma unroll
-    for (int o = 0; o < kO; ++o) s = fmaf(s_o[o], ori[3 * o + c], s);   // to_from_sphere.py:10-11
-    s *= (1.0f / kO);
-    ab[Z + c] = first_layer ? s : ab[Z + c] + s;
+    for (int a = 0; a < kReadoutNodes; ++a)
+      if (b0 + a < N) {
+        float* p = acc + (size_t)(b0 + a) * (Z + 6) + slot;
+        *p = first_layer ? r[a] : *p + r[a];
+      }
+  } else if (tid >= R && tid < R + 3 * kReadoutNodes && tid - R < 3 * kReadoutNodes) {
+    const int a = (tid - R) / 3, d = (tid - R) % 3;
+    if (b0 + a < N) {
+      float sacc = 0.f;
+#pragma unroll
+      for (int o = 0; o < kO; ++o) sacc = fmaf(s_o[a][o], ori[3 * o + d], sacc);   // to_from_sphere.py:10-11
+      sacc *= (1.0f / kO);
+      float* p = acc + (size_t)(b0 + a) * (Z + 6) + Z + d;
+      *p = first_layer ? sacc : *p + sacc;
+    }
   }
 }
 
@@ -645,7 +689,9 @@ extern "C" int arreau_readout_accumulate(const float* h, const float* wr_t, cons
   if (N == 0) return ARREAU_OK;
   if (!h || !wr_t || !br || !ori || !acc) return ARREAU_ERR_NULL;
   if (N < 0 || Z <= 0) return ARREAU_ERR_BAD_SHAPE;
-  readout_accumulate_kernel<<<N, kC, 0, (cudaStream_t)stream>>>(h, wr_t, br, ori, N, Z, first_layer, acc);
+  if (Z + 4 + 3 * kReadoutNodes > kC) return ARREAU_ERR_UNSUPPORTED;
+  readout_accumulate_kernel<<<(N + kReadoutNodes - 1) / kReadoutNodes, kC, 0, (cudaStream_t)stream>>>(h, wr_t, br, ori, N,
+                                                                                                    Z, first_layer, acc);
   CUDA_LAUNCH_CHECK();
   return ARREAU_OK;
 }

@@ -3,13 +3,13 @@
 //   convnext_mlp_tc_kernel   K6   h += layer_scale * (W2 gelu(W1 y + b1) + b2)          convnext.py:26-32
 //   edge_kernels_tc_kernel   K3+K4a invariants -> monomials -> basis MLP -> window -> 5 kernel projections
 //
-// Both are persistent (one CTA per SM, 128-row tiles) and warp specialised:
+// Both are persistent (one CTA per SM, 128-row tiles) and warp specialised (640 threads):
 //   warp 0   producer: cp.async.bulk (TMA engine) of pre-swizzled weight / activation tiles into an mbarrier ring
 //   warp 1   MMA issuer: one thread issues tcgen05.mma (M = 128, N = 128, K = 16) and tcgen05.commit
 //   warp 2   TMEM allocation / release
-//   warps 4..11  epilogue: tcgen05.ld -> bias / GELU / window in registers -> bf16 operand tile of the next GEMM
-//                written back to shared memory in the UMMA layout (the intermediate never leaves the SM), or the
-//                final result to HBM.
+//   warps 4..19  epilogue (16 warps: 4 per TMEM lane quarter, each a quarter of the columns): tcgen05.ld ->
+//                bias / GELU / window in registers -> bf16 operand tile of the next GEMM written back to shared
+//                memory in the UMMA layout (the intermediate never leaves the SM), or the final result to HBM.
 #include "common.cuh"
 #include "tc_common.cuh"
 
@@ -17,9 +17,10 @@ namespace {
 
 using namespace tc;
 
-constexpr int kThreads = 384;
+constexpr int kThreads = 640;
 constexpr int kEpiWarp0 = 4;
-constexpr int kEpiWarps = 8;
+constexpr int kEpiWarps = 16;
+constexpr int kEpiThreads = kEpiWarps * 32;
 constexpr int kTileM = 128;
 constexpr uint32_t kIdesc128 = umma_idesc_bf16(128, 128);
 
@@ -32,13 +33,44 @@ __device__ __forceinline__ void mma_slab(uint32_t tmem_d, uint32_t a_slab, uint3
   }
 }
 
+// 32 accumulator columns -> (+ bias) -> GELU (* scale) -> bf16 -> the four 16-byte chunks chunk0..chunk0+3 of
+// operand row m (row base pointer `row`, chunk positions XOR-swizzled by the row index)
+template <bool kBias, bool kScale>
+__device__ __forceinline__ void gelu_store32(const float (&v)[32], const float* __restrict__ bias_s, float scale,
+                                             uint8_t* row, int chunk0, int m) {
+#pragma unroll
+  for (int cc = 0; cc < 4; ++cc) {
+    float x[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) x[i] = v[cc * 8 + i];
+    if constexpr (kBias) {
+      const float4 b0 = *reinterpret_cast<const float4*>(bias_s + cc * 8);       // warp-uniform: smem broadcast
+      const float4 b1 = *reinterpret_cast<const float4*>(bias_s + cc * 8 + 4);
+      x[0] += b0.x; x[1] += b0.y; x[2] += b0.z; x[3] += b0.w;
+      x[4] += b1.x; x[5] += b1.y; x[6] += b1.z; x[7] += b1.w;
+    }
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      x[i] = gelu_fast(x[i]);
+      if constexpr (kScale) x[i] *= scale;
+    }
+    uint4 pk;
+    pk.x = pack_bf16(x[0], x[1]);
+    pk.y = pack_bf16(x[2], x[3]);
+    pk.z = pack_bf16(x[4], x[5]);
+    pk.w = pack_bf16(x[6], x[7]);
+    *reinterpret_cast<uint4*>(row + (((chunk0 + cc) ^ (m & 7)) << 4)) = pk;
+  }
+}
+
 // =================================================================================================
 // K6  ConvNext channel MLP
 // =================================================================================================
 namespace mlp {
 constexpr int kTileBytes = 32768;     // [128 rows x 128 K] bf16 = 2 slabs
 constexpr int kWStages = 3;
-constexpr int kSmemBytes = (2 + 2 + kWStages) * kTileBytes + 1024;
+constexpr int kTilesBytes = (2 + 2 + kWStages) * kTileBytes;
+constexpr int kSmemBytes = 232448;    // everything (tiles, bias, barriers) is carved from the dynamic window
 constexpr int kChunksPerTile = 8;     // W1_0, W1_1, W2_0, W1_2, W2_1, W1_3, W2_2, W2_3
 
 struct Bars {
@@ -52,17 +84,20 @@ convnext_mlp_tc_kernel(const uint8_t* __restrict__ y_img, const uint8_t* __restr
                        const float* __restrict__ b2, const float* __restrict__ layer_scale, long long rows,
                        float* __restrict__ h) {
   using namespace mlp;
-  extern __shared__ uint8_t smem_raw[];
-  __shared__ Bars bars;
-  __shared__ uint32_t tmem_base_s;
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
   const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
   uint8_t* smem = smem_raw + (base - smem_u32(smem_raw));
-  uint8_t* A[2] = {smem, smem + kTileBytes};
-  uint8_t* H[2] = {smem + 2 * kTileBytes, smem + 3 * kTileBytes};
-  uint8_t* W = smem + 4 * kTileBytes;
+  uint8_t* const A0 = smem;                       // A[ab] = A0 + ab * kTileBytes
+  uint8_t* const H0 = smem + 2 * kTileBytes;      // H[b]  = H0 + b * kTileBytes
+  uint8_t* const W = smem + 4 * kTileBytes;
+  float* const s_b1 = reinterpret_cast<float*>(smem + kTilesBytes);                 // [kW]
+  Bars& bars = *reinterpret_cast<Bars*>(smem + kTilesBytes + kW * sizeof(float));
+  uint32_t& tmem_base_s = *reinterpret_cast<uint32_t*>(smem + kTilesBytes + kW * sizeof(float) + sizeof(Bars));
+  if ((base - smem_u32(smem_raw)) + kTilesBytes + kW * sizeof(float) + sizeof(Bars) + 16 > (uint32_t)kSmemBytes) __trap();
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const long long tiles = (rows + kTileM - 1) / kTileM;
 
+  for (int i = threadIdx.x; i < kW; i += kThreads) s_b1[i] = b1[i];
   if (threadIdx.x == 0) {
     for (int i = 0; i < 2; ++i) {
       mbar_init(&bars.a_full[i], 1); mbar_init(&bars.a_empty[i], 1);
@@ -87,7 +122,7 @@ convnext_mlp_tc_kernel(const uint8_t* __restrict__ y_img, const uint8_t* __restr
       const int ab = it & 1;
       mbar_wait(&bars.a_empty[ab], ((it >> 1) & 1) ^ 1);
       mbar_expect_tx(&bars.a_full[ab], kTileBytes);
-      bulk_g2s(A[ab], y_img + (size_t)tile * kTileBytes, kTileBytes, &bars.a_full[ab]);
+      bulk_g2s(A0 + ab * kTileBytes, y_img + (size_t)tile * kTileBytes, kTileBytes, &bars.a_full[ab]);
       for (int c = 0; c < kChunksPerTile; ++c, ++chunk) {
         const int ws = chunk % kWStages;
         mbar_wait(&bars.w_empty[ws], ((chunk / kWStages) & 1) ^ 1);
@@ -103,7 +138,7 @@ convnext_mlp_tc_kernel(const uint8_t* __restrict__ y_img, const uint8_t* __restr
       const int ab = it & 1;
       mbar_wait(&bars.a_full[ab], (it >> 1) & 1);
       tc_fence_after();
-      const uint32_t a_addr = smem_u32(A[ab]);
+      const uint32_t a_addr = smem_u32(A0 + ab * kTileBytes);
       auto wait_w = [&]() -> uint32_t {
         const int ws = chunk % kWStages;
         mbar_wait(&bars.w_full[ws], (chunk / kWStages) & 1);
@@ -135,7 +170,7 @@ convnext_mlp_tc_kernel(const uint8_t* __restrict__ y_img, const uint8_t* __restr
         if (j == 0) mbar_wait(&bars.d2_empty, (it & 1) ^ 1);
         tc_fence_after();
         const uint32_t d = tmem + 256;
-        const uint32_t h_addr = smem_u32(H[b]);
+        const uint32_t h_addr = smem_u32(H0 + b * kTileBytes);
         mma_slab(d, h_addr, w_addr, 4, j > 0);
         mma_slab(d, h_addr + 16384, w_addr + 16384, 4, true);
         release_w();
@@ -145,8 +180,8 @@ convnext_mlp_tc_kernel(const uint8_t* __restrict__ y_img, const uint8_t* __restr
       gemm1(0); gemm1(1); gemm2(0); gemm1(2); gemm2(1); gemm1(3); gemm2(2); gemm2(3);
     }
   } else if (warp >= kEpiWarp0) {
-    // ---------------- epilogue ----------------
-    const int q = warp & 3, half = (warp - kEpiWarp0) >> 2;
+    // ---------------- epilogue: warp = (lane quarter q, column group cgi of 32 columns) ----------------
+    const int q = warp & 3, cgi = (warp - kEpiWarp0) >> 2;
     const int m = q * 32 + lane;
     const uint32_t lane_addr = (uint32_t)(q * 32) << 16;
     int it = 0;
@@ -157,22 +192,11 @@ convnext_mlp_tc_kernel(const uint8_t* __restrict__ y_img, const uint8_t* __restr
         mbar_wait(&bars.d1_full[b], use & 1);
         mbar_wait(&bars.h_empty[b], (use & 1) ^ 1);
         tc_fence_after();
-        uint8_t* hrow = H[b] + half * 16384 + m * kRowBytes;
-#pragma unroll
-        for (int g = 0; g < 2; ++g) {
-          float v[32];
-          tmem_ld32(tmem + lane_addr + b * 128 + half * 64 + g * 32, v);
-          const float* bias = b1 + j * 128 + half * 64 + g * 32;
-#pragma unroll
-          for (int cc = 0; cc < 4; ++cc) {
-            uint4 pk;
-            pk.x = pack_bf16(gelu_fast(v[cc * 8 + 0] + __ldg(bias + cc * 8 + 0)), gelu_fast(v[cc * 8 + 1] + __ldg(bias + cc * 8 + 1)));
-            pk.y = pack_bf16(gelu_fast(v[cc * 8 + 2] + __ldg(bias + cc * 8 + 2)), gelu_fast(v[cc * 8 + 3] + __ldg(bias + cc * 8 + 3)));
-            pk.z = pack_bf16(gelu_fast(v[cc * 8 + 4] + __ldg(bias + cc * 8 + 4)), gelu_fast(v[cc * 8 + 5] + __ldg(bias + cc * 8 + 5)));
-            pk.w = pack_bf16(gelu_fast(v[cc * 8 + 6] + __ldg(bias + cc * 8 + 6)), gelu_fast(v[cc * 8 + 7] + __ldg(bias + cc * 8 + 7)));
-            *reinterpret_cast<uint4*>(hrow + (((g * 4 + cc) ^ (m & 7)) << 4)) = pk;
-          }
-        }
+        float v[32];
+        tmem_ld32(tmem + lane_addr + b * 128 + cgi * 32, v);
+        // hidden unit k = cgi*32 .. +31 of this 128-slice -> slab cgi>>1, chunks (cgi&1)*4 .. +3
+        gelu_store32<true, false>(v, s_b1 + j * 128 + cgi * 32, 1.0f,
+                                  H0 + b * kTileBytes + (cgi >> 1) * 16384 + m * kRowBytes, (cgi & 1) * 4, m);
         tc_fence_before();
         fence_proxy_async();
         __syncwarp();
@@ -184,12 +208,14 @@ convnext_mlp_tc_kernel(const uint8_t* __restrict__ y_img, const uint8_t* __restr
       mbar_wait(&bars.d2_full, it & 1);
       tc_fence_after();
       const long long row = tile * kTileM + m;
-#pragma unroll
-      for (int g = 0; g < 2; ++g) {
+      {
         float v[32];
-        tmem_ld32(tmem + lane_addr + 256 + half * 64 + g * 32, v);
+        tmem_ld32(tmem + lane_addr + 256 + cgi * 32, v);
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&bars.d2_empty);       // accumulators are in registers: release D2 early
         if (row < rows) {
-          const int c0 = half * 64 + g * 32;
+          const int c0 = cgi * 32;
           float* hp = h + (size_t)row * kC + c0;
 #pragma unroll
           for (int i = 0; i < 8; ++i) {
@@ -204,9 +230,6 @@ convnext_mlp_tc_kernel(const uint8_t* __restrict__ y_img, const uint8_t* __restr
           }
         }
       }
-      tc_fence_before();
-      __syncwarp();
-      if (lane == 0) mbar_arrive(&bars.d2_empty);
     }
   }
   tc_fence_before();
@@ -226,7 +249,8 @@ constexpr int kStages = 6;
 constexpr int kW1Bytes = 32768;         // [128 x 96 -> 128] resident
 constexpr int kA2Bytes = 32768;
 constexpr int kA3Bytes = 65536;         // first 32 KB double as the monomial tile A1
-constexpr int kSmemBytes = kW1Bytes + kA2Bytes + kA3Bytes + kStages * kChunkBytes + 1024;
+constexpr int kTilesBytes = kW1Bytes + kA2Bytes + kA3Bytes + kStages * kChunkBytes;
+constexpr int kSmemBytes = 232448;      // everything (tiles, bias, barriers) is carved from the dynamic window
 constexpr int kChunksPerTile = 4 + 4 * kL;   // W2 (n-half, k-slab) x4, then Wk_l k-slabs
 constexpr int kEdgesPerTile = kTileM / kO;
 
@@ -235,6 +259,74 @@ struct Bars {
   uint64_t a1_full, a2_full, a3_full, d2_full;
   uint64_t x_full[2], x_empty[2];     // TMEM buffers X0 (D1, D3 even layers) / X1 (D3 odd layers)
 };
+
+// monomial n of csrc/common.cuh monomials83 as compile-time index triples; 83 = constant 1 (bias), > 83 = 0
+struct MonoIdx { int deg, a, b, c; };
+__host__ __device__ constexpr MonoIdx mono_idx(int n) {
+  if (n < 6) return {1, n, 0, 0};
+  int m = 6;
+  for (int i = 0; i < 6; ++i)
+    for (int j = i; j < 6; ++j) {
+      if (m == n) return {2, i, j, 0};
+      ++m;
+    }
+  for (int i = 0; i < 6; ++i)
+    for (int j = i; j < 6; ++j)
+      for (int k = j; k < 6; ++k) {
+        if (m == n) return {3, i, j, k};
+        ++m;
+      }
+  return {n == kMono ? 0 : -1, 0, 0, 0};
+}
+template <int N>
+__device__ __forceinline__ float mono_val(const float (&v)[6], float one) {
+  constexpr MonoIdx mi = mono_idx(N);
+  if constexpr (mi.deg == 1) return v[mi.a];
+  else if constexpr (mi.deg == 2) return v[mi.a] * v[mi.b];
+  else if constexpr (mi.deg == 3) return v[mi.a] * v[mi.b] * v[mi.c];
+  else if constexpr (mi.deg == 0) return one;
+  else return 0.f;
+}
+template <int C>
+__device__ __forceinline__ uint4 mono_chunk(const float (&v)[6], float one) {
+  uint4 pk;
+  pk.x = pack_bf16(mono_val<C * 8 + 0>(v, one), mono_val<C * 8 + 1>(v, one));
+  pk.y = pack_bf16(mono_val<C * 8 + 2>(v, one), mono_val<C * 8 + 3>(v, one));
+  pk.z = pack_bf16(mono_val<C * 8 + 4>(v, one), mono_val<C * 8 + 5>(v, one));
+  pk.w = pack_bf16(mono_val<C * 8 + 6>(v, one), mono_val<C * 8 + 7>(v, one));
+  return pk;
+}
+// chunks 3*PART .. 3*PART+2 of monomial row m (12 chunks of 8 = 96 columns; slab = chunk / 8)
+template <int PART>
+__device__ __forceinline__ void store_mono_part(const float (&v)[6], float one, uint8_t* a1, int m) {
+#pragma unroll
+  for (int i = 0; i < 3; ++i) {
+    constexpr int kBase = PART * 3;
+    const int c = kBase + i;
+    uint4 pk = i == 0 ? mono_chunk<kBase>(v, one) : (i == 1 ? mono_chunk<kBase + 1>(v, one) : mono_chunk<kBase + 2>(v, one));
+    *reinterpret_cast<uint4*>(a1 + (c >> 3) * 16384 + m * kRowBytes + (((c & 7) ^ (m & 7)) << 4)) = pk;
+  }
+}
+
+// fp32 edge invariants for the bf16 path (the monomials are rounded to bf16 right after; the fp32 path and the
+// graph keep fp64): [dir.ori, |dir - (dir.ori) ori|, dist, cos(dir,a), cos(dir,b), cos(dir,c)]
+__device__ __forceinline__ void edge_invariants_f32(const double* __restrict__ dir3, double dist, const double* __restrict__ lat9,
+                                                    const float* __restrict__ ori3, float (&attr)[6]) {
+  const float dx = (float)dir3[0], dy = (float)dir3[1], dz = (float)dir3[2];
+  const float ox = ori3[0], oy = ori3[1], oz = ori3[2];
+  const float i1 = dx * ox + dy * oy + dz * oz;
+  const float px = dx - i1 * ox, py = dy - i1 * oy, pz = dz - i1 * oz;
+  attr[0] = i1;
+  attr[1] = sqrtf(px * px + py * py + pz * pz);
+  attr[2] = (float)dist;
+  const float dd = dx * dx + dy * dy + dz * dz;
+#pragma unroll
+  for (int mm = 0; mm < 3; ++mm) {
+    const float ax = (float)lat9[3 * mm], ay = (float)lat9[3 * mm + 1], az = (float)lat9[3 * mm + 2];
+    const float w12 = dx * ax + dy * ay + dz * az, w2 = ax * ax + ay * ay + az * az;
+    attr[3 + mm] = w12 * rsqrtf(fmaxf(dd * w2, 1e-16f));     // CosineSimilarity, eps = 1e-8
+  }
+}
 }  // namespace edge
 
 __global__ void __launch_bounds__(kThreads, 1)
@@ -244,21 +336,26 @@ edge_kernels_tc_kernel(const double* __restrict__ dir, const double* __restrict_
                        const uint8_t* __restrict__ w1_img, const uint8_t* __restrict__ w_img, const float* __restrict__ b2,
                        double radius, __nv_bfloat16* __restrict__ kernels) {
   using namespace edge;
-  extern __shared__ uint8_t smem_raw[];
-  __shared__ Bars bars;
-  __shared__ uint32_t tmem_base_s;
-  __shared__ float s_win[kEdgesPerTile];
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
   const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
   uint8_t* smem = smem_raw + (base - smem_u32(smem_raw));
-  uint8_t* W1 = smem;
-  uint8_t* A2 = W1 + kW1Bytes;
-  uint8_t* A3 = A2 + kA2Bytes;          // A1 aliases A3[0 .. 32 KB)
-  uint8_t* W = A3 + kA3Bytes;
+  float* const s_b2 = reinterpret_cast<float*>(smem + kTilesBytes);                                   // [kD]
+  float* const s_win = s_b2 + kD;                                                                      // [8]
+  Bars& bars = *reinterpret_cast<Bars*>(smem + kTilesBytes + (kD + kEdgesPerTile) * sizeof(float));
+  uint32_t& tmem_base_s =
+      *reinterpret_cast<uint32_t*>(smem + kTilesBytes + (kD + kEdgesPerTile) * sizeof(float) + sizeof(Bars));
+  if ((base - smem_u32(smem_raw)) + kTilesBytes + (kD + kEdgesPerTile) * sizeof(float) + sizeof(Bars) + 16 > (uint32_t)kSmemBytes)
+    __trap();
+  uint8_t* const W1 = smem;
+  uint8_t* const A2 = W1 + kW1Bytes;
+  uint8_t* const A3 = A2 + kA2Bytes;          // A1 aliases A3[0 .. 32 KB)
+  uint8_t* const W = A3 + kA3Bytes;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   long long E = *num_edges_ptr;
   if (E > edge_capacity) E = edge_capacity;
   const long long tiles = (E + kEdgesPerTile - 1) / kEdgesPerTile;
 
+  for (int i = threadIdx.x; i < kD; i += kThreads) s_b2[i] = b2[i];
   if (threadIdx.x == 0) {
     mbar_init(&bars.w1_full, 1);
     for (int i = 0; i < kStages; ++i) { mbar_init(&bars.w_full[i], 1); mbar_init(&bars.w_empty[i], 1); }
@@ -273,7 +370,6 @@ edge_kernels_tc_kernel(const double* __restrict__ dir, const double* __restrict_
   tc_fence_after();
   const uint32_t tmem = tmem_base_s;
   // TMEM columns: X0 = [0,128)  D2 = [128,384)  X1 = [384,512)
-  const uint32_t tmem_x[2] = {tmem, tmem + 384};
 
   if (warp == 0 && lane == 0) {
     // ---------------- producer ----------------
@@ -292,7 +388,7 @@ edge_kernels_tc_kernel(const double* __restrict__ dir, const double* __restrict_
     // ---------------- MMA issuer ----------------
     mbar_wait(&bars.w1_full, 0);
     uint32_t chunk = 0;
-    uint32_t xuse[2] = {0, 0};
+    uint32_t xuse0 = 0, xuse1 = 0;
     int it = 0;
     const uint32_t w1_addr = smem_u32(W1), a2_addr = smem_u32(A2), a3_addr = smem_u32(A3);
     auto wait_w = [&]() -> uint32_t {
@@ -308,12 +404,12 @@ edge_kernels_tc_kernel(const double* __restrict__ dir, const double* __restrict_
     for (long long tile = blockIdx.x; tile < tiles; tile += gridDim.x, ++it) {
       // GEMM1: X0 = A1[128 x 96] . W1m^T
       mbar_wait(&bars.a1_full, it & 1);
-      mbar_wait(&bars.x_empty[0], (xuse[0] & 1) ^ 1);
+      mbar_wait(&bars.x_empty[0], (xuse0 & 1) ^ 1);
       tc_fence_after();
-      mma_slab(tmem_x[0], a3_addr, w1_addr, 4, false);
-      mma_slab(tmem_x[0], a3_addr + 16384, w1_addr + 16384, 2, true);
+      mma_slab(tmem, a3_addr, w1_addr, 4, false);
+      mma_slab(tmem, a3_addr + 16384, w1_addr + 16384, 2, true);
       umma_commit(&bars.x_full[0]);
-      ++xuse[0];
+      ++xuse0;
       // GEMM2: D2[:, nh*128 ..] = A2[128 x 128] . W2[nh]^T
       mbar_wait(&bars.a2_full, it & 1);
       tc_fence_after();
@@ -329,78 +425,58 @@ edge_kernels_tc_kernel(const double* __restrict__ dir, const double* __restrict_
       tc_fence_after();
       for (int l = 0; l < kL; ++l) {
         const int b = l & 1;
-        mbar_wait(&bars.x_empty[b], (xuse[b] & 1) ^ 1);
+        uint32_t& xuse = b ? xuse1 : xuse0;
+        mbar_wait(&bars.x_empty[b], (xuse & 1) ^ 1);
         tc_fence_after();
+        const uint32_t d = tmem + b * 384;
         for (int ks = 0; ks < 4; ++ks) {
           const uint32_t w_addr = wait_w();
-          mma_slab(tmem_x[b], a3_addr + ks * 16384, w_addr, 4, ks > 0);
+          mma_slab(d, a3_addr + ks * 16384, w_addr, 4, ks > 0);
           release_w();
         }
         umma_commit(&bars.x_full[b]);
-        ++xuse[b];
+        ++xuse;
       }
     }
   } else if (warp >= kEpiWarp0) {
-    // ---------------- generator + epilogues ----------------
-    const int q = warp & 3, half = (warp - kEpiWarp0) >> 2;
+    // ---------------- generator + epilogues: warp = (lane quarter q, column group cgi) ----------------
+    const int q = warp & 3, cgi = (warp - kEpiWarp0) >> 2;
     const int m = q * 32 + lane;                     // tile row = (edge m / 16, orientation m % 16)
     const uint32_t lane_addr = (uint32_t)(q * 32) << 16;
-    uint32_t xuse[2] = {0, 0};
+    uint32_t xuse0 = 0, xuse1 = 0;
     int it = 0;
     for (long long tile = blockIdx.x; tile < tiles; tile += gridDim.x, ++it) {
       const long long e = tile * kEdgesPerTile + (m >> 4);
       const bool valid = e < E;
-      // ---- A1: invariants -> 83 monomials + constant 1 (bias) -> bf16, 6 of the 12 16-byte chunks per thread.
+      // ---- A1: invariants -> 83 monomials + constant 1 (bias) -> bf16; 3 of the 12 16-byte chunks per thread.
       // The previous tile's GEMM3 finished reading A3 before its last x_full fired, which this warp waited on.
       {
         float attr[6] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
-        float mono[kMonoPad];
         if (valid) {
           const int g = crystal_of_atom[src[e]];
-          edge_invariants(dir + 3 * e, dist[e], lattice + 9 * (size_t)g, ori + 3 * (m & 15), attr);
-          if (half == 0 && (m & 15) == 0) s_win[m >> 4] = cutoff_window(dist[e], radius);
-        } else if (half == 0 && (m & 15) == 0) {
+          edge_invariants_f32(dir + 3 * e, dist[e], lattice + 9 * (size_t)g, ori + 3 * (m & 15), attr);
+          if (cgi == 0 && (m & 15) == 0) s_win[m >> 4] = cutoff_window(dist[e], radius);
+        } else if (cgi == 0 && (m & 15) == 0) {
           s_win[m >> 4] = 0.f;
         }
-        monomials83(attr, mono, 1);
-        mono[kMono] = valid ? 1.0f : 0.0f;
-#pragma unroll
-        for (int k = kMono + 1; k < kMonoPad; ++k) mono[k] = 0.f;
-        uint8_t* arow = A3 + m * kRowBytes;
-#pragma unroll
-        for (int c = 0; c < 12; ++c) {
-          if ((c < 6) == (half == 0)) {
-            uint4 pk;
-            pk.x = pack_bf16(mono[c * 8 + 0], mono[c * 8 + 1]);
-            pk.y = pack_bf16(mono[c * 8 + 2], mono[c * 8 + 3]);
-            pk.z = pack_bf16(mono[c * 8 + 4], mono[c * 8 + 5]);
-            pk.w = pack_bf16(mono[c * 8 + 6], mono[c * 8 + 7]);
-            *reinterpret_cast<uint4*>(arow + (c >> 3) * 16384 + (((c & 7) ^ (m & 7)) << 4)) = pk;
-          }
+        const float one = valid ? 1.0f : 0.0f;
+        switch (cgi) {
+          case 0: store_mono_part<0>(attr, one, A3, m); break;
+          case 1: store_mono_part<1>(attr, one, A3, m); break;
+          case 2: store_mono_part<2>(attr, one, A3, m); break;
+          default: store_mono_part<3>(attr, one, A3, m); break;
         }
       }
       fence_proxy_async();
       __syncwarp();
       if (lane == 0) mbar_arrive(&bars.a1_full);
-      // ---- epilogue 1: hidden = GELU(X0) -> A2 ----
-      mbar_wait(&bars.x_full[0], xuse[0] & 1);
+      // ---- epilogue 1: hidden = GELU(X0) -> A2 (hidden unit cgi*32.. -> slab cgi>>1, chunks (cgi&1)*4..) ----
+      mbar_wait(&bars.x_full[0], xuse0 & 1);
       tc_fence_after();
       {
-        uint8_t* hrow = A2 + half * 16384 + m * kRowBytes;
-#pragma unroll
-        for (int g = 0; g < 2; ++g) {
-          float v[32];
-          tmem_ld32(tmem_x[0] + lane_addr + half * 64 + g * 32, v);
-#pragma unroll
-          for (int cc = 0; cc < 4; ++cc) {
-            uint4 pk;
-            pk.x = pack_bf16(gelu_fast(v[cc * 8 + 0]), gelu_fast(v[cc * 8 + 1]));
-            pk.y = pack_bf16(gelu_fast(v[cc * 8 + 2]), gelu_fast(v[cc * 8 + 3]));
-            pk.z = pack_bf16(gelu_fast(v[cc * 8 + 4]), gelu_fast(v[cc * 8 + 5]));
-            pk.w = pack_bf16(gelu_fast(v[cc * 8 + 6]), gelu_fast(v[cc * 8 + 7]));
-            *reinterpret_cast<uint4*>(hrow + (((g * 4 + cc) ^ (m & 7)) << 4)) = pk;
-          }
-        }
+        float v[32];
+        tmem_ld32(tmem + lane_addr + cgi * 32, v);
+        gelu_store32<false, false>(v, nullptr, 1.0f, A2 + (cgi >> 1) * 16384 + m * kRowBytes, (cgi & 1) * 4, m);
       }
       tc_fence_before();
       fence_proxy_async();
@@ -409,61 +485,48 @@ edge_kernels_tc_kernel(const double* __restrict__ dir, const double* __restrict_
         mbar_arrive(&bars.x_empty[0]);
         mbar_arrive(&bars.a2_full);
       }
-      ++xuse[0];
-      // ---- epilogue 2: kernel basis = GELU(D2 + b2) * window -> A3 (this warp: 128 of the 256 columns) ----
+      ++xuse0;
+      // ---- epilogue 2: kernel basis = GELU(D2 + b2) * window -> A3; this warp: columns cgi*64 .. +63 = slab cgi ----
       mbar_wait(&bars.d2_full, it & 1);
       tc_fence_after();
       {
         const float win = s_win[m >> 4];
 #pragma unroll
-        for (int g = 0; g < 4; ++g) {
-          const int col0 = half * 128 + g * 32;            // kernel-basis channel = K index of GEMM3
+        for (int g = 0; g < 2; ++g) {
+          const int col0 = cgi * 64 + g * 32;
           float v[32];
           tmem_ld32(tmem + 128 + lane_addr + col0, v);
-          const float* bias = b2 + col0;
-          uint8_t* arow = A3 + (col0 >> 6) * 16384 + m * kRowBytes;
-#pragma unroll
-          for (int cc = 0; cc < 4; ++cc) {
-            uint4 pk;
-            pk.x = pack_bf16(gelu_fast(v[cc * 8 + 0] + __ldg(bias + cc * 8 + 0)) * win, gelu_fast(v[cc * 8 + 1] + __ldg(bias + cc * 8 + 1)) * win);
-            pk.y = pack_bf16(gelu_fast(v[cc * 8 + 2] + __ldg(bias + cc * 8 + 2)) * win, gelu_fast(v[cc * 8 + 3] + __ldg(bias + cc * 8 + 3)) * win);
-            pk.z = pack_bf16(gelu_fast(v[cc * 8 + 4] + __ldg(bias + cc * 8 + 4)) * win, gelu_fast(v[cc * 8 + 5] + __ldg(bias + cc * 8 + 5)) * win);
-            pk.w = pack_bf16(gelu_fast(v[cc * 8 + 6] + __ldg(bias + cc * 8 + 6)) * win, gelu_fast(v[cc * 8 + 7] + __ldg(bias + cc * 8 + 7)) * win);
-            const int chunk = ((col0 & 63) >> 3) + cc;
-            *reinterpret_cast<uint4*>(arow + ((chunk ^ (m & 7)) << 4)) = pk;
-          }
+          gelu_store32<true, true>(v, s_b2 + col0, win, A3 + cgi * 16384 + m * kRowBytes, g * 4, m);
         }
       }
       tc_fence_before();
       fence_proxy_async();
       __syncwarp();
       if (lane == 0) mbar_arrive(&bars.a3_full);
-      // ---- epilogue 3: kernels[l][e][o][c] = X[l&1] (bf16) ----
+      // ---- epilogue 3: kernels[l][e][o][c] = X[l&1] (bf16), channels cgi*32 .. +31 ----
       for (int l = 0; l < kL; ++l) {
         const int b = l & 1;
-        mbar_wait(&bars.x_full[b], xuse[b] & 1);
+        uint32_t& xuse = b ? xuse1 : xuse0;
+        mbar_wait(&bars.x_full[b], xuse & 1);
         tc_fence_after();
-        __nv_bfloat16* out = kernels + ((size_t)l * edge_capacity * kO + (size_t)tile * kTileM + m) * kC + half * 64;
-#pragma unroll
-        for (int g = 0; g < 2; ++g) {
-          float v[32];
-          tmem_ld32(tmem_x[b] + lane_addr + half * 64 + g * 32, v);
-          if (valid) {
-#pragma unroll
-            for (int cc = 0; cc < 4; ++cc) {
-              uint4 pk;
-              pk.x = pack_bf16(v[cc * 8 + 0], v[cc * 8 + 1]);
-              pk.y = pack_bf16(v[cc * 8 + 2], v[cc * 8 + 3]);
-              pk.z = pack_bf16(v[cc * 8 + 4], v[cc * 8 + 5]);
-              pk.w = pack_bf16(v[cc * 8 + 6], v[cc * 8 + 7]);
-              *reinterpret_cast<uint4*>(out + g * 32 + cc * 8) = pk;
-            }
-          }
-        }
+        float v[32];
+        tmem_ld32(tmem + b * 384 + lane_addr + cgi * 32, v);
         tc_fence_before();
         __syncwarp();
-        if (lane == 0) mbar_arrive(&bars.x_empty[b]);
-        ++xuse[b];
+        if (lane == 0) mbar_arrive(&bars.x_empty[b]);       // accumulators are in registers: release the buffer
+        ++xuse;
+        if (valid) {
+          __nv_bfloat16* out = kernels + ((size_t)l * edge_capacity * kO + (size_t)tile * kTileM + m) * kC + cgi * 32;
+#pragma unroll
+          for (int cc = 0; cc < 4; ++cc) {
+            uint4 pk;
+            pk.x = pack_bf16(v[cc * 8 + 0], v[cc * 8 + 1]);
+            pk.y = pack_bf16(v[cc * 8 + 2], v[cc * 8 + 3]);
+            pk.z = pack_bf16(v[cc * 8 + 4], v[cc * 8 + 5]);
+            pk.w = pack_bf16(v[cc * 8 + 6], v[cc * 8 + 7]);
+            *reinterpret_cast<uint4*>(out + cc * 8) = pk;
+          }
+        }
       }
     }
   }
