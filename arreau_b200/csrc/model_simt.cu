@@ -270,8 +270,14 @@ edge_kernels_simt_kernel(const double* __restrict__ dir, const double* __restric
 // ------------------------------------------------------------------------------------------------
 constexpr int kMsgNodes = 4;
 
-__device__ __forceinline__ float4 load_kernel4(const float* p) { return *reinterpret_cast<const float4*>(p); }
-__device__ __forceinline__ float4 load_kernel4(const __nv_bfloat16* p) {
+// Channels 4*cg .. +3 of kernel row (e, o).  fp32 kernels are plain [e][o][c]; bf16 kernels (tcgen05 path) keep
+// the 16-byte chunk k of a row at chunk position k ^ o (so the producing kernel can stage and bulk-store its
+// tiles without shared-memory bank conflicts, csrc/model_tc.cu); a warp still reads whole 256-byte rows.
+__device__ __forceinline__ float4 load_kernel4(const float* row, int cg, int /*o*/) {
+  return *reinterpret_cast<const float4*>(row + cg * 4);
+}
+__device__ __forceinline__ float4 load_kernel4(const __nv_bfloat16* row, int cg, int o) {
+  const __nv_bfloat16* p = row + ((((cg >> 1) ^ (o & 15)) << 3) | ((cg & 1) << 2));
   const uint2 raw = *reinterpret_cast<const uint2*>(p);
   const __nv_bfloat162 a = *reinterpret_cast<const __nv_bfloat162*>(&raw.x);
   const __nv_bfloat162 b = *reinterpret_cast<const __nv_bfloat162*>(&raw.y);
@@ -301,15 +307,15 @@ message_fiber_norm_kernel(const KT* __restrict__ kern, const float* __restrict__
       int e = e0;
       for (; e + 1 < e1; e += 2) {       // two edges in flight: 16 independent 16-byte loads per thread
         const int s0 = src[e], s1 = src[e + 1];
-        const KT* kp0 = kern + ((size_t)e * kO + og * 4) * kC + cg * 4;
+        const KT* kp0 = kern + ((size_t)e * kO + og * 4) * kC;
         const KT* kp1 = kp0 + kO * kC;
         const float* hp0 = h + ((size_t)s0 * kO + og * 4) * kC + cg * 4;
         const float* hp1 = h + ((size_t)s1 * kO + og * 4) * kC + cg * 4;
         float4 k0[4], k1[4], h0[4], h1[4];
 #pragma unroll
         for (int oo = 0; oo < 4; ++oo) {
-          k0[oo] = load_kernel4(kp0 + oo * kC);
-          k1[oo] = load_kernel4(kp1 + oo * kC);
+          k0[oo] = load_kernel4(kp0 + oo * kC, cg, og * 4 + oo);
+          k1[oo] = load_kernel4(kp1 + oo * kC, cg, og * 4 + oo);
           h0[oo] = *reinterpret_cast<const float4*>(hp0 + oo * kC);
           h1[oo] = *reinterpret_cast<const float4*>(hp1 + oo * kC);
         }
@@ -327,11 +333,11 @@ message_fiber_norm_kernel(const KT* __restrict__ kern, const float* __restrict__
       }
       if (e < e1) {
         const int s0 = src[e];
-        const KT* kp0 = kern + ((size_t)e * kO + og * 4) * kC + cg * 4;
+        const KT* kp0 = kern + ((size_t)e * kO + og * 4) * kC;
         const float* hp0 = h + ((size_t)s0 * kO + og * 4) * kC + cg * 4;
 #pragma unroll
         for (int oo = 0; oo < 4; ++oo) {
-          const float4 kv = load_kernel4(kp0 + oo * kC);
+          const float4 kv = load_kernel4(kp0 + oo * kC, cg, og * 4 + oo);
           const float4 hv = *reinterpret_cast<const float4*>(hp0 + oo * kC);
           a[oo].x = fmaf(kv.x, hv.x, a[oo].x);
           a[oo].y = fmaf(kv.y, hv.y, a[oo].y);

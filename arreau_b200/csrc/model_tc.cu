@@ -243,13 +243,20 @@ convnext_mlp_tc_kernel(const uint8_t* __restrict__ y_img, const uint8_t* __restr
 // =================================================================================================
 // K3 + K4a  edge pipeline
 // =================================================================================================
+__device__ long long* g_tc_prof = nullptr;   // debug: per-phase clock64 stamps of CTA 0 (scratch/prof_tc.py)
+#define TC_STAMP(slot)                                                                     \
+  do {                                                                                      \
+    if (prof && it < 6) prof[(it * 2 + prof_role) * 16 + (slot)] = clock64();               \
+  } while (0)
+
 namespace edge {
 constexpr int kChunkBytes = 16384;      // [128 rows x 64 K] bf16 = 1 slab
-constexpr int kStages = 6;
+constexpr int kStages = 4;
+constexpr int kOutBytes = 32768;        // staging of one layer's [128 rows x 128 ch] bf16 output tile (bulk store)
 constexpr int kW1Bytes = 32768;         // [128 x 96 -> 128] resident
 constexpr int kA2Bytes = 32768;
 constexpr int kA3Bytes = 65536;         // first 32 KB double as the monomial tile A1
-constexpr int kTilesBytes = kW1Bytes + kA2Bytes + kA3Bytes + kStages * kChunkBytes;
+constexpr int kTilesBytes = kW1Bytes + kA2Bytes + kA3Bytes + kStages * kChunkBytes + kOutBytes;
 constexpr int kSmemBytes = 232448;      // everything (tiles, bias, barriers) is carved from the dynamic window
 constexpr int kChunksPerTile = 4 + 4 * kL;   // W2 (n-half, k-slab) x4, then Wk_l k-slabs
 constexpr int kEdgesPerTile = kTileM / kO;
@@ -350,6 +357,7 @@ edge_kernels_tc_kernel(const double* __restrict__ dir, const double* __restrict_
   uint8_t* const A2 = W1 + kW1Bytes;
   uint8_t* const A3 = A2 + kA2Bytes;          // A1 aliases A3[0 .. 32 KB)
   uint8_t* const W = A3 + kA3Bytes;
+  uint8_t* const OUT = W + kStages * kChunkBytes;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   long long E = *num_edges_ptr;
   if (E > edge_capacity) E = edge_capacity;
@@ -390,6 +398,8 @@ edge_kernels_tc_kernel(const double* __restrict__ dir, const double* __restrict_
     uint32_t chunk = 0;
     uint32_t xuse0 = 0, xuse1 = 0;
     int it = 0;
+    long long* prof = blockIdx.x == 0 ? g_tc_prof : nullptr;
+    constexpr int prof_role = 0;
     const uint32_t w1_addr = smem_u32(W1), a2_addr = smem_u32(A2), a3_addr = smem_u32(A3);
     auto wait_w = [&]() -> uint32_t {
       const int ws = chunk % kStages;
@@ -403,16 +413,20 @@ edge_kernels_tc_kernel(const double* __restrict__ dir, const double* __restrict_
     };
     for (long long tile = blockIdx.x; tile < tiles; tile += gridDim.x, ++it) {
       // GEMM1: X0 = A1[128 x 96] . W1m^T
+      TC_STAMP(0);
       mbar_wait(&bars.a1_full, it & 1);
       mbar_wait(&bars.x_empty[0], (xuse0 & 1) ^ 1);
       tc_fence_after();
+      TC_STAMP(1);
       mma_slab(tmem, a3_addr, w1_addr, 4, false);
       mma_slab(tmem, a3_addr + 16384, w1_addr + 16384, 2, true);
       umma_commit(&bars.x_full[0]);
       ++xuse0;
       // GEMM2: D2[:, nh*128 ..] = A2[128 x 128] . W2[nh]^T
+      TC_STAMP(2);
       mbar_wait(&bars.a2_full, it & 1);
       tc_fence_after();
+      TC_STAMP(3);
       for (int nh = 0; nh < 2; ++nh)
         for (int ks = 0; ks < 2; ++ks) {
           const uint32_t w_addr = wait_w();
@@ -421,21 +435,26 @@ edge_kernels_tc_kernel(const double* __restrict__ dir, const double* __restrict_
         }
       umma_commit(&bars.d2_full);
       // GEMM3: X[l&1] = A3[128 x 256] . Wk_l^T
+      TC_STAMP(4);
       mbar_wait(&bars.a3_full, it & 1);
       tc_fence_after();
+      TC_STAMP(5);
       for (int l = 0; l < kL; ++l) {
         const int b = l & 1;
         uint32_t& xuse = b ? xuse1 : xuse0;
         mbar_wait(&bars.x_empty[b], (xuse & 1) ^ 1);
         tc_fence_after();
         const uint32_t d = tmem + b * 384;
+        if (l == 2) TC_STAMP(11);
         for (int ks = 0; ks < 4; ++ks) {
           const uint32_t w_addr = wait_w();
+          if (l == 2) TC_STAMP(12 + ks);
           mma_slab(d, a3_addr + ks * 16384, w_addr, 4, ks > 0);
           release_w();
         }
         umma_commit(&bars.x_full[b]);
         ++xuse;
+        TC_STAMP(6 + l);
       }
     }
   } else if (warp >= kEpiWarp0) {
@@ -445,9 +464,13 @@ edge_kernels_tc_kernel(const double* __restrict__ dir, const double* __restrict_
     const uint32_t lane_addr = (uint32_t)(q * 32) << 16;
     uint32_t xuse0 = 0, xuse1 = 0;
     int it = 0;
+    const bool is_issuer = threadIdx.x == kEpiWarp0 * 32;
+    long long* prof = (blockIdx.x == 0 && is_issuer) ? g_tc_prof : nullptr;
+    constexpr int prof_role = 1;
     for (long long tile = blockIdx.x; tile < tiles; tile += gridDim.x, ++it) {
       const long long e = tile * kEdgesPerTile + (m >> 4);
       const bool valid = e < E;
+      TC_STAMP(0);
       // ---- A1: invariants -> 83 monomials + constant 1 (bias) -> bf16; 3 of the 12 16-byte chunks per thread.
       // The previous tile's GEMM3 finished reading A3 before its last x_full fired, which this warp waited on.
       {
@@ -470,9 +493,15 @@ edge_kernels_tc_kernel(const double* __restrict__ dir, const double* __restrict_
       fence_proxy_async();
       __syncwarp();
       if (lane == 0) mbar_arrive(&bars.a1_full);
+      TC_STAMP(1);
       // ---- epilogue 1: hidden = GELU(X0) -> A2 (hidden unit cgi*32.. -> slab cgi>>1, chunks (cgi&1)*4..) ----
       mbar_wait(&bars.x_full[0], xuse0 & 1);
       tc_fence_after();
+      TC_STAMP(2);
+      if (it > 0) {   // the previous tile's layer-1/3 stores were staged in A2: they must have left shared memory
+        if (is_issuer) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+        asm volatile("bar.sync 1, %0;" ::"n"(kEpiThreads) : "memory");
+      }
       {
         float v[32];
         tmem_ld32(tmem + lane_addr + cgi * 32, v);
@@ -486,9 +515,11 @@ edge_kernels_tc_kernel(const double* __restrict__ dir, const double* __restrict_
         mbar_arrive(&bars.a2_full);
       }
       ++xuse0;
+      TC_STAMP(3);
       // ---- epilogue 2: kernel basis = GELU(D2 + b2) * window -> A3; this warp: columns cgi*64 .. +63 = slab cgi ----
       mbar_wait(&bars.d2_full, it & 1);
       tc_fence_after();
+      TC_STAMP(4);
       {
         const float win = s_win[m >> 4];
 #pragma unroll
@@ -503,6 +534,7 @@ edge_kernels_tc_kernel(const double* __restrict__ dir, const double* __restrict_
       fence_proxy_async();
       __syncwarp();
       if (lane == 0) mbar_arrive(&bars.a3_full);
+      TC_STAMP(5);
       // ---- epilogue 3: kernels[l][e][o][c] = X[l&1] (bf16), channels cgi*32 .. +31 ----
       for (int l = 0; l < kL; ++l) {
         const int b = l & 1;
@@ -515,20 +547,38 @@ edge_kernels_tc_kernel(const double* __restrict__ dir, const double* __restrict_
         __syncwarp();
         if (lane == 0) mbar_arrive(&bars.x_empty[b]);       // accumulators are in registers: release the buffer
         ++xuse;
-        if (valid) {
-          __nv_bfloat16* out = kernels + ((size_t)l * edge_capacity * kO + (size_t)tile * kTileM + m) * kC + cgi * 32;
+        // The layer's output tile is 32 KB contiguous in HBM: stage it in shared memory and let the TMA engine
+        // write it with one bulk store.  Rows are 256 B; the 16-byte chunk k of row (e, o) is stored at chunk
+        // position k ^ o (the bf16 kernels layout, undone by the message kernel's loads), which makes these
+        // 16-byte shared stores conflict free.  Two staging buffers (OUT and the idle A2 tile) alternate so the
+        // store of layer l-1 drains while layer l is staged.
+        uint8_t* stage = (l & 1) ? A2 : OUT;
+        if (is_issuer) asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");   // store of layer l-2 has left smem
+        asm volatile("bar.sync 1, %0;" ::"n"(kEpiThreads) : "memory");
+        uint8_t* orow = stage + m * 256;
 #pragma unroll
-          for (int cc = 0; cc < 4; ++cc) {
-            uint4 pk;
-            pk.x = pack_bf16(v[cc * 8 + 0], v[cc * 8 + 1]);
-            pk.y = pack_bf16(v[cc * 8 + 2], v[cc * 8 + 3]);
-            pk.z = pack_bf16(v[cc * 8 + 4], v[cc * 8 + 5]);
-            pk.w = pack_bf16(v[cc * 8 + 6], v[cc * 8 + 7]);
-            *reinterpret_cast<uint4*>(out + cc * 8) = pk;
-          }
+        for (int cc = 0; cc < 4; ++cc) {
+          uint4 pk;
+          pk.x = pack_bf16(v[cc * 8 + 0], v[cc * 8 + 1]);
+          pk.y = pack_bf16(v[cc * 8 + 2], v[cc * 8 + 3]);
+          pk.z = pack_bf16(v[cc * 8 + 4], v[cc * 8 + 5]);
+          pk.w = pack_bf16(v[cc * 8 + 6], v[cc * 8 + 7]);
+          *reinterpret_cast<uint4*>(orow + (((cgi * 4 + cc) ^ (m & 15)) << 4)) = pk;
         }
+        fence_proxy_async();
+        asm volatile("bar.sync 1, %0;" ::"n"(kEpiThreads) : "memory");
+        if (is_issuer) {
+          const long long left = E - tile * kEdgesPerTile;
+          const uint32_t bytes = (uint32_t)(left < kEdgesPerTile ? left : kEdgesPerTile) * (kO * kC * 2);
+          __nv_bfloat16* out = kernels + ((size_t)l * edge_capacity * kO + (size_t)tile * kTileM) * kC;
+          asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(out), "r"(smem_u32(stage)), "r"(bytes)
+                       : "memory");
+          asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+        }
+        TC_STAMP(6 + l);
       }
     }
+    if (is_issuer) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");   // all output tiles have landed
   }
   tc_fence_before();
   __syncthreads();
@@ -550,6 +600,11 @@ int num_sms_tc() {
 }
 
 }  // namespace
+
+// debug only (not part of the public ABI): clock64 stamps of CTA 0 of the edge kernel, [6 tiles][2 roles][16]
+extern "C" int arreau_debug_set_tc_profile(long long* buf) {
+  return (int)cudaMemcpyToSymbol(g_tc_prof, &buf, sizeof(buf));
+}
 
 extern "C" int arreau_convnext_mlp_bf16(const void* y_img, const void* w_img, const float* b1, const float* b2,
                                         const float* layer_scale, int64_t num_rows, float* h, void* stream) {

@@ -251,6 +251,18 @@ class DenoiseEngine:
         a.update_types = 1 if update_types else 0
         _lib.call("arreau_denoise_step", self.w.ref(), C.byref(self.ws), C.byref(a), self.stream)
 
+    def kernels_logical(self, layer: int, num_edges: Optional[int] = None) -> torch.Tensor:
+        """Spatial kernels of one layer as fp32 [E,O,C] in logical channel order (debug / tests).  The bf16 path
+        stores the 16-byte chunk k of row (e, o) at chunk position k ^ o (csrc/model_tc.cu); undo that here."""
+        E = self.num_edges() if num_edges is None else num_edges
+        k = self.kernels[layer, :E]
+        if self.precision != "bf16":
+            return k.float()
+        k = k.float().view(E, NUM_ORI, HIDDEN // 8, 8)
+        o = torch.arange(NUM_ORI, device=k.device)[:, None]
+        pos = torch.arange(HIDDEN // 8, device=k.device)[None, :] ^ o          # logical chunk c lives at c ^ o
+        return torch.gather(k, 2, pos[None, :, :, None].expand(E, -1, -1, 8)).reshape(E, NUM_ORI, HIDDEN)
+
     def edges(self):
         """Current edge list as (src, dst, cell, dist, dir) trimmed to E (host synchronisation)."""
         E = self.num_edges()
