@@ -257,8 +257,10 @@ graph_fill_kernel(const double* __restrict__ pos, const double* __restrict__ lat
   // O(m^2) selection passes at O(log) instead of one per 224 candidates.
   double thr_d2 = INFINITY;
   int thr_c = 0x7fffffff;
+  // compact as soon as cap + 64 candidates are buffered: the selection pass is O(m^2 / 32) per lane
+  const int sel_limit = min(kSelBuf, ((cap + 31) / 32) * 32 + 64);
   for (int c0 = 0; c0 < total; c0 += 32) {
-    if (m + 32 > kSelBuf) {
+    if (m + 32 > sel_limit) {
       m = select_topk(sd2, sc, s_mask[warp], m, cap, lane);
       // threshold = the largest kept key
       double kd = -INFINITY;

@@ -24,6 +24,12 @@ constexpr int kEpiThreads = kEpiWarps * 32;
 constexpr int kTileM = 128;
 constexpr uint32_t kIdesc128 = umma_idesc_bf16(128, 128);
 
+__device__ long long* g_tc_prof = nullptr;   // debug: per-phase clock64 stamps of CTA 0 (scratch/prof_tc.py)
+#define TC_STAMP(slot)                                                                     \
+  do {                                                                                      \
+    if (prof && it < 6) prof[(it * 2 + prof_role) * 16 + (slot)] = clock64();               \
+  } while (0)
+
 // issue the UMMA_K = 16 steps of one 64-wide K slab: D[128 x 128] (+)= A_slab[128 x 64] * B_slab[128 x 64]^T
 __device__ __forceinline__ void mma_slab(uint32_t tmem_d, uint32_t a_slab, uint32_t b_slab, int ksteps, bool accumulate_first) {
   const uint64_t ad = umma_desc_sw128(a_slab), bd = umma_desc_sw128(b_slab);
@@ -134,10 +140,14 @@ convnext_mlp_tc_kernel(const uint8_t* __restrict__ y_img, const uint8_t* __restr
     // ---------------- MMA issuer ----------------
     uint32_t chunk = 0;
     int it = 0;
+    long long* prof = blockIdx.x == 0 ? g_tc_prof : nullptr;
+    constexpr int prof_role = 0;
     for (long long tile = blockIdx.x; tile < tiles; tile += gridDim.x, ++it) {
       const int ab = it & 1;
+      TC_STAMP(0);
       mbar_wait(&bars.a_full[ab], (it >> 1) & 1);
       tc_fence_after();
+      TC_STAMP(1);
       const uint32_t a_addr = smem_u32(A0 + ab * kTileBytes);
       auto wait_w = [&]() -> uint32_t {
         const int ws = chunk % kWStages;
@@ -161,6 +171,7 @@ convnext_mlp_tc_kernel(const uint8_t* __restrict__ y_img, const uint8_t* __restr
         release_w();
         umma_commit(&bars.d1_full[b]);
         if (j == 3) umma_commit(&bars.a_empty[ab]);
+        TC_STAMP(2 + j);
       };
       auto gemm2 = [&](int j) {        // D2 (+)= H[j&1] . W2_j^T
         const int b = j & 1;
@@ -176,6 +187,7 @@ convnext_mlp_tc_kernel(const uint8_t* __restrict__ y_img, const uint8_t* __restr
         release_w();
         umma_commit(&bars.h_empty[b]);
         if (j == 3) umma_commit(&bars.d2_full);
+        TC_STAMP(6 + j);
       };
       gemm1(0); gemm1(1); gemm2(0); gemm1(2); gemm2(1); gemm1(3); gemm2(2); gemm2(3);
     }
@@ -185,13 +197,17 @@ convnext_mlp_tc_kernel(const uint8_t* __restrict__ y_img, const uint8_t* __restr
     const int m = q * 32 + lane;
     const uint32_t lane_addr = (uint32_t)(q * 32) << 16;
     int it = 0;
+    long long* prof = (blockIdx.x == 0 && threadIdx.x == kEpiWarp0 * 32) ? g_tc_prof : nullptr;
+    constexpr int prof_role = 1;
     for (long long tile = blockIdx.x; tile < tiles; tile += gridDim.x, ++it) {
+      TC_STAMP(0);
       for (int j = 0; j < 4; ++j) {
         const int b = j & 1;
         const uint32_t use = (uint32_t)it * 2 + (j >> 1);
         mbar_wait(&bars.d1_full[b], use & 1);
         mbar_wait(&bars.h_empty[b], (use & 1) ^ 1);
         tc_fence_after();
+        TC_STAMP(1 + 2 * j);
         float v[32];
         tmem_ld32(tmem + lane_addr + b * 128 + cgi * 32, v);
         // hidden unit k = cgi*32 .. +31 of this 128-slice -> slab cgi>>1, chunks (cgi&1)*4 .. +3
@@ -204,10 +220,20 @@ convnext_mlp_tc_kernel(const uint8_t* __restrict__ y_img, const uint8_t* __restr
           mbar_arrive(&bars.d1_empty[b]);
           mbar_arrive(&bars.h_full[b]);
         }
+        TC_STAMP(2 + 2 * j);
       }
+      // residual row segment (32 channels = 128 B of this thread's row): fetched before the accumulator is
+      // ready so the HBM latency hides under the last GEMM
+      const long long row = tile * kTileM + m;
+      const int c0 = cgi * 32;
+      float* hp = h + (size_t)(row < rows ? row : 0) * kC + c0;
+      float hv[4][8];
+#pragma unroll
+      for (int i = 0; i < 4; ++i) ldg256(hp + 8 * i, hv[i]);
+      TC_STAMP(9);
       mbar_wait(&bars.d2_full, it & 1);
       tc_fence_after();
-      const long long row = tile * kTileM + m;
+      TC_STAMP(10);
       {
         float v[32];
         tmem_ld32(tmem + lane_addr + 256 + cgi * 32, v);
@@ -215,21 +241,25 @@ convnext_mlp_tc_kernel(const uint8_t* __restrict__ y_img, const uint8_t* __restr
         __syncwarp();
         if (lane == 0) mbar_arrive(&bars.d2_empty);       // accumulators are in registers: release D2 early
         if (row < rows) {
-          const int c0 = cgi * 32;
-          float* hp = h + (size_t)row * kC + c0;
 #pragma unroll
-          for (int i = 0; i < 8; ++i) {
-            float4 hv = *reinterpret_cast<float4*>(hp + 4 * i);
-            const float4 bb = __ldg(reinterpret_cast<const float4*>(b2 + c0 + 4 * i));
-            const float4 ls = __ldg(reinterpret_cast<const float4*>(layer_scale + c0 + 4 * i));
-            hv.x = fmaf(ls.x, v[4 * i + 0] + bb.x, hv.x);
-            hv.y = fmaf(ls.y, v[4 * i + 1] + bb.y, hv.y);
-            hv.z = fmaf(ls.z, v[4 * i + 2] + bb.z, hv.z);
-            hv.w = fmaf(ls.w, v[4 * i + 3] + bb.w, hv.w);
-            *reinterpret_cast<float4*>(hp + 4 * i) = hv;
+          for (int i = 0; i < 4; ++i) {
+            const float4 b0 = __ldg(reinterpret_cast<const float4*>(b2 + c0 + 8 * i));
+            const float4 b1 = __ldg(reinterpret_cast<const float4*>(b2 + c0 + 8 * i + 4));
+            const float4 l0 = __ldg(reinterpret_cast<const float4*>(layer_scale + c0 + 8 * i));
+            const float4 l1 = __ldg(reinterpret_cast<const float4*>(layer_scale + c0 + 8 * i + 4));
+            hv[i][0] = fmaf(l0.x, v[8 * i + 0] + b0.x, hv[i][0]);
+            hv[i][1] = fmaf(l0.y, v[8 * i + 1] + b0.y, hv[i][1]);
+            hv[i][2] = fmaf(l0.z, v[8 * i + 2] + b0.z, hv[i][2]);
+            hv[i][3] = fmaf(l0.w, v[8 * i + 3] + b0.w, hv[i][3]);
+            hv[i][4] = fmaf(l1.x, v[8 * i + 4] + b1.x, hv[i][4]);
+            hv[i][5] = fmaf(l1.y, v[8 * i + 5] + b1.y, hv[i][5]);
+            hv[i][6] = fmaf(l1.z, v[8 * i + 6] + b1.z, hv[i][6]);
+            hv[i][7] = fmaf(l1.w, v[8 * i + 7] + b1.w, hv[i][7]);
+            stg256(hp + 8 * i, hv[i]);
           }
         }
       }
+      TC_STAMP(11);
     }
   }
   tc_fence_before();
@@ -243,12 +273,6 @@ convnext_mlp_tc_kernel(const uint8_t* __restrict__ y_img, const uint8_t* __restr
 // =================================================================================================
 // K3 + K4a  edge pipeline
 // =================================================================================================
-__device__ long long* g_tc_prof = nullptr;   // debug: per-phase clock64 stamps of CTA 0 (scratch/prof_tc.py)
-#define TC_STAMP(slot)                                                                     \
-  do {                                                                                      \
-    if (prof && it < 6) prof[(it * 2 + prof_role) * 16 + (slot)] = clock64();               \
-  } while (0)
-
 namespace edge {
 constexpr int kChunkBytes = 16384;      // [128 rows x 64 K] bf16 = 1 slab
 constexpr int kStages = 4;

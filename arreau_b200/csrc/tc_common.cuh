@@ -133,6 +133,18 @@ __device__ __forceinline__ float gelu_fast(float x) {
   return fmaf(hx, t, hx);
 }
 
+// 32-byte global accesses (sm_100: LDG.256 / STG.256): one full sector per thread and instruction
+__device__ __forceinline__ void ldg256(const float* p, float (&v)[8]) {
+  asm volatile("ld.global.v8.f32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+               : "=f"(v[0]), "=f"(v[1]), "=f"(v[2]), "=f"(v[3]), "=f"(v[4]), "=f"(v[5]), "=f"(v[6]), "=f"(v[7])
+               : "l"(p));
+}
+__device__ __forceinline__ void stg256(float* p, const float (&v)[8]) {
+  asm volatile("st.global.v8.f32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8};" ::"l"(p), "f"(v[0]), "f"(v[1]), "f"(v[2]), "f"(v[3]),
+               "f"(v[4]), "f"(v[5]), "f"(v[6]), "f"(v[7])
+               : "memory");
+}
+
 __device__ __forceinline__ uint32_t pack_bf16(float lo, float hi) {
   const __nv_bfloat162 v = __floats2bfloat162_rn(lo, hi);
   return *reinterpret_cast<const uint32_t*>(&v);
