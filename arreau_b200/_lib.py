@@ -32,7 +32,7 @@ class Weights(C.Structure):
 
 
 class Workspace(C.Structure):
-    _fields_ = [("h", vp), ("y", vp), ("kernels", vp), ("acc", vp), ("x1_debug", vp), ("x2_debug", vp),
+    _fields_ = [("h", vp), ("y", vp), ("kernels", vp), ("acc", vp), ("x1", vp), ("x1_debug", vp), ("x2_debug", vp),
                 ("h_debug", vp), ("edge_capacity", i64)]
 
 

@@ -268,7 +268,6 @@ edge_kernels_simt_kernel(const double* __restrict__ dir, const double* __restric
 // K4b + K5 + LayerNorm: receiver-sorted CSR reduction, fiber conv, norm.  Deterministic.
 // 128 threads: warp og owns orientations og*4..+3, lane cg owns channels cg*4..+3.
 // ------------------------------------------------------------------------------------------------
-constexpr int kMsgNodes = 4;
 
 // Channels 4*cg .. +3 of kernel row (e, o).  fp32 kernels are plain [e][o][c]; bf16 kernels (tcgen05 path) keep
 // the 16-byte chunk k of a row at chunk position k ^ o (so the producing kernel can stage and bulk-store its
@@ -285,134 +284,138 @@ __device__ __forceinline__ float4 load_kernel4(const __nv_bfloat16* row, int cg,
   return make_float4(fa.x, fa.y, fb.x, fb.y);
 }
 
-template <typename KT, typename YT>
-__global__ void __launch_bounds__(128, 6)
-message_fiber_norm_kernel(const KT* __restrict__ kern, const float* __restrict__ h, const int32_t* __restrict__ row_ptr,
-                          const int32_t* __restrict__ src, const float* __restrict__ fk,
-                          const float* __restrict__ bias, const float* __restrict__ ln_w,
-                          const float* __restrict__ ln_b, int N, YT* __restrict__ y, float* __restrict__ x1_dbg,
-                          float* __restrict__ x2_dbg) {
-  __shared__ __align__(16) float x1s[kMsgNodes][kO][kC];
-  const int tid = threadIdx.x, og = tid >> 5, cg = tid & 31;
-  const int node0 = blockIdx.x * kMsgNodes;
-  // ---- phase 1: x1[node][o][c] = sum over the node's edges (fixed CSR order) of kernel * h[src] ----
-#pragma unroll 1
-  for (int nb = 0; nb < kMsgNodes; ++nb) {
-    const int node = node0 + nb;
-    float4 a[4];
+// K4b  message_gather_kernel: one warp per (receiver, orientation), lane = 4 channels.
+//        x1[i][o][c] = sum over the receiver's edges (fixed CSR order -> deterministic, no atomics) of
+//        kernel[e][o][c] * h[src_e][o][c]; 8 edges (16 independent 8/16-byte loads per lane) in flight.
+// K5   fiber_norm_kernel: persistent CTAs of 16 warps; thread (warp p, lane cg) keeps its 16 fiber-kernel values
+//        fk[.][p][4cg..] in registers for the whole kernel and streams x1 rows (coalesced 512-byte rows):
+//        x2[i][p][c] = (1/O) sum_o x1[i][o][c] fk[o][p][c] + bias[c], then LayerNorm over c as a warp reduction.
+constexpr int kGatherWarps = 8;
+
+template <typename KT>
+__global__ void __launch_bounds__(kGatherWarps * 32)
+message_gather_kernel(const KT* __restrict__ kern, const float* __restrict__ h, const int32_t* __restrict__ row_ptr,
+                      const int32_t* __restrict__ src, long long rows, float* __restrict__ x1) {
+  const long long r = (long long)blockIdx.x * kGatherWarps + (threadIdx.x >> 5);   // row = node * kO + o
+  if (r >= rows) return;
+  const int cg = threadIdx.x & 31;
+  const int node = (int)(r >> 4), o = (int)(r & (kO - 1));
+  const int e0 = row_ptr[node], e1 = row_ptr[node + 1];
+  float4 a = make_float4(0.f, 0.f, 0.f, 0.f);
+  int e = e0;
+  for (; e + 8 <= e1; e += 8) {
+    int sidx[8];
+    float4 kv[8], hv[8];
 #pragma unroll
-    for (int oo = 0; oo < 4; ++oo) a[oo] = make_float4(0.f, 0.f, 0.f, 0.f);
-    if (node < N) {
-      const int e0 = row_ptr[node], e1 = row_ptr[node + 1];
-      int e = e0;
-      for (; e + 1 < e1; e += 2) {       // two edges in flight: 16 independent 16-byte loads per thread
-        const int s0 = src[e], s1 = src[e + 1];
-        const KT* kp0 = kern + ((size_t)e * kO + og * 4) * kC;
-        const KT* kp1 = kp0 + kO * kC;
-        const float* hp0 = h + ((size_t)s0 * kO + og * 4) * kC + cg * 4;
-        const float* hp1 = h + ((size_t)s1 * kO + og * 4) * kC + cg * 4;
-        float4 k0[4], k1[4], h0[4], h1[4];
+    for (int u = 0; u < 8; ++u) sidx[u] = __ldg(src + e + u);
 #pragma unroll
-        for (int oo = 0; oo < 4; ++oo) {
-          k0[oo] = load_kernel4(kp0 + oo * kC, cg, og * 4 + oo);
-          k1[oo] = load_kernel4(kp1 + oo * kC, cg, og * 4 + oo);
-          h0[oo] = *reinterpret_cast<const float4*>(hp0 + oo * kC);
-          h1[oo] = *reinterpret_cast<const float4*>(hp1 + oo * kC);
-        }
-#pragma unroll
-        for (int oo = 0; oo < 4; ++oo) {   // edge e then e+1: the reference order of the sum
-          a[oo].x = fmaf(k0[oo].x, h0[oo].x, a[oo].x);
-          a[oo].y = fmaf(k0[oo].y, h0[oo].y, a[oo].y);
-          a[oo].z = fmaf(k0[oo].z, h0[oo].z, a[oo].z);
-          a[oo].w = fmaf(k0[oo].w, h0[oo].w, a[oo].w);
-          a[oo].x = fmaf(k1[oo].x, h1[oo].x, a[oo].x);
-          a[oo].y = fmaf(k1[oo].y, h1[oo].y, a[oo].y);
-          a[oo].z = fmaf(k1[oo].z, h1[oo].z, a[oo].z);
-          a[oo].w = fmaf(k1[oo].w, h1[oo].w, a[oo].w);
-        }
-      }
-      if (e < e1) {
-        const int s0 = src[e];
-        const KT* kp0 = kern + ((size_t)e * kO + og * 4) * kC;
-        const float* hp0 = h + ((size_t)s0 * kO + og * 4) * kC + cg * 4;
-#pragma unroll
-        for (int oo = 0; oo < 4; ++oo) {
-          const float4 kv = load_kernel4(kp0 + oo * kC, cg, og * 4 + oo);
-          const float4 hv = *reinterpret_cast<const float4*>(hp0 + oo * kC);
-          a[oo].x = fmaf(kv.x, hv.x, a[oo].x);
-          a[oo].y = fmaf(kv.y, hv.y, a[oo].y);
-          a[oo].z = fmaf(kv.z, hv.z, a[oo].z);
-          a[oo].w = fmaf(kv.w, hv.w, a[oo].w);
-        }
-      }
+    for (int u = 0; u < 8; ++u) {
+      kv[u] = load_kernel4(kern + ((size_t)(e + u) * kO + o) * kC, cg, o);
+      hv[u] = *reinterpret_cast<const float4*>(h + ((size_t)sidx[u] * kO + o) * kC + cg * 4);
     }
 #pragma unroll
-    for (int oo = 0; oo < 4; ++oo) {
-      *reinterpret_cast<float4*>(&x1s[nb][og * 4 + oo][cg * 4]) = a[oo];
-      if (x1_dbg && node < N)
-        *reinterpret_cast<float4*>(x1_dbg + ((size_t)node * kO + og * 4 + oo) * kC + cg * 4) = a[oo];
+    for (int u = 0; u < 8; ++u) {
+      a.x = fmaf(kv[u].x, hv[u].x, a.x);
+      a.y = fmaf(kv[u].y, hv[u].y, a.y);
+      a.z = fmaf(kv[u].z, hv[u].z, a.z);
+      a.w = fmaf(kv[u].w, hv[u].w, a.w);
     }
   }
-  __syncthreads();
-  // ---- phase 2: x2[nb][p][c] = (1/O) sum_o x1[nb][o][c] * fk[o][p][c] + bias[c]; LayerNorm; one output
-  // orientation p at a time so only 4 float4 accumulators are live (occupancy) ----
+  for (; e < e1; ++e) {
+    const float4 kv = load_kernel4(kern + ((size_t)e * kO + o) * kC, cg, o);
+    const float4 hv = *reinterpret_cast<const float4*>(h + ((size_t)__ldg(src + e) * kO + o) * kC + cg * 4);
+    a.x = fmaf(kv.x, hv.x, a.x);
+    a.y = fmaf(kv.y, hv.y, a.y);
+    a.z = fmaf(kv.z, hv.z, a.z);
+    a.w = fmaf(kv.w, hv.w, a.w);
+  }
+  *reinterpret_cast<float4*>(x1 + (size_t)r * kC + cg * 4) = a;
+}
+
+constexpr int kFiberThreads = 512;
+constexpr int kFiberStages = 3;
+constexpr int kFiberNB = 2;     // nodes per pipeline stage
+
+template <typename YT>
+__device__ __forceinline__ void store_y_row(YT* __restrict__ y, size_t row, int cg, const float4& r) {
+  if constexpr (sizeof(YT) == 4) {
+    *reinterpret_cast<float4*>(y + row * kC + cg * 4) = r;
+  } else {
+    // bf16 y goes straight into the UMMA operand image of the ConvNext MLP kernel: 128-row tiles of
+    // 32 KB, two 64-channel slabs of 128-byte rows, 16-byte chunks XOR-swizzled by (row & 7)
+    // (csrc/tc_common.cuh), so that kernel fetches a tile with one bulk copy.
+    const int rr = (int)(row & 127), c0 = cg * 4;
+    uint8_t* tile = reinterpret_cast<uint8_t*>(y) + (row >> 7) * 32768;
+    const int off = (c0 >> 6) * 16384 + rr * 128 + (((((c0 & 63) >> 3) ^ (rr & 7)) << 4) | ((c0 & 7) << 1));
+    __nv_bfloat162 p0 = __floats2bfloat162_rn(r.x, r.y), p1 = __floats2bfloat162_rn(r.z, r.w);
+    uint2 raw;
+    raw.x = *reinterpret_cast<unsigned*>(&p0);
+    raw.y = *reinterpret_cast<unsigned*>(&p1);
+    *reinterpret_cast<uint2*>(tile + off) = raw;
+  }
+}
+
+template <typename YT>
+__global__ void __launch_bounds__(kFiberThreads, 1)
+fiber_norm_kernel(const float* __restrict__ x1, const float* __restrict__ fk, const float* __restrict__ bias,
+                  const float* __restrict__ ln_w, const float* __restrict__ ln_b, int N, YT* __restrict__ y,
+                  float* __restrict__ x2_dbg) {
+  // kFiberNB nodes' x1 (16 x 128 fp32 = 8 KB each = one 16-byte cp.async per thread and node) per stage
+  __shared__ __align__(16) float xs[kFiberStages][kFiberNB][kO * kC];
+  const int p = threadIdx.x >> 5, cg = threadIdx.x & 31;
+  float4 fkr[kO];
+#pragma unroll
+  for (int o = 0; o < kO; ++o) fkr[o] = __ldg(reinterpret_cast<const float4*>(fk + ((size_t)(o * kO + p)) * kC + cg * 4));
   const float4 bv = *reinterpret_cast<const float4*>(bias + cg * 4);
   const float4 gw = *reinterpret_cast<const float4*>(ln_w + cg * 4);
   const float4 gb = *reinterpret_cast<const float4*>(ln_b + cg * 4);
   constexpr float inv_o = 1.0f / kO;
-#pragma unroll 1
-  for (int pp = 0; pp < 4; ++pp) {
-    const int p = og * 4 + pp;
-    float4 x2[kMsgNodes];
+  // this CTA's node groups: g = blockIdx.x, + gridDim.x, ... (group g = nodes kFiberNB*g ..)
+  const int groups = (N + kFiberNB - 1) / kFiberNB;
+  auto issue = [&](int k) {
+    const long long g = (long long)blockIdx.x + (long long)k * gridDim.x;
+    if (g < groups) {
 #pragma unroll
-    for (int nb = 0; nb < kMsgNodes; ++nb) x2[nb] = make_float4(0.f, 0.f, 0.f, 0.f);
-#pragma unroll 4
-    for (int o = 0; o < kO; ++o) {
-      const float4 f = __ldg(reinterpret_cast<const float4*>(fk + ((size_t)(o * kO + p)) * kC + cg * 4));
-#pragma unroll
-      for (int nb = 0; nb < kMsgNodes; ++nb) {
-        const float4 xv = *reinterpret_cast<const float4*>(&x1s[nb][o][cg * 4]);
-        x2[nb].x = fmaf(xv.x, f.x, x2[nb].x);
-        x2[nb].y = fmaf(xv.y, f.y, x2[nb].y);
-        x2[nb].z = fmaf(xv.z, f.z, x2[nb].z);
-        x2[nb].w = fmaf(xv.w, f.w, x2[nb].w);
+      for (int nb = 0; nb < kFiberNB; ++nb) {
+        const long long node = g * kFiberNB + nb;
+        if (node < N) cp_async16(&xs[k % kFiberStages][nb][threadIdx.x * 4], x1 + (size_t)node * kO * kC + threadIdx.x * 4);
       }
     }
+    cp_async_commit();
+  };
 #pragma unroll
-    for (int nb = 0; nb < kMsgNodes; ++nb) {
-      const int node = node0 + nb;
-      float4 v = x2[nb];
-      v.x = v.x * inv_o + bv.x;
-      v.y = v.y * inv_o + bv.y;
-      v.z = v.z * inv_o + bv.z;
-      v.w = v.w * inv_o + bv.w;
-      if (x2_dbg && node < N)
-        *reinterpret_cast<float4*>(x2_dbg + ((size_t)node * kO + p) * kC + cg * 4) = v;
+  for (int k = 0; k < kFiberStages - 1; ++k) issue(k);
+  int k = 0;
+  for (int g = blockIdx.x; g < groups; g += gridDim.x, ++k) {
+    cp_async_wait<kFiberStages - 2>();
+    __syncthreads();                       // stage k has landed for every thread; stage k-1 is free again
+    issue(k + kFiberStages - 1);
+#pragma unroll 1
+    for (int nb = 0; nb < kFiberNB; ++nb) {          // one node at a time: the 16 fk registers leave room for one accumulator set
+      const int node = g * kFiberNB + nb;
+      if (node >= N) break;
+      float4 t = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+      for (int o = 0; o < kO; ++o) {
+        const float4 xv = *reinterpret_cast<const float4*>(&xs[k % kFiberStages][nb][o * kC + cg * 4]);
+        t.x = fmaf(xv.x, fkr[o].x, t.x);
+        t.y = fmaf(xv.y, fkr[o].y, t.y);
+        t.z = fmaf(xv.z, fkr[o].z, t.z);
+        t.w = fmaf(xv.w, fkr[o].w, t.w);
+      }
+      t.x = t.x * inv_o + bv.x;
+      t.y = t.y * inv_o + bv.y;
+      t.z = t.z * inv_o + bv.z;
+      t.w = t.w * inv_o + bv.w;
+      if (x2_dbg) *reinterpret_cast<float4*>(x2_dbg + ((size_t)node * kO + p) * kC + cg * 4) = t;
       // LayerNorm over the 128 channels held by this warp (biased variance, eps 1e-5)
-      const float mean = warp_sum((v.x + v.y) + (v.z + v.w)) * (1.0f / kC);
-      const float dx = v.x - mean, dy = v.y - mean, dz = v.z - mean, dw = v.w - mean;
+      const float mean = warp_sum((t.x + t.y) + (t.z + t.w)) * (1.0f / kC);
+      const float dx = t.x - mean, dy = t.y - mean, dz = t.z - mean, dw = t.w - mean;
       const float var = warp_sum((dx * dx + dy * dy) + (dz * dz + dw * dw)) * (1.0f / kC);
       const float rstd = 1.0f / sqrtf(var + 1e-5f);
-      const float4 r = make_float4(dx * rstd * gw.x + gb.x, dy * rstd * gw.y + gb.y, dz * rstd * gw.z + gb.z,
-                                   dw * rstd * gw.w + gb.w);
-      if (node < N) {
-        if constexpr (sizeof(YT) == 4) {
-          *reinterpret_cast<float4*>(y + ((size_t)node * kO + p) * kC + cg * 4) = r;
-        } else {
-          // bf16 y goes straight into the UMMA operand image of the ConvNext MLP kernel: 128-row tiles of
-          // 32 KB, two 64-channel slabs of 128-byte rows, 16-byte chunks XOR-swizzled by (row & 7)
-          // (csrc/tc_common.cuh), so that kernel fetches a tile with one bulk copy.
-          const size_t row = (size_t)node * kO + p;
-          const int rr = (int)(row & 127), c0 = cg * 4;
-          uint8_t* tile = reinterpret_cast<uint8_t*>(y) + (row >> 7) * 32768;
-          const int off = (c0 >> 6) * 16384 + rr * 128 + (((((c0 & 63) >> 3) ^ (rr & 7)) << 4) | ((c0 & 7) << 1));
-          __nv_bfloat162 p0 = __floats2bfloat162_rn(r.x, r.y), p1 = __floats2bfloat162_rn(r.z, r.w);
-          uint2 raw;
-          raw.x = *reinterpret_cast<unsigned*>(&p0);
-          raw.y = *reinterpret_cast<unsigned*>(&p1);
-          *reinterpret_cast<uint2*>(tile + off) = raw;
-        }
-      }
+      store_y_row(y, (size_t)node * kO + p, cg,
+                  make_float4(dx * rstd * gw.x + gb.x, dy * rstd * gw.y + gb.y, dz * rstd * gw.z + gb.z,
+                              dw * rstd * gw.w + gb.w));
     }
   }
 }
@@ -644,27 +647,24 @@ extern "C" int arreau_edge_kernels_f32(const double* dir, const double* dist, co
 extern "C" int arreau_message_fiber_norm(const void* kernels, int32_t kernels_bf16, const float* h,
                                          const int32_t* row_ptr, const int32_t* src, const float* fiber_kernel,
                                          const float* conv_bias, const float* ln_w, const float* ln_b, int32_t N,
-                                         void* y, int32_t y_bf16, float* x1_debug, float* x2_debug, void* stream) {
+                                         void* y, int32_t y_bf16, float* x1, float* x2_debug, void* stream) {
   if (N == 0) return ARREAU_OK;
-  if (!h || !row_ptr || !fiber_kernel || !conv_bias || !ln_w || !ln_b || !y) return ARREAU_ERR_NULL;
+  if (!h || !row_ptr || !fiber_kernel || !conv_bias || !ln_w || !ln_b || !y || !x1) return ARREAU_ERR_NULL;
   if (N < 0) return ARREAU_ERR_BAD_SHAPE;
-  const int grid = (N + kMsgNodes - 1) / kMsgNodes;
   cudaStream_t s = (cudaStream_t)stream;
-  if (!kernels_bf16 && !y_bf16)
-    message_fiber_norm_kernel<float, float><<<grid, 128, 0, s>>>((const float*)kernels, h, row_ptr, src, fiber_kernel,
-                                                                 conv_bias, ln_w, ln_b, N, (float*)y, x1_debug, x2_debug);
-  else if (kernels_bf16 && y_bf16)
-    message_fiber_norm_kernel<__nv_bfloat16, __nv_bfloat16><<<grid, 128, 0, s>>>(
-        (const __nv_bfloat16*)kernels, h, row_ptr, src, fiber_kernel, conv_bias, ln_w, ln_b, N, (__nv_bfloat16*)y,
-        x1_debug, x2_debug);
-  else if (kernels_bf16)
-    message_fiber_norm_kernel<__nv_bfloat16, float><<<grid, 128, 0, s>>>((const __nv_bfloat16*)kernels, h, row_ptr, src,
-                                                                         fiber_kernel, conv_bias, ln_w, ln_b, N,
-                                                                         (float*)y, x1_debug, x2_debug);
+  const long long rows = (long long)N * kO;
+  const unsigned ggrid = (unsigned)((rows + kGatherWarps - 1) / kGatherWarps);
+  if (kernels_bf16)
+    message_gather_kernel<__nv_bfloat16><<<ggrid, kGatherWarps * 32, 0, s>>>((const __nv_bfloat16*)kernels, h, row_ptr, src, rows, x1);
   else
-    message_fiber_norm_kernel<float, __nv_bfloat16><<<grid, 128, 0, s>>>((const float*)kernels, h, row_ptr, src,
-                                                                         fiber_kernel, conv_bias, ln_w, ln_b, N,
-                                                                         (__nv_bfloat16*)y, x1_debug, x2_debug);
+    message_gather_kernel<float><<<ggrid, kGatherWarps * 32, 0, s>>>((const float*)kernels, h, row_ptr, src, rows, x1);
+  CUDA_LAUNCH_CHECK();
+  const int fgroups = (N + kFiberNB - 1) / kFiberNB;
+  const int fgrid = fgroups < num_sms() ? fgroups : num_sms();
+  if (y_bf16)
+    fiber_norm_kernel<__nv_bfloat16><<<fgrid, kFiberThreads, 0, s>>>(x1, fiber_kernel, conv_bias, ln_w, ln_b, N, (__nv_bfloat16*)y, x2_debug);
+  else
+    fiber_norm_kernel<float><<<fgrid, kFiberThreads, 0, s>>>(x1, fiber_kernel, conv_bias, ln_w, ln_b, N, (float*)y, x2_debug);
   CUDA_LAUNCH_CHECK();
   return ARREAU_OK;
 }

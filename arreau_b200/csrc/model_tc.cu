@@ -69,6 +69,19 @@ __device__ __forceinline__ void gelu_store32(const float (&v)[32], const float* 
   }
 }
 
+// 32 accumulator columns -> + bias -> GELU -> four packed bf16 chunks (registers only)
+__device__ __forceinline__ void gelu_pack32(const float (&v)[32], const float* __restrict__ bias_s, uint4 (&pk)[4]) {
+#pragma unroll
+  for (int cc = 0; cc < 4; ++cc) {
+    const float4 b0 = *reinterpret_cast<const float4*>(bias_s + cc * 8);
+    const float4 b1 = *reinterpret_cast<const float4*>(bias_s + cc * 8 + 4);
+    pk[cc].x = pack_bf16(gelu_fast(v[cc * 8 + 0] + b0.x), gelu_fast(v[cc * 8 + 1] + b0.y));
+    pk[cc].y = pack_bf16(gelu_fast(v[cc * 8 + 2] + b0.z), gelu_fast(v[cc * 8 + 3] + b0.w));
+    pk[cc].z = pack_bf16(gelu_fast(v[cc * 8 + 4] + b1.x), gelu_fast(v[cc * 8 + 5] + b1.y));
+    pk[cc].w = pack_bf16(gelu_fast(v[cc * 8 + 6] + b1.z), gelu_fast(v[cc * 8 + 7] + b1.w));
+  }
+}
+
 // =================================================================================================
 // K6  ConvNext channel MLP
 // =================================================================================================
@@ -197,7 +210,8 @@ convnext_mlp_tc_kernel(const uint8_t* __restrict__ y_img, const uint8_t* __restr
     const int m = q * 32 + lane;
     const uint32_t lane_addr = (uint32_t)(q * 32) << 16;
     int it = 0;
-    long long* prof = (blockIdx.x == 0 && threadIdx.x == kEpiWarp0 * 32) ? g_tc_prof : nullptr;
+    const bool is_issuer = threadIdx.x == kEpiWarp0 * 32;
+    long long* prof = (blockIdx.x == 0 && is_issuer) ? g_tc_prof : nullptr;
     constexpr int prof_role = 1;
     for (long long tile = blockIdx.x; tile < tiles; tile += gridDim.x, ++it) {
       TC_STAMP(0);
@@ -210,9 +224,24 @@ convnext_mlp_tc_kernel(const uint8_t* __restrict__ y_img, const uint8_t* __restr
         TC_STAMP(1 + 2 * j);
         float v[32];
         tmem_ld32(tmem + lane_addr + b * 128 + cgi * 32, v);
-        // hidden unit k = cgi*32 .. +31 of this 128-slice -> slab cgi>>1, chunks (cgi&1)*4 .. +3
-        gelu_store32<true, false>(v, s_b1 + j * 128 + cgi * 32, 1.0f,
-                                  H0 + b * kTileBytes + (cgi >> 1) * 16384 + m * kRowBytes, (cgi & 1) * 4, m);
+        uint4 pk[4];
+        gelu_pack32(v, s_b1 + j * 128 + cgi * 32, pk);
+        if (j < 2 && it > 0) {
+          // H[j] doubled as the staging area of the previous tile's residual reduce (rows 64j .. 64j+63): its bulk
+          // reduce must have finished reading shared memory before the buffer is rewritten
+          if (is_issuer) {
+            if (j == 0) asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");
+            else asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+          }
+          asm volatile("bar.sync 1, %0;" ::"n"(kEpiThreads) : "memory");
+        }
+        {
+          // hidden unit k = cgi*32 .. +31 of this 128-slice -> slab cgi>>1, chunks (cgi&1)*4 .. +3
+          uint8_t* hrow = H0 + b * kTileBytes + (cgi >> 1) * 16384 + m * kRowBytes;
+#pragma unroll
+          for (int cc = 0; cc < 4; ++cc)
+            *reinterpret_cast<uint4*>(hrow + ((((cgi & 1) * 4 + cc) ^ (m & 7)) << 4)) = pk[cc];
+        }
         tc_fence_before();
         fence_proxy_async();
         __syncwarp();
@@ -222,45 +251,66 @@ convnext_mlp_tc_kernel(const uint8_t* __restrict__ y_img, const uint8_t* __restr
         }
         TC_STAMP(2 + 2 * j);
       }
-      // residual row segment (32 channels = 128 B of this thread's row): fetched before the accumulator is
-      // ready so the HBM latency hides under the last GEMM
-      const long long row = tile * kTileM + m;
-      const int c0 = cgi * 32;
-      float* hp = h + (size_t)(row < rows ? row : 0) * kC + c0;
-      float hv[4][8];
-#pragma unroll
-      for (int i = 0; i < 4; ++i) ldg256(hp + 8 * i, hv[i]);
       TC_STAMP(9);
       mbar_wait(&bars.d2_full, it & 1);
       tc_fence_after();
       TC_STAMP(10);
       {
+        // h += layer_scale * (D2 + b2): the update tile [128 rows x 128 ch] fp32 is 64 KB contiguous in HBM.  It is
+        // staged in the two (now idle) H buffers and added into h by the TMA engine (cp.reduce.async.bulk .add.f32:
+        // every element is added exactly once, so the result is deterministic) -- no uncoalesced read-modify-write
+        // from the SM.  A thread owns 8 16-byte chunks of its row; it writes them in a lane-rotated order
+        // (chunk (s + lane) & 7 at step s), which spreads a warp over all banks (4-way = optimal for 512 B).
         float v[32];
         tmem_ld32(tmem + lane_addr + 256 + cgi * 32, v);
         tc_fence_before();
         __syncwarp();
         if (lane == 0) mbar_arrive(&bars.d2_empty);       // accumulators are in registers: release D2 early
-        if (row < rows) {
+        const int c0 = cgi * 32;
+        float4 d[8];
 #pragma unroll
-          for (int i = 0; i < 4; ++i) {
-            const float4 b0 = __ldg(reinterpret_cast<const float4*>(b2 + c0 + 8 * i));
-            const float4 b1 = __ldg(reinterpret_cast<const float4*>(b2 + c0 + 8 * i + 4));
-            const float4 l0 = __ldg(reinterpret_cast<const float4*>(layer_scale + c0 + 8 * i));
-            const float4 l1 = __ldg(reinterpret_cast<const float4*>(layer_scale + c0 + 8 * i + 4));
-            hv[i][0] = fmaf(l0.x, v[8 * i + 0] + b0.x, hv[i][0]);
-            hv[i][1] = fmaf(l0.y, v[8 * i + 1] + b0.y, hv[i][1]);
-            hv[i][2] = fmaf(l0.z, v[8 * i + 2] + b0.z, hv[i][2]);
-            hv[i][3] = fmaf(l0.w, v[8 * i + 3] + b0.w, hv[i][3]);
-            hv[i][4] = fmaf(l1.x, v[8 * i + 4] + b1.x, hv[i][4]);
-            hv[i][5] = fmaf(l1.y, v[8 * i + 5] + b1.y, hv[i][5]);
-            hv[i][6] = fmaf(l1.z, v[8 * i + 6] + b1.z, hv[i][6]);
-            hv[i][7] = fmaf(l1.w, v[8 * i + 7] + b1.w, hv[i][7]);
-            stg256(hp + 8 * i, hv[i]);
+        for (int i = 0; i < 8; ++i) {
+          const float4 bb = __ldg(reinterpret_cast<const float4*>(b2 + c0 + 4 * i));
+          const float4 ls = __ldg(reinterpret_cast<const float4*>(layer_scale + c0 + 4 * i));
+          d[i] = make_float4(ls.x * (v[4 * i + 0] + bb.x), ls.y * (v[4 * i + 1] + bb.y), ls.z * (v[4 * i + 2] + bb.z),
+                             ls.w * (v[4 * i + 3] + bb.w));
+        }
+        // barrel-rotate the 8 chunks by r = lane & 7 so that register slot s holds chunk (s + r) & 7
+        const int r = lane & 7;
+#pragma unroll
+        for (int sh = 4; sh >= 1; sh >>= 1) {
+          if (r & sh) {
+            float4 t[8];
+#pragma unroll
+            for (int i = 0; i < 8; ++i) t[i] = d[(i + sh) & 7];
+#pragma unroll
+            for (int i = 0; i < 8; ++i) d[i] = t[i];
+          }
+        }
+        uint8_t* srow = H0 + m * 512 + cgi * 128;
+#pragma unroll
+        for (int st = 0; st < 8; ++st) *reinterpret_cast<float4*>(srow + (((st + r) & 7) << 4)) = d[st];
+        fence_proxy_async();
+        asm volatile("bar.sync 1, %0;" ::"n"(kEpiThreads) : "memory");
+        if (is_issuer) {
+          const long long row0 = tile * kTileM;
+          const long long left = rows - row0;
+          const int valid = (int)(left < kTileM ? left : kTileM);
+#pragma unroll
+          for (int half = 0; half < 2; ++half) {
+            const int n = valid - half * 64 < 64 ? valid - half * 64 : 64;
+            if (n > 0)
+              asm volatile("cp.reduce.async.bulk.global.shared::cta.bulk_group.add.f32 [%0], [%1], %2;" ::"l"(
+                               h + (size_t)(row0 + half * 64) * kC),
+                           "r"(smem_u32(H0 + half * kTileBytes)), "r"((uint32_t)n * 512u)
+                           : "memory");
+            asm volatile("cp.async.bulk.commit_group;" ::: "memory");   // (possibly empty) group per half
           }
         }
       }
       TC_STAMP(11);
     }
+    if (is_issuer) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");   // every update has been added into h
   }
   tc_fence_before();
   __syncthreads();

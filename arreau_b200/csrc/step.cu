@@ -99,7 +99,7 @@ extern "C" int arreau_ponita_forward(const arreau_weights* w, const arreau_works
   if (!w || !ws) return ARREAU_ERR_NULL;
   if (N < 0 || G < 0) return ARREAU_ERR_BAD_SHAPE;
   if (N == 0) return ARREAU_OK;
-  if (!row_ptr || !ws->h || !ws->y || !ws->acc || (ws->edge_capacity > 0 && !ws->kernels)) return ARREAU_ERR_NULL;
+  if (!row_ptr || !ws->h || !ws->y || !ws->acc || !ws->x1 || (ws->edge_capacity > 0 && !ws->kernels)) return ARREAU_ERR_NULL;
   if (precision != ARREAU_PRECISION_FP32 && precision != ARREAU_PRECISION_BF16) return ARREAU_ERR_UNSUPPORTED;
   const bool bf16 = precision == ARREAU_PRECISION_BF16;
   const int Z = w->num_states;
@@ -124,7 +124,7 @@ extern "C" int arreau_ponita_forward(const arreau_weights* w, const arreau_works
                             : (const void*)((const float*)ws->kernels + (size_t)l * layer_elems);
     ARREAU_TRY(arreau_message_fiber_norm(kern, bf16, ws->h, row_ptr, src, w->fiber_kernel + (size_t)l * kO * kO * kC,
                                          w->conv_bias + l * kC, w->ln_w + l * kC, w->ln_b + l * kC, N, ws->y, bf16,
-                                         ws->x1_debug ? ws->x1_debug + l * node_elems : nullptr,
+                                         ws->x1_debug ? ws->x1_debug + l * node_elems : ws->x1,
                                          ws->x2_debug ? ws->x2_debug + l * node_elems : nullptr, stream));
     if (bf16)
       ARREAU_TRY(arreau_convnext_mlp_bf16(ws->y, (const uint8_t*)w->mlp_w_img + (size_t)l * 8 * 32768,

@@ -76,7 +76,7 @@ class DenoiseEngine:
         self.emb = (self.F - Z - 10) // 2
         self.x, self.vec = f32(N, self.F), f32(N, 4, 3)
         self.logits, self.score, self.len0 = f32(N, Z), f32(N, 3), f32(G, 3)
-        self.h, self.acc = f32(N, NUM_ORI, HIDDEN), f32(N, Z + 6)
+        self.h, self.acc, self.x1 = f32(N, NUM_ORI, HIDDEN), f32(N, Z + 6), f32(N, NUM_ORI, HIDDEN)
         if precision == "bf16":     # 128-row UMMA tile images (32 KB each), see arreau_message_fiber_norm
             self.y = torch.zeros(((N * NUM_ORI + 127) // 128) * 128 * HIDDEN, device=dev, dtype=torch.bfloat16)
         else:
@@ -117,6 +117,7 @@ class DenoiseEngine:
             self.x1_debug = self.x2_debug = self.h_debug = None
         ws = _lib.Workspace()
         ws.h, ws.y, ws.kernels, ws.acc = self.h.data_ptr(), self.y.data_ptr(), self.kernels.data_ptr(), self.acc.data_ptr()
+        ws.x1 = self.x1.data_ptr()
         ws.x1_debug, ws.x2_debug, ws.h_debug = _lib.ptr(self.x1_debug), _lib.ptr(self.x2_debug), _lib.ptr(self.h_debug)
         ws.edge_capacity = capacity
         self.ws = ws
@@ -306,7 +307,7 @@ class DenoiseEngine:
                 "arreau_message_fiber_norm", self.kernels[l].data_ptr(), int(bf16), self.h.data_ptr(),
                 self.row_ptr.data_ptr(), self.src.data_ptr(), w["fiber_kernel"][l].data_ptr(),
                 w["conv_bias"][l].data_ptr(), w["ln_w"][l].data_ptr(), w["ln_b"][l].data_ptr(), self.N,
-                self.y.data_ptr(), int(bf16), None, None, self.stream))
+                self.y.data_ptr(), int(bf16), self.x1.data_ptr(), None, self.stream))
             if bf16:
                 add("convnext_mlp", lambda l=l: _lib.call(
                     "arreau_convnext_mlp_bf16", self.y.data_ptr(), w["mlp_w_img"].data_ptr() + l * 8 * 32768,

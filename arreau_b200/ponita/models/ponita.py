@@ -136,13 +136,14 @@ class PonitaFiberBundle(nn.Module):
         cap = max(E, 1)
         f32 = lambda *s: torch.empty(*s, dtype=torch.float32, device=dev)  # noqa: E731
         ws = _lib.Workspace()
-        h, acc = f32(N, NUM_ORI, HIDDEN), f32(N, w.num_states + 6)
+        h, acc, x1 = f32(N, NUM_ORI, HIDDEN), f32(N, w.num_states + 6), f32(N, NUM_ORI, HIDDEN)
         if bf16:     # 128-row UMMA tile images
             y = torch.zeros(((N * NUM_ORI + 127) // 128) * 128 * HIDDEN, dtype=torch.bfloat16, device=dev)
         else:
             y = torch.empty(N, NUM_ORI, HIDDEN, dtype=torch.float32, device=dev)
         kern = torch.empty(LAYERS, cap, NUM_ORI, HIDDEN, dtype=torch.bfloat16 if bf16 else torch.float32, device=dev)
         ws.h, ws.y, ws.kernels, ws.acc, ws.edge_capacity = h.data_ptr(), y.data_ptr(), kern.data_ptr(), acc.data_ptr(), cap
+        ws.x1 = x1.data_ptr()
         logits, score, len0 = f32(N, w.num_states), f32(N, 3), f32(G, 3)
         xf = x.to(torch.float32).contiguous()
         vf = graph.vec.to(torch.float32).contiguous()

@@ -151,13 +151,13 @@ int arreau_edge_kernels_bf16(const double* dir, const double* dist, const double
  *         y = LayerNorm_C(x2) * ln_w + ln_b                              (convnext.py:25)
  * `kernels` is ONE layer's [edge_capacity,O,C] slab (f32, or bf16 when kernels_bf16 != 0);
  * fiber_kernel is that layer's [O,O,C].  y[N,O,C] is f32 row-major, or (y_bf16) bf16 in 128-row UMMA tile
- * images for arreau_convnext_mlp_bf16.  x1_debug/x2_debug
- * (f32 [N,O,C], may be NULL) receive the intermediates for the parity tests.
- * Deterministic receiver-sorted CSR reduction (fixed order, no atomics). */
+ * images for arreau_convnext_mlp_bf16.  x1 (f32 [N,O,C], required) is the workspace between the two
+ * launches (gather, then fiber conv + norm); x2_debug (f32 [N,O,C], may be NULL) receives x2 for the parity
+ * tests.  Deterministic receiver-sorted CSR reduction (fixed order, no atomics). */
 int arreau_message_fiber_norm(const void* kernels, int32_t kernels_bf16, const float* h, const int32_t* row_ptr,
                               const int32_t* src, const float* fiber_kernel, const float* conv_bias,
                               const float* ln_w, const float* ln_b, int32_t num_atoms_total, void* y,
-                              int32_t y_bf16, float* x1_debug, float* x2_debug, void* stream);
+                              int32_t y_bf16, float* x1, float* x2_debug, void* stream);
 
 /* K6: h <- h + layer_scale * (W2 gelu(W1 y + b1) + b2)   (convnext.py:26-32); rows = N*O.
  * _f32: w1_t[C,4C], w2_t[4C,C] f32.  _bf16: y_img = bf16 y as 128-row UMMA tile images (32 KB per tile, written
@@ -218,6 +218,7 @@ typedef struct arreau_workspace {
   void* y;          /* [N,O,C] f32 (fp32 path) or bf16 tile images, ceil(N*O/128)*32 KB (bf16 path) */
   void* kernels;    /* [L,edge_capacity,O,C] f32 or bf16                                     */
   float* acc;       /* [N,Z+6] f32                                                           */
+  float* x1;        /* [N,O,C] f32: message sums between the gather and the fiber conv       */
   float* x1_debug;  /* NULL, or [L,N,O,C] f32                                                */
   float* x2_debug;  /* NULL, or [L,N,O,C] f32                                                */
   float* h_debug;   /* NULL, or [L+1,N,O,C] f32 (h after the embedding and after each layer) */
