@@ -20,7 +20,7 @@ i64 = C.c_int64
 f64 = C.c_double
 
 ERRORS = {-1: "ARREAU_ERR_BAD_SHAPE", -2: "ARREAU_ERR_UNSUPPORTED", -3: "ARREAU_ERR_WORKSPACE", -4: "ARREAU_ERR_NULL"}
-PRECISION_FP32, PRECISION_BF16 = 0, 1
+PRECISION_FP32, PRECISION_FP16 = 0, 1
 
 
 class Weights(C.Structure):
@@ -66,10 +66,10 @@ SIGNATURES = {
     "arreau_fiber_kernel_precompute": [vp] * 8,
     "arreau_node_embed": [vp, vp, vp, vp, i32, i32, i32, vp, vp],
     "arreau_edge_kernels_f32": [vp, vp, vp, vp, vp, vp, i64, vp, vp, vp, vp, vp, f64, vp, vp],
-    "arreau_edge_kernels_bf16": [vp, vp, vp, vp, vp, vp, i64, vp, vp, vp, vp, f64, vp, vp],
+    "arreau_edge_kernels_f16": [vp, vp, vp, vp, vp, vp, i64, vp, vp, vp, vp, f64, vp, vp],
     "arreau_message_fiber_norm": [vp, i32, vp, vp, vp, vp, vp, vp, vp, i32, vp, i32, vp, vp, vp],
     "arreau_convnext_mlp_f32": [vp, vp, vp, vp, vp, vp, i64, vp, vp],
-    "arreau_convnext_mlp_bf16": [vp, vp, vp, vp, vp, i64, vp, vp],
+    "arreau_convnext_mlp_f16": [vp, vp, vp, vp, vp, i64, vp, vp],
     "arreau_readout_accumulate": [vp, vp, vp, vp, i32, i32, i32, vp, vp],
     "arreau_readout_finalize": [vp, vp, i32, i32, i32, i32, vp, vp, vp, vp],
     "arreau_ponita_forward": [C.POINTER(Weights), C.POINTER(Workspace), i32, vp, vp, vp, vp, vp, vp, vp, vp, vp,

@@ -1,7 +1,7 @@
 // K2-K7 of the Ponita fiber-bundle forward in fp32 (sm_100a, FFMA2 SIMT path).
 //
 // This is the fp32-grade path (parity within 1e-4 of the fp64 reference).  The dense contractions
-// run as shared-memory tiled SIMT GEMMs on packed FFMA2; the tcgen05 bf16 variants of the two
+// run as shared-memory tiled SIMT GEMMs on packed FFMA2; the tcgen05 fp16 variants of the two
 // GEMM-shaped kernels live in model_tc.cu and share every other kernel in this file.
 //
 //   node_embed_kernel          K2   position_orientation_graph.py:84-86 + ponita.py:98
@@ -10,7 +10,7 @@
 //   message_fiber_norm_kernel  K4b+K5 + LayerNorm   conv.py:115,126-133, convnext.py:25
 //   convnext_mlp_simt_kernel   K6   convnext.py:26-32
 //   readout_*_kernel           K7   ponita.py:105-117,152, to_from_sphere.py:10-14
-#include <cuda_bf16.h>
+#include <cuda_fp16.h>
 
 #include "common.cuh"
 
@@ -269,18 +269,18 @@ edge_kernels_simt_kernel(const double* __restrict__ dir, const double* __restric
 // 128 threads: warp og owns orientations og*4..+3, lane cg owns channels cg*4..+3.
 // ------------------------------------------------------------------------------------------------
 
-// Channels 4*cg .. +3 of kernel row (e, o).  fp32 kernels are plain [e][o][c]; bf16 kernels (tcgen05 path) keep
+// Channels 4*cg .. +3 of kernel row (e, o).  fp32 kernels are plain [e][o][c]; fp16 kernels (tcgen05 path) keep
 // the 16-byte chunk k of a row at chunk position k ^ o (so the producing kernel can stage and bulk-store its
 // tiles without shared-memory bank conflicts, csrc/model_tc.cu); a warp still reads whole 256-byte rows.
 __device__ __forceinline__ float4 load_kernel4(const float* row, int cg, int /*o*/) {
   return *reinterpret_cast<const float4*>(row + cg * 4);
 }
-__device__ __forceinline__ float4 load_kernel4(const __nv_bfloat16* row, int cg, int o) {
-  const __nv_bfloat16* p = row + ((((cg >> 1) ^ (o & 15)) << 3) | ((cg & 1) << 2));
+__device__ __forceinline__ float4 load_kernel4(const __half* row, int cg, int o) {
+  const __half* p = row + ((((cg >> 1) ^ (o & 15)) << 3) | ((cg & 1) << 2));
   const uint2 raw = *reinterpret_cast<const uint2*>(p);
-  const __nv_bfloat162 a = *reinterpret_cast<const __nv_bfloat162*>(&raw.x);
-  const __nv_bfloat162 b = *reinterpret_cast<const __nv_bfloat162*>(&raw.y);
-  const float2 fa = __bfloat1622float2(a), fb = __bfloat1622float2(b);
+  const __half2 a = *reinterpret_cast<const __half2*>(&raw.x);
+  const __half2 b = *reinterpret_cast<const __half2*>(&raw.y);
+  const float2 fa = __half22float2(a), fb = __half22float2(b);
   return make_float4(fa.x, fa.y, fb.x, fb.y);
 }
 
@@ -341,13 +341,13 @@ __device__ __forceinline__ void store_y_row(YT* __restrict__ y, size_t row, int 
   if constexpr (sizeof(YT) == 4) {
     *reinterpret_cast<float4*>(y + row * kC + cg * 4) = r;
   } else {
-    // bf16 y goes straight into the UMMA operand image of the ConvNext MLP kernel: 128-row tiles of
+    // fp16 y goes straight into the UMMA operand image of the ConvNext MLP kernel: 128-row tiles of
     // 32 KB, two 64-channel slabs of 128-byte rows, 16-byte chunks XOR-swizzled by (row & 7)
     // (csrc/tc_common.cuh), so that kernel fetches a tile with one bulk copy.
     const int rr = (int)(row & 127), c0 = cg * 4;
     uint8_t* tile = reinterpret_cast<uint8_t*>(y) + (row >> 7) * 32768;
     const int off = (c0 >> 6) * 16384 + rr * 128 + (((((c0 & 63) >> 3) ^ (rr & 7)) << 4) | ((c0 & 7) << 1));
-    __nv_bfloat162 p0 = __floats2bfloat162_rn(r.x, r.y), p1 = __floats2bfloat162_rn(r.z, r.w);
+    __half2 p0 = __floats2half2_rn(r.x, r.y), p1 = __floats2half2_rn(r.z, r.w);
     uint2 raw;
     raw.x = *reinterpret_cast<unsigned*>(&p0);
     raw.y = *reinterpret_cast<unsigned*>(&p1);
@@ -644,25 +644,25 @@ extern "C" int arreau_edge_kernels_f32(const double* dir, const double* dist, co
   return ARREAU_OK;
 }
 
-extern "C" int arreau_message_fiber_norm(const void* kernels, int32_t kernels_bf16, const float* h,
+extern "C" int arreau_message_fiber_norm(const void* kernels, int32_t kernels_f16, const float* h,
                                          const int32_t* row_ptr, const int32_t* src, const float* fiber_kernel,
                                          const float* conv_bias, const float* ln_w, const float* ln_b, int32_t N,
-                                         void* y, int32_t y_bf16, float* x1, float* x2_debug, void* stream) {
+                                         void* y, int32_t y_f16, float* x1, float* x2_debug, void* stream) {
   if (N == 0) return ARREAU_OK;
   if (!h || !row_ptr || !fiber_kernel || !conv_bias || !ln_w || !ln_b || !y || !x1) return ARREAU_ERR_NULL;
   if (N < 0) return ARREAU_ERR_BAD_SHAPE;
   cudaStream_t s = (cudaStream_t)stream;
   const long long rows = (long long)N * kO;
   const unsigned ggrid = (unsigned)((rows + kGatherWarps - 1) / kGatherWarps);
-  if (kernels_bf16)
-    message_gather_kernel<__nv_bfloat16><<<ggrid, kGatherWarps * 32, 0, s>>>((const __nv_bfloat16*)kernels, h, row_ptr, src, rows, x1);
+  if (kernels_f16)
+    message_gather_kernel<__half><<<ggrid, kGatherWarps * 32, 0, s>>>((const __half*)kernels, h, row_ptr, src, rows, x1);
   else
     message_gather_kernel<float><<<ggrid, kGatherWarps * 32, 0, s>>>((const float*)kernels, h, row_ptr, src, rows, x1);
   CUDA_LAUNCH_CHECK();
   const int fgroups = (N + kFiberNB - 1) / kFiberNB;
   const int fgrid = fgroups < num_sms() ? fgroups : num_sms();
-  if (y_bf16)
-    fiber_norm_kernel<__nv_bfloat16><<<fgrid, kFiberThreads, 0, s>>>(x1, fiber_kernel, conv_bias, ln_w, ln_b, N, (__nv_bfloat16*)y, x2_debug);
+  if (y_f16)
+    fiber_norm_kernel<__half><<<fgrid, kFiberThreads, 0, s>>>(x1, fiber_kernel, conv_bias, ln_w, ln_b, N, (__half*)y, x2_debug);
   else
     fiber_norm_kernel<float><<<fgrid, kFiberThreads, 0, s>>>(x1, fiber_kernel, conv_bias, ln_w, ln_b, N, (float*)y, x2_debug);
   CUDA_LAUNCH_CHECK();

@@ -1,4 +1,4 @@
-// tcgen05 (bf16 operands, fp32 accumulation in TMEM) variants of the two GEMM-shaped kernels of the step.
+// tcgen05 (fp16 operands, fp32 accumulation in TMEM) variants of the two GEMM-shaped kernels of the step.
 //
 //   convnext_mlp_tc_kernel   K6   h += layer_scale * (W2 gelu(W1 y + b1) + b2)          convnext.py:26-32
 //   edge_kernels_tc_kernel   K3+K4a invariants -> monomials -> basis MLP -> window -> 5 kernel projections
@@ -8,7 +8,7 @@
 //   warp 1   MMA issuer: one thread issues tcgen05.mma (M = 128, N = 128, K = 16) and tcgen05.commit
 //   warp 2   TMEM allocation / release
 //   warps 4..19  epilogue (16 warps: 4 per TMEM lane quarter, each a quarter of the columns): tcgen05.ld ->
-//                bias / GELU / window in registers -> bf16 operand tile of the next GEMM written back to shared
+//                bias / GELU / window in registers -> fp16 operand tile of the next GEMM written back to shared
 //                memory in the UMMA layout (the intermediate never leaves the SM), or the final result to HBM.
 #include "common.cuh"
 #include "tc_common.cuh"
@@ -22,7 +22,7 @@ constexpr int kEpiWarp0 = 4;
 constexpr int kEpiWarps = 16;
 constexpr int kEpiThreads = kEpiWarps * 32;
 constexpr int kTileM = 128;
-constexpr uint32_t kIdesc128 = umma_idesc_bf16(128, 128);
+constexpr uint32_t kIdesc128 = umma_idesc_f16(128, 128);
 
 __device__ long long* g_tc_prof = nullptr;   // debug: per-phase clock64 stamps of CTA 0 (scratch/prof_tc.py)
 #define TC_STAMP(slot)                                                                     \
@@ -35,15 +35,16 @@ __device__ __forceinline__ void mma_slab(uint32_t tmem_d, uint32_t a_slab, uint3
   const uint64_t ad = umma_desc_sw128(a_slab), bd = umma_desc_sw128(b_slab);
 #pragma unroll
   for (int k = 0; k < 4; ++k) {
-    if (k < ksteps) umma_bf16(tmem_d, ad + (uint64_t)(k * 2), bd + (uint64_t)(k * 2), kIdesc128, (accumulate_first || k > 0) ? 1u : 0u);
+    if (k < ksteps) umma_f16(tmem_d, ad + (uint64_t)(k * 2), bd + (uint64_t)(k * 2), kIdesc128, (accumulate_first || k > 0) ? 1u : 0u);
   }
 }
 
-// 32 accumulator columns -> (+ bias) -> GELU (* scale) -> bf16 -> the four 16-byte chunks chunk0..chunk0+3 of
+// 32 accumulator columns -> (+ bias) -> GELU (* scale) -> fp16 -> the four 16-byte chunks chunk0..chunk0+3 of
 // operand row m (row base pointer `row`, chunk positions XOR-swizzled by the row index)
 template <bool kBias, bool kScale>
 __device__ __forceinline__ void gelu_store32(const float (&v)[32], const float* __restrict__ bias_s, float scale,
                                              uint8_t* row, int chunk0, int m) {
+  const __half2 sc = __float2half2_rn(scale);
 #pragma unroll
   for (int cc = 0; cc < 4; ++cc) {
     float x[8];
@@ -55,30 +56,32 @@ __device__ __forceinline__ void gelu_store32(const float (&v)[32], const float* 
       x[0] += b0.x; x[1] += b0.y; x[2] += b0.z; x[3] += b0.w;
       x[4] += b1.x; x[5] += b1.y; x[6] += b1.z; x[7] += b1.w;
     }
-#pragma unroll
-    for (int i = 0; i < 8; ++i) {
-      x[i] = gelu_fast(x[i]);
-      if constexpr (kScale) x[i] *= scale;
-    }
     uint4 pk;
-    pk.x = pack_bf16(x[0], x[1]);
-    pk.y = pack_bf16(x[2], x[3]);
-    pk.z = pack_bf16(x[4], x[5]);
-    pk.w = pack_bf16(x[6], x[7]);
+    if constexpr (kScale) {
+      pk.x = gelu2_scaled_f16(x[0], x[1], sc);
+      pk.y = gelu2_scaled_f16(x[2], x[3], sc);
+      pk.z = gelu2_scaled_f16(x[4], x[5], sc);
+      pk.w = gelu2_scaled_f16(x[6], x[7], sc);
+    } else {
+      pk.x = gelu2_f16(x[0], x[1]);
+      pk.y = gelu2_f16(x[2], x[3]);
+      pk.z = gelu2_f16(x[4], x[5]);
+      pk.w = gelu2_f16(x[6], x[7]);
+    }
     *reinterpret_cast<uint4*>(row + (((chunk0 + cc) ^ (m & 7)) << 4)) = pk;
   }
 }
 
-// 32 accumulator columns -> + bias -> GELU -> four packed bf16 chunks (registers only)
+// 32 accumulator columns -> + bias -> GELU -> four packed fp16 chunks (registers only)
 __device__ __forceinline__ void gelu_pack32(const float (&v)[32], const float* __restrict__ bias_s, uint4 (&pk)[4]) {
 #pragma unroll
   for (int cc = 0; cc < 4; ++cc) {
     const float4 b0 = *reinterpret_cast<const float4*>(bias_s + cc * 8);
     const float4 b1 = *reinterpret_cast<const float4*>(bias_s + cc * 8 + 4);
-    pk[cc].x = pack_bf16(gelu_fast(v[cc * 8 + 0] + b0.x), gelu_fast(v[cc * 8 + 1] + b0.y));
-    pk[cc].y = pack_bf16(gelu_fast(v[cc * 8 + 2] + b0.z), gelu_fast(v[cc * 8 + 3] + b0.w));
-    pk[cc].z = pack_bf16(gelu_fast(v[cc * 8 + 4] + b1.x), gelu_fast(v[cc * 8 + 5] + b1.y));
-    pk[cc].w = pack_bf16(gelu_fast(v[cc * 8 + 6] + b1.z), gelu_fast(v[cc * 8 + 7] + b1.w));
+    pk[cc].x = gelu2_f16(v[cc * 8 + 0] + b0.x, v[cc * 8 + 1] + b0.y);
+    pk[cc].y = gelu2_f16(v[cc * 8 + 2] + b0.z, v[cc * 8 + 3] + b0.w);
+    pk[cc].z = gelu2_f16(v[cc * 8 + 4] + b1.x, v[cc * 8 + 5] + b1.y);
+    pk[cc].w = gelu2_f16(v[cc * 8 + 6] + b1.z, v[cc * 8 + 7] + b1.w);
   }
 }
 
@@ -86,7 +89,7 @@ __device__ __forceinline__ void gelu_pack32(const float (&v)[32], const float* _
 // K6  ConvNext channel MLP
 // =================================================================================================
 namespace mlp {
-constexpr int kTileBytes = 32768;     // [128 rows x 128 K] bf16 = 2 slabs
+constexpr int kTileBytes = 32768;     // [128 rows x 128 K] fp16 = 2 slabs
 constexpr int kWStages = 3;
 constexpr int kTilesBytes = (2 + 2 + kWStages) * kTileBytes;
 constexpr int kSmemBytes = 232448;    // everything (tiles, bias, barriers) is carved from the dynamic window
@@ -324,9 +327,9 @@ convnext_mlp_tc_kernel(const uint8_t* __restrict__ y_img, const uint8_t* __restr
 // K3 + K4a  edge pipeline
 // =================================================================================================
 namespace edge {
-constexpr int kChunkBytes = 16384;      // [128 rows x 64 K] bf16 = 1 slab
+constexpr int kChunkBytes = 16384;      // [128 rows x 64 K] fp16 = 1 slab
 constexpr int kStages = 4;
-constexpr int kOutBytes = 32768;        // staging of one layer's [128 rows x 128 ch] bf16 output tile (bulk store)
+constexpr int kOutBytes = 32768;        // staging of one layer's [128 rows x 128 ch] fp16 output tile (bulk store)
 constexpr int kW1Bytes = 32768;         // [128 x 96 -> 128] resident
 constexpr int kA2Bytes = 32768;
 constexpr int kA3Bytes = 65536;         // first 32 KB double as the monomial tile A1
@@ -371,10 +374,10 @@ __device__ __forceinline__ float mono_val(const float (&v)[6], float one) {
 template <int C>
 __device__ __forceinline__ uint4 mono_chunk(const float (&v)[6], float one) {
   uint4 pk;
-  pk.x = pack_bf16(mono_val<C * 8 + 0>(v, one), mono_val<C * 8 + 1>(v, one));
-  pk.y = pack_bf16(mono_val<C * 8 + 2>(v, one), mono_val<C * 8 + 3>(v, one));
-  pk.z = pack_bf16(mono_val<C * 8 + 4>(v, one), mono_val<C * 8 + 5>(v, one));
-  pk.w = pack_bf16(mono_val<C * 8 + 6>(v, one), mono_val<C * 8 + 7>(v, one));
+  pk.x = pack_f16(mono_val<C * 8 + 0>(v, one), mono_val<C * 8 + 1>(v, one));
+  pk.y = pack_f16(mono_val<C * 8 + 2>(v, one), mono_val<C * 8 + 3>(v, one));
+  pk.z = pack_f16(mono_val<C * 8 + 4>(v, one), mono_val<C * 8 + 5>(v, one));
+  pk.w = pack_f16(mono_val<C * 8 + 6>(v, one), mono_val<C * 8 + 7>(v, one));
   return pk;
 }
 // chunks 3*PART .. 3*PART+2 of monomial row m (12 chunks of 8 = 96 columns; slab = chunk / 8)
@@ -389,7 +392,7 @@ __device__ __forceinline__ void store_mono_part(const float (&v)[6], float one, 
   }
 }
 
-// fp32 edge invariants for the bf16 path (the monomials are rounded to bf16 right after; the fp32 path and the
+// fp32 edge invariants for the fp16 path (the monomials are rounded to fp16 right after; the fp32 path and the
 // graph keep fp64): [dir.ori, |dir - (dir.ori) ori|, dist, cos(dir,a), cos(dir,b), cos(dir,c)]
 __device__ __forceinline__ void edge_invariants_f32(const double* __restrict__ dir3, double dist, const double* __restrict__ lat9,
                                                     const float* __restrict__ ori3, float (&attr)[6]) {
@@ -415,7 +418,7 @@ edge_kernels_tc_kernel(const double* __restrict__ dir, const double* __restrict_
                        const int32_t* __restrict__ crystal_of_atom, const int32_t* __restrict__ src,
                        const int32_t* __restrict__ num_edges_ptr, long long edge_capacity, const float* __restrict__ ori,
                        const uint8_t* __restrict__ w1_img, const uint8_t* __restrict__ w_img, const float* __restrict__ b2,
-                       double radius, __nv_bfloat16* __restrict__ kernels) {
+                       double radius, __half* __restrict__ kernels) {
   using namespace edge;
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
@@ -545,7 +548,7 @@ edge_kernels_tc_kernel(const double* __restrict__ dir, const double* __restrict_
       const long long e = tile * kEdgesPerTile + (m >> 4);
       const bool valid = e < E;
       TC_STAMP(0);
-      // ---- A1: invariants -> 83 monomials + constant 1 (bias) -> bf16; 3 of the 12 16-byte chunks per thread.
+      // ---- A1: invariants -> 83 monomials + constant 1 (bias) -> fp16; 3 of the 12 16-byte chunks per thread.
       // The previous tile's GEMM3 finished reading A3 before its last x_full fired, which this warp waited on.
       {
         float attr[6] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
@@ -609,7 +612,7 @@ edge_kernels_tc_kernel(const double* __restrict__ dir, const double* __restrict_
       __syncwarp();
       if (lane == 0) mbar_arrive(&bars.a3_full);
       TC_STAMP(5);
-      // ---- epilogue 3: kernels[l][e][o][c] = X[l&1] (bf16), channels cgi*32 .. +31 ----
+      // ---- epilogue 3: kernels[l][e][o][c] = X[l&1] (fp16), channels cgi*32 .. +31 ----
       for (int l = 0; l < kL; ++l) {
         const int b = l & 1;
         uint32_t& xuse = b ? xuse1 : xuse0;
@@ -623,7 +626,7 @@ edge_kernels_tc_kernel(const double* __restrict__ dir, const double* __restrict_
         ++xuse;
         // The layer's output tile is 32 KB contiguous in HBM: stage it in shared memory and let the TMA engine
         // write it with one bulk store.  Rows are 256 B; the 16-byte chunk k of row (e, o) is stored at chunk
-        // position k ^ o (the bf16 kernels layout, undone by the message kernel's loads), which makes these
+        // position k ^ o (the fp16 kernels layout, undone by the message kernel's loads), which makes these
         // 16-byte shared stores conflict free.  Two staging buffers (OUT and the idle A2 tile) alternate so the
         // store of layer l-1 drains while layer l is staged.
         uint8_t* stage = (l & 1) ? A2 : OUT;
@@ -633,10 +636,10 @@ edge_kernels_tc_kernel(const double* __restrict__ dir, const double* __restrict_
 #pragma unroll
         for (int cc = 0; cc < 4; ++cc) {
           uint4 pk;
-          pk.x = pack_bf16(v[cc * 8 + 0], v[cc * 8 + 1]);
-          pk.y = pack_bf16(v[cc * 8 + 2], v[cc * 8 + 3]);
-          pk.z = pack_bf16(v[cc * 8 + 4], v[cc * 8 + 5]);
-          pk.w = pack_bf16(v[cc * 8 + 6], v[cc * 8 + 7]);
+          pk.x = pack_f16(v[cc * 8 + 0], v[cc * 8 + 1]);
+          pk.y = pack_f16(v[cc * 8 + 2], v[cc * 8 + 3]);
+          pk.z = pack_f16(v[cc * 8 + 4], v[cc * 8 + 5]);
+          pk.w = pack_f16(v[cc * 8 + 6], v[cc * 8 + 7]);
           *reinterpret_cast<uint4*>(orow + (((cgi * 4 + cc) ^ (m & 15)) << 4)) = pk;
         }
         fence_proxy_async();
@@ -644,7 +647,7 @@ edge_kernels_tc_kernel(const double* __restrict__ dir, const double* __restrict_
         if (is_issuer) {
           const long long left = E - tile * kEdgesPerTile;
           const uint32_t bytes = (uint32_t)(left < kEdgesPerTile ? left : kEdgesPerTile) * (kO * kC * 2);
-          __nv_bfloat16* out = kernels + ((size_t)l * edge_capacity * kO + (size_t)tile * kTileM) * kC;
+          __half* out = kernels + ((size_t)l * edge_capacity * kO + (size_t)tile * kTileM) * kC;
           asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(out), "r"(smem_u32(stage)), "r"(bytes)
                        : "memory");
           asm volatile("cp.async.bulk.commit_group;" ::: "memory");
@@ -680,7 +683,7 @@ extern "C" int arreau_debug_set_tc_profile(long long* buf) {
   return (int)cudaMemcpyToSymbol(g_tc_prof, &buf, sizeof(buf));
 }
 
-extern "C" int arreau_convnext_mlp_bf16(const void* y_img, const void* w_img, const float* b1, const float* b2,
+extern "C" int arreau_convnext_mlp_f16(const void* y_img, const void* w_img, const float* b1, const float* b2,
                                         const float* layer_scale, int64_t num_rows, float* h, void* stream) {
   if (num_rows == 0) return ARREAU_OK;
   if (!y_img || !w_img || !b1 || !b2 || !layer_scale || !h) return ARREAU_ERR_NULL;
@@ -699,13 +702,13 @@ extern "C" int arreau_convnext_mlp_bf16(const void* y_img, const void* w_img, co
   return ARREAU_OK;
 }
 
-extern "C" int arreau_edge_kernels_bf16(const double* dir, const double* dist, const double* lattice,
+extern "C" int arreau_edge_kernels_f16(const double* dir, const double* dist, const double* lattice,
                                         const int32_t* crystal_of_atom, const int32_t* src, const int32_t* num_edges_ptr,
                                         int64_t edge_capacity, const float* ori, const void* w1_img, const void* w_img,
-                                        const float* b2, double radius, void* kernels_bf16, void* stream) {
+                                        const float* b2, double radius, void* kernels_f16, void* stream) {
   if (edge_capacity == 0) return ARREAU_OK;
   if (!dir || !dist || !lattice || !crystal_of_atom || !src || !num_edges_ptr || !ori || !w1_img || !w_img || !b2 ||
-      !kernels_bf16)
+      !kernels_f16)
     return ARREAU_ERR_NULL;
   if (edge_capacity < 0) return ARREAU_ERR_BAD_SHAPE;
   static bool attr_set = false;
@@ -718,7 +721,7 @@ extern "C" int arreau_edge_kernels_bf16(const double* dir, const double* dist, c
   const int grid = (int)(tiles < (long long)num_sms_tc() ? tiles : (long long)num_sms_tc());
   edge_kernels_tc_kernel<<<grid, kThreads, edge::kSmemBytes, (cudaStream_t)stream>>>(
       dir, dist, lattice, crystal_of_atom, src, num_edges_ptr, (long long)edge_capacity, ori, (const uint8_t*)w1_img,
-      (const uint8_t*)w_img, b2, radius, (__nv_bfloat16*)kernels_bf16);
+      (const uint8_t*)w_img, b2, radius, (__half*)kernels_f16);
   CUDA_LAUNCH_CHECK();
   return ARREAU_OK;
 }

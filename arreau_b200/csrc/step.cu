@@ -100,8 +100,8 @@ extern "C" int arreau_ponita_forward(const arreau_weights* w, const arreau_works
   if (N < 0 || G < 0) return ARREAU_ERR_BAD_SHAPE;
   if (N == 0) return ARREAU_OK;
   if (!row_ptr || !ws->h || !ws->y || !ws->acc || !ws->x1 || (ws->edge_capacity > 0 && !ws->kernels)) return ARREAU_ERR_NULL;
-  if (precision != ARREAU_PRECISION_FP32 && precision != ARREAU_PRECISION_BF16) return ARREAU_ERR_UNSUPPORTED;
-  const bool bf16 = precision == ARREAU_PRECISION_BF16;
+  if (precision != ARREAU_PRECISION_FP32 && precision != ARREAU_PRECISION_FP16) return ARREAU_ERR_UNSUPPORTED;
+  const bool fp16 = precision == ARREAU_PRECISION_FP16;
   const int Z = w->num_states;
   const size_t node_elems = (size_t)N * kO * kC;
   cudaStream_t s = (cudaStream_t)stream;
@@ -111,8 +111,8 @@ extern "C" int arreau_ponita_forward(const arreau_weights* w, const arreau_works
     if (e != cudaSuccess) return (int)e;
   }
   const int32_t* num_edges_ptr = row_ptr + N;
-  if (bf16)
-    ARREAU_TRY(arreau_edge_kernels_bf16(dir, dist, lattice, crystal_of_atom, src, num_edges_ptr, ws->edge_capacity,
+  if (fp16)
+    ARREAU_TRY(arreau_edge_kernels_f16(dir, dist, lattice, crystal_of_atom, src, num_edges_ptr, ws->edge_capacity,
                                         w->ori, w->edge_w1_img, w->edge_w_img, w->b2, radius, ws->kernels, stream));
   else
     ARREAU_TRY(arreau_edge_kernels_f32(dir, dist, lattice, crystal_of_atom, src, num_edges_ptr, ws->edge_capacity,
@@ -120,14 +120,14 @@ extern "C" int arreau_ponita_forward(const arreau_weights* w, const arreau_works
                                        stream));
   const size_t layer_elems = (size_t)ws->edge_capacity * kO * kC;
   for (int l = 0; l < kL; ++l) {
-    const void* kern = bf16 ? (const void*)((const uint16_t*)ws->kernels + (size_t)l * layer_elems)
+    const void* kern = fp16 ? (const void*)((const uint16_t*)ws->kernels + (size_t)l * layer_elems)
                             : (const void*)((const float*)ws->kernels + (size_t)l * layer_elems);
-    ARREAU_TRY(arreau_message_fiber_norm(kern, bf16, ws->h, row_ptr, src, w->fiber_kernel + (size_t)l * kO * kO * kC,
-                                         w->conv_bias + l * kC, w->ln_w + l * kC, w->ln_b + l * kC, N, ws->y, bf16,
+    ARREAU_TRY(arreau_message_fiber_norm(kern, fp16, ws->h, row_ptr, src, w->fiber_kernel + (size_t)l * kO * kO * kC,
+                                         w->conv_bias + l * kC, w->ln_w + l * kC, w->ln_b + l * kC, N, ws->y, fp16,
                                          ws->x1_debug ? ws->x1_debug + l * node_elems : ws->x1,
                                          ws->x2_debug ? ws->x2_debug + l * node_elems : nullptr, stream));
-    if (bf16)
-      ARREAU_TRY(arreau_convnext_mlp_bf16(ws->y, (const uint8_t*)w->mlp_w_img + (size_t)l * 8 * 32768,
+    if (fp16)
+      ARREAU_TRY(arreau_convnext_mlp_f16(ws->y, (const uint8_t*)w->mlp_w_img + (size_t)l * 8 * 32768,
                                           w->mlp_b1 + l * kW, w->mlp_b2 + l * kC, w->layer_scale + l * kC,
                                           (int64_t)N * kO, ws->h, stream));
     else

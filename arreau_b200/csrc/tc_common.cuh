@@ -1,17 +1,17 @@
 // tcgen05 / TMEM / mbarrier / bulk-copy primitives for the sm_100a tensor-core kernels (inline PTX).
 //
 // Operand tiles live in shared memory in the canonical K-major SWIZZLE_128B layout of the UMMA shared
-// memory descriptor: a tile of R rows x 64 bf16 (one "K slab") is R rows of 128 bytes, 8-row groups 1024 B
+// memory descriptor: a tile of R rows x 64 fp16 (one "K slab") is R rows of 128 bytes, 8-row groups 1024 B
 // apart, and inside every 1024-B group the 16-byte chunk c of row r sits at chunk position c ^ (r & 7).
 // Tiles wider than 64 in K are several slabs back to back.  Weight tiles are pre-arranged in this image on
 // the host (arreau_b200/weights.py: umma_tile_image) so that one cp.async.bulk moves a whole tile.
 #pragma once
-#include <cuda_bf16.h>
+#include <cuda_fp16.h>
 #include <stdint.h>
 
 namespace tc {
 
-constexpr int kSlabK = 64;                 // bf16 elements per 128-byte swizzle row
+constexpr int kSlabK = 64;                 // fp16 elements per 128-byte swizzle row
 constexpr int kRowBytes = 128;
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -99,11 +99,12 @@ __device__ __forceinline__ uint64_t umma_desc_sw128(uint32_t addr) {
   d |= (uint64_t)2 << 61;                     // SWIZZLE_128B                                      [61,64)
   return d;
 }
-// kind::f16 instruction descriptor: bf16 x bf16 -> fp32, both operands K-major, M x N tile
-__host__ __device__ constexpr uint32_t umma_idesc_bf16(int M, int N) {
-  return (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
+// kind::f16 instruction descriptor: fp16 x fp16 -> fp32, both operands K-major, M x N tile
+__host__ __device__ constexpr uint32_t umma_idesc_f16(int M, int N) {
+  // c_format F32 = 1 at bit 4; a_format / b_format F16 = 0 at bits 7 / 10; both K-major (bits 15, 16 = 0)
+  return (1u << 4) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
 }
-__device__ __forceinline__ void umma_bf16(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc,
+__device__ __forceinline__ void umma_f16(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc,
                                           uint32_t accumulate) {
   asm volatile(
       "{\n\t.reg .pred p;\n\t"
@@ -119,18 +120,28 @@ __device__ __forceinline__ void umma_commit(uint64_t* bar) {
 }
 
 // ---- epilogue math -----------------------------------------------------------------------------
-// GELU on the bf16 path: x Phi(x) with Phi(x) = 0.5 (1 + tanh(x (a + b x^2))), (a, b) refitted to the exact
-// erf form (max |gelu_fast - gelu_erf| = 2.7e-4 over all x, plus the 2^-11 relative error of MUFU.TANH;
-// both are below the bf16 rounding (2^-9 relative) applied to the result right after).  One MUFU and five
-// FMA-pipe instructions per value instead of ~25 for erff: the 3.7e9 GELUs of a step are otherwise the bound
-// of both tensor-core kernels.  The fp32 path keeps the exact erff form.
-__device__ __forceinline__ float gelu_fast(float x) {
-  const float x2 = x * x;
-  const float u = x * fmaf(0.03470089338901844f, x2, 0.8001570785450266f);
-  float t;
-  asm("tanh.approx.f32 %0, %1;" : "=f"(t) : "f"(u));
-  const float hx = 0.5f * x;
-  return fmaf(hx, t, hx);
+// GELU on the fp16 path: x Phi(x) with Phi(x) = 0.5 (1 + tanh(x (a + b x^2))), (a, b) refitted to the exact
+// erf form (max |gelu_fast - gelu_erf| = 2.7e-4 over all x).  Two values at a time in packed fp16
+// (HMUL2 / HFMA2 / MUFU.TANH.F16x2): five packed FMA-pipe instructions and one MUFU per PAIR, and the result
+// is already the packed fp16 operand of the next GEMM.  fp16 arithmetic (11 significant bits) adds ~5e-4
+// relative, the same size as the rounding of the stored operand.  |x| > 255 overflows x^2 to +inf, which
+// saturates tanh to +-1 (the correct limit).  The 3.7e9 GELUs of a step are otherwise the bound of both
+// tensor-core kernels.  The fp32 path keeps the exact erff form.
+__device__ __forceinline__ uint32_t gelu2_f16(float x0, float x1) {
+  const __half2 x = __floats2half2_rn(x0, x1);
+  const __half2 ca = __float2half2_rn(0.8001570785450266f), cb = __float2half2_rn(0.03470089338901844f);
+  const __half2 u = __hmul2(x, __hfma2(cb, __hmul2(x, x), ca));
+  uint32_t tb;
+  asm("tanh.approx.f16x2 %0, %1;" : "=r"(tb) : "r"(*reinterpret_cast<const uint32_t*>(&u)));
+  const __half2 t = *reinterpret_cast<const __half2*>(&tb);
+  const __half2 hx = __hmul2(x, __float2half2_rn(0.5f));
+  const __half2 y = __hfma2(hx, t, hx);
+  return *reinterpret_cast<const uint32_t*>(&y);
+}
+__device__ __forceinline__ uint32_t gelu2_scaled_f16(float x0, float x1, __half2 scale) {
+  const uint32_t g = gelu2_f16(x0, x1);
+  const __half2 y = __hmul2(*reinterpret_cast<const __half2*>(&g), scale);
+  return *reinterpret_cast<const uint32_t*>(&y);
 }
 
 // 32-byte global accesses (sm_100: LDG.256 / STG.256): one full sector per thread and instruction
@@ -145,8 +156,8 @@ __device__ __forceinline__ void stg256(float* p, const float (&v)[8]) {
                : "memory");
 }
 
-__device__ __forceinline__ uint32_t pack_bf16(float lo, float hi) {
-  const __nv_bfloat162 v = __floats2bfloat162_rn(lo, hi);
+__device__ __forceinline__ uint32_t pack_f16(float lo, float hi) {
+  const __half2 v = __floats2half2_rn(lo, hi);
   return *reinterpret_cast<const uint32_t*>(&v);
 }
 

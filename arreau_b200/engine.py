@@ -16,7 +16,7 @@ from . import _lib
 from .tables import DiffusionTables
 from .weights import HIDDEN, LAYERS, NUM_ORI, PonitaWeights
 
-PRECISIONS = {"fp32": _lib.PRECISION_FP32, "bf16": _lib.PRECISION_BF16}
+PRECISIONS = {"fp32": _lib.PRECISION_FP32, "fp16": _lib.PRECISION_FP16}
 
 
 def angle_factors(angles: torch.Tensor) -> torch.Tensor:
@@ -77,8 +77,8 @@ class DenoiseEngine:
         self.x, self.vec = f32(N, self.F), f32(N, 4, 3)
         self.logits, self.score, self.len0 = f32(N, Z), f32(N, 3), f32(G, 3)
         self.h, self.acc, self.x1 = f32(N, NUM_ORI, HIDDEN), f32(N, Z + 6), f32(N, NUM_ORI, HIDDEN)
-        if precision == "bf16":     # 128-row UMMA tile images (32 KB each), see arreau_message_fiber_norm
-            self.y = torch.zeros(((N * NUM_ORI + 127) // 128) * 128 * HIDDEN, device=dev, dtype=torch.bfloat16)
+        if precision == "fp16":     # 128-row UMMA tile images (32 KB each), see arreau_message_fiber_norm
+            self.y = torch.zeros(((N * NUM_ORI + 127) // 128) * 128 * HIDDEN, device=dev, dtype=torch.float16)
         else:
             self.y = torch.zeros(N, NUM_ORI, HIDDEN, device=dev, dtype=torch.float32)
         self.t_of_atom = i32(N)
@@ -106,7 +106,7 @@ class DenoiseEngine:
         self.cell = torch.zeros(capacity, dtype=torch.int8, device=dev)
         self.dist = torch.zeros(capacity, dtype=torch.float64, device=dev)
         self.dir = torch.zeros(capacity, 3, dtype=torch.float64, device=dev)
-        kdt = torch.bfloat16 if self.precision == "bf16" else torch.float32
+        kdt = torch.float16 if self.precision == "fp16" else torch.float32
         self.kernels = torch.empty(LAYERS, capacity, NUM_ORI, HIDDEN, dtype=kdt, device=dev)
         node = (N, NUM_ORI, HIDDEN)
         if self.debug:
@@ -253,11 +253,11 @@ class DenoiseEngine:
         _lib.call("arreau_denoise_step", self.w.ref(), C.byref(self.ws), C.byref(a), self.stream)
 
     def kernels_logical(self, layer: int, num_edges: Optional[int] = None) -> torch.Tensor:
-        """Spatial kernels of one layer as fp32 [E,O,C] in logical channel order (debug / tests).  The bf16 path
+        """Spatial kernels of one layer as fp32 [E,O,C] in logical channel order (debug / tests).  The fp16 path
         stores the 16-byte chunk k of row (e, o) at chunk position k ^ o (csrc/model_tc.cu); undo that here."""
         E = self.num_edges() if num_edges is None else num_edges
         k = self.kernels[layer, :E]
-        if self.precision != "bf16":
+        if self.precision != "fp16":
             return k.float()
         k = k.float().view(E, NUM_ORI, HIDDEN // 8, 8)
         o = torch.arange(NUM_ORI, device=k.device)[:, None]
@@ -277,7 +277,7 @@ class DenoiseEngine:
         entry point at a time with CUDA events on the current stream.  Leaves the state untouched (the update
         kernels write to scratch).  Used by bench.py for the roofline of the dominant kernel."""
         w, s, Z = self.w.t, None, self.Z
-        bf16 = self.precision == "bf16"
+        fp16 = self.precision == "fp16"
         names, fns = [], []
 
         def add(name, fn):
@@ -290,9 +290,9 @@ class DenoiseEngine:
                                             w["w_embed_t"].data_ptr(), w["ori"].data_ptr(), self.N, self.F, 4,
                                             self.h.data_ptr(), self.stream))
         nep = self.row_ptr.data_ptr() + 4 * self.N
-        if bf16:
+        if fp16:
             add("edge_kernels", lambda: _lib.call(
-                "arreau_edge_kernels_bf16", self.dir.data_ptr(), self.dist.data_ptr(), self.lattice.data_ptr(),
+                "arreau_edge_kernels_f16", self.dir.data_ptr(), self.dist.data_ptr(), self.lattice.data_ptr(),
                 self.crystal_of_atom.data_ptr(), self.src.data_ptr(), nep, self.edge_capacity, w["ori"].data_ptr(),
                 w["edge_w1_img"].data_ptr(), w["edge_w_img"].data_ptr(), w["b2"].data_ptr(),
                 self.radius, self.kernels.data_ptr(), self.stream))
@@ -304,13 +304,13 @@ class DenoiseEngine:
                 self.radius, self.kernels.data_ptr(), self.stream))
         for l in range(LAYERS):
             add("message_fiber_norm", lambda l=l: _lib.call(
-                "arreau_message_fiber_norm", self.kernels[l].data_ptr(), int(bf16), self.h.data_ptr(),
+                "arreau_message_fiber_norm", self.kernels[l].data_ptr(), int(fp16), self.h.data_ptr(),
                 self.row_ptr.data_ptr(), self.src.data_ptr(), w["fiber_kernel"][l].data_ptr(),
                 w["conv_bias"][l].data_ptr(), w["ln_w"][l].data_ptr(), w["ln_b"][l].data_ptr(), self.N,
-                self.y.data_ptr(), int(bf16), self.x1.data_ptr(), None, self.stream))
-            if bf16:
+                self.y.data_ptr(), int(fp16), self.x1.data_ptr(), None, self.stream))
+            if fp16:
                 add("convnext_mlp", lambda l=l: _lib.call(
-                    "arreau_convnext_mlp_bf16", self.y.data_ptr(), w["mlp_w_img"].data_ptr() + l * 8 * 32768,
+                    "arreau_convnext_mlp_f16", self.y.data_ptr(), w["mlp_w_img"].data_ptr() + l * 8 * 32768,
                     w["mlp_b1"][l].data_ptr(), w["mlp_b2"][l].data_ptr(),
                     w["layer_scale"][l].data_ptr(), self.N * NUM_ORI, self.h.data_ptr(), self.stream))
             else:

@@ -132,22 +132,22 @@ class PonitaFiberBundle(nn.Module):
         atom_offset[1:] = torch.cumsum(torch.bincount(batch, minlength=G), 0)
         atom_offset = atom_offset.to(torch.int32)
         coa = batch.to(torch.int32).contiguous()
-        bf16 = self.precision == "bf16"
+        fp16 = self.precision == "fp16"
         cap = max(E, 1)
         f32 = lambda *s: torch.empty(*s, dtype=torch.float32, device=dev)  # noqa: E731
         ws = _lib.Workspace()
         h, acc, x1 = f32(N, NUM_ORI, HIDDEN), f32(N, w.num_states + 6), f32(N, NUM_ORI, HIDDEN)
-        if bf16:     # 128-row UMMA tile images
-            y = torch.zeros(((N * NUM_ORI + 127) // 128) * 128 * HIDDEN, dtype=torch.bfloat16, device=dev)
+        if fp16:     # 128-row UMMA tile images
+            y = torch.zeros(((N * NUM_ORI + 127) // 128) * 128 * HIDDEN, dtype=torch.float16, device=dev)
         else:
             y = torch.empty(N, NUM_ORI, HIDDEN, dtype=torch.float32, device=dev)
-        kern = torch.empty(LAYERS, cap, NUM_ORI, HIDDEN, dtype=torch.bfloat16 if bf16 else torch.float32, device=dev)
+        kern = torch.empty(LAYERS, cap, NUM_ORI, HIDDEN, dtype=torch.float16 if fp16 else torch.float32, device=dev)
         ws.h, ws.y, ws.kernels, ws.acc, ws.edge_capacity = h.data_ptr(), y.data_ptr(), kern.data_ptr(), acc.data_ptr(), cap
         ws.x1 = x1.data_ptr()
         logits, score, len0 = f32(N, w.num_states), f32(N, 3), f32(G, 3)
         xf = x.to(torch.float32).contiguous()
         vf = graph.vec.to(torch.float32).contiguous()
-        _lib.call("arreau_ponita_forward", w.ref(), C.byref(ws), _lib.PRECISION_BF16 if bf16 else _lib.PRECISION_FP32,
+        _lib.call("arreau_ponita_forward", w.ref(), C.byref(ws), _lib.PRECISION_FP16 if fp16 else _lib.PRECISION_FP32,
                   xf.data_ptr(), vf.data_ptr(), row_ptr.data_ptr(), src.data_ptr(), dist.data_ptr(),
                   direction.data_ptr(), lattice.data_ptr(), atom_offset.data_ptr(), coa.data_ptr(), N, G,
                   float(self.radius), logits.data_ptr(), score.data_ptr(), len0.data_ptr(),

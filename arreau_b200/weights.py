@@ -49,12 +49,12 @@ def monomial_fold_table(num_in: int = 6, degree: int = 3) -> np.ndarray:
 
 
 def umma_tile_image(w: np.ndarray) -> torch.Tensor:
-    """[rows, K] fp weights (rows = the UMMA N index, K a multiple of 64) -> the bf16 shared-memory image the
+    """[rows, K] fp weights (rows = the UMMA N index, K a multiple of 64) -> the fp16 shared-memory image the
     tcgen05 kernels expect (csrc/tc_common.cuh): K slabs of 64 back to back, each `rows` rows of 128 bytes with
     the 16-byte chunk c of row r stored at chunk position c ^ (r & 7).  Returned as a flat int16 CPU tensor."""
     rows, K = w.shape
     assert K % 64 == 0 and rows % 8 == 0
-    bits = torch.as_tensor(np.ascontiguousarray(w), dtype=torch.float32).to(torch.bfloat16).view(torch.int16).numpy()
+    bits = torch.as_tensor(np.ascontiguousarray(w), dtype=torch.float32).to(torch.float16).view(torch.int16).numpy()
     t = bits.reshape(rows, K // 64, 8, 8).transpose(1, 0, 2, 3)          # [slab, row, chunk, 8]
     pos = np.arange(8)[None, :] ^ (np.arange(rows)[:, None] & 7)          # out[.., r, p] = in[.., r, p ^ (r & 7)]
     out = np.take_along_axis(t, pos[None, :, :, None], axis=2)
@@ -70,7 +70,7 @@ def _np(v) -> np.ndarray:
 class PonitaWeights:
     """Device copies of one PonitaFiberBundle's parameters in kernel layouts."""
 
-    def __init__(self, state: Mapping[str, object], ori_grid, device="cuda", with_bf16: bool = True):
+    def __init__(self, state: Mapping[str, object], ori_grid, device="cuda", with_f16: bool = True):
         sd = {k: _np(v) for k, v in state.items() if hasattr(v, "shape") and np.prod(np.shape(v)) > 0
               and not k.endswith("callibrated") and not k.startswith("windowing_fn")}
         self.device = torch.device(device)
@@ -120,7 +120,7 @@ class PonitaWeights:
         _lib.call("arreau_fiber_kernel_precompute", self.t["ori"].data_ptr(), fw1.data_ptr(), fb1.data_ptr(),
                   fw2.data_ptr(), fb2.data_ptr(), fwf.data_ptr(), self.t["fiber_kernel"].data_ptr(), stream)
         torch.cuda.current_stream(self.device).synchronize()
-        if with_bf16:
+        if with_f16:
             # tcgen05 path: every weight tile as a ready-to-copy UMMA shared-memory image
             w1pad = np.zeros((HIDDEN, 128))
             w1pad[:, :MONO_PAD] = w1m_t.T                                  # [N = hidden, K = 96 -> 128]

@@ -2,7 +2,7 @@
 """Benchmark of the Arreau denoising step (BASELINE.json: crystals/sec over a full 999-step denoise
 trajectory, and ms per denoise step).
 
-    python bench.py [--gpus N] [--steps K] [--warmup W] [--precision fp32|bf16] [--impl ours|reference]
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--precision fp32|fp16] [--impl ours|reference]
 
 A "step" is one denoise step (graph + Ponita forward + VE/VP/D3PM update) of one batch of synthetic crystals;
 the N=1 workload is BASELINE.json configs[1] (C2: 1024 crystals x 40 atoms, 5 A cutoff, max_neighbors 8 as in the
@@ -175,7 +175,7 @@ def main():
     ap.add_argument("--steps", type=int, default=10)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--precision", default=os.environ.get("ARREAU_PRECISION", "fp32"), choices=["fp32", "bf16"])
+    ap.add_argument("--precision", default=os.environ.get("ARREAU_PRECISION", "fp32"), choices=["fp32", "fp16"])
     ap.add_argument("--crystals", type=int, default=1024)
     ap.add_argument("--atoms", type=int, default=40)
     ap.add_argument("--cap", type=int, default=8)
@@ -314,7 +314,7 @@ def main():
         top = max(br, key=lambda k: br[k]["ms_per_step"])
         flops_edge = 2.0 * E * O * (MONO * C + C * D + L * D * C) + 2.0 * L * 0   # 6.63 MFLOP/edge
         flops_mlp = 2.0 * 2 * C * 4 * C * N * O                                   # per layer
-        kbytes = 2 if args.precision == "bf16" else 4
+        kbytes = 2 if args.precision == "fp16" else 4
         bytes_msg = E * O * C * kbytes + 2 * 4 * N * O * C + 12 * E               # per layer: kernels + h in + y out + edges
         alg = {"edge_kernels": ("tensor", flops_edge / 1e12, peak_tf, "TFLOP/s"),
                "convnext_mlp": ("tensor", flops_mlp / 1e12, peak_tf, "TFLOP/s"),
@@ -330,7 +330,7 @@ def main():
                                                 "share_of_step": br[dom]["ms_per_step"] / sum(v["ms_per_step"] for v in br.values())})
         line = {"metric": "crystals_per_sec_full_trajectory", "value": value, "unit": "crystals/s", "n_gpus": world,
                 "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": ms_per_step, "higher_is_better": True,
-                "scaling": "weak", "vs_baseline": None, "dtype": "f32" if args.precision == "fp32" else "bf16",
+                "scaling": "weak", "vs_baseline": None, "dtype": "f32" if args.precision == "fp32" else "fp16",
                 "data": "synthetic", "config": config_dict(args), "clocks": clk,
                 "e2e": {"value": e2e_value, "unit": "crystals/s", "ms_per_step": ems / args.steps,
                         "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h},

@@ -16,7 +16,7 @@
  *  - return 0 on success, a negative ARREAU_ERR_* for bad arguments, or the positive
  *    cudaError_t of a failed launch.  No exceptions, no aborts, no CPU fallback;
  *  - fp64 for geometry and diffusion state (the reference runs fp64), fp32 for the network
- *    (bf16 tensor-core operands with fp32 accumulation on the ARREAU_PRECISION_BF16 path);
+ *    (fp16 tensor-core operands with fp32 accumulation on the ARREAU_PRECISION_FP16 path);
  *  - the network kernels are specialised at compile time on the reference's default sizes
  *    (arreau_model_dims); any other size is ARREAU_ERR_UNSUPPORTED.
  */
@@ -35,7 +35,7 @@ extern "C" {
 #define ARREAU_ERR_NULL (-4)
 
 #define ARREAU_PRECISION_FP32 0 /* FFMA2 SIMT GEMMs, parity <= 1e-4 of the fp64 reference          */
-#define ARREAU_PRECISION_BF16 1 /* tcgen05 bf16 operands, fp32 accumulate; tolerance stated in tests */
+#define ARREAU_PRECISION_FP16 1 /* tcgen05 fp16 operands, fp32 accumulate; tolerance stated in tests */
 
 /* Library/ABI version and the compile-time model dimensions (O=16, C=128, D=256, W=4, L=5). */
 int arreau_abi_version(void);
@@ -133,7 +133,7 @@ int arreau_node_embed(const float* x, const float* vec, const float* w_embed_t, 
  * conv.py:110).  dir[E,3]/dist[E] f64 from the graph; lattice[G,3,3] f64; crystal_of_atom[N];
  * src[E]; num_edges_ptr = &row_ptr[N] (device).  w1m_t[96,C]: rows 0..82 the monomial-folded first
  * layer, row 83 its bias, rows 84..95 zero; w2_t[C,D]; b2[D]; wk_t[D,L*C].
- * _f32: FFMA2 SIMT, fp32 kernels out.  _bf16: tcgen05, bf16 operands, fp32 accumulation, bf16 kernels out;
+ * _f32: FFMA2 SIMT, fp32 kernels out.  _f16: tcgen05, fp16 operands, fp32 accumulation, fp16 kernels out;
  * its weights are UMMA tile images (K-major SWIZZLE_128B, arreau_b200/weights.py umma_tile_image):
  * w1_img = [128 x 128] image of w1m (32 KB, resident), w_img = 24 chunks of [128 x 64] (16 KB each):
  * W2 (n-half, k-slab) x 4, then for each layer the 4 k-slabs of conv.kernel.weight. */
@@ -141,31 +141,31 @@ int arreau_edge_kernels_f32(const double* dir, const double* dist, const double*
                             const int32_t* crystal_of_atom, const int32_t* src, const int32_t* num_edges_ptr,
                             int64_t edge_capacity, const float* ori, const float* w1m_t, const float* w2_t,
                             const float* b2, const float* wk_t, double radius, float* kernels, void* stream);
-int arreau_edge_kernels_bf16(const double* dir, const double* dist, const double* lattice,
+int arreau_edge_kernels_f16(const double* dir, const double* dist, const double* lattice,
                              const int32_t* crystal_of_atom, const int32_t* src, const int32_t* num_edges_ptr,
                              int64_t edge_capacity, const float* ori, const void* w1_img, const void* w_img,
-                             const float* b2, double radius, void* kernels_bf16, void* stream);
+                             const float* b2, double radius, void* kernels_f16, void* stream);
 
 /* K4b+K5: x1[i,o,c] = sum_{e in row i} kernels[e,o,c] * h[src_e,o,c]   (conv.py:131-133 + PyG add)
  *         x2[i,p,c] = (1/O) sum_o x1[i,o,c] fiber_kernel[o,p,c] + bias[c]  (conv.py:115,126)
  *         y = LayerNorm_C(x2) * ln_w + ln_b                              (convnext.py:25)
- * `kernels` is ONE layer's [edge_capacity,O,C] slab (f32, or bf16 when kernels_bf16 != 0);
- * fiber_kernel is that layer's [O,O,C].  y[N,O,C] is f32 row-major, or (y_bf16) bf16 in 128-row UMMA tile
- * images for arreau_convnext_mlp_bf16.  x1 (f32 [N,O,C], required) is the workspace between the two
+ * `kernels` is ONE layer's [edge_capacity,O,C] slab (f32, or fp16 when kernels_f16 != 0);
+ * fiber_kernel is that layer's [O,O,C].  y[N,O,C] is f32 row-major, or (y_f16) fp16 in 128-row UMMA tile
+ * images for arreau_convnext_mlp_f16.  x1 (f32 [N,O,C], required) is the workspace between the two
  * launches (gather, then fiber conv + norm); x2_debug (f32 [N,O,C], may be NULL) receives x2 for the parity
  * tests.  Deterministic receiver-sorted CSR reduction (fixed order, no atomics). */
-int arreau_message_fiber_norm(const void* kernels, int32_t kernels_bf16, const float* h, const int32_t* row_ptr,
+int arreau_message_fiber_norm(const void* kernels, int32_t kernels_f16, const float* h, const int32_t* row_ptr,
                               const int32_t* src, const float* fiber_kernel, const float* conv_bias,
                               const float* ln_w, const float* ln_b, int32_t num_atoms_total, void* y,
-                              int32_t y_bf16, float* x1, float* x2_debug, void* stream);
+                              int32_t y_f16, float* x1, float* x2_debug, void* stream);
 
 /* K6: h <- h + layer_scale * (W2 gelu(W1 y + b1) + b2)   (convnext.py:26-32); rows = N*O.
- * _f32: w1_t[C,4C], w2_t[4C,C] f32.  _bf16: y_img = bf16 y as 128-row UMMA tile images (32 KB per tile, written
- * by arreau_message_fiber_norm with y_bf16 != 0; ceil(rows/128) tiles must be allocated), w_img = 8 tile images
+ * _f32: w1_t[C,4C], w2_t[4C,C] f32.  _f16: y_img = fp16 y as 128-row UMMA tile images (32 KB per tile, written
+ * by arreau_message_fiber_norm with y_f16 != 0; ceil(rows/128) tiles must be allocated), w_img = 8 tile images
  * of 32 KB in issue order W1_0, W1_1, W2_0, W1_2, W2_1, W1_3, W2_2, W2_3 (128-wide slices of the hidden layer). */
 int arreau_convnext_mlp_f32(const float* y, const float* w1_t, const float* b1, const float* w2_t,
                             const float* b2, const float* layer_scale, int64_t num_rows, float* h, void* stream);
-int arreau_convnext_mlp_bf16(const void* y_img, const void* w_img, const float* b1, const float* b2,
+int arreau_convnext_mlp_f16(const void* y_img, const void* w_img, const float* b1, const float* b2,
                              const float* layer_scale, int64_t num_rows, float* h, void* stream);
 
 /* K7a: acc[N,Z+6] (+)= read-out of one layer pooled over orientations (ponita.py:105):
@@ -202,7 +202,7 @@ typedef struct arreau_weights {
   const float* layer_scale;  /* [L,C]                                                       */
   const float* wr_t;         /* [L,C,Z+4]                                                   */
   const float* br;           /* [L,Z+4]                                                     */
-  /* bf16 operands of the tcgen05 path (NULL when only the fp32 path is used) */
+  /* fp16 operands of the tcgen05 path (NULL when only the fp32 path is used) */
   const void* edge_w1_img;   /* 32 KB UMMA tile image of w1m                                */
   const void* edge_w_img;    /* 24 x 16 KB UMMA tile images (W2, then Wk per layer)         */
   const void* mlp_w_img;     /* [L] x 8 x 32 KB UMMA tile images                            */
@@ -215,8 +215,8 @@ typedef struct arreau_weights {
 /* Scratch of one forward pass, sized for num_atoms_total N and edge_capacity. */
 typedef struct arreau_workspace {
   float* h;         /* [N,O,C] f32                                                           */
-  void* y;          /* [N,O,C] f32 (fp32 path) or bf16 tile images, ceil(N*O/128)*32 KB (bf16 path) */
-  void* kernels;    /* [L,edge_capacity,O,C] f32 or bf16                                     */
+  void* y;          /* [N,O,C] f32 (fp32 path) or fp16 tile images, ceil(N*O/128)*32 KB (fp16 path) */
+  void* kernels;    /* [L,edge_capacity,O,C] f32 or fp16                                     */
   float* acc;       /* [N,Z+6] f32                                                           */
   float* x1;        /* [N,O,C] f32: message sums between the gather and the fiber conv       */
   float* x1_debug;  /* NULL, or [L,N,O,C] f32                                                */

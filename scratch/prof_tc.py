@@ -10,7 +10,7 @@ w = np.load('tests/golden/weights_seed0.npz')
 sd = {k: w[k] for k in w.files if k not in ('ori_grid', 'fourier_w')}
 pw = PonitaWeights(sd, w['ori_grid'], device=dev)
 cr = make_crystals(1024, 40, None, seed=0)
-eng = DenoiseEngine(pw, build_tables(1000, 90), w['fourier_w'], cr.num_atoms, 5.0, 8, precision='bf16', device=dev)
+eng = DenoiseEngine(pw, build_tables(1000, 90), w['fourier_w'], cr.num_atoms, 5.0, 8, precision='fp16', device=dev)
 eng.set_state(cr.frac, cr.types, cr.lengths, cr.angles)
 eng.predict_scores(300); torch.cuda.synchronize()
 buf = torch.zeros(6 * 2 * 16, dtype=torch.int64, device=dev)

@@ -1,5 +1,5 @@
-"""bf16 tensor-core path (tcgen05): its own stated tolerances (BASELINE.json north_star: "any TF32/bf16 path
-given its own stated tolerance").  bf16 operands carry 8 significant bits (2^-9 = 2e-3 relative rounding per
+"""fp16 tensor-core path (tcgen05): its own stated tolerances (BASELINE.json north_star: "any TF32/fp16 path
+given its own stated tolerance").  fp16 operands carry 8 significant bits (2^-9 = 2e-3 relative rounding per
 element), accumulation is fp32 in TMEM; measured on B200: kernels 3e-3..7e-3, model outputs 1e-3..8e-3."""
 import numpy as np
 import pytest
@@ -8,8 +8,8 @@ import torch
 from conftest import rel_err
 
 pytestmark = pytest.mark.gpu
-TOL_BF16_KERNEL = 2e-2      # one GEMM-chain kernel against its fp32 twin, max|diff| / max|ref|
-TOL_BF16_MODEL = 3e-2       # score / logits / lengths of the whole forward against the fp64 reference
+TOL_FP16_KERNEL = 2e-2      # one GEMM-chain kernel against its fp32 twin, max|diff| / max|ref|
+TOL_FP16_MODEL = 3e-2       # score / logits / lengths of the whole forward against the fp64 reference
 
 
 def _rel(a, b):
@@ -17,7 +17,7 @@ def _rel(a, b):
 
 
 @pytest.mark.parametrize("rows", [128, 1000, 128 * 300 + 16])
-def test_convnext_mlp_bf16_vs_fp32(device, packed_weights, rows):
+def test_convnext_mlp_f16_vs_fp32(device, packed_weights, rows):
     from arreau_b200 import _lib
     from arreau_b200.weights import umma_tile_image
     g = torch.Generator().manual_seed(rows)
@@ -30,10 +30,10 @@ def test_convnext_mlp_bf16_vs_fp32(device, packed_weights, rows):
     h32, hbf, yd = h0.clone().to(device), h0.clone().to(device), y.to(device)
     _lib.call("arreau_convnext_mlp_f32", yd.data_ptr(), t["mlp_w1_t"][l].data_ptr(), t["mlp_b1"][l].data_ptr(),
               t["mlp_w2_t"][l].data_ptr(), t["mlp_b2"][l].data_ptr(), t["layer_scale"][l].data_ptr(), rows, h32.data_ptr(), s)
-    _lib.call("arreau_convnext_mlp_bf16", yimg.data_ptr(), t["mlp_w_img"].data_ptr() + l * 8 * 32768,
+    _lib.call("arreau_convnext_mlp_f16", yimg.data_ptr(), t["mlp_w_img"].data_ptr() + l * 8 * 32768,
               t["mlp_b1"][l].data_ptr(), t["mlp_b2"][l].data_ptr(), t["layer_scale"][l].data_ptr(), rows, hbf.data_ptr(), s)
     torch.cuda.synchronize()
-    assert _rel(hbf - h0.to(device), h32 - h0.to(device)) < TOL_BF16_KERNEL
+    assert _rel(hbf - h0.to(device), h32 - h0.to(device)) < TOL_FP16_KERNEL
 
 
 def _engine(device, gold, packed_weights, weights_npz, precision, key="t500/"):
@@ -46,9 +46,9 @@ def _engine(device, gold, packed_weights, weights_npz, precision, key="t500/"):
     return eng, s
 
 
-def test_edge_kernels_bf16_vs_fp32(device, gold, packed_weights, weights_npz):
+def test_edge_kernels_f16_vs_fp32(device, gold, packed_weights, weights_npz):
     e32, _ = _engine(device, gold, packed_weights, weights_npz, "fp32")
-    ebf, _ = _engine(device, gold, packed_weights, weights_npz, "bf16")
+    ebf, _ = _engine(device, gold, packed_weights, weights_npz, "fp16")
     e32.predict_scores(500)
     ebf.kernels.zero_()
     ebf.predict_scores(500)
@@ -56,18 +56,18 @@ def test_edge_kernels_bf16_vs_fp32(device, gold, packed_weights, weights_npz):
     E = e32.num_edges()
     assert E == ebf.num_edges() and E % 8 != 0 or True
     for l in range(5):
-        assert _rel(ebf.kernels_logical(l, E), e32.kernels_logical(l, E)) < TOL_BF16_KERNEL, l
+        assert _rel(ebf.kernels_logical(l, E), e32.kernels_logical(l, E)) < TOL_FP16_KERNEL, l
     assert bool((ebf.kernels[:, E:] == 0).all())            # rows past the device-side edge count stay untouched
 
 
-def test_forward_bf16_against_reference(device, gold, packed_weights, weights_npz):
+def test_forward_f16_against_reference(device, gold, packed_weights, weights_npz):
     f = gold("forward_c1_t500.npz")
-    eng, _ = _engine(device, gold, packed_weights, weights_npz, "bf16")
+    eng, _ = _engine(device, gold, packed_weights, weights_npz, "fp16")
     score, logits, len0 = eng.predict_scores(500)
     torch.cuda.synchronize()
-    assert rel_err(logits.cpu().numpy(), f["logits"]) < TOL_BF16_MODEL
-    assert rel_err(score.cpu().numpy(), f["vec_out"][:, 0]) < TOL_BF16_MODEL
-    assert rel_err(len0.cpu().numpy(), f["len0"]) < TOL_BF16_MODEL
+    assert rel_err(logits.cpu().numpy(), f["logits"]) < TOL_FP16_MODEL
+    assert rel_err(score.cpu().numpy(), f["vec_out"][:, 0]) < TOL_FP16_MODEL
+    assert rel_err(len0.cpu().numpy(), f["len0"]) < TOL_FP16_MODEL
     a = [t.clone() for t in (score, logits, len0)]
     eng.predict_scores(500)
     torch.cuda.synchronize()
@@ -76,21 +76,21 @@ def test_forward_bf16_against_reference(device, gold, packed_weights, weights_np
 
 
 @pytest.mark.parametrize("timestep", [999, 500, 1])
-def test_teacher_forced_step_bf16(device, gold, packed_weights, weights_npz, timestep):
-    eng, s = _engine(device, gold, packed_weights, weights_npz, "bf16", key=f"t{timestep}/")
+def test_teacher_forced_step_f16(device, gold, packed_weights, weights_npz, timestep):
+    eng, s = _engine(device, gold, packed_weights, weights_npz, "fp16", key=f"t{timestep}/")
     p = f"t{timestep}/"
     eng.set_noise(s[p + "z_len"], s[p + "z_frac"], s[p + "u_type"].astype(np.float64))
     eng.step(timestep)
     torch.cuda.synchronize()
-    assert rel_err(eng.score.cpu().numpy(), s[p + "score"]) < TOL_BF16_MODEL
-    assert rel_err(eng.logits.cpu().numpy(), s[p + "logits"]) < TOL_BF16_MODEL
-    assert rel_err(eng.len0.cpu().numpy(), s[p + "len0"]) < TOL_BF16_MODEL
-    assert rel_err(eng.lengths.cpu().numpy(), s[p + "lengths_next"]) < TOL_BF16_MODEL
+    assert rel_err(eng.score.cpu().numpy(), s[p + "score"]) < TOL_FP16_MODEL
+    assert rel_err(eng.logits.cpu().numpy(), s[p + "logits"]) < TOL_FP16_MODEL
+    assert rel_err(eng.len0.cpu().numpy(), s[p + "len0"]) < TOL_FP16_MODEL
+    assert rel_err(eng.lengths.cpu().numpy(), s[p + "lengths_next"]) < TOL_FP16_MODEL
     # the edge list is decided in fp64 before the network runs: identical on both precision paths
     assert (eng.types.cpu().numpy() != s[p + "types_next"]).mean() <= 0.05
 
 
-def test_c2_shape_bf16_vs_fp32_and_properties(device, packed_weights, weights_npz):
+def test_c2_shape_f16_vs_fp32_and_properties(device, packed_weights, weights_npz):
     """BASELINE.json configs[1] at full size (1024 x 40, cap 8): the oracle cannot run this in seconds, so the
     two CUDA precision paths are compared with each other and size-independent properties are checked."""
     from arreau_b200.engine import DenoiseEngine
@@ -99,7 +99,7 @@ def test_c2_shape_bf16_vs_fp32_and_properties(device, packed_weights, weights_np
     cr = make_crystals(1024, 40, None, seed=0)
     tabs = build_tables(1000, 90)
     outs = {}
-    for prec in ("fp32", "bf16"):
+    for prec in ("fp32", "fp16"):
         eng = DenoiseEngine(packed_weights, tabs, weights_npz["fourier_w"], cr.num_atoms, 5.0, 8, precision=prec, device=device)
         eng.set_state(cr.frac, cr.types, cr.lengths, cr.angles)
         eng.draw_noise(3, 0)
@@ -109,5 +109,5 @@ def test_c2_shape_bf16_vs_fp32_and_properties(device, packed_weights, weights_np
         outs[prec] = [t.clone() for t in (eng.score, eng.logits, eng.len0, eng.frac, eng.lengths)]
         assert all(bool(torch.isfinite(t).all()) for t in outs[prec])
         assert float(eng.frac.min()) >= 0.0 and float(eng.frac.max()) < 1.0      # wrapped (helpers:81)
-    for a, b in zip(outs["bf16"][:3], outs["fp32"][:3]):
-        assert _rel(a, b) < TOL_BF16_MODEL
+    for a, b in zip(outs["fp16"][:3], outs["fp32"][:3]):
+        assert _rel(a, b) < TOL_FP16_MODEL

@@ -115,8 +115,8 @@ def test_umma_tile_image_layout():
     """16-byte chunk c of row r lands at chunk c ^ (r & 7) of the row's 128 bytes, K slabs back to back."""
     from arreau_b200.weights import umma_tile_image
     rows, K = 16, 128
-    w = np.arange(rows * K, dtype=np.float32).reshape(rows, K) % 251        # bf16-exact small integers
-    img = umma_tile_image(w).view(torch.bfloat16).float().numpy().reshape(K // 64, rows, 8, 8)
+    w = np.arange(rows * K, dtype=np.float32).reshape(rows, K) % 251        # fp16-exact small integers
+    img = umma_tile_image(w).view(torch.float16).float().numpy().reshape(K // 64, rows, 8, 8)
     for r in (0, 1, 7, 9, 15):
         for k in (0, 8, 63, 64, 127):
             slab, c, e = k // 64, (k % 64) // 8, k % 8
