@@ -328,12 +328,11 @@ convnext_mlp_tc_kernel(const uint8_t* __restrict__ y_img, const uint8_t* __restr
 // =================================================================================================
 namespace edge {
 constexpr int kChunkBytes = 16384;      // [128 rows x 64 K] fp16 = 1 slab
-constexpr int kStages = 4;
-constexpr int kOutBytes = 32768;        // staging of one layer's [128 rows x 128 ch] fp16 output tile (bulk store)
+constexpr int kStages = 6;
 constexpr int kW1Bytes = 32768;         // [128 x 96 -> 128] resident
 constexpr int kA2Bytes = 32768;
 constexpr int kA3Bytes = 65536;         // first 32 KB double as the monomial tile A1
-constexpr int kTilesBytes = kW1Bytes + kA2Bytes + kA3Bytes + kStages * kChunkBytes + kOutBytes;
+constexpr int kTilesBytes = kW1Bytes + kA2Bytes + kA3Bytes + kStages * kChunkBytes;
 constexpr int kSmemBytes = 232448;      // everything (tiles, bias, barriers) is carved from the dynamic window
 constexpr int kChunksPerTile = 4 + 4 * kL;   // W2 (n-half, k-slab) x4, then Wk_l k-slabs
 constexpr int kEdgesPerTile = kTileM / kO;
@@ -424,7 +423,6 @@ edge_kernels_tc_kernel(const double* __restrict__ dir, const double* __restrict_
   const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
   uint8_t* smem = smem_raw + (base - smem_u32(smem_raw));
   float* const s_b2 = reinterpret_cast<float*>(smem + kTilesBytes);                                   // [kD]
-  float* const s_win = s_b2 + kD;                                                                      // [8]
   Bars& bars = *reinterpret_cast<Bars*>(smem + kTilesBytes + (kD + kEdgesPerTile) * sizeof(float));
   uint32_t& tmem_base_s =
       *reinterpret_cast<uint32_t*>(smem + kTilesBytes + (kD + kEdgesPerTile) * sizeof(float) + sizeof(Bars));
@@ -434,7 +432,6 @@ edge_kernels_tc_kernel(const double* __restrict__ dir, const double* __restrict_
   uint8_t* const A2 = W1 + kW1Bytes;
   uint8_t* const A3 = A2 + kA2Bytes;          // A1 aliases A3[0 .. 32 KB)
   uint8_t* const W = A3 + kA3Bytes;
-  uint8_t* const OUT = W + kStages * kChunkBytes;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   long long E = *num_edges_ptr;
   if (E > edge_capacity) E = edge_capacity;
@@ -541,32 +538,37 @@ edge_kernels_tc_kernel(const double* __restrict__ dir, const double* __restrict_
     const uint32_t lane_addr = (uint32_t)(q * 32) << 16;
     uint32_t xuse0 = 0, xuse1 = 0;
     int it = 0;
-    const bool is_issuer = threadIdx.x == kEpiWarp0 * 32;
-    long long* prof = (blockIdx.x == 0 && is_issuer) ? g_tc_prof : nullptr;
+    const bool is_issuer = cgi == 0 && (q & 1) == 0 && lane == 0;     // one bulk-store issuer per half tile
+    long long* prof = (blockIdx.x == 0 && threadIdx.x == kEpiWarp0 * 32) ? g_tc_prof : nullptr;
     constexpr int prof_role = 1;
-    for (long long tile = blockIdx.x; tile < tiles; tile += gridDim.x, ++it) {
-      const long long e = tile * kEdgesPerTile + (m >> 4);
-      const bool valid = e < E;
-      TC_STAMP(0);
-      // ---- A1: invariants -> 83 monomials + constant 1 (bias) -> fp16; 3 of the 12 16-byte chunks per thread.
-      // The previous tile's GEMM3 finished reading A3 before its last x_full fired, which this warp waited on.
-      {
-        float attr[6] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
-        if (valid) {
-          const int g = crystal_of_atom[src[e]];
-          edge_invariants_f32(dir + 3 * e, dist[e], lattice + 9 * (size_t)g, ori + 3 * (m & 15), attr);
-          if (cgi == 0 && (m & 15) == 0) s_win[m >> 4] = cutoff_window(dist[e], radius);
-        } else if (cgi == 0 && (m & 15) == 0) {
-          s_win[m >> 4] = 0.f;
-        }
-        const float one = valid ? 1.0f : 0.0f;
-        switch (cgi) {
-          case 0: store_mono_part<0>(attr, one, A3, m); break;
-          case 1: store_mono_part<1>(attr, one, A3, m); break;
-          case 2: store_mono_part<2>(attr, one, A3, m); break;
-          default: store_mono_part<3>(attr, one, A3, m); break;
-        }
+    // invariants + window of this thread's row, computed one tile ahead (under GEMM3 of the previous tile) so the
+    // dependent global loads (src -> crystal -> lattice, dir, dist) are off the critical path
+    float attr[6], one, win;
+    auto compute_attr = [&](long long t) {
+      const long long e = t * kEdgesPerTile + (m >> 4);
+#pragma unroll
+      for (int i = 0; i < 6; ++i) attr[i] = 0.f;
+      one = 0.f;
+      win = 0.f;
+      if (t < tiles && e < E) {
+        const int g = crystal_of_atom[src[e]];
+        edge_invariants_f32(dir + 3 * e, dist[e], lattice + 9 * (size_t)g, ori + 3 * (m & 15), attr);
+        win = cutoff_window(dist[e], radius);
+        one = 1.0f;
       }
+    };
+    compute_attr(blockIdx.x);
+    for (long long tile = blockIdx.x; tile < tiles; tile += gridDim.x, ++it) {
+      TC_STAMP(0);
+      // ---- A1: 83 monomials + constant 1 (bias) -> fp16; 3 of the 12 16-byte chunks per thread.
+      // The previous tile's GEMM3 finished reading A3 before its last x_full fired, which this warp waited on.
+      switch (cgi) {
+        case 0: store_mono_part<0>(attr, one, A3, m); break;
+        case 1: store_mono_part<1>(attr, one, A3, m); break;
+        case 2: store_mono_part<2>(attr, one, A3, m); break;
+        default: store_mono_part<3>(attr, one, A3, m); break;
+      }
+      const float win_cur = win;
       fence_proxy_async();
       __syncwarp();
       if (lane == 0) mbar_arrive(&bars.a1_full);
@@ -575,9 +577,9 @@ edge_kernels_tc_kernel(const double* __restrict__ dir, const double* __restrict_
       mbar_wait(&bars.x_full[0], xuse0 & 1);
       tc_fence_after();
       TC_STAMP(2);
-      if (it > 0) {   // the previous tile's layer-1/3 stores were staged in A2: they must have left shared memory
+      if (it > 0) {   // the previous tile's output stores were staged in A2: they must have left shared memory
         if (is_issuer) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
-        asm volatile("bar.sync 1, %0;" ::"n"(kEpiThreads) : "memory");
+        asm volatile("bar.sync 3, %0;" ::"n"(kEpiThreads) : "memory");
       }
       {
         float v[32];
@@ -598,7 +600,7 @@ edge_kernels_tc_kernel(const double* __restrict__ dir, const double* __restrict_
       tc_fence_after();
       TC_STAMP(4);
       {
-        const float win = s_win[m >> 4];
+        const float win = win_cur;
 #pragma unroll
         for (int g = 0; g < 2; ++g) {
           const int col0 = cgi * 64 + g * 32;
@@ -612,6 +614,7 @@ edge_kernels_tc_kernel(const double* __restrict__ dir, const double* __restrict_
       __syncwarp();
       if (lane == 0) mbar_arrive(&bars.a3_full);
       TC_STAMP(5);
+      compute_attr(tile + gridDim.x);        // next tile's geometry, hidden under this tile's GEMM3
       // ---- epilogue 3: kernels[l][e][o][c] = X[l&1] (fp16), channels cgi*32 .. +31 ----
       for (int l = 0; l < kL; ++l) {
         const int b = l & 1;
@@ -625,14 +628,16 @@ edge_kernels_tc_kernel(const double* __restrict__ dir, const double* __restrict_
         if (lane == 0) mbar_arrive(&bars.x_empty[b]);       // accumulators are in registers: release the buffer
         ++xuse;
         // The layer's output tile is 32 KB contiguous in HBM: stage it in shared memory and let the TMA engine
-        // write it with one bulk store.  Rows are 256 B; the 16-byte chunk k of row (e, o) is stored at chunk
-        // position k ^ o (the fp16 kernels layout, undone by the message kernel's loads), which makes these
-        // 16-byte shared stores conflict free.  Two staging buffers (OUT and the idle A2 tile) alternate so the
-        // store of layer l-1 drains while layer l is staged.
-        uint8_t* stage = (l & 1) ? A2 : OUT;
-        if (is_issuer) asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");   // store of layer l-2 has left smem
-        asm volatile("bar.sync 1, %0;" ::"n"(kEpiThreads) : "memory");
-        uint8_t* orow = stage + m * 256;
+        // write it with bulk stores.  Rows are 256 B; the 16-byte chunk k of row (e, o) is stored at chunk position
+        // k ^ o (the fp16 kernels layout, undone by the message kernel's loads), which makes these 16-byte shared
+        // stores conflict free.  The idle A2 tile is the staging area, split in two 16 KB halves (rows 0..63 /
+        // 64..127) that are staged, stored and recycled independently by the 8 warps owning those rows: the store
+        // of layer l-1 has a whole GEMM3 layer (~1000 cycles) to leave shared memory before layer l restages.
+        const int hf = q >> 1;
+        uint8_t* stage = A2 + hf * 16384;
+        if (is_issuer) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");   // this half's previous store has left smem
+        asm volatile("bar.sync %0, %1;" ::"r"(1 + hf), "n"(kEpiThreads / 2) : "memory");
+        uint8_t* orow = stage + (m & 63) * 256;
 #pragma unroll
         for (int cc = 0; cc < 4; ++cc) {
           uint4 pk;
@@ -643,13 +648,15 @@ edge_kernels_tc_kernel(const double* __restrict__ dir, const double* __restrict_
           *reinterpret_cast<uint4*>(orow + (((cgi * 4 + cc) ^ (m & 15)) << 4)) = pk;
         }
         fence_proxy_async();
-        asm volatile("bar.sync 1, %0;" ::"n"(kEpiThreads) : "memory");
+        asm volatile("bar.sync %0, %1;" ::"r"(1 + hf), "n"(kEpiThreads / 2) : "memory");
         if (is_issuer) {
-          const long long left = E - tile * kEdgesPerTile;
-          const uint32_t bytes = (uint32_t)(left < kEdgesPerTile ? left : kEdgesPerTile) * (kO * kC * 2);
-          __half* out = kernels + ((size_t)l * edge_capacity * kO + (size_t)tile * kTileM) * kC;
-          asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(out), "r"(smem_u32(stage)), "r"(bytes)
-                       : "memory");
+          const long long left = E - tile * kEdgesPerTile - hf * (kEdgesPerTile / 2);   // edges of this half still valid
+          if (left > 0) {
+            const uint32_t bytes = (uint32_t)(left < kEdgesPerTile / 2 ? left : kEdgesPerTile / 2) * (kO * kC * 2);
+            __half* out = kernels + ((size_t)l * edge_capacity * kO + (size_t)tile * kTileM + hf * 64) * kC;
+            asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(out), "r"(smem_u32(stage)), "r"(bytes)
+                         : "memory");
+          }
           asm volatile("cp.async.bulk.commit_group;" ::: "memory");
         }
         TC_STAMP(6 + l);

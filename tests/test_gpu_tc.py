@@ -1,6 +1,7 @@
-"""fp16 tensor-core path (tcgen05): its own stated tolerances (BASELINE.json north_star: "any TF32/fp16 path
-given its own stated tolerance").  fp16 operands carry 8 significant bits (2^-9 = 2e-3 relative rounding per
-element), accumulation is fp32 in TMEM; measured on B200: kernels 3e-3..7e-3, model outputs 1e-3..8e-3."""
+"""fp16 tensor-core path (tcgen05): its own stated tolerances (BASELINE.json north_star: "any TF32/bf16 path
+given its own stated tolerance").  fp16 operands carry 11 significant bits (2^-12 = 2.4e-4 relative rounding per
+element), accumulation is fp32 in TMEM, the GELU epilogues use a packed-fp16 tanh form (max 2.7e-4 from the erf
+form); measured on B200: kernels 6e-4..1.5e-3, model outputs 2e-4..2e-3 of max|ref|."""
 import numpy as np
 import pytest
 import torch
@@ -8,8 +9,8 @@ import torch
 from conftest import rel_err
 
 pytestmark = pytest.mark.gpu
-TOL_FP16_KERNEL = 2e-2      # one GEMM-chain kernel against its fp32 twin, max|diff| / max|ref|
-TOL_FP16_MODEL = 3e-2       # score / logits / lengths of the whole forward against the fp64 reference
+TOL_FP16_KERNEL = 5e-3      # one GEMM-chain kernel against its fp32 twin, max|diff| / max|ref|
+TOL_FP16_MODEL = 1e-2       # score / logits / lengths of the whole forward against the fp64 reference
 
 
 def _rel(a, b):
