@@ -292,10 +292,10 @@ __device__ __forceinline__ float4 load_kernel4(const __half* row, int cg, int o)
 //        x2[i][p][c] = (1/O) sum_o x1[i][o][c] fk[o][p][c] + bias[c], then LayerNorm over c as a warp reduction.
 constexpr int kGatherWarps = 8;
 
-template <typename KT>
+template <typename KT, typename XT>
 __global__ void __launch_bounds__(kGatherWarps * 32)
 message_gather_kernel(const KT* __restrict__ kern, const float* __restrict__ h, const int32_t* __restrict__ row_ptr,
-                      const int32_t* __restrict__ src, long long rows, float* __restrict__ x1) {
+                      const int32_t* __restrict__ src, long long rows, XT* __restrict__ x1) {
   const long long r = (long long)blockIdx.x * kGatherWarps + (threadIdx.x >> 5);   // row = node * kO + o
   if (r >= rows) return;
   const int cg = threadIdx.x & 31;
@@ -329,7 +329,15 @@ message_gather_kernel(const KT* __restrict__ kern, const float* __restrict__ h, 
     a.z = fmaf(kv.z, hv.z, a.z);
     a.w = fmaf(kv.w, hv.w, a.w);
   }
-  *reinterpret_cast<float4*>(x1 + (size_t)r * kC + cg * 4) = a;
+  if constexpr (sizeof(XT) == 4) {
+    *reinterpret_cast<float4*>(x1 + (size_t)r * kC + cg * 4) = a;
+  } else {   // fp16 path: the message sums feed a LayerNorm whose output is rounded to fp16 anyway
+    __half2 p0 = __floats2half2_rn(a.x, a.y), p1 = __floats2half2_rn(a.z, a.w);
+    uint2 raw;
+    raw.x = *reinterpret_cast<unsigned*>(&p0);
+    raw.y = *reinterpret_cast<unsigned*>(&p1);
+    *reinterpret_cast<uint2*>(x1 + (size_t)r * kC + cg * 4) = raw;
+  }
 }
 
 constexpr int kFiberThreads = 512;
@@ -355,13 +363,15 @@ __device__ __forceinline__ void store_y_row(YT* __restrict__ y, size_t row, int 
   }
 }
 
-template <typename YT>
+template <typename XT, typename YT>
 __global__ void __launch_bounds__(kFiberThreads, 1)
-fiber_norm_kernel(const float* __restrict__ x1, const float* __restrict__ fk, const float* __restrict__ bias,
+fiber_norm_kernel(const XT* __restrict__ x1, const float* __restrict__ fk, const float* __restrict__ bias,
                   const float* __restrict__ ln_w, const float* __restrict__ ln_b, int N, YT* __restrict__ y,
                   float* __restrict__ x2_dbg) {
-  // kFiberNB nodes' x1 (16 x 128 fp32 = 8 KB each = one 16-byte cp.async per thread and node) per stage
-  __shared__ __align__(16) float xs[kFiberStages][kFiberNB][kO * kC];
+  // kFiberNB nodes' x1 (16 x 128 values = 8 KB fp32 / 4 KB fp16 each: one 16-byte cp.async per thread) per stage
+  __shared__ __align__(16) XT xs[kFiberStages][kFiberNB][kO * kC];
+  constexpr int kPer16 = 16 / sizeof(XT);                     // elements per 16-byte copy
+  constexpr int kCopyThreads = kO * kC / kPer16;
   const int p = threadIdx.x >> 5, cg = threadIdx.x & 31;
   float4 fkr[kO];
 #pragma unroll
@@ -378,7 +388,8 @@ fiber_norm_kernel(const float* __restrict__ x1, const float* __restrict__ fk, co
 #pragma unroll
       for (int nb = 0; nb < kFiberNB; ++nb) {
         const long long node = g * kFiberNB + nb;
-        if (node < N) cp_async16(&xs[k % kFiberStages][nb][threadIdx.x * 4], x1 + (size_t)node * kO * kC + threadIdx.x * 4);
+        if (node < N && threadIdx.x < kCopyThreads)
+          cp_async16(&xs[k % kFiberStages][nb][threadIdx.x * kPer16], x1 + (size_t)node * kO * kC + threadIdx.x * kPer16);
       }
     }
     cp_async_commit();
@@ -397,7 +408,15 @@ fiber_norm_kernel(const float* __restrict__ x1, const float* __restrict__ fk, co
       float4 t = make_float4(0.f, 0.f, 0.f, 0.f);
 #pragma unroll
       for (int o = 0; o < kO; ++o) {
-        const float4 xv = *reinterpret_cast<const float4*>(&xs[k % kFiberStages][nb][o * kC + cg * 4]);
+        float4 xv;
+        if constexpr (sizeof(XT) == 4) {
+          xv = *reinterpret_cast<const float4*>(&xs[k % kFiberStages][nb][o * kC + cg * 4]);
+        } else {
+          const uint2 raw = *reinterpret_cast<const uint2*>(&xs[k % kFiberStages][nb][o * kC + cg * 4]);
+          const float2 lo = __half22float2(*reinterpret_cast<const __half2*>(&raw.x));
+          const float2 hi = __half22float2(*reinterpret_cast<const __half2*>(&raw.y));
+          xv = make_float4(lo.x, lo.y, hi.x, hi.y);
+        }
         t.x = fmaf(xv.x, fkr[o].x, t.x);
         t.y = fmaf(xv.y, fkr[o].y, t.y);
         t.z = fmaf(xv.z, fkr[o].z, t.z);
@@ -654,17 +673,23 @@ extern "C" int arreau_message_fiber_norm(const void* kernels, int32_t kernels_f1
   cudaStream_t s = (cudaStream_t)stream;
   const long long rows = (long long)N * kO;
   const unsigned ggrid = (unsigned)((rows + kGatherWarps - 1) / kGatherWarps);
-  if (kernels_f16)
-    message_gather_kernel<__half><<<ggrid, kGatherWarps * 32, 0, s>>>((const __half*)kernels, h, row_ptr, src, rows, x1);
+  // fp16 tensor path (fp16 kernels in, fp16 y out): x1 is kept in fp16 too; otherwise fp32
+  const bool x1_f16 = kernels_f16 && y_f16;
+  if (x1_f16)
+    message_gather_kernel<__half, __half><<<ggrid, kGatherWarps * 32, 0, s>>>((const __half*)kernels, h, row_ptr, src, rows, (__half*)x1);
+  else if (kernels_f16)
+    message_gather_kernel<__half, float><<<ggrid, kGatherWarps * 32, 0, s>>>((const __half*)kernels, h, row_ptr, src, rows, x1);
   else
-    message_gather_kernel<float><<<ggrid, kGatherWarps * 32, 0, s>>>((const float*)kernels, h, row_ptr, src, rows, x1);
+    message_gather_kernel<float, float><<<ggrid, kGatherWarps * 32, 0, s>>>((const float*)kernels, h, row_ptr, src, rows, x1);
   CUDA_LAUNCH_CHECK();
   const int fgroups = (N + kFiberNB - 1) / kFiberNB;
   const int fgrid = fgroups < num_sms() ? fgroups : num_sms();
-  if (y_f16)
-    fiber_norm_kernel<__half><<<fgrid, kFiberThreads, 0, s>>>(x1, fiber_kernel, conv_bias, ln_w, ln_b, N, (__half*)y, x2_debug);
+  if (x1_f16)
+    fiber_norm_kernel<__half, __half><<<fgrid, kFiberThreads, 0, s>>>((const __half*)x1, fiber_kernel, conv_bias, ln_w, ln_b, N, (__half*)y, x2_debug);
+  else if (y_f16)
+    fiber_norm_kernel<float, __half><<<fgrid, kFiberThreads, 0, s>>>(x1, fiber_kernel, conv_bias, ln_w, ln_b, N, (__half*)y, x2_debug);
   else
-    fiber_norm_kernel<float><<<fgrid, kFiberThreads, 0, s>>>(x1, fiber_kernel, conv_bias, ln_w, ln_b, N, (float*)y, x2_debug);
+    fiber_norm_kernel<float, float><<<fgrid, kFiberThreads, 0, s>>>(x1, fiber_kernel, conv_bias, ln_w, ln_b, N, (float*)y, x2_debug);
   CUDA_LAUNCH_CHECK();
   return ARREAU_OK;
 }

@@ -151,8 +151,8 @@ int arreau_edge_kernels_f16(const double* dir, const double* dist, const double*
  *         y = LayerNorm_C(x2) * ln_w + ln_b                              (convnext.py:25)
  * `kernels` is ONE layer's [edge_capacity,O,C] slab (f32, or fp16 when kernels_f16 != 0);
  * fiber_kernel is that layer's [O,O,C].  y[N,O,C] is f32 row-major, or (y_f16) fp16 in 128-row UMMA tile
- * images for arreau_convnext_mlp_f16.  x1 (f32 [N,O,C], required) is the workspace between the two
- * launches (gather, then fiber conv + norm); x2_debug (f32 [N,O,C], may be NULL) receives x2 for the parity
+ * images for arreau_convnext_mlp_f16.  x1 ([N,O,C] f32 capacity, required) is the workspace between the two
+ * launches (gather, then fiber conv + norm); it holds f32 values, or f16 values when both kernels_f16 and y_f16 are set; x2_debug (f32 [N,O,C], may be NULL) receives x2 for the parity
  * tests.  Deterministic receiver-sorted CSR reduction (fixed order, no atomics). */
 int arreau_message_fiber_norm(const void* kernels, int32_t kernels_f16, const float* h, const int32_t* row_ptr,
                               const int32_t* src, const float* fiber_kernel, const float* conv_bias,
