@@ -101,6 +101,7 @@ class DenoiseEngine:
         dev, N = self.device, self.N
         capacity = max(int(capacity), 1)
         self.edge_capacity = capacity
+        self.kernels = None            # release the old slab first: at C3 uncapped one slab is ~100 GB
         self.src = torch.zeros(capacity, dtype=torch.int32, device=dev)
         self.dst = torch.zeros(capacity, dtype=torch.int32, device=dev)
         self.cell = torch.zeros(capacity, dtype=torch.int8, device=dev)
@@ -180,7 +181,7 @@ class DenoiseEngine:
         self._count()
         E = int(self.row_ptr[self.N].item())
         if E > self.edge_capacity:
-            self._alloc_edges(int(E * 1.25) + 1024)
+            self._alloc_edges(int(E * 1.1) + 1024)
 
     def build_graph(self, edge_index_i64: Optional[torch.Tensor] = None, cell_offsets: Optional[torch.Tensor] = None):
         """lattice/pos must be current.  count -> scan -> fill."""

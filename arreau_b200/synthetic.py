@@ -59,17 +59,19 @@ CONFIGS = {
 def calibrate_length_readout(state: dict, atoms_per_crystal: int, num_layers: int = 5, first_row: int = 91) -> dict:
     """Quirk B7: with random-init weights the predicted lengths explode and
     the graph empties within a few steps.  For throughput/trajectory runs scale the three
-    length read-out rows by 1e-3 and set their bias to a_target / n^2 so that
-    x0_hat = len0 * n ~= a_target = (18.05 n)^(1/3); cost and architecture are unchanged.
+    length read-out rows by 1e-3 * min(1, (40/n)^2) (the weight part of x0_hat = n * sum_b r_b grows like n^2) and
+    set their bias to a_target / n^2 so that x0_hat = len0 * n ~= a_target = (18.05 n)^(1/3); cost and
+    architecture are unchanged.
     Works on any mapping name -> array (numpy or torch); returns a shallow copy."""
     out = dict(state)
     a_target = float(np.cbrt(VOLUME_PER_ATOM * atoms_per_crystal))
+    scale = 1e-3 * min(1.0, (40.0 / atoms_per_crystal) ** 2)
     for l in range(num_layers):
         w = out[f"read_out_layers.{l}.weight"].copy() if hasattr(out[f"read_out_layers.{l}.weight"], "copy") \
             else out[f"read_out_layers.{l}.weight"].clone()
         b = out[f"read_out_layers.{l}.bias"].copy() if hasattr(out[f"read_out_layers.{l}.bias"], "copy") \
             else out[f"read_out_layers.{l}.bias"].clone()
-        w[first_row:first_row + 3] = w[first_row:first_row + 3] * 1e-3
+        w[first_row:first_row + 3] = w[first_row:first_row + 3] * scale
         b[first_row:first_row + 3] = a_target / atoms_per_crystal ** 2
         out[f"read_out_layers.{l}.weight"], out[f"read_out_layers.{l}.bias"] = w, b
     return out

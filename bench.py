@@ -53,6 +53,24 @@ def sampler_init(G: int, n: int, seed: int):
     return frac, types, lengths, angles
 
 
+def teacher_state(G: int, n: int, seed: int, t: int):
+    """Teacher-forced state at timestep t: synthetic Alexandria-shaped crystals pushed through the
+    reference's forward noising (VE on frac helpers:43-46, VP on lengths :156-163, D3PM mask chain d3pm.py:140-143),
+    so that E/N is realistic for per-step timing at any t."""
+    from arreau_b200.synthetic import make_crystals
+    from arreau_b200.tables import build_tables
+    tb = build_tables(T_STEPS, Z)
+    cr = make_crystals(G, n, None, seed=seed)
+    rng = np.random.default_rng(seed + 7)
+    sig = float(tb.ve_sigmas[t])
+    frac = (cr.frac + sig * rng.standard_normal(cr.frac.shape)) % 1.0
+    ab = float(tb.vp_alpha_bars[t])
+    lengths = np.sqrt(ab) * cr.lengths + np.sqrt(1 - ab) * rng.standard_normal(cr.lengths.shape)
+    keep = float(tb.q_keep[t - 1])
+    types = np.where(rng.random(cr.types.shape) < keep, cr.types, Z - 1).astype(np.int64)
+    return frac, types, lengths, cr.angles
+
+
 class ClockSampler:
     """nvidia-smi clocks / throttle reasons sampled while the timed region runs."""
     Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
@@ -103,7 +121,7 @@ class ClockSampler:
                 "samples": len(sm), "reasons": sorted(reasons)}
 
 
-def oracle_step_time(G_s: int, n: int, steps: int, warmup: int, cap: int, threads: int):
+def oracle_step_time(G_s: int, n: int, steps: int, warmup: int, cap: int, threads: int, radius: float = RADIUS):
     """Times the CPU restatement of the reference step (oracle/restatement.py, fp64 like the reference) on
     G_s crystals x n atoms.  Returns (seconds per step, edges per atom)."""
     import torch
@@ -115,7 +133,7 @@ def oracle_step_time(G_s: int, n: int, steps: int, warmup: int, cap: int, thread
     try:
         sd, ori, fw = load_weights(n)
         T64 = lambda a: torch.as_tensor(np.asarray(a), dtype=torch.float64)  # noqa: E731
-        W = R.PonitaWeights({k: T64(v) for k, v in sd.items()}, T64(ori), RADIUS)
+        W = R.PonitaWeights({k: T64(v) for k, v in sd.items()}, T64(ori), radius)
         tabs = R.DiffusionTables.build(T_STEPS, Z)
         cr = make_crystals(G_s, n, None, seed=0)       # Alexandria-shaped cells: E/N = cap like the GPU run
         frac, types, lengths, angles = T64(cr.frac), torch.as_tensor(cr.types), T64(cr.lengths), T64(cr.angles)
@@ -127,12 +145,12 @@ def oracle_step_time(G_s: int, n: int, steps: int, warmup: int, cap: int, thread
             t = T_STEPS - 1 - it
             z_len = torch.randn(G_s, 3, generator=g); z_frac = torch.randn(N, 3, generator=g); u = torch.rand(N, Z, generator=g)
             t0 = time.perf_counter()
-            out = R.denoise_step(W, tabs, T64(fw), frac, types, lengths, angles, na, t, z_len, z_frac, u, RADIUS, cap)
+            out = R.denoise_step(W, tabs, T64(fw), frac, types, lengths, angles, na, t, z_len, z_frac, u, radius, cap)
             dt = time.perf_counter() - t0
             if it >= warmup:
                 times.append(dt)
         lat = R.lattice_from_params(lengths, angles)
-        ei = R.radius_graph_pbc(R.frac_to_cart_coords(frac, lat, na), lat, na, RADIUS, cap)[0]
+        ei = R.radius_graph_pbc(R.frac_to_cart_coords(frac, lat, na), lat, na, radius, cap)[0]
         epa = ei.shape[1] / N
         return float(np.mean(times)), epa
     finally:
@@ -145,7 +163,7 @@ def run_reference(args):
         return
     cores = os.cpu_count() or 1
     G_s = args.ref_crystals
-    t_step, epa = oracle_step_time(G_s, args.atoms, args.steps, args.warmup, args.cap, cores)
+    t_step, epa = oracle_step_time(G_s, args.atoms, args.steps, args.warmup, args.cap, cores, args.radius)
     value = G_s / ((T_STEPS - 1) * t_step)
     sample = f"{G_s} crystals x {args.atoms} atoms, {args.steps} denoise steps (+{args.warmup} warm-up), E/N={epa:.2f}"
     line = {"impl": "reference", "metric": "crystals_per_sec_full_trajectory", "value": value, "unit": "crystals/s",
@@ -159,12 +177,15 @@ def run_reference(args):
 
 
 def config_dict(args):
-    return {"workload": f"C2: full-trajectory sampling, {args.crystals} crystals x {args.atoms} atoms per GPU "
-                        f"(Alexandria-shaped), {RADIUS:g} A PBC cutoff, max_neighbors {args.cap}, T={T_STEPS} "
+    tag = "C2" if (args.crystals, args.atoms) == (1024, 40) else ("C3" if args.atoms >= 200 else "custom")
+    return {"workload": f"{tag}: full-trajectory sampling, {args.crystals} crystals x {args.atoms} atoms per GPU "
+                        f"(Alexandria-shaped), {args.radius:g} A PBC cutoff, max_neighbors {args.cap}, T={T_STEPS} "
                         f"(999 denoise steps per trajectory)",
             "model": "random-init reference architecture, 1 170 678 params (hidden 128, basis 256, 5 layers, 16 ori), "
                      "length read-out calibrated (SURVEY B7)",
             "crystals_per_gpu": args.crystals, "atoms_per_crystal": args.atoms, "max_neighbors": args.cap,
+            "state": ("free-running from the reference sampler init (t=999)" if args.state == "sampler" else
+                      f"teacher-forced at t={args.t0} (reference forward noising of the synthetic crystals)"),
             "l2": "inputs larger than L2 (per-layer kernel slabs >= 1.3 GB, node features 335 MB)",
             "parallelism": f"crystal-sharded x{args.gpus}, no per-step collective"}
 
@@ -181,7 +202,12 @@ def main():
     ap.add_argument("--crystals", type=int, default=1024)
     ap.add_argument("--atoms", type=int, default=40)
     ap.add_argument("--cap", type=int, default=8)
-    ap.add_argument("--ref-crystals", type=int, default=16)
+    ap.add_argument("--radius", type=float, default=RADIUS)
+    ap.add_argument("--ref-crystals", type=int, default=64)
+    ap.add_argument("--state", default="sampler", choices=["sampler", "teacher"],
+                    help="sampler: free-running from the reference sampler's init at t=999 (the headline); teacher: "
+                         "teacher-forced state at --t0 (needed for uncapped graphs, whose 1 A initial cells are all images)")
+    ap.add_argument("--t0", type=int, default=500)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-other-precision", action="store_true")
     args = ap.parse_args()
@@ -208,9 +234,14 @@ def main():
     G, n = args.crystals, args.atoms
     N = G * n
     sd, ori, fw = load_weights(n)
-    eng = DenoiseEngine(PonitaWeights(sd, ori, device=dev), build_tables(T_STEPS, Z), fw, [n] * G, RADIUS, args.cap,
+    eng = DenoiseEngine(PonitaWeights(sd, ori, device=dev), build_tables(T_STEPS, Z), fw, [n] * G, args.radius, args.cap,
                         precision=args.precision, device=dev)
-    frac, types, lengths, angles = sampler_init(G, n, seed=1234 + rank)
+    if args.state == "teacher":
+        frac, types, lengths, angles = teacher_state(G, n, 1234 + rank, args.t0)
+        t_start = args.t0
+    else:
+        frac, types, lengths, angles = sampler_init(G, n, seed=1234 + rank)
+        t_start = T_STEPS - 1
     eng.set_state(frac, types, lengths, angles)
     seed = 99 + rank
 
@@ -221,7 +252,7 @@ def main():
             torch.cuda.synchronize(dev)
 
     # ---- device-resident trajectory steps -------------------------------------------------------------
-    t = T_STEPS - 1
+    t = t_start
     for i in range(max(args.warmup, 3)):
         eng.draw_noise(seed, i)
         eng.step(t); t -= 1
@@ -255,8 +286,12 @@ def main():
     # ---- end to end: state + noise from pinned host memory every step, result read back --------------
     pin = lambda a: torch.as_tensor(a).pin_memory()  # noqa: E731
     g = torch.Generator().manual_seed(5 + rank)
-    h_in = [pin(torch.randn(N, 3, generator=g, dtype=torch.float64)), pin(torch.as_tensor(types)),
-            pin(torch.as_tensor(np.abs(lengths) + 5.0)), pin(torch.as_tensor(angles))]
+    if args.state == "teacher":
+        h_in = [pin(torch.as_tensor(frac)), pin(torch.as_tensor(types)), pin(torch.as_tensor(lengths)),
+                pin(torch.as_tensor(angles))]
+    else:
+        h_in = [pin(torch.randn(N, 3, generator=g, dtype=torch.float64)), pin(torch.as_tensor(types)),
+                pin(torch.as_tensor(np.abs(lengths) + 5.0)), pin(torch.as_tensor(angles))]
     h_noise = [pin(torch.randn(G, 3, generator=g, dtype=torch.float64)), pin(torch.randn(N, 3, generator=g, dtype=torch.float64)),
                pin(torch.rand(N, Z, generator=g, dtype=torch.float64))]
     h_out = [torch.empty(N, 3, dtype=torch.float64).pin_memory(), torch.empty(N, dtype=torch.int64).pin_memory(),
@@ -345,10 +380,10 @@ def main():
             other = "fp32" if args.precision == "fp16" else "fp16"
             del eng
             torch.cuda.empty_cache()
-            eng2 = DenoiseEngine(PonitaWeights(sd, ori, device=dev), build_tables(T_STEPS, Z), fw, [n] * G, RADIUS, args.cap,
+            eng2 = DenoiseEngine(PonitaWeights(sd, ori, device=dev), build_tables(T_STEPS, Z), fw, [n] * G, args.radius, args.cap,
                                  precision=other, device=dev)
             eng2.set_state(frac, types, lengths, angles)
-            t2 = T_STEPS - 1
+            t2 = t_start
             for i in range(3):
                 eng2.draw_noise(seed, i); eng2.step(t2); t2 -= 1
             torch.cuda.synchronize(dev)
@@ -363,7 +398,7 @@ def main():
                                             "unit": "crystals/s"}
         if not args.no_cpu_baseline and world == 1:
             cores = os.cpu_count() or 1
-            t_cpu, epa = oracle_step_time(args.ref_crystals, n, 3, 1, args.cap, cores)
+            t_cpu, epa = oracle_step_time(args.ref_crystals, n, 3, 1, args.cap, cores, args.radius)
             line["cpu_baseline"] = {"value": args.ref_crystals / ((T_STEPS - 1) * t_cpu), "unit": "crystals/s", "cores": cores,
                                     "kind": "port", "ms_per_step_sample": t_cpu * 1e3,
                                     "sample": f"{args.ref_crystals} crystals x {n} atoms, 3 denoise steps (+1 warm-up), "

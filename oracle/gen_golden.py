@@ -392,12 +392,110 @@ def gen_model_goldens(ref):
     print("sample_T11.npz done")
 
 
+def gen_training(ref):
+    """Training step: the LIVE reference's DiffusionLoss.__call__ + loss.backward() on a small
+    C5-shaped batch; pins oracle/training.py (loss, every intermediate, every parameter gradient) and the
+    callibrate pass, and writes tests/golden/train_c5small.npz."""
+    from oracle import training as TR
+    T, radius, cap = 1000, 5.0, 8
+    w = np.load(os.path.join(GOLD, "weights_seed0.npz"))
+    m = build_reference_model(ref, T, radius, cap, seed=0)
+    sd = {k: torch.as_tensor(w[k], dtype=torch.float64) for k in w.files if k not in ("ori_grid", "fourier_w")}
+    ori, fw = T64(w["ori_grid"]), T64(w["fourier_w"])
+    load_state(m, sd)
+    m.model.transform.transforms[0].ori_grid_s2 = ori.clone()
+    with torch.no_grad():
+        m.t_emb.gaussian_fourier_proj_w.copy_(fw)
+    m.train()                                      # callibrated is already True: train == eval numerics
+    W = oracle_weights(sd, ori, radius)
+    tabs = R.DiffusionTables.build(T, Z)
+    out = {}
+    for case, (G, lo, hi, seed) in enumerate([(6, 2, 12, 31), (4, 1, 30, 32)]):
+        cr = make_crystals(G, lo, hi, seed=seed)
+        na = I64(cr.num_atoms)
+        N = cr.total_atoms
+        L0 = R.lattice_from_params(T64(cr.lengths), T64(cr.angles))
+        batch = ref.Batch(X0=T64(cr.frac), A0=I64(cr.types), L0=L0.reshape(-1, 3).clone(), num_atoms=na,
+                          batch=torch.repeat_interleave(torch.arange(G), na))
+        m.zero_grad()
+        torch.manual_seed(500 + case)
+        with torch.enable_grad(), ref_loader.stable_sort():
+            loss = m.diffusion_loss(m, batch, m.t_emb)
+            loss.backward()
+        torch.manual_seed(500 + case)
+        timestep, eps_x, u, eps_l = TR.draw_training_noise(G, N, Z, T)
+        with torch.enable_grad():
+            o_loss, o_grads, parts = TR.training_grads(W, tabs, fw, T64(cr.frac), I64(cr.types), L0, na, timestep, eps_x,
+                                                       u, eps_l, radius, cap)
+        assert abs(o_loss.item() - loss.item()) <= 1e-12 * max(1.0, abs(loss.item())), (o_loss.item(), loss.item())
+        ref_grads = {k: p.grad for k, p in m.model.named_parameters() if p.numel() and p.grad is not None}
+        assert set(ref_grads) == set(o_grads), set(ref_grads) ^ set(o_grads)
+        worst = 0.0
+        for k, g in ref_grads.items():
+            err = (g - o_grads[k]).abs().max().item() / max(g.abs().max().item(), 1e-30)
+            worst = max(worst, err)
+            assert err < 1e-9, (k, err)
+        p = f"{case}/"
+        out.update({p + "frac0": cr.frac, p + "types0": cr.types, p + "lattice0": L0.numpy(), p + "num_atoms": cr.num_atoms,
+                    p + "timestep": timestep.numpy(), p + "eps_x": eps_x.numpy(), p + "u": u.numpy(),
+                    p + "eps_l": eps_l.numpy(), p + "loss": np.float64(loss.item())})
+        for k in ("noisy_frac", "target_eps", "noisy_types", "lengths", "angles", "noisy_lengths", "pred_eps",
+                  "pred_logits", "pred_len", "e_frac", "e_type", "vb", "ce", "e_lat"):
+            out[p + k] = parts[k].numpy()
+        for k, g in ref_grads.items():        # case 0: full gradients (fp32); others: norms + leading entries
+            if case == 0:
+                out[p + "grad/" + k] = g.numpy().astype(np.float32)
+            else:
+                out[p + "gradnorm/" + k] = np.float64(g.norm().item())
+                out[p + "gradhead/" + k] = g.reshape(-1)[:64].numpy()
+        print(f"  train case {case}: G={G} N={N} loss={loss.item():.6f} (frac {parts['e_frac']:.4f} type "
+              f"{parts['e_type']:.4f} lat {parts['e_lat']:.4f}) worst grad err {worst:.2e}")
+
+    # ---- callibrate: the reference's first train-mode forward (flags reset) vs the restated pass ----
+    # "before" weights = the committed weights_seed0.npz, so only the rescaled matrices need storing
+    for layer in m.model.interaction_layers:
+        layer.conv.callibrated = torch.tensor(False)
+    cr = make_crystals(6, 3, 14, seed=41)
+    na = I64(cr.num_atoms)
+    G, N = cr.num_crystals, cr.total_atoms
+    batch = ref.Batch(num_atoms=na, batch=torch.repeat_interleave(torch.arange(G), na))
+    t = torch.full((N,), 300, dtype=torch.long)
+    onehot = torch.nn.functional.one_hot(I64(cr.types), Z)
+    m.train()
+    with torch.no_grad(), ref_loader.stable_sort():
+        m.diffusion_loss.predict_scores(T64(cr.frac), onehot, t, na, T64(cr.lengths), T64(cr.angles), m, batch, m.t_emb)
+    assert all(bool(layer.conv.callibrated) for layer in m.model.interaction_layers)
+    sd_after, _, _ = export_weights(m)
+    lat = R.lattice_from_params(T64(cr.lengths), T64(cr.angles))
+    rep = lambda a: torch.repeat_interleave(a, na, dim=0)  # noqa: E731
+    x = torch.cat([onehot, R.fourier_time_embedding(tabs.vp_betas[t].view(-1, 1), fw), rep(na).unsqueeze(-1),
+                   rep(T64(cr.lengths)), rep(T64(cr.angles)), rep((T64(cr.lengths) / na.unsqueeze(-1)).abs())], dim=1)
+    vec = torch.cat([T64(cr.frac).unsqueeze(1), rep(lat)], dim=1)
+    bvec = torch.repeat_interleave(torch.arange(G), na)
+    ei, _, _, dist, direction = R.radius_graph_pbc(R.frac_to_cart_coords(T64(cr.frac), lat, na), lat, na, radius, cap)
+    new = TR.calibrate(W, x, vec, ei, dist, direction, lat, bvec, G)
+    for k in sd_after:
+        err = (new[k] - sd_after[k]).abs().max().item() / max(sd_after[k].abs().max().item(), 1e-30)
+        assert err < 1e-10, (k, err)
+    out.update({"cal/frac": cr.frac, "cal/types": cr.types, "cal/lengths": cr.lengths, "cal/angles": cr.angles,
+                "cal/num_atoms": cr.num_atoms, "cal/timestep": np.int64(300)})
+    for k in sd_after:
+        if "conv.kernel.weight" in k or "conv.fiber_kernel.weight" in k:
+            out["cal/after/" + k] = sd_after[k].numpy().astype(np.float32)
+            print(f"  callibrate {k}: x{(sd_after[k].abs().max() / sd[k].abs().max()).item():.4f}")
+    np.savez_compressed(os.path.join(GOLD, "train_c5small.npz"), **out)
+    print("train_c5small.npz done")
+
+
 def main():
     os.makedirs(GOLD, exist_ok=True)
     ref = ref_loader.import_reference()
+    if "--training-only" in sys.argv:
+        return gen_training(ref)
     gen_kats(ref)
     gen_graph_cases(ref)
     gen_model_goldens(ref)
+    gen_training(ref)
 
 
 if __name__ == "__main__":
