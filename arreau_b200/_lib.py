@@ -51,6 +51,13 @@ class StepArgs(C.Structure):
         ("precision", i32), ("update_types", i32)]
 
 
+class TrainLayout(C.Structure):
+    FIELDS = ("basis_w1", "basis_b1", "basis_w2", "basis_b2", "fiber_w1", "fiber_b1", "fiber_w2", "fiber_b2", "embed_w",
+              "layer_scale", "conv_bias", "conv_kernel_w", "conv_fiber_w", "lin1_w", "lin1_b", "lin2_w", "lin2_b",
+              "norm_w", "norm_b", "readout_w", "readout_b", "total")
+    _fields_ = [(n, i64) for n in FIELDS]
+
+
 # name -> argtypes (restype is int unless noted); must list every symbol include/arreau_b200.h declares
 SIGNATURES = {
     "arreau_abi_version": [],
@@ -79,8 +86,21 @@ SIGNATURES = {
     "arreau_d3pm_reverse": [vp, vp, vp, vp, i32, vp, vp, f64, f64, i32, i32, i32, vp, vp],
     "arreau_step_noise": [C.c_uint64, i32, i32, i32, i32, vp, vp, vp, vp],
     "arreau_denoise_step": [C.POINTER(Weights), C.POINTER(Workspace), C.POINTER(StepArgs), vp],
+    # training step
+    "arreau_matrix_to_params": [vp, i32, vp, vp, vp],
+    "arreau_ve_pbc_forward": [vp, vp, vp, vp, vp, vp, i32, vp, vp, vp],
+    "arreau_vp_lattice_forward": [vp, vp, vp, vp, i32, vp, vp],
+    "arreau_d3pm_q_sample": [vp, vp, vp, vp, vp, i32, i32, vp, vp],
+    "arreau_training_loss": [vp, vp, vp, vp, vp, vp, vp, vp, vp, vp, vp, f64, f64, i32, i32, i32, i32, f64, vp, vp, vp,
+                             vp, vp, vp],
+    "arreau_train_layout": [i32, i32, i32, C.POINTER(TrainLayout)],
+    "arreau_ponita_backward_workspace_bytes": [i32, i64, i32, i32],
+    "arreau_ponita_backward": [vp, C.POINTER(TrainLayout), C.POINTER(Weights), C.POINTER(Workspace), vp, vp, vp, vp, vp,
+                               vp, vp, vp, vp, vp, vp, i32, i32, f64, vp, vp, vp, vp, i64, vp, vp],
+    "arreau_sgemm": [i32, i32, vp, i64, vp, i64, vp, i64, i32, i32, i64, C.c_float, vp, i32, vp, i64, vp],
+    "arreau_moments": [vp, vp, i64, vp, vp, vp],
 }
-RESTYPES = {"arreau_launch_count": i64}
+RESTYPES = {"arreau_launch_count": i64, "arreau_ponita_backward_workspace_bytes": i64}
 
 
 def library_path() -> str:

@@ -1,0 +1,922 @@
+// Backward pass of the Ponita fiber-bundle network (training step) in fp32, sm_100a.
+//
+// The reference obtains parameter gradients with torch autograd through
+//   ponita/models/ponita.py:88-155, ponita/nn/conv.py:105-133, ponita/nn/convnext.py:20-33,
+//   ponita/nn/embedding.py:4-14, ponita/utils/windowing.py:21-29, ponita/utils/to_from_sphere.py:4-14
+// (inputs carry no gradient: positions, lattice and the graph are data).  Here the same derivatives are
+// written out by hand as a fixed sequence of kernels on one stream:
+//
+//   * every dense contraction (recomputed activations, input gradients, weight gradients) goes through ONE
+//     tiled fp32 SIMT GEMM (sgemm_kernel: 128x128x16 tiles, packed FFMA2, register-staged double buffering)
+//     that reads either operand in either storage order, so that the parameters and their gradients stay in
+//     the reference's own state_dict layouts ([out, in] row-major) with no transposed copies;
+//   * weight gradients reduce over the rows (edges x orientations, or atoms x orientations): split-K with
+//     per-split partial tiles and a fixed-order second stage -- no atomics, bit-reproducible run to run;
+//   * the message pass is transposed with a sender-side gather in edge order (deterministic) instead of
+//     scatter atomics.
+//
+// The forward pass of a training step is the ordinary fp32 forward (arreau_ponita_forward) run with its
+// per-layer buffers kept (h, x1, x2 of every layer and the per-layer spatial kernels).
+#include "common.cuh"
+
+namespace {
+
+// ================================================================================================
+// generic fp32 GEMM   C[M,N] (=|+=) alpha * A x B (+ bias[n])
+//   AK: A stored [M][K] (K contiguous, row pitch lda)   else [K][M] (M contiguous)
+//   BK: B stored [N][K] (K contiguous, row pitch ldb)   else [K][N] (N contiguous)
+// grid = (ceil(N/128), ceil(M/128), splits); with splits > 1 the raw tile sums go to
+// partial[split][M][N] and sgemm_reduce_kernel finishes (alpha, bias, accumulate).
+// Requirements: K-contiguous operands need K % 4 == 0 and pitch % 4 == 0; the other storage order needs
+// the contiguous extent % 4 == 0; pointers 16-byte aligned.
+// ================================================================================================
+constexpr int kBM = 128, kBN = 128, kBK = 16, kSP = 132, kGT = 256;
+
+template <bool KCONTIG>
+__device__ __forceinline__ void tile_fetch(const float* __restrict__ X, long long ld, int x0, int xext, long long k0,
+                                           long long kend, int tid, float4 (&r)[2]) {
+  // KCONTIG: X[x][k]: float4 v -> x = v >> 2, k = (v & 3) * 4 ; else X[k][x]: v -> k = v >> 5, x = (v & 31) * 4
+#pragma unroll
+  for (int u = 0; u < 2; ++u) {
+    const int v = tid + u * kGT;
+    r[u] = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (KCONTIG) {
+      const int x = x0 + (v >> 2);
+      const long long k = k0 + (v & 3) * 4;
+      if (x < xext && k < kend) r[u] = __ldg(reinterpret_cast<const float4*>(X + (long long)x * ld + k));
+    } else {
+      const long long k = k0 + (v >> 5);
+      const int x = x0 + (v & 31) * 4;
+      if (k < kend && x < xext) r[u] = __ldg(reinterpret_cast<const float4*>(X + k * ld + x));
+    }
+  }
+}
+
+template <bool KCONTIG>
+__device__ __forceinline__ void tile_stage(float* __restrict__ S, int tid, const float4 (&r)[2]) {
+#pragma unroll
+  for (int u = 0; u < 2; ++u) {
+    const int v = tid + u * kGT;
+    if (KCONTIG) {
+      const int x = v >> 2, k = (v & 3) * 4;
+      S[(k + 0) * kSP + x] = r[u].x;
+      S[(k + 1) * kSP + x] = r[u].y;
+      S[(k + 2) * kSP + x] = r[u].z;
+      S[(k + 3) * kSP + x] = r[u].w;
+    } else {
+      const int k = v >> 5, x = (v & 31) * 4;
+      *reinterpret_cast<float4*>(S + k * kSP + x) = r[u];
+    }
+  }
+}
+
+template <bool AK, bool BK>
+__global__ void __launch_bounds__(kGT)
+sgemm_kernel(const float* __restrict__ A, long long lda, const float* __restrict__ B, long long ldb, float* __restrict__ C,
+             long long ldc, int M, int N, long long K, long long k_per_split, float alpha,
+             const float* __restrict__ bias, int accumulate, float* __restrict__ partial) {
+  __shared__ __align__(16) float As[2][kBK * kSP];
+  __shared__ __align__(16) float Bs[2][kBK * kSP];
+  const int tid = threadIdx.x, ty = tid >> 4, tx = tid & 15;
+  const int m0 = blockIdx.y * kBM, n0 = blockIdx.x * kBN;
+  const long long kbeg = (long long)blockIdx.z * k_per_split;
+  const long long kend = (kbeg + k_per_split < K) ? kbeg + k_per_split : K;
+  float2 acc[8][4];
+#pragma unroll
+  for (int i = 0; i < 8; ++i)
+#pragma unroll
+    for (int j = 0; j < 4; ++j) acc[i][j] = make_float2(0.f, 0.f);
+  float4 ra[2], rb[2];
+  if (kbeg < kend) {
+    tile_fetch<AK>(A, lda, m0, M, kbeg, kend, tid, ra);
+    tile_fetch<BK>(B, ldb, n0, N, kbeg, kend, tid, rb);
+    tile_stage<AK>(As[0], tid, ra);
+    tile_stage<BK>(Bs[0], tid, rb);
+  }
+  __syncthreads();
+  int buf = 0;
+  for (long long k0 = kbeg; k0 < kend; k0 += kBK) {
+    const bool more = k0 + kBK < kend;
+    if (more) {
+      tile_fetch<AK>(A, lda, m0, M, k0 + kBK, kend, tid, ra);
+      tile_fetch<BK>(B, ldb, n0, N, k0 + kBK, kend, tid, rb);
+    }
+    const float* a = As[buf];
+    const float* b = Bs[buf];
+#pragma unroll
+    for (int k = 0; k < kBK; ++k) {
+      const float4 a0 = *reinterpret_cast<const float4*>(a + k * kSP + ty * 4);
+      const float4 a1 = *reinterpret_cast<const float4*>(a + k * kSP + 64 + ty * 4);
+      const float4 b0 = *reinterpret_cast<const float4*>(b + k * kSP + tx * 4);
+      const float4 b1 = *reinterpret_cast<const float4*>(b + k * kSP + 64 + tx * 4);
+      const float av[8] = {a0.x, a0.y, a0.z, a0.w, a1.x, a1.y, a1.z, a1.w};
+      const float2 bv[4] = {make_float2(b0.x, b0.y), make_float2(b0.z, b0.w), make_float2(b1.x, b1.y),
+                            make_float2(b1.z, b1.w)};
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        const float2 aa = make_float2(av[i], av[i]);
+#pragma unroll
+        for (int j = 0; j < 4; ++j) acc[i][j] = __ffma2_rn(aa, bv[j], acc[i][j]);
+      }
+    }
+    if (more) {
+      tile_stage<AK>(As[buf ^ 1], tid, ra);
+      tile_stage<BK>(Bs[buf ^ 1], tid, rb);
+    }
+    __syncthreads();
+    buf ^= 1;
+  }
+  const bool split = gridDim.z > 1;
+  float* out = split ? partial + (size_t)blockIdx.z * M * N : C;
+  const long long ldo = split ? (long long)N : ldc;
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    const int m = m0 + ((i < 4) ? (ty * 4 + i) : (64 + ty * 4 + i - 4));
+    if (m >= M) continue;
+#pragma unroll
+    for (int half = 0; half < 2; ++half) {
+      const int n = n0 + half * 64 + tx * 4;
+      if (n >= N) continue;
+      float4 v = make_float4(acc[i][half * 2].x, acc[i][half * 2].y, acc[i][half * 2 + 1].x, acc[i][half * 2 + 1].y);
+      float* p = out + (long long)m * ldo + n;
+      if (!split) {
+        v.x *= alpha; v.y *= alpha; v.z *= alpha; v.w *= alpha;
+        if (bias) {
+          const float4 bb = *reinterpret_cast<const float4*>(bias + n);
+          v.x += bb.x; v.y += bb.y; v.z += bb.z; v.w += bb.w;
+        }
+        if (accumulate) {
+          const float4 c = *reinterpret_cast<const float4*>(p);
+          v.x += c.x; v.y += c.y; v.z += c.z; v.w += c.w;
+        }
+      }
+      *reinterpret_cast<float4*>(p) = v;
+    }
+  }
+}
+
+// second stage of every split reduction: out[i] (=|+=) alpha * sum_s partial[s][i] (fixed order)
+__global__ void reduce_partials_kernel(const float* __restrict__ partial, int splits, long long n, long long ldo, int ncols,
+                                       float alpha, int accumulate, float* __restrict__ out) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  float s = 0.f;
+  for (int k = 0; k < splits; ++k) s += partial[(size_t)k * n + i];
+  s *= alpha;
+  float* p = out + (i / ncols) * ldo + (i % ncols);
+  *p = accumulate ? *p + s : s;
+}
+
+struct Gemm {
+  cudaStream_t s;
+  float* partial;          // split-K scratch
+  size_t partial_floats;
+  int sms;
+};
+
+// op: C[M,N] (=|+=) alpha A B (+bias).  Returns ARREAU_* / cudaError.
+template <bool AK, bool BK>
+int gemm(const Gemm& g, const float* A, long long lda, const float* B, long long ldb, float* C, long long ldc, int M,
+         int N, long long K, float alpha, const float* bias, bool accumulate) {
+  if (M <= 0 || N <= 0) return ARREAU_OK;
+  const int tiles = ((M + kBM - 1) / kBM) * ((N + kBN - 1) / kBN);
+  int splits = 1;
+  if (K > 4096 && tiles < g.sms) {      // reduction-dominated (weight gradients): split the rows
+    splits = (2 * g.sms + tiles - 1) / tiles;
+    const long long max_by_k = (K + 511) / 512;
+    if (splits > max_by_k) splits = (int)max_by_k;
+    while (splits > 1 && (size_t)splits * M * N > g.partial_floats) --splits;
+  }
+  long long kps = (K + splits - 1) / splits;
+  kps = (kps + kBK - 1) / kBK * kBK;
+  splits = (int)((K + kps - 1) / kps);
+  if (splits < 1) splits = 1;
+  dim3 grid((N + kBN - 1) / kBN, (M + kBM - 1) / kBM, splits);
+  sgemm_kernel<AK, BK><<<grid, kGT, 0, g.s>>>(A, lda, B, ldb, C, ldc, M, N, K, kps, alpha, splits == 1 ? bias : nullptr,
+                                              accumulate ? 1 : 0, g.partial);
+  CUDA_LAUNCH_CHECK();
+  if (splits > 1) {
+    if (bias) return ARREAU_ERR_UNSUPPORTED;
+    const long long n = (long long)M * N;
+    reduce_partials_kernel<<<(unsigned)((n + 255) / 256), 256, 0, g.s>>>(g.partial, splits, n, ldc, N, alpha,
+                                                                         accumulate ? 1 : 0, C);
+    CUDA_LAUNCH_CHECK();
+  }
+  return ARREAU_OK;
+}
+
+// ================================================================================================
+// column sums over rows (bias / scale gradients): out[c] (=|+=) sum_r X[r][c] (* Y[r][c])
+// two stages, fixed order.  ncols % 128 == 0.
+// ================================================================================================
+constexpr int kColSplits = 128;
+
+template <bool PROD>
+__global__ void __launch_bounds__(128)
+colsum_kernel(const float* __restrict__ X, const float* __restrict__ Y, long long rows, int ncols, long long ld,
+              float* __restrict__ partial) {
+  const int c = blockIdx.x * 128 + threadIdx.x;
+  const long long per = (rows + gridDim.y - 1) / gridDim.y;
+  const long long r0 = (long long)blockIdx.y * per, r1 = (r0 + per < rows) ? r0 + per : rows;
+  float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f;
+  long long r = r0;
+  for (; r + 4 <= r1; r += 4) {
+    float a0 = X[(r + 0) * ld + c], a1 = X[(r + 1) * ld + c], a2 = X[(r + 2) * ld + c], a3 = X[(r + 3) * ld + c];
+    if (PROD) {
+      a0 *= Y[(r + 0) * ld + c]; a1 *= Y[(r + 1) * ld + c]; a2 *= Y[(r + 2) * ld + c]; a3 *= Y[(r + 3) * ld + c];
+    }
+    s0 += a0; s1 += a1; s2 += a2; s3 += a3;
+  }
+  for (; r < r1; ++r) s0 += PROD ? X[r * ld + c] * Y[r * ld + c] : X[r * ld + c];
+  partial[(size_t)blockIdx.y * ncols + c] = (s0 + s1) + (s2 + s3);
+}
+
+int colsum(const Gemm& g, const float* X, const float* Y, long long rows, int ncols, long long ld, float* out,
+           bool accumulate) {
+  if (ncols % 128 != 0 || (size_t)kColSplits * ncols > g.partial_floats) return ARREAU_ERR_UNSUPPORTED;
+  if (rows <= 0) return ARREAU_OK;
+  int splits = (int)((rows + 63) / 64);
+  if (splits > kColSplits) splits = kColSplits;
+  dim3 grid(ncols / 128, splits);
+  if (Y) colsum_kernel<true><<<grid, 128, 0, g.s>>>(X, Y, rows, ncols, ld, g.partial);
+  else colsum_kernel<false><<<grid, 128, 0, g.s>>>(X, nullptr, rows, ncols, ld, g.partial);
+  CUDA_LAUNCH_CHECK();
+  reduce_partials_kernel<<<(ncols + 255) / 256, 256, 0, g.s>>>(g.partial, splits, ncols, ncols, ncols, 1.0f,
+                                                               accumulate ? 1 : 0, out);
+  CUDA_LAUNCH_CHECK();
+  return ARREAU_OK;
+}
+
+// ================================================================================================
+// elementwise / rowwise kernels
+// ================================================================================================
+__device__ __forceinline__ float gelu_grad(float x) {
+  // d/dx [0.5 x (1 + erf(x / sqrt 2))] = 0.5 (1 + erf(x / sqrt 2)) + x exp(-x^2 / 2) / sqrt(2 pi)
+  return 0.5f * (1.0f + erff(x * 0.70710678118654752440f)) + x * expf(-0.5f * x * x) * 0.39894228040143267794f;
+}
+
+// a = gelu(z) [* rowscale[r / rows_per_scale]]
+__global__ void gelu_fwd_kernel(const float* __restrict__ z, long long n, int ncols, const float* __restrict__ rowscale,
+                                int rows_per_scale, float* __restrict__ a) {
+  const long long i = ((long long)blockIdx.x * blockDim.x + threadIdx.x) * 4;
+  if (i >= n) return;
+  const float4 v = *reinterpret_cast<const float4*>(z + i);
+  const float sc = rowscale ? rowscale[(i / ncols) / rows_per_scale] : 1.0f;
+  *reinterpret_cast<float4*>(a + i) = make_float4(gelu_erf(v.x) * sc, gelu_erf(v.y) * sc, gelu_erf(v.z) * sc, gelu_erf(v.w) * sc);
+}
+
+// dz = da * gelu'(z) [* rowscale]      (in place on da allowed)
+__global__ void gelu_bwd_kernel(const float* __restrict__ z, const float* da, long long n, int ncols,
+                                const float* __restrict__ rowscale, int rows_per_scale, float* dz) {
+  const long long i = ((long long)blockIdx.x * blockDim.x + threadIdx.x) * 4;
+  if (i >= n) return;
+  const float4 v = *reinterpret_cast<const float4*>(z + i);
+  const float4 d = *reinterpret_cast<const float4*>(da + i);
+  const float sc = rowscale ? rowscale[(i / ncols) / rows_per_scale] : 1.0f;
+  *reinterpret_cast<float4*>(dz + i) = make_float4(d.x * gelu_grad(v.x) * sc, d.y * gelu_grad(v.y) * sc,
+                                                   d.z * gelu_grad(v.z) * sc, d.w * gelu_grad(v.w) * sc);
+}
+
+// out[r][c] = x[r][c] * colscale[c]     (ncols == kC)
+__global__ void scale_cols_kernel(const float* __restrict__ x, const float* __restrict__ colscale, long long n,
+                                  float* __restrict__ out) {
+  const long long i = ((long long)blockIdx.x * blockDim.x + threadIdx.x) * 4;
+  if (i >= n) return;
+  const float4 v = *reinterpret_cast<const float4*>(x + i);
+  const float4 s = *reinterpret_cast<const float4*>(colscale + (i & (kC - 1)));
+  *reinterpret_cast<float4*>(out + i) = make_float4(v.x * s.x, v.y * s.y, v.z * s.z, v.w * s.w);
+}
+
+__global__ void fill_kernel(float* __restrict__ p, long long n, float v) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) p[i] = v;
+}
+
+// ---- edge rows: invariants -> 83 monomials (+ constant 1, zero padding to 128) and the cutoff window ----------
+// (geometry/invariants.py:17-22, transforms/invariants.py:81-87, embedding.py:10-14, windowing.py:21-29)
+__global__ void __launch_bounds__(128)
+edge_mono_kernel(const double* __restrict__ dir, const double* __restrict__ dist, const double* __restrict__ lattice,
+                 const int32_t* __restrict__ crystal_of_atom, const int32_t* __restrict__ src,
+                 const int32_t* __restrict__ num_edges_ptr, long long edge_capacity, const float* __restrict__ ori,
+                 double radius, float* __restrict__ mono, float* __restrict__ win) {
+  const long long row = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  long long E = *num_edges_ptr;
+  if (E > edge_capacity) E = edge_capacity;
+  if (row >= edge_capacity * kO) return;
+  const long long e = row >> 4;
+  const int o = (int)(row & (kO - 1));
+  float* out = mono + row * 128;
+  if (e >= E) {
+    for (int k = 0; k < 128; ++k) out[k] = 0.f;
+    if (o == 0) win[e] = 0.f;
+    return;
+  }
+  float attr[6];
+  edge_invariants(dir + 3 * e, dist[e], lattice + 9 * (size_t)crystal_of_atom[src[e]], ori + 3 * o, attr);
+  monomials83(attr, out, 1);
+  out[kMono] = 1.0f;
+  for (int k = kMono + 1; k < 128; ++k) out[k] = 0.f;
+  if (o == 0) win[e] = cutoff_window(dist[e], radius);
+}
+
+// ---- LayerNorm over C = 128 channels, one warp per row (convnext.py:25) -------------------------------------
+__global__ void __launch_bounds__(256)
+ln_fwd_kernel(const float* __restrict__ x2, const float* __restrict__ gw, const float* __restrict__ gb, long long rows,
+              float* __restrict__ y) {
+  const long long r = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int lane = threadIdx.x & 31;
+  if (r >= rows) return;
+  const float4 t = *reinterpret_cast<const float4*>(x2 + r * kC + lane * 4);
+  const float mean = warp_sum((t.x + t.y) + (t.z + t.w)) * (1.0f / kC);
+  const float dx = t.x - mean, dy = t.y - mean, dz = t.z - mean, dw = t.w - mean;
+  const float var = warp_sum((dx * dx + dy * dy) + (dz * dz + dw * dw)) * (1.0f / kC);
+  const float rstd = 1.0f / sqrtf(var + 1e-5f);
+  const float4 w = *reinterpret_cast<const float4*>(gw + lane * 4), b = *reinterpret_cast<const float4*>(gb + lane * 4);
+  *reinterpret_cast<float4*>(y + r * kC + lane * 4) =
+      make_float4(dx * rstd * w.x + b.x, dy * rstd * w.y + b.y, dz * rstd * w.z + b.z, dw * rstd * w.w + b.w);
+}
+
+// dx2 = rstd (g - mean(g) - xhat mean(g xhat)), g = dy * gamma; per-block partials of
+// dgamma = sum dy xhat, dbeta = sum dy, dbias(conv) = sum dx2    -> partial[block][3][128]
+constexpr int kLnWarps = 8;
+__global__ void __launch_bounds__(kLnWarps * 32)
+ln_bwd_kernel(const float* __restrict__ x2, const float* __restrict__ dy, const float* __restrict__ gw, long long rows,
+              float* __restrict__ dx2, float* __restrict__ partial) {
+  __shared__ float red[kLnWarps][3][kC];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const float4 w = *reinterpret_cast<const float4*>(gw + lane * 4);
+  float4 sg = make_float4(0.f, 0.f, 0.f, 0.f), sb = sg, sx = sg;
+  for (long long r = (long long)blockIdx.x * kLnWarps + warp; r < rows; r += (long long)gridDim.x * kLnWarps) {
+    const float4 t = *reinterpret_cast<const float4*>(x2 + r * kC + lane * 4);
+    const float4 d = *reinterpret_cast<const float4*>(dy + r * kC + lane * 4);
+    const float mean = warp_sum((t.x + t.y) + (t.z + t.w)) * (1.0f / kC);
+    const float cx = t.x - mean, cy = t.y - mean, cz = t.z - mean, cw = t.w - mean;
+    const float var = warp_sum((cx * cx + cy * cy) + (cz * cz + cw * cw)) * (1.0f / kC);
+    const float rstd = 1.0f / sqrtf(var + 1e-5f);
+    const float hx = cx * rstd, hy = cy * rstd, hz = cz * rstd, hw = cw * rstd;
+    const float gx = d.x * w.x, gy = d.y * w.y, gz = d.z * w.z, gw_ = d.w * w.w;
+    const float m1 = warp_sum((gx + gy) + (gz + gw_)) * (1.0f / kC);
+    const float m2 = warp_sum((gx * hx + gy * hy) + (gz * hz + gw_ * hw)) * (1.0f / kC);
+    const float4 o = make_float4(rstd * (gx - m1 - hx * m2), rstd * (gy - m1 - hy * m2), rstd * (gz - m1 - hz * m2),
+                                 rstd * (gw_ - m1 - hw * m2));
+    *reinterpret_cast<float4*>(dx2 + r * kC + lane * 4) = o;
+    sg.x += d.x * hx; sg.y += d.y * hy; sg.z += d.z * hz; sg.w += d.w * hw;
+    sb.x += d.x; sb.y += d.y; sb.z += d.z; sb.w += d.w;
+    sx.x += o.x; sx.y += o.y; sx.z += o.z; sx.w += o.w;
+  }
+  *reinterpret_cast<float4*>(&red[warp][0][lane * 4]) = sg;
+  *reinterpret_cast<float4*>(&red[warp][1][lane * 4]) = sb;
+  *reinterpret_cast<float4*>(&red[warp][2][lane * 4]) = sx;
+  __syncthreads();
+  for (int i = threadIdx.x; i < 3 * kC; i += blockDim.x) {
+    float s = 0.f;
+    for (int k = 0; k < kLnWarps; ++k) s += red[k][i / kC][i % kC];
+    partial[(size_t)blockIdx.x * 3 * kC + i] = s;
+  }
+}
+
+// ---- fiber conv backward (conv.py:115): x2[b,p,c] = (1/O) sum_o x1[b,o,c] fk[o,p,c] ------------------------
+// dx1[b,o,c] = (1/O) sum_p dx2[b,p,c] fk[o,p,c]; thread = (atom, channel)
+__global__ void __launch_bounds__(kC)
+fiber_bwd_dx1_kernel(const float* __restrict__ dx2, const float* __restrict__ fk, int N, float* __restrict__ dx1) {
+  const int c = threadIdx.x;
+  for (int b = blockIdx.x; b < N; b += gridDim.x) {
+    float d[kO];
+#pragma unroll
+    for (int p = 0; p < kO; ++p) d[p] = dx2[((size_t)b * kO + p) * kC + c];
+#pragma unroll 4
+    for (int o = 0; o < kO; ++o) {
+      float s = 0.f;
+#pragma unroll
+      for (int p = 0; p < kO; ++p) s = fmaf(d[p], __ldg(fk + ((size_t)o * kO + p) * kC + c), s);
+      dx1[((size_t)b * kO + o) * kC + c] = s * (1.0f / kO);
+    }
+  }
+}
+
+// dfk[o,p,c] = (1/O) sum_b x1[b,o,c] dx2[b,p,c]: 1024 threads = (o pair, channel), atoms strided over blocks,
+// per-block partial [O][O][C]
+__global__ void __launch_bounds__(1024)
+fiber_bwd_dfk_kernel(const float* __restrict__ x1, const float* __restrict__ dx2, int N, float* __restrict__ partial) {
+  const int c = threadIdx.x & (kC - 1), og = threadIdx.x >> 7;   // og in 0..7 -> o = 2 og, 2 og + 1
+  float acc[2][kO];
+#pragma unroll
+  for (int i = 0; i < 2; ++i)
+#pragma unroll
+    for (int p = 0; p < kO; ++p) acc[i][p] = 0.f;
+  for (int b = blockIdx.x; b < N; b += gridDim.x) {
+    const float xa = x1[((size_t)b * kO + 2 * og) * kC + c], xb = x1[((size_t)b * kO + 2 * og + 1) * kC + c];
+#pragma unroll
+    for (int p = 0; p < kO; ++p) {
+      const float d = dx2[((size_t)b * kO + p) * kC + c];
+      acc[0][p] = fmaf(xa, d, acc[0][p]);
+      acc[1][p] = fmaf(xb, d, acc[1][p]);
+    }
+  }
+  float* out = partial + (size_t)blockIdx.x * kO * kO * kC;
+#pragma unroll
+  for (int i = 0; i < 2; ++i)
+#pragma unroll
+    for (int p = 0; p < kO; ++p) out[((size_t)(2 * og + i) * kO + p) * kC + c] = acc[i][p];
+}
+
+// ---- message pass backward (conv.py:131-133 + PyG add aggregation) -------------------------------------------
+// dkern[e,o,c] = dx1[dst_e,o,c] * h[src_e,o,c]
+__global__ void __launch_bounds__(256)
+message_bwd_dkern_kernel(const float* __restrict__ dx1, const float* __restrict__ h, const int32_t* __restrict__ src,
+                         const int32_t* __restrict__ dst, const int32_t* __restrict__ num_edges_ptr,
+                         long long edge_capacity, float* __restrict__ dkern) {
+  const long long i = ((long long)blockIdx.x * blockDim.x + threadIdx.x) * 4;
+  long long E = *num_edges_ptr;
+  if (E > edge_capacity) E = edge_capacity;
+  if (i >= edge_capacity * kO * kC) return;
+  const long long e = i / (kO * kC);
+  const int oc = (int)(i % (kO * kC));
+  float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+  if (e < E) {
+    const float4 a = *reinterpret_cast<const float4*>(dx1 + (size_t)dst[e] * kO * kC + oc);
+    const float4 b = *reinterpret_cast<const float4*>(h + (size_t)src[e] * kO * kC + oc);
+    v = make_float4(a.x * b.x, a.y * b.y, a.z * b.z, a.w * b.w);
+  }
+  *reinterpret_cast<float4*>(dkern + i) = v;
+}
+
+// dh[j,o,c] += sum_{e: src_e = j} kern[e,o,c] * dx1[dst_e,o,c]   (edges of j's crystal scanned in edge order:
+// deterministic, no atomics).  One block per sender atom; thread owns 8 of the 2048 (o,c) entries.
+__global__ void __launch_bounds__(256)
+message_bwd_dh_kernel(const float* __restrict__ kern, const float* __restrict__ dx1, const int32_t* __restrict__ row_ptr,
+                      const int32_t* __restrict__ src, const int32_t* __restrict__ dst,
+                      const int32_t* __restrict__ atom_offset, const int32_t* __restrict__ crystal_of_atom,
+                      long long edge_capacity, float* __restrict__ dh) {
+  __shared__ int s_list[256];
+  __shared__ int s_wcount[8];
+  const int j = blockIdx.x, tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int g = crystal_of_atom[j];
+  long long e_lo = row_ptr[atom_offset[g]], e_hi = row_ptr[atom_offset[g + 1]];
+  if (e_hi > edge_capacity) e_hi = edge_capacity;
+  float4 acc0 = make_float4(0.f, 0.f, 0.f, 0.f), acc1 = acc0;
+  const int i0 = tid * 4, i1 = 1024 + tid * 4;
+  for (long long base = e_lo; base < e_hi; base += 256) {
+    const long long e = base + tid;
+    const bool match = e < e_hi && src[e] == j;
+    const unsigned bal = __ballot_sync(0xffffffffu, match);
+    if (lane == 0) s_wcount[warp] = __popc(bal);
+    __syncthreads();
+    int off = 0, total = 0;
+#pragma unroll
+    for (int w = 0; w < 8; ++w) {
+      if (w < warp) off += s_wcount[w];
+      total += s_wcount[w];
+    }
+    if (match) s_list[off + __popc(bal & ((1u << lane) - 1u))] = (int)(e - base);
+    __syncthreads();
+    for (int m = 0; m < total; ++m) {
+      const long long ee = base + s_list[m];
+      const size_t ko = (size_t)ee * kO * kC, xo = (size_t)dst[ee] * kO * kC;
+      const float4 k0 = *reinterpret_cast<const float4*>(kern + ko + i0), k1 = *reinterpret_cast<const float4*>(kern + ko + i1);
+      const float4 d0 = *reinterpret_cast<const float4*>(dx1 + xo + i0), d1 = *reinterpret_cast<const float4*>(dx1 + xo + i1);
+      acc0.x = fmaf(k0.x, d0.x, acc0.x); acc0.y = fmaf(k0.y, d0.y, acc0.y);
+      acc0.z = fmaf(k0.z, d0.z, acc0.z); acc0.w = fmaf(k0.w, d0.w, acc0.w);
+      acc1.x = fmaf(k1.x, d1.x, acc1.x); acc1.y = fmaf(k1.y, d1.y, acc1.y);
+      acc1.z = fmaf(k1.z, d1.z, acc1.z); acc1.w = fmaf(k1.w, d1.w, acc1.w);
+    }
+    __syncthreads();
+  }
+  float* p = dh + (size_t)j * kO * kC;
+  float4 a = *reinterpret_cast<float4*>(p + i0), b = *reinterpret_cast<float4*>(p + i1);
+  a.x += acc0.x; a.y += acc0.y; a.z += acc0.z; a.w += acc0.w;
+  b.x += acc1.x; b.y += acc1.y; b.z += acc1.z; b.w += acc1.w;
+  *reinterpret_cast<float4*>(p + i0) = a;
+  *reinterpret_cast<float4*>(p + i1) = b;
+}
+
+// ---- read-out gradient rows (ponita.py:105-117,152; to_from_sphere.py:10-14) ---------------------------------
+// dr[(b,o)][z] for the per-orientation read-out r_l[b,o,:] of ANY layer (the layers are averaged):
+//   z < Z: dlogits[b,z] / (L O);  z == Z: sum_d dscore[b,d] ori[o,d] / (L O);  Z < z < Z+4: dlen0[g(b), z-Z-1] / (L O)
+//   columns Z+4 .. 127 are zero padding.
+__global__ void __launch_bounds__(128)
+readout_grad_rows_kernel(const float* __restrict__ dlogits, const float* __restrict__ dscore,
+                         const float* __restrict__ dlen0, const int32_t* __restrict__ crystal_of_atom,
+                         const float* __restrict__ ori, int N, int Z, float scale, float* __restrict__ dr) {
+  const long long row = blockIdx.x;
+  const int b = (int)(row >> 4), o = (int)(row & (kO - 1)), z = threadIdx.x;
+  if (b >= N) return;
+  float v = 0.f;
+  if (z < Z) v = dlogits[(size_t)b * Z + z];
+  else if (z == Z) v = dscore[3 * b] * ori[3 * o] + dscore[3 * b + 1] * ori[3 * o + 1] + dscore[3 * b + 2] * ori[3 * o + 2];
+  else if (z < Z + 4) v = dlen0[3 * crystal_of_atom[b] + (z - Z - 1)];
+  dr[row * 128 + z] = v * scale;
+}
+
+// x_lift[(b,o)][0..F) = x[b], [F..F+V) = vec[b,v] . ori[o], zero padded to `pitch` (position_orientation_graph.py:84-86)
+__global__ void __launch_bounds__(256)
+lift_rows_kernel(const float* __restrict__ x, const float* __restrict__ vec, const float* __restrict__ ori, int N, int F,
+                 int V, int pitch, float* __restrict__ xl) {
+  const long long row = blockIdx.x;
+  const int b = (int)(row >> 4), o = (int)(row & (kO - 1));
+  if (b >= N) return;
+  for (int f = threadIdx.x; f < pitch; f += blockDim.x) {
+    float v = 0.f;
+    if (f < F) v = x[(size_t)b * F + f];
+    else if (f < F + V) {
+      const float* p = vec + ((size_t)b * V + (f - F)) * 3;
+      v = p[0] * ori[3 * o] + p[1] * ori[3 * o + 1] + p[2] * ori[3 * o + 2];
+    }
+    xl[row * pitch + f] = v;
+  }
+}
+
+// fiber rows: [fa, fa^2, fa^3, 1, 0...] (16 wide), fa = ori_o . ori_p   (geometry/invariants.py:23, embedding.py)
+__global__ void fiber_rows_kernel(const float* __restrict__ ori, float* __restrict__ rows16) {
+  const int r = blockIdx.x * blockDim.x + threadIdx.x;
+  if (r >= kO * kO) return;
+  const int o = r / kO, p = r % kO;
+  const float fa = ori[3 * o] * ori[3 * p] + ori[3 * o + 1] * ori[3 * p + 1] + ori[3 * o + 2] * ori[3 * p + 2];
+  float* out = rows16 + r * 16;
+  out[0] = fa; out[1] = fa * fa; out[2] = fa * fa * fa; out[3] = 1.0f;
+  for (int k = 4; k < 16; ++k) out[k] = 0.f;
+}
+
+// folded first basis layer W1m[c][0..82] = sum of basis_fn.1.weight columns of equal monomials, [83] = bias, rest 0
+// (pitch 128), and the gradient scatter back: dW1[c][f] = dW1m[c][fold[f]], db1[c] = dW1m[c][83]
+__global__ void fold_w1_kernel(const float* __restrict__ w1, const float* __restrict__ b1, const int32_t* __restrict__ fold,
+                               int nfeat, float* __restrict__ w1m) {
+  const int c = blockIdx.x, k = threadIdx.x;   // 128 threads
+  float s = 0.f;
+  if (k < kMono) {
+    for (int f = 0; f < nfeat; ++f)
+      if (fold[f] == k) s += w1[(size_t)c * nfeat + f];
+  } else if (k == kMono) {
+    s = b1[c];
+  }
+  w1m[c * 128 + k] = s;
+}
+__global__ void unfold_w1_grad_kernel(const float* __restrict__ dw1m, const int32_t* __restrict__ fold, int nfeat,
+                                      float* __restrict__ dw1, float* __restrict__ db1) {
+  const int c = blockIdx.x;
+  for (int f = threadIdx.x; f < nfeat; f += blockDim.x) dw1[(size_t)c * nfeat + f] = dw1m[c * 128 + fold[f]];
+  if (threadIdx.x == 0) db1[c] = dw1m[c * 128 + kMono];
+}
+// fiber first layer: W1f16[c][0..2] = fiber_basis_fn.1.weight[c], [3] = bias, rest 0 (pitch 16) and back
+__global__ void pack_fiber_w1_kernel(const float* __restrict__ w1, const float* __restrict__ b1, float* __restrict__ w16) {
+  const int c = blockIdx.x, k = threadIdx.x;   // 16 threads
+  w16[c * 16 + k] = k < 3 ? w1[c * 3 + k] : (k == 3 ? b1[c] : 0.f);
+}
+__global__ void unpack_fiber_w1_grad_kernel(const float* __restrict__ d16, float* __restrict__ dw1, float* __restrict__ db1) {
+  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= kC) return;
+  dw1[c * 3] = d16[c * 16]; dw1[c * 3 + 1] = d16[c * 16 + 1]; dw1[c * 3 + 2] = d16[c * 16 + 2];
+  db1[c] = d16[c * 16 + 3];
+}
+
+// sum and sum of squares of a tensor in fp64 (std for FiberBundleConv.callibrate, conv.py:122-123): two stages
+__global__ void __launch_bounds__(256)
+moments_kernel(const float* __restrict__ x, const float* __restrict__ sub_cols, long long n, double* __restrict__ partial) {
+  __shared__ double sh[2][8];
+  double s = 0.0, q = 0.0;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+    double v = (double)x[i];
+    if (sub_cols) v -= (double)sub_cols[i & (kC - 1)];
+    s += v;
+    q += v * v;
+  }
+  s = warp_sum(s);
+  q = warp_sum(q);
+  if ((threadIdx.x & 31) == 0) { sh[0][threadIdx.x >> 5] = s; sh[1][threadIdx.x >> 5] = q; }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    double ts = 0.0, tq = 0.0;
+    for (int k = 0; k < 8; ++k) { ts += sh[0][k]; tq += sh[1][k]; }
+    partial[2 * blockIdx.x] = ts;
+    partial[2 * blockIdx.x + 1] = tq;
+  }
+}
+__global__ void moments_finish_kernel(const double* __restrict__ partial, int blocks, double* __restrict__ out) {
+  if (threadIdx.x == 0 && blockIdx.x == 0) {
+    double s = 0.0, q = 0.0;
+    for (int k = 0; k < blocks; ++k) { s += partial[2 * k]; q += partial[2 * k + 1]; }
+    out[0] = s;
+    out[1] = q;
+  }
+}
+
+int sm_count() {
+  static int sms = 0;
+  if (!sms) {
+    int dev = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    if (sms <= 0) sms = 148;
+  }
+  return sms;
+}
+
+inline unsigned blocks_for(long long n, int per_block) { return (unsigned)((n + per_block - 1) / per_block); }
+
+#define TRY(call)                          \
+  do {                                     \
+    const int rc__ = (call);               \
+    if (rc__ != ARREAU_OK) return rc__;    \
+  } while (0)
+
+// carve a float workspace
+struct Carver {
+  float* base;
+  size_t used = 0;
+  explicit Carver(float* b) : base(b) {}
+  float* take(size_t n) {
+    float* p = base ? base + used : nullptr;
+    used += (n + 63) & ~(size_t)63;      // 256-byte granules
+    return p;
+  }
+};
+
+constexpr size_t kPartialFloats = (size_t)4 << 20;   // 16 MB of split scratch
+constexpr int kDfkBlocks = 64;
+constexpr int kLnBlocks = 296;
+
+struct BwdBuffers {
+  // edge rows (Re = edge_capacity * O)
+  float *mono, *z1, *a1, *z2, *kb, *dkb, *dkern, *da1, *win;
+  // node rows (Rn = N * O)
+  float *dh, *dr, *y, *z, *a, *m, *da, *dy, *dx2, *dx1, *xl;
+  // fiber chain (256 rows)
+  float *frow, *fz1, *fa1, *fz2, *fkb, *dfk, *dfkb, *fda1, *fw16, *fdw16;
+  float *w1m, *dw1m, *partial, *small;   // small: [128 x 512] scratch for narrow outputs
+  size_t total;
+};
+
+BwdBuffers carve(float* base, long long N, long long Ecap, int xl_pitch) {
+  Carver c(base);
+  BwdBuffers b;
+  const size_t Re = (size_t)Ecap * kO, Rn = (size_t)N * kO;
+  b.mono = c.take(Re * 128); b.z1 = c.take(Re * kC); b.a1 = c.take(Re * kC); b.z2 = c.take(Re * kD);
+  b.kb = c.take(Re * kD); b.dkb = c.take(Re * kD); b.dkern = c.take(Re * kC); b.da1 = c.take(Re * kC);
+  b.win = c.take((size_t)Ecap);
+  b.dh = c.take(Rn * kC); b.dr = c.take(Rn * 128); b.y = c.take(Rn * kC); b.z = c.take(Rn * kW); b.a = c.take(Rn * kW);
+  b.m = c.take(Rn * kC); b.da = c.take(Rn * kW); b.dy = c.take(Rn * kC); b.dx2 = c.take(Rn * kC);
+  b.dx1 = c.take(Rn * kC); b.xl = c.take(Rn * xl_pitch);
+  const size_t Rf = kO * kO;
+  b.frow = c.take(Rf * 16); b.fz1 = c.take(Rf * kC); b.fa1 = c.take(Rf * kC); b.fz2 = c.take(Rf * kD);
+  b.fkb = c.take(Rf * kD); b.dfk = c.take((size_t)kL * Rf * kC); b.dfkb = c.take(Rf * kD); b.fda1 = c.take(Rf * kC);
+  b.fw16 = c.take(kC * 16); b.fdw16 = c.take(kC * 16);
+  b.w1m = c.take(kC * 128); b.dw1m = c.take(kC * 128);
+  b.partial = c.take(kPartialFloats);
+  b.small = c.take((size_t)128 * 512);
+  b.total = c.used;
+  return b;
+}
+
+}  // namespace
+
+// ================================================================================================
+// C ABI
+// ================================================================================================
+extern "C" int arreau_train_layout(int32_t num_scalar, int32_t num_vec, int32_t num_states, arreau_train_layout_t* lay) {
+  if (!lay) return ARREAU_ERR_NULL;
+  if (num_scalar <= 0 || num_vec < 0 || num_states <= 0) return ARREAU_ERR_BAD_SHAPE;
+  const int64_t R = num_states + 4, FV = num_scalar + num_vec;
+  int64_t o = 0;
+  auto put = [&](int64_t& field, int64_t n) { field = o; o += n; };
+  put(lay->basis_w1, (int64_t)kC * 258); put(lay->basis_b1, kC); put(lay->basis_w2, (int64_t)kD * kC); put(lay->basis_b2, kD);
+  put(lay->fiber_w1, kC * 3); put(lay->fiber_b1, kC); put(lay->fiber_w2, (int64_t)kD * kC); put(lay->fiber_b2, kD);
+  put(lay->embed_w, kC * FV);
+  put(lay->layer_scale, kL * kC); put(lay->conv_bias, kL * kC); put(lay->conv_kernel_w, (int64_t)kL * kC * kD);
+  put(lay->conv_fiber_w, (int64_t)kL * kC * kD); put(lay->lin1_w, (int64_t)kL * kW * kC); put(lay->lin1_b, kL * kW);
+  put(lay->lin2_w, (int64_t)kL * kC * kW); put(lay->lin2_b, kL * kC); put(lay->norm_w, kL * kC); put(lay->norm_b, kL * kC);
+  put(lay->readout_w, kL * R * kC); put(lay->readout_b, kL * R);
+  lay->total = o;
+  return ARREAU_OK;
+}
+
+extern "C" int64_t arreau_ponita_backward_workspace_bytes(int32_t N, int64_t edge_capacity, int32_t num_scalar,
+                                                          int32_t num_vec) {
+  if (N < 0 || edge_capacity < 0) return ARREAU_ERR_BAD_SHAPE;
+  const int xl_pitch = ((num_scalar + num_vec + 127) / 128) * 128;
+  return (int64_t)(carve(nullptr, N, edge_capacity, xl_pitch).total * sizeof(float));
+}
+
+extern "C" int arreau_moments(const float* x, const float* sub_cols, int64_t n, double* scratch, double* out,
+                              void* stream) {
+  if (!x || !scratch || !out) return ARREAU_ERR_NULL;
+  if (n <= 0) return ARREAU_ERR_BAD_SHAPE;
+  const int blocks = 256;
+  moments_kernel<<<blocks, 256, 0, (cudaStream_t)stream>>>(x, sub_cols, n, scratch);
+  CUDA_LAUNCH_CHECK();
+  moments_finish_kernel<<<1, 32, 0, (cudaStream_t)stream>>>(scratch, blocks, out);
+  CUDA_LAUNCH_CHECK();
+  return ARREAU_OK;
+}
+
+extern "C" int arreau_sgemm(int32_t a_k_contiguous, int32_t b_k_contiguous, const float* A, int64_t lda, const float* B,
+                            int64_t ldb, float* C, int64_t ldc, int32_t M, int32_t N, int64_t K, float alpha,
+                            const float* bias, int32_t accumulate, float* partial, int64_t partial_floats, void* stream) {
+  if (!A || !B || !C) return ARREAU_ERR_NULL;
+  if (M < 0 || N < 0 || K < 0 || (N & 3) || (lda & 3) || (ldb & 3) || (ldc & 3)) return ARREAU_ERR_BAD_SHAPE;
+  Gemm g{(cudaStream_t)stream, partial, partial ? (size_t)partial_floats : 0, sm_count()};
+  if (a_k_contiguous && b_k_contiguous) return gemm<true, true>(g, A, lda, B, ldb, C, ldc, M, N, K, alpha, bias, accumulate);
+  if (a_k_contiguous) return gemm<true, false>(g, A, lda, B, ldb, C, ldc, M, N, K, alpha, bias, accumulate);
+  if (b_k_contiguous) return gemm<false, true>(g, A, lda, B, ldb, C, ldc, M, N, K, alpha, bias, accumulate);
+  return gemm<false, false>(g, A, lda, B, ldb, C, ldc, M, N, K, alpha, bias, accumulate);
+}
+
+extern "C" int arreau_ponita_backward(const float* params, const arreau_train_layout_t* lay, const arreau_weights* w,
+                                      const arreau_workspace* ws, const int32_t* fold_table, const float* x,
+                                      const float* vec, const int32_t* row_ptr, const int32_t* src, const int32_t* dst,
+                                      const double* dist, const double* dir, const double* lattice,
+                                      const int32_t* atom_offset, const int32_t* crystal_of_atom, int32_t N, int32_t G,
+                                      double radius, const float* dlogits, const float* dscore, const float* dlen0,
+                                      float* workspace, int64_t workspace_bytes, float* grads, void* stream) {
+  if (!params || !lay || !w || !ws || !fold_table || !grads || !workspace) return ARREAU_ERR_NULL;
+  if (N < 0 || G < 0) return ARREAU_ERR_BAD_SHAPE;
+  if (N == 0) return ARREAU_OK;
+  if (!ws->h_debug || !ws->x1_debug || !ws->x2_debug || !ws->kernels || !x || !vec || !row_ptr || !src || !dst ||
+      !dist || !dir || !lattice || !atom_offset || !crystal_of_atom || !dlogits || !dscore || !dlen0)
+    return ARREAU_ERR_NULL;
+  const int Z = w->num_states, F = w->num_scalar, V = w->num_vec, R = Z + 4, FV = F + V;
+  if (R > 128) return ARREAU_ERR_UNSUPPORTED;
+  const int xl_pitch = ((FV + 127) / 128) * 128;
+  const long long Ecap = ws->edge_capacity;
+  BwdBuffers b = carve(workspace, N, Ecap, xl_pitch);
+  if ((int64_t)(b.total * sizeof(float)) > workspace_bytes) return ARREAU_ERR_WORKSPACE;
+  cudaStream_t s = (cudaStream_t)stream;
+  Gemm g{s, b.partial, kPartialFloats, sm_count()};
+  const long long Re = Ecap * kO, Rn = (long long)N * kO;
+  const size_t node_elems = (size_t)N * kO * kC, layer_kernel_elems = (size_t)Ecap * kO * kC;
+  const int32_t* num_edges_ptr = row_ptr + N;
+  const float* P = params;
+  float* Gd = grads;
+  auto zero = [&](float* p, long long n) -> int {
+    if (n <= 0) return ARREAU_OK;
+    fill_kernel<<<blocks_for(n, 256), 256, 0, s>>>(p, n, 0.f);
+    CUDA_LAUNCH_CHECK();
+    return ARREAU_OK;
+  };
+  auto gelu_f = [&](const float* z, long long rows, int ncols, const float* rs, int rps, float* a) -> int {
+    if (rows <= 0) return ARREAU_OK;
+    gelu_fwd_kernel<<<blocks_for(rows * ncols / 4, 256), 256, 0, s>>>(z, rows * ncols, ncols, rs, rps, a);
+    CUDA_LAUNCH_CHECK();
+    return ARREAU_OK;
+  };
+  auto gelu_b = [&](const float* z, const float* da, long long rows, int ncols, const float* rs, int rps, float* dz) -> int {
+    if (rows <= 0) return ARREAU_OK;
+    gelu_bwd_kernel<<<blocks_for(rows * ncols / 4, 256), 256, 0, s>>>(z, da, rows * ncols, ncols, rs, rps, dz);
+    CUDA_LAUNCH_CHECK();
+    return ARREAU_OK;
+  };
+
+  // ---- 0. gradient rows of the read-outs, zero dh ---------------------------------------------------------
+  TRY(zero(Gd, lay->total));
+  TRY(zero(b.dh, (long long)node_elems));
+  readout_grad_rows_kernel<<<(unsigned)Rn, 128, 0, s>>>(dlogits, dscore, dlen0, crystal_of_atom, w->ori, N, Z,
+                                                        1.0f / (float)(kL * kO), b.dr);
+  CUDA_LAUNCH_CHECK();
+
+  // ---- 1. recompute the edge chain: monomials -> z1 -> a1 -> z2 -> kernel basis kb ------------------------
+  fold_w1_kernel<<<kC, 128, 0, s>>>(P + lay->basis_w1, P + lay->basis_b1, fold_table, 258, b.w1m);
+  CUDA_LAUNCH_CHECK();
+  if (Re > 0) {
+    edge_mono_kernel<<<blocks_for(Re, 128), 128, 0, s>>>(dir, dist, lattice, crystal_of_atom, src, num_edges_ptr, Ecap,
+                                                         w->ori, radius, b.mono, b.win);
+    CUDA_LAUNCH_CHECK();
+    TRY((gemm<true, true>(g, b.mono, 128, b.w1m, 128, b.z1, kC, (int)Re, kC, kMonoPad, 1.f, nullptr, false)));
+    TRY(gelu_f(b.z1, Re, kC, nullptr, 1, b.a1));
+    TRY((gemm<true, true>(g, b.a1, kC, P + lay->basis_w2, kC, b.z2, kD, (int)Re, kD, kC, 1.f, P + lay->basis_b2, false)));
+    TRY(gelu_f(b.z2, Re, kD, b.win, kO, b.kb));
+    TRY(zero(b.dkb, Re * kD));
+  }
+  // fiber chain forward (ponita.py:66,95): rows (o,p)
+  const int Rf = kO * kO;
+  fiber_rows_kernel<<<1, 256, 0, s>>>(w->ori, b.frow);
+  CUDA_LAUNCH_CHECK();
+  pack_fiber_w1_kernel<<<kC, 16, 0, s>>>(P + lay->fiber_w1, P + lay->fiber_b1, b.fw16);
+  CUDA_LAUNCH_CHECK();
+  TRY((gemm<true, true>(g, b.frow, 16, b.fw16, 16, b.fz1, kC, Rf, kC, 16, 1.f, nullptr, false)));
+  TRY(gelu_f(b.fz1, Rf, kC, nullptr, 1, b.fa1));
+  TRY((gemm<true, true>(g, b.fa1, kC, P + lay->fiber_w2, kC, b.fz2, kD, Rf, kD, kC, 1.f, P + lay->fiber_b2, false)));
+  TRY(gelu_f(b.fz2, Rf, kD, nullptr, 1, b.fkb));
+  TRY(zero(b.dfkb, (long long)Rf * kD));
+
+  // ---- 2. layers, last to first -------------------------------------------------------------------------
+  for (int l = kL - 1; l >= 0; --l) {
+    const float* h_out = ws->h_debug + (size_t)(l + 1) * node_elems;
+    const float* h_in = ws->h_debug + (size_t)l * node_elems;
+    const float* x1 = ws->x1_debug + (size_t)l * node_elems;
+    const float* x2 = ws->x2_debug + (size_t)l * node_elems;
+    const float* kern = (const float*)ws->kernels + (size_t)l * layer_kernel_elems;
+    const float* Wr = P + lay->readout_w + (size_t)l * R * kC;
+    const float* W1 = P + lay->lin1_w + (size_t)l * kW * kC;
+    const float* W2 = P + lay->lin2_w + (size_t)l * kC * kW;
+    const float* Wk = P + lay->conv_kernel_w + (size_t)l * kC * kD;
+    const float* Wf = P + lay->conv_fiber_w + (size_t)l * kC * kD;
+    const float* ls = P + lay->layer_scale + l * kC;
+    // read-out l: r = h_out Wr^T + br   (ponita.py:105)
+    //   dWr[R,C] = dr^T h_out   (dr is 128 wide, only the first R rows of the product are parameters)
+    TRY((gemm<false, false>(g, b.dr, 128, h_out, kC, b.small, kC, 128, kC, Rn, 1.f, nullptr, false)));
+    {
+      cudaError_t e = cudaMemcpyAsync(Gd + lay->readout_w + (size_t)l * R * kC, b.small, sizeof(float) * R * kC,
+                                      cudaMemcpyDeviceToDevice, s);
+      if (e != cudaSuccess) return (int)e;
+    }
+    TRY(colsum(g, b.dr, nullptr, Rn, 128, 128, b.small, false));
+    {
+      cudaError_t e = cudaMemcpyAsync(Gd + lay->readout_b + (size_t)l * R, b.small, sizeof(float) * R, cudaMemcpyDeviceToDevice, s);
+      if (e != cudaSuccess) return (int)e;
+    }
+    //   dh += dr Wr      (K = R rows of Wr; dr columns beyond R are zero, so K = R rounded down to the stored rows)
+    TRY((gemm<true, false>(g, b.dr, 128, Wr, kC, b.dh, kC, (int)Rn, kC, R, 1.f, nullptr, true)));
+    // ConvNext MLP recompute (convnext.py:25-32): y = LN(x2), z = y W1^T + b1, a = gelu(z), m = a W2^T + b2
+    ln_fwd_kernel<<<blocks_for(Rn * 32, 256), 256, 0, s>>>(x2, P + lay->norm_w + l * kC, P + lay->norm_b + l * kC, Rn, b.y);
+    CUDA_LAUNCH_CHECK();
+    TRY((gemm<true, true>(g, b.y, kC, W1, kC, b.z, kW, (int)Rn, kW, kC, 1.f, P + lay->lin1_b + l * kW, false)));
+    TRY(gelu_f(b.z, Rn, kW, nullptr, 1, b.a));
+    TRY((gemm<true, true>(g, b.a, kW, W2, kW, b.m, kC, (int)Rn, kC, kW, 1.f, P + lay->lin2_b + l * kC, false)));
+    // h_out = h_in + ls * m
+    TRY(colsum(g, b.dh, b.m, Rn, kC, kC, Gd + lay->layer_scale + l * kC, false));
+    scale_cols_kernel<<<blocks_for(Rn * kC / 4, 256), 256, 0, s>>>(b.dh, ls, Rn * kC, b.m);            // b.m = dm
+    CUDA_LAUNCH_CHECK();
+    TRY(colsum(g, b.m, nullptr, Rn, kC, kC, Gd + lay->lin2_b + l * kC, false));
+    TRY((gemm<false, false>(g, b.m, kC, b.a, kW, Gd + lay->lin2_w + (size_t)l * kC * kW, kW, kC, kW, Rn, 1.f, nullptr, false)));
+    TRY((gemm<true, false>(g, b.m, kC, W2, kW, b.da, kW, (int)Rn, kW, kC, 1.f, nullptr, false)));
+    TRY(gelu_b(b.z, b.da, Rn, kW, nullptr, 1, b.da));                                                  // b.da = dz
+    TRY(colsum(g, b.da, nullptr, Rn, kW, kW, Gd + lay->lin1_b + l * kW, false));
+    TRY((gemm<false, false>(g, b.da, kW, b.y, kC, Gd + lay->lin1_w + (size_t)l * kW * kC, kC, kW, kC, Rn, 1.f, nullptr, false)));
+    TRY((gemm<true, false>(g, b.da, kW, W1, kC, b.dy, kC, (int)Rn, kC, kW, 1.f, nullptr, false)));
+    // LayerNorm backward + conv bias gradient
+    {
+      int blocks = (int)((Rn + kLnWarps - 1) / kLnWarps);
+      if (blocks > kLnBlocks) blocks = kLnBlocks;
+      ln_bwd_kernel<<<blocks, kLnWarps * 32, 0, s>>>(x2, b.dy, P + lay->norm_w + l * kC, Rn, b.dx2, b.partial);
+      CUDA_LAUNCH_CHECK();
+      reduce_partials_kernel<<<(3 * kC + 255) / 256, 256, 0, s>>>(b.partial, blocks, 3 * kC, 3 * kC, 3 * kC, 1.f, 0, b.small);
+      CUDA_LAUNCH_CHECK();
+      // b.small[0..383] = [dgamma | dbeta | dbias]
+      cudaError_t e = cudaMemcpyAsync(Gd + lay->norm_w + l * kC, b.small, sizeof(float) * kC, cudaMemcpyDeviceToDevice, s);
+      if (e == cudaSuccess) e = cudaMemcpyAsync(Gd + lay->norm_b + l * kC, b.small + kC, sizeof(float) * kC, cudaMemcpyDeviceToDevice, s);
+      if (e == cudaSuccess) e = cudaMemcpyAsync(Gd + lay->conv_bias + l * kC, b.small + 2 * kC, sizeof(float) * kC, cudaMemcpyDeviceToDevice, s);
+      if (e != cudaSuccess) return (int)e;
+    }
+    // fiber conv backward
+    const float* fk = w->fiber_kernel + (size_t)l * kO * kO * kC;
+    {
+      int blocks = N < 2 * g.sms ? N : 2 * g.sms;
+      fiber_bwd_dx1_kernel<<<blocks, kC, 0, s>>>(b.dx2, fk, N, b.dx1);
+      CUDA_LAUNCH_CHECK();
+      int fb = N < kDfkBlocks ? N : kDfkBlocks;
+      fiber_bwd_dfk_kernel<<<fb, 1024, 0, s>>>(x1, b.dx2, N, b.partial);
+      CUDA_LAUNCH_CHECK();
+      float* dfk = b.dfk + (size_t)l * Rf * kC;
+      reduce_partials_kernel<<<blocks_for((long long)Rf * kC, 256), 256, 0, s>>>(b.partial, fb, (long long)Rf * kC, Rf * kC,
+                                                                               Rf * kC, 1.0f / kO, 0, dfk);
+      CUDA_LAUNCH_CHECK();
+      // fiber_kernel = fkb Wf^T: dWf[C,D] = dfk^T fkb ; dfkb += dfk Wf
+      TRY((gemm<false, false>(g, dfk, kC, b.fkb, kD, Gd + lay->conv_fiber_w + (size_t)l * kC * kD, kD, kC, kD, Rf, 1.f, nullptr, false)));
+      TRY((gemm<true, false>(g, dfk, kC, Wf, kD, b.dfkb, kD, Rf, kD, kC, 1.f, nullptr, true)));
+    }
+    // message pass backward
+    if (Re > 0) {
+      message_bwd_dkern_kernel<<<blocks_for(Re * kC / 4, 256), 256, 0, s>>>(b.dx1, h_in, src, dst, num_edges_ptr, Ecap, b.dkern);
+      CUDA_LAUNCH_CHECK();
+      message_bwd_dh_kernel<<<N, 256, 0, s>>>(kern, b.dx1, row_ptr, src, dst, atom_offset, crystal_of_atom, Ecap, b.dh);
+      CUDA_LAUNCH_CHECK();
+      // kernel = kb Wk^T: dWk[C,D] = dkern^T kb ; dkb += dkern Wk
+      TRY((gemm<false, false>(g, b.dkern, kC, b.kb, kD, Gd + lay->conv_kernel_w + (size_t)l * kC * kD, kD, kC, kD, Re, 1.f, nullptr, false)));
+      TRY((gemm<true, false>(g, b.dkern, kC, Wk, kD, b.dkb, kD, (int)Re, kD, kC, 1.f, nullptr, true)));
+    }
+  }
+
+  // ---- 3. node embedding: h0 = x_lift We^T  (ponita.py:98) ------------------------------------------------
+  lift_rows_kernel<<<(unsigned)Rn, 256, 0, s>>>(x, vec, w->ori, N, F, V, xl_pitch, b.xl);
+  CUDA_LAUNCH_CHECK();
+  //   dWe[C, FV] = dh0^T x_lift  (computed xl_pitch wide into scratch, then the FV parameter columns are copied)
+  if (xl_pitch > 512) return ARREAU_ERR_UNSUPPORTED;
+  TRY((gemm<false, false>(g, b.dh, kC, b.xl, xl_pitch, b.small, xl_pitch, kC, xl_pitch, Rn, 1.f, nullptr, false)));
+  {
+    cudaError_t e = cudaMemcpy2DAsync(Gd + lay->embed_w, sizeof(float) * FV, b.small, sizeof(float) * xl_pitch, sizeof(float) * FV,
+                                      kC, cudaMemcpyDeviceToDevice, s);
+    if (e != cudaSuccess) return (int)e;
+  }
+
+  // ---- 4. edge chain backward ------------------------------------------------------------------------------
+  if (Re > 0) {
+    TRY(gelu_b(b.z2, b.dkb, Re, kD, b.win, kO, b.dkb));                                              // b.dkb = dz2
+    TRY(colsum(g, b.dkb, nullptr, Re, kD, kD, Gd + lay->basis_b2, false));
+    TRY((gemm<false, false>(g, b.dkb, kD, b.a1, kC, Gd + lay->basis_w2, kC, kD, kC, Re, 1.f, nullptr, false)));
+    TRY((gemm<true, false>(g, b.dkb, kD, P + lay->basis_w2, kC, b.da1, kC, (int)Re, kC, kD, 1.f, nullptr, false)));
+    TRY(gelu_b(b.z1, b.da1, Re, kC, nullptr, 1, b.da1));                                             // b.da1 = dz1
+    TRY((gemm<false, false>(g, b.da1, kC, b.mono, 128, b.dw1m, 128, kC, kMonoPad, Re, 1.f, nullptr, false)));
+    unfold_w1_grad_kernel<<<kC, 128, 0, s>>>(b.dw1m, fold_table, 258, Gd + lay->basis_w1, Gd + lay->basis_b1);
+    CUDA_LAUNCH_CHECK();
+  }
+
+  // ---- 5. fiber chain backward -----------------------------------------------------------------------------
+  TRY(gelu_b(b.fz2, b.dfkb, Rf, kD, nullptr, 1, b.dfkb));
+  TRY(colsum(g, b.dfkb, nullptr, Rf, kD, kD, Gd + lay->fiber_b2, false));
+  TRY((gemm<false, false>(g, b.dfkb, kD, b.fa1, kC, Gd + lay->fiber_w2, kC, kD, kC, Rf, 1.f, nullptr, false)));
+  TRY((gemm<true, false>(g, b.dfkb, kD, P + lay->fiber_w2, kC, b.fda1, kC, Rf, kC, kD, 1.f, nullptr, false)));
+  TRY(gelu_b(b.fz1, b.fda1, Rf, kC, nullptr, 1, b.fda1));
+  TRY((gemm<false, false>(g, b.fda1, kC, b.frow, 16, b.fdw16, 16, kC, 16, Rf, 1.f, nullptr, false)));
+  unpack_fiber_w1_grad_kernel<<<1, kC, 0, s>>>(b.fdw16, Gd + lay->fiber_w1, Gd + lay->fiber_b1);
+  CUDA_LAUNCH_CHECK();
+  return ARREAU_OK;
+}

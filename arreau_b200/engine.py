@@ -198,16 +198,21 @@ class DenoiseEngine:
         return int(self.row_ptr[self.N].item())
 
     # ------------------------------------------------------------------ predict_scores
-    def prepare_inputs(self, t) -> None:
-        """lattice_from_params, feature assembly, frac -> cart (diffusion_loss.py:124-158)."""
+    def prepare_inputs(self, t, from_trig: bool = True) -> None:
+        """lattice_from_params, feature assembly, frac -> cart (diffusion_loss.py:124-158).  from_trig=False
+        evaluates the angle factors on the device (training batches, whose angles come from matrix_to_params)."""
         s = self.stream
         if isinstance(t, int):
             t_ptr, t_scalar = None, t
         else:
             self.t_of_atom.copy_(torch.as_tensor(t).reshape(self.N).to(torch.int32), non_blocking=True)
             t_ptr, t_scalar = self.t_of_atom.data_ptr(), 0
-        _lib.call("arreau_lattice_from_trig", self.lengths.data_ptr(), self.angle_trig.data_ptr(), self.G,
-                  self.lattice.data_ptr(), s)
+        if from_trig:
+            _lib.call("arreau_lattice_from_trig", self.lengths.data_ptr(), self.angle_trig.data_ptr(), self.G,
+                      self.lattice.data_ptr(), s)
+        else:
+            _lib.call("arreau_lattice_from_params", self.lengths.data_ptr(), self.angles.data_ptr(), self.G,
+                      self.lattice.data_ptr(), s)
         _lib.call("arreau_assemble_features", self.frac.data_ptr(), self.types.data_ptr(), self.lengths.data_ptr(),
                   self.angles.data_ptr(), self.lattice.data_ptr(), self.atom_offset.data_ptr(),
                   self.crystal_of_atom.data_ptr(), t_ptr, t_scalar, self.d_vp_betas.data_ptr(),

@@ -1,0 +1,206 @@
+"""Training step of the Arreau diffusion model on the GPU.
+
+Host logic only: buffer ownership and the launch sequence of one step
+    noising (VE / D3PM / VP)  ->  predict_scores (graph + fp32 forward, per-layer buffers kept)
+    ->  three-term loss + output gradients  ->  hand-written backward  ->  flat gradient buffer
+mirroring DiffusionLoss.__call__ (diffusion/diffusion_loss.py:204-274) followed by loss.backward().  Every
+computation is a kernel of libarreau_b200.so (csrc/train_ops.cu, csrc/train_net.cu, and the forward kernels).
+Parameters and gradients live in ONE flat fp32 buffer each (arreau_train_layout_t order) whose slices are exposed
+under the reference's state_dict names, so an optimizer / all-reduce sees a single tensor.
+"""
+from __future__ import annotations
+
+import ctypes as C
+from typing import Dict, Mapping, Optional, Sequence
+
+import numpy as np
+import torch
+
+from . import _lib
+from .engine import DenoiseEngine
+from .tables import DiffusionTables
+from .weights import BASIS, HIDDEN, LAYERS, WIDEN, PonitaWeights, monomial_fold_table
+
+HYBRID_LOSS_COEFF = 0.001    # diffusion/d3pm.py:15
+
+
+class FlatParams:
+    """The model's trainable tensors as slices of one flat fp32 device buffer (+ a gradient buffer of the same
+    layout), keyed like the reference's state_dict."""
+
+    def __init__(self, num_scalar: int, num_vec: int, num_states: int, device):
+        self.device = torch.device(device)
+        self.layout = _lib.TrainLayout()
+        _lib.call("arreau_train_layout", num_scalar, num_vec, num_states, C.byref(self.layout))
+        self.num_scalar, self.num_vec, self.num_states = num_scalar, num_vec, num_states
+        self.total = int(self.layout.total)
+        self.data = torch.zeros(self.total, dtype=torch.float32, device=self.device)
+        self.grad = torch.zeros(self.total, dtype=torch.float32, device=self.device)
+        R, FV, L, Cc, D, W = num_states + 4, num_scalar + num_vec, LAYERS, HIDDEN, BASIS, WIDEN * HIDDEN
+        lay = self.layout
+        self.specs = {   # name -> (offset, shape)
+            "basis_fn.1.weight": (lay.basis_w1, (Cc, 258)), "basis_fn.1.bias": (lay.basis_b1, (Cc,)),
+            "basis_fn.3.weight": (lay.basis_w2, (D, Cc)), "basis_fn.3.bias": (lay.basis_b2, (D,)),
+            "fiber_basis_fn.1.weight": (lay.fiber_w1, (Cc, 3)), "fiber_basis_fn.1.bias": (lay.fiber_b1, (Cc,)),
+            "fiber_basis_fn.3.weight": (lay.fiber_w2, (D, Cc)), "fiber_basis_fn.3.bias": (lay.fiber_b2, (D,)),
+            "x_embedder.weight": (lay.embed_w, (Cc, FV)),
+        }
+        per_layer = {"layer_scale": (lay.layer_scale, (Cc,)), "conv.bias": (lay.conv_bias, (Cc,)),
+                     "conv.kernel.weight": (lay.conv_kernel_w, (Cc, D)),
+                     "conv.fiber_kernel.weight": (lay.conv_fiber_w, (Cc, D)),
+                     "linear_1.weight": (lay.lin1_w, (W, Cc)), "linear_1.bias": (lay.lin1_b, (W,)),
+                     "linear_2.weight": (lay.lin2_w, (Cc, W)), "linear_2.bias": (lay.lin2_b, (Cc,)),
+                     "norm.weight": (lay.norm_w, (Cc,)), "norm.bias": (lay.norm_b, (Cc,))}
+        for l in range(L):
+            for name, (off, shape) in per_layer.items():
+                self.specs[f"interaction_layers.{l}.{name}"] = (off + l * int(np.prod(shape)), shape)
+            self.specs[f"read_out_layers.{l}.weight"] = (lay.readout_w + l * R * Cc, (R, Cc))
+            self.specs[f"read_out_layers.{l}.bias"] = (lay.readout_b + l * R, (R,))
+        assert sum(int(np.prod(s)) for _, s in self.specs.values()) == self.total
+
+    def _views(self, buf: torch.Tensor) -> Dict[str, torch.Tensor]:
+        return {k: buf[off:off + int(np.prod(shape))].view(shape) for k, (off, shape) in self.specs.items()}
+
+    def views(self) -> Dict[str, torch.Tensor]:
+        return self._views(self.data)
+
+    def grad_views(self) -> Dict[str, torch.Tensor]:
+        return self._views(self.grad)
+
+    def load_state_dict(self, sd: Mapping[str, object]) -> None:
+        for k, v in self.views().items():
+            v.copy_(torch.as_tensor(np.asarray(sd[k].detach().cpu()) if isinstance(sd[k], torch.Tensor) else np.asarray(sd[k]),
+                                    dtype=torch.float32).reshape(v.shape))
+
+    def state_dict(self) -> Dict[str, torch.Tensor]:
+        return {k: v.clone() for k, v in self.views().items()}
+
+
+class TrainEngine:
+    """One batch topology (atoms per crystal) on one GPU."""
+
+    def __init__(self, params: FlatParams, tables: DiffusionTables, fourier_w, ori_grid, num_atoms: Sequence[int],
+                 radius: float, max_neighbors: int, device="cuda"):
+        self.p, self.tabs = params, tables
+        self.device = dev = torch.device(device)
+        self.ori = torch.as_tensor(np.asarray(ori_grid), dtype=torch.float32).to(dev)
+        self.w = PonitaWeights.from_device_params(params.views(), self.ori)
+        self.eng = DenoiseEngine(self.w, tables, fourier_w, num_atoms, radius, max_neighbors, precision="fp32",
+                                 debug=True, device=dev)
+        e = self.eng
+        N, G, Z = e.N, e.G, e.Z
+        f64 = lambda *s: torch.zeros(*s, dtype=torch.float64, device=dev)  # noqa: E731
+        f32 = lambda *s: torch.zeros(*s, dtype=torch.float32, device=dev)  # noqa: E731
+        self.frac0, self.types0, self.lattice0 = f64(N, 3), torch.zeros(N, dtype=torch.int64, device=dev), f64(G, 3, 3)
+        self.lengths0, self.angles0, self.target_eps = f64(G, 3), f64(G, 3), f64(N, 3)
+        self.eps_x, self.u, self.eps_l = f64(N, 3), f64(N, Z), f64(G, 3)
+        self.t_crystal = torch.ones(G, dtype=torch.int32, device=dev)
+        self.t_atom = torch.ones(N, dtype=torch.int32, device=dev)
+        self.terms, self.loss = f64(3 * N), f64(5)
+        self.dscore, self.dlogits, self.dlen0 = f32(N, 3), f32(N, Z), f32(G, 3)
+        self.d_alpha_bars = tables.vp_alpha_bars.to(torch.float32).to(dev)
+        self.fold = torch.as_tensor(monomial_fold_table(), dtype=torch.int32).to(dev)
+        self.mom_scratch, self.mom_out = f64(512), f64(2)
+        self._bwd_ws = None
+
+    # ------------------------------------------------------------------ pieces (each = the mirrored reference call)
+    def repack(self) -> None:
+        """Kernel layouts of the current flat parameters (after an optimizer step)."""
+        self.w = PonitaWeights.from_device_params(self.p.views(), self.ori)
+        self.eng.w = self.w
+
+    def set_batch(self, frac0, types0, lattice0, timestep, eps_x, u, eps_l) -> None:
+        """Batch{X0, A0, L0} and the step's random draws (diffusion_loss.py:205-237).  timestep: [G] or [G,1]."""
+        e = self.eng
+        self.frac0.copy_(torch.as_tensor(frac0).reshape(e.N, 3), non_blocking=True)
+        self.types0.copy_(torch.as_tensor(types0).reshape(e.N), non_blocking=True)
+        self.lattice0.copy_(torch.as_tensor(lattice0).reshape(e.G, 3, 3), non_blocking=True)
+        self.t_crystal.copy_(torch.as_tensor(timestep).reshape(e.G).to(torch.int32), non_blocking=True)
+        self.t_atom.copy_(torch.repeat_interleave(self.t_crystal, e.num_atoms.to(self.device)))
+        self.eps_x.copy_(torch.as_tensor(eps_x).reshape(e.N, 3), non_blocking=True)
+        self.u.copy_(torch.as_tensor(u).reshape(e.N, e.Z), non_blocking=True)
+        self.eps_l.copy_(torch.as_tensor(eps_l).reshape(e.G, 3), non_blocking=True)
+
+    def noise_batch(self) -> None:
+        """VE_pbc.forward, D3PM.get_xt, matrix_to_params + VP_lattice.forward into the forward engine's state."""
+        e, s = self.eng, self.eng.stream
+        _lib.call("arreau_matrix_to_params", self.lattice0.data_ptr(), e.G, self.lengths0.data_ptr(),
+                  self.angles0.data_ptr(), s)
+        _lib.call("arreau_ve_pbc_forward", self.frac0.data_ptr(), self.eps_x.data_ptr(), self.t_atom.data_ptr(),
+                  e.d_ve_sigmas.data_ptr(), self.lattice0.data_ptr(), e.crystal_of_atom.data_ptr(), e.N,
+                  e.frac.data_ptr(), self.target_eps.data_ptr(), s)
+        _lib.call("arreau_d3pm_q_sample", self.types0.data_ptr(), self.u.data_ptr(), self.t_atom.data_ptr(),
+                  e.d_q_keep.data_ptr(), e.d_q_to_mask.data_ptr(), e.N, e.Z, e.types.data_ptr(), s)
+        _lib.call("arreau_vp_lattice_forward", self.lengths0.data_ptr(), self.eps_l.data_ptr(), self.t_crystal.data_ptr(),
+                  self.d_alpha_bars.data_ptr(), e.G, e.lengths.data_ptr(), s)
+        e.angles.copy_(self.angles0)
+
+    def predict(self) -> None:
+        """DiffusionLoss.predict_scores (diffusion_loss.py:112-197) on the noised batch; per-layer buffers kept."""
+        e = self.eng
+        e.prepare_inputs(self.t_atom, from_trig=False)
+        e._ensure_capacity()
+        e.build_graph()
+        e.forward()
+
+    def compute_loss(self) -> torch.Tensor:
+        e, tb = self.eng, self.tabs
+        _lib.call("arreau_training_loss", e.score.data_ptr(), e.logits.data_ptr(), e.len0.data_ptr(),
+                  self.target_eps.data_ptr(), self.types0.data_ptr(), e.types.data_ptr(), self.t_atom.data_ptr(),
+                  self.lengths0.data_ptr(), e.atom_offset.data_ptr(), e.d_q_keep.data_ptr(), e.d_q_to_mask.data_ptr(),
+                  tb.onestep_keep, tb.onestep_to_mask, tb.T, e.N, e.G, e.Z, HYBRID_LOSS_COEFF, self.terms.data_ptr(),
+                  self.loss.data_ptr(), self.dscore.data_ptr(), self.dlogits.data_ptr(), self.dlen0.data_ptr(), e.stream)
+        return self.loss
+
+    def backward(self, dlogits: Optional[torch.Tensor] = None, dscore: Optional[torch.Tensor] = None,
+                 dlen0: Optional[torch.Tensor] = None) -> torch.Tensor:
+        """Parameter gradients of the last predict() for the given output gradients (default: the loss's)."""
+        e = self.eng
+        dlogits = self.dlogits if dlogits is None else dlogits
+        dscore = self.dscore if dscore is None else dscore
+        dlen0 = self.dlen0 if dlen0 is None else dlen0
+        need = int(_lib.load().arreau_ponita_backward_workspace_bytes(e.N, e.edge_capacity, e.F, 4))
+        if need < 0:
+            _lib.check(need, "arreau_ponita_backward_workspace_bytes")
+        if self._bwd_ws is None or self._bwd_ws.numel() * 4 < need:
+            self._bwd_ws = torch.empty((need + 3) // 4, dtype=torch.float32, device=self.device)
+        _lib.call("arreau_ponita_backward", self.p.data.data_ptr(), C.byref(self.p.layout), self.w.ref(), C.byref(e.ws),
+                  self.fold.data_ptr(), e.x.data_ptr(), e.vec.data_ptr(), e.row_ptr.data_ptr(), e.src.data_ptr(),
+                  e.dst.data_ptr(), e.dist.data_ptr(), e.dir.data_ptr(), e.lattice.data_ptr(), e.atom_offset.data_ptr(),
+                  e.crystal_of_atom.data_ptr(), e.N, e.G, e.radius, dlogits.data_ptr(), dscore.data_ptr(),
+                  dlen0.data_ptr(), self._bwd_ws.data_ptr(), self._bwd_ws.numel() * 4, self.p.grad.data_ptr(), e.stream)
+        return self.p.grad
+
+    # ------------------------------------------------------------------ the step
+    def loss_and_grads(self, frac0, types0, lattice0, timestep, eps_x, u, eps_l):
+        """DiffusionLoss.__call__ + loss.backward(): returns (loss[5] f64 device = {total, frac, vb, ce, lattice},
+        flat gradient buffer)."""
+        self.set_batch(frac0, types0, lattice0, timestep, eps_x, u, eps_l)
+        self.noise_batch()
+        self.predict()
+        self.compute_loss()
+        self.backward()
+        return self.loss, self.p.grad
+
+    # ------------------------------------------------------------------ callibrate (conv.py:122-123,140-146)
+    def _std(self, x: torch.Tensor, sub_cols: Optional[torch.Tensor] = None) -> float:
+        n = x.numel()
+        _lib.call("arreau_moments", x.data_ptr(), _lib.ptr(sub_cols), n, self.mom_scratch.data_ptr(),
+                  self.mom_out.data_ptr(), self.eng.stream)
+        s, q = self.mom_out.tolist()
+        return float(np.sqrt(max(q - s * s / n, 0.0) / (n - 1)))      # torch.std: unbiased
+
+    def calibrate(self, frac, types, lengths, angles, t) -> None:
+        """The one-time re-initialisation of the reference's first train-mode forward: per layer,
+        kernel.weight *= std(x) / std(x1) and fiber_kernel.weight *= std(x1) / std(x2) with that forward's own
+        tensors (x2 before the bias).  The statistics are reduced on the device (arreau_moments)."""
+        e = self.eng
+        e.set_state(frac, types, lengths, angles)
+        e.predict_scores(t)
+        v = self.p.views()
+        for l in range(LAYERS):
+            s_in, s_1 = self._std(e.h_debug[l]), self._std(e.x1_debug[l])
+            s_2 = self._std(e.x2_debug[l], v[f"interaction_layers.{l}.conv.bias"])
+            v[f"interaction_layers.{l}.conv.kernel.weight"].mul_(s_in / s_1)
+            v[f"interaction_layers.{l}.conv.fiber_kernel.weight"].mul_(s_1 / s_2)
+        self.repack()

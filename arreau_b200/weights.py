@@ -142,5 +142,50 @@ class PonitaWeights:
                 setattr(self.c, name, self.t[name].data_ptr())
         self.c.num_scalar, self.c.num_vec, self.c.num_states = self.num_scalar, self.num_vec, self.num_states
 
+    @classmethod
+    def from_device_params(cls, sd: Mapping[str, torch.Tensor], ori_grid: torch.Tensor) -> "PonitaWeights":
+        """Kernel layouts of the fp32 path from fp32 DEVICE tensors keyed like the reference state_dict, with device
+        ops only (no host round trip): the training step re-packs its flat parameter buffer with this every step.
+        (Transposes / stacking are layout plumbing; the fiber kernels are evaluated by
+        arreau_fiber_kernel_precompute.)"""
+        self = cls.__new__(cls)
+        dev = sd["basis_fn.1.weight"].device
+        self.device = dev
+        L = LAYERS
+        f = lambda a: a.to(torch.float32).contiguous()  # noqa: E731
+        w1 = sd["basis_fn.1.weight"]
+        fold = torch.as_tensor(monomial_fold_table(), device=dev)
+        w1m_t = torch.zeros(MONO_PAD, HIDDEN, dtype=torch.float32, device=dev)
+        w1m_t[:NUM_MONO] = torch.zeros(HIDDEN, NUM_MONO, dtype=torch.float32, device=dev).index_add_(1, fold, w1.float()).T
+        w1m_t[NUM_MONO] = sd["basis_fn.1.bias"]
+        lay = lambda name: torch.stack([sd[f"interaction_layers.{l}.{name}"] for l in range(L)])  # noqa: E731
+        wk = lay("conv.kernel.weight")
+        wemb = sd["x_embedder.weight"]
+        wr = torch.stack([sd[f"read_out_layers.{l}.weight"] for l in range(L)])
+        br = torch.stack([sd[f"read_out_layers.{l}.bias"] for l in range(L)])
+        self.num_readout = wr.shape[1]
+        self.num_states = self.num_readout - 4
+        self.num_vec = 4
+        self.num_scalar = wemb.shape[1] - self.num_vec
+        self.t = dict(
+            ori=f(ori_grid.to(dev)), w_embed_t=f(wemb.T), w1m_t=w1m_t, w2_t=f(sd["basis_fn.3.weight"].T),
+            b2=f(sd["basis_fn.3.bias"]), wk_t=f(wk.permute(2, 0, 1).reshape(BASIS, L * HIDDEN)),
+            conv_bias=f(lay("conv.bias")), ln_w=f(lay("norm.weight")), ln_b=f(lay("norm.bias")),
+            mlp_w1_t=f(lay("linear_1.weight").transpose(1, 2)), mlp_b1=f(lay("linear_1.bias")),
+            mlp_w2_t=f(lay("linear_2.weight").transpose(1, 2)), mlp_b2=f(lay("linear_2.bias")),
+            layer_scale=f(lay("layer_scale")), wr_t=f(wr.transpose(1, 2)), br=f(br),
+            fiber_kernel=torch.empty(L, NUM_ORI, NUM_ORI, HIDDEN, dtype=torch.float32, device=dev))
+        keep = [f(sd["fiber_basis_fn.1.weight"]), f(sd["fiber_basis_fn.1.bias"]), f(sd["fiber_basis_fn.3.weight"]),
+                f(sd["fiber_basis_fn.3.bias"]), f(lay("conv.fiber_kernel.weight"))]
+        _lib.call("arreau_fiber_kernel_precompute", self.t["ori"].data_ptr(), *[k.data_ptr() for k in keep],
+                  self.t["fiber_kernel"].data_ptr(), torch.cuda.current_stream(dev).cuda_stream)
+        self._keep = keep            # stay alive until the stream has consumed them
+        self.c = _lib.Weights()
+        for name, _ in _lib.Weights._fields_:
+            if name in self.t:
+                setattr(self.c, name, self.t[name].data_ptr())
+        self.c.num_scalar, self.c.num_vec, self.c.num_states = self.num_scalar, self.num_vec, self.num_states
+        return self
+
     def ref(self):
         return C.byref(self.c)

@@ -322,6 +322,83 @@ typedef struct arreau_step_args {
 int arreau_denoise_step(const arreau_weights* w, const arreau_workspace* ws, const arreau_step_args* a,
                         void* stream);
 
+/* ---------------------------------------------------------------------------------------------
+ * Training step   replaces DiffusionLoss.__call__ (diffusion/diffusion_loss.py:204-274),
+ *     the forward noising it calls, and the autograd backward of the network (trainer.fit, main_diffusion.py:307).
+ *     The forward pass of a training step is arreau_ponita_forward (fp32) run with ws->h_debug / x1_debug /
+ *     x2_debug set, so that every layer's h, x1, x2 and the per-layer spatial kernels stay in memory.
+ * ------------------------------------------------------------------------------------------- */
+
+/* lengths[G,3], angles[G,3] (radians) of lattice[G,3,3]            (diffusion/lattice_helpers.py:16-35) */
+int arreau_matrix_to_params(const double* lattice, int32_t num_crystals, double* lengths, double* angles, void* stream);
+
+/* VE_pbc.forward (diffusion/diffusion_helpers.py:43-63): frac_noisy = (frac0 + eps * sigma_t) % 1 and the training
+ * target = frac coordinates (% 1) of the minimum-image cartesian vector from the clean to the noisy position over the
+ * 27 cells (min_distance_sqr_pbc :254-325, cart_to_frac_coords :233-251).  eps[N,3] is the injected randn. */
+int arreau_ve_pbc_forward(const double* frac0, const double* eps, const int32_t* t_of_atom, const double* ve_sigmas,
+                          const double* lattice, const int32_t* crystal_of_atom, int32_t num_atoms_total,
+                          double* frac_noisy, double* target_eps, void* stream);
+
+/* VP_lattice.forward (helpers:156-163): sqrt(abar_t) lengths + sqrt(1 - abar_t) eps with the fp32 abar table (B1). */
+int arreau_vp_lattice_forward(const double* lengths, const double* eps, const int32_t* t_of_crystal,
+                              const float* vp_alpha_bars, int32_t num_crystals, double* noisy_lengths, void* stream);
+
+/* D3PM.get_xt / q_sample (diffusion/d3pm.py:119-127,139-143), mask chain: argmax(log(Qbar_t[x0,:] + eps) + gumbel(u)). */
+int arreau_d3pm_q_sample(const int64_t* types0, const double* u, const int32_t* t_of_atom, const double* q_keep,
+                         const double* q_to_mask, int32_t num_atoms_total, int32_t num_states, int64_t* types_t,
+                         void* stream);
+
+/* The three-term loss (diffusion_loss.py:95-110,253-274; d3pm.py:74-117,145-163) and its gradient with respect to
+ * the network outputs.  loss_out[5] f64 = {loss, wrapped-MSE(frac), vb, ce, MSE(lengths / n)} with
+ * loss = frac + (hybrid_coeff * vb + ce) + lattice.  terms_scratch: 3*N doubles.  Fixed-order reductions. */
+int arreau_training_loss(const float* score, const float* logits, const float* len0, const double* target_eps,
+                         const int64_t* types0, const int64_t* types_t, const int32_t* t_of_atom, const double* lengths,
+                         const int32_t* atom_offset, const double* q_keep, const double* q_to_mask, double onestep_keep,
+                         double onestep_to_mask, int32_t num_steps, int32_t num_atoms_total, int32_t num_crystals,
+                         int32_t num_states, double hybrid_coeff, double* terms_scratch, double* loss_out, float* dscore,
+                         float* dlogits, float* dlen0, void* stream);
+
+/* Flat parameter / gradient buffer: every trainable tensor of the reference's state_dict in its own layout
+ * ([out, in] row-major), per-layer tensors stacked over the L layers, at these float offsets (SURVEY 8b names):
+ * basis_fn.{1,3}.{weight,bias}, fiber_basis_fn.{1,3}.{weight,bias}, x_embedder.weight, then per layer
+ * layer_scale, conv.bias, conv.kernel.weight, conv.fiber_kernel.weight, linear_1.{weight,bias},
+ * linear_2.{weight,bias}, norm.{weight,bias}, read_out_layers.{weight,bias}. */
+typedef struct arreau_train_layout_t {
+  int64_t basis_w1, basis_b1, basis_w2, basis_b2, fiber_w1, fiber_b1, fiber_w2, fiber_b2, embed_w;
+  int64_t layer_scale, conv_bias, conv_kernel_w, conv_fiber_w, lin1_w, lin1_b, lin2_w, lin2_b, norm_w, norm_b;
+  int64_t readout_w, readout_b, total;
+} arreau_train_layout_t;
+int arreau_train_layout(int32_t num_scalar, int32_t num_vec, int32_t num_states, arreau_train_layout_t* layout);
+
+/* Bytes of float workspace arreau_ponita_backward needs for N atoms and this edge capacity. */
+int64_t arreau_ponita_backward_workspace_bytes(int32_t num_atoms_total, int64_t edge_capacity, int32_t num_scalar,
+                                               int32_t num_vec);
+
+/* Gradient of sum(dlogits*logits) + sum(dscore*score) + sum(dlen0*len0) with respect to every parameter (autograd
+ * of ponita/models/ponita.py:88-155 and the layers it calls).  params / grads: flat buffers in arreau_train_layout_t
+ * order (grads is overwritten).  w / ws: the packed weights and the workspace of the forward pass that produced the
+ * outputs (ws->h_debug, x1_debug, x2_debug, kernels must hold that pass; fp32 path).  fold_table[258] i32: monomial
+ * index of each PolynomialFeatures(3) column.  Deterministic: split reductions with a fixed-order second stage and a
+ * sender-side gather for the transposed message pass, no atomics. */
+int arreau_ponita_backward(const float* params, const arreau_train_layout_t* layout, const arreau_weights* w,
+                           const arreau_workspace* ws, const int32_t* fold_table, const float* x, const float* vec,
+                           const int32_t* row_ptr, const int32_t* src, const int32_t* dst, const double* dist,
+                           const double* dir, const double* lattice, const int32_t* atom_offset,
+                           const int32_t* crystal_of_atom, int32_t num_atoms_total, int32_t num_crystals, double radius,
+                           const float* dlogits, const float* dscore, const float* dlen0, float* workspace,
+                           int64_t workspace_bytes, float* grads, void* stream);
+
+/* The fp32 GEMM the backward pass is built from: C[M,N] (=|+=) alpha * A * B (+ bias[n]).  a_k_contiguous: A is stored
+ * [M][K] (else [K][M]); b_k_contiguous: B is stored [N][K] (else [K][N]).  Long reductions (K) are split over CTAs
+ * into `partial` and summed in a fixed order.  Exposed for the parity tests. */
+int arreau_sgemm(int32_t a_k_contiguous, int32_t b_k_contiguous, const float* A, int64_t lda, const float* B, int64_t ldb,
+                 float* C, int64_t ldc, int32_t M, int32_t N, int64_t K, float alpha, const float* bias,
+                 int32_t accumulate, float* partial, int64_t partial_floats, void* stream);
+
+/* out[2] f64 = {sum, sum of squares} of x[n] f32 (minus sub_cols[i % 128] when given): the statistics of
+ * FiberBundleConv.callibrate (ponita/nn/conv.py:122-123,140-146).  scratch: 512 doubles. */
+int arreau_moments(const float* x, const float* sub_cols, int64_t n, double* scratch, double* out, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

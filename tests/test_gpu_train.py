@@ -1,0 +1,186 @@
+"""Training step on the GPU against the fixtures generated from the LIVE reference
+(tests/golden/train_c5small.npz: DiffusionLoss.__call__ + loss.backward() of the unmodified reference, fp64) and
+against the oracle (oracle/training.py) on seeded inputs.  Everything goes through the C ABI.
+
+Tolerances: noising / targets are fp64 kernels -> 1e-12 (types bit exact); the network runs in fp32 -> loss and
+outputs 1e-4 of max|ref| (north_star), parameter gradients 2e-3 of max|ref| per tensor (fp32 accumulation over up to
+E*O rows against an fp64 reference; measured ~1e-5)."""
+import ctypes as C
+
+import numpy as np
+import pytest
+import torch
+
+from conftest import f64_default, rel_err
+
+pytestmark = pytest.mark.gpu
+T, Z = 1000, 90
+
+
+def _case(z, case):
+    p = f"{case}/"
+    return {k[len(p):]: z[k] for k in z.files if k.startswith(p)}
+
+
+def _engine(device, weights_npz, num_atoms, sd=None):
+    from arreau_b200.tables import build_tables
+    from arreau_b200.training import FlatParams, TrainEngine
+    sd = {k: weights_npz[k] for k in weights_npz.files if k not in ("ori_grid", "fourier_w")} if sd is None else sd
+    p = FlatParams(164, 4, Z, device)
+    p.load_state_dict(sd)
+    return TrainEngine(p, build_tables(T, Z), weights_npz["fourier_w"], weights_npz["ori_grid"], num_atoms, 5.0, 8,
+                       device=device)
+
+
+@pytest.mark.parametrize("M,N,K,ak,bk,acc", [(300, 128, 96, 1, 1, 0), (128, 256, 20000, 0, 0, 0), (1000, 512, 128, 1, 0, 1),
+                                             (128, 16, 256, 0, 0, 0), (77, 128, 94, 1, 0, 1), (512, 128, 5000, 0, 0, 1)])
+def test_sgemm_against_torch(device, M, N, K, ak, bk, acc):
+    """The generic GEMM of the backward pass against a torch fp64 matmul of the same operands."""
+    from arreau_b200 import _lib
+    g = torch.Generator(device="cpu").manual_seed(M + N + K)
+    Kp = (K + 3) // 4 * 4
+    A = torch.randn((M, Kp) if ak else (K, M), generator=g).to(device)
+    B = torch.randn((N, Kp) if bk else (K, N), generator=g).to(device)
+    if ak:
+        A[:, K:] = 0
+    if bk:
+        B[:, K:] = 0
+    Cm = torch.randn(M, N, generator=g).to(device)
+    bias = torch.randn(N, generator=g).to(device)
+    ref = (A.double()[:, :K] if ak else A.double().T) @ (B.double()[:, :K].T if bk else B.double())
+    ref = 0.5 * ref + (Cm.double() if acc else 0)
+    use_bias = K <= 4096
+    if use_bias:
+        ref = ref + bias.double()
+    partial = torch.empty(4 << 20, device=device)
+    _lib.call("arreau_sgemm", ak, bk, A.data_ptr(), A.stride(0), B.data_ptr(), B.stride(0), Cm.data_ptr(), N, M, N, K,
+              C.c_float(0.5), bias.data_ptr() if use_bias else None, acc, partial.data_ptr(), partial.numel(),
+              torch.cuda.current_stream().cuda_stream)
+    assert rel_err(Cm.cpu().numpy(), ref.cpu().numpy()) < 2e-6 * max(1.0, np.sqrt(K) / 16)
+
+
+@pytest.mark.parametrize("case", [0, 1])
+def test_noising_matches_reference(device, gold, weights_npz, case):
+    c = _case(gold("train_c5small.npz"), case)
+    te = _engine(device, weights_npz, c["num_atoms"])
+    te.set_batch(c["frac0"], c["types0"], c["lattice0"], c["timestep"], c["eps_x"], c["u"], c["eps_l"])
+    te.noise_batch()
+    e = te.eng
+    assert np.array_equal(e.types.cpu().numpy(), c["noisy_types"])
+    d = np.abs(e.frac.cpu().numpy() - c["noisy_frac"])
+    assert np.minimum(d, 1 - d).max() < 1e-12
+    d = np.abs(te.target_eps.cpu().numpy() - c["target_eps"])
+    assert np.minimum(d, 1 - d).max() < 1e-10
+    assert rel_err(te.lengths0.cpu().numpy(), c["lengths"]) < 1e-14
+    assert rel_err(te.angles0.cpu().numpy(), c["angles"]) < 1e-13
+    assert rel_err(e.lengths.cpu().numpy(), c["noisy_lengths"]) < 1e-14
+
+
+@pytest.mark.parametrize("case", [0, 1])
+def test_loss_and_gradients_match_reference(device, gold, weights_npz, case):
+    c = _case(gold("train_c5small.npz"), case)
+    te = _engine(device, weights_npz, c["num_atoms"])
+    loss, _ = te.loss_and_grads(c["frac0"], c["types0"], c["lattice0"], c["timestep"], c["eps_x"], c["u"], c["eps_l"])
+    torch.cuda.synchronize()
+    e = te.eng
+    assert rel_err(e.score.cpu().numpy(), c["pred_eps"]) < 1e-4
+    assert rel_err(e.logits.cpu().numpy(), c["pred_logits"]) < 1e-4
+    assert rel_err(e.len0.cpu().numpy(), c["pred_len"]) < 1e-4
+    got = loss.cpu().numpy()
+    assert abs(got[0] - float(c["loss"])) <= 1e-4 * abs(float(c["loss"]))
+    for i, k in enumerate(("e_frac", "vb", "ce", "e_lat"), start=1):
+        assert abs(got[i] - float(c[k])) <= 1e-4 * max(abs(float(c[k])), 1e-3), (k, got[i], float(c[k]))
+    gv = te.p.grad_views()
+    worst = {}
+    for k, g in gv.items():
+        g = g.cpu().numpy()
+        if case == 0:
+            err = rel_err(g, c["grad/" + k])
+        else:
+            ref_norm = float(c["gradnorm/" + k])
+            err = max(abs(float(np.linalg.norm(g.astype(np.float64))) - ref_norm) / max(ref_norm, 1e-30),
+                      rel_err(g.reshape(-1)[:64], c["gradhead/" + k]) if np.abs(c["gradhead/" + k]).max() > 1e-3 * ref_norm else 0.0)
+        worst[k] = err
+    bad = {k: v for k, v in worst.items() if not v < 2e-3}
+    assert not bad, bad
+
+
+def test_loss_gradients_wrt_outputs_against_oracle(device, gold, weights_npz):
+    """dloss/d(score, logits, len0) of arreau_training_loss against autograd on the oracle's loss (fp64)."""
+    from oracle import restatement as R, training as TR
+    c = _case(gold("train_c5small.npz"), 0)
+    te = _engine(device, weights_npz, c["num_atoms"])
+    te.set_batch(c["frac0"], c["types0"], c["lattice0"], c["timestep"], c["eps_x"], c["u"], c["eps_l"])
+    te.noise_batch()
+    e = te.eng
+    N, G = e.N, e.G
+    g = torch.Generator().manual_seed(3)
+    score = torch.randn(N, 3, generator=g, dtype=torch.float64) * 0.7
+    logits = torch.randn(N, Z, generator=g, dtype=torch.float64) * 2.0
+    len0 = torch.randn(G, 3, generator=g, dtype=torch.float64) + 2.0
+    e.score.copy_(score)
+    e.logits.copy_(logits)
+    e.len0.copy_(len0)
+    te.compute_loss()
+    with f64_default():
+        tabs = R.DiffusionTables.build(T, Z)
+        s, l, n = [x.float().double().requires_grad_(True) for x in (score, logits, len0)]
+        t_atom = torch.as_tensor(c["timestep"]).reshape(-1).repeat_interleave(torch.as_tensor(c["num_atoms"]))
+        ef = TR.frac_x_error(s, torch.as_tensor(c["target_eps"]))
+        et, vb, ce = TR.d3pm_calculate_loss(tabs, torch.as_tensor(c["types0"]), l, torch.as_tensor(c["noisy_types"]), t_atom)
+        el = torch.nn.functional.mse_loss(n, torch.as_tensor(c["lengths"]) / torch.as_tensor(c["num_atoms"]).unsqueeze(-1))
+        total = ef + et + el
+        gs, gl, gn = torch.autograd.grad(total, [s, l, n])
+    got = te.loss.cpu().numpy()
+    for a, b in zip(got, (total, ef, vb, ce, el)):
+        assert abs(a - b.item()) <= 1e-10 * max(1.0, abs(b.item()))
+    assert rel_err(te.dscore.cpu().numpy(), gs.numpy()) < 1e-6
+    assert rel_err(te.dlogits.cpu().numpy(), gl.numpy()) < 1e-6
+    assert rel_err(te.dlen0.cpu().numpy(), gn.numpy()) < 1e-6
+
+
+def test_backward_is_deterministic(device, gold, weights_npz):
+    c = _case(gold("train_c5small.npz"), 1)
+    te = _engine(device, weights_npz, c["num_atoms"])
+    args = (c["frac0"], c["types0"], c["lattice0"], c["timestep"], c["eps_x"], c["u"], c["eps_l"])
+    te.loss_and_grads(*args)
+    g0, l0 = te.p.grad.clone(), te.loss.clone()
+    te.loss_and_grads(*args)
+    assert torch.equal(g0, te.p.grad) and torch.equal(l0, te.loss)
+
+
+def test_calibrate_matches_reference(device, gold, weights_npz):
+    """FiberBundleConv.callibrate (conv.py:122-123,140-146): the rescaled kernel / fiber_kernel weights."""
+    c = _case(gold("train_c5small.npz"), "cal")
+    te = _engine(device, weights_npz, c["num_atoms"])
+    te.calibrate(c["frac"], c["types"], c["lengths"], c["angles"], int(c["timestep"]))
+    v = te.p.views()
+    for k in c:
+        if k.startswith("after/"):
+            assert rel_err(v[k[6:]].cpu().numpy(), c[k]) < 1e-4, k
+
+
+def test_larger_batch_against_oracle(device, weights_npz):
+    """A C5-shaped batch (48 crystals, 1..40 atoms): loss and gradients against the oracle's autograd."""
+    from arreau_b200.synthetic import make_crystals
+    from oracle import restatement as R, training as TR
+    cr = make_crystals(48, 1, 40, seed=77)
+    G, N = cr.num_crystals, cr.total_atoms
+    with f64_default():
+        torch.manual_seed(9)
+        timestep, eps_x, u, eps_l = TR.draw_training_noise(G, N, Z, T)
+        sd = {k: torch.as_tensor(weights_npz[k], dtype=torch.float64) for k in weights_npz.files
+              if k not in ("ori_grid", "fourier_w")}
+        W = R.PonitaWeights(sd, torch.as_tensor(weights_npz["ori_grid"], dtype=torch.float64), 5.0)
+        tabs = R.DiffusionTables.build(T, Z)
+        L0 = R.lattice_from_params(torch.as_tensor(cr.lengths), torch.as_tensor(cr.angles))
+        loss, grads, parts = TR.training_grads(W, tabs, torch.as_tensor(weights_npz["fourier_w"], dtype=torch.float64),
+                                               torch.as_tensor(cr.frac), torch.as_tensor(cr.types), L0,
+                                               torch.as_tensor(cr.num_atoms), timestep, eps_x, u, eps_l, 5.0, 8)
+    te = _engine(device, weights_npz, cr.num_atoms)
+    got, _ = te.loss_and_grads(cr.frac, cr.types, L0.numpy(), timestep.numpy(), eps_x.numpy(), u.numpy(), eps_l.numpy())
+    assert abs(got[0].item() - loss.item()) <= 1e-4 * abs(loss.item())
+    gv = te.p.grad_views()
+    bad = {k: rel_err(gv[k].cpu().numpy(), grads[k].numpy()) for k in grads}
+    bad = {k: v for k, v in bad.items() if not v < 2e-3}
+    assert not bad, bad
