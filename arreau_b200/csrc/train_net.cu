@@ -551,6 +551,19 @@ __global__ void fold_w1_kernel(const float* __restrict__ w1, const float* __rest
   }
   w1m[c * 128 + k] = s;
 }
+// the same fold in the forward's layout: w1m_t[k][c], k < 96 (rows 84..95 zero)
+__global__ void fold_w1_t_kernel(const float* __restrict__ w1, const float* __restrict__ b1, const int32_t* __restrict__ fold,
+                                 int nfeat, float* __restrict__ w1m_t) {
+  const int k = blockIdx.x, c = threadIdx.x;   // grid 96, 128 threads
+  float s = 0.f;
+  if (k < kMono) {
+    for (int f = 0; f < nfeat; ++f)
+      if (fold[f] == k) s += w1[(size_t)c * nfeat + f];
+  } else if (k == kMono) {
+    s = b1[c];
+  }
+  w1m_t[k * kC + c] = s;
+}
 __global__ void unfold_w1_grad_kernel(const float* __restrict__ dw1m, const int32_t* __restrict__ fold, int nfeat,
                                       float* __restrict__ dw1, float* __restrict__ db1) {
   const int c = blockIdx.x;
@@ -694,6 +707,13 @@ extern "C" int64_t arreau_ponita_backward_workspace_bytes(int32_t N, int64_t edg
   if (N < 0 || edge_capacity < 0) return ARREAU_ERR_BAD_SHAPE;
   const int xl_pitch = ((num_scalar + num_vec + 127) / 128) * 128;
   return (int64_t)(carve(nullptr, N, edge_capacity, xl_pitch).total * sizeof(float));
+}
+
+extern "C" int arreau_fold_basis_w1(const float* w1, const float* b1, const int32_t* fold_table, float* w1m_t, void* stream) {
+  if (!w1 || !b1 || !fold_table || !w1m_t) return ARREAU_ERR_NULL;
+  fold_w1_t_kernel<<<kMonoPad, kC, 0, (cudaStream_t)stream>>>(w1, b1, fold_table, 258, w1m_t);
+  CUDA_LAUNCH_CHECK();
+  return ARREAU_OK;
 }
 
 extern "C" int arreau_moments(const float* x, const float* sub_cols, int64_t n, double* scratch, double* out,

@@ -335,7 +335,48 @@ loss_finish_kernel(const double* __restrict__ terms, const float* __restrict__ l
   }
 }
 
+// torch.optim.Adam step (diffusion.py:161-210: two weight-decay groups, L2 decay folded into the gradient) with the
+// trainer's global-norm clip (main_diffusion.py:297, clip_grad_norm_: coef = min(1, max_norm / (norm + 1e-6))) read
+// from the device so that the step never synchronises with the host.
+__global__ void __launch_bounds__(256)
+adam_step_kernel(float* __restrict__ p, const float* __restrict__ g, float* __restrict__ m, float* __restrict__ v,
+                 const uint8_t* __restrict__ decay_mask, long long n, float lr, float beta1, float beta2, float eps,
+                 float weight_decay, float bias_c1, float bias_c2_sqrt, float max_grad_norm,
+                 const double* __restrict__ grad_moments) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  float coef = 1.0f;
+  if (grad_moments && max_grad_norm > 0.f) {
+    const float norm = (float)sqrt(grad_moments[1]);
+    coef = fminf(max_grad_norm / (norm + 1e-6f), 1.0f);
+  }
+  float gi = g[i] * coef;
+  const float pi = p[i];
+  if (decay_mask && decay_mask[i]) gi = fmaf(weight_decay, pi, gi);
+  const float mi = beta1 * m[i] + (1.0f - beta1) * gi;
+  const float vi = beta2 * v[i] + (1.0f - beta2) * gi * gi;
+  m[i] = mi;
+  v[i] = vi;
+  const float denom = sqrtf(vi) / bias_c2_sqrt + eps;
+  p[i] = pi - (lr / bias_c1) * (mi / denom);
+}
+
 }  // namespace
+
+extern "C" int arreau_adam_step(float* params, const float* grads, float* exp_avg, float* exp_avg_sq,
+                                const uint8_t* decay_mask, int64_t n, double lr, double beta1, double beta2, double eps,
+                                double weight_decay, int64_t step, double max_grad_norm, const double* grad_moments,
+                                void* stream) {
+  if (n == 0) return ARREAU_OK;
+  if (!params || !grads || !exp_avg || !exp_avg_sq) return ARREAU_ERR_NULL;
+  if (n < 0 || step < 1) return ARREAU_ERR_BAD_SHAPE;
+  const double c1 = 1.0 - pow(beta1, (double)step), c2 = 1.0 - pow(beta2, (double)step);
+  adam_step_kernel<<<(unsigned)((n + 255) / 256), 256, 0, (cudaStream_t)stream>>>(
+      params, grads, exp_avg, exp_avg_sq, decay_mask, n, (float)lr, (float)beta1, (float)beta2, (float)eps,
+      (float)weight_decay, (float)c1, (float)sqrt(c2), (float)max_grad_norm, grad_moments);
+  CUDA_LAUNCH_CHECK();
+  return ARREAU_OK;
+}
 
 extern "C" int arreau_matrix_to_params(const double* lattice, int32_t G, double* lengths, double* angles, void* stream) {
   if (G == 0) return ARREAU_OK;

@@ -87,7 +87,7 @@ def radius_graph_pbc(cart_coords, lattice, num_atoms, radius, max_num_neighbors_
 
 
 class VE_pbc(nn.Module):
-    """diffusion/diffusion_helpers.py:28-81 (reverse step only; the forward noising is a training-path item)."""
+    """diffusion/diffusion_helpers.py:28-81: forward noising (training) and reverse step (sampling)."""
 
     def __init__(self, num_steps, sigma_min, sigma_max):
         super().__init__()
@@ -99,6 +99,20 @@ class VE_pbc(nn.Module):
         finally:
             torch.set_default_dtype(prev)
         self.register_buffer("sigmas", sig)
+
+    def forward(self, frac_x0, t, lattice, num_atoms, noise=None, **kwargs):
+        """helpers:43-63: returns (frac_noisy, wrapped_frac_eps_x, used_sigmas).  `noise` injects randn_like(frac_x0)."""
+        frac0 = _cuda(frac_x0, torch.float64)
+        dev = frac0.device
+        eps = torch.randn_like(frac0) if noise is None else _cuda(noise, torch.float64)
+        lat = _cuda(lattice.reshape(-1, 3, 3), torch.float64)
+        tt = _cuda(t.reshape(-1), torch.int32)
+        _, coa = _topology(num_atoms, dev)
+        sigmas = self.sigmas.to(dev)
+        noisy, target = torch.empty_like(frac0), torch.empty_like(frac0)
+        _lib.call("arreau_ve_pbc_forward", frac0.data_ptr(), eps.data_ptr(), tt.data_ptr(), sigmas.data_ptr(),
+                  lat.data_ptr(), coa.data_ptr(), frac0.shape[0], noisy.data_ptr(), target.data_ptr(), _stream(dev))
+        return noisy, target, sigmas[tt.long()].view(-1, 1)
 
     def reverse(self, xt, epx_x, t, lattice=None, num_atoms=None, noise=None):
         """Returns (xt - eps (s_t^2 - s_{t-1}^2) + sqrt(s_{t-1}^2 (s_t^2 - s_{t-1}^2) / s_t^2) z) % 1.
@@ -126,6 +140,18 @@ class VP_lattice(nn.Module):
         self.register_buffer("alpha_bars", self.tables.vp_alpha_bars)
         self.register_buffer("betas", self.tables.vp_betas)
         self.register_buffer("sigmas", self.tables.vp_sigmas)
+
+    def forward(self, h0, t, noise=None):
+        """helpers:156-163: (sqrt(abar_t) h0 + sqrt(1 - abar_t) eps, eps); t is [G] or [G,1]."""
+        lengths = _cuda(h0, torch.float64)
+        dev = lengths.device
+        eps = torch.randn_like(lengths) if noise is None else _cuda(noise, torch.float64)
+        tt = _cuda(t.reshape(-1), torch.int32)
+        ab = self.alpha_bars.to(dev, torch.float32)
+        out = torch.empty_like(lengths)
+        _lib.call("arreau_vp_lattice_forward", lengths.data_ptr(), eps.data_ptr(), tt.data_ptr(), ab.data_ptr(),
+                  lengths.shape[0], out.data_ptr(), _stream(dev))
+        return out, eps
 
     def reverse_given_x0(self, xt, pred_x0, t, noise=None):
         """`pred_x0` is the already scaled prediction (len0 * num_atoms, diffusion_loss.py:338)."""

@@ -12,10 +12,12 @@ import numpy as np
 import torch
 import torch.nn.functional as F
 
+from .. import _lib
 from ..engine import DenoiseEngine
 from ..tables import POS_SIGMA_MAX, POS_SIGMA_MIN, build_tables
 from .d3pm import D3PM
 from .diffusion_helpers import VE_pbc, VP_lattice
+from .lattice_helpers import matrix_to_params
 
 pos_sigma_min = POS_SIGMA_MIN
 pos_sigma_max = POS_SIGMA_MAX
@@ -38,6 +40,22 @@ def sample_bravais_angles(lattice_type: str = "monoclinic"):
     return [90.0, np.random.uniform(90, 180), 90.0]
 
 
+class _TrainStepLoss(torch.autograd.Function):
+    """The scalar loss of one training step as an autograd node: the step's kernels have already produced the flat
+    gradient buffer (TrainEngine.loss_and_grads), backward() hands its slices to the parameters."""
+
+    @staticmethod
+    def forward(ctx, engine, names, out_dtype, *params):
+        ctx.engine, ctx.names = engine, names
+        return engine.loss[0].to(out_dtype).clone()
+
+    @staticmethod
+    def backward(ctx, grad_out):
+        gv = ctx.engine.p.grad_views()
+        scale = grad_out.to(torch.float32)
+        return (None, None, None) + tuple(gv[n] * scale for n in ctx.names)
+
+
 class DiffusionLoss(torch.nn.Module):
     """diffusion/diffusion_loss.py:67-93.  `args` needs .radius, .max_neighbors, .num_timesteps."""
 
@@ -52,6 +70,8 @@ class DiffusionLoss(torch.nn.Module):
         self.lattice_diffusion = VP_lattice(num_steps=self.T)
         self._engine = None
         self._engine_key = None
+        self._train_engines = {}
+        self.coord_loss_weight = self.atom_type_loss_weight = self.lattice_loss_weight = 1
 
     # -- engine cache: one per (model weights, topology) --------------------------------------------
     def engine_for(self, model, t_emb_weights, num_atoms, device, debug=False) -> DenoiseEngine:
@@ -66,6 +86,67 @@ class DiffusionLoss(torch.nn.Module):
                                          precision=self.precision, debug=debug, device=device)
             self._engine_key = key
         return self._engine
+
+    # -- training step (diffusion_loss.py:95-110,199-274) ---------------------------------------------
+    def train_engine_for(self, net, t_emb_weights, num_atoms, device, max_cached: int = 8):
+        """One TrainEngine per batch topology (atoms per crystal), a few kept."""
+        from ..training import TrainEngine
+        flat = net.flat if getattr(net, "flat", None) is not None and net.flat.device == torch.device(device) \
+            else net.flatten_parameters(device)
+        na = tuple(int(v) for v in torch.as_tensor(num_atoms).reshape(-1).tolist())
+        key = (id(flat), na)
+        te = self._train_engines.pop(key, None)
+        if te is None:
+            fw = t_emb_weights.gaussian_fourier_proj_w if hasattr(t_emb_weights, "gaussian_fourier_proj_w") else t_emb_weights
+            te = TrainEngine(flat, self.tables, fw, net.ori_grid, na, self.cutoff, self.max_neighbors, device=device)
+            while len(self._train_engines) >= max_cached:
+                self._train_engines.pop(next(iter(self._train_engines)))
+        self._train_engines[key] = te
+        return te
+
+    def compute_frac_x_error(self, pred_frac_eps_x, target_frac_eps_x, batch=None):
+        """diffusion_loss.py:95-110 (value only; gradients flow through __call__)."""
+        d = torch.clamp(torch.remainder((pred_frac_eps_x - target_frac_eps_x).abs(), 1), min=0, max=1)
+        d = torch.min(d, 1 - d)
+        return torch.mean(torch.sum(d ** 2, dim=1))
+
+    def diffuse_lattice_params(self, lattice: torch.Tensor, t_int: torch.Tensor):
+        """diffusion_loss.py:199-202."""
+        lengths, angles = matrix_to_params(lattice)
+        noisy_lengths, _ = self.lattice_diffusion(lengths, t_int)
+        return noisy_lengths, lengths, angles
+
+    def __call__(self, model, batch, t_emb_weights, timestep=None, noise=None):
+        """diffusion_loss.py:204-274: samples t and the noise (the reference's draws, in its order, on the batch's
+        device), noises the batch, predicts, and returns the scalar loss.  The returned tensor is attached to the
+        model's parameters: `.backward()` delivers the gradients the step's backward kernels produced.  `noise`
+        optionally injects (eps_x[N,3], u[N,Z], eps_l[G,3]).  Loss parts of the last call: `self.last_loss_parts`."""
+        frac_x_0, atom_type_0 = batch.X0, batch.A0
+        lattice_0 = batch.L0.view(-1, 3, 3)
+        num_atoms = batch.num_atoms
+        dev = frac_x_0.device
+        if dev.type != "cuda":
+            raise RuntimeError("arreau_b200 runs on CUDA tensors only (no CPU fallback)")
+        G, N, Z = num_atoms.size(0), frac_x_0.shape[0], self.num_atomic_states
+        if timestep is None:
+            timestep = torch.randint(1, self.T + 1, size=(G, 1), device=dev).long()
+        else:
+            timestep = torch.ones((G, 1), device=dev).long() * timestep
+        if noise is None:   # VE_pbc.forward, D3PM.get_xt, VP_lattice.forward draw in this order (:228-237)
+            eps_x = torch.randn_like(frac_x_0)
+            u = torch.rand((N, Z), device=dev)
+            eps_l = torch.randn((G, 3), device=dev, dtype=frac_x_0.dtype)
+        else:
+            eps_x, u, eps_l = noise
+        net = getattr(model, "model", model)
+        te = self.train_engine_for(net, t_emb_weights, num_atoms, dev)
+        te.loss_and_grads(frac_x_0, atom_type_0, lattice_0, timestep, eps_x, u, eps_l)
+        self.last_loss_parts = te.loss
+        names = [n for n, p in net.named_parameters() if p.numel() > 0]
+        params = [p for _, p in net.named_parameters() if p.numel() > 0]
+        return _TrainStepLoss.apply(te, names, frac_x_0.dtype, *params)
+
+    forward = __call__
 
     def predict_scores(self, noisy_frac_x, noisy_atom_types, t_feat, num_atoms, noisy_lengths, angles, model, batch,
                        t_emb_weights):

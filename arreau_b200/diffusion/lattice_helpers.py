@@ -21,3 +21,14 @@ def lattice_from_params(lengths: torch.Tensor, angles: torch.Tensor) -> torch.Te
     _lib.call("arreau_lattice_from_params", lengths.data_ptr(), angles.data_ptr(), G, out.data_ptr(),
               torch.cuda.current_stream(lengths.device).cuda_stream)
     return out
+
+
+def matrix_to_params(matrix: torch.Tensor):
+    """diffusion/lattice_helpers.py:16-35: (lengths[G,3], angles[G,3] in radians) of [G,3,3] row-vector lattices."""
+    m = _dev(matrix).to(torch.float64).reshape(-1, 3, 3).contiguous()
+    G = m.shape[0]
+    lengths = torch.empty(G, 3, dtype=torch.float64, device=m.device)
+    angles = torch.empty(G, 3, dtype=torch.float64, device=m.device)
+    _lib.call("arreau_matrix_to_params", m.data_ptr(), G, lengths.data_ptr(), angles.data_ptr(),
+              torch.cuda.current_stream(m.device).cuda_stream)
+    return lengths, angles

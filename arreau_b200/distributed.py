@@ -48,3 +48,30 @@ def gather_sample_results(local: SampleResult, group=None, device: Optional[torc
     idx_start = np.concatenate([[0], np.cumsum(num_atoms)[:-1]]) if num_atoms.size else num_atoms
     return SampleResult(frac_x=cat(frac, 0), atomic_numbers=cat(zs, 0), lattice=cat(lat, 1), idx_start=idx_start,
                         num_atoms=num_atoms)
+
+
+def allreduce_gradients(flat_grad: torch.Tensor, group=None) -> torch.Tensor:
+    """The DDP step of the training config: ONE all-reduce of the flat gradient buffer
+    (1 170 646 fp32 = 4.7 MB), averaged over the ranks like Lightning's DDP strategy.  NCCL on the GPUs, gloo in
+    the CPU tests.  In place; returns the buffer."""
+    if dist.is_initialized() and dist.get_world_size(group) > 1:
+        dist.all_reduce(flat_grad, op=dist.ReduceOp.SUM, group=group)
+        flat_grad.div_(dist.get_world_size(group))
+    return flat_grad
+
+
+def reduce_loss_metric(total_loss: torch.Tensor, total_samples: torch.Tensor, group=None) -> torch.Tensor:
+    """DiffusionLossMetric (diffusion/diffusion_loss.py:52-65): both states are summed over the ranks
+    (dist_reduce_fx="sum"), compute() = total_loss / total_samples."""
+    if dist.is_initialized() and dist.get_world_size(group) > 1:
+        pair = torch.stack([total_loss.double().reshape(()), total_samples.double().reshape(())])
+        dist.all_reduce(pair, op=dist.ReduceOp.SUM, group=group)
+        return pair[0] / pair[1]
+    return total_loss.double() / total_samples.double()
+
+
+def broadcast_parameters(flat_data: torch.Tensor, src: int = 0, group=None) -> torch.Tensor:
+    """Replicas start from rank `src`'s weights (DDP's initial broadcast)."""
+    if dist.is_initialized() and dist.get_world_size(group) > 1:
+        dist.broadcast(flat_data, src=src, group=group)
+    return flat_data

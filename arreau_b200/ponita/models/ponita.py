@@ -82,6 +82,7 @@ class PonitaFiberBundle(nn.Module):
                              persistent=False)
         self._packed = None
         self._ws = None
+        self.flat = None
 
     # -- weights ------------------------------------------------------------------------------
     def set_orientation_grid(self, ori_grid) -> None:
@@ -93,6 +94,25 @@ class PonitaFiberBundle(nn.Module):
         sd = {k: v for k, v in state_dict.items() if k in own and tuple(v.shape) == tuple(own[k].shape)}
         self._packed = None
         return super().load_state_dict(sd, strict=False, **kw)
+
+    def flatten_parameters(self, device):
+        """Re-home every trainable tensor into ONE flat fp32 CUDA buffer (arreau_train_layout_t order, see
+        arreau_b200/training.py FlatParams): the nn.Parameters become views of it, keep their reference names, and an
+        optimizer / gradient all-reduce sees a single tensor.  Returns the FlatParams (also kept as `self.flat`)."""
+        from ...training import FlatParams
+        n_out = self.read_out_layers[0].out_features
+        flat = FlatParams(self.x_embedder.in_features - 4, 4, n_out - 4, device)
+        views = flat.views()
+        with torch.no_grad():
+            for name, p in self.named_parameters():
+                if p.numel() == 0:
+                    continue
+                views[name].copy_(p.detach().to(torch.float32))
+                p.data = views[name]
+                p.grad = None
+        self.flat = flat
+        self._packed = None
+        return flat
 
     def pack(self, device) -> PonitaWeights:
         """(Re)build the kernel weight layouts; call after changing parameters in place."""

@@ -75,3 +75,16 @@ def calibrate_length_readout(state: dict, atoms_per_crystal: int, num_layers: in
         b[first_row:first_row + 3] = a_target / atoms_per_crystal ** 2
         out[f"read_out_layers.{l}.weight"], out[f"read_out_layers.{l}.bias"] = w, b
     return out
+
+
+def make_training_batch(num_crystals: int = 270, seed: int = 0, mean_atoms: float = 8.5, max_atoms: int = 236) -> Crystals:
+    """C5: a training batch of `num_crystals` (Makefile:7 batch size 270) small cells, n drawn from a
+    shifted exponential with mean ~8.5 atoms (152.5 A^3 mean cell x 0.0554 atoms/A^3) capped at the dataset's
+    largest cell (236 atoms); Alexandria-shaped geometry like make_crystals."""
+    rng = np.random.default_rng(seed)
+    n = np.minimum(1 + np.floor(rng.exponential(mean_atoms - 1.0, size=num_crystals)).astype(np.int64), max_atoms)
+    a = np.cbrt(VOLUME_PER_ATOM * n.astype(np.float64))
+    lengths = a[:, None] * (1.0 + 0.1 * rng.standard_normal((num_crystals, 3)))
+    angles = np.pi / 2 + 0.1 * rng.standard_normal((num_crystals, 3))
+    N = int(n.sum())
+    return Crystals(rng.random((N, 3)), rng.integers(0, NUM_ELEMENT_STATES, size=N).astype(np.int64), lengths, angles, n)

@@ -58,6 +58,15 @@ class FlatParams:
             self.specs[f"read_out_layers.{l}.bias"] = (lay.readout_b + l * R, (R,))
         assert sum(int(np.prod(s)) for _, s in self.specs.values()) == self.total
 
+    def decay_mask(self) -> torch.Tensor:
+        """1 for the elements torch.optim.Adam decays in the reference (lightning_wrappers/diffusion.py:161-186: the
+        `weight` of every nn.Linear), 0 for biases, LayerNorm weights and layer_scale."""
+        mask = torch.zeros(self.total, dtype=torch.uint8)
+        for k, (off, shape) in self.specs.items():
+            if k.endswith(".weight") and ".norm." not in k:
+                mask[off:off + int(np.prod(shape))] = 1
+        return mask.to(self.device)
+
     def _views(self, buf: torch.Tensor) -> Dict[str, torch.Tensor]:
         return {k: buf[off:off + int(np.prod(shape))].view(shape) for k, (off, shape) in self.specs.items()}
 
@@ -76,6 +85,45 @@ class FlatParams:
         return {k: v.clone() for k, v in self.views().items()}
 
 
+def cosine_warmup_factor(epoch: int, warmup: int, max_iters: int) -> float:
+    """lightning_wrappers/scheduler.py:14-18."""
+    f = 0.5 * (1 + np.cos(np.pi * epoch / max_iters))
+    if epoch <= warmup:
+        f *= (epoch + 1e-6) * 1.0 / (warmup + 1e-6)
+    return float(f)
+
+
+class FusedAdam:
+    """torch.optim.Adam over the flat buffers as one kernel (arreau_adam_step) with the reference's two weight-decay
+    groups and the trainer's global-norm clip (gradient_clip_val=0.5, main_diffusion.py:297)."""
+
+    def __init__(self, params: FlatParams, lr: float = 3e-4, betas=(0.9, 0.999), eps: float = 1e-8,
+                 weight_decay: float = 0.0, max_grad_norm: float = 0.5):
+        self.p, self.base_lr, self.lr = params, lr, lr
+        self.betas, self.eps, self.weight_decay, self.max_grad_norm = betas, eps, weight_decay, max_grad_norm
+        self.exp_avg, self.exp_avg_sq = torch.zeros_like(params.data), torch.zeros_like(params.data)
+        self.mask = params.decay_mask()
+        self.step_count = 0
+        self.scratch = torch.zeros(512, dtype=torch.float64, device=params.device)
+        self.moments = torch.zeros(2, dtype=torch.float64, device=params.device)
+
+    def set_epoch(self, epoch: int, warmup: int, max_epochs: int) -> None:
+        self.lr = self.base_lr * cosine_warmup_factor(epoch, warmup, max_epochs)
+
+    def step(self) -> None:
+        p = self.p
+        s = torch.cuda.current_stream(p.device).cuda_stream
+        self.step_count += 1
+        _lib.call("arreau_moments", p.grad.data_ptr(), None, p.total, self.scratch.data_ptr(), self.moments.data_ptr(), s)
+        _lib.call("arreau_adam_step", p.data.data_ptr(), p.grad.data_ptr(), self.exp_avg.data_ptr(),
+                  self.exp_avg_sq.data_ptr(), self.mask.data_ptr(), p.total, self.lr, self.betas[0], self.betas[1],
+                  self.eps, self.weight_decay, self.step_count, self.max_grad_norm, self.moments.data_ptr(), s)
+
+    def grad_norm(self) -> float:
+        """Global L2 norm of the last step's (unclipped) gradient (host synchronisation)."""
+        return float(np.sqrt(self.moments[1].item()))
+
+
 class TrainEngine:
     """One batch topology (atoms per crystal) on one GPU."""
 
@@ -83,7 +131,8 @@ class TrainEngine:
                  radius: float, max_neighbors: int, device="cuda"):
         self.p, self.tabs = params, tables
         self.device = dev = torch.device(device)
-        self.ori = torch.as_tensor(np.asarray(ori_grid), dtype=torch.float32).to(dev)
+        self.ori = (ori_grid.detach() if isinstance(ori_grid, torch.Tensor) else torch.as_tensor(np.asarray(ori_grid))) \
+            .to(dev, torch.float32).contiguous()
         self.w = PonitaWeights.from_device_params(params.views(), self.ori)
         self.eng = DenoiseEngine(self.w, tables, fourier_w, num_atoms, radius, max_neighbors, precision="fp32",
                                  debug=True, device=dev)
@@ -175,6 +224,7 @@ class TrainEngine:
     def loss_and_grads(self, frac0, types0, lattice0, timestep, eps_x, u, eps_l):
         """DiffusionLoss.__call__ + loss.backward(): returns (loss[5] f64 device = {total, frac, vb, ce, lattice},
         flat gradient buffer)."""
+        self.repack()
         self.set_batch(frac0, types0, lattice0, timestep, eps_x, u, eps_l)
         self.noise_batch()
         self.predict()

@@ -153,11 +153,11 @@ class PonitaWeights:
         self.device = dev
         L = LAYERS
         f = lambda a: a.to(torch.float32).contiguous()  # noqa: E731
-        w1 = sd["basis_fn.1.weight"]
-        fold = torch.as_tensor(monomial_fold_table(), device=dev)
-        w1m_t = torch.zeros(MONO_PAD, HIDDEN, dtype=torch.float32, device=dev)
-        w1m_t[:NUM_MONO] = torch.zeros(HIDDEN, NUM_MONO, dtype=torch.float32, device=dev).index_add_(1, fold, w1.float()).T
-        w1m_t[NUM_MONO] = sd["basis_fn.1.bias"]
+        w1, b1 = f(sd["basis_fn.1.weight"]), f(sd["basis_fn.1.bias"])
+        fold = torch.as_tensor(monomial_fold_table(), dtype=torch.int32).to(dev)
+        w1m_t = torch.empty(MONO_PAD, HIDDEN, dtype=torch.float32, device=dev)
+        _lib.call("arreau_fold_basis_w1", w1.data_ptr(), b1.data_ptr(), fold.data_ptr(), w1m_t.data_ptr(),
+                  torch.cuda.current_stream(dev).cuda_stream)      # fixed summation order (no atomics)
         lay = lambda name: torch.stack([sd[f"interaction_layers.{l}.{name}"] for l in range(L)])  # noqa: E731
         wk = lay("conv.kernel.weight")
         wemb = sd["x_embedder.weight"]
@@ -179,7 +179,7 @@ class PonitaWeights:
                 f(sd["fiber_basis_fn.3.bias"]), f(lay("conv.fiber_kernel.weight"))]
         _lib.call("arreau_fiber_kernel_precompute", self.t["ori"].data_ptr(), *[k.data_ptr() for k in keep],
                   self.t["fiber_kernel"].data_ptr(), torch.cuda.current_stream(dev).cuda_stream)
-        self._keep = keep            # stay alive until the stream has consumed them
+        self._keep = keep + [w1, b1, fold]   # stay alive until the stream has consumed them
         self.c = _lib.Weights()
         for name, _ in _lib.Weights._fields_:
             if name in self.t:

@@ -190,8 +190,98 @@ def config_dict(args):
             "parallelism": f"crystal-sharded x{args.gpus}, no per-step collective"}
 
 
+def run_train(args):
+    """--workload train: BASELINE.json configs[4] (C5): one training step = noising + predict_scores + 3-term loss +
+    backward + gradient all-reduce (N>1) + Adam on a synthetic 270-crystal batch per GPU.  Not the headline metric;
+    prints its own JSON line (train_crystals_per_sec) with a per-phase breakdown."""
+    import torch
+    import torch.distributed as dist
+    from arreau_b200 import _lib
+    from arreau_b200.distributed import allreduce_gradients, broadcast_parameters
+    from arreau_b200.synthetic import make_training_batch
+    from arreau_b200.tables import build_tables
+    from arreau_b200.training import FlatParams, FusedAdam, TrainEngine
+    rank, world = int(os.environ.get("RANK", "0")), int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    w = np.load(os.path.join(ROOT, "tests", "golden", "weights_seed0.npz"))
+    sd = {k: w[k] for k in w.files if k not in ("ori_grid", "fourier_w")}
+    p = FlatParams(164, 4, Z, dev)
+    p.load_state_dict(sd)
+    broadcast_parameters(p.data)
+    cr = make_training_batch(args.crystals if args.crystals != 1024 else 270, seed=100 + rank)
+    G, N = cr.num_crystals, cr.total_atoms
+    te = TrainEngine(p, build_tables(T_STEPS, Z), w["fourier_w"], w["ori_grid"], cr.num_atoms, args.radius, args.cap, device=dev)
+    opt = FusedAdam(p, lr=3e-4, max_grad_norm=0.5)
+    from arreau_b200.diffusion.lattice_helpers import lattice_from_params
+    lat0 = lattice_from_params(torch.as_tensor(cr.lengths).to(dev), torch.as_tensor(cr.angles).to(dev))
+    g = torch.Generator(device=dev).manual_seed(7 + rank)
+    phases = ["noise", "forward", "loss", "backward", "allreduce", "adam"]
+    frac0, types0 = torch.as_tensor(cr.frac).to(dev), torch.as_tensor(cr.types).to(dev)
+
+    def step(timed):
+        ts = torch.randint(1, T_STEPS + 1, (G,), device=dev, generator=g)
+        eps_x = torch.randn(N, 3, device=dev, dtype=torch.float64, generator=g)
+        u = torch.rand(N, Z, device=dev, dtype=torch.float64, generator=g)
+        eps_l = torch.randn(G, 3, device=dev, dtype=torch.float64, generator=g)
+        evs = [torch.cuda.Event(enable_timing=True) for _ in range(len(phases) + 1)] if timed else None
+        mark = (lambda i: evs[i].record()) if timed else (lambda i: None)
+        mark(0)
+        te.repack(); te.set_batch(frac0, types0, lat0, ts, eps_x, u, eps_l); te.noise_batch(); mark(1)
+        te.predict(); mark(2)
+        te.compute_loss(); mark(3)
+        te.backward(); mark(4)
+        allreduce_gradients(p.grad); mark(5)
+        opt.step(); mark(6)
+        return evs
+
+    for _ in range(max(args.warmup, 3)):
+        step(False)
+    torch.cuda.synchronize(dev)
+    if world > 1:
+        dist.barrier()
+    l0 = _lib.launch_count()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(args.steps):
+        step(False)
+    e1.record()
+    torch.cuda.synchronize(dev)
+    launches = _lib.launch_count() - l0
+    ms = e0.elapsed_time(e1) / args.steps
+    if world > 1:
+        tmax = torch.tensor([ms], device=dev)
+        dist.all_reduce(tmax, op=dist.ReduceOp.MAX)
+        ms = float(tmax.item())
+    br = {k: 0.0 for k in phases}
+    for _ in range(3):
+        evs = step(True)
+        torch.cuda.synchronize(dev)
+        for i, k in enumerate(phases):
+            br[k] += evs[i].elapsed_time(evs[i + 1]) / 3
+    if rank == 0:
+        E = te.eng.num_edges()
+        print(json.dumps({"metric": "train_crystals_per_sec", "value": world * G / (ms * 1e-3), "unit": "crystals/s",
+                          "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": ms,
+                          "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
+                          "data": "synthetic", "impl": "ours",
+                          "config": {"workload": f"C5: training step (score-matching + D3PM + lattice loss), {G} crystals "
+                                                 f"/ {N} atoms / {E} edges per GPU, max_neighbors {args.cap}, "
+                                                 f"{'DDP x' + str(world) if world > 1 else 'single GPU'}",
+                                     "parallelism": f"data parallel x{world}: one all-reduce of the flat 4.7 MB gradient"},
+                          "loss": te.loss.tolist(), "gpu_launches": int(launches),
+                          "breakdown_ms_per_step": {k: round(v, 4) for k, v in br.items()}}))
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
 def main():
     ap = argparse.ArgumentParser()
+    ap.add_argument("--workload", default="sample", choices=["sample", "train"])
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=10)
     ap.add_argument("--warmup", type=int, default=3)
@@ -214,6 +304,8 @@ def main():
     args.warmup = max(args.warmup, 0)
     if args.impl == "reference":
         return run_reference(args)
+    if args.workload == "train":
+        return run_train(args)
 
     import torch
     import torch.distributed as dist

@@ -395,9 +395,23 @@ int arreau_sgemm(int32_t a_k_contiguous, int32_t b_k_contiguous, const float* A,
                  float* C, int64_t ldc, int32_t M, int32_t N, int64_t K, float alpha, const float* bias,
                  int32_t accumulate, float* partial, int64_t partial_floats, void* stream);
 
+/* w1m_t[96,C]: basis_fn.1.weight[C,258] with the columns of equal monomials summed (fixed order), row 83 = the bias,
+ * rows 84..95 zero -- the first-layer operand of arreau_edge_kernels_f32 (embedding.py:10-14 has only 83 distinct
+ * monomials).  Used to re-pack the weights on the device after every optimizer step. */
+int arreau_fold_basis_w1(const float* w1, const float* b1, const int32_t* fold_table, float* w1m_t, void* stream);
+
 /* out[2] f64 = {sum, sum of squares} of x[n] f32 (minus sub_cols[i % 128] when given): the statistics of
  * FiberBundleConv.callibrate (ponita/nn/conv.py:122-123,140-146).  scratch: 512 doubles. */
 int arreau_moments(const float* x, const float* sub_cols, int64_t n, double* scratch, double* out, void* stream);
+
+/* One torch.optim.Adam step on the flat buffers (lightning_wrappers/diffusion.py:161-210: L2 weight decay on the
+ * elements whose decay_mask byte is set, i.e. the Linear weights) after the trainer's global-norm clip
+ * (main_diffusion.py:297, gradient_clip_val = 0.5): coef = min(1, max_grad_norm / (sqrt(grad_moments[1]) + 1e-6)),
+ * grad_moments = the {sum, sum of squares} arreau_moments wrote for the gradient buffer (device memory, so the step
+ * does not synchronise; NULL or max_grad_norm <= 0 disables clipping).  step counts from 1. */
+int arreau_adam_step(float* params, const float* grads, float* exp_avg, float* exp_avg_sq, const uint8_t* decay_mask,
+                     int64_t n, double lr, double beta1, double beta2, double eps, double weight_decay, int64_t step,
+                     double max_grad_norm, const double* grad_moments, void* stream);
 
 #ifdef __cplusplus
 }

@@ -50,3 +50,34 @@ def test_shard_and_gather_world2(tmp_path):
         assert np.allclose(z["frac"][:, 0], np.arange(sizes.sum()) + 0.1)
         assert np.array_equal(z["z"], np.arange(sizes.sum()) % 89 + 1)
         assert np.array_equal(z["lat"][:, 0, 0], np.arange(7))
+
+
+def _ddp_worker(rank, world, port, out):
+    import torch
+    import torch.distributed as dist
+    from arreau_b200.distributed import allreduce_gradients, broadcast_parameters, reduce_loss_metric
+    dist.init_process_group("gloo", init_method=f"tcp://127.0.0.1:{port}", rank=rank, world_size=world)
+    try:
+        grad = torch.full((1170646,), float(rank + 1))
+        allreduce_gradients(grad)
+        params = torch.full((16,), float(rank))
+        broadcast_parameters(params, src=0)
+        metric = reduce_loss_metric(torch.tensor(3.0 * (rank + 1)), torch.tensor(rank + 1))
+        out[rank] = (float(grad[0]), float(grad[-1]), float(params.sum()), float(metric))
+    finally:
+        dist.destroy_process_group()
+
+
+def test_ddp_gradient_allreduce_world2_gloo():
+    """C5's only collectives: mean of the flat gradient buffer, the initial weight broadcast and the
+    2-scalar loss metric, over a 2-rank gloo group on CPU."""
+    import socket
+    import torch.multiprocessing as mp
+    with socket.socket() as s:
+        s.bind(("127.0.0.1", 0))
+        port = s.getsockname()[1]
+    out = mp.Manager().dict()
+    mp.spawn(_ddp_worker, args=(2, port, out), nprocs=2, join=True)
+    for r in range(2):
+        g0, g1, psum, metric = out[r]
+        assert g0 == g1 == 1.5 and psum == 0.0 and abs(metric - 3.0) < 1e-12

@@ -152,3 +152,33 @@ def test_product_does_not_import_the_oracle():
             if f.endswith(".py"):
                 src = open(os.path.join(dirpath, f)).read()
                 assert not re.search(r"^\s*(from|import)\s+oracle\b", src, flags=re.M), f
+
+
+def test_flat_param_layout_matches_reference_state_dict(weights_npz):
+    """arreau_train_layout (host-only entry point): every trainable tensor of the reference's state_dict has a slice
+    of the flat buffer with its own shape; 1 170 646 parameters in total."""
+    import torch
+    from arreau_b200.training import FlatParams
+    p = FlatParams(164, 4, 90, "cpu")
+    names = [k for k in weights_npz.files if k not in ("ori_grid", "fourier_w")]
+    assert p.total == 1170646 == sum(weights_npz[k].size for k in names)
+    assert set(p.specs) == set(names)
+    for k in names:
+        assert tuple(p.specs[k][1]) == tuple(weights_npz[k].shape), k
+    spans = sorted((off, off + int(np.prod(shape))) for off, shape in p.specs.values())
+    assert spans[0][0] == 0 and all(a[1] == b[0] for a, b in zip(spans, spans[1:])) and spans[-1][1] == p.total
+    p.load_state_dict({k: weights_npz[k] for k in names})
+    sd = p.state_dict()
+    assert all(np.array_equal(sd[k].numpy(), weights_npz[k]) for k in names)
+    # weight-decay groups of lightning_wrappers/diffusion.py:161-186
+    mask = p.decay_mask()
+    v = p._views(mask)
+    assert all(bool(v[k].all()) == (k.endswith(".weight") and ".norm." not in k) for k in names)
+    assert all(bool(v[k].any()) == bool(v[k].all()) for k in names)
+
+
+def test_cosine_warmup_factor():
+    from arreau_b200.training import cosine_warmup_factor
+    assert abs(cosine_warmup_factor(0, 10, 100)) < 1e-6
+    assert abs(cosine_warmup_factor(10, 10, 100) - 0.5 * (1 + np.cos(np.pi * 0.1))) < 1e-12
+    assert abs(cosine_warmup_factor(50, 10, 100) - 0.5) < 1e-12
