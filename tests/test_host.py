@@ -182,3 +182,79 @@ def test_cosine_warmup_factor():
     assert abs(cosine_warmup_factor(0, 10, 100)) < 1e-6
     assert abs(cosine_warmup_factor(10, 10, 100) - 0.5 * (1 + np.cos(np.pi * 0.1))) < 1e-12
     assert abs(cosine_warmup_factor(50, 10, 100) - 0.5) < 1e-12
+
+
+def _ref_args(T=1000):
+    import argparse
+    return argparse.Namespace(dataset="synthetic", lr=3e-4, weight_decay=0.0, epochs=1, warmup=0, layer_scale=1e-6,
+                              train_augm=False, hidden_dim=128, layers=5, radius=5.0, num_ori=16, basis_dim=256, degree=3,
+                              widening_factor=4, multiple_readouts=True, num_timesteps=T, max_neighbors=8)
+
+
+def test_sample_result_writer_round_trip(tmp_path):
+    """Wire format of generated crystals (inference/process_generated_crystals.py:8-31): five arrays under crystals/."""
+    from arreau_b200.diffusion.diffusion_loss import SampleResult
+    from arreau_b200.inference.process_generated_crystals import (KEYS, get_crystal_indexes, load_sample_results_from_hdf5,
+                                                                  save_sample_results_to_hdf5)
+    rng = np.random.default_rng(0)
+    res = SampleResult(frac_x=rng.random((12, 3)), atomic_numbers=rng.integers(1, 90, 12), lattice=rng.random((3, 3, 3)),
+                       idx_start=np.array([0, 4, 8]), num_atoms=np.array([4, 4, 4]))
+    path = save_sample_results_to_hdf5(res, str(tmp_path / "out" / "crystals.h5"))
+    back = load_sample_results_from_hdf5(path)
+    for k in KEYS:
+        assert np.array_equal(getattr(back, k), getattr(res, k)), k
+    assert get_crystal_indexes(back, 1) == (4, 8)
+
+
+def test_checkpoint_ingestion_remaps_reference_classes(tmp_path, weights_npz):
+    """A Lightning-shaped .ckpt whose pickled z_table lives at the REFERENCE's module path
+    (diffusion.tools.atomic_number_table) loads into the mirror by parameter name."""
+    import sys
+    import types
+    import torch
+    from arreau_b200.lightning_wrappers.diffusion import PONITA_DIFFUSION
+    mod_names = ["diffusion", "diffusion.tools", "diffusion.tools.atomic_number_table"]
+    saved = {n: sys.modules.get(n) for n in mod_names}
+    fake = types.ModuleType("diffusion.tools.atomic_number_table")
+
+    class AtomicNumberTable:   # stands in for the reference's class at pickling time
+        def __init__(self, zs):
+            self.zs = zs
+    AtomicNumberTable.__module__ = "diffusion.tools.atomic_number_table"
+    AtomicNumberTable.__qualname__ = "AtomicNumberTable"
+    fake.AtomicNumberTable = AtomicNumberTable
+    for n in mod_names[:2]:
+        sys.modules[n] = types.ModuleType(n)
+    sys.modules[mod_names[2]] = fake
+    try:
+        sd = {"model." + k: torch.as_tensor(weights_npz[k]) for k in weights_npz.files if k not in ("ori_grid", "fourier_w")}
+        sd["t_emb.gaussian_fourier_proj_w"] = torch.as_tensor(weights_npz["fourier_w"])
+        sd["z_table_zs"] = torch.tensor(list(range(1, 90)) + [2001])
+        sd["diffusion_loss.d3pm.q_mats"] = torch.zeros(2, 2)          # ignored: tables are rebuilt
+        ckpt = {"state_dict": sd, "hyper_parameters": {"args": _ref_args(), "z_table": AtomicNumberTable(list(range(1, 90)) + [2001])}}
+        path = str(tmp_path / "model.ckpt")
+        torch.save(ckpt, path)
+    finally:
+        for n in mod_names:
+            if saved[n] is None:
+                sys.modules.pop(n, None)
+            else:
+                sys.modules[n] = saved[n]
+    m = PONITA_DIFFUSION.load_from_checkpoint(path, ori_grid=weights_npz["ori_grid"], strict=True)
+    own = m.state_dict()
+    for k in weights_npz.files:
+        if k not in ("ori_grid", "fourier_w"):
+            assert np.array_equal(own["model." + k].numpy().astype(np.float32), weights_npz[k]), k
+    assert np.array_equal(own["t_emb.gaussian_fourier_proj_w"].numpy().astype(np.float32), weights_npz["fourier_w"])
+    assert m.z_table_zs.tolist()[-1] == 2001 and len(m.hparams.z_table) == 90
+    # round trip through the mirror's own checkpoint writer (carries the orientation grid, quirk B2)
+    p2 = str(tmp_path / "m2.ckpt")
+    m.save_checkpoint(p2)
+    m2 = PONITA_DIFFUSION.load_from_checkpoint(p2, strict=True)
+    assert np.allclose(m2.model.ori_grid.numpy(), weights_npz["ori_grid"])
+
+
+def test_atomic_symbols_to_indices():
+    from arreau_b200.tools.atomic_number_table import AtomicNumberTable, atomic_symbols_to_indices
+    zt = AtomicNumberTable(list(range(1, 90)) + [2001])
+    assert atomic_symbols_to_indices(zt, ["H", "C", "Ac"]).tolist() == [0, 5, 88]
