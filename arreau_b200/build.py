@@ -48,7 +48,7 @@ def build(force: bool = False, verbose: bool = False) -> str:
     for s in SOURCES:
         obj = os.path.join(LIB_DIR, s.replace(".cu", ".o"))
         objs.append(obj)
-        cmd = [_nvcc(), *NVCC_FLAGS, "-c", os.path.join(CSRC, s), "-o", obj]
+        cmd = [_nvcc(), *NVCC_FLAGS, *os.environ.get("ARREAU_NVCC_EXTRA", "").split(), "-c", os.path.join(CSRC, s), "-o", obj]
         procs.append((s, subprocess.Popen(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)))
     log = []
     for s, p in procs:

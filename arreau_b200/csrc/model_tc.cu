@@ -25,10 +25,14 @@ constexpr int kTileM = 128;
 constexpr uint32_t kIdesc128 = umma_idesc_f16(128, 128);
 
 __device__ long long* g_tc_prof = nullptr;   // debug: per-phase clock64 stamps of CTA 0 (scratch/prof_tc.py)
+#ifdef ARREAU_TC_PROFILE
 #define TC_STAMP(slot)                                                                     \
   do {                                                                                      \
     if (prof && it < 6) prof[(it * 2 + prof_role) * 16 + (slot)] = clock64();               \
   } while (0)
+#else
+#define TC_STAMP(slot) do { (void)prof; } while (0)
+#endif
 
 // issue the UMMA_K = 16 steps of one 64-wide K slab: D[128 x 128] (+)= A_slab[128 x 64] * B_slab[128 x 64]^T
 __device__ __forceinline__ void mma_slab(uint32_t tmem_d, uint32_t a_slab, uint32_t b_slab, int ksteps, bool accumulate_first) {
@@ -327,19 +331,21 @@ convnext_mlp_tc_kernel(const uint8_t* __restrict__ y_img, const uint8_t* __restr
 // K3 + K4a  edge pipeline
 // =================================================================================================
 namespace edge {
-constexpr int kChunkBytes = 16384;      // [128 rows x 64 K] fp16 = 1 slab
-constexpr int kStages = 6;
-constexpr int kW1Bytes = 32768;         // [128 x 96 -> 128] resident
-constexpr int kA2Bytes = 32768;
-constexpr int kA3Bytes = 65536;         // first 32 KB double as the monomial tile A1
-constexpr int kTilesBytes = kW1Bytes + kA2Bytes + kA3Bytes + kStages * kChunkBytes;
+constexpr int kChunkBytes = 32768;      // ring unit: two K slabs [128 rows x 64 K] fp16 of one weight matrix
+constexpr int kStages = 3;
+constexpr int kStageBytes = 32768;      // output staging: two 16 KB halves
+constexpr int kA2Bytes = 32768;         // doubles as the monomial tile A1
+constexpr int kA3Bytes = 65536;
+constexpr int kTilesBytes = kA2Bytes + kA3Bytes + kStageBytes + kStages * kChunkBytes;
 constexpr int kSmemBytes = 232448;      // everything (tiles, bias, barriers) is carved from the dynamic window
-constexpr int kChunksPerTile = 4 + 4 * kL;   // W2 (n-half, k-slab) x4, then Wk_l k-slabs
+constexpr int kChunksPerTile = 3 + 2 * kL;   // W1, W2 (n-half) x2, then two per Wk_l
 constexpr int kEdgesPerTile = kTileM / kO;
+constexpr int kGeo = 12;                // floats per edge: dir (3), dist, cos(dir, a/b/c) (3), window, valid, pad
 
 struct Bars {
-  uint64_t w1_full, w_full[kStages], w_empty[kStages];
-  uint64_t a1_full, a2_full, a3_full, d2_full;
+  uint64_t w_full[kStages], w_empty[kStages];
+  uint64_t a1_full, a2_full, a3_full, d1_full, d2_full;
+  uint64_t g_full[2], g_empty[2];     // per-edge geometry of a tile (warp 3 -> epilogue warps), double buffered
   uint64_t x_full[2], x_empty[2];     // TMEM buffers X0 (D1, D3 even layers) / X1 (D3 odd layers)
 };
 
@@ -418,32 +424,41 @@ edge_kernels_tc_kernel(const double* __restrict__ dir, const double* __restrict_
                        const int32_t* __restrict__ num_edges_ptr, long long edge_capacity, const float* __restrict__ ori,
                        const uint8_t* __restrict__ w1_img, const uint8_t* __restrict__ w_img, const float* __restrict__ b2,
                        double radius, __half* __restrict__ kernels) {
+  // Software pipeline over the CTA's tiles: while the tensor pipe runs the five kernel projections (GEMM3) of tile i
+  // out of A3, the head of tile i+1 -- monomials, GEMM1, GELU, GEMM2 -- runs in the shadow, so that only the second
+  // GELU epilogue (which has to overwrite A3) sits between two GEMM3 phases.
+  //   shared:  A2: monomial tile A1, then the hidden layer | A3: kernel basis | S: output staging | weight ring
+  //   TMEM:    X0 = [0,128) and X1 = [384,512): GEMM3 double buffer;  D2 = [128,384): GEMM1 (first half) then GEMM2
+  //   MMA issue order per tile i:   L0 L1 G1(i+1) L2 L3 G2(i+1) L4   (ring order Wk0 Wk1 W1 Wk2 Wk3 W2 Wk4, 26 chunks)
+  //   epilogue order per tile i:    gen(i+1) E0 E1 Q1(i+1) E2 E3 E4 Q2(i+1)
   using namespace edge;
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
   uint8_t* smem = smem_raw + (base - smem_u32(smem_raw));
   float* const s_b2 = reinterpret_cast<float*>(smem + kTilesBytes);                                   // [kD]
-  Bars& bars = *reinterpret_cast<Bars*>(smem + kTilesBytes + (kD + kEdgesPerTile) * sizeof(float));
+  float* const s_geo = s_b2 + kD;                                                                      // [2][8 edges][kGeo]
+  Bars& bars = *reinterpret_cast<Bars*>(smem + kTilesBytes + (kD + 2 * kEdgesPerTile * kGeo) * sizeof(float));
   uint32_t& tmem_base_s =
-      *reinterpret_cast<uint32_t*>(smem + kTilesBytes + (kD + kEdgesPerTile) * sizeof(float) + sizeof(Bars));
-  if ((base - smem_u32(smem_raw)) + kTilesBytes + (kD + kEdgesPerTile) * sizeof(float) + sizeof(Bars) + 16 > (uint32_t)kSmemBytes)
+      *reinterpret_cast<uint32_t*>(smem + kTilesBytes + (kD + 2 * kEdgesPerTile * kGeo) * sizeof(float) + sizeof(Bars));
+  if ((base - smem_u32(smem_raw)) + kTilesBytes + (kD + 2 * kEdgesPerTile * kGeo) * sizeof(float) + sizeof(Bars) + 16 > (uint32_t)kSmemBytes)
     __trap();
-  uint8_t* const W1 = smem;
-  uint8_t* const A2 = W1 + kW1Bytes;
-  uint8_t* const A3 = A2 + kA2Bytes;          // A1 aliases A3[0 .. 32 KB)
-  uint8_t* const W = A3 + kA3Bytes;
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  uint8_t* const A2 = smem;                   // A1 (monomials) aliases A2
+  uint8_t* const A3 = A2 + kA2Bytes;
+  uint8_t* const S = A3 + kA3Bytes;           // two 16 KB halves (rows 0..63 / 64..127) of one layer's output tile
+  uint8_t* const W = S + kStageBytes;
+  const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0), lane = threadIdx.x & 31;   // warp-uniform
   long long E = *num_edges_ptr;
   if (E > edge_capacity) E = edge_capacity;
   const long long tiles = (E + kEdgesPerTile - 1) / kEdgesPerTile;
+  const long long first = blockIdx.x, stride = gridDim.x;
 
   for (int i = threadIdx.x; i < kD; i += kThreads) s_b2[i] = b2[i];
   if (threadIdx.x == 0) {
-    mbar_init(&bars.w1_full, 1);
     for (int i = 0; i < kStages; ++i) { mbar_init(&bars.w_full[i], 1); mbar_init(&bars.w_empty[i], 1); }
     mbar_init(&bars.a1_full, kEpiWarps); mbar_init(&bars.a2_full, kEpiWarps); mbar_init(&bars.a3_full, kEpiWarps);
-    mbar_init(&bars.d2_full, 1);
+    mbar_init(&bars.d1_full, 1); mbar_init(&bars.d2_full, 1);
     for (int i = 0; i < 2; ++i) { mbar_init(&bars.x_full[i], 1); mbar_init(&bars.x_empty[i], kEpiWarps); }
+    for (int i = 0; i < 2; ++i) { mbar_init(&bars.g_full[i], 1); mbar_init(&bars.g_empty[i], kEpiWarps); }
     fence_barrier_init();
   }
   if (warp == 2) tmem_alloc(&tmem_base_s, 512);
@@ -451,84 +466,126 @@ edge_kernels_tc_kernel(const double* __restrict__ dir, const double* __restrict_
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem = tmem_base_s;
-  // TMEM columns: X0 = [0,128)  D2 = [128,384)  X1 = [384,512)
 
-  if (warp == 0 && lane == 0) {
-    // ---------------- producer ----------------
-    mbar_expect_tx(&bars.w1_full, kW1Bytes);
-    bulk_g2s(W1, w1_img, kW1Bytes, &bars.w1_full);
-    uint32_t chunk = 0;
-    for (long long tile = blockIdx.x; tile < tiles; tile += gridDim.x) {
-      for (int c = 0; c < kChunksPerTile; ++c, ++chunk) {
-        const int ws = chunk % kStages;
-        mbar_wait(&bars.w_empty[ws], ((chunk / kStages) & 1) ^ 1);
-        mbar_expect_tx(&bars.w_full[ws], kChunkBytes);
-        bulk_g2s(W + ws * kChunkBytes, w_img + (size_t)c * kChunkBytes, kChunkBytes, &bars.w_full[ws]);
+  if (warp == 3) {
+    // ---------------- geometry: the per-edge part of the invariants, up to two tiles ahead ----------------
+    // (src -> crystal -> lattice, dir, dist are dependent global loads of ~3000 cycles; here they are off every
+    // critical path).  fp32 like the rest of the fp16 path: the monomials are rounded to fp16 right after.
+    uint32_t k = 0;
+    for (long long tile = first; tile < tiles; tile += stride, ++k) {
+      const int buf = k & 1;
+      mbar_wait(&bars.g_empty[buf], ((k >> 1) & 1) ^ 1);
+      if (lane < kEdgesPerTile) {
+        const long long e = tile * kEdgesPerTile + lane;
+        float* gp = s_geo + (buf * kEdgesPerTile + lane) * kGeo;
+        float vals[9] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+        if (e < E) {
+          const double* lat9 = lattice + 9 * (size_t)crystal_of_atom[src[e]];
+          const float dx = (float)dir[3 * e], dy = (float)dir[3 * e + 1], dz = (float)dir[3 * e + 2];
+          const float dd = dx * dx + dy * dy + dz * dz;
+          vals[0] = dx; vals[1] = dy; vals[2] = dz;
+          vals[3] = (float)dist[e];
+#pragma unroll
+          for (int mm = 0; mm < 3; ++mm) {
+            const float ax = (float)lat9[3 * mm], ay = (float)lat9[3 * mm + 1], az = (float)lat9[3 * mm + 2];
+            const float w12 = dx * ax + dy * ay + dz * az, w2 = ax * ax + ay * ay + az * az;
+            vals[4 + mm] = w12 * rsqrtf(fmaxf(dd * w2, 1e-16f));     // CosineSimilarity, eps = 1e-8
+          }
+          vals[7] = cutoff_window(dist[e], radius);
+          vals[8] = 1.0f;
+        }
+#pragma unroll
+        for (int i = 0; i < 9; ++i) gp[i] = vals[i];
+      }
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&bars.g_full[buf]);
+    }
+  } else if (warp == 0 && lane == 0) {
+    // ---------------- producer: 32 KB weight chunks (two K slabs) in the order the MMA warp consumes them ----------------
+    if (first < tiles) {
+      uint32_t st = 0, par = 1;          // waits on w_empty start at parity 1 (a fresh barrier passes)
+      auto push = [&](const uint8_t* src_chunk) {
+        mbar_wait(&bars.w_empty[st], par);
+        mbar_expect_tx(&bars.w_full[st], kChunkBytes);
+        bulk_g2s(W + st * kChunkBytes, src_chunk, kChunkBytes, &bars.w_full[st]);
+        if (++st == kStages) { st = 0; par ^= 1; }
+      };
+      auto push_w = [&](int c0, int n) { for (int c = c0; c < c0 + n; ++c) push(w_img + (size_t)c * kChunkBytes); };
+      push(w1_img);
+      push_w(0, 2);                                   // first tile: W1, W2
+      for (long long tile = first; tile < tiles; tile += stride) {
+        const bool has_next = tile + stride < tiles;
+        push_w(2, 4);                                 // Wk_0, Wk_1
+        if (has_next) push(w1_img);
+        push_w(6, 4);                                 // Wk_2, Wk_3
+        if (has_next) push_w(0, 2);                   // W2 of the next tile
+        push_w(10, 2);                                // Wk_4
       }
     }
-  } else if (warp == 1 && lane == 0) {
+  } else if (warp == 1) {
     // ---------------- MMA issuer ----------------
-    mbar_wait(&bars.w1_full, 0);
-    uint32_t chunk = 0;
-    uint32_t xuse0 = 0, xuse1 = 0;
-    int it = 0;
-    long long* prof = blockIdx.x == 0 ? g_tc_prof : nullptr;
-    constexpr int prof_role = 0;
-    const uint32_t w1_addr = smem_u32(W1), a2_addr = smem_u32(A2), a3_addr = smem_u32(A3);
-    auto wait_w = [&]() -> uint32_t {
-      const int ws = chunk % kStages;
-      mbar_wait(&bars.w_full[ws], (chunk / kStages) & 1);
-      tc_fence_after();
-      return smem_u32(W + ws * kChunkBytes);
-    };
-    auto release_w = [&]() {
-      umma_commit(&bars.w_empty[chunk % kStages]);
-      ++chunk;
-    };
-    for (long long tile = blockIdx.x; tile < tiles; tile += gridDim.x, ++it) {
-      // GEMM1: X0 = A1[128 x 96] . W1m^T
-      TC_STAMP(0);
-      mbar_wait(&bars.a1_full, it & 1);
-      mbar_wait(&bars.x_empty[0], (xuse0 & 1) ^ 1);
-      tc_fence_after();
-      TC_STAMP(1);
-      mma_slab(tmem, a3_addr, w1_addr, 4, false);
-      mma_slab(tmem, a3_addr + 16384, w1_addr + 16384, 2, true);
-      umma_commit(&bars.x_full[0]);
-      ++xuse0;
-      // GEMM2: D2[:, nh*128 ..] = A2[128 x 128] . W2[nh]^T
-      TC_STAMP(2);
-      mbar_wait(&bars.a2_full, it & 1);
-      tc_fence_after();
-      TC_STAMP(3);
-      for (int nh = 0; nh < 2; ++nh)
-        for (int ks = 0; ks < 2; ++ks) {
-          const uint32_t w_addr = wait_w();
-          mma_slab(tmem + 128 + nh * 128, a2_addr + ks * 16384, w_addr, 4, ks > 0);
-          release_w();
-        }
-      umma_commit(&bars.d2_full);
-      // GEMM3: X[l&1] = A3[128 x 256] . Wk_l^T
-      TC_STAMP(4);
-      mbar_wait(&bars.a3_full, it & 1);
-      tc_fence_after();
-      TC_STAMP(5);
-      for (int l = 0; l < kL; ++l) {
-        const int b = l & 1;
-        uint32_t& xuse = b ? xuse1 : xuse0;
-        mbar_wait(&bars.x_empty[b], (xuse & 1) ^ 1);
+    // The tensor pipe's issue queue is shallow: every cycle the issuer spends between two tcgen05.mma is an idle
+    // tensor cycle.  The whole warp runs this loop uniformly (descriptors and barrier addresses stay in uniform
+    // registers) and one elected lane issues; ring chunks are waited for in pairs, so that a barrier round covers
+    // 8 MMAs = 512 tensor cycles (measured: the pipe's floor of 64 cycles per MMA, scratch/ubench/mma_ring.cu).
+    if (first < tiles) {
+      const uint32_t el = elect_one();
+      const uint32_t a2_lo = umma_desc_lo(smem_u32(A2)), a3_lo = umma_desc_lo(smem_u32(A3)), w_lo = umma_desc_lo(smem_u32(W));
+      const uint32_t wfull = smem_u32(&bars.w_full[0]), wempty = smem_u32(&bars.w_empty[0]);
+      constexpr uint32_t kSlabLo = 16384 >> 4;          // descriptor step of one 16 KB slab / ring stage
+      uint32_t st = 0, par = 0;
+      // one ring chunk = two K slabs: D (+)= A[:, slab a] . chunk[0]^T + A[:, slab a+1] . chunk[1]^T, then hand it back
+      auto pair = [&](uint32_t d, uint32_t a_lo, int ksteps1, uint32_t accumulate) {
+        mbar_wait_addr(wfull + 8 * st, par);
+        const uint32_t b_lo = w_lo + st * (2 * kSlabLo);
+        umma_slab_e<4>(d, a_lo, b_lo, kIdesc128, el, accumulate);
+        if (ksteps1 == 4) umma_slab_e<4>(d, a_lo + kSlabLo, b_lo + kSlabLo, kIdesc128, el, 1u);
+        else umma_slab_e<2>(d, a_lo + kSlabLo, b_lo + kSlabLo, kIdesc128, el, 1u);
+        umma_commit_e(wempty + 8 * st, el);
+        if (++st == kStages) { st = 0; par ^= 1; }
+      };
+      auto gemm1 = [&](uint32_t k) {       // D2[:, 0:128] = A1[128 x 96] . W1m^T   (tile ordinal k)
+        mbar_wait(&bars.a1_full, k & 1);
         tc_fence_after();
-        const uint32_t d = tmem + b * 384;
-        if (l == 2) TC_STAMP(11);
-        for (int ks = 0; ks < 4; ++ks) {
-          const uint32_t w_addr = wait_w();
-          if (l == 2) TC_STAMP(12 + ks);
-          mma_slab(d, a3_addr + ks * 16384, w_addr, 4, ks > 0);
-          release_w();
+        pair(tmem + 128, a2_lo, 2, 0u);
+        umma_commit_e(smem_u32(&bars.d1_full), el);
+      };
+      auto gemm2 = [&](uint32_t k) {       // D2[:, nh*128 ..] = A2[128 x 128] . W2[nh]^T, chunks (nh, ks)
+        mbar_wait(&bars.a2_full, k & 1);
+        tc_fence_after();
+        pair(tmem + 128, a2_lo, 4, 0u);
+        pair(tmem + 256, a2_lo, 4, 0u);
+        umma_commit_e(smem_u32(&bars.d2_full), el);
+      };
+      gemm1(0);
+      gemm2(0);
+      uint32_t it = 0;
+      long long* prof = (blockIdx.x == 0 && el) ? g_tc_prof : nullptr;
+      constexpr int prof_role = 0;
+      for (long long tile = first; tile < tiles; tile += stride, ++it) {
+        const bool has_next = tile + stride < tiles;
+        TC_STAMP(0);
+        mbar_wait(&bars.a3_full, it & 1);      // kernel basis of tile `it` is in A3 (and D2 has been read out)
+        tc_fence_after();
+        TC_STAMP(1);
+#pragma unroll 1
+        for (int l = 0; l < kL; ++l) {
+          // X0 is used by layers 0, 2, 4 (use number 3 it + l/2), X1 by layers 1, 3 (2 it + l/2)
+          const int b = l & 1;
+          const uint32_t use_par = b ? (uint32_t)(l >> 1) & 1u : (it + (uint32_t)(l >> 1)) & 1u;
+          mbar_wait(&bars.x_empty[b], use_par ^ 1u);
+          tc_fence_after();
+          const uint32_t d = tmem + b * 384;
+          pair(d, a3_lo, 4, 0u);
+          pair(d, a3_lo + 2 * kSlabLo, 4, 1u);
+          umma_commit_e(smem_u32(&bars.x_full[b]), el);
+          TC_STAMP(2 + 2 * l);
+          if (has_next) {
+            if (l == 1) gemm1(it + 1);
+            if (l == 3) gemm2(it + 1);
+          }
+          TC_STAMP(3 + 2 * l);
         }
-        umma_commit(&bars.x_full[b]);
-        ++xuse;
-        TC_STAMP(6 + l);
       }
     }
   } else if (warp >= kEpiWarp0) {
@@ -536,133 +593,161 @@ edge_kernels_tc_kernel(const double* __restrict__ dir, const double* __restrict_
     const int q = warp & 3, cgi = (warp - kEpiWarp0) >> 2;
     const int m = q * 32 + lane;                     // tile row = (edge m / 16, orientation m % 16)
     const uint32_t lane_addr = (uint32_t)(q * 32) << 16;
-    uint32_t xuse0 = 0, xuse1 = 0;
-    int it = 0;
+    const int hf = q >> 1;                           // staging half of this warp's rows
     const bool is_issuer = cgi == 0 && (q & 1) == 0 && lane == 0;     // one bulk-store issuer per half tile
-    long long* prof = (blockIdx.x == 0 && threadIdx.x == kEpiWarp0 * 32) ? g_tc_prof : nullptr;
-    constexpr int prof_role = 1;
-    // invariants + window of this thread's row, computed one tile ahead (under GEMM3 of the previous tile) so the
-    // dependent global loads (src -> crystal -> lattice, dir, dist) are off the critical path
-    float attr[6], one, win;
-    auto compute_attr = [&](long long t) {
-      const long long e = t * kEdgesPerTile + (m >> 4);
-#pragma unroll
-      for (int i = 0; i < 6; ++i) attr[i] = 0.f;
-      one = 0.f;
-      win = 0.f;
-      if (t < tiles && e < E) {
-        const int g = crystal_of_atom[src[e]];
-        edge_invariants_f32(dir + 3 * e, dist[e], lattice + 9 * (size_t)g, ori + 3 * (m & 15), attr);
-        win = cutoff_window(dist[e], radius);
-        one = 1.0f;
-      }
-    };
-    compute_attr(blockIdx.x);
-    for (long long tile = blockIdx.x; tile < tiles; tile += gridDim.x, ++it) {
-      TC_STAMP(0);
-      // ---- A1: 83 monomials + constant 1 (bias) -> fp16; 3 of the 12 16-byte chunks per thread.
-      // The previous tile's GEMM3 finished reading A3 before its last x_full fired, which this warp waited on.
+    const float ox = ori[3 * (m & 15)], oy = ori[3 * (m & 15) + 1], oz = ori[3 * (m & 15) + 2];
+    float win_cur = 0.f;
+    // A1 of tile ordinal k: [dir.ori, |dir - (dir.ori) ori|, dist, cos(dir,a), cos(dir,b), cos(dir,c)] -> 83 monomials
+    // + constant 1 (bias) -> fp16 into A2; 3 of the 12 16-byte chunks per thread
+    auto gen = [&](uint32_t k) {
+      const int buf = k & 1;
+      mbar_wait(&bars.g_full[buf], (k >> 1) & 1);
+      const float* gp = s_geo + (buf * kEdgesPerTile + (m >> 4)) * kGeo;
+      const float dx = gp[0], dy = gp[1], dz = gp[2];
+      float attr[6];
+      const float i1 = dx * ox + dy * oy + dz * oz;
+      const float px = dx - i1 * ox, py = dy - i1 * oy, pz = dz - i1 * oz;
+      attr[0] = i1;
+      attr[1] = sqrtf(px * px + py * py + pz * pz);
+      attr[2] = gp[3]; attr[3] = gp[4]; attr[4] = gp[5]; attr[5] = gp[6];
+      win_cur = gp[7];
+      const float one = gp[8];
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&bars.g_empty[buf]);
       switch (cgi) {
-        case 0: store_mono_part<0>(attr, one, A3, m); break;
-        case 1: store_mono_part<1>(attr, one, A3, m); break;
-        case 2: store_mono_part<2>(attr, one, A3, m); break;
-        default: store_mono_part<3>(attr, one, A3, m); break;
+        case 0: store_mono_part<0>(attr, one, A2, m); break;
+        case 1: store_mono_part<1>(attr, one, A2, m); break;
+        case 2: store_mono_part<2>(attr, one, A2, m); break;
+        default: store_mono_part<3>(attr, one, A2, m); break;
       }
-      const float win_cur = win;
       fence_proxy_async();
       __syncwarp();
       if (lane == 0) mbar_arrive(&bars.a1_full);
-      TC_STAMP(1);
-      // ---- epilogue 1: hidden = GELU(X0) -> A2 (hidden unit cgi*32.. -> slab cgi>>1, chunks (cgi&1)*4..) ----
-      mbar_wait(&bars.x_full[0], xuse0 & 1);
+    };
+    // epilogue 1: hidden = GELU(D2[:, 0:128]) -> A2 (hidden unit cgi*32.. -> slab cgi>>1, chunks (cgi&1)*4..)
+    auto epi1 = [&](uint32_t k) {
+      mbar_wait(&bars.d1_full, k & 1);
       tc_fence_after();
-      TC_STAMP(2);
-      if (it > 0) {   // the previous tile's output stores were staged in A2: they must have left shared memory
-        if (is_issuer) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
-        asm volatile("bar.sync 3, %0;" ::"n"(kEpiThreads) : "memory");
-      }
-      {
-        float v[32];
-        tmem_ld32(tmem + lane_addr + cgi * 32, v);
-        gelu_store32<false, false>(v, nullptr, 1.0f, A2 + (cgi >> 1) * 16384 + m * kRowBytes, (cgi & 1) * 4, m);
-      }
+      float v[32];
+      tmem_ld32(tmem + 128 + lane_addr + cgi * 32, v);
+      gelu_store32<false, false>(v, nullptr, 1.0f, A2 + (cgi >> 1) * 16384 + m * kRowBytes, (cgi & 1) * 4, m);
       tc_fence_before();
       fence_proxy_async();
       __syncwarp();
-      if (lane == 0) {
-        mbar_arrive(&bars.x_empty[0]);
-        mbar_arrive(&bars.a2_full);
-      }
-      ++xuse0;
-      TC_STAMP(3);
-      // ---- epilogue 2: kernel basis = GELU(D2 + b2) * window -> A3; this warp: columns cgi*64 .. +63 = slab cgi ----
-      mbar_wait(&bars.d2_full, it & 1);
+      if (lane == 0) mbar_arrive(&bars.a2_full);
+    };
+    // epilogue 2: kernel basis = GELU(D2 + b2) * window -> A3; this warp: columns cgi*64 .. +63 = slab cgi
+    auto epi2 = [&](uint32_t k) {
+      mbar_wait(&bars.d2_full, k & 1);
       tc_fence_after();
-      TC_STAMP(4);
-      {
-        const float win = win_cur;
 #pragma unroll
-        for (int g = 0; g < 2; ++g) {
-          const int col0 = cgi * 64 + g * 32;
-          float v[32];
-          tmem_ld32(tmem + 128 + lane_addr + col0, v);
-          gelu_store32<true, true>(v, s_b2 + col0, win, A3 + cgi * 16384 + m * kRowBytes, g * 4, m);
-        }
+      for (int g = 0; g < 2; ++g) {
+        const int col0 = cgi * 64 + g * 32;
+        float v[32];
+        tmem_ld32(tmem + 128 + lane_addr + col0, v);
+        gelu_store32<true, true>(v, s_b2 + col0, win_cur, A3 + cgi * 16384 + m * kRowBytes, g * 4, m);
       }
       tc_fence_before();
       fence_proxy_async();
       __syncwarp();
       if (lane == 0) mbar_arrive(&bars.a3_full);
-      TC_STAMP(5);
-      compute_attr(tile + gridDim.x);        // next tile's geometry, hidden under this tile's GEMM3
-      // ---- epilogue 3: kernels[l][e][o][c] = X[l&1] (fp16), channels cgi*32 .. +31 ----
-      for (int l = 0; l < kL; ++l) {
-        const int b = l & 1;
-        uint32_t& xuse = b ? xuse1 : xuse0;
-        mbar_wait(&bars.x_full[b], xuse & 1);
-        tc_fence_after();
-        float v[32];
-        tmem_ld32(tmem + b * 384 + lane_addr + cgi * 32, v);
-        tc_fence_before();
-        __syncwarp();
-        if (lane == 0) mbar_arrive(&bars.x_empty[b]);       // accumulators are in registers: release the buffer
-        ++xuse;
-        // The layer's output tile is 32 KB contiguous in HBM: stage it in shared memory and let the TMA engine
-        // write it with bulk stores.  Rows are 256 B; the 16-byte chunk k of row (e, o) is stored at chunk position
-        // k ^ o (the fp16 kernels layout, undone by the message kernel's loads), which makes these 16-byte shared
-        // stores conflict free.  The idle A2 tile is the staging area, split in two 16 KB halves (rows 0..63 /
-        // 64..127) that are staged, stored and recycled independently by the 8 warps owning those rows: the store
-        // of layer l-1 has a whole GEMM3 layer (~1000 cycles) to leave shared memory before layer l restages.
-        const int hf = q >> 1;
-        uint8_t* stage = A2 + hf * 16384;
-        if (is_issuer) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");   // this half's previous store has left smem
-        asm volatile("bar.sync %0, %1;" ::"r"(1 + hf), "n"(kEpiThreads / 2) : "memory");
-        uint8_t* orow = stage + (m & 63) * 256;
+    };
+    // epilogue 3: kernels[l][e][o][c] = X[l&1] (fp16), channels cgi*32 .. +31.  The layer's output tile is 32 KB
+    // contiguous in HBM: it is staged in shared memory and written by the TMA engine with bulk stores (scattered
+    // 32-byte stores from 512 threads would monopolise the LSU).  Rows are 256 B; the 16-byte chunk k of row (e, o)
+    // is stored at chunk position k ^ o (the fp16 kernels layout, undone by the message kernel's loads), which
+    // makes these 16-byte shared stores conflict free.  The two 16 KB halves (rows 0..63 / 64..127) are staged,
+    // stored and recycled independently by the 8 warps owning those rows.
+    auto epi3 = [&](int l, long long tile, uint32_t it) {
+      const int b = l & 1;
+      const uint32_t use_par = b ? (uint32_t)(l >> 1) & 1u : (it + (uint32_t)(l >> 1)) & 1u;
+      mbar_wait(&bars.x_full[b], use_par);
+      tc_fence_after();
+      float v[32];
+      tmem_ld32(tmem + b * 384 + lane_addr + cgi * 32, v);
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&bars.x_empty[b]);       // accumulators are in registers: release the buffer
+#ifdef ARREAU_EDGE_DIRECT_STORE
+      if (tile * kEdgesPerTile + (m >> 4) < E) {
+        // 64 contiguous bytes per thread as two full 32-byte sectors, 16-byte chunks at positions k ^ o
+        __half* out = kernels + ((size_t)l * edge_capacity * kO + (size_t)tile * kTileM + m) * kC;
+        const int o = m & 15, grp = (cgi ^ (o >> 2)) * 4, r = o & 3;
+        uint4 pk[4];
 #pragma unroll
         for (int cc = 0; cc < 4; ++cc) {
-          uint4 pk;
-          pk.x = pack_f16(v[cc * 8 + 0], v[cc * 8 + 1]);
-          pk.y = pack_f16(v[cc * 8 + 2], v[cc * 8 + 3]);
-          pk.z = pack_f16(v[cc * 8 + 4], v[cc * 8 + 5]);
-          pk.w = pack_f16(v[cc * 8 + 6], v[cc * 8 + 7]);
-          *reinterpret_cast<uint4*>(orow + (((cgi * 4 + cc) ^ (m & 15)) << 4)) = pk;
+          pk[cc].x = pack_f16(v[cc * 8 + 0], v[cc * 8 + 1]);
+          pk[cc].y = pack_f16(v[cc * 8 + 2], v[cc * 8 + 3]);
+          pk[cc].z = pack_f16(v[cc * 8 + 4], v[cc * 8 + 5]);
+          pk[cc].w = pack_f16(v[cc * 8 + 6], v[cc * 8 + 7]);
         }
-        fence_proxy_async();
-        asm volatile("bar.sync %0, %1;" ::"r"(1 + hf), "n"(kEpiThreads / 2) : "memory");
-        if (is_issuer) {
-          const long long left = E - tile * kEdgesPerTile - hf * (kEdgesPerTile / 2);   // edges of this half still valid
-          if (left > 0) {
-            const uint32_t bytes = (uint32_t)(left < kEdgesPerTile / 2 ? left : kEdgesPerTile / 2) * (kO * kC * 2);
-            __half* out = kernels + ((size_t)l * edge_capacity * kO + (size_t)tile * kTileM + hf * 64) * kC;
-            asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(out), "r"(smem_u32(stage)), "r"(bytes)
-                         : "memory");
-          }
-          asm volatile("cp.async.bulk.commit_group;" ::: "memory");
-        }
-        TC_STAMP(6 + l);
+        // position p of the group holds logical chunk p ^ r
+        uint4 q0 = pk[0 ^ 0], q1 = pk[1], q2 = pk[2], q3 = pk[3];
+        if (r & 1) { uint4 t = q0; q0 = q1; q1 = t; t = q2; q2 = q3; q3 = t; }
+        if (r & 2) { uint4 t = q0; q0 = q2; q2 = t; t = q1; q1 = q3; q3 = t; }
+        uint32_t lo8[8] = {q0.x, q0.y, q0.z, q0.w, q1.x, q1.y, q1.z, q1.w};
+        uint32_t hi8[8] = {q2.x, q2.y, q2.z, q2.w, q3.x, q3.y, q3.z, q3.w};
+        stg256_b32(out + grp * 8, lo8);
+        stg256_b32(out + grp * 8 + 16, hi8);
       }
+      return;
+#endif
+      uint8_t* stage = S + hf * 16384;
+      if (is_issuer) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");   // this half's previous store has left smem
+      asm volatile("bar.sync %0, %1;" ::"r"(1 + hf), "n"(kEpiThreads / 2) : "memory");
+      uint8_t* orow = stage + (m & 63) * 256;
+#pragma unroll
+      for (int cc = 0; cc < 4; ++cc) {
+        uint4 pk;
+        pk.x = pack_f16(v[cc * 8 + 0], v[cc * 8 + 1]);
+        pk.y = pack_f16(v[cc * 8 + 2], v[cc * 8 + 3]);
+        pk.z = pack_f16(v[cc * 8 + 4], v[cc * 8 + 5]);
+        pk.w = pack_f16(v[cc * 8 + 6], v[cc * 8 + 7]);
+        *reinterpret_cast<uint4*>(orow + (((cgi * 4 + cc) ^ (m & 15)) << 4)) = pk;
+      }
+      fence_proxy_async();
+      asm volatile("bar.sync %0, %1;" ::"r"(1 + hf), "n"(kEpiThreads / 2) : "memory");
+      if (is_issuer) {
+        const long long left = E - tile * kEdgesPerTile - hf * (kEdgesPerTile / 2);   // edges of this half still valid
+        if (left > 0) {
+          const uint32_t bytes = (uint32_t)(left < kEdgesPerTile / 2 ? left : kEdgesPerTile / 2) * (kO * kC * 2);
+          __half* out = kernels + ((size_t)l * edge_capacity * kO + (size_t)tile * kTileM + hf * 64) * kC;
+          asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(out), "r"(smem_u32(stage)), "r"(bytes)
+                       : "memory");
+        }
+        asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+      }
+    };
+    if (first < tiles) {
+      gen(0);
+      epi1(0);
+      epi2(0);
+      uint32_t it = 0;
+      long long* prof = (blockIdx.x == 0 && threadIdx.x == kEpiWarp0 * 32) ? g_tc_prof : nullptr;
+      constexpr int prof_role = 1;
+      for (long long tile = first; tile < tiles; tile += stride, ++it) {
+        const bool has_next = tile + stride < tiles;
+        TC_STAMP(0);
+        if (has_next) gen(it + 1);                 // A2 is free: GEMM2 of this tile completed before d2_full fired
+        TC_STAMP(1);
+        TC_STAMP(2);
+        epi3(0, tile, it);
+        TC_STAMP(3);
+        epi3(1, tile, it);
+        TC_STAMP(4);
+        if (has_next) epi1(it + 1);
+        TC_STAMP(5);
+        epi3(2, tile, it);
+        TC_STAMP(6);
+        epi3(3, tile, it);
+        TC_STAMP(7);
+        epi3(4, tile, it);                         // its x_full also says GEMM3 has finished reading A3
+        TC_STAMP(8);
+        if (has_next) epi2(it + 1);
+        TC_STAMP(9);
+      }
+      if (is_issuer) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");   // all output tiles have landed
     }
-    if (is_issuer) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");   // all output tiles have landed
   }
   tc_fence_before();
   __syncthreads();

@@ -113,6 +113,133 @@ __device__ __forceinline__ void umma_f16(uint32_t tmem_d, uint64_t adesc, uint64
       ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
       : "memory");
 }
+// The single MMA-issuing thread is instruction bound (a 128x128x16 MMA retires every 64 cycles): keep the
+// descriptors as precomputed 32-bit halves.  The low word carries the start address (>> 4, 14 bits) and the
+// leading byte offset; stepping K by 16 fp16 (32 B) adds 2 to it and never carries into the high word.
+constexpr uint32_t kDescHiSw128 = (uint32_t)(1024 >> 4) | (1u << 14) | (2u << 29);
+__device__ __forceinline__ uint32_t umma_desc_lo(uint32_t addr) { return ((addr & 0x3FFFFu) >> 4) | (1u << 16); }
+template <bool kAccumulate>
+__device__ __forceinline__ void umma_f16_lo(uint32_t tmem_d, uint32_t a_lo, uint32_t b_lo, uint32_t idesc) {
+  if constexpr (kAccumulate)
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t.reg .b64 da, db;\n\t"
+        "mov.b64 da, {%1, %4};\n\tmov.b64 db, {%2, %4};\n\t"
+        "setp.eq.u32 p, 0, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], da, db, %3, p;\n\t}"
+        ::"r"(tmem_d), "r"(a_lo), "r"(b_lo), "r"(idesc), "r"(kDescHiSw128)
+        : "memory");
+  else
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t.reg .b64 da, db;\n\t"
+        "mov.b64 da, {%1, %4};\n\tmov.b64 db, {%2, %4};\n\t"
+        "setp.ne.u32 p, 0, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], da, db, %3, p;\n\t}"
+        ::"r"(tmem_d), "r"(a_lo), "r"(b_lo), "r"(idesc), "r"(kDescHiSw128)
+        : "memory");
+}
+// runtime accumulate flag (first K step of a GEMM)
+__device__ __forceinline__ void umma_f16_lo_p(uint32_t tmem_d, uint32_t a_lo, uint32_t b_lo, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t.reg .b64 da, db;\n\t"
+      "mov.b64 da, {%1, %4};\n\tmov.b64 db, {%2, %4};\n\t"
+      "setp.ne.u32 p, %5, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], da, db, %3, p;\n\t}"
+      ::"r"(tmem_d), "r"(a_lo), "r"(b_lo), "r"(idesc), "r"(kDescHiSw128), "r"(accumulate)
+      : "memory");
+}
+// the KSTEPS (<= 4) UMMA_K = 16 steps of one 64-wide K slab; kFirst: the first step overwrites the accumulator
+template <int KSTEPS, bool kFirst>
+__device__ __forceinline__ void umma_slab_lo(uint32_t tmem_d, uint32_t a_lo, uint32_t b_lo, uint32_t idesc) {
+  if constexpr (kFirst) umma_f16_lo<false>(tmem_d, a_lo, b_lo, idesc);
+  else umma_f16_lo<true>(tmem_d, a_lo, b_lo, idesc);
+#pragma unroll
+  for (int k = 1; k < KSTEPS; ++k) umma_f16_lo<true>(tmem_d, a_lo + 2 * k, b_lo + 2 * k, idesc);
+}
+__device__ __forceinline__ void mbar_wait_addr(uint32_t addr, uint32_t parity) {
+  uint32_t done;
+  do {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(done)
+        : "r"(addr), "r"(parity)
+        : "memory");
+  } while (!done);
+}
+// Warp-uniform MMA issue: the whole warp runs the issue loop (so that descriptors and addresses live in uniform
+// registers -- a single divergent thread pays an R2UR round trip per operand, ~50 cycles per MMA) and one elected
+// lane issues.  Measured (scratch/ubench/mma_ring.cu): 64 cycles per 128x128x16 MMA = the tensor-pipe floor with one
+// barrier round per 8 MMAs, against 121 for single-thread issue with a round per 4.
+__device__ __forceinline__ uint32_t elect_one() {
+  uint32_t pred;
+  asm volatile("{\n\t.reg .pred p;\n\telect.sync _|p, 0xffffffff;\n\tselp.u32 %0, 1, 0, p;\n\t}" : "=r"(pred));
+  return pred;
+}
+__device__ __forceinline__ void umma_f16_e(uint32_t tmem_d, uint32_t a_lo, uint32_t b_lo, uint32_t idesc, uint32_t elected,
+                                           uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p, e;\n\t.reg .b64 da, db;\n\t"
+      "mov.b64 da, {%1, %4};\n\tmov.b64 db, {%2, %4};\n\t"
+      "setp.ne.u32 e, %5, 0;\n\t"
+      "setp.ne.u32 p, %6, 0;\n\t"
+      "@e tcgen05.mma.cta_group::1.kind::f16 [%0], da, db, %3, p;\n\t}"
+      ::"r"(tmem_d), "r"(a_lo), "r"(b_lo), "r"(idesc), "r"(kDescHiSw128), "r"(elected), "r"(accumulate)
+      : "memory");
+}
+// KSTEPS (2 or 4) UMMA_K = 16 steps of one 64-wide K slab
+template <int KSTEPS>
+__device__ __forceinline__ void umma_slab_e(uint32_t tmem_d, uint32_t a_lo, uint32_t b_lo, uint32_t idesc, uint32_t elected,
+                                            uint32_t accumulate_first) {
+  umma_f16_e(tmem_d, a_lo, b_lo, idesc, elected, accumulate_first);
+#pragma unroll
+  for (int k = 1; k < KSTEPS; ++k) umma_f16_e(tmem_d, a_lo + 2 * k, b_lo + 2 * k, idesc, elected, 1u);
+}
+__device__ __forceinline__ void umma_commit_e(uint32_t bar_addr, uint32_t elected) {
+  asm volatile(
+      "{\n\t.reg .pred e;\n\tsetp.ne.u32 e, %1, 0;\n\t"
+      "@e tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];\n\t}" ::"r"(bar_addr), "r"(elected)
+      : "memory");
+}
+
+// wait for two / four barriers at once: the try_waits are issued back to back so that their latencies overlap
+// (the MMA-issuing thread has no slack: the tensor pipe's issue queue is shallow, any gap between two
+// tcgen05.mma shows up as idle tensor cycles)
+__device__ __forceinline__ void mbar_wait4_addr(uint32_t a0, uint32_t p0, uint32_t a1, uint32_t p1, uint32_t a2, uint32_t p2,
+                                                uint32_t a3, uint32_t p3) {
+  uint32_t done;
+  do {
+    asm volatile(
+        "{\n\t.reg .pred q0, q1, q2, q3;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 q0, [%1], %2;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 q1, [%3], %4;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 q2, [%5], %6;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 q3, [%7], %8;\n\t"
+        "and.pred q0, q0, q1;\n\tand.pred q2, q2, q3;\n\tand.pred q0, q0, q2;\n\t"
+        "selp.u32 %0, 1, 0, q0;\n\t}"
+        : "=r"(done)
+        : "r"(a0), "r"(p0), "r"(a1), "r"(p1), "r"(a2), "r"(p2), "r"(a3), "r"(p3)
+        : "memory");
+  } while (!done);
+}
+__device__ __forceinline__ void mbar_wait2_addr(uint32_t a0, uint32_t p0, uint32_t a1, uint32_t p1) {
+  uint32_t done;
+  do {
+    asm volatile(
+        "{\n\t.reg .pred q0, q1;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 q0, [%1], %2;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 q1, [%3], %4;\n\t"
+        "and.pred q0, q0, q1;\n\t"
+        "selp.u32 %0, 1, 0, q0;\n\t}"
+        : "=r"(done)
+        : "r"(a0), "r"(p0), "r"(a1), "r"(p1)
+        : "memory");
+  } while (!done);
+}
+__device__ __forceinline__ void umma_commit_addr(uint32_t bar_addr) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar_addr) : "memory");
+}
+
 // arrive on an mbarrier when every tcgen05 operation issued so far by this thread has completed
 __device__ __forceinline__ void umma_commit(uint64_t* bar) {
   asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar))
@@ -153,6 +280,12 @@ __device__ __forceinline__ void ldg256(const float* p, float (&v)[8]) {
 __device__ __forceinline__ void stg256(float* p, const float (&v)[8]) {
   asm volatile("st.global.v8.f32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8};" ::"l"(p), "f"(v[0]), "f"(v[1]), "f"(v[2]), "f"(v[3]),
                "f"(v[4]), "f"(v[5]), "f"(v[6]), "f"(v[7])
+               : "memory");
+}
+
+__device__ __forceinline__ void stg256_b32(void* p, const uint32_t* v) {
+  asm volatile("st.global.v8.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8};" ::"l"(p), "r"(v[0]), "r"(v[1]), "r"(v[2]), "r"(v[3]),
+               "r"(v[4]), "r"(v[5]), "r"(v[6]), "r"(v[7])
                : "memory");
 }
 
