@@ -120,7 +120,7 @@ convnext_mlp_tc_kernel(const uint8_t* __restrict__ y_img, const uint8_t* __restr
   Bars& bars = *reinterpret_cast<Bars*>(smem + kTilesBytes + kW * sizeof(float));
   uint32_t& tmem_base_s = *reinterpret_cast<uint32_t*>(smem + kTilesBytes + kW * sizeof(float) + sizeof(Bars));
   if ((base - smem_u32(smem_raw)) + kTilesBytes + kW * sizeof(float) + sizeof(Bars) + 16 > (uint32_t)kSmemBytes) __trap();
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0), lane = threadIdx.x & 31;   // warp-uniform
   const long long tiles = (rows + kTileM - 1) / kTileM;
 
   for (int i = threadIdx.x; i < kW; i += kThreads) s_b1[i] = b1[i];
@@ -156,11 +156,16 @@ convnext_mlp_tc_kernel(const uint8_t* __restrict__ y_img, const uint8_t* __restr
         bulk_g2s(W + ws * kTileBytes, w_img + (size_t)c * kTileBytes, kTileBytes, &bars.w_full[ws]);
       }
     }
-  } else if (warp == 1 && lane == 0) {
-    // ---------------- MMA issuer ----------------
-    uint32_t chunk = 0;
+  } else if (warp == 1) {
+    // ---------------- MMA issuer: the whole warp runs the loop uniformly, one elected lane issues
+    // (see tc_common.cuh: a divergent single thread pays ~50 cycles per MMA for operand moves) ----------------
+    const uint32_t el = elect_one();
+    const uint32_t a_lo0 = umma_desc_lo(smem_u32(A0)), h_lo0 = umma_desc_lo(smem_u32(H0)), w_lo0 = umma_desc_lo(smem_u32(W));
+    const uint32_t wfull = smem_u32(&bars.w_full[0]), wempty = smem_u32(&bars.w_empty[0]);
+    constexpr uint32_t kSlabLo = 16384 >> 4, kTileLo = kTileBytes >> 4;
+    uint32_t ws = 0, wpar = 0;
     int it = 0;
-    long long* prof = blockIdx.x == 0 ? g_tc_prof : nullptr;
+    long long* prof = (blockIdx.x == 0 && el) ? g_tc_prof : nullptr;
     constexpr int prof_role = 0;
     for (long long tile = blockIdx.x; tile < tiles; tile += gridDim.x, ++it) {
       const int ab = it & 1;
@@ -168,45 +173,36 @@ convnext_mlp_tc_kernel(const uint8_t* __restrict__ y_img, const uint8_t* __restr
       mbar_wait(&bars.a_full[ab], (it >> 1) & 1);
       tc_fence_after();
       TC_STAMP(1);
-      const uint32_t a_addr = smem_u32(A0 + ab * kTileBytes);
-      auto wait_w = [&]() -> uint32_t {
-        const int ws = chunk % kWStages;
-        mbar_wait(&bars.w_full[ws], (chunk / kWStages) & 1);
-        tc_fence_after();
-        return smem_u32(W + ws * kTileBytes);
-      };
-      auto release_w = [&]() {
-        umma_commit(&bars.w_empty[chunk % kWStages]);
-        ++chunk;
+      const uint32_t a_lo = a_lo0 + ab * kTileLo;
+      // one 32 KB weight tile (two K slabs): D (+)= X[:, 0:64] . W[0]^T + X[:, 64:128] . W[1]^T, then release it
+      auto mma_tile = [&](uint32_t d, uint32_t x_lo, uint32_t accumulate) {
+        const uint32_t w_lo = w_lo0 + ws * kTileLo;
+        umma_slab_e<4>(d, x_lo, w_lo, kIdesc128, el, accumulate);
+        umma_slab_e<4>(d, x_lo + kSlabLo, w_lo + kSlabLo, kIdesc128, el, 1u);
+        umma_commit_e(wempty + 8 * ws, el);
+        if (++ws == (uint32_t)kWStages) { ws = 0; wpar ^= 1; }
       };
       auto gemm1 = [&](int j) {        // D1[j&1] = y_tile . W1_j^T
         const int b = j & 1;
         const uint32_t use = (uint32_t)it * 2 + (j >> 1);
-        const uint32_t w_addr = wait_w();
+        mbar_wait_addr(wfull + 8 * ws, wpar);
         mbar_wait(&bars.d1_empty[b], (use & 1) ^ 1);
         tc_fence_after();
-        const uint32_t d = tmem + b * 128;
-        mma_slab(d, a_addr, w_addr, 4, false);
-        mma_slab(d, a_addr + 16384, w_addr + 16384, 4, true);
-        release_w();
-        umma_commit(&bars.d1_full[b]);
-        if (j == 3) umma_commit(&bars.a_empty[ab]);
+        mma_tile(tmem + b * 128, a_lo, 0u);
+        umma_commit_e(smem_u32(&bars.d1_full[b]), el);
+        if (j == 3) umma_commit_e(smem_u32(&bars.a_empty[ab]), el);
         TC_STAMP(2 + j);
       };
       auto gemm2 = [&](int j) {        // D2 (+)= H[j&1] . W2_j^T
         const int b = j & 1;
         const uint32_t use = (uint32_t)it * 2 + (j >> 1);
-        const uint32_t w_addr = wait_w();
+        mbar_wait_addr(wfull + 8 * ws, wpar);
         mbar_wait(&bars.h_full[b], use & 1);
         if (j == 0) mbar_wait(&bars.d2_empty, (it & 1) ^ 1);
         tc_fence_after();
-        const uint32_t d = tmem + 256;
-        const uint32_t h_addr = smem_u32(H0 + b * kTileBytes);
-        mma_slab(d, h_addr, w_addr, 4, j > 0);
-        mma_slab(d, h_addr + 16384, w_addr + 16384, 4, true);
-        release_w();
-        umma_commit(&bars.h_empty[b]);
-        if (j == 3) umma_commit(&bars.d2_full);
+        mma_tile(tmem + 256, h_lo0 + b * kTileLo, j > 0 ? 1u : 0u);
+        umma_commit_e(smem_u32(&bars.h_empty[b]), el);
+        if (j == 3) umma_commit_e(smem_u32(&bars.d2_full), el);
         TC_STAMP(6 + j);
       };
       gemm1(0); gemm1(1); gemm2(0); gemm1(2); gemm2(1); gemm1(3); gemm2(2); gemm2(3);
