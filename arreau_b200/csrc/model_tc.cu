@@ -76,6 +76,21 @@ __device__ __forceinline__ void gelu_store32(const float (&v)[32], const float* 
   }
 }
 
+// 32 accumulator columns -> + bias -> GELU * scale -> 16 packed fp16 registers
+__device__ __forceinline__ void gelu_scaled_pack32(const float (&v)[32], const float* __restrict__ bias_s, float scale,
+                                                   uint32_t (&pk)[16]) {
+  const __half2 sc = __float2half2_rn(scale);
+#pragma unroll
+  for (int cc = 0; cc < 4; ++cc) {
+    const float4 b0 = *reinterpret_cast<const float4*>(bias_s + cc * 8);
+    const float4 b1 = *reinterpret_cast<const float4*>(bias_s + cc * 8 + 4);
+    pk[cc * 4 + 0] = gelu2_scaled_f16(v[cc * 8 + 0] + b0.x, v[cc * 8 + 1] + b0.y, sc);
+    pk[cc * 4 + 1] = gelu2_scaled_f16(v[cc * 8 + 2] + b0.z, v[cc * 8 + 3] + b0.w, sc);
+    pk[cc * 4 + 2] = gelu2_scaled_f16(v[cc * 8 + 4] + b1.x, v[cc * 8 + 5] + b1.y, sc);
+    pk[cc * 4 + 3] = gelu2_scaled_f16(v[cc * 8 + 6] + b1.z, v[cc * 8 + 7] + b1.w, sc);
+  }
+}
+
 // 32 accumulator columns -> + bias -> GELU -> four packed fp16 chunks (registers only)
 __device__ __forceinline__ void gelu_pack32(const float (&v)[32], const float* __restrict__ bias_s, uint4 (&pk)[4]) {
 #pragma unroll
@@ -632,8 +647,12 @@ edge_kernels_tc_kernel(const double* __restrict__ dir, const double* __restrict_
       __syncwarp();
       if (lane == 0) mbar_arrive(&bars.a2_full);
     };
-    // epilogue 2: kernel basis = GELU(D2 + b2) * window -> A3; this warp: columns cgi*64 .. +63 = slab cgi
-    auto epi2 = [&](uint32_t k) {
+    // epilogue 2: kernel basis = GELU(D2 + b2) * window -> A3; this warp: columns cgi*64 .. +63 = slab cgi.
+    // A3 is still being read by GEMM3 of the current tile when D2 of the next tile is ready, and the 64 GELUs per
+    // thread are the longest stretch of the epilogue: so the math runs early (epi2_compute) and parks the packed
+    // fp16 rows in the accumulator buffer X1, which is idle between layers 3 and 1; once GEMM3 has finished only
+    // a TMEM -> shared copy (epi2_store) stands between two GEMM3 phases.  The first tile writes A3 directly.
+    auto epi2_direct = [&](uint32_t k) {
       mbar_wait(&bars.d2_full, k & 1);
       tc_fence_after();
 #pragma unroll
@@ -648,13 +667,43 @@ edge_kernels_tc_kernel(const double* __restrict__ dir, const double* __restrict_
       __syncwarp();
       if (lane == 0) mbar_arrive(&bars.a3_full);
     };
+    auto epi2_compute = [&](uint32_t k) {          // needs: D2 of tile k complete, X1 drained (layer 3 read out)
+      mbar_wait(&bars.d2_full, k & 1);
+      tc_fence_after();
+#pragma unroll
+      for (int g = 0; g < 2; ++g) {
+        const int col0 = cgi * 64 + g * 32;
+        float v[32];
+        tmem_ld32(tmem + 128 + lane_addr + col0, v);
+        uint32_t pk[16];
+        gelu_scaled_pack32(v, s_b2 + col0, win_cur, pk);
+        tmem_st16(tmem + 384 + lane_addr + cgi * 32 + g * 16, pk);
+      }
+      tmem_wait_st();
+    };
+    auto epi2_store = [&]() {                      // needs: GEMM3 of the current tile complete (A3 free)
+#pragma unroll
+      for (int g = 0; g < 2; ++g) {
+        uint32_t pk[16];
+        tmem_ld16(tmem + 384 + lane_addr + cgi * 32 + g * 16, pk);
+        uint8_t* row = A3 + cgi * 16384 + m * kRowBytes;
+#pragma unroll
+        for (int cc = 0; cc < 4; ++cc)
+          *reinterpret_cast<uint4*>(row + (((g * 4 + cc) ^ (m & 7)) << 4)) =
+              make_uint4(pk[cc * 4], pk[cc * 4 + 1], pk[cc * 4 + 2], pk[cc * 4 + 3]);
+      }
+      tc_fence_before();
+      fence_proxy_async();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&bars.a3_full);
+    };
     // epilogue 3: kernels[l][e][o][c] = X[l&1] (fp16), channels cgi*32 .. +31.  The layer's output tile is 32 KB
     // contiguous in HBM: it is staged in shared memory and written by the TMA engine with bulk stores (scattered
     // 32-byte stores from 512 threads would monopolise the LSU).  Rows are 256 B; the 16-byte chunk k of row (e, o)
     // is stored at chunk position k ^ o (the fp16 kernels layout, undone by the message kernel's loads), which
     // makes these 16-byte shared stores conflict free.  The two 16 KB halves (rows 0..63 / 64..127) are staged,
     // stored and recycled independently by the 8 warps owning those rows.
-    auto epi3 = [&](int l, long long tile, uint32_t it) {
+    auto epi3 = [&](int l, long long tile, uint32_t it, bool store_next_a3) {
       const int b = l & 1;
       const uint32_t use_par = b ? (uint32_t)(l >> 1) & 1u : (it + (uint32_t)(l >> 1)) & 1u;
       mbar_wait(&bars.x_full[b], use_par);
@@ -664,30 +713,14 @@ edge_kernels_tc_kernel(const double* __restrict__ dir, const double* __restrict_
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(&bars.x_empty[b]);       // accumulators are in registers: release the buffer
-#ifdef ARREAU_EDGE_DIRECT_STORE
-      if (tile * kEdgesPerTile + (m >> 4) < E) {
-        // 64 contiguous bytes per thread as two full 32-byte sectors, 16-byte chunks at positions k ^ o
-        __half* out = kernels + ((size_t)l * edge_capacity * kO + (size_t)tile * kTileM + m) * kC;
-        const int o = m & 15, grp = (cgi ^ (o >> 2)) * 4, r = o & 3;
-        uint4 pk[4];
-#pragma unroll
-        for (int cc = 0; cc < 4; ++cc) {
-          pk[cc].x = pack_f16(v[cc * 8 + 0], v[cc * 8 + 1]);
-          pk[cc].y = pack_f16(v[cc * 8 + 2], v[cc * 8 + 3]);
-          pk[cc].z = pack_f16(v[cc * 8 + 4], v[cc * 8 + 5]);
-          pk[cc].w = pack_f16(v[cc * 8 + 6], v[cc * 8 + 7]);
-        }
-        // position p of the group holds logical chunk p ^ r
-        uint4 q0 = pk[0 ^ 0], q1 = pk[1], q2 = pk[2], q3 = pk[3];
-        if (r & 1) { uint4 t = q0; q0 = q1; q1 = t; t = q2; q2 = q3; q3 = t; }
-        if (r & 2) { uint4 t = q0; q0 = q2; q2 = t; t = q1; q1 = q3; q3 = t; }
-        uint32_t lo8[8] = {q0.x, q0.y, q0.z, q0.w, q1.x, q1.y, q1.z, q1.w};
-        uint32_t hi8[8] = {q2.x, q2.y, q2.z, q2.w, q3.x, q3.y, q3.z, q3.w};
-        stg256_b32(out + grp * 8, lo8);
-        stg256_b32(out + grp * 8 + 16, hi8);
-      }
-      return;
-#endif
+      if (store_next_a3) epi2_store();                    // layer 4: GEMM3 is done with A3 -> next tile's kernel basis
+      // The layer's output tile is 32 KB contiguous in HBM: it is staged in shared memory and written by the TMA
+      // engine with bulk stores.  (Measured alternatives: scattered 32-byte stores straight from registers 2.94 ms,
+      // coalesced 16-byte stores from the staging buffer 2.49 ms, bulk stores 2.39 ms; without any output store the
+      // kernel takes 1.75 ms -- a per-SM write path of ~32 B/clk has to carry 160 KB per tile.)  Rows are 256 B; the
+      // 16-byte chunk k of row (e, o) is staged at chunk position k ^ o -- conflict-free shared stores -- and that
+      // is also the fp16 kernels layout in HBM (undone by the message kernel's loads).  The two 16 KB halves
+      // (rows 0..63 / 64..127) are staged, stored and recycled independently by the 8 warps owning those rows.
       uint8_t* stage = S + hf * 16384;
       if (is_issuer) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");   // this half's previous store has left smem
       asm volatile("bar.sync %0, %1;" ::"r"(1 + hf), "n"(kEpiThreads / 2) : "memory");
@@ -717,7 +750,7 @@ edge_kernels_tc_kernel(const double* __restrict__ dir, const double* __restrict_
     if (first < tiles) {
       gen(0);
       epi1(0);
-      epi2(0);
+      epi2_direct(0);
       uint32_t it = 0;
       long long* prof = (blockIdx.x == 0 && threadIdx.x == kEpiWarp0 * 32) ? g_tc_prof : nullptr;
       constexpr int prof_role = 1;
@@ -727,19 +760,19 @@ edge_kernels_tc_kernel(const double* __restrict__ dir, const double* __restrict_
         if (has_next) gen(it + 1);                 // A2 is free: GEMM2 of this tile completed before d2_full fired
         TC_STAMP(1);
         TC_STAMP(2);
-        epi3(0, tile, it);
+        epi3(0, tile, it, false);
         TC_STAMP(3);
-        epi3(1, tile, it);
+        epi3(1, tile, it, false);
         TC_STAMP(4);
         if (has_next) epi1(it + 1);
         TC_STAMP(5);
-        epi3(2, tile, it);
+        epi3(2, tile, it, false);
         TC_STAMP(6);
-        epi3(3, tile, it);
+        epi3(3, tile, it, false);                  // X1 is drained: it can hold the next tile's packed kernel basis
         TC_STAMP(7);
-        epi3(4, tile, it);                         // its x_full also says GEMM3 has finished reading A3
+        if (has_next) epi2_compute(it + 1);
         TC_STAMP(8);
-        if (has_next) epi2(it + 1);
+        epi3(4, tile, it, has_next);               // its x_full also says GEMM3 has finished reading A3
         TC_STAMP(9);
       }
       if (is_issuer) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");   // all output tiles have landed
