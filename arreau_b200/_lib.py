@@ -25,7 +25,7 @@ PRECISION_FP32, PRECISION_FP16 = 0, 1
 
 class Weights(C.Structure):
     _fields_ = [(n, vp) for n in (
-        "ori", "w_embed_t", "w1m_t", "w2_t", "b2", "wk_t", "fiber_kernel", "conv_bias", "ln_w", "ln_b",
+        "ori", "w_embed_t", "w1m_t", "w2_t", "b2", "wk_t", "fiber_kernel", "fiber_frag", "conv_bias", "ln_w", "ln_b",
         "mlp_w1_t", "mlp_b1", "mlp_w2_t", "mlp_b2", "layer_scale", "wr_t", "br",
         "edge_w1_img", "edge_w_img", "mlp_w_img")] + [
         ("num_scalar", i32), ("num_vec", i32), ("num_states", i32), ("reserved", i32)]
@@ -33,7 +33,7 @@ class Weights(C.Structure):
 
 class Workspace(C.Structure):
     _fields_ = [("h", vp), ("y", vp), ("kernels", vp), ("acc", vp), ("x1", vp), ("x1_debug", vp), ("x2_debug", vp),
-                ("h_debug", vp), ("edge_capacity", i64)]
+                ("h_debug", vp), ("edge_capacity", i64), ("onehot_types", vp)]
 
 
 class StepArgs(C.Structure):
@@ -72,9 +72,11 @@ SIGNATURES = {
     "arreau_assemble_features": [vp, vp, vp, vp, vp, vp, vp, vp, i32, vp, vp, i32, i32, i32, i32, vp, vp, vp],
     "arreau_fiber_kernel_precompute": [vp] * 8,
     "arreau_node_embed": [vp, vp, vp, vp, i32, i32, i32, vp, vp],
+    "arreau_node_embed_typed": [vp, vp, i32, vp, vp, vp, i32, i32, i32, vp, vp],
     "arreau_edge_kernels_f32": [vp, vp, vp, vp, vp, vp, i64, vp, vp, vp, vp, vp, f64, vp, vp],
     "arreau_edge_kernels_f16": [vp, vp, vp, vp, vp, vp, i64, vp, vp, vp, vp, f64, vp, vp],
-    "arreau_message_fiber_norm": [vp, i32, vp, vp, vp, vp, vp, vp, vp, i32, vp, i32, vp, vp, vp],
+    "arreau_message_fiber_norm": [vp, i32, vp, vp, vp, vp, vp, vp, vp, vp, i32, vp, i32, vp, vp, vp],
+    "arreau_fiber_frag_pack": [vp, i32, vp, vp],
     "arreau_convnext_mlp_f32": [vp, vp, vp, vp, vp, vp, i64, vp, vp],
     "arreau_convnext_mlp_f16": [vp, vp, vp, vp, vp, i64, vp, vp],
     "arreau_readout_accumulate": [vp, vp, vp, vp, i32, i32, i32, vp, vp],

@@ -13,6 +13,7 @@
 #include <cuda_fp16.h>
 
 #include "common.cuh"
+#include "tc_common.cuh"
 
 namespace {
 
@@ -95,42 +96,55 @@ __device__ __forceinline__ float acc_get(const float2 (&acc)[8][4], int i, int j
 constexpr int kEmbedNodes = 8;
 constexpr int kMaxVec = 8;
 
-__global__ void __launch_bounds__(kC)
+// thread = (atom a of the CTA's 8, 4 channels): s = sum_f x[b,f] W[f, 4 cg..] once per atom, then the 16 orientations
+// only add the vector part (linearity) and store 16 bytes.  `types` (optional): the first Z features are a one-hot of
+// types[b] (diffusion_loss.py:140-150) -> one row lookup instead of Z multiply-adds with zeros.
+__global__ void __launch_bounds__(kEmbedNodes * 32)
 node_embed_kernel(const float* __restrict__ x, const float* __restrict__ vec, const float* __restrict__ w_t,
-                  const float* __restrict__ ori, int N, int F, int V, float* __restrict__ h) {
+                  const float* __restrict__ ori, const int64_t* __restrict__ types, int Z, int N, int F, int V,
+                  float* __restrict__ h) {
   extern __shared__ float sm[];
   float* xs = sm;                                   // [kEmbedNodes][F]
   float* dots = sm + kEmbedNodes * F;               // [kEmbedNodes][V][kO]
-  const int c = threadIdx.x;
+  const int tid = threadIdx.x, a = tid >> 5, lane = tid & 31;
   const int b0 = blockIdx.x * kEmbedNodes;
   const int nb = min(kEmbedNodes, N - b0);
-  for (int idx = c; idx < nb * F; idx += kC) xs[idx] = x[(size_t)b0 * F + idx];
-  for (int idx = c; idx < nb * V * kO; idx += kC) {
+  for (int idx = tid; idx < nb * F; idx += kEmbedNodes * 32) xs[idx] = x[(size_t)b0 * F + idx];
+  for (int idx = tid; idx < nb * V * kO; idx += kEmbedNodes * 32) {
     const int o = idx % kO, v = (idx / kO) % V, b = idx / (kO * V);
     const float* p = vec + ((size_t)(b0 + b) * V + v) * 3;
     dots[idx] = p[0] * ori[3 * o] + p[1] * ori[3 * o + 1] + p[2] * ori[3 * o + 2];   // to_from_sphere.py:7-8
   }
   __syncthreads();
-  float s[kEmbedNodes];
-#pragma unroll
-  for (int b = 0; b < kEmbedNodes; ++b) s[b] = 0.f;
-  for (int f = 0; f < F; ++f) {
-    const float w = w_t[(size_t)f * kC + c];
-#pragma unroll
-    for (int b = 0; b < kEmbedNodes; ++b) s[b] = fmaf(xs[b * F + f], w, s[b]);   // rows >= nb read stale smem, unused
+  if (a >= nb) return;
+  const float* xr = xs + a * F;
+  float4 s = make_float4(0.f, 0.f, 0.f, 0.f);
+  int f0 = 0;
+  if (types) {
+    s = __ldg(reinterpret_cast<const float4*>(w_t + (size_t)types[b0 + a] * kC + lane * 4));
+    f0 = Z;
   }
-  float wv[kMaxVec];
+#pragma unroll 4
+  for (int f = f0; f < F; ++f) {
+    const float4 w = __ldg(reinterpret_cast<const float4*>(w_t + (size_t)f * kC + lane * 4));
+    const float xv = xr[f];
+    s.x = fmaf(xv, w.x, s.x); s.y = fmaf(xv, w.y, s.y); s.z = fmaf(xv, w.z, s.z); s.w = fmaf(xv, w.w, s.w);
+  }
+  float4 wv[kMaxVec];
 #pragma unroll
-  for (int v = 0; v < kMaxVec; ++v) wv[v] = v < V ? w_t[(size_t)(F + v) * kC + c] : 0.f;
-  for (int b = 0; b < nb; ++b) {
+  for (int v = 0; v < kMaxVec; ++v)
+    wv[v] = v < V ? __ldg(reinterpret_cast<const float4*>(w_t + (size_t)(F + v) * kC + lane * 4)) : make_float4(0.f, 0.f, 0.f, 0.f);
+  float* hp = h + (size_t)(b0 + a) * kO * kC + lane * 4;
+#pragma unroll 4
+  for (int o = 0; o < kO; ++o) {
+    float4 r = s;
 #pragma unroll
-    for (int o = 0; o < kO; ++o) {
-      float r = s[b];
-#pragma unroll
-      for (int v = 0; v < kMaxVec; ++v)
-        if (v < V) r = fmaf(dots[(b * V + v) * kO + o], wv[v], r);
-      h[((size_t)(b0 + b) * kO + o) * kC + c] = r;
-    }
+    for (int v = 0; v < kMaxVec; ++v)
+      if (v < V) {
+        const float dv = dots[(a * V + v) * kO + o];
+        r.x = fmaf(dv, wv[v].x, r.x); r.y = fmaf(dv, wv[v].y, r.y); r.z = fmaf(dv, wv[v].z, r.z); r.w = fmaf(dv, wv[v].w, r.w);
+      }
+    *reinterpret_cast<float4*>(hp + o * kC) = r;
   }
 }
 
@@ -340,6 +354,259 @@ message_gather_kernel(const KT* __restrict__ kern, const float* __restrict__ h, 
   }
 }
 
+// ---- fp16 tensor path: transposed message sums + tensor-core fiber conv ----------------------------------------
+// K4b (fp16 path)  message_gather_t_kernel: one CTA of 16 warps per receiver atom (warp = orientation, lane = 4
+//   channels); the 16 x 128 message sums are transposed through shared memory and written as x1t[atom][c][o] fp16
+//   (the 16 orientations of a channel are 32 contiguous bytes), the A-operand layout of the fiber conv below.
+constexpr int kGatherTThreads = kO * 32;
+
+__global__ void __launch_bounds__(kGatherTThreads)
+message_gather_t_kernel(const __half* __restrict__ kern, const float* __restrict__ h, const int32_t* __restrict__ row_ptr,
+                        const int32_t* __restrict__ src, int N, __half* __restrict__ x1t) {
+  __shared__ __align__(16) __half tile[kO][kC + 8];       // +8 halfs: conflict-free column reads
+  const int node = blockIdx.x, o = threadIdx.x >> 5, cg = threadIdx.x & 31;
+  const int e0 = row_ptr[node], e1 = row_ptr[node + 1];
+  float4 a = make_float4(0.f, 0.f, 0.f, 0.f);
+  int e = e0;
+  for (; e + 8 <= e1; e += 8) {
+    int sidx[8];
+    float4 kv[8], hv[8];
+#pragma unroll
+    for (int u = 0; u < 8; ++u) sidx[u] = __ldg(src + e + u);
+#pragma unroll
+    for (int u = 0; u < 8; ++u) {
+      kv[u] = load_kernel4(kern + ((size_t)(e + u) * kO + o) * kC, cg, o);
+      hv[u] = *reinterpret_cast<const float4*>(h + ((size_t)sidx[u] * kO + o) * kC + cg * 4);
+    }
+#pragma unroll
+    for (int u = 0; u < 8; ++u) {
+      a.x = fmaf(kv[u].x, hv[u].x, a.x);
+      a.y = fmaf(kv[u].y, hv[u].y, a.y);
+      a.z = fmaf(kv[u].z, hv[u].z, a.z);
+      a.w = fmaf(kv[u].w, hv[u].w, a.w);
+    }
+  }
+  for (; e < e1; ++e) {
+    const float4 kv = load_kernel4(kern + ((size_t)e * kO + o) * kC, cg, o);
+    const float4 hv = *reinterpret_cast<const float4*>(h + ((size_t)__ldg(src + e) * kO + o) * kC + cg * 4);
+    a.x = fmaf(kv.x, hv.x, a.x);
+    a.y = fmaf(kv.y, hv.y, a.y);
+    a.z = fmaf(kv.z, hv.z, a.z);
+    a.w = fmaf(kv.w, hv.w, a.w);
+  }
+  {
+    const __half2 p0 = __floats2half2_rn(a.x, a.y), p1 = __floats2half2_rn(a.z, a.w);
+    uint2 raw;
+    raw.x = *reinterpret_cast<const unsigned*>(&p0);
+    raw.y = *reinterpret_cast<const unsigned*>(&p1);
+    *reinterpret_cast<uint2*>(&tile[o][cg * 4]) = raw;
+  }
+  __syncthreads();
+  {
+    // thread -> (channel c, orientations 4 oq .. +3): 8 bytes, the CTA writes the atom's 4 KB contiguously
+    const int c = threadIdx.x >> 2, oq = (threadIdx.x & 3) * 4;
+    const __half2 p0 = __halves2half2(tile[oq][c], tile[oq + 1][c]), p1 = __halves2half2(tile[oq + 2][c], tile[oq + 3][c]);
+    uint2 raw;
+    raw.x = *reinterpret_cast<const unsigned*>(&p0);
+    raw.y = *reinterpret_cast<const unsigned*>(&p1);
+    *reinterpret_cast<uint2*>(x1t + ((size_t)node * kC + c) * kO + oq) = raw;
+  }
+}
+
+// K5 (fp16 path)  fiber_norm_mma_kernel.  For a fixed channel the fiber conv is a 16 x 16 matrix product over the
+//   orientations, x2[atom][p] = sum_o x1[atom][o] fk[o][p]: one warp takes 16 atoms and runs it as two
+//   mma.sync.m16n8k16 (fp16 operands, fp32 accumulation) per channel, 5x fewer instructions than the SIMT form
+//   (tcgen05 has no shape for a per-channel 16 x 16 x 16 product).  Every (atom, p) pair lives in exactly one lane, so
+//   the LayerNorm statistics over the 128 channels need no shuffles: pass 1 accumulates sum and sum of squares,
+//   pass 2 recomputes the (cheap) products, normalises and emits 8 channels = one 16-byte chunk of the ConvNext
+//   kernel's UMMA operand image at a time.
+//   fk_frag[c][lane] (uint4): the B fragments of channel c for the two n-tiles, with the 1/O of conv.py:115 folded in.
+constexpr int kFiberMmaWarps = 8;    // warp w owns channels 16 w .. 16 w + 15 (16 warps measured slower: the statistics exchange grows)
+
+__device__ __forceinline__ void mma16816(float (&d)[4], uint32_t a0, uint32_t a1, uint32_t a2, uint32_t a3, uint32_t b0, uint32_t b1) {
+  asm volatile(
+      "mma.sync.aligned.m16n8k16.row.col.f32.f16.f16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%10,%10,%10,%10};"
+      : "=f"(d[0]), "=f"(d[1]), "=f"(d[2]), "=f"(d[3])
+      : "r"(a0), "r"(a1), "r"(a2), "r"(a3), "r"(b0), "r"(b1), "f"(0.f));
+}
+
+__global__ void fiber_frag_kernel(const float* __restrict__ fk, uint4* __restrict__ frag) {
+  // grid = L * C blocks of 32 threads; fk[l][o][p][c]
+  const int l = blockIdx.x / kC, c = blockIdx.x % kC, lane = threadIdx.x, g = lane >> 2, t = lane & 3;
+  const float* f = fk + (size_t)l * kO * kO * kC + c;
+  auto at = [&](int o, int p) { return f[((size_t)o * kO + p) * kC] * (1.0f / kO); };
+  auto pack = [&](int o, int p) {
+    const __half2 v = __floats2half2_rn(at(o, p), at(o + 1, p));
+    return *reinterpret_cast<const uint32_t*>(&v);
+  };
+  uint4 r;
+  r.x = pack(2 * t, g);       r.y = pack(2 * t + 8, g);          // n-tile 0: p = g
+  r.z = pack(2 * t, 8 + g);   r.w = pack(2 * t + 8, 8 + g);      // n-tile 1: p = 8 + g
+  frag[(size_t)blockIdx.x * 32 + lane] = r;
+}
+
+constexpr int kFiberGroup = 16;                                   // atoms per tile (the M of the mma)
+constexpr int kFiberRowBytes = kC * kO * 2 + 16;                  // one atom's [c][o] fp16 block + 16 B: conflict-free fragment loads
+constexpr int kFiberTileBytes = kFiberGroup * kFiberRowBytes;
+constexpr size_t kFiberSmem = (size_t)kC * 32 * sizeof(uint4) + 2 * (size_t)kFiberTileBytes +
+                              (size_t)kFiberMmaWarps * 32 * 16 * sizeof(float) + 3 * kC * sizeof(float) + 64;
+
+__global__ void __launch_bounds__(kFiberMmaWarps * 32, 1)
+fiber_norm_mma_kernel(const __half* __restrict__ x1t, const uint4* __restrict__ fk_frag, const float* __restrict__ bias,
+                      const float* __restrict__ ln_w, const float* __restrict__ ln_b, int N, __half* __restrict__ y,
+                      float* __restrict__ x2_dbg) {
+  // Persistent CTA of 8 warps; a tile = 16 atoms (64 KB of x1t, contiguous) arrives by bulk copies into one of two
+  // shared buffers while the previous tile is processed; warp w owns channels 16 w .. 16 w + 15 of the tile.
+  extern __shared__ __align__(128) uint8_t fsm[];
+  uint4* s_frag = reinterpret_cast<uint4*>(fsm);                                 // [kC][32]
+  uint8_t* s_a = fsm + (size_t)kC * 32 * sizeof(uint4);                          // [2][16 atoms][kFiberRowBytes]
+  float* s_stats = reinterpret_cast<float*>(s_a + 2 * (size_t)kFiberTileBytes);  // [warps][32 lanes][16]
+  float* s_bias = s_stats + kFiberMmaWarps * 32 * 16;
+  float* s_g = s_bias + kC;
+  float* s_b = s_g + kC;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(s_b + kC);                        // full[2]
+  for (int i = threadIdx.x; i < kC * 32; i += blockDim.x) s_frag[i] = fk_frag[i];
+  for (int i = threadIdx.x; i < kC; i += blockDim.x) { s_bias[i] = bias[i]; s_g[i] = ln_w[i]; s_b[i] = ln_b[i]; }
+  if (threadIdx.x == 0) {
+    tc::mbar_init(&bars[0], 1);
+    tc::mbar_init(&bars[1], 1);
+    tc::fence_barrier_init();
+  }
+  __syncthreads();
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, g = lane >> 2, t = lane & 3;
+  const int groups = (N + kFiberGroup - 1) / kFiberGroup;
+  auto issue = [&](int grp, int buf) {        // thread 0: the valid atoms of tile grp -> buffer buf
+    const int atom0 = grp * kFiberGroup;
+    const int n = min(kFiberGroup, N - atom0);
+    tc::mbar_expect_tx(&bars[buf], (uint32_t)n * (kC * kO * 2));
+    for (int a = 0; a < n; ++a)
+      tc::bulk_g2s(s_a + (size_t)buf * kFiberTileBytes + (size_t)a * kFiberRowBytes, x1t + (size_t)(atom0 + a) * kC * kO,
+                   kC * kO * 2, &bars[buf]);
+  };
+  if (threadIdx.x == 0 && (int)blockIdx.x < groups) issue(blockIdx.x, 0);
+  int it = 0;
+  for (int grp = blockIdx.x; grp < groups; grp += gridDim.x, ++it) {
+    const int buf = it & 1;
+    if (threadIdx.x == 0 && grp + (int)gridDim.x < groups) {     // buffer buf ^ 1 was released by the barrier that ended the previous tile
+      tc::fence_proxy_async();
+      issue(grp + gridDim.x, buf ^ 1);
+    }
+    tc::mbar_wait(&bars[buf], (it >> 1) & 1);
+    const int atom0 = grp * kFiberGroup;
+    const bool v0 = atom0 + g < N, v1 = atom0 + g + 8 < N;
+    const uint8_t* a0p = s_a + (size_t)buf * kFiberTileBytes + (size_t)g * kFiberRowBytes + 4 * t;
+    const uint8_t* a1p = a0p + 8 * (size_t)kFiberRowBytes;
+    auto load_a = [&](int c, uint32_t (&a)[4]) {
+      a[0] = *reinterpret_cast<const uint32_t*>(a0p + c * (kO * 2));
+      a[1] = *reinterpret_cast<const uint32_t*>(a1p + c * (kO * 2));
+      a[2] = *reinterpret_cast<const uint32_t*>(a0p + c * (kO * 2) + 16);
+      a[3] = *reinterpret_cast<const uint32_t*>(a1p + c * (kO * 2) + 16);
+    };
+    // pass 1: partial statistics over this warp's 16 channels of the 8 (atom, p) pairs of the lane
+    // pair index = ntile * 4 + {(g, 2t), (g, 2t+1), (g+8, 2t), (g+8, 2t+1)}
+    float sum[8], sq[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) { sum[i] = 0.f; sq[i] = 0.f; }
+#pragma unroll 4
+    for (int cc = 0; cc < kC / kFiberMmaWarps; ++cc) {
+      const int c = warp * (kC / kFiberMmaWarps) + cc;
+      uint32_t a[4];
+      load_a(c, a);
+      const uint4 b = s_frag[c * 32 + lane];
+      float d0[4], d1[4];
+      mma16816(d0, a[0], a[1], a[2], a[3], b.x, b.y);
+      mma16816(d1, a[0], a[1], a[2], a[3], b.z, b.w);
+      const float bc = s_bias[c];
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        const float x0 = d0[i] + bc, x1v = d1[i] + bc;
+        sum[i] += x0; sq[i] = fmaf(x0, x0, sq[i]);
+        sum[4 + i] += x1v; sq[4 + i] = fmaf(x1v, x1v, sq[4 + i]);
+      }
+    }
+    {
+      float4* st = reinterpret_cast<float4*>(s_stats + ((size_t)warp * 32 + lane) * 16);
+      st[0] = make_float4(sum[0], sum[1], sum[2], sum[3]);
+      st[1] = make_float4(sum[4], sum[5], sum[6], sum[7]);
+      st[2] = make_float4(sq[0], sq[1], sq[2], sq[3]);
+      st[3] = make_float4(sq[4], sq[5], sq[6], sq[7]);
+    }
+    __syncthreads();
+#pragma unroll
+    for (int i = 0; i < 8; ++i) { sum[i] = 0.f; sq[i] = 0.f; }
+#pragma unroll
+    for (int w = 0; w < kFiberMmaWarps; ++w) {      // fixed order: deterministic
+      const float4* st = reinterpret_cast<const float4*>(s_stats + ((size_t)w * 32 + lane) * 16);
+      const float4 s0 = st[0], s1 = st[1], q0 = st[2], q1 = st[3];
+      sum[0] += s0.x; sum[1] += s0.y; sum[2] += s0.z; sum[3] += s0.w;
+      sum[4] += s1.x; sum[5] += s1.y; sum[6] += s1.z; sum[7] += s1.w;
+      sq[0] += q0.x; sq[1] += q0.y; sq[2] += q0.z; sq[3] += q0.w;
+      sq[4] += q1.x; sq[5] += q1.y; sq[6] += q1.z; sq[7] += q1.w;
+    }
+    float rstd[8], shift[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      const float mean = sum[i] * (1.0f / kC);
+      const float var = fmaxf(sq[i] * (1.0f / kC) - mean * mean, 0.f);      // biased variance, eps 1e-5 (convnext.py:25)
+      rstd[i] = 1.0f / sqrtf(var + 1e-5f);
+      shift[i] = -mean * rstd[i];
+    }
+    // pass 2: recompute, normalise, emit 16-byte chunks (8 channels) of the y tile image
+    // row of pair i: (atom0 + g + 8 * ((i >> 1) & 1)) * 16 + p,  p = 8 * (i >> 2) + 2 t + (i & 1)
+#pragma unroll 1
+    for (int half = 0; half < 2; ++half) {
+      const int cb = warp * 2 + half;
+      uint32_t pk[8][4];
+#pragma unroll
+      for (int j = 0; j < 8; j += 2) {
+        float o0[8], o1[8];
+#pragma unroll
+        for (int jj = 0; jj < 2; ++jj) {
+          const int c = cb * 8 + j + jj;
+          uint32_t a[4];
+          load_a(c, a);
+          const uint4 b = s_frag[c * 32 + lane];
+          float d0[4], d1[4];
+          mma16816(d0, a[0], a[1], a[2], a[3], b.x, b.y);
+          mma16816(d1, a[0], a[1], a[2], a[3], b.z, b.w);
+          const float bc = s_bias[c], gw = s_g[c], gb = s_b[c];
+          float* o = jj ? o1 : o0;
+#pragma unroll
+          for (int i = 0; i < 4; ++i) {
+            const float x0 = d0[i] + bc, x1v = d1[i] + bc;
+            if (x2_dbg) {
+              const int at0 = atom0 + g + 8 * ((i >> 1) & 1);
+              if (at0 < N) {
+                x2_dbg[((size_t)at0 * kO + 2 * t + (i & 1)) * kC + c] = x0;
+                x2_dbg[((size_t)at0 * kO + 8 + 2 * t + (i & 1)) * kC + c] = x1v;
+              }
+            }
+            o[i] = fmaf(fmaf(x0, rstd[i], shift[i]), gw, gb);
+            o[4 + i] = fmaf(fmaf(x1v, rstd[4 + i], shift[4 + i]), gw, gb);
+          }
+        }
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          const __half2 v = __floats2half2_rn(o0[i], o1[i]);
+          pk[i][j >> 1] = *reinterpret_cast<const uint32_t*>(&v);
+        }
+      }
+      const int slab = cb >> 3, chunk = cb & 7;
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        const bool valid = ((i >> 1) & 1) ? v1 : v0;
+        if (valid) {
+          const long long row = (long long)(atom0 + g + 8 * ((i >> 1) & 1)) * kO + 8 * (i >> 2) + 2 * t + (i & 1);
+          const int rr = (int)(row & 127);
+          *reinterpret_cast<uint4*>(reinterpret_cast<uint8_t*>(y) + (size_t)(row >> 7) * 32768 + (size_t)slab * 16384 +
+                                    (size_t)rr * 128 + ((chunk ^ (rr & 7)) << 4)) = make_uint4(pk[i][0], pk[i][1], pk[i][2], pk[i][3]);
+        }
+      }
+    }
+    __syncthreads();       // every warp is done with this tile's buffer and the statistics scratch
+  }
+}
+
 constexpr int kFiberThreads = 512;
 constexpr int kFiberStages = 3;
 constexpr int kFiberNB = 2;     // nodes per pipeline stage
@@ -523,7 +790,9 @@ readout_accumulate_kernel(const float* __restrict__ h, const float* __restrict__
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int R = Z + 4;   // read-out rows: Z scalars, 1 vector channel, 3 global scalars (ponita.py:111)
   const int b0 = blockIdx.x * kReadoutNodes;
-  // phase A: one warp per atom (two atoms per warp), lane = 4 channels
+  // phase A: one warp per atom (two atoms per warp), lane = 4 channels.  The 16 per-orientation dot products with
+  // the vector-channel row are reduced across the warp with a transpose-reduce (16 values over 32 lanes:
+  // 8 + 4 + 2 + 1 + 1 = 16 shuffles instead of 16 x 5).
   float4 wv;
   wv.x = wr_t[(size_t)(lane * 4 + 0) * R + Z];
   wv.y = wr_t[(size_t)(lane * 4 + 1) * R + Z];
@@ -536,15 +805,47 @@ readout_accumulate_kernel(const float* __restrict__ h, const float* __restrict__
     float4 sum = make_float4(0.f, 0.f, 0.f, 0.f);
     if (b < N) {
       const float* hp = h + (size_t)b * kO * kC + lane * 4;
-      float4 hv[kO];
+      float4 hv[kO];                                    // all 16 rows in flight before the first use
 #pragma unroll
-      for (int o = 0; o < kO; ++o) hv[o] = *reinterpret_cast<const float4*>(hp + o * kC);
+      for (int o = 0; o < kO; ++o) hv[o] = __ldcs(reinterpret_cast<const float4*>(hp + o * kC));
+      float d[kO];
 #pragma unroll
       for (int o = 0; o < kO; ++o) {
         sum.x += hv[o].x; sum.y += hv[o].y; sum.z += hv[o].z; sum.w += hv[o].w;
-        const float d = warp_sum((hv[o].x * wv.x + hv[o].y * wv.y) + (hv[o].z * wv.z + hv[o].w * wv.w));
-        if (lane == o) s_o[a][o] = d + bz;
+        d[o] = (hv[o].x * wv.x + hv[o].y * wv.y) + (hv[o].z * wv.z + hv[o].w * wv.w);
       }
+      // transpose-reduce: after the step with lane distance `dist`, a lane keeps half of its values
+      // (those whose index bit matches its lane bit) summed with the partner's copy
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {                     // distance 16: keep d[i] (lane bit 4 = 0) or d[i + 8]
+        const bool up = lane & 16;
+        const float send = up ? d[i] : d[i + 8];
+        const float keep = up ? d[i + 8] : d[i];
+        d[i] = keep + __shfl_xor_sync(0xffffffffu, send, 16);
+      }
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {                     // distance 8
+        const bool up = lane & 8;
+        const float send = up ? d[i] : d[i + 4];
+        const float keep = up ? d[i + 4] : d[i];
+        d[i] = keep + __shfl_xor_sync(0xffffffffu, send, 8);
+      }
+#pragma unroll
+      for (int i = 0; i < 2; ++i) {                     // distance 4
+        const bool up = lane & 4;
+        const float send = up ? d[i] : d[i + 2];
+        const float keep = up ? d[i + 2] : d[i];
+        d[i] = keep + __shfl_xor_sync(0xffffffffu, send, 4);
+      }
+      {                                                 // distance 2
+        const bool up = lane & 2;
+        const float send = up ? d[0] : d[1];
+        const float keep = up ? d[1] : d[0];
+        d[0] = keep + __shfl_xor_sync(0xffffffffu, send, 2);
+      }
+      d[0] += __shfl_xor_sync(0xffffffffu, d[0], 1);    // distance 1: both lanes of a pair hold the total
+      // this lane now holds orientation o = 8 b4 + 4 b3 + 2 b2 + b1 of its lane bits
+      if ((lane & 1) == 0) s_o[a][((lane >> 4) & 1) * 8 + ((lane >> 3) & 1) * 4 + ((lane >> 2) & 1) * 2 + ((lane >> 1) & 1)] = d[0] + bz;
     }
     constexpr float inv = 1.0f / kO;
     *reinterpret_cast<float4*>(&hbar[a][lane * 4]) = make_float4(sum.x * inv, sum.y * inv, sum.z * inv, sum.w * inv);
@@ -616,17 +917,29 @@ int num_sms() {
 // ================================================================================================
 // C ABI
 // ================================================================================================
-extern "C" int arreau_node_embed(const float* x, const float* vec, const float* w_embed_t, const float* ori,
-                                 int32_t N, int32_t F, int32_t V, float* h, void* stream) {
+static int node_embed_launch(const float* x, const float* vec, const float* w_embed_t, const float* ori,
+                             const int64_t* types, int32_t Z, int32_t N, int32_t F, int32_t V, float* h, void* stream) {
   if (N == 0) return ARREAU_OK;
   if (!x || !vec || !w_embed_t || !ori || !h) return ARREAU_ERR_NULL;
-  if (N < 0 || F <= 0 || V < 0 || V > kMaxVec) return ARREAU_ERR_BAD_SHAPE;
+  if (N < 0 || F <= 0 || V < 0 || V > kMaxVec || (types && (Z <= 0 || Z > F))) return ARREAU_ERR_BAD_SHAPE;
   const size_t smem = sizeof(float) * (size_t)kEmbedNodes * (F + V * kO);
   if (smem > 48 * 1024) return ARREAU_ERR_UNSUPPORTED;
-  node_embed_kernel<<<(N + kEmbedNodes - 1) / kEmbedNodes, kC, smem, (cudaStream_t)stream>>>(x, vec, w_embed_t, ori,
-                                                                                            N, F, V, h);
+  node_embed_kernel<<<(N + kEmbedNodes - 1) / kEmbedNodes, kEmbedNodes * 32, smem, (cudaStream_t)stream>>>(
+      x, vec, w_embed_t, ori, types, Z, N, F, V, h);
   CUDA_LAUNCH_CHECK();
   return ARREAU_OK;
+}
+
+extern "C" int arreau_node_embed(const float* x, const float* vec, const float* w_embed_t, const float* ori,
+                                 int32_t N, int32_t F, int32_t V, float* h, void* stream) {
+  return node_embed_launch(x, vec, w_embed_t, ori, nullptr, 0, N, F, V, h, stream);
+}
+
+extern "C" int arreau_node_embed_typed(const float* x, const int64_t* types, int32_t Z, const float* vec,
+                                       const float* w_embed_t, const float* ori, int32_t N, int32_t F, int32_t V,
+                                       float* h, void* stream) {
+  if (!types) return ARREAU_ERR_NULL;
+  return node_embed_launch(x, vec, w_embed_t, ori, types, Z, N, F, V, h, stream);
 }
 
 extern "C" int arreau_fiber_kernel_precompute(const float* ori, const float* w1, const float* b1, const float* w2,
@@ -663,30 +976,52 @@ extern "C" int arreau_edge_kernels_f32(const double* dir, const double* dist, co
   return ARREAU_OK;
 }
 
+extern "C" int arreau_fiber_frag_pack(const float* fiber_kernel, int32_t num_layers, void* fiber_frag, void* stream) {
+  if (!fiber_kernel || !fiber_frag) return ARREAU_ERR_NULL;
+  if (num_layers <= 0) return ARREAU_ERR_BAD_SHAPE;
+  fiber_frag_kernel<<<num_layers * kC, 32, 0, (cudaStream_t)stream>>>(fiber_kernel, (uint4*)fiber_frag);
+  CUDA_LAUNCH_CHECK();
+  return ARREAU_OK;
+}
+
 extern "C" int arreau_message_fiber_norm(const void* kernels, int32_t kernels_f16, const float* h,
                                          const int32_t* row_ptr, const int32_t* src, const float* fiber_kernel,
-                                         const float* conv_bias, const float* ln_w, const float* ln_b, int32_t N,
-                                         void* y, int32_t y_f16, float* x1, float* x2_debug, void* stream) {
+                                         const void* fiber_frag, const float* conv_bias, const float* ln_w,
+                                         const float* ln_b, int32_t N, void* y, int32_t y_f16, float* x1,
+                                         float* x2_debug, void* stream) {
   if (N == 0) return ARREAU_OK;
   if (!h || !row_ptr || !fiber_kernel || !conv_bias || !ln_w || !ln_b || !y || !x1) return ARREAU_ERR_NULL;
   if (N < 0) return ARREAU_ERR_BAD_SHAPE;
   cudaStream_t s = (cudaStream_t)stream;
   const long long rows = (long long)N * kO;
+  if (kernels_f16 && y_f16) {
+    // fp16 tensor path: transposed fp16 message sums, tensor-core fiber conv
+    if (!fiber_frag) return ARREAU_ERR_NULL;
+    message_gather_t_kernel<<<N, kGatherTThreads, 0, s>>>((const __half*)kernels, h, row_ptr, src, N, (__half*)x1);
+    CUDA_LAUNCH_CHECK();
+    static bool attr_set = false;
+    const size_t smem = kFiberSmem;
+    if (!attr_set) {
+      cudaError_t e = cudaFuncSetAttribute(fiber_norm_mma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+      if (e != cudaSuccess) return (int)e;
+      attr_set = true;
+    }
+    const int groups = (N + kFiberGroup - 1) / kFiberGroup;
+    const int grid = groups < num_sms() ? groups : num_sms();
+    fiber_norm_mma_kernel<<<grid, kFiberMmaWarps * 32, smem, s>>>((const __half*)x1, (const uint4*)fiber_frag, conv_bias, ln_w,
+                                                                  ln_b, N, (__half*)y, x2_debug);
+    CUDA_LAUNCH_CHECK();
+    return ARREAU_OK;
+  }
   const unsigned ggrid = (unsigned)((rows + kGatherWarps - 1) / kGatherWarps);
-  // fp16 tensor path (fp16 kernels in, fp16 y out): x1 is kept in fp16 too; otherwise fp32
-  const bool x1_f16 = kernels_f16 && y_f16;
-  if (x1_f16)
-    message_gather_kernel<__half, __half><<<ggrid, kGatherWarps * 32, 0, s>>>((const __half*)kernels, h, row_ptr, src, rows, (__half*)x1);
-  else if (kernels_f16)
+  if (kernels_f16)
     message_gather_kernel<__half, float><<<ggrid, kGatherWarps * 32, 0, s>>>((const __half*)kernels, h, row_ptr, src, rows, x1);
   else
     message_gather_kernel<float, float><<<ggrid, kGatherWarps * 32, 0, s>>>((const float*)kernels, h, row_ptr, src, rows, x1);
   CUDA_LAUNCH_CHECK();
   const int fgroups = (N + kFiberNB - 1) / kFiberNB;
   const int fgrid = fgroups < num_sms() ? fgroups : num_sms();
-  if (x1_f16)
-    fiber_norm_kernel<__half, __half><<<fgrid, kFiberThreads, 0, s>>>((const __half*)x1, fiber_kernel, conv_bias, ln_w, ln_b, N, (__half*)y, x2_debug);
-  else if (y_f16)
+  if (y_f16)
     fiber_norm_kernel<float, __half><<<fgrid, kFiberThreads, 0, s>>>(x1, fiber_kernel, conv_bias, ln_w, ln_b, N, (__half*)y, x2_debug);
   else
     fiber_norm_kernel<float, float><<<fgrid, kFiberThreads, 0, s>>>(x1, fiber_kernel, conv_bias, ln_w, ln_b, N, (float*)y, x2_debug);

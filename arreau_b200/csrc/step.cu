@@ -105,7 +105,11 @@ extern "C" int arreau_ponita_forward(const arreau_weights* w, const arreau_works
   const int Z = w->num_states;
   const size_t node_elems = (size_t)N * kO * kC;
   cudaStream_t s = (cudaStream_t)stream;
-  ARREAU_TRY(arreau_node_embed(x, vec, w->w_embed_t, w->ori, N, w->num_scalar, w->num_vec, ws->h, stream));
+  if (ws->onehot_types)
+    ARREAU_TRY(arreau_node_embed_typed(x, ws->onehot_types, Z, vec, w->w_embed_t, w->ori, N, w->num_scalar, w->num_vec,
+                                       ws->h, stream));
+  else
+    ARREAU_TRY(arreau_node_embed(x, vec, w->w_embed_t, w->ori, N, w->num_scalar, w->num_vec, ws->h, stream));
   if (ws->h_debug) {
     cudaError_t e = cudaMemcpyAsync(ws->h_debug, ws->h, node_elems * sizeof(float), cudaMemcpyDeviceToDevice, s);
     if (e != cudaSuccess) return (int)e;
@@ -123,6 +127,7 @@ extern "C" int arreau_ponita_forward(const arreau_weights* w, const arreau_works
     const void* kern = fp16 ? (const void*)((const uint16_t*)ws->kernels + (size_t)l * layer_elems)
                             : (const void*)((const float*)ws->kernels + (size_t)l * layer_elems);
     ARREAU_TRY(arreau_message_fiber_norm(kern, fp16, ws->h, row_ptr, src, w->fiber_kernel + (size_t)l * kO * kO * kC,
+                                         w->fiber_frag ? (const uint8_t*)w->fiber_frag + (size_t)l * kC * 32 * 16 : nullptr,
                                          w->conv_bias + l * kC, w->ln_w + l * kC, w->ln_b + l * kC, N, ws->y, fp16,
                                          ws->x1_debug ? ws->x1_debug + l * node_elems : ws->x1,
                                          ws->x2_debug ? ws->x2_debug + l * node_elems : nullptr, stream));

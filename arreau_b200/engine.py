@@ -121,6 +121,7 @@ class DenoiseEngine:
         ws.x1 = self.x1.data_ptr()
         ws.x1_debug, ws.x2_debug, ws.h_debug = _lib.ptr(self.x1_debug), _lib.ptr(self.x2_debug), _lib.ptr(self.h_debug)
         ws.edge_capacity = capacity
+        ws.onehot_types = None          # set by predict_scores / step: x[:, :Z] is one_hot(self.types) there
         self.ws = ws
         a = _lib.StepArgs()
         p = _lib.ptr
@@ -238,7 +239,11 @@ class DenoiseEngine:
         self.prepare_inputs(t)
         self._ensure_capacity()
         self.build_graph()
-        self.forward()
+        self.ws.onehot_types = self.types.data_ptr()      # x was assembled from self.types
+        try:
+            self.forward()
+        finally:
+            self.ws.onehot_types = None
         return self.score, self.logits, self.len0
 
     # ------------------------------------------------------------------ step
@@ -256,7 +261,11 @@ class DenoiseEngine:
         a.vp_cx0, a.vp_cxt = float(tb.vp_cx0[t]), float(tb.vp_cxt[t])
         a.vp_denom, a.vp_var = float(tb.vp_denom[t]), float(tb.vp_var[t])
         a.update_types = 1 if update_types else 0
-        _lib.call("arreau_denoise_step", self.w.ref(), C.byref(self.ws), C.byref(a), self.stream)
+        self.ws.onehot_types = self.types.data_ptr()      # the step assembles x from the state's types
+        try:
+            _lib.call("arreau_denoise_step", self.w.ref(), C.byref(self.ws), C.byref(a), self.stream)
+        finally:
+            self.ws.onehot_types = None
 
     def kernels_logical(self, layer: int, num_edges: Optional[int] = None) -> torch.Tensor:
         """Spatial kernels of one layer as fp32 [E,O,C] in logical channel order (debug / tests).  The fp16 path
@@ -292,9 +301,9 @@ class DenoiseEngine:
 
         add("features", lambda: self.prepare_inputs(t))
         add("graph", lambda: self.build_graph())
-        add("node_embed", lambda: _lib.call("arreau_node_embed", self.x.data_ptr(), self.vec.data_ptr(),
-                                            w["w_embed_t"].data_ptr(), w["ori"].data_ptr(), self.N, self.F, 4,
-                                            self.h.data_ptr(), self.stream))
+        add("node_embed", lambda: _lib.call("arreau_node_embed_typed", self.x.data_ptr(), self.types.data_ptr(), Z,
+                                            self.vec.data_ptr(), w["w_embed_t"].data_ptr(), w["ori"].data_ptr(),
+                                            self.N, self.F, 4, self.h.data_ptr(), self.stream))
         nep = self.row_ptr.data_ptr() + 4 * self.N
         if fp16:
             add("edge_kernels", lambda: _lib.call(
@@ -312,6 +321,7 @@ class DenoiseEngine:
             add("message_fiber_norm", lambda l=l: _lib.call(
                 "arreau_message_fiber_norm", self.kernels[l].data_ptr(), int(fp16), self.h.data_ptr(),
                 self.row_ptr.data_ptr(), self.src.data_ptr(), w["fiber_kernel"][l].data_ptr(),
+                (w["fiber_frag"].data_ptr() + l * HIDDEN * 32 * 16) if fp16 else None,
                 w["conv_bias"][l].data_ptr(), w["ln_w"][l].data_ptr(), w["ln_b"][l].data_ptr(), self.N,
                 self.y.data_ptr(), int(fp16), self.x1.data_ptr(), None, self.stream))
             if fp16:

@@ -119,6 +119,9 @@ class PonitaWeights:
         stream = torch.cuda.current_stream(self.device).cuda_stream
         _lib.call("arreau_fiber_kernel_precompute", self.t["ori"].data_ptr(), fw1.data_ptr(), fb1.data_ptr(),
                   fw2.data_ptr(), fb2.data_ptr(), fwf.data_ptr(), self.t["fiber_kernel"].data_ptr(), stream)
+        if with_f16:   # fp16 mma fragments of the fiber kernels for the tensor-core fiber conv
+            self.t["fiber_frag"] = torch.empty(L * HIDDEN * 32 * 4, dtype=torch.int32, device=self.device)
+            _lib.call("arreau_fiber_frag_pack", self.t["fiber_kernel"].data_ptr(), L, self.t["fiber_frag"].data_ptr(), stream)
         torch.cuda.current_stream(self.device).synchronize()
         if with_f16:
             # tcgen05 path: every weight tile as a ready-to-copy UMMA shared-memory image

@@ -127,6 +127,12 @@ int arreau_fiber_kernel_precompute(const float* ori, const float* w1, const floa
 int arreau_node_embed(const float* x, const float* vec, const float* w_embed_t, const float* ori,
                       int32_t num_atoms_total, int32_t num_scalar, int32_t num_vec, float* h, void* stream);
 
+/* Same, when the first Z scalar features of x are a one-hot of types[N] (i64) as in predict_scores
+ * (diffusion_loss.py:140-150): the one-hot block becomes one row lookup of the weight. */
+int arreau_node_embed_typed(const float* x, const int64_t* types, int32_t num_states, const float* vec,
+                            const float* w_embed_t, const float* ori, int32_t num_atoms_total, int32_t num_scalar,
+                            int32_t num_vec, float* h, void* stream);
+
 /* K3+K4a: per (edge, orientation) invariants -> 83 monomials -> Linear+GELU -> Linear+GELU -> *window
  * -> all L per-layer spatial kernels  kernels[L, edge_capacity, O, C] (ponita/geometry/invariants.py:17-22,
  * transforms/invariants.py:81-87, embedding.py:10-14, ponita.py:65,94, windowing.py:21-29,
@@ -152,12 +158,17 @@ int arreau_edge_kernels_f16(const double* dir, const double* dist, const double*
  * `kernels` is ONE layer's [edge_capacity,O,C] slab (f32, or fp16 when kernels_f16 != 0);
  * fiber_kernel is that layer's [O,O,C].  y[N,O,C] is f32 row-major, or (y_f16) fp16 in 128-row UMMA tile
  * images for arreau_convnext_mlp_f16.  x1 ([N,O,C] f32 capacity, required) is the workspace between the two
- * launches (gather, then fiber conv + norm); it holds f32 values, or f16 values when both kernels_f16 and y_f16 are set; x2_debug (f32 [N,O,C], may be NULL) receives x2 for the parity
+ * launches (gather, then fiber conv + norm); it holds f32 [N,O,C] values, or -- when both kernels_f16 and y_f16 are set
+ * (the fp16 tensor path, which also needs fiber_frag of this layer) -- f16 values transposed to [N,C,O]; x2_debug (f32 [N,O,C], may be NULL) receives x2 for the parity
  * tests.  Deterministic receiver-sorted CSR reduction (fixed order, no atomics). */
 int arreau_message_fiber_norm(const void* kernels, int32_t kernels_f16, const float* h, const int32_t* row_ptr,
-                              const int32_t* src, const float* fiber_kernel, const float* conv_bias,
-                              const float* ln_w, const float* ln_b, int32_t num_atoms_total, void* y,
-                              int32_t y_f16, float* x1, float* x2_debug, void* stream);
+                              const int32_t* src, const float* fiber_kernel, const void* fiber_frag,
+                              const float* conv_bias, const float* ln_w, const float* ln_b, int32_t num_atoms_total,
+                              void* y, int32_t y_f16, float* x1, float* x2_debug, void* stream);
+
+/* fiber_frag[L][C][32] (16 bytes each): the fp16 mma.sync B fragments of fiber_kernel[L,O,O,C] / O, one per
+ * (layer, channel, lane) -- the operand of the tensor-core fiber conv of the fp16 path (64 KB per layer). */
+int arreau_fiber_frag_pack(const float* fiber_kernel, int32_t num_layers, void* fiber_frag, void* stream);
 
 /* K6: h <- h + layer_scale * (W2 gelu(W1 y + b1) + b2)   (convnext.py:26-32); rows = N*O.
  * _f32: w1_t[C,4C], w2_t[4C,C] f32.  _f16: y_img = fp16 y as 128-row UMMA tile images (32 KB per tile, written
@@ -192,6 +203,7 @@ typedef struct arreau_weights {
   const float* b2;           /* [D]                                                         */
   const float* wk_t;         /* [D, L*C]                                                    */
   const float* fiber_kernel; /* [L,O,O,C]                                                   */
+  const void* fiber_frag;    /* [L,C,32] x 16 B mma fragments of fiber_kernel / O (fp16 path), or NULL */
   const float* conv_bias;    /* [L,C]                                                       */
   const float* ln_w;         /* [L,C]                                                       */
   const float* ln_b;         /* [L,C]                                                       */
@@ -223,6 +235,7 @@ typedef struct arreau_workspace {
   float* x2_debug;  /* NULL, or [L,N,O,C] f32                                                */
   float* h_debug;   /* NULL, or [L+1,N,O,C] f32 (h after the embedding and after each layer) */
   int64_t edge_capacity;
+  const int64_t* onehot_types; /* NULL, or types[N]: x[:, 0:Z] is one_hot(types) (lets the embedding skip the zeros) */
 } arreau_workspace;
 
 /* PonitaFiberBundle.forward (ponita/models/ponita.py:88-123) on a prebuilt graph: x[N,F], vec[N,V,3] f32;
