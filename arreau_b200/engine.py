@@ -161,6 +161,41 @@ class DenoiseEngine:
         self.z_frac.copy_(torch.as_tensor(z_frac).reshape(self.N, 3), non_blocking=True)
         self.u_type.copy_(torch.as_tensor(u_type).reshape(self.N, self.Z), non_blocking=True)
 
+    def stage_noise(self, z_len, z_frac, u_type) -> None:
+        """Upload the NEXT step's noise (pinned host tensors) into the second set of device buffers on a side
+        stream, so that the host->device copy (30 MB of uniforms per step at C2) runs under the current step's
+        kernels.  `use_staged_noise()` makes the staged set current once the copy has landed;
+        `release_noise()` after a step marks the set that step read as reusable."""
+        if not hasattr(self, "_noise_sets"):
+            other = (torch.empty_like(self.z_len), torch.empty_like(self.z_frac), torch.empty_like(self.u_type))
+            self._noise_sets = [(self.z_len, self.z_frac, self.u_type), other]
+            self._noise_front = 0
+            self._copy_stream = torch.cuda.Stream(self.device)
+            self._noise_ready = torch.cuda.Event()
+            self._noise_consumed = [torch.cuda.Event(), torch.cuda.Event()]
+            for ev in self._noise_consumed:
+                ev.record(torch.cuda.current_stream(self.device))
+        back = 1 - self._noise_front
+        self._copy_stream.wait_event(self._noise_consumed[back])     # the step that read this set has finished
+        with torch.cuda.stream(self._copy_stream):
+            for dst_, src_, shape in zip(self._noise_sets[back], (z_len, z_frac, u_type),
+                                         ((self.G, 3), (self.N, 3), (self.N, self.Z))):
+                dst_.copy_(torch.as_tensor(src_).reshape(shape), non_blocking=True)
+            self._noise_ready.record(self._copy_stream)
+
+    def use_staged_noise(self) -> None:
+        """Swap the staged noise in (device-side wait on the copy; no host synchronisation)."""
+        torch.cuda.current_stream(self.device).wait_event(self._noise_ready)
+        self._noise_front = 1 - self._noise_front
+        self.z_len, self.z_frac, self.u_type = self._noise_sets[self._noise_front]
+        a = self.args
+        a.z_len, a.z_frac, a.u_type = _lib.ptr(self.z_len), _lib.ptr(self.z_frac), _lib.ptr(self.u_type)
+
+    def release_noise(self) -> None:
+        """After enqueueing a step: the noise set it reads may be refilled once the stream gets here."""
+        if hasattr(self, "_noise_sets"):
+            self._noise_consumed[self._noise_front].record(torch.cuda.current_stream(self.device))
+
     def draw_noise(self, seed: int, step: int) -> None:
         """Philox noise on the device for throughput runs (the reference draws torch CPU noise)."""
         _lib.call("arreau_step_noise", C.c_uint64(seed), step, self.G, self.N, self.Z, self.z_len.data_ptr(),

@@ -78,3 +78,38 @@ def test_reference_sample_T11_teacher_forced(device, gold, weights_npz):
         else:
             assert _wrapped(eng.frac.cpu().numpy(), s["frac_x"]) < TOL_FP32 * max(1.0, np.abs(s["step_score"][k]).max())
             assert rel_err(eng.lattice.cpu().numpy(), s["lattice"]) < TOL_FP32
+
+
+def test_staged_noise_equals_direct(device, gold, packed_weights, weights_npz):
+    """engine.stage_noise / use_staged_noise (next step's draws uploaded on a side stream into a second buffer set)
+    gives bit-identical steps to set_noise."""
+    from arreau_b200.engine import DenoiseEngine
+    from arreau_b200.tables import build_tables
+    s = gold("steps_c1_T1000.npz")
+    g = torch.Generator().manual_seed(11)
+
+    def run(staged):
+        eng = DenoiseEngine(packed_weights, build_tables(1000, 90), weights_npz["fourier_w"], s["num_atoms"], 5.0, 8,
+                            device=device)
+        eng.set_state(s["t500/frac"], s["t500/types"], s["t500/lengths"], s["angles"])
+        g.manual_seed(11)
+        noises = [(torch.randn(eng.G, 3, generator=g, dtype=torch.float64).pin_memory(),
+                   torch.randn(eng.N, 3, generator=g, dtype=torch.float64).pin_memory(),
+                   torch.rand(eng.N, 90, generator=g, dtype=torch.float64).pin_memory()) for _ in range(4)]
+        if staged:
+            eng.stage_noise(*noises[0])
+        for k, t in enumerate((500, 499, 498, 497)):
+            if staged:
+                eng.use_staged_noise()
+            else:
+                eng.set_noise(*noises[k])
+            eng.step(t)
+            if staged:
+                eng.release_noise()
+                if k + 1 < 4:
+                    eng.stage_noise(*noises[k + 1])
+        torch.cuda.synchronize()
+        return eng.frac.clone(), eng.types.clone(), eng.lengths.clone()
+
+    a, b = run(False), run(True)
+    assert all(torch.equal(x, y) for x, y in zip(a, b))
