@@ -112,3 +112,34 @@ def test_c2_shape_f16_vs_fp32_and_properties(device, packed_weights, weights_npz
         assert float(eng.frac.min()) >= 0.0 and float(eng.frac.max()) < 1.0      # wrapped (helpers:81)
     for a, b in zip(outs["fp16"][:3], outs["fp32"][:3]):
         assert _rel(a, b) < TOL_FP16_MODEL
+
+
+@pytest.mark.parametrize("num_atoms,radius,cap", [([1], 5.0, 8), ([3, 1, 2], 5.0, 8), ([5, 17, 2, 9], 2.5, 8),
+                                                   ([30, 7], 5.0, 0), ([2, 2, 2], 0.5, 8)])
+def test_ragged_and_sparse_batches_f16_vs_fp32(device, packed_weights, weights_npz, num_atoms, radius, cap):
+    """Edge cases of the tensor path's tiling: atom counts that are not multiples of the 16-atom fiber tiles or
+    the 8-edge GEMM tiles, an odd number of edge tiles, atoms without any neighbour (radius 2.5) and a batch
+    without a single edge (radius 0.5, one atom per ~18 A^3); fp16 path against the fp32 path."""
+    from arreau_b200.engine import DenoiseEngine
+    from arreau_b200.synthetic import make_crystals
+    from arreau_b200.tables import build_tables
+    rng = np.random.default_rng(5)
+    na = np.asarray(num_atoms)
+    a = np.cbrt(18.05 * na)
+    lengths = a[:, None] * (1.0 + 0.1 * rng.standard_normal((len(na), 3)))
+    angles = np.pi / 2 + 0.1 * rng.standard_normal((len(na), 3))
+    frac, types = rng.random((int(na.sum()), 3)), rng.integers(0, 89, int(na.sum()))
+    outs = {}
+    for prec in ("fp32", "fp16"):
+        eng = DenoiseEngine(packed_weights, build_tables(1000, 90), weights_npz["fourier_w"], na, radius, cap,
+                            precision=prec, device=device)
+        eng.set_state(frac, types, lengths, angles)
+        score, logits, len0 = eng.predict_scores(400)
+        torch.cuda.synchronize()
+        outs[prec] = (score.clone(), logits.clone(), len0.clone(), eng.num_edges())
+        assert all(bool(torch.isfinite(t).all()) for t in outs[prec][:3])
+    assert outs["fp16"][3] == outs["fp32"][3]
+    if radius < 1.0:
+        assert outs["fp16"][3] == 0
+    for x, y in zip(outs["fp16"][:3], outs["fp32"][:3]):
+        assert _rel(x, y) < TOL_FP16_MODEL
