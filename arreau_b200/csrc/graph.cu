@@ -97,38 +97,48 @@ graph_count_kernel(const double* __restrict__ pos, const double* __restrict__ la
   }
 }
 
-// Single-CTA exclusive scan (N is at most a few 100k atoms per micro-batch).
+// Single-CTA exclusive scan (N is at most a few 100k atoms per micro-batch): coalesced tiles of 4096 elements
+// (int4 per thread), block scan per tile, running carry.
 __global__ void __launch_bounds__(1024) scan_kernel(const int32_t* __restrict__ in, int32_t* __restrict__ out, int n) {
   __shared__ int warp_tot[32];
   __shared__ int carry_s;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  const int per = (n + 1023) / 1024;
-  const int lo = min(n, tid * per), hi = min(n, lo + per);
-  int s = 0;
-  for (int k = lo; k < hi; ++k) s += in[k];
-  int incl = s;
-#pragma unroll
-  for (int o = 1; o < 32; o <<= 1) {
-    int v = __shfl_up_sync(0xffffffffu, incl, o);
-    if (lane >= o) incl += v;
-  }
-  if (lane == 31) warp_tot[warp] = incl;
+  if (tid == 0) carry_s = 0;
   __syncthreads();
-  if (warp == 0) {
-    int w = warp_tot[lane], wi = w;
+  for (int base = 0; base < n; base += 4096) {
+    const int carry = carry_s;           // written before the barrier that ended the previous tile
+    const int i0 = base + tid * 4;
+    int v[4];
+#pragma unroll
+    for (int k = 0; k < 4; ++k) v[k] = (i0 + k < n) ? in[i0 + k] : 0;
+    const int s = (v[0] + v[1]) + (v[2] + v[3]);
+    int incl = s;
 #pragma unroll
     for (int o = 1; o < 32; o <<= 1) {
-      int v = __shfl_up_sync(0xffffffffu, wi, o);
-      if (lane >= o) wi += v;
+      const int t = __shfl_up_sync(0xffffffffu, incl, o);
+      if (lane >= o) incl += t;
     }
-    warp_tot[lane] = wi - w;
-    if (lane == 31) carry_s = wi;
-  }
-  __syncthreads();
-  int run = warp_tot[warp] + incl - s;
-  for (int k = lo; k < hi; ++k) {
-    out[k] = run;
-    run += in[k];
+    if (lane == 31) warp_tot[warp] = incl;
+    __syncthreads();
+    if (warp == 0) {
+      const int w = warp_tot[lane];
+      int wi = w;
+#pragma unroll
+      for (int o = 1; o < 32; o <<= 1) {
+        const int t = __shfl_up_sync(0xffffffffu, wi, o);
+        if (lane >= o) wi += t;
+      }
+      warp_tot[lane] = wi - w;
+      if (lane == 31) carry_s = carry + wi;
+    }
+    __syncthreads();
+    int run = carry + warp_tot[warp] + incl - s;
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      if (i0 + k < n) out[i0 + k] = run;
+      run += v[k];
+    }
+    __syncthreads();
   }
   if (tid == 0) out[n] = carry_s;
 }

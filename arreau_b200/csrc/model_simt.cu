@@ -984,49 +984,67 @@ extern "C" int arreau_fiber_frag_pack(const float* fiber_kernel, int32_t num_lay
   return ARREAU_OK;
 }
 
-extern "C" int arreau_message_fiber_norm(const void* kernels, int32_t kernels_f16, const float* h,
-                                         const int32_t* row_ptr, const int32_t* src, const float* fiber_kernel,
-                                         const void* fiber_frag, const float* conv_bias, const float* ln_w,
-                                         const float* ln_b, int32_t N, void* y, int32_t y_f16, float* x1,
-                                         float* x2_debug, void* stream) {
+extern "C" int arreau_message_gather(const void* kernels, int32_t kernels_f16, const float* h, const int32_t* row_ptr,
+                                     const int32_t* src, int32_t N, int32_t x1_f16_transposed, float* x1, void* stream) {
   if (N == 0) return ARREAU_OK;
-  if (!h || !row_ptr || !fiber_kernel || !conv_bias || !ln_w || !ln_b || !y || !x1) return ARREAU_ERR_NULL;
-  if (N < 0) return ARREAU_ERR_BAD_SHAPE;
+  if (!h || !row_ptr || !x1 || !kernels) return ARREAU_ERR_NULL;
+  if (N < 0 || (x1_f16_transposed && !kernels_f16)) return ARREAU_ERR_BAD_SHAPE;
   cudaStream_t s = (cudaStream_t)stream;
   const long long rows = (long long)N * kO;
-  if (kernels_f16 && y_f16) {
-    // fp16 tensor path: transposed fp16 message sums, tensor-core fiber conv
-    if (!fiber_frag) return ARREAU_ERR_NULL;
+  if (x1_f16_transposed) {
     message_gather_t_kernel<<<N, kGatherTThreads, 0, s>>>((const __half*)kernels, h, row_ptr, src, N, (__half*)x1);
-    CUDA_LAUNCH_CHECK();
+  } else {
+    const unsigned ggrid = (unsigned)((rows + kGatherWarps - 1) / kGatherWarps);
+    if (kernels_f16)
+      message_gather_kernel<__half, float><<<ggrid, kGatherWarps * 32, 0, s>>>((const __half*)kernels, h, row_ptr, src, rows, x1);
+    else
+      message_gather_kernel<float, float><<<ggrid, kGatherWarps * 32, 0, s>>>((const float*)kernels, h, row_ptr, src, rows, x1);
+  }
+  CUDA_LAUNCH_CHECK();
+  return ARREAU_OK;
+}
+
+extern "C" int arreau_fiber_norm(const float* x1, int32_t x1_f16_transposed, const float* fiber_kernel,
+                                 const void* fiber_frag, const float* conv_bias, const float* ln_w, const float* ln_b,
+                                 int32_t N, void* y, int32_t y_f16, float* x2_debug, void* stream) {
+  if (N == 0) return ARREAU_OK;
+  if (!x1 || !fiber_kernel || !conv_bias || !ln_w || !ln_b || !y) return ARREAU_ERR_NULL;
+  if (N < 0 || (x1_f16_transposed && !y_f16)) return ARREAU_ERR_BAD_SHAPE;
+  cudaStream_t s = (cudaStream_t)stream;
+  if (x1_f16_transposed) {
+    if (!fiber_frag) return ARREAU_ERR_NULL;
     static bool attr_set = false;
-    const size_t smem = kFiberSmem;
     if (!attr_set) {
-      cudaError_t e = cudaFuncSetAttribute(fiber_norm_mma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+      cudaError_t e = cudaFuncSetAttribute(fiber_norm_mma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kFiberSmem);
       if (e != cudaSuccess) return (int)e;
       attr_set = true;
     }
     const int groups = (N + kFiberGroup - 1) / kFiberGroup;
     const int grid = groups < num_sms() ? groups : num_sms();
-    fiber_norm_mma_kernel<<<grid, kFiberMmaWarps * 32, smem, s>>>((const __half*)x1, (const uint4*)fiber_frag, conv_bias, ln_w,
-                                                                  ln_b, N, (__half*)y, x2_debug);
-    CUDA_LAUNCH_CHECK();
-    return ARREAU_OK;
+    fiber_norm_mma_kernel<<<grid, kFiberMmaWarps * 32, kFiberSmem, s>>>((const __half*)x1, (const uint4*)fiber_frag, conv_bias,
+                                                                        ln_w, ln_b, N, (__half*)y, x2_debug);
+  } else {
+    const int fgroups = (N + kFiberNB - 1) / kFiberNB;
+    const int fgrid = fgroups < num_sms() ? fgroups : num_sms();
+    if (y_f16)
+      fiber_norm_kernel<float, __half><<<fgrid, kFiberThreads, 0, s>>>(x1, fiber_kernel, conv_bias, ln_w, ln_b, N, (__half*)y, x2_debug);
+    else
+      fiber_norm_kernel<float, float><<<fgrid, kFiberThreads, 0, s>>>(x1, fiber_kernel, conv_bias, ln_w, ln_b, N, (float*)y, x2_debug);
   }
-  const unsigned ggrid = (unsigned)((rows + kGatherWarps - 1) / kGatherWarps);
-  if (kernels_f16)
-    message_gather_kernel<__half, float><<<ggrid, kGatherWarps * 32, 0, s>>>((const __half*)kernels, h, row_ptr, src, rows, x1);
-  else
-    message_gather_kernel<float, float><<<ggrid, kGatherWarps * 32, 0, s>>>((const float*)kernels, h, row_ptr, src, rows, x1);
-  CUDA_LAUNCH_CHECK();
-  const int fgroups = (N + kFiberNB - 1) / kFiberNB;
-  const int fgrid = fgroups < num_sms() ? fgroups : num_sms();
-  if (y_f16)
-    fiber_norm_kernel<float, __half><<<fgrid, kFiberThreads, 0, s>>>(x1, fiber_kernel, conv_bias, ln_w, ln_b, N, (__half*)y, x2_debug);
-  else
-    fiber_norm_kernel<float, float><<<fgrid, kFiberThreads, 0, s>>>(x1, fiber_kernel, conv_bias, ln_w, ln_b, N, (float*)y, x2_debug);
   CUDA_LAUNCH_CHECK();
   return ARREAU_OK;
+}
+
+extern "C" int arreau_message_fiber_norm(const void* kernels, int32_t kernels_f16, const float* h,
+                                         const int32_t* row_ptr, const int32_t* src, const float* fiber_kernel,
+                                         const void* fiber_frag, const float* conv_bias, const float* ln_w,
+                                         const float* ln_b, int32_t N, void* y, int32_t y_f16, float* x1,
+                                         float* x2_debug, void* stream) {
+  // fp16 tensor path (fp16 kernels in, fp16 y out): transposed fp16 message sums + tensor-core fiber conv
+  const int32_t t = (kernels_f16 && y_f16) ? 1 : 0;
+  const int rc = arreau_message_gather(kernels, kernels_f16, h, row_ptr, src, N, t, x1, stream);
+  if (rc != ARREAU_OK) return rc;
+  return arreau_fiber_norm(x1, t, fiber_kernel, fiber_frag, conv_bias, ln_w, ln_b, N, y, y_f16, x2_debug, stream);
 }
 
 extern "C" int arreau_convnext_mlp_f32(const float* y, const float* w1_t, const float* b1, const float* w2_t,

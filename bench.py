@@ -451,10 +451,15 @@ def main():
         flops_edge = 2.0 * E * O * (MONO * C + C * D + L * D * C) + 2.0 * L * 0   # 6.63 MFLOP/edge
         flops_mlp = 2.0 * 2 * C * 4 * C * N * O                                   # per layer
         kbytes = 2 if args.precision == "fp16" else 4
-        bytes_msg = E * O * C * kbytes + 2 * 4 * N * O * C + 12 * E               # per layer: kernels + h in + y out + edges
+        # per layer: the gather streams the layer's kernel slab once, reads h once (compulsory) and the
+        # edge list, and writes the message sums; the fiber conv + LayerNorm reads them and writes y
+        x1b = kbytes
+        bytes_gather = E * O * C * kbytes + 4 * N * O * C + 12 * E + x1b * N * O * C
+        bytes_fiber = x1b * N * O * C + kbytes * N * O * C
         alg = {"edge_kernels": ("tensor", flops_edge / 1e12, peak_tf, "TFLOP/s"),
                "convnext_mlp": ("tensor", flops_mlp / 1e12, peak_tf, "TFLOP/s"),
-               "message_fiber_norm": ("hbm", bytes_msg / 1e9, peak_bw, "GB/s")}
+               "message_gather": ("hbm", bytes_gather / 1e9, peak_bw, "GB/s"),
+               "fiber_norm": ("hbm", bytes_fiber / 1e9, peak_bw, "GB/s")}
         kernels = {}
         for name, (bound, work, peak, unit) in alg.items():
             sec = br[name]["ms_per_launch"] * 1e-3
@@ -462,7 +467,17 @@ def main():
             kernels[name] = {"bound": bound, "achieved": ach, "peak": peak, "unit": unit, "frac": ach / peak,
                              "ms_per_launch": br[name]["ms_per_launch"], "launches_per_step": br[name]["launches_per_step"]}
         dom = top if top in kernels else "edge_kernels"
-        roof = dict(kernels[dom]); roof.update({"kernel": dom, "traffic": None, "peak_source": peak_src,
+        # measured DRAM bytes per launch (dram__bytes_read.sum + dram__bytes_write.sum of one `ncu --set full`
+        # capture of this workload, profiles/r1_traffic.json); only valid for the configuration it was captured on
+        traffic = None
+        tpath = os.path.join(ROOT, "profiles", "r1_traffic.json")
+        if os.path.exists(tpath):
+            tj = json.load(open(tpath))
+            if tj.get("workload") == [args.crystals, args.atoms, args.cap, args.radius, args.precision]:
+                traffic = tj["bytes_per_launch"].get(dom)
+                for kname, kv in kernels.items():
+                    kv["traffic"] = tj["bytes_per_launch"].get(kname)
+        roof = dict(kernels[dom]); roof.update({"kernel": dom, "traffic": traffic, "peak_source": peak_src,
                                                 "share_of_step": br[dom]["ms_per_step"] / sum(v["ms_per_step"] for v in br.values())})
         line = {"metric": "crystals_per_sec_full_trajectory", "value": value, "unit": "crystals/s", "n_gpus": world,
                 "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": ms_per_step, "higher_is_better": True,

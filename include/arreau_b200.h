@@ -166,6 +166,16 @@ int arreau_message_fiber_norm(const void* kernels, int32_t kernels_f16, const fl
                               const float* conv_bias, const float* ln_w, const float* ln_b, int32_t num_atoms_total,
                               void* y, int32_t y_f16, float* x1, float* x2_debug, void* stream);
 
+/* The two launches of arreau_message_fiber_norm as separate entry points (same arguments; used for per-kernel timing):
+ * K4b gather: x1 = receiver-sorted CSR sums of kernels * h[src]; x1_f16_transposed != 0 (needs fp16 kernels) writes
+ * fp16 x1t[N,C,O] instead of f32 x1[N,O,C].  K5: fiber conv + bias + LayerNorm of x1 -> y. */
+int arreau_message_gather(const void* kernels, int32_t kernels_f16, const float* h, const int32_t* row_ptr,
+                          const int32_t* src, int32_t num_atoms_total, int32_t x1_f16_transposed, float* x1,
+                          void* stream);
+int arreau_fiber_norm(const float* x1, int32_t x1_f16_transposed, const float* fiber_kernel, const void* fiber_frag,
+                      const float* conv_bias, const float* ln_w, const float* ln_b, int32_t num_atoms_total, void* y,
+                      int32_t y_f16, float* x2_debug, void* stream);
+
 /* fiber_frag[L][C][32] (16 bytes each): the fp16 mma.sync B fragments of fiber_kernel[L,O,O,C] / O, one per
  * (layer, channel, lane) -- the operand of the tensor-core fiber conv of the fp16 path (64 KB per layer). */
 int arreau_fiber_frag_pack(const float* fiber_kernel, int32_t num_layers, void* fiber_frag, void* stream);
