@@ -20,7 +20,7 @@ i64 = C.c_int64
 f64 = C.c_double
 
 ERRORS = {-1: "ARREAU_ERR_BAD_SHAPE", -2: "ARREAU_ERR_UNSUPPORTED", -3: "ARREAU_ERR_WORKSPACE", -4: "ARREAU_ERR_NULL"}
-PRECISION_FP32, PRECISION_FP16 = 0, 1
+PRECISION_FP32, PRECISION_FP16, PRECISION_TF32 = 0, 1, 2
 
 
 class Weights(C.Structure):
@@ -100,7 +100,7 @@ SIGNATURES = {
     "arreau_train_layout": [i32, i32, i32, C.POINTER(TrainLayout)],
     "arreau_ponita_backward_workspace_bytes": [i32, i64, i32, i32],
     "arreau_ponita_backward": [vp, C.POINTER(TrainLayout), C.POINTER(Weights), C.POINTER(Workspace), vp, vp, vp, vp, vp,
-                               vp, vp, vp, vp, vp, vp, i32, i32, f64, vp, vp, vp, vp, i64, vp, vp],
+                               vp, vp, vp, vp, vp, vp, i32, i32, f64, vp, vp, vp, vp, i64, vp, i32, vp],
     "arreau_sgemm": [i32, i32, vp, i64, vp, i64, vp, i64, i32, i32, i64, C.c_float, vp, i32, vp, i64, vp],
     "arreau_fold_basis_w1": [vp, vp, vp, vp, vp],
     "arreau_moments": [vp, vp, i64, vp, vp, vp],

@@ -52,20 +52,28 @@ __device__ __forceinline__ void tile_fetch(const float* __restrict__ X, long lon
   }
 }
 
-template <bool KCONTIG>
+__device__ __forceinline__ float to_tf32(float x) {
+  uint32_t r;
+  asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(x));
+  return __uint_as_float(r);
+}
+
+template <bool KCONTIG, int PITCH = kSP, bool TF32 = false>
 __device__ __forceinline__ void tile_stage(float* __restrict__ S, int tid, const float4 (&r)[2]) {
 #pragma unroll
   for (int u = 0; u < 2; ++u) {
     const int v = tid + u * kGT;
+    float4 q = r[u];
+    if (TF32) q = make_float4(to_tf32(q.x), to_tf32(q.y), to_tf32(q.z), to_tf32(q.w));
     if (KCONTIG) {
       const int x = v >> 2, k = (v & 3) * 4;
-      S[(k + 0) * kSP + x] = r[u].x;
-      S[(k + 1) * kSP + x] = r[u].y;
-      S[(k + 2) * kSP + x] = r[u].z;
-      S[(k + 3) * kSP + x] = r[u].w;
+      S[(k + 0) * PITCH + x] = q.x;
+      S[(k + 1) * PITCH + x] = q.y;
+      S[(k + 2) * PITCH + x] = q.z;
+      S[(k + 3) * PITCH + x] = q.w;
     } else {
       const int k = v >> 5, x = (v & 31) * 4;
-      *reinterpret_cast<float4*>(S + k * kSP + x) = r[u];
+      *reinterpret_cast<float4*>(S + k * PITCH + x) = q;
     }
   }
 }
@@ -155,6 +163,109 @@ sgemm_kernel(const float* __restrict__ A, long long lda, const float* __restrict
   }
 }
 
+// TF32 variant of the same GEMM (ARREAU_PRECISION_TF32): identical tiling and operand staging (values rounded to
+// TF32 with cvt.rna on their way into shared memory), the inner product on mma.sync.m16n8k8 with fp32 accumulation.
+// 8 warps = 2 (M) x 4 (N); a warp owns a 64 x 32 block = 4 x 4 mma tiles.  Shared pitch 136: fragment loads
+// (address = k * 136 + column) hit 32 distinct banks.
+constexpr int kTP = 136;
+
+template <bool AK, bool BK>
+__global__ void __launch_bounds__(kGT)
+sgemm_tf32_kernel(const float* __restrict__ A, long long lda, const float* __restrict__ B, long long ldb, float* __restrict__ C,
+                  long long ldc, int M, int N, long long K, long long k_per_split, float alpha,
+                  const float* __restrict__ bias, int accumulate, float* __restrict__ partial) {
+  __shared__ __align__(16) float As[2][kBK * kTP];
+  __shared__ __align__(16) float Bs[2][kBK * kTP];
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31, g = lane >> 2, t = lane & 3;
+  const int wm = (warp & 1) * 64, wn = (warp >> 1) * 32;
+  const int m0 = blockIdx.y * kBM, n0 = blockIdx.x * kBN;
+  const long long kbeg = (long long)blockIdx.z * k_per_split;
+  const long long kend = (kbeg + k_per_split < K) ? kbeg + k_per_split : K;
+  float acc[4][4][4];
+#pragma unroll
+  for (int i = 0; i < 4; ++i)
+#pragma unroll
+    for (int j = 0; j < 4; ++j)
+#pragma unroll
+      for (int q = 0; q < 4; ++q) acc[i][j][q] = 0.f;
+  float4 ra[2], rb[2];
+  if (kbeg < kend) {
+    tile_fetch<AK>(A, lda, m0, M, kbeg, kend, tid, ra);
+    tile_fetch<BK>(B, ldb, n0, N, kbeg, kend, tid, rb);
+    tile_stage<AK, kTP, true>(As[0], tid, ra);
+    tile_stage<BK, kTP, true>(Bs[0], tid, rb);
+  }
+  __syncthreads();
+  int buf = 0;
+  for (long long k0 = kbeg; k0 < kend; k0 += kBK) {
+    const bool more = k0 + kBK < kend;
+    if (more) {
+      tile_fetch<AK>(A, lda, m0, M, k0 + kBK, kend, tid, ra);
+      tile_fetch<BK>(B, ldb, n0, N, k0 + kBK, kend, tid, rb);
+    }
+    const float* a = As[buf];
+    const float* b = Bs[buf];
+#pragma unroll
+    for (int ks = 0; ks < kBK; ks += 8) {
+      uint32_t af[4][4], bf[4][2];
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        const float* p = a + (ks + t) * kTP + wm + i * 16 + g;
+        af[i][0] = __float_as_uint(p[0]);
+        af[i][1] = __float_as_uint(p[8]);
+        af[i][2] = __float_as_uint(p[4 * kTP]);
+        af[i][3] = __float_as_uint(p[4 * kTP + 8]);
+      }
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const float* p = b + (ks + t) * kTP + wn + j * 8 + g;
+        bf[j][0] = __float_as_uint(p[0]);
+        bf[j][1] = __float_as_uint(p[4 * kTP]);
+      }
+#pragma unroll
+      for (int i = 0; i < 4; ++i)
+#pragma unroll
+        for (int j = 0; j < 4; ++j)
+          asm volatile(
+              "mma.sync.aligned.m16n8k8.row.col.f32.tf32.tf32.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+              : "+f"(acc[i][j][0]), "+f"(acc[i][j][1]), "+f"(acc[i][j][2]), "+f"(acc[i][j][3])
+              : "r"(af[i][0]), "r"(af[i][1]), "r"(af[i][2]), "r"(af[i][3]), "r"(bf[j][0]), "r"(bf[j][1]));
+    }
+    if (more) {
+      tile_stage<AK, kTP, true>(As[buf ^ 1], tid, ra);
+      tile_stage<BK, kTP, true>(Bs[buf ^ 1], tid, rb);
+    }
+    __syncthreads();
+    buf ^= 1;
+  }
+  const bool split = gridDim.z > 1;
+  float* out = split ? partial + (size_t)blockIdx.z * M * N : C;
+  const long long ldo = split ? (long long)N : ldc;
+#pragma unroll
+  for (int i = 0; i < 4; ++i)
+#pragma unroll
+    for (int hrow = 0; hrow < 2; ++hrow) {
+      const int m = m0 + wm + i * 16 + g + hrow * 8;
+      if (m >= M) continue;
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const int n = n0 + wn + j * 8 + 2 * t;
+        if (n >= N) continue;
+        float2 v = make_float2(acc[i][j][hrow * 2], acc[i][j][hrow * 2 + 1]);
+        float* p = out + (long long)m * ldo + n;
+        if (!split) {
+          v.x *= alpha; v.y *= alpha;
+          if (bias) { v.x += bias[n]; v.y += bias[n + 1]; }
+          if (accumulate) {
+            const float2 c = *reinterpret_cast<const float2*>(p);
+            v.x += c.x; v.y += c.y;
+          }
+        }
+        *reinterpret_cast<float2*>(p) = v;
+      }
+    }
+}
+
 // second stage of every split reduction: out[i] (=|+=) alpha * sum_s partial[s][i] (fixed order)
 __global__ void reduce_partials_kernel(const float* __restrict__ partial, int splits, long long n, long long ldo, int ncols,
                                        float alpha, int accumulate, float* __restrict__ out) {
@@ -172,6 +283,7 @@ struct Gemm {
   float* partial;          // split-K scratch
   size_t partial_floats;
   int sms;
+  bool tf32 = false;       // tensor-core TF32 products (fp32 accumulation) instead of fp32 FFMA
 };
 
 // op: C[M,N] (=|+=) alpha A B (+bias).  Returns ARREAU_* / cudaError.
@@ -192,8 +304,12 @@ int gemm(const Gemm& g, const float* A, long long lda, const float* B, long long
   splits = (int)((K + kps - 1) / kps);
   if (splits < 1) splits = 1;
   dim3 grid((N + kBN - 1) / kBN, (M + kBM - 1) / kBM, splits);
-  sgemm_kernel<AK, BK><<<grid, kGT, 0, g.s>>>(A, lda, B, ldb, C, ldc, M, N, K, kps, alpha, splits == 1 ? bias : nullptr,
-                                              accumulate ? 1 : 0, g.partial);
+  if (g.tf32)
+    sgemm_tf32_kernel<AK, BK><<<grid, kGT, 0, g.s>>>(A, lda, B, ldb, C, ldc, M, N, K, kps, alpha,
+                                                     splits == 1 ? bias : nullptr, accumulate ? 1 : 0, g.partial);
+  else
+    sgemm_kernel<AK, BK><<<grid, kGT, 0, g.s>>>(A, lda, B, ldb, C, ldc, M, N, K, kps, alpha, splits == 1 ? bias : nullptr,
+                                                accumulate ? 1 : 0, g.partial);
   CUDA_LAUNCH_CHECK();
   if (splits > 1) {
     if (bias) return ARREAU_ERR_UNSUPPORTED;
@@ -734,6 +850,9 @@ extern "C" int arreau_sgemm(int32_t a_k_contiguous, int32_t b_k_contiguous, cons
   if (!A || !B || !C) return ARREAU_ERR_NULL;
   if (M < 0 || N < 0 || K < 0 || (N & 3) || (lda & 3) || (ldb & 3) || (ldc & 3)) return ARREAU_ERR_BAD_SHAPE;
   Gemm g{(cudaStream_t)stream, partial, partial ? (size_t)partial_floats : 0, sm_count()};
+  g.tf32 = (a_k_contiguous & 2) || (b_k_contiguous & 2);     // bit 1 of either flag selects the TF32 tensor-core variant
+  a_k_contiguous &= 1;
+  b_k_contiguous &= 1;
   if (a_k_contiguous && b_k_contiguous) return gemm<true, true>(g, A, lda, B, ldb, C, ldc, M, N, K, alpha, bias, accumulate);
   if (a_k_contiguous) return gemm<true, false>(g, A, lda, B, ldb, C, ldc, M, N, K, alpha, bias, accumulate);
   if (b_k_contiguous) return gemm<false, true>(g, A, lda, B, ldb, C, ldc, M, N, K, alpha, bias, accumulate);
@@ -746,7 +865,8 @@ extern "C" int arreau_ponita_backward(const float* params, const arreau_train_la
                                       const double* dist, const double* dir, const double* lattice,
                                       const int32_t* atom_offset, const int32_t* crystal_of_atom, int32_t N, int32_t G,
                                       double radius, const float* dlogits, const float* dscore, const float* dlen0,
-                                      float* workspace, int64_t workspace_bytes, float* grads, void* stream) {
+                                      float* workspace, int64_t workspace_bytes, float* grads, int32_t precision,
+                                      void* stream) {
   if (!params || !lay || !w || !ws || !fold_table || !grads || !workspace) return ARREAU_ERR_NULL;
   if (N < 0 || G < 0) return ARREAU_ERR_BAD_SHAPE;
   if (N == 0) return ARREAU_OK;
@@ -760,7 +880,9 @@ extern "C" int arreau_ponita_backward(const float* params, const arreau_train_la
   BwdBuffers b = carve(workspace, N, Ecap, xl_pitch);
   if ((int64_t)(b.total * sizeof(float)) > workspace_bytes) return ARREAU_ERR_WORKSPACE;
   cudaStream_t s = (cudaStream_t)stream;
+  if (precision != ARREAU_PRECISION_FP32 && precision != ARREAU_PRECISION_TF32) return ARREAU_ERR_UNSUPPORTED;
   Gemm g{s, b.partial, kPartialFloats, sm_count()};
+  g.tf32 = precision == ARREAU_PRECISION_TF32;
   const long long Re = Ecap * kO, Rn = (long long)N * kO;
   const size_t node_elems = (size_t)N * kO * kC, layer_kernel_elems = (size_t)Ecap * kO * kC;
   const int32_t* num_edges_ptr = row_ptr + N;

@@ -128,7 +128,12 @@ class TrainEngine:
     """One batch topology (atoms per crystal) on one GPU."""
 
     def __init__(self, params: FlatParams, tables: DiffusionTables, fourier_w, ori_grid, num_atoms: Sequence[int],
-                 radius: float, max_neighbors: int, device="cuda"):
+                 radius: float, max_neighbors: int, device="cuda", backward_precision: str = "fp32"):
+        """backward_precision: "fp32" (FFMA GEMMs: the parity path) or "tf32" (tensor-core GEMMs with fp32
+        accumulation in the backward pass; the forward stays fp32)."""
+        if backward_precision not in ("fp32", "tf32"):
+            raise ValueError("backward_precision must be 'fp32' or 'tf32'")
+        self.backward_precision = _lib.PRECISION_TF32 if backward_precision == "tf32" else _lib.PRECISION_FP32
         self.p, self.tabs = params, tables
         self.device = dev = torch.device(device)
         self.ori = (ori_grid.detach() if isinstance(ori_grid, torch.Tensor) else torch.as_tensor(np.asarray(ori_grid))) \
@@ -217,7 +222,8 @@ class TrainEngine:
                   self.fold.data_ptr(), e.x.data_ptr(), e.vec.data_ptr(), e.row_ptr.data_ptr(), e.src.data_ptr(),
                   e.dst.data_ptr(), e.dist.data_ptr(), e.dir.data_ptr(), e.lattice.data_ptr(), e.atom_offset.data_ptr(),
                   e.crystal_of_atom.data_ptr(), e.N, e.G, e.radius, dlogits.data_ptr(), dscore.data_ptr(),
-                  dlen0.data_ptr(), self._bwd_ws.data_ptr(), self._bwd_ws.numel() * 4, self.p.grad.data_ptr(), e.stream)
+                  dlen0.data_ptr(), self._bwd_ws.data_ptr(), self._bwd_ws.numel() * 4, self.p.grad.data_ptr(),
+                  self.backward_precision, e.stream)
         return self.p.grad
 
     # ------------------------------------------------------------------ the step

@@ -214,7 +214,9 @@ def run_train(args):
     broadcast_parameters(p.data)
     cr = make_training_batch(args.crystals if args.crystals != 1024 else 270, seed=100 + rank)
     G, N = cr.num_crystals, cr.total_atoms
-    te = TrainEngine(p, build_tables(T_STEPS, Z), w["fourier_w"], w["ori_grid"], cr.num_atoms, args.radius, args.cap, device=dev)
+    bwd_prec = "fp32" if args.precision == "fp32" else "tf32"
+    te = TrainEngine(p, build_tables(T_STEPS, Z), w["fourier_w"], w["ori_grid"], cr.num_atoms, args.radius, args.cap, device=dev,
+                     backward_precision=bwd_prec)
     opt = FusedAdam(p, lr=3e-4, max_grad_norm=0.5)
     from arreau_b200.diffusion.lattice_helpers import lattice_from_params
     lat0 = lattice_from_params(torch.as_tensor(cr.lengths).to(dev), torch.as_tensor(cr.angles).to(dev))
@@ -266,7 +268,8 @@ def run_train(args):
         E = te.eng.num_edges()
         print(json.dumps({"metric": "train_crystals_per_sec", "value": world * G / (ms * 1e-3), "unit": "crystals/s",
                           "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": ms,
-                          "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
+                          "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+                          "dtype": "f32" if bwd_prec == "fp32" else "f32 forward, tf32 backward GEMMs",
                           "data": "synthetic", "impl": "ours",
                           "config": {"workload": f"C5: training step (score-matching + D3PM + lattice loss), {G} crystals "
                                                  f"/ {N} atoms / {E} edges per GPU, max_neighbors {args.cap}, "

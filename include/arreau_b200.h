@@ -36,6 +36,7 @@ extern "C" {
 
 #define ARREAU_PRECISION_FP32 0 /* FFMA2 SIMT GEMMs, parity <= 1e-4 of the fp64 reference          */
 #define ARREAU_PRECISION_FP16 1 /* tcgen05 fp16 operands, fp32 accumulate; tolerance stated in tests */
+#define ARREAU_PRECISION_TF32 2 /* training backward only: TF32 tensor-core GEMMs, fp32 accumulate          */
 
 /* Library/ABI version and the compile-time model dimensions (O=16, C=128, D=256, W=4, L=5). */
 int arreau_abi_version(void);
@@ -402,18 +403,21 @@ int64_t arreau_ponita_backward_workspace_bytes(int32_t num_atoms_total, int64_t 
  * order (grads is overwritten).  w / ws: the packed weights and the workspace of the forward pass that produced the
  * outputs (ws->h_debug, x1_debug, x2_debug, kernels must hold that pass; fp32 path).  fold_table[258] i32: monomial
  * index of each PolynomialFeatures(3) column.  Deterministic: split reductions with a fixed-order second stage and a
- * sender-side gather for the transposed message pass, no atomics. */
+ * sender-side gather for the transposed message pass, no atomics.  precision: ARREAU_PRECISION_FP32 (FFMA GEMMs,
+ * the parity path) or ARREAU_PRECISION_TF32 (every GEMM of the backward on mma.sync TF32 tensor cores with fp32
+ * accumulation: operands rounded to 10 mantissa bits, gradients within ~1e-3 of the fp32 path). */
 int arreau_ponita_backward(const float* params, const arreau_train_layout_t* layout, const arreau_weights* w,
                            const arreau_workspace* ws, const int32_t* fold_table, const float* x, const float* vec,
                            const int32_t* row_ptr, const int32_t* src, const int32_t* dst, const double* dist,
                            const double* dir, const double* lattice, const int32_t* atom_offset,
                            const int32_t* crystal_of_atom, int32_t num_atoms_total, int32_t num_crystals, double radius,
                            const float* dlogits, const float* dscore, const float* dlen0, float* workspace,
-                           int64_t workspace_bytes, float* grads, void* stream);
+                           int64_t workspace_bytes, float* grads, int32_t precision, void* stream);
 
 /* The fp32 GEMM the backward pass is built from: C[M,N] (=|+=) alpha * A * B (+ bias[n]).  a_k_contiguous: A is stored
  * [M][K] (else [K][M]); b_k_contiguous: B is stored [N][K] (else [K][N]).  Long reductions (K) are split over CTAs
- * into `partial` and summed in a fixed order.  Exposed for the parity tests. */
+ * into `partial` and summed in a fixed order.  Bit 1 of either flag (value 2 or 3) selects the TF32 tensor-core variant.
+ * Exposed for the parity tests. */
 int arreau_sgemm(int32_t a_k_contiguous, int32_t b_k_contiguous, const float* A, int64_t lda, const float* B, int64_t ldb,
                  float* C, int64_t ldc, int32_t M, int32_t N, int64_t K, float alpha, const float* bias,
                  int32_t accumulate, float* partial, int64_t partial_floats, void* stream);
