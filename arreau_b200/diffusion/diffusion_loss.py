@@ -71,6 +71,7 @@ class DiffusionLoss(torch.nn.Module):
         self._engine = None
         self._engine_key = None
         self._train_engines = {}
+        self.backward_precision = "fp32"      # "tf32": tensor-core GEMMs in the backward pass (training.py)
         self.coord_loss_weight = self.atom_type_loss_weight = self.lattice_loss_weight = 1
 
     # -- engine cache: one per (model weights, topology) --------------------------------------------
@@ -94,11 +95,12 @@ class DiffusionLoss(torch.nn.Module):
         flat = net.flat if getattr(net, "flat", None) is not None and net.flat.device == torch.device(device) \
             else net.flatten_parameters(device)
         na = tuple(int(v) for v in torch.as_tensor(num_atoms).reshape(-1).tolist())
-        key = (id(flat), na)
+        key = (id(flat), na, self.backward_precision)
         te = self._train_engines.pop(key, None)
         if te is None:
             fw = t_emb_weights.gaussian_fourier_proj_w if hasattr(t_emb_weights, "gaussian_fourier_proj_w") else t_emb_weights
-            te = TrainEngine(flat, self.tables, fw, net.ori_grid, na, self.cutoff, self.max_neighbors, device=device)
+            te = TrainEngine(flat, self.tables, fw, net.ori_grid, na, self.cutoff, self.max_neighbors, device=device,
+                             backward_precision=self.backward_precision)
             while len(self._train_engines) >= max_cached:
                 self._train_engines.pop(next(iter(self._train_engines)))
         self._train_engines[key] = te

@@ -36,7 +36,7 @@ class _ConvParams(nn.Module):
         self.kernel = nn.Linear(basis, hidden, bias=False)
         self.fiber_kernel = nn.Linear(basis, hidden, bias=False)
         self.bias = nn.Parameter(torch.zeros(hidden))
-        self.register_buffer("callibrated", torch.tensor(True))
+        self.register_buffer("callibrated", torch.tensor(False))   # conv.py:103; set by the callibrate pass
 
 
 class _ConvNextParams(nn.Module):

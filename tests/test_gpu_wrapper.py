@@ -75,3 +75,24 @@ def test_wrapper_training_loop(device, weights_npz):
             opt.step()
             losses.append(loss.item())
     assert losses[-1] < losses[0], losses
+
+
+def test_fit_loop_on_a_tiny_dataset(device, weights_npz, tmp_path):
+    """arreau_b200.train.fit (the training entry point without Lightning): dataset file -> collate -> callibrate ->
+    steps with the TF32 backward -> epoch metric; the loss falls over a few epochs on a tiny dataset."""
+    from arreau_b200.diffusion.lattice_dataset import CrystalDataset, save_dataset_npz
+    from arreau_b200.lightning_wrappers.diffusion import PONITA_DIFFUSION
+    from arreau_b200.synthetic import make_crystals
+    from arreau_b200.train import default_args, fit
+    cr = make_crystals(24, 2, 10, seed=9)
+    off = np.concatenate([[0], np.cumsum(cr.num_atoms)])
+    zs = [cr.types[off[i]:off[i + 1]] % 5 + 1 for i in range(24)]
+    frac = [cr.frac[off[i]:off[i + 1]] for i in range(24)]
+    lat = np.stack([np.diag(cr.lengths[i]) for i in range(24)])
+    ds = CrystalDataset([save_dataset_npz(str(tmp_path / "tiny"), zs, lat, frac)])
+    torch.manual_seed(0)
+    args = default_args(lr=2e-3, epochs=6, warmup=1, layer_scale=1e-6)
+    model = PONITA_DIFFUSION(args, ds.z_table)
+    hist = fit(model, ds, epochs=6, batch_size=12, device=device, backward_precision="tf32", log=lambda *_: None)
+    assert len(hist) == 6 and all(np.isfinite(hist)) and min(hist[3:]) < hist[0], hist
+    assert all(bool(l.conv.callibrated) for l in model.model.interaction_layers)

@@ -258,3 +258,27 @@ def test_atomic_symbols_to_indices():
     from arreau_b200.tools.atomic_number_table import AtomicNumberTable, atomic_symbols_to_indices
     zt = AtomicNumberTable(list(range(1, 90)) + [2001])
     assert atomic_symbols_to_indices(zt, ["H", "C", "Ac"]).tolist() == [0, 5, 88]
+
+
+def test_crystal_dataset_and_collate(tmp_path):
+    """Input pipeline (lattice_dataset.py): dataset file -> items -> flat batch, sharded over 2 ranks."""
+    from arreau_b200.diffusion.lattice_dataset import CrystalDataset, batches, collate_crystals, save_dataset_npz
+    from arreau_b200.synthetic import make_crystals
+    cr = make_crystals(7, 1, 9, seed=2)
+    off = np.concatenate([[0], np.cumsum(cr.num_atoms)])
+    zs = [cr.types[off[i]:off[i + 1]] + 1 for i in range(7)]                    # atomic numbers 1..89
+    frac = [cr.frac[off[i]:off[i + 1]] for i in range(7)]
+    lat = np.stack([np.diag(cr.lengths[i]) for i in range(7)])
+    path = save_dataset_npz(str(tmp_path / "alexandria_tiny"), zs, lat, frac)
+    ds = CrystalDataset([path])
+    assert len(ds) == 7 and ds.z_table.zs[-1] == 2001 and len(ds.z_table) == len(set(np.concatenate(zs))) + 1
+    b = collate_crystals([ds[i] for i in range(7)])
+    assert b.X0.shape == (cr.total_atoms, 3) and b.L0.shape == (21, 3) and b.num_atoms.tolist() == cr.num_atoms.tolist()
+    assert np.array_equal(b.batch.numpy(), np.repeat(np.arange(7), cr.num_atoms))
+    assert np.array_equal(np.asarray(ds.z_table.zs)[b.A0.numpy()], np.concatenate(zs))
+    assert np.allclose(b.pos.numpy(), cr.frac * cr.lengths[b.batch.numpy()])
+    seen = []
+    for rank in range(2):
+        for bb in batches(ds, 2, shuffle=True, seed=3, rank=rank, world=2):
+            seen.append(int(bb.num_atoms.shape[0]))
+    assert sum(seen) == 7
