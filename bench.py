@@ -28,6 +28,9 @@ import numpy as np
 
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
+# NCCL writes its version banner to stdout (NCCL_DEBUG=VERSION in this image); stdout must carry the ONE JSON line
+if os.environ.get("NCCL_DEBUG", "VERSION").upper() == "VERSION":
+    os.environ["NCCL_DEBUG"] = "WARN"
 
 T_STEPS = 1000          # Makefile:7 num_timesteps -> 999 denoise steps per trajectory
 Z = 90
