@@ -448,53 +448,49 @@ __global__ void fiber_frag_kernel(const float* __restrict__ fk, uint4* __restric
 constexpr int kFiberGroup = 16;                                   // atoms per tile (the M of the mma)
 constexpr int kFiberRowBytes = kC * kO * 2 + 16;                  // one atom's [c][o] fp16 block + 16 B: conflict-free fragment loads
 constexpr int kFiberTileBytes = kFiberGroup * kFiberRowBytes;
-constexpr size_t kFiberSmem = (size_t)kC * 32 * sizeof(uint4) + 2 * (size_t)kFiberTileBytes +
-                              (size_t)kFiberMmaWarps * 32 * 16 * sizeof(float) + 3 * kC * sizeof(float) + 64;
+constexpr size_t kFiberSmem = (size_t)kFiberTileBytes + (size_t)kFiberMmaWarps * 32 * 16 * sizeof(float) +
+                              3 * kC * sizeof(float) + 64;      // 84 KB: two CTAs per SM
 
-__global__ void __launch_bounds__(kFiberMmaWarps * 32, 1)
+__global__ void __launch_bounds__(kFiberMmaWarps * 32, 2)
 fiber_norm_mma_kernel(const __half* __restrict__ x1t, const uint4* __restrict__ fk_frag, const float* __restrict__ bias,
                       const float* __restrict__ ln_w, const float* __restrict__ ln_b, int N, __half* __restrict__ y,
                       float* __restrict__ x2_dbg) {
-  // Persistent CTA of 8 warps; a tile = 16 atoms (64 KB of x1t, contiguous) arrives by bulk copies into one of two
-  // shared buffers while the previous tile is processed; warp w owns channels 16 w .. 16 w + 15 of the tile.
+  // Persistent CTAs of 8 warps, two per SM (one loads while the other computes); a tile = 16 atoms (64 KB of x1t,
+  // contiguous) arrives by bulk copies; warp w owns channels 16 w .. 16 w + 15 of the tile.  The B fragments (64 KB
+  // per layer, the same for every tile) are read through L1.
   extern __shared__ __align__(128) uint8_t fsm[];
-  uint4* s_frag = reinterpret_cast<uint4*>(fsm);                                 // [kC][32]
-  uint8_t* s_a = fsm + (size_t)kC * 32 * sizeof(uint4);                          // [2][16 atoms][kFiberRowBytes]
-  float* s_stats = reinterpret_cast<float*>(s_a + 2 * (size_t)kFiberTileBytes);  // [warps][32 lanes][16]
+  const uint4* __restrict__ s_frag = fk_frag;                                    // [kC][32], L1 resident
+  uint8_t* s_a = fsm;                                                            // [16 atoms][kFiberRowBytes]
+  float* s_stats = reinterpret_cast<float*>(s_a + (size_t)kFiberTileBytes);      // [warps][32 lanes][16]
   float* s_bias = s_stats + kFiberMmaWarps * 32 * 16;
   float* s_g = s_bias + kC;
   float* s_b = s_g + kC;
-  uint64_t* bars = reinterpret_cast<uint64_t*>(s_b + kC);                        // full[2]
-  for (int i = threadIdx.x; i < kC * 32; i += blockDim.x) s_frag[i] = fk_frag[i];
+  uint64_t* bars = reinterpret_cast<uint64_t*>(s_b + kC);                        // full
   for (int i = threadIdx.x; i < kC; i += blockDim.x) { s_bias[i] = bias[i]; s_g[i] = ln_w[i]; s_b[i] = ln_b[i]; }
   if (threadIdx.x == 0) {
     tc::mbar_init(&bars[0], 1);
-    tc::mbar_init(&bars[1], 1);
     tc::fence_barrier_init();
   }
   __syncthreads();
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, g = lane >> 2, t = lane & 3;
   const int groups = (N + kFiberGroup - 1) / kFiberGroup;
-  auto issue = [&](int grp, int buf) {        // thread 0: the valid atoms of tile grp -> buffer buf
+  auto issue = [&](int grp) {                 // thread 0: the valid atoms of tile grp
     const int atom0 = grp * kFiberGroup;
     const int n = min(kFiberGroup, N - atom0);
-    tc::mbar_expect_tx(&bars[buf], (uint32_t)n * (kC * kO * 2));
+    tc::mbar_expect_tx(&bars[0], (uint32_t)n * (kC * kO * 2));
     for (int a = 0; a < n; ++a)
-      tc::bulk_g2s(s_a + (size_t)buf * kFiberTileBytes + (size_t)a * kFiberRowBytes, x1t + (size_t)(atom0 + a) * kC * kO,
-                   kC * kO * 2, &bars[buf]);
+      tc::bulk_g2s(s_a + (size_t)a * kFiberRowBytes, x1t + (size_t)(atom0 + a) * kC * kO, kC * kO * 2, &bars[0]);
   };
-  if (threadIdx.x == 0 && (int)blockIdx.x < groups) issue(blockIdx.x, 0);
   int it = 0;
   for (int grp = blockIdx.x; grp < groups; grp += gridDim.x, ++it) {
-    const int buf = it & 1;
-    if (threadIdx.x == 0 && grp + (int)gridDim.x < groups) {     // buffer buf ^ 1 was released by the barrier that ended the previous tile
+    if (threadIdx.x == 0) {                   // the buffer was released by the barrier that ended the previous tile
       tc::fence_proxy_async();
-      issue(grp + gridDim.x, buf ^ 1);
+      issue(grp);
     }
-    tc::mbar_wait(&bars[buf], (it >> 1) & 1);
+    tc::mbar_wait(&bars[0], it & 1);
     const int atom0 = grp * kFiberGroup;
     const bool v0 = atom0 + g < N, v1 = atom0 + g + 8 < N;
-    const uint8_t* a0p = s_a + (size_t)buf * kFiberTileBytes + (size_t)g * kFiberRowBytes + 4 * t;
+    const uint8_t* a0p = s_a + (size_t)g * kFiberRowBytes + 4 * t;
     const uint8_t* a1p = a0p + 8 * (size_t)kFiberRowBytes;
     auto load_a = [&](int c, uint32_t (&a)[4]) {
       a[0] = *reinterpret_cast<const uint32_t*>(a0p + c * (kO * 2));
@@ -512,7 +508,7 @@ fiber_norm_mma_kernel(const __half* __restrict__ x1t, const uint4* __restrict__ 
       const int c = warp * (kC / kFiberMmaWarps) + cc;
       uint32_t a[4];
       load_a(c, a);
-      const uint4 b = s_frag[c * 32 + lane];
+      const uint4 b = __ldg(s_frag + c * 32 + lane);
       float d0[4], d1[4];
       mma16816(d0, a[0], a[1], a[2], a[3], b.x, b.y);
       mma16816(d1, a[0], a[1], a[2], a[3], b.z, b.w);
@@ -565,7 +561,7 @@ fiber_norm_mma_kernel(const __half* __restrict__ x1t, const uint4* __restrict__ 
           const int c = cb * 8 + j + jj;
           uint32_t a[4];
           load_a(c, a);
-          const uint4 b = s_frag[c * 32 + lane];
+          const uint4 b = __ldg(s_frag + c * 32 + lane);
           float d0[4], d1[4];
           mma16816(d0, a[0], a[1], a[2], a[3], b.x, b.y);
           mma16816(d1, a[0], a[1], a[2], a[3], b.z, b.w);
@@ -1020,7 +1016,7 @@ extern "C" int arreau_fiber_norm(const float* x1, int32_t x1_f16_transposed, con
       attr_set = true;
     }
     const int groups = (N + kFiberGroup - 1) / kFiberGroup;
-    const int grid = groups < num_sms() ? groups : num_sms();
+    const int grid = groups < 2 * num_sms() ? groups : 2 * num_sms();
     fiber_norm_mma_kernel<<<grid, kFiberMmaWarps * 32, kFiberSmem, s>>>((const __half*)x1, (const uint4*)fiber_frag, conv_bias,
                                                                         ln_w, ln_b, N, (__half*)y, x2_debug);
   } else {
