@@ -27,13 +27,13 @@ class Weights(C.Structure):
     _fields_ = [(n, vp) for n in (
         "ori", "w_embed_t", "w1m_t", "w2_t", "b2", "wk_t", "fiber_kernel", "fiber_frag", "conv_bias", "ln_w", "ln_b",
         "mlp_w1_t", "mlp_b1", "mlp_w2_t", "mlp_b2", "layer_scale", "wr_t", "br",
-        "edge_w1_img", "edge_w_img", "mlp_w_img")] + [
+        "edge_w1_img", "edge_w_img", "mlp_w_img", "readout_v", "readout_bias")] + [
         ("num_scalar", i32), ("num_vec", i32), ("num_states", i32), ("reserved", i32)]
 
 
 class Workspace(C.Structure):
     _fields_ = [("h", vp), ("y", vp), ("kernels", vp), ("acc", vp), ("x1", vp), ("x1_debug", vp), ("x2_debug", vp),
-                ("h_debug", vp), ("edge_capacity", i64), ("onehot_types", vp)]
+                ("h_debug", vp), ("edge_capacity", i64), ("onehot_types", vp), ("pool", vp)]
 
 
 class StepArgs(C.Structure):
@@ -82,6 +82,9 @@ SIGNATURES = {
     "arreau_convnext_mlp_f32": [vp, vp, vp, vp, vp, vp, i64, vp, vp],
     "arreau_convnext_mlp_f16": [vp, vp, vp, vp, vp, i64, vp, vp],
     "arreau_readout_accumulate": [vp, vp, vp, vp, i32, i32, i32, vp, vp],
+    "arreau_node_embed_pooled": [vp, vp, i32, vp, vp, vp, i32, i32, i32, vp, vp, vp],
+    "arreau_convnext_mlp_f16_pooled": [vp, vp, vp, vp, vp, i64, vp, vp, vp, vp],
+    "arreau_readout_pooled": [vp, vp, vp, i32, i32, i32, vp, vp],
     "arreau_readout_finalize": [vp, vp, i32, i32, i32, i32, vp, vp, vp, vp],
     "arreau_ponita_forward": [C.POINTER(Weights), C.POINTER(Workspace), i32, vp, vp, vp, vp, vp, vp, vp, vp, vp,
                               i32, i32, f64, vp, vp, vp, vp],

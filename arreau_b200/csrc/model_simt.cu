@@ -102,7 +102,7 @@ constexpr int kMaxVec = 8;
 __global__ void __launch_bounds__(kEmbedNodes * 32)
 node_embed_kernel(const float* __restrict__ x, const float* __restrict__ vec, const float* __restrict__ w_t,
                   const float* __restrict__ ori, const int64_t* __restrict__ types, int Z, int N, int F, int V,
-                  float* __restrict__ h) {
+                  float* __restrict__ h, float* __restrict__ pool) {
   extern __shared__ float sm[];
   float* xs = sm;                                   // [kEmbedNodes][F]
   float* dots = sm + kEmbedNodes * F;               // [kEmbedNodes][V][kO]
@@ -135,6 +135,10 @@ node_embed_kernel(const float* __restrict__ x, const float* __restrict__ vec, co
   for (int v = 0; v < kMaxVec; ++v)
     wv[v] = v < V ? __ldg(reinterpret_cast<const float4*>(w_t + (size_t)(F + v) * kC + lane * 4)) : make_float4(0.f, 0.f, 0.f, 0.f);
   float* hp = h + (size_t)(b0 + a) * kO * kC + lane * 4;
+  // optional orientation-pooled copy for the pooled read-out (pool[b][0] = mean_o h, pool[b][1+d] = (1/O) sum_o ori[o][d] h)
+  float4 pq[4];
+#pragma unroll
+  for (int q = 0; q < 4; ++q) pq[q] = make_float4(0.f, 0.f, 0.f, 0.f);
 #pragma unroll 4
   for (int o = 0; o < kO; ++o) {
     float4 r = s;
@@ -145,6 +149,22 @@ node_embed_kernel(const float* __restrict__ x, const float* __restrict__ vec, co
         r.x = fmaf(dv, wv[v].x, r.x); r.y = fmaf(dv, wv[v].y, r.y); r.z = fmaf(dv, wv[v].z, r.z); r.w = fmaf(dv, wv[v].w, r.w);
       }
     *reinterpret_cast<float4*>(hp + o * kC) = r;
+    if (pool) {
+      pq[0].x += r.x; pq[0].y += r.y; pq[0].z += r.z; pq[0].w += r.w;
+#pragma unroll
+      for (int d = 0; d < 3; ++d) {
+        const float od = __ldg(ori + 3 * o + d);
+        pq[1 + d].x = fmaf(od, r.x, pq[1 + d].x); pq[1 + d].y = fmaf(od, r.y, pq[1 + d].y);
+        pq[1 + d].z = fmaf(od, r.z, pq[1 + d].z); pq[1 + d].w = fmaf(od, r.w, pq[1 + d].w);
+      }
+    }
+  }
+  if (pool) {
+    constexpr float inv = 1.0f / kO;
+    float* pp = pool + (size_t)(b0 + a) * 4 * kC + lane * 4;
+#pragma unroll
+    for (int q = 0; q < 4; ++q)
+      *reinterpret_cast<float4*>(pp + q * kC) = make_float4(pq[q].x * inv, pq[q].y * inv, pq[q].z * inv, pq[q].w * inv);
   }
 }
 
@@ -879,6 +899,88 @@ readout_accumulate_kernel(const float* __restrict__ h, const float* __restrict__
   }
 }
 
+// Pooled read-out of all layers in one pass (fp16 tensor path).  pool[k][b][4][C], k = 0..L, holds the orientation-pooled
+// features after the embedding (k = 0, node_embed_kernel) and the pooled residual UPDATE of interaction layer k
+// (k = 1..L, epilogue of convnext_mlp_tc_kernel): [mean_o . | (1/O) sum_o ori[o][d] ., d = 0..2].  The read-out Linear
+// commutes with the pooling (to_from_sphere.py:10-14) and the feature after layer l is the sum of entries 0..l, so
+//   mean_l read_out_l(h_l) = sum_k V_k pool[k] + bias,   V_k = (1/L) sum_{l >= max(k,1)} Wr_l
+// with V_k[C][96] and bias[96] combined once on the host (weights.py) in the column layout of acc[N][Z+6]:
+// columns 0..Z-1 logits, Z..Z+2 the score vector (weight row Z applied to pool[.][1+d]), Z+3..Z+5 length channels.
+// Persistent CTAs; per k the 48 KB matrix sits in shared memory, 16-atom groups stream through a cp.async double
+// buffer, thread j owns output column j (warps 0..2; the three score columns are recomputed by warp 3 on the vector
+// part), acc is updated in place in a fixed order (deterministic).
+constexpr int kPoolAtoms = 16;
+constexpr int kPoolCols = 96;
+constexpr int kPoolSmem = (kC * kPoolCols + 2 * kPoolAtoms * 4 * kC) * (int)sizeof(float);
+
+__global__ void __launch_bounds__(kC)
+readout_pooled_kernel(const float* __restrict__ pool, const float* __restrict__ v, const float* __restrict__ bias, int N,
+                      int Z, int entries, float* __restrict__ acc) {
+  extern __shared__ __align__(16) float rp_sm[];
+  float* const vs = rp_sm;                                  // [kC][kPoolCols]
+  float* const ps = rp_sm + kC * kPoolCols;                 // [2][kPoolAtoms][4][kC]
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int groups = (N + kPoolAtoms - 1) / kPoolAtoms;
+  // column and pooled part of this thread
+  const bool vec_thread = warp == 3;
+  const bool active = vec_thread ? lane < 3 : !(tid >= Z && tid < Z + 3);
+  const int col = vec_thread ? Z + (lane < 3 ? lane : 0) : tid;
+  const int part = vec_thread ? 1 + (lane < 3 ? lane : 0) : 0;
+  auto load_group = [&](int k, int g, int buf) {
+    const int b0 = g * kPoolAtoms;
+    const int nb = min(kPoolAtoms, N - b0);
+    const float* src = pool + ((size_t)k * N + b0) * 4 * kC;
+    float* dst = ps + buf * kPoolAtoms * 4 * kC;
+    for (int i = tid; i < nb * kC; i += kC) cp_async16(dst + 4 * i, src + 4 * i);
+    cp_async_commit();
+  };
+  for (int k = 0; k < entries; ++k) {
+    __syncthreads();                                        // previous matrix and buffers are no longer read
+    for (int i = tid; i < kC * kPoolCols / 4; i += kC)
+      reinterpret_cast<float4*>(vs)[i] = __ldg(reinterpret_cast<const float4*>(v + (size_t)k * kC * kPoolCols) + i);
+    int it = 0;
+    if ((int)blockIdx.x < groups) load_group(k, blockIdx.x, 0);
+    for (int g = blockIdx.x; g < groups; g += gridDim.x, ++it) {
+      const int buf = it & 1;
+      if (g + (int)gridDim.x < groups) {
+        load_group(k, g + gridDim.x, buf ^ 1);
+        cp_async_wait<1>();
+      } else {
+        cp_async_wait<0>();
+      }
+      __syncthreads();
+      const int b0 = g * kPoolAtoms;
+      const int nb = min(kPoolAtoms, N - b0);
+      if (active) {
+        float r[kPoolAtoms];
+        if (k == 0) {
+          const float bb = bias[col];
+#pragma unroll
+          for (int a = 0; a < kPoolAtoms; ++a) r[a] = bb;
+        } else {
+#pragma unroll
+          for (int a = 0; a < kPoolAtoms; ++a) r[a] = a < nb ? acc[(size_t)(b0 + a) * kPoolCols + col] : 0.f;
+        }
+        const float* pp = ps + buf * kPoolAtoms * 4 * kC + part * kC;
+#pragma unroll 2
+        for (int c = 0; c < kC; c += 4) {
+          const float w0 = vs[(c + 0) * kPoolCols + col], w1 = vs[(c + 1) * kPoolCols + col];
+          const float w2 = vs[(c + 2) * kPoolCols + col], w3 = vs[(c + 3) * kPoolCols + col];
+#pragma unroll
+          for (int a = 0; a < kPoolAtoms; ++a) {
+            const float4 p = *reinterpret_cast<const float4*>(pp + a * 4 * kC + c);
+            r[a] = fmaf(w0, p.x, r[a]); r[a] = fmaf(w1, p.y, r[a]); r[a] = fmaf(w2, p.z, r[a]); r[a] = fmaf(w3, p.w, r[a]);
+          }
+        }
+#pragma unroll
+        for (int a = 0; a < kPoolAtoms; ++a)
+          if (a < nb) acc[(size_t)(b0 + a) * kPoolCols + col] = r[a];
+      }
+      __syncthreads();                                      // buffer `buf` is free for the load issued next iteration
+    }
+  }
+}
+
 __global__ void readout_finalize_kernel(const float* __restrict__ acc, const int32_t* __restrict__ atom_offset, int N,
                                         int G, int Z, float inv_layers, float* __restrict__ logits,
                                         float* __restrict__ score, float* __restrict__ len0) {
@@ -914,28 +1016,36 @@ int num_sms() {
 // C ABI
 // ================================================================================================
 static int node_embed_launch(const float* x, const float* vec, const float* w_embed_t, const float* ori,
-                             const int64_t* types, int32_t Z, int32_t N, int32_t F, int32_t V, float* h, void* stream) {
+                             const int64_t* types, int32_t Z, int32_t N, int32_t F, int32_t V, float* h, float* pool,
+                             void* stream) {
   if (N == 0) return ARREAU_OK;
   if (!x || !vec || !w_embed_t || !ori || !h) return ARREAU_ERR_NULL;
   if (N < 0 || F <= 0 || V < 0 || V > kMaxVec || (types && (Z <= 0 || Z > F))) return ARREAU_ERR_BAD_SHAPE;
   const size_t smem = sizeof(float) * (size_t)kEmbedNodes * (F + V * kO);
   if (smem > 48 * 1024) return ARREAU_ERR_UNSUPPORTED;
   node_embed_kernel<<<(N + kEmbedNodes - 1) / kEmbedNodes, kEmbedNodes * 32, smem, (cudaStream_t)stream>>>(
-      x, vec, w_embed_t, ori, types, Z, N, F, V, h);
+      x, vec, w_embed_t, ori, types, Z, N, F, V, h, pool);
   CUDA_LAUNCH_CHECK();
   return ARREAU_OK;
 }
 
 extern "C" int arreau_node_embed(const float* x, const float* vec, const float* w_embed_t, const float* ori,
                                  int32_t N, int32_t F, int32_t V, float* h, void* stream) {
-  return node_embed_launch(x, vec, w_embed_t, ori, nullptr, 0, N, F, V, h, stream);
+  return node_embed_launch(x, vec, w_embed_t, ori, nullptr, 0, N, F, V, h, nullptr, stream);
 }
 
 extern "C" int arreau_node_embed_typed(const float* x, const int64_t* types, int32_t Z, const float* vec,
                                        const float* w_embed_t, const float* ori, int32_t N, int32_t F, int32_t V,
                                        float* h, void* stream) {
   if (!types) return ARREAU_ERR_NULL;
-  return node_embed_launch(x, vec, w_embed_t, ori, types, Z, N, F, V, h, stream);
+  return node_embed_launch(x, vec, w_embed_t, ori, types, Z, N, F, V, h, nullptr, stream);
+}
+
+extern "C" int arreau_node_embed_pooled(const float* x, const int64_t* types, int32_t Z, const float* vec,
+                                        const float* w_embed_t, const float* ori, int32_t N, int32_t F, int32_t V,
+                                        float* h, float* pool, void* stream) {
+  if (N > 0 && !pool) return ARREAU_ERR_NULL;
+  return node_embed_launch(x, vec, w_embed_t, ori, types, Z, N, F, V, h, pool, stream);
 }
 
 extern "C" int arreau_fiber_kernel_precompute(const float* ori, const float* w1, const float* b1, const float* w2,
@@ -1072,6 +1182,25 @@ extern "C" int arreau_readout_accumulate(const float* h, const float* wr_t, cons
   if (Z + 4 + 3 * kReadoutNodes > kC) return ARREAU_ERR_UNSUPPORTED;
   readout_accumulate_kernel<<<(N + kReadoutNodes - 1) / kReadoutNodes, kC, 0, (cudaStream_t)stream>>>(h, wr_t, br, ori, N,
                                                                                                     Z, first_layer, acc);
+  CUDA_LAUNCH_CHECK();
+  return ARREAU_OK;
+}
+
+extern "C" int arreau_readout_pooled(const float* pool, const float* readout_v, const float* readout_bias, int32_t N,
+                                     int32_t Z, int32_t entries, float* acc, void* stream) {
+  if (N == 0) return ARREAU_OK;
+  if (!pool || !readout_v || !readout_bias || !acc) return ARREAU_ERR_NULL;
+  if (N < 0 || entries <= 0) return ARREAU_ERR_BAD_SHAPE;
+  if (Z + 6 != kPoolCols) return ARREAU_ERR_UNSUPPORTED;
+  static bool attr_set = false;
+  if (!attr_set) {
+    cudaError_t e = cudaFuncSetAttribute(readout_pooled_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kPoolSmem);
+    if (e != cudaSuccess) return (int)e;
+    attr_set = true;
+  }
+  const int groups = (N + kPoolAtoms - 1) / kPoolAtoms;
+  const int grid = groups < 2 * num_sms() ? groups : 2 * num_sms();
+  readout_pooled_kernel<<<grid, kC, kPoolSmem, (cudaStream_t)stream>>>(pool, readout_v, readout_bias, N, Z, entries, acc);
   CUDA_LAUNCH_CHECK();
   return ARREAU_OK;
 }

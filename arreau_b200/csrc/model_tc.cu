@@ -123,7 +123,7 @@ struct Bars {
 __global__ void __launch_bounds__(kThreads, 1)
 convnext_mlp_tc_kernel(const uint8_t* __restrict__ y_img, const uint8_t* __restrict__ w_img, const float* __restrict__ b1,
                        const float* __restrict__ b2, const float* __restrict__ layer_scale, long long rows,
-                       float* __restrict__ h) {
+                       float* __restrict__ h, const float* __restrict__ ori, float* __restrict__ pool_out) {
   using namespace mlp;
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
@@ -134,11 +134,15 @@ convnext_mlp_tc_kernel(const uint8_t* __restrict__ y_img, const uint8_t* __restr
   float* const s_b1 = reinterpret_cast<float*>(smem + kTilesBytes);                 // [kW]
   Bars& bars = *reinterpret_cast<Bars*>(smem + kTilesBytes + kW * sizeof(float));
   uint32_t& tmem_base_s = *reinterpret_cast<uint32_t*>(smem + kTilesBytes + kW * sizeof(float) + sizeof(Bars));
-  if ((base - smem_u32(smem_raw)) + kTilesBytes + kW * sizeof(float) + sizeof(Bars) + 16 > (uint32_t)kSmemBytes) __trap();
+  float* const s_ori = reinterpret_cast<float*>(smem + kTilesBytes + kW * sizeof(float) + sizeof(Bars) + 16);   // [kO][3]
+  if ((base - smem_u32(smem_raw)) + kTilesBytes + kW * sizeof(float) + sizeof(Bars) + 16 + kO * 3 * sizeof(float) >
+      (uint32_t)kSmemBytes)
+    __trap();
   const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0), lane = threadIdx.x & 31;   // warp-uniform
   const long long tiles = (rows + kTileM - 1) / kTileM;
 
   for (int i = threadIdx.x; i < kW; i += kThreads) s_b1[i] = b1[i];
+  if (pool_out && threadIdx.x < kO * 3) s_ori[threadIdx.x] = ori[threadIdx.x];
   if (threadIdx.x == 0) {
     for (int i = 0; i < 2; ++i) {
       mbar_init(&bars.a_full[i], 1); mbar_init(&bars.a_empty[i], 1);
@@ -270,6 +274,11 @@ convnext_mlp_tc_kernel(const uint8_t* __restrict__ y_img, const uint8_t* __restr
         TC_STAMP(2 + 2 * j);
       }
       TC_STAMP(9);
+      // pooled read-out (see readout_pooled_kernel): epilogue thread et owns channel et & 127 of atoms (et >> 7) and
+      // (et >> 7) + 4 of the tile's 8
+      const int et = (int)threadIdx.x - kEpiWarp0 * 32;
+      const int pc = et & 127, pa = et >> 7;
+      const long long n_atoms = rows / kO;
       mbar_wait(&bars.d2_full, it & 1);
       tc_fence_after();
       TC_STAMP(10);
@@ -323,6 +332,33 @@ convnext_mlp_tc_kernel(const uint8_t* __restrict__ y_img, const uint8_t* __restr
                            "r"(smem_u32(H0 + half * kTileBytes)), "r"((uint32_t)n * 512u)
                            : "memory");
             asm volatile("cp.async.bulk.commit_group;" ::: "memory");   // (possibly empty) group per half
+          }
+        }
+        if (pool_out) {
+          // pool the staged update over the 16 orientation rows of each atom (read-only on the staging buffers, which
+          // stay intact until the next tile's bar.sync)
+          const float* stage = reinterpret_cast<const float*>(H0);
+          constexpr float inv = 1.0f / kO;
+#pragma unroll
+          for (int rep = 0; rep < 2; ++rep) {
+            const int a = pa + 4 * rep;
+            const long long atom = tile * (kTileM / kO) + a;
+            float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f;
+#pragma unroll
+            for (int o = 0; o < kO; ++o) {
+              const float u = stage[(a * kO + o) * kC + pc];
+              s0 += u;
+              s1 = fmaf(s_ori[3 * o + 0], u, s1);
+              s2 = fmaf(s_ori[3 * o + 1], u, s2);
+              s3 = fmaf(s_ori[3 * o + 2], u, s3);
+            }
+            if (atom < n_atoms) {
+              float* po = pool_out + (size_t)atom * 4 * kC + pc;
+              po[0] = s0 * inv;
+              po[kC] = s1 * inv;
+              po[2 * kC] = s2 * inv;
+              po[3 * kC] = s3 * inv;
+            }
           }
         }
       }
@@ -804,11 +840,12 @@ extern "C" int arreau_debug_set_tc_profile(long long* buf) {
   return (int)cudaMemcpyToSymbol(g_tc_prof, &buf, sizeof(buf));
 }
 
-extern "C" int arreau_convnext_mlp_f16(const void* y_img, const void* w_img, const float* b1, const float* b2,
-                                        const float* layer_scale, int64_t num_rows, float* h, void* stream) {
+static int convnext_mlp_f16_launch(const void* y_img, const void* w_img, const float* b1, const float* b2,
+                                   const float* layer_scale, int64_t num_rows, float* h, const float* ori,
+                                   float* pool_out, void* stream) {
   if (num_rows == 0) return ARREAU_OK;
   if (!y_img || !w_img || !b1 || !b2 || !layer_scale || !h) return ARREAU_ERR_NULL;
-  if (num_rows < 0) return ARREAU_ERR_BAD_SHAPE;
+  if (num_rows < 0 || (pool_out && num_rows % kO != 0)) return ARREAU_ERR_BAD_SHAPE;
   static bool attr_set = false;
   if (!attr_set) {
     cudaError_t e = cudaFuncSetAttribute(convnext_mlp_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, mlp::kSmemBytes);
@@ -818,9 +855,21 @@ extern "C" int arreau_convnext_mlp_f16(const void* y_img, const void* w_img, con
   const long long tiles = (num_rows + kTileM - 1) / kTileM;
   const int grid = (int)(tiles < (long long)num_sms_tc() ? tiles : (long long)num_sms_tc());
   convnext_mlp_tc_kernel<<<grid, kThreads, mlp::kSmemBytes, (cudaStream_t)stream>>>(
-      (const uint8_t*)y_img, (const uint8_t*)w_img, b1, b2, layer_scale, (long long)num_rows, h);
+      (const uint8_t*)y_img, (const uint8_t*)w_img, b1, b2, layer_scale, (long long)num_rows, h, ori, pool_out);
   CUDA_LAUNCH_CHECK();
   return ARREAU_OK;
+}
+
+extern "C" int arreau_convnext_mlp_f16(const void* y_img, const void* w_img, const float* b1, const float* b2,
+                                        const float* layer_scale, int64_t num_rows, float* h, void* stream) {
+  return convnext_mlp_f16_launch(y_img, w_img, b1, b2, layer_scale, num_rows, h, nullptr, nullptr, stream);
+}
+
+extern "C" int arreau_convnext_mlp_f16_pooled(const void* y_img, const void* w_img, const float* b1, const float* b2,
+                                               const float* layer_scale, int64_t num_rows, float* h, const float* ori,
+                                               float* pool_out, void* stream) {
+  if (num_rows > 0 && (!ori || !pool_out)) return ARREAU_ERR_NULL;
+  return convnext_mlp_f16_launch(y_img, w_img, b1, b2, layer_scale, num_rows, h, ori, pool_out, stream);
 }
 
 extern "C" int arreau_edge_kernels_f16(const double* dir, const double* dist, const double* lattice,

@@ -105,7 +105,14 @@ extern "C" int arreau_ponita_forward(const arreau_weights* w, const arreau_works
   const int Z = w->num_states;
   const size_t node_elems = (size_t)N * kO * kC;
   cudaStream_t s = (cudaStream_t)stream;
-  if (ws->onehot_types)
+  // fp16 tensor path with a pool buffer: the read-outs run on orientation-pooled features that the embedding and the
+  // MLP epilogues keep up to date, so h is never re-read for them (one pooled read-out launch instead of L passes)
+  float* const pool = (fp16 && w->readout_v && w->readout_bias) ? ws->pool : nullptr;
+  const size_t pool_elems = (size_t)N * 4 * kC;
+  if (pool)
+    ARREAU_TRY(arreau_node_embed_pooled(x, ws->onehot_types, Z, vec, w->w_embed_t, w->ori, N, w->num_scalar, w->num_vec,
+                                        ws->h, pool, stream));
+  else if (ws->onehot_types)
     ARREAU_TRY(arreau_node_embed_typed(x, ws->onehot_types, Z, vec, w->w_embed_t, w->ori, N, w->num_scalar, w->num_vec,
                                        ws->h, stream));
   else
@@ -131,7 +138,12 @@ extern "C" int arreau_ponita_forward(const arreau_weights* w, const arreau_works
                                          w->conv_bias + l * kC, w->ln_w + l * kC, w->ln_b + l * kC, N, ws->y, fp16,
                                          ws->x1_debug ? ws->x1_debug + l * node_elems : ws->x1,
                                          ws->x2_debug ? ws->x2_debug + l * node_elems : nullptr, stream));
-    if (fp16)
+    if (pool)
+      ARREAU_TRY(arreau_convnext_mlp_f16_pooled(ws->y, (const uint8_t*)w->mlp_w_img + (size_t)l * 8 * 32768,
+                                                 w->mlp_b1 + l * kW, w->mlp_b2 + l * kC, w->layer_scale + l * kC,
+                                                 (int64_t)N * kO, ws->h, w->ori, pool + (size_t)(l + 1) * pool_elems,
+                                                 stream));
+    else if (fp16)
       ARREAU_TRY(arreau_convnext_mlp_f16(ws->y, (const uint8_t*)w->mlp_w_img + (size_t)l * 8 * 32768,
                                           w->mlp_b1 + l * kW, w->mlp_b2 + l * kC, w->layer_scale + l * kC,
                                           (int64_t)N * kO, ws->h, stream));
@@ -144,10 +156,12 @@ extern "C" int arreau_ponita_forward(const arreau_weights* w, const arreau_works
                                       cudaMemcpyDeviceToDevice, s);
       if (e != cudaSuccess) return (int)e;
     }
-    ARREAU_TRY(arreau_readout_accumulate(ws->h, w->wr_t + (size_t)l * kC * (Z + 4), w->br + l * (Z + 4), w->ori, N, Z,
-                                         l == 0, ws->acc, stream));
+    if (!pool)
+      ARREAU_TRY(arreau_readout_accumulate(ws->h, w->wr_t + (size_t)l * kC * (Z + 4), w->br + l * (Z + 4), w->ori, N, Z,
+                                           l == 0, ws->acc, stream));
   }
-  ARREAU_TRY(arreau_readout_finalize(ws->acc, atom_offset, N, G, Z, kL, logits, score, len0, stream));
+  if (pool) ARREAU_TRY(arreau_readout_pooled(pool, w->readout_v, w->readout_bias, N, Z, kL + 1, ws->acc, stream));
+  ARREAU_TRY(arreau_readout_finalize(ws->acc, atom_offset, N, G, Z, pool ? 1 : kL, logits, score, len0, stream));
   return ARREAU_OK;
 }
 

@@ -40,7 +40,7 @@ def _i32(a, device):
 class DenoiseEngine:
     def __init__(self, weights: PonitaWeights, tables: DiffusionTables, fourier_w, num_atoms: Sequence[int],
                  radius: float, max_neighbors: int, precision: str = "fp32", edge_capacity: Optional[int] = None,
-                 debug: bool = False, device="cuda"):
+                 debug: bool = False, device="cuda", pooled_readout: bool = False):
         if precision not in PRECISIONS:
             raise ValueError(f"precision must be one of {sorted(PRECISIONS)}")
         _lib.load()
@@ -77,6 +77,9 @@ class DenoiseEngine:
         self.x, self.vec = f32(N, self.F), f32(N, 4, 3)
         self.logits, self.score, self.len0 = f32(N, Z), f32(N, 3), f32(G, 3)
         self.h, self.acc, self.x1 = f32(N, NUM_ORI, HIDDEN), f32(N, Z + 6), f32(N, NUM_ORI, HIDDEN)
+        # orientation-pooled features per layer: the fp16 path's read-outs run on these (arreau_readout_pooled)
+        self.pool = (f32(LAYERS + 1, N, 4, HIDDEN)
+                     if (self.precision == "fp16" and pooled_readout and "readout_v" in weights.t) else None)
         if precision == "fp16":     # 128-row UMMA tile images (32 KB each), see arreau_message_fiber_norm
             self.y = torch.zeros(((N * NUM_ORI + 127) // 128) * 128 * HIDDEN, device=dev, dtype=torch.float16)
         else:
@@ -122,6 +125,7 @@ class DenoiseEngine:
         ws.x1_debug, ws.x2_debug, ws.h_debug = _lib.ptr(self.x1_debug), _lib.ptr(self.x2_debug), _lib.ptr(self.h_debug)
         ws.edge_capacity = capacity
         ws.onehot_types = None          # set by predict_scores / step: x[:, :Z] is one_hot(self.types) there
+        ws.pool = _lib.ptr(self.pool)
         self.ws = ws
         a = _lib.StepArgs()
         p = _lib.ptr
@@ -336,9 +340,15 @@ class DenoiseEngine:
 
         add("features", lambda: self.prepare_inputs(t))
         add("graph", lambda: self.build_graph())
-        add("node_embed", lambda: _lib.call("arreau_node_embed_typed", self.x.data_ptr(), self.types.data_ptr(), Z,
-                                            self.vec.data_ptr(), w["w_embed_t"].data_ptr(), w["ori"].data_ptr(),
-                                            self.N, self.F, 4, self.h.data_ptr(), self.stream))
+        pooled = self.pool is not None
+        if pooled:
+            add("node_embed", lambda: _lib.call("arreau_node_embed_pooled", self.x.data_ptr(), self.types.data_ptr(), Z,
+                                                self.vec.data_ptr(), w["w_embed_t"].data_ptr(), w["ori"].data_ptr(),
+                                                self.N, self.F, 4, self.h.data_ptr(), self.pool[0].data_ptr(), self.stream))
+        else:
+            add("node_embed", lambda: _lib.call("arreau_node_embed_typed", self.x.data_ptr(), self.types.data_ptr(), Z,
+                                                self.vec.data_ptr(), w["w_embed_t"].data_ptr(), w["ori"].data_ptr(),
+                                                self.N, self.F, 4, self.h.data_ptr(), self.stream))
         nep = self.row_ptr.data_ptr() + 4 * self.N
         if fp16:
             add("edge_kernels", lambda: _lib.call(
@@ -361,7 +371,13 @@ class DenoiseEngine:
                 (w["fiber_frag"].data_ptr() + l * HIDDEN * 32 * 16) if fp16 else None,
                 w["conv_bias"][l].data_ptr(), w["ln_w"][l].data_ptr(), w["ln_b"][l].data_ptr(), self.N,
                 self.y.data_ptr(), int(fp16), None, self.stream))
-            if fp16:
+            if pooled:
+                add("convnext_mlp", lambda l=l: _lib.call(
+                    "arreau_convnext_mlp_f16_pooled", self.y.data_ptr(), w["mlp_w_img"].data_ptr() + l * 8 * 32768,
+                    w["mlp_b1"][l].data_ptr(), w["mlp_b2"][l].data_ptr(),
+                    w["layer_scale"][l].data_ptr(), self.N * NUM_ORI, self.h.data_ptr(), w["ori"].data_ptr(),
+                    self.pool[l + 1].data_ptr(), self.stream))
+            elif fp16:
                 add("convnext_mlp", lambda l=l: _lib.call(
                     "arreau_convnext_mlp_f16", self.y.data_ptr(), w["mlp_w_img"].data_ptr() + l * 8 * 32768,
                     w["mlp_b1"][l].data_ptr(), w["mlp_b2"][l].data_ptr(),
@@ -371,11 +387,16 @@ class DenoiseEngine:
                     "arreau_convnext_mlp_f32", self.y.data_ptr(), w["mlp_w1_t"][l].data_ptr(),
                     w["mlp_b1"][l].data_ptr(), w["mlp_w2_t"][l].data_ptr(), w["mlp_b2"][l].data_ptr(),
                     w["layer_scale"][l].data_ptr(), self.N * NUM_ORI, self.h.data_ptr(), self.stream))
-            add("readout", lambda l=l: _lib.call(
-                "arreau_readout_accumulate", self.h.data_ptr(), w["wr_t"][l].data_ptr(), w["br"][l].data_ptr(),
-                w["ori"].data_ptr(), self.N, Z, int(l == 0), self.acc.data_ptr(), self.stream))
+            if not pooled:
+                add("readout", lambda l=l: _lib.call(
+                    "arreau_readout_accumulate", self.h.data_ptr(), w["wr_t"][l].data_ptr(), w["br"][l].data_ptr(),
+                    w["ori"].data_ptr(), self.N, Z, int(l == 0), self.acc.data_ptr(), self.stream))
+        if pooled:
+            add("readout", lambda: _lib.call("arreau_readout_pooled", self.pool.data_ptr(), w["readout_v"].data_ptr(),
+                                             w["readout_bias"].data_ptr(), self.N, Z, LAYERS + 1,
+                                             self.acc.data_ptr(), self.stream))
         add("readout", lambda: _lib.call("arreau_readout_finalize", self.acc.data_ptr(), self.atom_offset.data_ptr(),
-                                         self.N, self.G, Z, LAYERS, self.logits.data_ptr(), self.score.data_ptr(),
+                                         self.N, self.G, Z, 1 if pooled else LAYERS, self.logits.data_ptr(), self.score.data_ptr(),
                                          self.len0.data_ptr(), self.stream))
         sc_len, sc_frac, sc_types = torch.empty_like(self.lengths), torch.empty_like(self.frac), torch.empty_like(self.types)
         tb = self.tabs

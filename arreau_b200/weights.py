@@ -67,6 +67,24 @@ def _np(v) -> np.ndarray:
     return np.asarray(v, dtype=np.float64)
 
 
+def pooled_readout_weights(wr: np.ndarray, br: np.ndarray, ori: np.ndarray):
+    """Combined matrices of the pooled read-out (arreau_readout_pooled).  wr[L,R,C], br[L,R] with R = Z + 4 rows
+    (Z scalars | 1 vector channel | 3 global scalars, ponita.py:111); ori[O,3].  The feature after layer l is
+    pool[0] + ... + pool[l] (embedding + residual updates), and the result is the mean over layers of the read-outs
+    (ponita.py:108), so entry k meets V_k = (1/L) sum_{l >= max(k,1)} Wr_l.  Columns follow acc[N][Z+6]:
+    Z logits | 3 score components (all three use weight row Z, applied to the vector-pooled parts) | 3 length channels.
+    The vector channel's bias meets mean_o ori_o (to_from_sphere.py:10-11)."""
+    L, R, Cc = wr.shape
+    Z = R - 4
+    rows = np.concatenate([np.arange(Z), [Z, Z, Z], np.arange(Z + 1, Z + 4)])
+    v = np.zeros((L + 1, Cc, Z + 6))
+    for k in range(L + 1):
+        v[k] = wr[max(k, 1) - 1:].sum(0)[rows].T / L
+    bias = br.sum(0)[rows] / L
+    bias[Z:Z + 3] *= ori.mean(0)
+    return v, bias
+
+
 class PonitaWeights:
     """Device copies of one PonitaFiberBundle's parameters in kernel layouts."""
 
@@ -139,6 +157,8 @@ class PonitaWeights:
                 mlp += [g1[0], g1[1], g2[0], g1[2], g2[1], g1[3], g2[2], g2[3]]   # MMA issue order
             self.t.update(edge_w1_img=umma_tile_image(w1pad).to(self.device),
                           edge_w_img=torch.cat(chunks).to(self.device), mlp_w_img=torch.cat(mlp).to(self.device))
+            rv, rb = pooled_readout_weights(wr, br, ori)
+            self.t.update(readout_v=f32(rv), readout_bias=f32(rb))
         self.c = _lib.Weights()
         for name, _ in _lib.Weights._fields_:
             if name in self.t:

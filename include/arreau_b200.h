@@ -190,6 +190,26 @@ int arreau_convnext_mlp_f32(const float* y, const float* w1_t, const float* b1, 
 int arreau_convnext_mlp_f16(const void* y_img, const void* w_img, const float* b1, const float* b2,
                              const float* layer_scale, int64_t num_rows, float* h, void* stream);
 
+/* Pooled read-out path of the fp16 tensor path (K7 fused into K2 / K6; ponita.py:105-117, to_from_sphere.py:10-14).
+ * The read-out Linear commutes with the orientation pooling, so only pooled features are needed:
+ *   pool[b][0][c] = mean_o h[b,o,c],   pool[b][1+d][c] = (1/O) sum_o ori[o][d] h[b,o,c]      ([N,4,C] f32 per layer).
+ * pool is [L+1,N,4,C]: entry 0 = pooled features after the embedding, entry k = 1..L the pooled residual UPDATE of
+ * interaction layer k (the feature after layer l is the sum of entries 0..l).
+ * arreau_node_embed_pooled: K2 that also writes entry 0 (types may be NULL).
+ * arreau_convnext_mlp_f16_pooled: K6 whose epilogue pools the residual update it has staged in shared memory into
+ *   pool_out ([N,4,C], one entry); h itself is updated as by arreau_convnext_mlp_f16.
+ * arreau_readout_pooled: acc[N,Z+6] (column layout of arreau_readout_accumulate, already divided by L) =
+ *   sum_k readout_v[k] pool[k] + readout_bias, with readout_v[L+1][C][Z+6], readout_bias[Z+6] the per-entry sums of
+ *   the read-out weights combined on the host (arreau_b200/weights.py: pooled_readout_weights); entries = L+1. */
+int arreau_node_embed_pooled(const float* x, const int64_t* types, int32_t num_states, const float* vec,
+                             const float* w_embed_t, const float* ori, int32_t num_atoms_total, int32_t num_scalar,
+                             int32_t num_vec, float* h, float* pool, void* stream);
+int arreau_convnext_mlp_f16_pooled(const void* y_img, const void* w_img, const float* b1, const float* b2,
+                                    const float* layer_scale, int64_t num_rows, float* h, const float* ori,
+                                    float* pool_out, void* stream);
+int arreau_readout_pooled(const float* pool, const float* readout_v, const float* readout_bias,
+                          int32_t num_atoms_total, int32_t num_states, int32_t entries, float* acc, void* stream);
+
 /* K7a: acc[N,Z+6] (+)= read-out of one layer pooled over orientations (ponita.py:105):
  *   acc[b, 0:Z]      mean_o (Wr h[b,o] + br)[0:Z]                (to_from_sphere.py:13-14)
  *   acc[b, Z:Z+3]    (1/O) sum_o (Wr h[b,o] + br)[Z] * ori_o      (to_from_sphere.py:10-11)
@@ -229,6 +249,8 @@ typedef struct arreau_weights {
   const void* edge_w1_img;   /* 32 KB UMMA tile image of w1m                                */
   const void* edge_w_img;    /* 24 x 16 KB UMMA tile images (W2, then Wk per layer)         */
   const void* mlp_w_img;     /* [L] x 8 x 32 KB UMMA tile images                            */
+  const float* readout_v;    /* [L+1,C,Z+6] combined read-out matrices of the pooled read-out, or NULL */
+  const float* readout_bias; /* [Z+6]                                                       */
   int32_t num_scalar;        /* F                                                           */
   int32_t num_vec;           /* V                                                           */
   int32_t num_states;        /* Z                                                           */
@@ -247,6 +269,7 @@ typedef struct arreau_workspace {
   float* h_debug;   /* NULL, or [L+1,N,O,C] f32 (h after the embedding and after each layer) */
   int64_t edge_capacity;
   const int64_t* onehot_types; /* NULL, or types[N]: x[:, 0:Z] is one_hot(types) (lets the embedding skip the zeros) */
+  float* pool;      /* NULL, or [L+1,N,4,C] f32 pooled features / updates -> the fp16 path uses the pooled read-out */
 } arreau_workspace;
 
 /* PonitaFiberBundle.forward (ponita/models/ponita.py:88-123) on a prebuilt graph: x[N,F], vec[N,V,3] f32;

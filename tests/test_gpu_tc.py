@@ -143,3 +143,30 @@ def test_ragged_and_sparse_batches_f16_vs_fp32(device, packed_weights, weights_n
         assert outs["fp16"][3] == 0
     for x, y in zip(outs["fp16"][:3], outs["fp32"][:3]):
         assert _rel(x, y) < TOL_FP16_MODEL
+
+
+@pytest.mark.parametrize("num_atoms", [[40] * 64, [5, 17, 2, 9, 1], [3]])
+def test_pooled_readout_matches_per_layer_readout(device, packed_weights, weights_npz, num_atoms):
+    """The fp16 path's read-outs run on orientation-pooled features maintained by the embedding and the MLP epilogues
+    (arreau_node_embed_pooled / arreau_convnext_mlp_f16_pooled / arreau_readout_pooled); by linearity this equals the
+    per-layer read-out of h (arreau_readout_accumulate) up to fp32 summation order.  Atom counts that are not
+    multiples of the 8-atom MLP tiles included."""
+    from arreau_b200.engine import DenoiseEngine
+    from arreau_b200.tables import build_tables
+    rng = np.random.default_rng(11)
+    na = np.asarray(num_atoms)
+    lengths = np.cbrt(18.05 * na)[:, None] * (1.0 + 0.1 * rng.standard_normal((len(na), 3)))
+    angles = np.pi / 2 + 0.1 * rng.standard_normal((len(na), 3))
+    frac, types = rng.random((int(na.sum()), 3)), rng.integers(0, 89, int(na.sum()))
+    outs = []
+    for pooled in (False, True):
+        eng = DenoiseEngine(packed_weights, build_tables(1000, 90), weights_npz["fourier_w"], na, 5.0, 8,
+                            precision="fp16", device=device, pooled_readout=pooled)
+        assert (eng.pool is not None) == pooled
+        eng.set_state(frac, types, lengths, angles)
+        score, logits, len0 = eng.predict_scores(400)
+        torch.cuda.synchronize()
+        outs.append((score.clone(), logits.clone(), len0.clone(), eng.h.clone()))
+    assert torch.equal(outs[0][3], outs[1][3])                  # the residual stream itself is untouched by the fusion
+    for x, y in zip(outs[1][:3], outs[0][:3]):
+        assert _rel(x, y) < 2e-5
