@@ -77,6 +77,7 @@ SIGNATURES = {
     "arreau_edge_kernels_f16": [vp, vp, vp, vp, vp, vp, i64, vp, vp, vp, vp, f64, vp, vp],
     "arreau_message_fiber_norm": [vp, i32, vp, vp, vp, vp, vp, vp, vp, vp, i32, vp, i32, vp, vp, vp],
     "arreau_fiber_frag_pack": [vp, i32, vp, vp],
+    "arreau_message_fiber_norm_fused": [vp, vp, vp, vp, vp, vp, vp, vp, i32, vp, vp, vp],
     "arreau_message_gather": [vp, i32, vp, vp, vp, i32, i32, vp, vp],
     "arreau_fiber_norm": [vp, i32, vp, vp, vp, vp, vp, i32, vp, i32, vp, vp],
     "arreau_convnext_mlp_f32": [vp, vp, vp, vp, vp, vp, i64, vp, vp],

@@ -623,6 +623,200 @@ fiber_norm_mma_kernel(const __half* __restrict__ x1t, const uint4* __restrict__ 
   }
 }
 
+// K4b + K5 + LayerNorm fused (fp16 path): the message sums never leave the SM.  Persistent CTAs of 8 warps, two per SM;
+// per 16-atom tile a CTA alternates between two phases and the co-resident CTAs (and the other SMs) drift out of phase,
+// so the HBM-bound gather of one overlaps the latency-bound tensor-core fiber conv of another:
+//   phase 1  warp w gathers atoms 2w, 2w+1 of the tile: lane = 4 channels, orientations in pairs, 8 edges (16
+//            independent 8/16-byte loads per lane) in flight, edges in CSR order (deterministic, no atomics); the
+//            fp16 sums go to shared memory as the A operand [atom][c][o] of the fiber conv
+//   phase 2  fiber_norm_mma_kernel's two passes on that tile (statistics, then recompute + normalise + emit the
+//            ConvNext kernel's UMMA operand image)
+// Shared-memory rows: a channel's 16 orientations are 32 contiguous bytes; 16 bytes of padding after every 4 channels
+// (one lane's 128 bytes) and per atom keep both the gather's stores and the mma fragment loads conflict-free.
+constexpr int kFusedWarps = 8;
+constexpr int kFusedRowBytes = kC * kO * 2 + (kC / 4) * 16 + 16;              // 4624
+constexpr int kFusedTileBytes = kFiberGroup * kFusedRowBytes;
+constexpr size_t kFusedSmem = (size_t)kFusedTileBytes + (size_t)kFusedWarps * 32 * 16 * sizeof(float) + 3 * kC * sizeof(float);
+
+__device__ __forceinline__ uint32_t pack_h2(float lo, float hi) {
+  const __half2 v = __floats2half2_rn(lo, hi);
+  return *reinterpret_cast<const uint32_t*>(&v);
+}
+
+__global__ void __launch_bounds__(kFusedWarps * 32, 2)
+message_fiber_norm_fused_kernel(const __half* __restrict__ kern, const float* __restrict__ h,
+                                const int32_t* __restrict__ row_ptr, const int32_t* __restrict__ src,
+                                const uint4* __restrict__ fk_frag, const float* __restrict__ bias,
+                                const float* __restrict__ ln_w, const float* __restrict__ ln_b, int N,
+                                __half* __restrict__ y, float* __restrict__ x2_dbg) {
+  extern __shared__ __align__(128) uint8_t fsm[];
+  uint8_t* s_a = fsm;                                                            // [16 atoms][kFusedRowBytes]
+  float* s_stats = reinterpret_cast<float*>(s_a + (size_t)kFusedTileBytes);      // [warps][32 lanes][16]
+  float* s_bias = s_stats + kFusedWarps * 32 * 16;
+  float* s_g = s_bias + kC;
+  float* s_b = s_g + kC;
+  for (int i = threadIdx.x; i < kC; i += blockDim.x) { s_bias[i] = bias[i]; s_g[i] = ln_w[i]; s_b[i] = ln_b[i]; }
+  __syncthreads();
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, g = lane >> 2, t = lane & 3;
+  const int groups = (N + kFiberGroup - 1) / kFiberGroup;
+  for (int grp = blockIdx.x; grp < groups; grp += gridDim.x) {
+    const int atom0 = grp * kFiberGroup;
+    // ---------------- phase 1: gather ----------------
+#pragma unroll 1
+    for (int rep = 0; rep < 2; ++rep) {
+      const int a = warp * 2 + rep, node = atom0 + a;
+      if (node >= N) break;                                    // rows past N are never stored (v0 / v1 below)
+      const int e0 = row_ptr[node], e1 = row_ptr[node + 1];
+      uint8_t* dst = s_a + (size_t)a * kFusedRowBytes + lane * 144;
+#pragma unroll 1
+      for (int op = 0; op < kO / 2; ++op) {
+        float4 acc[2];
+#pragma unroll
+        for (int oo = 0; oo < 2; ++oo) {
+          const int o = 2 * op + oo;
+          float4 s4 = make_float4(0.f, 0.f, 0.f, 0.f);
+          for (int e = e0; e < e1; e += 8) {
+            uint2 kv[8];
+            float4 hv[8];
+#pragma unroll
+            for (int u = 0; u < 8; ++u) {
+              const int ee = min(e + u, e1 - 1);                // clamped: loads stay in range, the tail is masked below
+              const int sj = __ldg(src + ee);
+              const __half* krow = kern + ((size_t)ee * kO + o) * kC;
+              kv[u] = *reinterpret_cast<const uint2*>(krow + ((((lane >> 1) ^ o) << 3) | ((lane & 1) << 2)));
+              hv[u] = *reinterpret_cast<const float4*>(h + ((size_t)sj * kO + o) * kC + lane * 4);
+            }
+#pragma unroll
+            for (int u = 0; u < 8; ++u) {
+              if (e + u < e1) {
+                const float2 k0 = __half22float2(*reinterpret_cast<const __half2*>(&kv[u].x));
+                const float2 k1 = __half22float2(*reinterpret_cast<const __half2*>(&kv[u].y));
+                s4.x = fmaf(k0.x, hv[u].x, s4.x);
+                s4.y = fmaf(k0.y, hv[u].y, s4.y);
+                s4.z = fmaf(k1.x, hv[u].z, s4.z);
+                s4.w = fmaf(k1.y, hv[u].w, s4.w);
+              }
+            }
+          }
+          acc[oo] = s4;
+        }
+        // channel 4 lane + i, orientations (2 op, 2 op + 1): one half2 at [c][o]
+        *reinterpret_cast<uint32_t*>(dst + 0 * 32 + op * 4) = pack_h2(acc[0].x, acc[1].x);
+        *reinterpret_cast<uint32_t*>(dst + 1 * 32 + op * 4) = pack_h2(acc[0].y, acc[1].y);
+        *reinterpret_cast<uint32_t*>(dst + 2 * 32 + op * 4) = pack_h2(acc[0].z, acc[1].z);
+        *reinterpret_cast<uint32_t*>(dst + 3 * 32 + op * 4) = pack_h2(acc[0].w, acc[1].w);
+      }
+    }
+    __syncthreads();
+    // ---------------- phase 2: fiber conv + LayerNorm (see fiber_norm_mma_kernel) ----------------
+    const bool v0 = atom0 + g < N, v1 = atom0 + g + 8 < N;
+    const uint8_t* a0p = s_a + (size_t)g * kFusedRowBytes + 4 * t;
+    const uint8_t* a1p = a0p + 8 * (size_t)kFusedRowBytes;
+    auto load_a = [&](int c, uint32_t (&a)[4]) {
+      const int off = c * (kO * 2) + (c >> 2) * 16;
+      a[0] = *reinterpret_cast<const uint32_t*>(a0p + off);
+      a[1] = *reinterpret_cast<const uint32_t*>(a1p + off);
+      a[2] = *reinterpret_cast<const uint32_t*>(a0p + off + 16);
+      a[3] = *reinterpret_cast<const uint32_t*>(a1p + off + 16);
+    };
+    float sum[8], sq[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) { sum[i] = 0.f; sq[i] = 0.f; }
+#pragma unroll 4
+    for (int cc = 0; cc < kC / kFusedWarps; ++cc) {
+      const int c = warp * (kC / kFusedWarps) + cc;
+      uint32_t a[4];
+      load_a(c, a);
+      const uint4 b = __ldg(fk_frag + c * 32 + lane);
+      float d0[4], d1[4];
+      mma16816(d0, a[0], a[1], a[2], a[3], b.x, b.y);
+      mma16816(d1, a[0], a[1], a[2], a[3], b.z, b.w);
+      const float bc = s_bias[c];
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        const float x0 = d0[i] + bc, x1v = d1[i] + bc;
+        sum[i] += x0; sq[i] = fmaf(x0, x0, sq[i]);
+        sum[4 + i] += x1v; sq[4 + i] = fmaf(x1v, x1v, sq[4 + i]);
+      }
+    }
+    {
+      float4* st = reinterpret_cast<float4*>(s_stats + ((size_t)warp * 32 + lane) * 16);
+      st[0] = make_float4(sum[0], sum[1], sum[2], sum[3]);
+      st[1] = make_float4(sum[4], sum[5], sum[6], sum[7]);
+      st[2] = make_float4(sq[0], sq[1], sq[2], sq[3]);
+      st[3] = make_float4(sq[4], sq[5], sq[6], sq[7]);
+    }
+    __syncthreads();
+#pragma unroll
+    for (int i = 0; i < 8; ++i) { sum[i] = 0.f; sq[i] = 0.f; }
+#pragma unroll
+    for (int w = 0; w < kFusedWarps; ++w) {      // fixed order: deterministic
+      const float4* st = reinterpret_cast<const float4*>(s_stats + ((size_t)w * 32 + lane) * 16);
+      const float4 s0 = st[0], s1 = st[1], q0 = st[2], q1 = st[3];
+      sum[0] += s0.x; sum[1] += s0.y; sum[2] += s0.z; sum[3] += s0.w;
+      sum[4] += s1.x; sum[5] += s1.y; sum[6] += s1.z; sum[7] += s1.w;
+      sq[0] += q0.x; sq[1] += q0.y; sq[2] += q0.z; sq[3] += q0.w;
+      sq[4] += q1.x; sq[5] += q1.y; sq[6] += q1.z; sq[7] += q1.w;
+    }
+    float rstd[8], shift[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      const float mean = sum[i] * (1.0f / kC);
+      const float var = fmaxf(sq[i] * (1.0f / kC) - mean * mean, 0.f);      // biased variance, eps 1e-5 (convnext.py:25)
+      rstd[i] = 1.0f / sqrtf(var + 1e-5f);
+      shift[i] = -mean * rstd[i];
+    }
+#pragma unroll 1
+    for (int half = 0; half < 2; ++half) {
+      const int cb = warp * 2 + half;
+      uint32_t pk[8][4];
+#pragma unroll
+      for (int j = 0; j < 8; j += 2) {
+        float o0[8], o1[8];
+#pragma unroll
+        for (int jj = 0; jj < 2; ++jj) {
+          const int c = cb * 8 + j + jj;
+          uint32_t a[4];
+          load_a(c, a);
+          const uint4 b = __ldg(fk_frag + c * 32 + lane);
+          float d0[4], d1[4];
+          mma16816(d0, a[0], a[1], a[2], a[3], b.x, b.y);
+          mma16816(d1, a[0], a[1], a[2], a[3], b.z, b.w);
+          const float bc = s_bias[c], gw = s_g[c], gb = s_b[c];
+          float* o = jj ? o1 : o0;
+#pragma unroll
+          for (int i = 0; i < 4; ++i) {
+            const float x0 = d0[i] + bc, x1v = d1[i] + bc;
+            if (x2_dbg) {
+              const int at0 = atom0 + g + 8 * ((i >> 1) & 1);
+              if (at0 < N) {
+                x2_dbg[((size_t)at0 * kO + 2 * t + (i & 1)) * kC + c] = x0;
+                x2_dbg[((size_t)at0 * kO + 8 + 2 * t + (i & 1)) * kC + c] = x1v;
+              }
+            }
+            o[i] = fmaf(fmaf(x0, rstd[i], shift[i]), gw, gb);
+            o[4 + i] = fmaf(fmaf(x1v, rstd[4 + i], shift[4 + i]), gw, gb);
+          }
+        }
+#pragma unroll
+        for (int i = 0; i < 8; ++i) pk[i][j >> 1] = pack_h2(o0[i], o1[i]);
+      }
+      const int slab = cb >> 3, chunk = cb & 7;
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        const bool valid = ((i >> 1) & 1) ? v1 : v0;
+        if (valid) {
+          const long long row = (long long)(atom0 + g + 8 * ((i >> 1) & 1)) * kO + 8 * (i >> 2) + 2 * t + (i & 1);
+          const int rr = (int)(row & 127);
+          *reinterpret_cast<uint4*>(reinterpret_cast<uint8_t*>(y) + (size_t)(row >> 7) * 32768 + (size_t)slab * 16384 +
+                                    (size_t)rr * 128 + ((chunk ^ (rr & 7)) << 4)) = make_uint4(pk[i][0], pk[i][1], pk[i][2], pk[i][3]);
+        }
+      }
+    }
+    __syncthreads();       // every warp is done with this tile's buffer and the statistics scratch
+  }
+}
+
 constexpr int kFiberThreads = 512;
 constexpr int kFiberStages = 3;
 constexpr int kFiberNB = 2;     // nodes per pipeline stage
@@ -1141,13 +1335,35 @@ extern "C" int arreau_fiber_norm(const float* x1, int32_t x1_f16_transposed, con
   return ARREAU_OK;
 }
 
+extern "C" int arreau_message_fiber_norm_fused(const void* kernels_f16, const float* h, const int32_t* row_ptr,
+                                               const int32_t* src, const void* fiber_frag, const float* conv_bias,
+                                               const float* ln_w, const float* ln_b, int32_t N, void* y_f16,
+                                               float* x2_debug, void* stream) {
+  if (N == 0) return ARREAU_OK;
+  if (!kernels_f16 || !h || !row_ptr || !src || !fiber_frag || !conv_bias || !ln_w || !ln_b || !y_f16) return ARREAU_ERR_NULL;
+  if (N < 0) return ARREAU_ERR_BAD_SHAPE;
+  static bool attr_set = false;
+  if (!attr_set) {
+    cudaError_t e = cudaFuncSetAttribute(message_fiber_norm_fused_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kFusedSmem);
+    if (e != cudaSuccess) return (int)e;
+    attr_set = true;
+  }
+  const int groups = (N + kFiberGroup - 1) / kFiberGroup;
+  const int grid = groups < 2 * num_sms() ? groups : 2 * num_sms();
+  message_fiber_norm_fused_kernel<<<grid, kFusedWarps * 32, kFusedSmem, (cudaStream_t)stream>>>(
+      (const __half*)kernels_f16, h, row_ptr, src, (const uint4*)fiber_frag, conv_bias, ln_w, ln_b, N, (__half*)y_f16, x2_debug);
+  CUDA_LAUNCH_CHECK();
+  return ARREAU_OK;
+}
+
 extern "C" int arreau_message_fiber_norm(const void* kernels, int32_t kernels_f16, const float* h,
                                          const int32_t* row_ptr, const int32_t* src, const float* fiber_kernel,
                                          const void* fiber_frag, const float* conv_bias, const float* ln_w,
                                          const float* ln_b, int32_t N, void* y, int32_t y_f16, float* x1,
                                          float* x2_debug, void* stream) {
-  // fp16 tensor path (fp16 kernels in, fp16 y out): transposed fp16 message sums + tensor-core fiber conv
+  // fp16 tensor path (fp16 kernels in, fp16 y out): ONE fused launch, the message sums stay in shared memory
   const int32_t t = (kernels_f16 && y_f16) ? 1 : 0;
+  if (t) return arreau_message_fiber_norm_fused(kernels, h, row_ptr, src, fiber_frag, conv_bias, ln_w, ln_b, N, y, x2_debug, stream);
   const int rc = arreau_message_gather(kernels, kernels_f16, h, row_ptr, src, N, t, x1, stream);
   if (rc != ARREAU_OK) return rc;
   return arreau_fiber_norm(x1, t, fiber_kernel, fiber_frag, conv_bias, ln_w, ln_b, N, y, y_f16, x2_debug, stream);

@@ -363,14 +363,20 @@ class DenoiseEngine:
                 w["w1m_t"].data_ptr(), w["w2_t"].data_ptr(), w["b2"].data_ptr(), w["wk_t"].data_ptr(),
                 self.radius, self.kernels.data_ptr(), self.stream))
         for l in range(LAYERS):
-            add("message_gather", lambda l=l: _lib.call(
-                "arreau_message_gather", self.kernels[l].data_ptr(), int(fp16), self.h.data_ptr(),
-                self.row_ptr.data_ptr(), self.src.data_ptr(), self.N, int(fp16), self.x1.data_ptr(), self.stream))
-            add("fiber_norm", lambda l=l: _lib.call(
-                "arreau_fiber_norm", self.x1.data_ptr(), int(fp16), w["fiber_kernel"][l].data_ptr(),
-                (w["fiber_frag"].data_ptr() + l * HIDDEN * 32 * 16) if fp16 else None,
-                w["conv_bias"][l].data_ptr(), w["ln_w"][l].data_ptr(), w["ln_b"][l].data_ptr(), self.N,
-                self.y.data_ptr(), int(fp16), None, self.stream))
+            if fp16:      # one fused launch (the message sums stay in shared memory)
+                add("message_fiber_norm", lambda l=l: _lib.call(
+                    "arreau_message_fiber_norm_fused", self.kernels[l].data_ptr(), self.h.data_ptr(),
+                    self.row_ptr.data_ptr(), self.src.data_ptr(), w["fiber_frag"].data_ptr() + l * HIDDEN * 32 * 16,
+                    w["conv_bias"][l].data_ptr(), w["ln_w"][l].data_ptr(), w["ln_b"][l].data_ptr(), self.N,
+                    self.y.data_ptr(), None, self.stream))
+            else:
+                add("message_gather", lambda l=l: _lib.call(
+                    "arreau_message_gather", self.kernels[l].data_ptr(), 0, self.h.data_ptr(),
+                    self.row_ptr.data_ptr(), self.src.data_ptr(), self.N, 0, self.x1.data_ptr(), self.stream))
+                add("fiber_norm", lambda l=l: _lib.call(
+                    "arreau_fiber_norm", self.x1.data_ptr(), 0, w["fiber_kernel"][l].data_ptr(), None,
+                    w["conv_bias"][l].data_ptr(), w["ln_w"][l].data_ptr(), w["ln_b"][l].data_ptr(), self.N,
+                    self.y.data_ptr(), 0, None, self.stream))
             if pooled:
                 add("convnext_mlp", lambda l=l: _lib.call(
                     "arreau_convnext_mlp_f16_pooled", self.y.data_ptr(), w["mlp_w_img"].data_ptr() + l * 8 * 32768,

@@ -177,6 +177,15 @@ int arreau_fiber_norm(const float* x1, int32_t x1_f16_transposed, const float* f
                       const float* conv_bias, const float* ln_w, const float* ln_b, int32_t num_atoms_total, void* y,
                       int32_t y_f16, float* x2_debug, void* stream);
 
+/* K4b+K5+LayerNorm of the fp16 tensor path as ONE launch (what arreau_message_fiber_norm runs when kernels_f16 and
+ * y_f16 are both set): per 16-atom tile the receiver-sorted CSR sums are formed in shared memory (fp16, [atom][c][o]) and
+ * consumed there by the tensor-core fiber conv + LayerNorm; x1 never goes to HBM.  Same arguments and results as the
+ * gather + fiber_norm pair (bit-identical: same summation order, same roundings). */
+int arreau_message_fiber_norm_fused(const void* kernels_f16, const float* h, const int32_t* row_ptr, const int32_t* src,
+                                    const void* fiber_frag, const float* conv_bias, const float* ln_w,
+                                    const float* ln_b, int32_t num_atoms_total, void* y_f16, float* x2_debug,
+                                    void* stream);
+
 /* fiber_frag[L][C][32] (16 bytes each): the fp16 mma.sync B fragments of fiber_kernel[L,O,O,C] / O, one per
  * (layer, channel, lane) -- the operand of the tensor-core fiber conv of the fp16 path (64 KB per layer). */
 int arreau_fiber_frag_pack(const float* fiber_kernel, int32_t num_layers, void* fiber_frag, void* stream);

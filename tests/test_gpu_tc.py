@@ -170,3 +170,39 @@ def test_pooled_readout_matches_per_layer_readout(device, packed_weights, weight
     assert torch.equal(outs[0][3], outs[1][3])                  # the residual stream itself is untouched by the fusion
     for x, y in zip(outs[1][:3], outs[0][:3]):
         assert _rel(x, y) < 2e-5
+
+
+@pytest.mark.parametrize("num_atoms,cap", [([40] * 32, 8), ([5, 17, 2, 9, 1], 8), ([30, 7], 0), ([3], 8)])
+def test_fused_message_fiber_norm_equals_the_two_kernel_pair(device, packed_weights, weights_npz, num_atoms, cap):
+    """arreau_message_fiber_norm_fused (message sums kept in shared memory) against arreau_message_gather +
+    arreau_fiber_norm through HBM: same edge order, same roundings -> bit-identical y tile images.  Ragged tiles
+    (atom counts that are not multiples of 16), degrees that are not multiples of 8 and an uncapped graph included."""
+    from arreau_b200 import _lib
+    from arreau_b200.engine import DenoiseEngine, HIDDEN, NUM_ORI
+    from arreau_b200.tables import build_tables
+    rng = np.random.default_rng(17)
+    na = np.asarray(num_atoms)
+    lengths = np.cbrt(18.05 * na)[:, None] * (1.0 + 0.1 * rng.standard_normal((len(na), 3)))
+    angles = np.pi / 2 + 0.1 * rng.standard_normal((len(na), 3))
+    frac, types = rng.random((int(na.sum()), 3)), rng.integers(0, 89, int(na.sum()))
+    eng = DenoiseEngine(packed_weights, build_tables(1000, 90), weights_npz["fourier_w"], na, 5.0, cap,
+                        precision="fp16", device=device)
+    eng.set_state(frac, types, lengths, angles)
+    eng.predict_scores(400)                     # fills the kernel slabs and h (after the last layer)
+    torch.cuda.synchronize()
+    w, s = eng.w.t, torch.cuda.current_stream().cuda_stream
+    n_valid = eng.N * NUM_ORI * HIDDEN          # the tail of the last 128-row tile image is never written
+    for l in (0, 4):
+        frag = w["fiber_frag"].data_ptr() + l * HIDDEN * 32 * 16
+        args = (w["conv_bias"][l].data_ptr(), w["ln_w"][l].data_ptr(), w["ln_b"][l].data_ptr(), eng.N)
+        y_pair, y_fused = torch.zeros_like(eng.y), torch.zeros_like(eng.y)
+        _lib.call("arreau_message_gather", eng.kernels[l].data_ptr(), 1, eng.h.data_ptr(), eng.row_ptr.data_ptr(),
+                  eng.src.data_ptr(), eng.N, 1, eng.x1.data_ptr(), s)
+        _lib.call("arreau_fiber_norm", eng.x1.data_ptr(), 1, w["fiber_kernel"][l].data_ptr(), frag, *args,
+                  y_pair.data_ptr(), 1, None, s)
+        _lib.call("arreau_message_fiber_norm_fused", eng.kernels[l].data_ptr(), eng.h.data_ptr(), eng.row_ptr.data_ptr(),
+                  eng.src.data_ptr(), frag, *args, y_fused.data_ptr(), None, s)
+        torch.cuda.synchronize()
+        assert bool(torch.isfinite(y_pair.float()).all())
+        assert float(y_pair.float().abs().max()) > 0.1
+        assert torch.equal(y_pair.view(torch.int16), y_fused.view(torch.int16)), l
