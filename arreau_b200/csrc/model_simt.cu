@@ -116,7 +116,10 @@ node_embed_kernel(const float* __restrict__ x, const float* __restrict__ vec, co
     dots[idx] = p[0] * ori[3 * o] + p[1] * ori[3 * o + 1] + p[2] * ori[3 * o + 2];   // to_from_sphere.py:7-8
   }
   __syncthreads();
-  if (a >= nb) return;
+  float4 pq[4];
+#pragma unroll
+  for (int q = 0; q < 4; ++q) pq[q] = make_float4(0.f, 0.f, 0.f, 0.f);
+  if (a < nb) {
   const float* xr = xs + a * F;
   float4 s = make_float4(0.f, 0.f, 0.f, 0.f);
   int f0 = 0;
@@ -135,10 +138,7 @@ node_embed_kernel(const float* __restrict__ x, const float* __restrict__ vec, co
   for (int v = 0; v < kMaxVec; ++v)
     wv[v] = v < V ? __ldg(reinterpret_cast<const float4*>(w_t + (size_t)(F + v) * kC + lane * 4)) : make_float4(0.f, 0.f, 0.f, 0.f);
   float* hp = h + (size_t)(b0 + a) * kO * kC + lane * 4;
-  // optional orientation-pooled copy for the pooled read-out (pool[b][0] = mean_o h, pool[b][1+d] = (1/O) sum_o ori[o][d] h)
-  float4 pq[4];
-#pragma unroll
-  for (int q = 0; q < 4; ++q) pq[q] = make_float4(0.f, 0.f, 0.f, 0.f);
+  // optional orientation-pooled copy for the pooled read-out (part 0 = mean_o h, part 1+d = (1/O) sum_o ori[o][d] h)
 #pragma unroll 4
   for (int o = 0; o < kO; ++o) {
     float4 r = s;
@@ -159,12 +159,27 @@ node_embed_kernel(const float* __restrict__ x, const float* __restrict__ vec, co
       }
     }
   }
+  }
   if (pool) {
+    // pool[group of 16 atoms][4 parts][C][16 atoms] (the layout readout_pooled_kernel streams): the CTA's 8 atoms are
+    // one half of a group; transpose [atom][part][c] -> [part][c][atom] through shared memory (re-using xs / dots)
     constexpr float inv = 1.0f / kO;
-    float* pp = pool + (size_t)(b0 + a) * 4 * kC + lane * 4;
+    __syncthreads();
+    float* tp = sm;                                            // [8 atoms][4][kC]
 #pragma unroll
     for (int q = 0; q < 4; ++q)
-      *reinterpret_cast<float4*>(pp + q * kC) = make_float4(pq[q].x * inv, pq[q].y * inv, pq[q].z * inv, pq[q].w * inv);
+      *reinterpret_cast<float4*>(tp + (a * 4 + q) * kC + lane * 4) =
+          make_float4(pq[q].x * inv, pq[q].y * inv, pq[q].z * inv, pq[q].w * inv);
+    __syncthreads();
+    float* pg = pool + (size_t)(blockIdx.x >> 1) * 4 * kC * 16 + (size_t)(blockIdx.x & 1) * 8;
+    for (int pc = tid; pc < 4 * kC; pc += kEmbedNodes * 32) {  // pc = part * kC + c
+      float v[8];
+#pragma unroll
+      for (int aa = 0; aa < 8; ++aa) v[aa] = tp[aa * 4 * kC + pc];
+      float4* po = reinterpret_cast<float4*>(pg + (size_t)pc * 16);
+      po[0] = make_float4(v[0], v[1], v[2], v[3]);
+      po[1] = make_float4(v[4], v[5], v[6], v[7]);
+    }
   }
 }
 
@@ -1093,84 +1108,136 @@ readout_accumulate_kernel(const float* __restrict__ h, const float* __restrict__
   }
 }
 
-// Pooled read-out of all layers in one pass (fp16 tensor path).  pool[k][b][4][C], k = 0..L, holds the orientation-pooled
-// features after the embedding (k = 0, node_embed_kernel) and the pooled residual UPDATE of interaction layer k
-// (k = 1..L, epilogue of convnext_mlp_tc_kernel): [mean_o . | (1/O) sum_o ori[o][d] ., d = 0..2].  The read-out Linear
-// commutes with the pooling (to_from_sphere.py:10-14) and the feature after layer l is the sum of entries 0..l, so
+// Pooled read-out of all layers in one pass (fp16 tensor path).  pool[k], k = 0..L, holds the orientation-pooled features
+// after the embedding (k = 0, node_embed_kernel) and the pooled residual UPDATE of interaction layer k (k = 1..L, pool
+// warps of convnext_mlp_tc_kernel), as [group of 16 atoms][4 parts][C][16 atoms] with parts
+// [mean_o . | (1/O) sum_o ori[o][d] ., d = 0..2].  The read-out Linear commutes with the pooling
+// (to_from_sphere.py:10-14) and the feature after layer l is the sum of entries 0..l, so
 //   mean_l read_out_l(h_l) = sum_k V_k pool[k] + bias,   V_k = (1/L) sum_{l >= max(k,1)} Wr_l
 // with V_k[C][96] and bias[96] combined once on the host (weights.py) in the column layout of acc[N][Z+6]:
-// columns 0..Z-1 logits, Z..Z+2 the score vector (weight row Z applied to pool[.][1+d]), Z+3..Z+5 length channels.
-// Persistent CTAs; per k the 48 KB matrix sits in shared memory, 16-atom groups stream through a cp.async double
-// buffer, thread j owns output column j (warps 0..2; the three score columns are recomputed by warp 3 on the vector
-// part), acc is updated in place in a fixed order (deterministic).
+// columns 0..Z-1 logits, Z..Z+2 the score vector (weight row Z applied to parts 1..3), Z+3..Z+5 length channels.
+// One persistent CTA per SM; per entry k the 48 KB matrix sits in shared memory; a warp owns a group of 16 atoms:
+// lane = output columns (lane, lane + 32, lane + 64), 16 atoms x 3 columns accumulated as packed FFMA2 over atom pairs;
+// the group's pooled block streams through a per-warp cp.async double buffer in chunks of 32 channels; acc is updated
+// in place in a fixed order (deterministic).
 constexpr int kPoolAtoms = 16;
 constexpr int kPoolCols = 96;
-constexpr int kPoolSmem = (kC * kPoolCols + 2 * kPoolAtoms * 4 * kC) * (int)sizeof(float);
+constexpr int kPoolWarps = 8;
+constexpr int kPoolChunkC = 32;                                                 // channels per chunk
+constexpr int kPoolChunkFloats = 4 * kPoolChunkC * kPoolAtoms;                  // 2048 floats = 8 KB
+constexpr int kPoolSmem = (kC * kPoolCols + kPoolWarps * 2 * kPoolChunkFloats) * (int)sizeof(float);   // 176 KB
 
-__global__ void __launch_bounds__(kC)
+__global__ void __launch_bounds__(kPoolWarps * 32, 1)
 readout_pooled_kernel(const float* __restrict__ pool, const float* __restrict__ v, const float* __restrict__ bias, int N,
                       int Z, int entries, float* __restrict__ acc) {
   extern __shared__ __align__(16) float rp_sm[];
-  float* const vs = rp_sm;                                  // [kC][kPoolCols]
-  float* const ps = rp_sm + kC * kPoolCols;                 // [2][kPoolAtoms][4][kC]
+  float* const vs = rp_sm;                                                       // [kC][kPoolCols]
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  float* const pb = rp_sm + kC * kPoolCols + warp * 2 * kPoolChunkFloats;        // this warp's [2][4 parts][32 c][16 atoms]
   const int groups = (N + kPoolAtoms - 1) / kPoolAtoms;
-  // column and pooled part of this thread
-  const bool vec_thread = warp == 3;
-  const bool active = vec_thread ? lane < 3 : !(tid >= Z && tid < Z + 3);
-  const int col = vec_thread ? Z + (lane < 3 ? lane : 0) : tid;
-  const int part = vec_thread ? 1 + (lane < 3 ? lane : 0) : 0;
-  auto load_group = [&](int k, int g, int buf) {
-    const int b0 = g * kPoolAtoms;
-    const int nb = min(kPoolAtoms, N - b0);
-    const float* src = pool + ((size_t)k * N + b0) * 4 * kC;
-    float* dst = ps + buf * kPoolAtoms * 4 * kC;
-    for (int i = tid; i < nb * kC; i += kC) cp_async16(dst + 4 * i, src + 4 * i);
+  const size_t entry_floats = (size_t)groups * 4 * kC * kPoolAtoms;
+  // columns Z..Z+2 (the score vector) read parts 1..3 instead of part 0: they are computed on the side with
+  // lane = (atom sa, half of the chunk's channels sh); the lanes that own them as a "third column" skip that column
+  const int col2 = lane + 64;
+  const bool skip2 = col2 >= Z && col2 < Z + 3;
+  const int sa = lane & 15, sh = lane >> 4;
+  auto load_chunk = [&](const float* gsrc, int ch, int buf) {                    // 4 parts x 2 KB, 16 bytes per lane and copy
+    float* dst = pb + buf * kPoolChunkFloats;
+#pragma unroll
+    for (int part = 0; part < 4; ++part)
+#pragma unroll
+      for (int i = 0; i < 4; ++i)
+        cp_async16(dst + part * kPoolChunkC * kPoolAtoms + (i * 32 + lane) * 4,
+                   gsrc + ((size_t)part * kC + ch * kPoolChunkC) * kPoolAtoms + (i * 32 + lane) * 4);
     cp_async_commit();
   };
   for (int k = 0; k < entries; ++k) {
-    __syncthreads();                                        // previous matrix and buffers are no longer read
-    for (int i = tid; i < kC * kPoolCols / 4; i += kC)
+    __syncthreads();                                                             // the previous matrix is no longer read
+    for (int i = tid; i < kC * kPoolCols / 4; i += kPoolWarps * 32)
       reinterpret_cast<float4*>(vs)[i] = __ldg(reinterpret_cast<const float4*>(v + (size_t)k * kC * kPoolCols) + i);
-    int it = 0;
-    if ((int)blockIdx.x < groups) load_group(k, blockIdx.x, 0);
-    for (int g = blockIdx.x; g < groups; g += gridDim.x, ++it) {
-      const int buf = it & 1;
-      if (g + (int)gridDim.x < groups) {
-        load_group(k, g + gridDim.x, buf ^ 1);
-        cp_async_wait<1>();
-      } else {
-        cp_async_wait<0>();
-      }
-      __syncthreads();
+    __syncthreads();
+    for (int g = blockIdx.x * kPoolWarps + warp; g < groups; g += gridDim.x * kPoolWarps) {
+      const float* gsrc = pool + (size_t)k * entry_floats + (size_t)g * 4 * kC * kPoolAtoms;
       const int b0 = g * kPoolAtoms;
-      const int nb = min(kPoolAtoms, N - b0);
-      if (active) {
-        float r[kPoolAtoms];
-        if (k == 0) {
-          const float bb = bias[col];
+      load_chunk(gsrc, 0, 0);
+      float2 r[3][kPoolAtoms / 2];
+      float sc[3];
+      if (k == 0) {
 #pragma unroll
-          for (int a = 0; a < kPoolAtoms; ++a) r[a] = bb;
-        } else {
+        for (int j = 0; j < 3; ++j) {
+          const float bb = bias[lane + 32 * j];
 #pragma unroll
-          for (int a = 0; a < kPoolAtoms; ++a) r[a] = a < nb ? acc[(size_t)(b0 + a) * kPoolCols + col] : 0.f;
+          for (int a = 0; a < kPoolAtoms / 2; ++a) r[j][a] = make_float2(bb, bb);
         }
-        const float* pp = ps + buf * kPoolAtoms * 4 * kC + part * kC;
-#pragma unroll 2
-        for (int c = 0; c < kC; c += 4) {
-          const float w0 = vs[(c + 0) * kPoolCols + col], w1 = vs[(c + 1) * kPoolCols + col];
-          const float w2 = vs[(c + 2) * kPoolCols + col], w3 = vs[(c + 3) * kPoolCols + col];
 #pragma unroll
-          for (int a = 0; a < kPoolAtoms; ++a) {
-            const float4 p = *reinterpret_cast<const float4*>(pp + a * 4 * kC + c);
-            r[a] = fmaf(w0, p.x, r[a]); r[a] = fmaf(w1, p.y, r[a]); r[a] = fmaf(w2, p.z, r[a]); r[a] = fmaf(w3, p.w, r[a]);
+        for (int d = 0; d < 3; ++d) sc[d] = sh == 0 ? bias[Z + d] : 0.f;
+      } else {
+#pragma unroll
+        for (int j = 0; j < 3; ++j)
+#pragma unroll
+          for (int a = 0; a < kPoolAtoms / 2; ++a) {
+            const int a0 = b0 + 2 * a;
+            const bool skip = j == 2 && skip2;
+            r[j][a].x = (a0 < N && !skip) ? acc[(size_t)a0 * kPoolCols + lane + 32 * j] : 0.f;
+            r[j][a].y = (a0 + 1 < N && !skip) ? acc[(size_t)(a0 + 1) * kPoolCols + lane + 32 * j] : 0.f;
+          }
+#pragma unroll
+        for (int d = 0; d < 3; ++d) sc[d] = (sh == 0 && b0 + sa < N) ? acc[(size_t)(b0 + sa) * kPoolCols + Z + d] : 0.f;
+      }
+#pragma unroll 1
+      for (int ch = 0; ch < kC / kPoolChunkC; ++ch) {
+        if (ch + 1 < kC / kPoolChunkC) {
+          load_chunk(gsrc, ch + 1, (ch + 1) & 1);
+          cp_async_wait<1>();
+        } else {
+          cp_async_wait<0>();
+        }
+        __syncwarp();
+        const float* p0 = pb + (ch & 1) * kPoolChunkFloats;
+        const float* w = vs + (size_t)ch * kPoolChunkC * kPoolCols + lane;
+        {
+          // score vector: sc[d] += V[c][Z] * part(1+d)[c][atom sa] over this lane's half of the chunk's channels
+          const float* wz = vs + ((size_t)ch * kPoolChunkC + sh * (kPoolChunkC / 2)) * kPoolCols + Z;
+          const float* ps = p0 + (kPoolChunkC + sh * (kPoolChunkC / 2)) * kPoolAtoms + sa;
+#pragma unroll 4
+          for (int c = 0; c < kPoolChunkC / 2; ++c) {
+            const float wv = wz[c * kPoolCols];
+#pragma unroll
+            for (int d = 0; d < 3; ++d) sc[d] = fmaf(wv, ps[(d * kPoolChunkC + c) * kPoolAtoms], sc[d]);
           }
         }
+#pragma unroll 2
+        for (int c = 0; c < kPoolChunkC; ++c) {
+          const float w0 = w[c * kPoolCols], w1 = w[c * kPoolCols + 32], w2 = w[c * kPoolCols + 64];
+          const float2 w0d = make_float2(w0, w0), w1d = make_float2(w1, w1), w2d = make_float2(w2, w2);
 #pragma unroll
-        for (int a = 0; a < kPoolAtoms; ++a)
-          if (a < nb) acc[(size_t)(b0 + a) * kPoolCols + col] = r[a];
+          for (int q4 = 0; q4 < kPoolAtoms / 4; ++q4) {
+            const float4 pa = *reinterpret_cast<const float4*>(p0 + c * kPoolAtoms + 4 * q4);
+            const float2 pa0 = make_float2(pa.x, pa.y), pa1 = make_float2(pa.z, pa.w);
+            r[0][2 * q4] = __ffma2_rn(w0d, pa0, r[0][2 * q4]);
+            r[0][2 * q4 + 1] = __ffma2_rn(w0d, pa1, r[0][2 * q4 + 1]);
+            r[1][2 * q4] = __ffma2_rn(w1d, pa0, r[1][2 * q4]);
+            r[1][2 * q4 + 1] = __ffma2_rn(w1d, pa1, r[1][2 * q4 + 1]);
+            r[2][2 * q4] = __ffma2_rn(w2d, pa0, r[2][2 * q4]);
+            r[2][2 * q4 + 1] = __ffma2_rn(w2d, pa1, r[2][2 * q4 + 1]);
+          }
+        }
+        __syncwarp();                                                            // the buffer is refilled two chunks later
       }
-      __syncthreads();                                      // buffer `buf` is free for the load issued next iteration
+#pragma unroll
+      for (int j = 0; j < 3; ++j)
+#pragma unroll
+        for (int a = 0; a < kPoolAtoms / 2; ++a) {
+          const int a0 = b0 + 2 * a;
+          const bool skip = j == 2 && skip2;
+          if (a0 < N && !skip) acc[(size_t)a0 * kPoolCols + lane + 32 * j] = r[j][a].x;
+          if (a0 + 1 < N && !skip) acc[(size_t)(a0 + 1) * kPoolCols + lane + 32 * j] = r[j][a].y;
+        }
+#pragma unroll
+      for (int d = 0; d < 3; ++d) {
+        const float tot = sc[d] + __shfl_xor_sync(0xffffffffu, sc[d], 16);
+        if (sh == 0 && b0 + sa < N) acc[(size_t)(b0 + sa) * kPoolCols + Z + d] = tot;
+      }
     }
   }
 }
@@ -1215,7 +1282,8 @@ static int node_embed_launch(const float* x, const float* vec, const float* w_em
   if (N == 0) return ARREAU_OK;
   if (!x || !vec || !w_embed_t || !ori || !h) return ARREAU_ERR_NULL;
   if (N < 0 || F <= 0 || V < 0 || V > kMaxVec || (types && (Z <= 0 || Z > F))) return ARREAU_ERR_BAD_SHAPE;
-  const size_t smem = sizeof(float) * (size_t)kEmbedNodes * (F + V * kO);
+  size_t smem = sizeof(float) * (size_t)kEmbedNodes * (F + V * kO);
+  if (pool && smem < sizeof(float) * kEmbedNodes * 4 * kC) smem = sizeof(float) * kEmbedNodes * 4 * kC;
   if (smem > 48 * 1024) return ARREAU_ERR_UNSUPPORTED;
   node_embed_kernel<<<(N + kEmbedNodes - 1) / kEmbedNodes, kEmbedNodes * 32, smem, (cudaStream_t)stream>>>(
       x, vec, w_embed_t, ori, types, Z, N, F, V, h, pool);
@@ -1415,8 +1483,10 @@ extern "C" int arreau_readout_pooled(const float* pool, const float* readout_v, 
     attr_set = true;
   }
   const int groups = (N + kPoolAtoms - 1) / kPoolAtoms;
-  const int grid = groups < 2 * num_sms() ? groups : 2 * num_sms();
-  readout_pooled_kernel<<<grid, kC, kPoolSmem, (cudaStream_t)stream>>>(pool, readout_v, readout_bias, N, Z, entries, acc);
+  const int ctas = (groups + kPoolWarps - 1) / kPoolWarps;
+  const int grid = ctas < num_sms() ? ctas : num_sms();
+  readout_pooled_kernel<<<grid, kPoolWarps * 32, kPoolSmem, (cudaStream_t)stream>>>(pool, readout_v, readout_bias, N, Z,
+                                                                                    entries, acc);
   CUDA_LAUNCH_CHECK();
   return ARREAU_OK;
 }

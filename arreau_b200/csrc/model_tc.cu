@@ -255,7 +255,10 @@ convnext_mlp_tc_kernel(const uint8_t* __restrict__ y_img, const uint8_t* __restr
             if (j == 0) asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");
             else asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
           }
-          asm volatile("bar.sync 1, %0;" ::"n"(kEpiThreads) : "memory");
+          // with pooling the pool warps (barriers 3 / 4) must also be done reading this half of the staged update
+          if (!pool_out) asm volatile("bar.sync 1, %0;" ::"n"(kEpiThreads) : "memory");
+          else if (j == 0) asm volatile("bar.sync 3, %0;" ::"n"(kEpiThreads + 64) : "memory");
+          else asm volatile("bar.sync 4, %0;" ::"n"(kEpiThreads + 64) : "memory");
         }
         {
           // hidden unit k = cgi*32 .. +31 of this 128-slice -> slab cgi>>1, chunks (cgi&1)*4 .. +3
@@ -274,11 +277,6 @@ convnext_mlp_tc_kernel(const uint8_t* __restrict__ y_img, const uint8_t* __restr
         TC_STAMP(2 + 2 * j);
       }
       TC_STAMP(9);
-      // pooled read-out (see readout_pooled_kernel): epilogue thread et owns channel et & 127 of atoms (et >> 7) and
-      // (et >> 7) + 4 of the tile's 8
-      const int et = (int)threadIdx.x - kEpiWarp0 * 32;
-      const int pc = et & 127, pa = et >> 7;
-      const long long n_atoms = rows / kO;
       mbar_wait(&bars.d2_full, it & 1);
       tc_fence_after();
       TC_STAMP(10);
@@ -318,6 +316,10 @@ convnext_mlp_tc_kernel(const uint8_t* __restrict__ y_img, const uint8_t* __restr
 #pragma unroll
         for (int st = 0; st < 8; ++st) *reinterpret_cast<float4*>(srow + (((st + r) & 7) << 4)) = d[st];
         fence_proxy_async();
+        if (pool_out) {                                  // staged tile complete -> pool warps
+          __threadfence_block();
+          asm volatile("bar.arrive 2, %0;" ::"n"(kEpiThreads + 64) : "memory");
+        }
         asm volatile("bar.sync 1, %0;" ::"n"(kEpiThreads) : "memory");
         if (is_issuer) {
           const long long row0 = tile * kTileM;
@@ -334,37 +336,60 @@ convnext_mlp_tc_kernel(const uint8_t* __restrict__ y_img, const uint8_t* __restr
             asm volatile("cp.async.bulk.commit_group;" ::: "memory");   // (possibly empty) group per half
           }
         }
-        if (pool_out) {
-          // pool the staged update over the 16 orientation rows of each atom (read-only on the staging buffers, which
-          // stay intact until the next tile's bar.sync)
-          const float* stage = reinterpret_cast<const float*>(H0);
-          constexpr float inv = 1.0f / kO;
-#pragma unroll
-          for (int rep = 0; rep < 2; ++rep) {
-            const int a = pa + 4 * rep;
-            const long long atom = tile * (kTileM / kO) + a;
-            float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f;
-#pragma unroll
-            for (int o = 0; o < kO; ++o) {
-              const float u = stage[(a * kO + o) * kC + pc];
-              s0 += u;
-              s1 = fmaf(s_ori[3 * o + 0], u, s1);
-              s2 = fmaf(s_ori[3 * o + 1], u, s2);
-              s3 = fmaf(s_ori[3 * o + 2], u, s3);
-            }
-            if (atom < n_atoms) {
-              float* po = pool_out + (size_t)atom * 4 * kC + pc;
-              po[0] = s0 * inv;
-              po[kC] = s1 * inv;
-              po[2 * kC] = s2 * inv;
-              po[3 * kC] = s3 * inv;
-            }
-          }
-        }
       }
       TC_STAMP(11);
     }
     if (is_issuer) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");   // every update has been added into h
+  } else if ((warp == 2 || warp == 3) && pool_out) {
+    // ---------------- pooled read-out (see readout_pooled_kernel): the two otherwise idle warps pool the staged residual
+    // update over the 16 orientation rows of each of the tile's 8 atoms.  Two phases, one per staging half (rows 0..63 =
+    // atoms 0..3, then atoms 4..7), each released to the epilogue warps separately (barriers 3 and 4) so the next
+    // tile's H writes are not held up; per phase warp 2 takes the first atom pair, warp 3 the second, lane = 4 channels.
+    // pool_out[group of 16 atoms][4 parts][C][16 atoms]; a tile is one half (8 atoms) of a group ----------------
+    const float* stage = reinterpret_cast<const float*>(H0);
+    constexpr float inv = 1.0f / kO;
+    const int c2 = (warp - 2) * 64 + lane * 2;               // this thread's channel pair
+    for (long long tile = blockIdx.x; tile < tiles; tile += gridDim.x) {
+      asm volatile("bar.sync 2, %0;" ::"n"(kEpiThreads + 64) : "memory");
+      const bool more = tile + gridDim.x < tiles;            // the last tile has no successor waiting on barriers 3 / 4
+      float2 acc[2][4][4];                                   // [phase][part][atom of the phase]: (channel c2, c2 + 1)
+#pragma unroll
+      for (int ph = 0; ph < 2; ++ph) {
+#pragma unroll
+        for (int part = 0; part < 4; ++part)
+#pragma unroll
+          for (int a = 0; a < 4; ++a) acc[ph][part][a] = make_float2(0.f, 0.f);
+#pragma unroll 2
+        for (int o = 0; o < kO; ++o) {
+          const float ox = s_ori[3 * o], oy = s_ori[3 * o + 1], oz = s_ori[3 * o + 2];
+          const float2 dx = make_float2(ox, ox), dy = make_float2(oy, oy), dz = make_float2(oz, oz);
+#pragma unroll
+          for (int a = 0; a < 4; ++a) {
+            const float2 v = *reinterpret_cast<const float2*>(stage + ((ph * 4 + a) * kO + o) * kC + c2);
+            acc[ph][0][a].x += v.x; acc[ph][0][a].y += v.y;
+            acc[ph][1][a] = __ffma2_rn(dx, v, acc[ph][1][a]);
+            acc[ph][2][a] = __ffma2_rn(dy, v, acc[ph][2][a]);
+            acc[ph][3][a] = __ffma2_rn(dz, v, acc[ph][3][a]);
+          }
+        }
+        // done reading this staging half
+        if (more) {
+          if (ph == 0) asm volatile("bar.arrive 3, %0;" ::"n"(kEpiThreads + 64) : "memory");
+          else asm volatile("bar.arrive 4, %0;" ::"n"(kEpiThreads + 64) : "memory");
+        }
+      }
+      // the tile's 8 atoms of one (part, channel) are one full 32-byte sector of the group's block
+      float* const pg = pool_out + (size_t)(tile >> 1) * 4 * kC * 16 + (size_t)(tile & 1) * 8;
+#pragma unroll
+      for (int part = 0; part < 4; ++part) {
+        float4* p0 = reinterpret_cast<float4*>(pg + ((size_t)part * kC + c2) * 16);
+        float4* p1 = reinterpret_cast<float4*>(pg + ((size_t)part * kC + c2 + 1) * 16);
+        p0[0] = make_float4(acc[0][part][0].x * inv, acc[0][part][1].x * inv, acc[0][part][2].x * inv, acc[0][part][3].x * inv);
+        p0[1] = make_float4(acc[1][part][0].x * inv, acc[1][part][1].x * inv, acc[1][part][2].x * inv, acc[1][part][3].x * inv);
+        p1[0] = make_float4(acc[0][part][0].y * inv, acc[0][part][1].y * inv, acc[0][part][2].y * inv, acc[0][part][3].y * inv);
+        p1[1] = make_float4(acc[1][part][0].y * inv, acc[1][part][1].y * inv, acc[1][part][2].y * inv, acc[1][part][3].y * inv);
+      }
+    }
   }
   tc_fence_before();
   __syncthreads();

@@ -40,7 +40,7 @@ def _i32(a, device):
 class DenoiseEngine:
     def __init__(self, weights: PonitaWeights, tables: DiffusionTables, fourier_w, num_atoms: Sequence[int],
                  radius: float, max_neighbors: int, precision: str = "fp32", edge_capacity: Optional[int] = None,
-                 debug: bool = False, device="cuda", pooled_readout: bool = False):
+                 debug: bool = False, device="cuda", pooled_readout: bool = True):
         if precision not in PRECISIONS:
             raise ValueError(f"precision must be one of {sorted(PRECISIONS)}")
         _lib.load()
@@ -78,7 +78,7 @@ class DenoiseEngine:
         self.logits, self.score, self.len0 = f32(N, Z), f32(N, 3), f32(G, 3)
         self.h, self.acc, self.x1 = f32(N, NUM_ORI, HIDDEN), f32(N, Z + 6), f32(N, NUM_ORI, HIDDEN)
         # orientation-pooled features per layer: the fp16 path's read-outs run on these (arreau_readout_pooled)
-        self.pool = (f32(LAYERS + 1, N, 4, HIDDEN)
+        self.pool = (f32(LAYERS + 1, (N + 15) // 16, 4, HIDDEN, 16)
                      if (self.precision == "fp16" and pooled_readout and "readout_v" in weights.t) else None)
         if precision == "fp16":     # 128-row UMMA tile images (32 KB each), see arreau_message_fiber_norm
             self.y = torch.zeros(((N * NUM_ORI + 127) // 128) * 128 * HIDDEN, device=dev, dtype=torch.float16)

@@ -200,13 +200,14 @@ int arreau_convnext_mlp_f16(const void* y_img, const void* w_img, const float* b
                              const float* layer_scale, int64_t num_rows, float* h, void* stream);
 
 /* Pooled read-out path of the fp16 tensor path (K7 fused into K2 / K6; ponita.py:105-117, to_from_sphere.py:10-14).
- * The read-out Linear commutes with the orientation pooling, so only pooled features are needed:
- *   pool[b][0][c] = mean_o h[b,o,c],   pool[b][1+d][c] = (1/O) sum_o ori[o][d] h[b,o,c]      ([N,4,C] f32 per layer).
- * pool is [L+1,N,4,C]: entry 0 = pooled features after the embedding, entry k = 1..L the pooled residual UPDATE of
- * interaction layer k (the feature after layer l is the sum of entries 0..l).
+ * The read-out Linear commutes with the orientation pooling, so only pooled features are needed.  One pool ENTRY is
+ * f32 [ceil(N/16)][4][C][16]: for each group of 16 atoms and channel c the 16 atoms' values of the four parts
+ *   part 0 = mean_o x[b,o,c],   part 1+d = (1/O) sum_o ori[o][d] x[b,o,c].
+ * pool is [L+1] entries: entry 0 pools the embedding output, entry k = 1..L pools the residual UPDATE of interaction
+ * layer k (the feature after layer l is the sum of entries 0..l).
  * arreau_node_embed_pooled: K2 that also writes entry 0 (types may be NULL).
- * arreau_convnext_mlp_f16_pooled: K6 whose epilogue pools the residual update it has staged in shared memory into
- *   pool_out ([N,4,C], one entry); h itself is updated as by arreau_convnext_mlp_f16.
+ * arreau_convnext_mlp_f16_pooled: K6 whose two spare warps pool the residual update staged in shared memory into
+ *   pool_out (one entry); h itself is updated as by arreau_convnext_mlp_f16.
  * arreau_readout_pooled: acc[N,Z+6] (column layout of arreau_readout_accumulate, already divided by L) =
  *   sum_k readout_v[k] pool[k] + readout_bias, with readout_v[L+1][C][Z+6], readout_bias[Z+6] the per-entry sums of
  *   the read-out weights combined on the host (arreau_b200/weights.py: pooled_readout_weights); entries = L+1. */
@@ -278,7 +279,7 @@ typedef struct arreau_workspace {
   float* h_debug;   /* NULL, or [L+1,N,O,C] f32 (h after the embedding and after each layer) */
   int64_t edge_capacity;
   const int64_t* onehot_types; /* NULL, or types[N]: x[:, 0:Z] is one_hot(types) (lets the embedding skip the zeros) */
-  float* pool;      /* NULL, or [L+1,N,4,C] f32 pooled features / updates -> the fp16 path uses the pooled read-out */
+  float* pool;      /* NULL, or [L+1] pool entries (see arreau_readout_pooled) -> the fp16 path uses the pooled read-out */
 } arreau_workspace;
 
 /* PonitaFiberBundle.forward (ponita/models/ponita.py:88-123) on a prebuilt graph: x[N,F], vec[N,V,3] f32;
