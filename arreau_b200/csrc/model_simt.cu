@@ -683,43 +683,54 @@ message_fiber_norm_fused_kernel(const __half* __restrict__ kern, const float* __
       if (node >= N) break;                                    // rows past N are never stored (v0 / v1 below)
       const int e0 = row_ptr[node], e1 = row_ptr[node + 1];
       uint8_t* dst = s_a + (size_t)a * kFusedRowBytes + lane * 144;
+      int sj0[8];                                              // sources of the first 8 edges: loaded once per atom
+#pragma unroll
+      for (int u = 0; u < 8; ++u) sj0[u] = e1 > e0 ? __ldg(src + min(e0 + u, e1 - 1)) : 0;
 #pragma unroll 1
       for (int op = 0; op < kO / 2; ++op) {
-        float4 acc[2];
+        // both orientations of the pair at once: 32 independent loads per lane in flight
+        const int o0 = 2 * op;
+        float4 s0 = make_float4(0.f, 0.f, 0.f, 0.f), s1 = s0;
+        const int koff0 = (((lane >> 1) ^ o0) << 3) | ((lane & 1) << 2);
+        const int koff1 = (((lane >> 1) ^ (o0 + 1)) << 3) | ((lane & 1) << 2);
+        for (int e = e0; e < e1; e += 8) {
+          uint2 kv0[8], kv1[8];
+          float4 hv0[8], hv1[8];
 #pragma unroll
-        for (int oo = 0; oo < 2; ++oo) {
-          const int o = 2 * op + oo;
-          float4 s4 = make_float4(0.f, 0.f, 0.f, 0.f);
-          for (int e = e0; e < e1; e += 8) {
-            uint2 kv[8];
-            float4 hv[8];
+          for (int u = 0; u < 8; ++u) {
+            const int ee = min(e + u, e1 - 1);                  // clamped: loads stay in range, the tail is masked below
+            const int sj = e == e0 ? sj0[u] : __ldg(src + ee);
+            const __half* krow = kern + ((size_t)ee * kO + o0) * kC;
+            // the slab is streamed once: keep it out of L1, which holds the fiber-kernel fragments and re-used h rows
+            asm volatile("ld.global.L1::no_allocate.v2.u32 {%0, %1}, [%2];" : "=r"(kv0[u].x), "=r"(kv0[u].y) : "l"(krow + koff0));
+            asm volatile("ld.global.L1::no_allocate.v2.u32 {%0, %1}, [%2];" : "=r"(kv1[u].x), "=r"(kv1[u].y) : "l"(krow + kC + koff1));
+            const float* hrow = h + ((size_t)sj * kO + o0) * kC + lane * 4;
+            hv0[u] = *reinterpret_cast<const float4*>(hrow);
+            hv1[u] = *reinterpret_cast<const float4*>(hrow + kC);
+          }
 #pragma unroll
-            for (int u = 0; u < 8; ++u) {
-              const int ee = min(e + u, e1 - 1);                // clamped: loads stay in range, the tail is masked below
-              const int sj = __ldg(src + ee);
-              const __half* krow = kern + ((size_t)ee * kO + o) * kC;
-              kv[u] = *reinterpret_cast<const uint2*>(krow + ((((lane >> 1) ^ o) << 3) | ((lane & 1) << 2)));
-              hv[u] = *reinterpret_cast<const float4*>(h + ((size_t)sj * kO + o) * kC + lane * 4);
-            }
-#pragma unroll
-            for (int u = 0; u < 8; ++u) {
-              if (e + u < e1) {
-                const float2 k0 = __half22float2(*reinterpret_cast<const __half2*>(&kv[u].x));
-                const float2 k1 = __half22float2(*reinterpret_cast<const __half2*>(&kv[u].y));
-                s4.x = fmaf(k0.x, hv[u].x, s4.x);
-                s4.y = fmaf(k0.y, hv[u].y, s4.y);
-                s4.z = fmaf(k1.x, hv[u].z, s4.z);
-                s4.w = fmaf(k1.y, hv[u].w, s4.w);
-              }
+          for (int u = 0; u < 8; ++u) {
+            if (e + u < e1) {
+              const float2 a0 = __half22float2(*reinterpret_cast<const __half2*>(&kv0[u].x));
+              const float2 a1 = __half22float2(*reinterpret_cast<const __half2*>(&kv0[u].y));
+              s0.x = fmaf(a0.x, hv0[u].x, s0.x);
+              s0.y = fmaf(a0.y, hv0[u].y, s0.y);
+              s0.z = fmaf(a1.x, hv0[u].z, s0.z);
+              s0.w = fmaf(a1.y, hv0[u].w, s0.w);
+              const float2 b0 = __half22float2(*reinterpret_cast<const __half2*>(&kv1[u].x));
+              const float2 b1 = __half22float2(*reinterpret_cast<const __half2*>(&kv1[u].y));
+              s1.x = fmaf(b0.x, hv1[u].x, s1.x);
+              s1.y = fmaf(b0.y, hv1[u].y, s1.y);
+              s1.z = fmaf(b1.x, hv1[u].z, s1.z);
+              s1.w = fmaf(b1.y, hv1[u].w, s1.w);
             }
           }
-          acc[oo] = s4;
         }
         // channel 4 lane + i, orientations (2 op, 2 op + 1): one half2 at [c][o]
-        *reinterpret_cast<uint32_t*>(dst + 0 * 32 + op * 4) = pack_h2(acc[0].x, acc[1].x);
-        *reinterpret_cast<uint32_t*>(dst + 1 * 32 + op * 4) = pack_h2(acc[0].y, acc[1].y);
-        *reinterpret_cast<uint32_t*>(dst + 2 * 32 + op * 4) = pack_h2(acc[0].z, acc[1].z);
-        *reinterpret_cast<uint32_t*>(dst + 3 * 32 + op * 4) = pack_h2(acc[0].w, acc[1].w);
+        *reinterpret_cast<uint32_t*>(dst + 0 * 32 + op * 4) = pack_h2(s0.x, s1.x);
+        *reinterpret_cast<uint32_t*>(dst + 1 * 32 + op * 4) = pack_h2(s0.y, s1.y);
+        *reinterpret_cast<uint32_t*>(dst + 2 * 32 + op * 4) = pack_h2(s0.z, s1.z);
+        *reinterpret_cast<uint32_t*>(dst + 3 * 32 + op * 4) = pack_h2(s0.w, s1.w);
       }
     }
     __syncthreads();
