@@ -1,10 +1,11 @@
 // K1 -- periodic radius graph over the 27 lattice images (sm_100a).
 //
 // Replaces diffusion/diffusion_helpers.py:328-564 (radius_graph_pbc).  The reference materialises
-// ~10 tensors of 27*sum(n_g^2) rows; here one warp owns one receiver atom, walks its 27*n_g
-// candidates in (j, cell) order with lanes striding the candidate index, filters them with a
-// ballot, and (under the neighbour cap) keeps the `cap` nearest through a small shared-memory
-// selection buffer.  No candidate list ever reaches HBM: the only traffic is pos/lattice in
+// ~10 tensors of 27*sum(n_g^2) rows; here one warp owns one receiver atom and walks its 27*n_g
+// candidates in (j, cell) order -- lane = image cell (offset in registers), loop over the senders j
+// (one broadcast load of pos_j) -- filters them with a ballot, and (under the neighbour cap) keeps
+// the `cap` nearest through a small shared-memory selection buffer, pre-filtered by a log-spaced
+// distance-bin bound that the count pass derives from a per-receiver histogram.  No candidate list ever reaches HBM: the only traffic is pos/lattice in
 // (L1/L2 resident per crystal) and the surviving edges out.
 //
 // Arithmetic is fp64 with explicit round-to-nearest adds/muls (no FMA contraction) in the
@@ -22,10 +23,6 @@ constexpr int kWarpsPerBlock = 8;
 constexpr int kSelBuf = 256;      // selection buffer entries per warp
 constexpr int kMaxCap = kSelBuf - 32;
 
-struct WarpCtx {
-  double off[27][3];
-};
-
 __device__ __forceinline__ void cell_of(int k, int& c0, int& c1, int& c2) {
   // k-th element of itertools.product((-1,0,1), repeat=3)   (helpers:10)
   c0 = k / 9 - 1;
@@ -33,32 +30,39 @@ __device__ __forceinline__ void cell_of(int k, int& c0, int& c1, int& c2) {
   c2 = k % 3 - 1;
 }
 
-__device__ __forceinline__ void load_offsets(WarpCtx& ctx, const double* __restrict__ lat, int lane) {
-  if (lane < 27) {
-    int c0, c1, c2;
-    cell_of(lane, c0, c1, c2);
+// Lane = image k (27 of 32 lanes), loop over the senders j: the image offset lives in registers, pos_j is one
+// broadcast load, and (iteration j, lane k) is the reference's candidate order c = 27 j + k.
+__device__ __forceinline__ void lane_offset(const double* __restrict__ lat, int lane, double (&off)[3]) {
+  int c0, c1, c2;
+  cell_of(lane < 27 ? lane : 0, c0, c1, c2);
 #pragma unroll
-    for (int a = 0; a < 3; ++a) {
-      // bmm(lattice^T, cells): sum over lattice rows m = 0,1,2 in order (helpers:390-393)
-      double t0 = __dmul_rn((double)c0, lat[0 * 3 + a]);
-      double t1 = __dmul_rn((double)c1, lat[1 * 3 + a]);
-      double t2 = __dmul_rn((double)c2, lat[2 * 3 + a]);
-      ctx.off[lane][a] = __dadd_rn(__dadd_rn(t0, t1), t2);
-    }
+  for (int a = 0; a < 3; ++a) {
+    // bmm(lattice^T, cells): sum over lattice rows m = 0,1,2 in order (helpers:390-393)
+    const double t0 = __dmul_rn((double)c0, lat[0 * 3 + a]);
+    const double t1 = __dmul_rn((double)c1, lat[1 * 3 + a]);
+    const double t2 = __dmul_rn((double)c2, lat[2 * 3 + a]);
+    off[a] = __dadd_rn(__dadd_rn(t0, t1), t2);
   }
-  __syncwarp();
 }
-
-__device__ __forceinline__ double cand_d2(const WarpCtx& ctx, const double* __restrict__ pos, int start,
-                                          int c, double pix, double piy, double piz, double& dx,
-                                          double& dy, double& dz) {
-  const int j = c / 27, k = c - j * 27;
-  const double* pj = pos + 3 * (size_t)(start + j);
-  dx = __dadd_rn(__dadd_rn(pj[0], ctx.off[k][0]), -pix);
-  dy = __dadd_rn(__dadd_rn(pj[1], ctx.off[k][1]), -piy);
-  dz = __dadd_rn(__dadd_rn(pj[2], ctx.off[k][2]), -piz);
+__device__ __forceinline__ double lane_d2(const double* __restrict__ pj, const double (&off)[3], double pix, double piy,
+                                          double piz, double& dx, double& dy, double& dz) {
+  dx = __dadd_rn(__dadd_rn(pj[0], off[0]), -pix);
+  dy = __dadd_rn(__dadd_rn(pj[1], off[1]), -piy);
+  dz = __dadd_rn(__dadd_rn(pj[2], off[2]), -piz);
   return __dadd_rn(__dadd_rn(__dmul_rn(dx, dx), __dmul_rn(dy, dy)), __dmul_rn(dz, dz));
 }
+
+// Log-spaced distance bins (4 per octave of d2, from the self-edge threshold 1e-4 up): monotone in d2, so "all
+// candidates in bins <= b" is a superset of the cap nearest as soon as those bins hold >= cap candidates.  The count
+// pass histograms the in-range candidates per receiver and leaves that bin in the top byte of raw_count; the fill pass
+// rejects everything beyond it before it reaches the selection buffer (exactness is unaffected: the selection itself
+// still runs on the full (d2, candidate) keys).
+constexpr int kBins = 128;
+__device__ __forceinline__ int dist_bin(double d2) {
+  const int b = (int)(__float_as_uint((float)d2) >> 21) - (int)(0x38D1B717u >> 21);   // 0x38D1B717 = 1e-4f
+  return b < 0 ? 0 : (b > kBins - 1 ? kBins - 1 : b);
+}
+constexpr int kCountMask = 0x00FFFFFF;
 
 __device__ __forceinline__ bool cand_pass(double d2, double r2, int remove_self) {
   return (d2 <= r2) && (!remove_self || d2 > 0.0001);   // helpers:432-436
@@ -69,26 +73,59 @@ graph_count_kernel(const double* __restrict__ pos, const double* __restrict__ la
                    const int32_t* __restrict__ atom_offset, const int32_t* __restrict__ crystal_of_atom,
                    int N, double r2, int cap, int remove_self, int32_t* __restrict__ raw_count,
                    int32_t* __restrict__ deg, unsigned long long* __restrict__ nimg) {
-  __shared__ WarpCtx ctxs[kWarpsPerBlock];
+  __shared__ int s_hist[kWarpsPerBlock][kBins];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int i = blockIdx.x * kWarpsPerBlock + warp;
   if (i >= N) return;
-  WarpCtx& ctx = ctxs[warp];
+  int* hist = s_hist[warp];
+#pragma unroll
+  for (int b = 0; b < kBins / 32; ++b) hist[b * 32 + lane] = 0;
   const int g = crystal_of_atom[i];
   const int start = atom_offset[g], n = atom_offset[g + 1] - start;
-  load_offsets(ctx, lattice + 9 * (size_t)g, lane);
+  double off[3];
+  lane_offset(lattice + 9 * (size_t)g, lane, off);
   const double pix = pos[3 * (size_t)i], piy = pos[3 * (size_t)i + 1], piz = pos[3 * (size_t)i + 2];
+  __syncwarp();
   int cnt = 0;
-  const int total = 27 * n;
-  for (int c = lane; c < total; c += 32) {
+  const bool live = lane < 27;
+  const bool want_hist = cap > 0;
+  for (int j = 0; j < n; ++j) {
     double dx, dy, dz;
-    const double d2 = cand_d2(ctx, pos, start, c, pix, piy, piz, dx, dy, dz);
-    cnt += cand_pass(d2, r2, remove_self) ? 1 : 0;
+    const double d2 = lane_d2(pos + 3 * (size_t)(start + j), off, pix, piy, piz, dx, dy, dz);
+    if (live && cand_pass(d2, r2, remove_self)) {
+      ++cnt;
+      if (want_hist) atomicAdd(&hist[dist_bin(d2)], 1);
+    }
   }
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) cnt += __shfl_xor_sync(0xffffffffu, cnt, o);
+  int hint = kBins - 1;
+  if (want_hist && cnt > cap) {
+    // first bin whose cumulative count reaches the cap
+    __syncwarp();
+    int v[kBins / 32], tot = 0;
+#pragma unroll
+    for (int b = 0; b < kBins / 32; ++b) { v[b] = hist[lane * (kBins / 32) + b]; tot += v[b]; }
+    int incl = tot;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      const int t = __shfl_up_sync(0xffffffffu, incl, o);
+      if (lane >= o) incl += t;
+    }
+    int run = incl - tot, mine = kBins - 1;
+#pragma unroll
+    for (int b = kBins / 32 - 1; b >= 0; --b) {
+      // scanned from the top so that the lowest qualifying bin of this lane wins
+      int upto = run;
+      for (int q = 0; q <= b; ++q) upto += v[q];
+      if (upto >= cap) mine = lane * (kBins / 32) + b;
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) mine = min(mine, __shfl_xor_sync(0xffffffffu, mine, o));
+    hint = mine;
+  }
   if (lane == 0) {
-    raw_count[i] = cnt;
+    raw_count[i] = cnt | (hint << 24);
     deg[i] = (cap > 0 && cnt > cap) ? cap : cnt;
     // helpers:456-465: _max_neighbors[_max_neighbors > threshold] = threshold, summed per crystal
     // (for cap <= 0 this is the reference's own quirk: zeros / negative numbers)
@@ -199,21 +236,22 @@ graph_fill_kernel(const double* __restrict__ pos, const double* __restrict__ lat
                   int32_t* __restrict__ dst, int8_t* __restrict__ cell, double* __restrict__ dist,
                   double* __restrict__ dir, long long* __restrict__ ei64, double* __restrict__ cell_offsets,
                   int32_t* __restrict__ overflow_flag) {
-  __shared__ WarpCtx ctxs[kWarpsPerBlock];
   __shared__ double s_d2[kWarpsPerBlock][kSelBuf];
   __shared__ int s_c[kWarpsPerBlock][kSelBuf];
   __shared__ unsigned s_mask[kWarpsPerBlock][kSelBuf / 32];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int i = blockIdx.x * kWarpsPerBlock + warp;
   if (i >= N) return;
-  WarpCtx& ctx = ctxs[warp];
   const int g = crystal_of_atom[i];
   const int start = atom_offset[g], n = atom_offset[g + 1] - start;
-  load_offsets(ctx, lattice + 9 * (size_t)g, lane);
+  double off[3];
+  lane_offset(lattice + 9 * (size_t)g, lane, off);
   const double pix = pos[3 * (size_t)i], piy = pos[3 * (size_t)i + 1], piz = pos[3 * (size_t)i + 2];
   const long long base = row_ptr[i];
-  const int total = 27 * n;
-  const bool select = cap > 0 && raw_count[i] > cap;
+  const bool live = lane < 27;
+  const int rc = raw_count[i];
+  const bool select = cap > 0 && (rc & kCountMask) > cap;
+  const int bin_max = rc >> 24;          // graph_count: the cap nearest all lie in distance bins <= bin_max
 
   auto emit = [&](long long e, int c, double d2, double dx, double dy, double dz) {
     if (e >= edge_capacity) {
@@ -243,16 +281,12 @@ graph_fill_kernel(const double* __restrict__ pos, const double* __restrict__ lat
 
   if (!select) {
     int written = 0;
-    for (int c0 = 0; c0 < total; c0 += 32) {
-      const int c = c0 + lane;
-      double dx = 0, dy = 0, dz = 0, d2 = 0;
-      bool ok = false;
-      if (c < total) {
-        d2 = cand_d2(ctx, pos, start, c, pix, piy, piz, dx, dy, dz);
-        ok = cand_pass(d2, r2, remove_self);
-      }
+    for (int j = 0; j < n; ++j) {
+      double dx, dy, dz;
+      const double d2 = lane_d2(pos + 3 * (size_t)(start + j), off, pix, piy, piz, dx, dy, dz);
+      const bool ok = live && cand_pass(d2, r2, remove_self);
       const unsigned bal = __ballot_sync(0xffffffffu, ok);
-      if (ok) emit(base + written + __popc(bal & ((1u << lane) - 1u)), c, d2, dx, dy, dz);
+      if (ok) emit(base + written + __popc(bal & ((1u << lane) - 1u)), 27 * j + lane, d2, dx, dy, dz);
       written += __popc(bal);
     }
     return;
@@ -269,7 +303,7 @@ graph_fill_kernel(const double* __restrict__ pos, const double* __restrict__ lat
   int thr_c = 0x7fffffff;
   // compact as soon as cap + 64 candidates are buffered: the selection pass is O(m^2 / 32) per lane
   const int sel_limit = min(kSelBuf, ((cap + 31) / 32) * 32 + 64);
-  for (int c0 = 0; c0 < total; c0 += 32) {
+  for (int j = 0; j < n; ++j) {
     if (m + 32 > sel_limit) {
       m = select_topk(sd2, sc, s_mask[warp], m, cap, lane);
       // threshold = the largest kept key
@@ -286,13 +320,11 @@ graph_fill_kernel(const double* __restrict__ pos, const double* __restrict__ lat
       thr_d2 = kd;
       thr_c = kc;
     }
-    const int c = c0 + lane;
-    double dx, dy, dz, d2 = 0;
-    bool ok = false;
-    if (c < total) {
-      d2 = cand_d2(ctx, pos, start, c, pix, piy, piz, dx, dy, dz);
-      ok = cand_pass(d2, r2, remove_self) && (d2 < thr_d2 || (d2 == thr_d2 && c < thr_c));
-    }
+    const int c = 27 * j + lane;
+    double dx, dy, dz;
+    const double d2 = lane_d2(pos + 3 * (size_t)(start + j), off, pix, piy, piz, dx, dy, dz);
+    const bool ok = live && cand_pass(d2, r2, remove_self) && dist_bin(d2) <= bin_max &&
+                    (d2 < thr_d2 || (d2 == thr_d2 && c < thr_c));
     const unsigned bal = __ballot_sync(0xffffffffu, ok);
     if (ok) {
       const int p = m + __popc(bal & ((1u << lane) - 1u));
@@ -304,9 +336,12 @@ graph_fill_kernel(const double* __restrict__ pos, const double* __restrict__ lat
   }
   if (m > cap) m = select_topk(sd2, sc, s_mask[warp], m, cap, lane);
   for (int a = lane; a < m; a += 32) {
-    double dx, dy, dz;
     const int c = sc[a];
-    const double d2 = cand_d2(ctx, pos, start, c, pix, piy, piz, dx, dy, dz);
+    const int j = c / 27, k = c - 27 * j;
+    // the emitting lane is not the image's lane: rebuild the image offset
+    double offk[3], dx, dy, dz;
+    lane_offset(lattice + 9 * (size_t)g, k, offk);
+    const double d2 = lane_d2(pos + 3 * (size_t)(start + j), offk, pix, piy, piz, dx, dy, dz);
     emit(base + a, c, d2, dx, dy, dz);
   }
 }

@@ -54,8 +54,10 @@ int64_t arreau_launch_count(void);
 /* Pass 1.  pos[N,3] f64 cartesian, lattice[G,3,3] f64 rows a,b,c, atom_offset[G+1] i32 (prefix
  * sum of num_atoms), crystal_of_atom[N] i32.  radius_sq = radius*radius evaluated by the caller
  * in double (helpers:432).  cap = max_num_neighbors_threshold (<= 0 disables, helpers:469-472).
- * Outputs: raw_count[N] i32 (candidates with 1e-4 < d2 <= r2), deg[N] i32 (= min(raw, cap) when
- * cap > 0), num_neighbors_image[G] i64 (helpers:456-465, incl. its cap<=0 quirk). */
+ * Outputs: raw_count[N] i32 (bits 0..23: candidates with 1e-4 < d2 <= r2; bits 24..30: a scratch
+ * hint for pass 2 -- the log-spaced distance bin that is known to contain the cap nearest; mask
+ * with 0xFFFFFF to read the count), deg[N] i32 (= min(raw, cap) when cap > 0),
+ * num_neighbors_image[G] i64 (helpers:456-465, incl. its cap<=0 quirk). */
 int arreau_graph_count(const double* pos, const double* lattice, const int32_t* atom_offset,
                        const int32_t* crystal_of_atom, int32_t num_atoms_total, int32_t num_crystals,
                        double radius_sq, int32_t cap, int32_t remove_self_edges, int32_t* raw_count,

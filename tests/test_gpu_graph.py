@@ -84,3 +84,31 @@ def test_full_size_properties_c2(device):
     sel2 = ei_u[0] < 400
     bwd = key(ei_u[1][sel2], ei_u[0][sel2], -off_u[sel2])
     assert fwd == bwd
+
+
+@pytest.mark.parametrize("scale", [1.0, 0.25])
+def test_full_size_cap_is_topk_of_uncapped(device, scale):
+    """C2 shape: the capped edge list must be, per receiver, the 8 smallest (d2, j, cell) keys of the uncapped list, in
+    (j, cell) order (helpers:469-540).  This pins the distance-bin pre-filter of the fill pass at a size the oracle
+    cannot reach; scale 0.25 shrinks the cells to the sampler's dense early-trajectory regime (hundreds of in-range
+    images per atom)."""
+    G, n = 256, 40
+    cr = make_crystals(G, n, None, seed=5)
+    from arreau_b200.diffusion.diffusion_helpers import frac_to_cart_coords
+    from arreau_b200.diffusion.lattice_helpers import lattice_from_params
+    lat = lattice_from_params(torch.as_tensor(cr.lengths * scale, device=device), torch.as_tensor(cr.angles, device=device))
+    na = torch.as_tensor(cr.num_atoms, device=device)
+    cart = frac_to_cart_coords(torch.as_tensor(cr.frac, device=device), lat, na)
+    ei_c, off_c, _, _, dir_c = _run(device, cart, lat, na, 5.0, 8)
+    ei_u, off_u, _, _, dir_u = _run(device, cart, lat, na, 5.0, 0)
+    d2 = (dir_u[:, 0] * dir_u[:, 0] + dir_u[:, 1] * dir_u[:, 1]) + dir_u[:, 2] * dir_u[:, 2]     # the kernel's own bits
+    cell = ((-off_u[:, 0] + 1) * 9 + (-off_u[:, 1] + 1) * 3 + (-off_u[:, 2] + 1)).astype(np.int64)
+    recv, send = ei_u[1], ei_u[0]
+    order = np.lexsort((cell, send, d2, recv))                 # by receiver, then (d2, j, cell)
+    start = np.searchsorted(recv[order], np.arange(G * n))
+    rank = np.arange(order.size) - start[recv[order]]
+    keep = np.zeros(order.size, dtype=bool)
+    keep[order[rank < 8]] = True                               # back in the uncapped list's (i, j, cell) order
+    assert np.array_equal(ei_c, ei_u[:, keep])
+    assert np.array_equal(off_c, off_u[keep])
+    assert np.array_equal(dir_c, dir_u[keep])
