@@ -274,7 +274,9 @@ __device__ __forceinline__ void umma_commit(uint64_t* bar) {
 // (HMUL2 / HFMA2 / MUFU.TANH.F16x2): five packed FMA-pipe instructions and one MUFU per PAIR, and the result
 // is already the packed fp16 operand of the next GEMM.  fp16 arithmetic (11 significant bits) adds ~5e-4
 // relative, the same size as the rounding of the stored operand.  |x| > 255 overflows x^2 to +inf, which
-// saturates tanh to +-1 (the correct limit).  The 3.7e9 GELUs of a step are otherwise the bound of both
+// saturates tanh to +-1 (the correct limit).  The function returns x (1 + tanh(.)) = 2 gelu(x): every consumer is a GEMM
+// whose weight image was packed with the factor 1/2 (arreau_b200/weights.py: W2 of the basis MLP, the five kernel
+// projections, linear_2 of the ConvNext MLP), a power of two and therefore exact, which saves one packed multiply per pair.  The 3.7e9 GELUs of a step are otherwise the bound of both
 // tensor-core kernels.  The fp32 path keeps the exact erff form.
 __device__ __forceinline__ uint32_t gelu2_f16(float x0, float x1) {
   const __half2 x = __floats2half2_rn(x0, x1);
@@ -283,8 +285,7 @@ __device__ __forceinline__ uint32_t gelu2_f16(float x0, float x1) {
   uint32_t tb;
   asm("tanh.approx.f16x2 %0, %1;" : "=r"(tb) : "r"(*reinterpret_cast<const uint32_t*>(&u)));
   const __half2 t = *reinterpret_cast<const __half2*>(&tb);
-  const __half2 hx = __hmul2(x, __float2half2_rn(0.5f));
-  const __half2 y = __hfma2(hx, t, hx);
+  const __half2 y = __hfma2(x, t, x);       // = 2 gelu(x): the factor 1/2 lives in the consuming weight image (exact)
   return *reinterpret_cast<const uint32_t*>(&y);
 }
 __device__ __forceinline__ uint32_t gelu2_scaled_f16(float x0, float x1, __half2 scale) {

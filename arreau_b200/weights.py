@@ -145,11 +145,13 @@ class PonitaWeights:
             # tcgen05 path: every weight tile as a ready-to-copy UMMA shared-memory image
             w1pad = np.zeros((HIDDEN, 128))
             w1pad[:, :MONO_PAD] = w1m_t.T                                  # [N = hidden, K = 96 -> 128]
-            w2 = sd["basis_fn.3.weight"]                                   # [D, C]
+            # the kernels' packed-fp16 GELU returns 2 gelu(x) (csrc/tc_common.cuh gelu2_f16): every matrix that consumes a
+            # GELU output carries the factor 1/2 (a power of two: exact in fp16)
+            w2 = 0.5 * np.asarray(sd["basis_fn.3.weight"])                 # [D, C]
             chunks = [umma_tile_image(w2[nh * 128:(nh + 1) * 128, ks * 64:(ks + 1) * 64])
                       for nh in range(2) for ks in range(2)]
-            chunks += [umma_tile_image(wk[l][:, ks * 64:(ks + 1) * 64]) for l in range(L) for ks in range(4)]
-            m1, m2 = lay("linear_1.weight"), lay("linear_2.weight")        # [L,4C,C], [L,C,4C]
+            chunks += [umma_tile_image(0.5 * wk[l][:, ks * 64:(ks + 1) * 64]) for l in range(L) for ks in range(4)]
+            m1, m2 = lay("linear_1.weight"), 0.5 * lay("linear_2.weight")  # [L,4C,C], [L,C,4C]
             mlp = []
             for l in range(L):
                 g1 = [umma_tile_image(m1[l][j * 128:(j + 1) * 128, :]) for j in range(4)]
