@@ -83,8 +83,8 @@ SIGNATURES = {
     "arreau_convnext_mlp_f32": [vp, vp, vp, vp, vp, vp, i64, vp, vp],
     "arreau_convnext_mlp_f16": [vp, vp, vp, vp, vp, i64, vp, vp],
     "arreau_readout_accumulate": [vp, vp, vp, vp, i32, i32, i32, vp, vp],
-    "arreau_node_embed_pooled": [vp, vp, i32, vp, vp, vp, i32, i32, i32, vp, vp, vp],
-    "arreau_convnext_mlp_f16_pooled": [vp, vp, vp, vp, vp, i64, vp, vp, vp, vp],
+    "arreau_node_embed_pooled": [vp, vp, i32, vp, vp, vp, i32, i32, i32, vp, vp, vp, vp],
+    "arreau_convnext_mlp_f16_pooled": [vp, vp, vp, vp, vp, i64, vp, vp, vp, vp, i32, vp],
     "arreau_readout_pooled": [vp, vp, vp, i32, i32, i32, vp, vp],
     "arreau_readout_finalize": [vp, vp, i32, i32, i32, i32, vp, vp, vp, vp],
     "arreau_ponita_forward": [C.POINTER(Weights), C.POINTER(Workspace), i32, vp, vp, vp, vp, vp, vp, vp, vp, vp,

@@ -10,6 +10,7 @@
 //   message_fiber_norm_kernel  K4b+K5 + LayerNorm   conv.py:115,126-133, convnext.py:25
 //   convnext_mlp_simt_kernel   K6   convnext.py:26-32
 //   readout_*_kernel           K7   ponita.py:105-117,152, to_from_sphere.py:10-14
+#include <cstdlib>
 #include <cuda_fp16.h>
 
 #include "common.cuh"
@@ -102,7 +103,7 @@ constexpr int kMaxVec = 8;
 __global__ void __launch_bounds__(kEmbedNodes * 32)
 node_embed_kernel(const float* __restrict__ x, const float* __restrict__ vec, const float* __restrict__ w_t,
                   const float* __restrict__ ori, const int64_t* __restrict__ types, int Z, int N, int F, int V,
-                  float* __restrict__ h, float* __restrict__ pool) {
+                  float* __restrict__ h, float* __restrict__ pool, const float* __restrict__ pool_wz, int pool_z) {
   extern __shared__ float sm[];
   float* xs = sm;                                   // [kEmbedNodes][F]
   float* dots = sm + kEmbedNodes * F;               // [kEmbedNodes][V][kO]
@@ -127,7 +128,7 @@ node_embed_kernel(const float* __restrict__ x, const float* __restrict__ vec, co
     s = __ldg(reinterpret_cast<const float4*>(w_t + (size_t)types[b0 + a] * kC + lane * 4));
     f0 = Z;
   }
-#pragma unroll 4
+#pragma unroll 16
   for (int f = f0; f < F; ++f) {
     const float4 w = __ldg(reinterpret_cast<const float4*>(w_t + (size_t)f * kC + lane * 4));
     const float xv = xr[f];
@@ -161,21 +162,37 @@ node_embed_kernel(const float* __restrict__ x, const float* __restrict__ vec, co
   }
   }
   if (pool) {
-    // pool[group of 16 atoms][4 parts][C][16 atoms] (the layout readout_pooled_kernel streams): the CTA's 8 atoms are
-    // one half of a group; transpose [atom][part][c] -> [part][c][atom] through shared memory (re-using xs / dots)
+    // pool entry (include/arreau_b200.h): [group of 16 atoms][C][16 atoms] of mean_o h, then per atom the 3 x 2 partial
+    // contractions of the vector-pooled parts with the score row of the read-out.  The CTA's 8 atoms are one half of a
+    // group; transpose [atom][c] -> [c][atom] through shared memory (re-using xs / dots)
     constexpr float inv = 1.0f / kO;
-    __syncthreads();
-    float* tp = sm;                                            // [8 atoms][4][kC]
+    const int groups = (N + 15) / 16;
+    if (a < nb) {
+      float sd[3];
 #pragma unroll
-    for (int q = 0; q < 4; ++q)
-      *reinterpret_cast<float4*>(tp + (a * 4 + q) * kC + lane * 4) =
-          make_float4(pq[q].x * inv, pq[q].y * inv, pq[q].z * inv, pq[q].w * inv);
+      for (int d = 0; d < 3; ++d) {
+        const float* wz = pool_wz + (size_t)(lane * 4) * (pool_z + 6) + pool_z;     // V_0[c][Z], c = 4 lane + i
+        float v = pq[1 + d].x * wz[0] + pq[1 + d].y * wz[pool_z + 6] + pq[1 + d].z * wz[2 * (pool_z + 6)] +
+                  pq[1 + d].w * wz[3 * (pool_z + 6)];
+#pragma unroll
+        for (int sft = 16; sft > 0; sft >>= 1) v += __shfl_xor_sync(0xffffffffu, v, sft);
+        sd[d] = v * inv;
+      }
+      if (lane == 0) {
+        float4* sp = reinterpret_cast<float4*>(pool + (size_t)groups * kC * 16 + (size_t)(b0 + a) * 8);
+        sp[0] = make_float4(sd[0], 0.f, sd[1], 0.f);                                // [2 d + half]: this kernel fills half 0
+        sp[1] = make_float4(sd[2], 0.f, 0.f, 0.f);
+      }
+    }
     __syncthreads();
-    float* pg = pool + (size_t)(blockIdx.x >> 1) * 4 * kC * 16 + (size_t)(blockIdx.x & 1) * 8;
-    for (int pc = tid; pc < 4 * kC; pc += kEmbedNodes * 32) {  // pc = part * kC + c
+    float* tp = sm;                                            // [8 atoms][kC]
+    *reinterpret_cast<float4*>(tp + a * kC + lane * 4) = make_float4(pq[0].x * inv, pq[0].y * inv, pq[0].z * inv, pq[0].w * inv);
+    __syncthreads();
+    float* pg = pool + (size_t)(blockIdx.x >> 1) * kC * 16 + (size_t)(blockIdx.x & 1) * 8;
+    for (int pc = tid; pc < kC; pc += kEmbedNodes * 32) {
       float v[8];
 #pragma unroll
-      for (int aa = 0; aa < 8; ++aa) v[aa] = tp[aa * 4 * kC + pc];
+      for (int aa = 0; aa < 8; ++aa) v[aa] = tp[aa * kC + pc];
       float4* po = reinterpret_cast<float4*>(pg + (size_t)pc * 16);
       po[0] = make_float4(v[0], v[1], v[2], v[3]);
       po[1] = make_float4(v[4], v[5], v[6], v[7]);
@@ -1134,120 +1151,141 @@ readout_accumulate_kernel(const float* __restrict__ h, const float* __restrict__
 constexpr int kPoolAtoms = 16;
 constexpr int kPoolCols = 96;
 constexpr int kPoolWarps = 8;
-constexpr int kPoolChunkC = 32;                                                 // channels per chunk
-constexpr int kPoolChunkFloats = 4 * kPoolChunkC * kPoolAtoms;                  // 2048 floats = 8 KB
-constexpr int kPoolSmem = (kC * kPoolCols + kPoolWarps * 2 * kPoolChunkFloats) * (int)sizeof(float);   // 176 KB
+// One pool entry = [groups][C][16 atoms] of the orientation mean, then [groups * 16 atoms][8] partial contractions of
+// the vector-pooled parts with the score row: element 2 d + half (d = 0..2; the producer's two channel halves).
+// Tensor cores: the [16 atoms x C] block of a group is the A operand of mma.sync.m16n8k8 TF32 products against
+// V_k[C][96] (12 n-tiles), with the 3xTF32 split (a_lo b_hi + a_hi b_lo + a_hi b_hi, fp32 accumulation) so that the
+// result keeps fp32 accuracy (the read-outs feed the D3PM argmax and the coordinate update directly).  V_k sits in
+// shared memory in fp32 (row stride 104 floats: conflict-free B fragments) and is split on the fly.  One persistent
+// CTA per SM, one warp per 16-atom group; the group's 8 KB block arrives through a per-warp cp.async double buffer
+// (the next group's block is in flight while this one is multiplied); acc is updated in place, entry by entry, in a
+// fixed order (deterministic).  Measured: 0.26 ms at C2, bound by the legacy mma.sync TF32 rate (8.8 M instructions,
+// ~33 cycles each per SM sub-partition, about 70 TFLOP/s) -- a tcgen05 kind::tf32 version is the next step.
+constexpr int kRpV = 104;
+constexpr int kRpBlockFloats = kC * kPoolAtoms;                                 // 2048 floats = 8 KB
+constexpr int kRpSmem = (kC * kRpV + kPoolWarps * 2 * kRpBlockFloats) * (int)sizeof(float);
+
+__device__ __forceinline__ uint32_t tf32_rna(float x) {
+  uint32_t r;
+  asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(x));
+  return r;
+}
+__device__ __forceinline__ void mma1688_tf32(float (&d)[4], const uint32_t (&a)[4], uint32_t b0, uint32_t b1) {
+  asm volatile("mma.sync.aligned.m16n8k8.row.col.f32.tf32.tf32.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+               : "+f"(d[0]), "+f"(d[1]), "+f"(d[2]), "+f"(d[3])
+               : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
+}
 
 __global__ void __launch_bounds__(kPoolWarps * 32, 1)
-readout_pooled_kernel(const float* __restrict__ pool, const float* __restrict__ v, const float* __restrict__ bias, int N,
-                      int Z, int entries, float* __restrict__ acc) {
+readout_pooled_kernel(const float* __restrict__ pool, size_t entry_stride, const float* __restrict__ v,
+                      const float* __restrict__ bias, int N, int Z, int entries, float* __restrict__ acc) {
   extern __shared__ __align__(16) float rp_sm[];
-  float* const vs = rp_sm;                                                       // [kC][kPoolCols]
-  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  float* const pb = rp_sm + kC * kPoolCols + warp * 2 * kPoolChunkFloats;        // this warp's [2][4 parts][32 c][16 atoms]
+  float* const vs = rp_sm;                                                       // [kC][kRpV]
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, g = lane >> 2, t = lane & 3;
+  float* const pb = rp_sm + kC * kRpV + warp * 2 * kRpBlockFloats;               // this warp's [2][C][16 atoms]
   const int groups = (N + kPoolAtoms - 1) / kPoolAtoms;
-  const size_t entry_floats = (size_t)groups * 4 * kC * kPoolAtoms;
-  // columns Z..Z+2 (the score vector) read parts 1..3 instead of part 0: they are computed on the side with
-  // lane = (atom sa, half of the chunk's channels sh); the lanes that own them as a "third column" skip that column
-  const int col2 = lane + 64;
-  const bool skip2 = col2 >= Z && col2 < Z + 3;
-  const int sa = lane & 15, sh = lane >> 4;
-  auto load_chunk = [&](const float* gsrc, int ch, int buf) {                    // 4 parts x 2 KB, 16 bytes per lane and copy
-    float* dst = pb + buf * kPoolChunkFloats;
+  auto load_block = [&](const float* gsrc, int buf) {                            // 8 KB, 16 bytes per lane and copy
+    float* dst = pb + buf * kRpBlockFloats;
 #pragma unroll
-    for (int part = 0; part < 4; ++part)
-#pragma unroll
-      for (int i = 0; i < 4; ++i)
-        cp_async16(dst + part * kPoolChunkC * kPoolAtoms + (i * 32 + lane) * 4,
-                   gsrc + ((size_t)part * kC + ch * kPoolChunkC) * kPoolAtoms + (i * 32 + lane) * 4);
+    for (int i = 0; i < kRpBlockFloats / 128; ++i) cp_async16(dst + (i * 32 + lane) * 4, gsrc + (i * 32 + lane) * 4);
     cp_async_commit();
   };
   for (int k = 0; k < entries; ++k) {
     __syncthreads();                                                             // the previous matrix is no longer read
-    for (int i = tid; i < kC * kPoolCols / 4; i += kPoolWarps * 32)
-      reinterpret_cast<float4*>(vs)[i] = __ldg(reinterpret_cast<const float4*>(v + (size_t)k * kC * kPoolCols) + i);
+    for (int i = tid; i < kC * kPoolCols; i += kPoolWarps * 32) {
+      const int c = i / kPoolCols, n = i - c * kPoolCols;
+      vs[c * kRpV + n] = __ldg(v + (size_t)k * kC * kPoolCols + i);
+    }
     __syncthreads();
-    for (int g = blockIdx.x * kPoolWarps + warp; g < groups; g += gridDim.x * kPoolWarps) {
-      const float* gsrc = pool + (size_t)k * entry_floats + (size_t)g * 4 * kC * kPoolAtoms;
-      const int b0 = g * kPoolAtoms;
-      load_chunk(gsrc, 0, 0);
-      float2 r[3][kPoolAtoms / 2];
-      float sc[3];
-      if (k == 0) {
-#pragma unroll
-        for (int j = 0; j < 3; ++j) {
-          const float bb = bias[lane + 32 * j];
-#pragma unroll
-          for (int a = 0; a < kPoolAtoms / 2; ++a) r[j][a] = make_float2(bb, bb);
-        }
-#pragma unroll
-        for (int d = 0; d < 3; ++d) sc[d] = sh == 0 ? bias[Z + d] : 0.f;
+    const float* entry = pool + (size_t)k * entry_stride;
+    const float* partials = entry + (size_t)groups * kRpBlockFloats;
+    const int g0 = blockIdx.x * kPoolWarps + warp, gstep = gridDim.x * kPoolWarps;
+    if (g0 < groups) load_block(entry + (size_t)g0 * kRpBlockFloats, 0);
+    int it = 0;
+    for (int grp = g0; grp < groups; grp += gstep, ++it) {
+      const int b0 = grp * kPoolAtoms;
+      if (grp + gstep < groups) {
+        load_block(entry + (size_t)(grp + gstep) * kRpBlockFloats, (it + 1) & 1);
+        cp_async_wait<1>();
       } else {
-#pragma unroll
-        for (int j = 0; j < 3; ++j)
-#pragma unroll
-          for (int a = 0; a < kPoolAtoms / 2; ++a) {
-            const int a0 = b0 + 2 * a;
-            const bool skip = j == 2 && skip2;
-            r[j][a].x = (a0 < N && !skip) ? acc[(size_t)a0 * kPoolCols + lane + 32 * j] : 0.f;
-            r[j][a].y = (a0 + 1 < N && !skip) ? acc[(size_t)(a0 + 1) * kPoolCols + lane + 32 * j] : 0.f;
-          }
-#pragma unroll
-        for (int d = 0; d < 3; ++d) sc[d] = (sh == 0 && b0 + sa < N) ? acc[(size_t)(b0 + sa) * kPoolCols + Z + d] : 0.f;
+        cp_async_wait<0>();
       }
-#pragma unroll 1
-      for (int ch = 0; ch < kC / kPoolChunkC; ++ch) {
-        if (ch + 1 < kC / kPoolChunkC) {
-          load_chunk(gsrc, ch + 1, (ch + 1) & 1);
-          cp_async_wait<1>();
+      __syncwarp();
+      const bool r0 = b0 + g < N, r1 = b0 + g + 8 < N;
+      float d[kPoolCols / 8][4];
+#pragma unroll
+      for (int nt = 0; nt < kPoolCols / 8; ++nt) {
+        const int col = nt * 8 + 2 * t;
+        if (k == 0) {
+          d[nt][0] = d[nt][2] = bias[col];
+          d[nt][1] = d[nt][3] = bias[col + 1];
         } else {
-          cp_async_wait<0>();
+          const float2 x0 = r0 ? *reinterpret_cast<const float2*>(acc + (size_t)(b0 + g) * kPoolCols + col) : make_float2(0.f, 0.f);
+          const float2 x1 = r1 ? *reinterpret_cast<const float2*>(acc + (size_t)(b0 + g + 8) * kPoolCols + col) : make_float2(0.f, 0.f);
+          d[nt][0] = x0.x; d[nt][1] = x0.y; d[nt][2] = x1.x; d[nt][3] = x1.y;
         }
-        __syncwarp();
-        const float* p0 = pb + (ch & 1) * kPoolChunkFloats;
-        const float* w = vs + (size_t)ch * kPoolChunkC * kPoolCols + lane;
-        {
-          // score vector: sc[d] += V[c][Z] * part(1+d)[c][atom sa] over this lane's half of the chunk's channels
-          const float* wz = vs + ((size_t)ch * kPoolChunkC + sh * (kPoolChunkC / 2)) * kPoolCols + Z;
-          const float* ps = p0 + (kPoolChunkC + sh * (kPoolChunkC / 2)) * kPoolAtoms + sa;
-#pragma unroll 4
-          for (int c = 0; c < kPoolChunkC / 2; ++c) {
-            const float wv = wz[c * kPoolCols];
-#pragma unroll
-            for (int d = 0; d < 3; ++d) sc[d] = fmaf(wv, ps[(d * kPoolChunkC + c) * kPoolAtoms], sc[d]);
-          }
-        }
-#pragma unroll 2
-        for (int c = 0; c < kPoolChunkC; ++c) {
-          const float w0 = w[c * kPoolCols], w1 = w[c * kPoolCols + 32], w2 = w[c * kPoolCols + 64];
-          const float2 w0d = make_float2(w0, w0), w1d = make_float2(w1, w1), w2d = make_float2(w2, w2);
-#pragma unroll
-          for (int q4 = 0; q4 < kPoolAtoms / 4; ++q4) {
-            const float4 pa = *reinterpret_cast<const float4*>(p0 + c * kPoolAtoms + 4 * q4);
-            const float2 pa0 = make_float2(pa.x, pa.y), pa1 = make_float2(pa.z, pa.w);
-            r[0][2 * q4] = __ffma2_rn(w0d, pa0, r[0][2 * q4]);
-            r[0][2 * q4 + 1] = __ffma2_rn(w0d, pa1, r[0][2 * q4 + 1]);
-            r[1][2 * q4] = __ffma2_rn(w1d, pa0, r[1][2 * q4]);
-            r[1][2 * q4 + 1] = __ffma2_rn(w1d, pa1, r[1][2 * q4 + 1]);
-            r[2][2 * q4] = __ffma2_rn(w2d, pa0, r[2][2 * q4]);
-            r[2][2 * q4 + 1] = __ffma2_rn(w2d, pa1, r[2][2 * q4 + 1]);
-          }
-        }
-        __syncwarp();                                                            // the buffer is refilled two chunks later
       }
+      // score vector (columns Z..Z+2): lanes 0..15 own one atom each and add the producers' partial contractions
+      float sc[3] = {0.f, 0.f, 0.f};
+      const bool sv = lane < kPoolAtoms && b0 + lane < N;
+      if (sv) {
+        const float4 s0 = __ldg(reinterpret_cast<const float4*>(partials + (size_t)(b0 + lane) * 8));
+        const float4 s1 = __ldg(reinterpret_cast<const float4*>(partials + (size_t)(b0 + lane) * 8) + 1);
+        const float* prev = acc + (size_t)(b0 + lane) * kPoolCols + Z;
+        sc[0] = (k == 0 ? bias[Z] : prev[0]) + (s0.x + s0.y);
+        sc[1] = (k == 0 ? bias[Z + 1] : prev[1]) + (s0.z + s0.w);
+        sc[2] = (k == 0 ? bias[Z + 2] : prev[2]) + (s1.x + s1.y);
+      }
+      const float* p0 = pb + (it & 1) * kRpBlockFloats;
+#pragma unroll 2
+      for (int ks = 0; ks < kC / 8; ++ks) {
+        uint32_t ahi[4], alo[4];
 #pragma unroll
-      for (int j = 0; j < 3; ++j)
-#pragma unroll
-        for (int a = 0; a < kPoolAtoms / 2; ++a) {
-          const int a0 = b0 + 2 * a;
-          const bool skip = j == 2 && skip2;
-          if (a0 < N && !skip) acc[(size_t)a0 * kPoolCols + lane + 32 * j] = r[j][a].x;
-          if (a0 + 1 < N && !skip) acc[(size_t)(a0 + 1) * kPoolCols + lane + 32 * j] = r[j][a].y;
+        for (int i = 0; i < 4; ++i) {
+          const float a = p0[(ks * 8 + t + 4 * (i >> 1)) * kPoolAtoms + g + 8 * (i & 1)];
+          ahi[i] = tf32_rna(a);
+          alo[i] = tf32_rna(a - __uint_as_float(ahi[i]));
         }
+        const float* vrow = vs + (ks * 8 + t) * kRpV + g;
+        // six n-tiles at a time, term by term: the three products into one accumulator are six independent
+        // instructions apart, so the warp does not wait on the tensor pipe's latency
 #pragma unroll
-      for (int d = 0; d < 3; ++d) {
-        const float tot = sc[d] + __shfl_xor_sync(0xffffffffu, sc[d], 16);
-        if (sh == 0 && b0 + sa < N) acc[(size_t)(b0 + sa) * kPoolCols + Z + d] = tot;
+        for (int nh = 0; nh < 2; ++nh) {
+          uint32_t bh[6][2], bl[6][2];
+#pragma unroll
+          for (int j = 0; j < 6; ++j) {
+            const float w0 = vrow[(nh * 6 + j) * 8], w1 = vrow[4 * kRpV + (nh * 6 + j) * 8];
+            bh[j][0] = tf32_rna(w0); bh[j][1] = tf32_rna(w1);
+            bl[j][0] = tf32_rna(w0 - __uint_as_float(bh[j][0])); bl[j][1] = tf32_rna(w1 - __uint_as_float(bh[j][1]));
+          }
+#pragma unroll
+          for (int j = 0; j < 6; ++j) mma1688_tf32(d[nh * 6 + j], alo, bh[j][0], bh[j][1]);
+#pragma unroll
+          for (int j = 0; j < 6; ++j) mma1688_tf32(d[nh * 6 + j], ahi, bl[j][0], bl[j][1]);
+#pragma unroll
+          for (int j = 0; j < 6; ++j) mma1688_tf32(d[nh * 6 + j], ahi, bh[j][0], bh[j][1]);
+        }
+      }
+      __syncwarp();                                                              // the buffer is refilled by the next iteration
+#pragma unroll
+      for (int nt = 0; nt < kPoolCols / 8; ++nt) {
+        const int col = nt * 8 + 2 * t;
+        // columns Z..Z+2 belong to the score side
+        const bool k0 = col < Z || col >= Z + 3, k1 = col + 1 < Z || col + 1 >= Z + 3;
+        if (r0) {
+          float* o = acc + (size_t)(b0 + g) * kPoolCols + col;
+          if (k0) o[0] = d[nt][0];
+          if (k1) o[1] = d[nt][1];
+        }
+        if (r1) {
+          float* o = acc + (size_t)(b0 + g + 8) * kPoolCols + col;
+          if (k0) o[0] = d[nt][2];
+          if (k1) o[1] = d[nt][3];
+        }
+      }
+      if (sv) {
+        float* o = acc + (size_t)(b0 + lane) * kPoolCols + Z;
+        o[0] = sc[0]; o[1] = sc[1]; o[2] = sc[2];
       }
     }
   }
@@ -1289,36 +1327,37 @@ int num_sms() {
 // ================================================================================================
 static int node_embed_launch(const float* x, const float* vec, const float* w_embed_t, const float* ori,
                              const int64_t* types, int32_t Z, int32_t N, int32_t F, int32_t V, float* h, float* pool,
-                             void* stream) {
+                             const float* pool_wz, void* stream) {
   if (N == 0) return ARREAU_OK;
   if (!x || !vec || !w_embed_t || !ori || !h) return ARREAU_ERR_NULL;
   if (N < 0 || F <= 0 || V < 0 || V > kMaxVec || (types && (Z <= 0 || Z > F))) return ARREAU_ERR_BAD_SHAPE;
   size_t smem = sizeof(float) * (size_t)kEmbedNodes * (F + V * kO);
-  if (pool && smem < sizeof(float) * kEmbedNodes * 4 * kC) smem = sizeof(float) * kEmbedNodes * 4 * kC;
+  if (pool && smem < sizeof(float) * kEmbedNodes * kC) smem = sizeof(float) * kEmbedNodes * kC;
   if (smem > 48 * 1024) return ARREAU_ERR_UNSUPPORTED;
   node_embed_kernel<<<(N + kEmbedNodes - 1) / kEmbedNodes, kEmbedNodes * 32, smem, (cudaStream_t)stream>>>(
-      x, vec, w_embed_t, ori, types, Z, N, F, V, h, pool);
+      x, vec, w_embed_t, ori, types, Z, N, F, V, h, pool, pool_wz, Z);
   CUDA_LAUNCH_CHECK();
   return ARREAU_OK;
 }
 
 extern "C" int arreau_node_embed(const float* x, const float* vec, const float* w_embed_t, const float* ori,
                                  int32_t N, int32_t F, int32_t V, float* h, void* stream) {
-  return node_embed_launch(x, vec, w_embed_t, ori, nullptr, 0, N, F, V, h, nullptr, stream);
+  return node_embed_launch(x, vec, w_embed_t, ori, nullptr, 0, N, F, V, h, nullptr, nullptr, stream);
 }
 
 extern "C" int arreau_node_embed_typed(const float* x, const int64_t* types, int32_t Z, const float* vec,
                                        const float* w_embed_t, const float* ori, int32_t N, int32_t F, int32_t V,
                                        float* h, void* stream) {
   if (!types) return ARREAU_ERR_NULL;
-  return node_embed_launch(x, vec, w_embed_t, ori, types, Z, N, F, V, h, nullptr, stream);
+  return node_embed_launch(x, vec, w_embed_t, ori, types, Z, N, F, V, h, nullptr, nullptr, stream);
 }
 
 extern "C" int arreau_node_embed_pooled(const float* x, const int64_t* types, int32_t Z, const float* vec,
                                         const float* w_embed_t, const float* ori, int32_t N, int32_t F, int32_t V,
-                                        float* h, float* pool, void* stream) {
-  if (N > 0 && !pool) return ARREAU_ERR_NULL;
-  return node_embed_launch(x, vec, w_embed_t, ori, types, Z, N, F, V, h, pool, stream);
+                                        float* h, float* pool, const float* readout_v0, void* stream) {
+  if (N > 0 && (!pool || !readout_v0)) return ARREAU_ERR_NULL;
+  if (Z + 6 != 96) return ARREAU_ERR_UNSUPPORTED;
+  return node_embed_launch(x, vec, w_embed_t, ori, types, Z, N, F, V, h, pool, readout_v0, stream);
 }
 
 extern "C" int arreau_fiber_kernel_precompute(const float* ori, const float* w1, const float* b1, const float* w2,
@@ -1489,15 +1528,15 @@ extern "C" int arreau_readout_pooled(const float* pool, const float* readout_v, 
   if (Z + 6 != kPoolCols) return ARREAU_ERR_UNSUPPORTED;
   static bool attr_set = false;
   if (!attr_set) {
-    cudaError_t e = cudaFuncSetAttribute(readout_pooled_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kPoolSmem);
+    cudaError_t e = cudaFuncSetAttribute(readout_pooled_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kRpSmem);
     if (e != cudaSuccess) return (int)e;
     attr_set = true;
   }
   const int groups = (N + kPoolAtoms - 1) / kPoolAtoms;
   const int ctas = (groups + kPoolWarps - 1) / kPoolWarps;
   const int grid = ctas < num_sms() ? ctas : num_sms();
-  readout_pooled_kernel<<<grid, kPoolWarps * 32, kPoolSmem, (cudaStream_t)stream>>>(pool, readout_v, readout_bias, N, Z,
-                                                                                    entries, acc);
+  readout_pooled_kernel<<<grid, kPoolWarps * 32, kRpSmem, (cudaStream_t)stream>>>(
+      pool, (size_t)groups * 4 * kC * kPoolAtoms, readout_v, readout_bias, N, Z, entries, acc);
   CUDA_LAUNCH_CHECK();
   return ARREAU_OK;
 }

@@ -123,7 +123,8 @@ struct Bars {
 __global__ void __launch_bounds__(kThreads, 1)
 convnext_mlp_tc_kernel(const uint8_t* __restrict__ y_img, const uint8_t* __restrict__ w_img, const float* __restrict__ b1,
                        const float* __restrict__ b2, const float* __restrict__ layer_scale, long long rows,
-                       float* __restrict__ h, const float* __restrict__ ori, float* __restrict__ pool_out) {
+                       float* __restrict__ h, const float* __restrict__ ori, float* __restrict__ pool_out,
+                       const float* __restrict__ pool_wz, int pool_cols) {
   using namespace mlp;
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
@@ -344,21 +345,33 @@ convnext_mlp_tc_kernel(const uint8_t* __restrict__ y_img, const uint8_t* __restr
     // ---------------- pooled read-out (see readout_pooled_kernel): the two otherwise idle warps pool the staged residual
     // update over the 16 orientation rows of each of the tile's 8 atoms.  Two phases, one per staging half (rows 0..63 =
     // atoms 0..3, then atoms 4..7), each released to the epilogue warps separately (barriers 3 and 4) so the next
-    // tile's H writes are not held up; per phase warp 2 takes the first atom pair, warp 3 the second, lane = 4 channels.
-    // pool_out[group of 16 atoms][4 parts][C][16 atoms]; a tile is one half (8 atoms) of a group ----------------
+    // tile's H writes are not held up; per phase warp 2 takes the first atom pair, warp 3 the second, lane = 2 channels.
+    // Pool entry (include/arreau_b200.h): the orientation mean goes to [group of 16 atoms][C][16 atoms] (a tile is one
+    // half of a group); the three vector-pooled parts only meet the score row of the read-out, so this warp contracts
+    // them with its 64 channels of that row and leaves 3 partial sums per atom ([atom][2 d + half]) ----------------
     const float* stage = reinterpret_cast<const float*>(H0);
     constexpr float inv = 1.0f / kO;
-    const int c2 = (warp - 2) * 64 + lane * 2;               // this thread's channel pair
+    const int half = warp - 2;
+    const int c2 = half * 64 + lane * 2;                     // this thread's channel pair
+    const float wz0 = pool_wz[(size_t)c2 * pool_cols] * inv, wz1 = pool_wz[(size_t)(c2 + 1) * pool_cols] * inv;
+    const long long groups = (rows / kO + 15) / 16;
+    float* const partials = pool_out + (size_t)groups * kC * 16;
     for (long long tile = blockIdx.x; tile < tiles; tile += gridDim.x) {
       asm volatile("bar.sync 2, %0;" ::"n"(kEpiThreads + 64) : "memory");
       const bool more = tile + gridDim.x < tiles;            // the last tile has no successor waiting on barriers 3 / 4
-      float2 acc[2][4][4];                                   // [phase][part][atom of the phase]: (channel c2, c2 + 1)
+      float2 mean[2][4];                                     // [phase][atom of the phase]: (channel c2, c2 + 1)
+      float sv[32];                                          // [(phase * 4 + atom) * 3 + d], padded to 32 for the reduction
+#pragma unroll
+      for (int i = 24; i < 32; ++i) sv[i] = 0.f;
 #pragma unroll
       for (int ph = 0; ph < 2; ++ph) {
+        float2 acc[3][4];
 #pragma unroll
-        for (int part = 0; part < 4; ++part)
+        for (int a = 0; a < 4; ++a) {
+          mean[ph][a] = make_float2(0.f, 0.f);
 #pragma unroll
-          for (int a = 0; a < 4; ++a) acc[ph][part][a] = make_float2(0.f, 0.f);
+          for (int d = 0; d < 3; ++d) acc[d][a] = make_float2(0.f, 0.f);
+        }
 #pragma unroll 2
         for (int o = 0; o < kO; ++o) {
           const float ox = s_ori[3 * o], oy = s_ori[3 * o + 1], oz = s_ori[3 * o + 2];
@@ -366,10 +379,10 @@ convnext_mlp_tc_kernel(const uint8_t* __restrict__ y_img, const uint8_t* __restr
 #pragma unroll
           for (int a = 0; a < 4; ++a) {
             const float2 v = *reinterpret_cast<const float2*>(stage + ((ph * 4 + a) * kO + o) * kC + c2);
-            acc[ph][0][a].x += v.x; acc[ph][0][a].y += v.y;
-            acc[ph][1][a] = __ffma2_rn(dx, v, acc[ph][1][a]);
-            acc[ph][2][a] = __ffma2_rn(dy, v, acc[ph][2][a]);
-            acc[ph][3][a] = __ffma2_rn(dz, v, acc[ph][3][a]);
+            mean[ph][a].x += v.x; mean[ph][a].y += v.y;
+            acc[0][a] = __ffma2_rn(dx, v, acc[0][a]);
+            acc[1][a] = __ffma2_rn(dy, v, acc[1][a]);
+            acc[2][a] = __ffma2_rn(dz, v, acc[2][a]);
           }
         }
         // done reading this staging half
@@ -377,18 +390,32 @@ convnext_mlp_tc_kernel(const uint8_t* __restrict__ y_img, const uint8_t* __restr
           if (ph == 0) asm volatile("bar.arrive 3, %0;" ::"n"(kEpiThreads + 64) : "memory");
           else asm volatile("bar.arrive 4, %0;" ::"n"(kEpiThreads + 64) : "memory");
         }
-      }
-      // the tile's 8 atoms of one (part, channel) are one full 32-byte sector of the group's block
-      float* const pg = pool_out + (size_t)(tile >> 1) * 4 * kC * 16 + (size_t)(tile & 1) * 8;
 #pragma unroll
-      for (int part = 0; part < 4; ++part) {
-        float4* p0 = reinterpret_cast<float4*>(pg + ((size_t)part * kC + c2) * 16);
-        float4* p1 = reinterpret_cast<float4*>(pg + ((size_t)part * kC + c2 + 1) * 16);
-        p0[0] = make_float4(acc[0][part][0].x * inv, acc[0][part][1].x * inv, acc[0][part][2].x * inv, acc[0][part][3].x * inv);
-        p0[1] = make_float4(acc[1][part][0].x * inv, acc[1][part][1].x * inv, acc[1][part][2].x * inv, acc[1][part][3].x * inv);
-        p1[0] = make_float4(acc[0][part][0].y * inv, acc[0][part][1].y * inv, acc[0][part][2].y * inv, acc[0][part][3].y * inv);
-        p1[1] = make_float4(acc[1][part][0].y * inv, acc[1][part][1].y * inv, acc[1][part][2].y * inv, acc[1][part][3].y * inv);
+        for (int a = 0; a < 4; ++a)
+#pragma unroll
+          for (int d = 0; d < 3; ++d) sv[(ph * 4 + a) * 3 + d] = fmaf(wz0, acc[d][a].x, wz1 * acc[d][a].y);
       }
+      // sum the 24 partial contractions over the warp's lanes: after the five halving exchanges lane i holds value i
+#pragma unroll
+      for (int bit = 16, n = 32; bit > 0; bit >>= 1, n >>= 1) {
+        const bool up = lane & bit;
+#pragma unroll
+        for (int j = 0; j < 16; ++j) {
+          if (j < n / 2) {
+            const float send = up ? sv[j] : sv[j + n / 2], keep = up ? sv[j + n / 2] : sv[j];
+            sv[j] = keep + __shfl_xor_sync(0xffffffffu, send, bit);
+          }
+        }
+      }
+      if (lane < 24) partials[(size_t)(tile * 8 + lane / 3) * 8 + 2 * (lane % 3) + half] = sv[0];
+      // the tile's 8 atoms of one channel are one full 32-byte sector of the group's block
+      float* const pg = pool_out + (size_t)(tile >> 1) * kC * 16 + (size_t)(tile & 1) * 8;
+      float4* p0 = reinterpret_cast<float4*>(pg + (size_t)c2 * 16);
+      float4* p1 = reinterpret_cast<float4*>(pg + (size_t)(c2 + 1) * 16);
+      p0[0] = make_float4(mean[0][0].x * inv, mean[0][1].x * inv, mean[0][2].x * inv, mean[0][3].x * inv);
+      p0[1] = make_float4(mean[1][0].x * inv, mean[1][1].x * inv, mean[1][2].x * inv, mean[1][3].x * inv);
+      p1[0] = make_float4(mean[0][0].y * inv, mean[0][1].y * inv, mean[0][2].y * inv, mean[0][3].y * inv);
+      p1[1] = make_float4(mean[1][0].y * inv, mean[1][1].y * inv, mean[1][2].y * inv, mean[1][3].y * inv);
     }
   }
   tc_fence_before();
@@ -867,7 +894,7 @@ extern "C" int arreau_debug_set_tc_profile(long long* buf) {
 
 static int convnext_mlp_f16_launch(const void* y_img, const void* w_img, const float* b1, const float* b2,
                                    const float* layer_scale, int64_t num_rows, float* h, const float* ori,
-                                   float* pool_out, void* stream) {
+                                   float* pool_out, const float* pool_wz, int pool_cols, void* stream) {
   if (num_rows == 0) return ARREAU_OK;
   if (!y_img || !w_img || !b1 || !b2 || !layer_scale || !h) return ARREAU_ERR_NULL;
   if (num_rows < 0 || (pool_out && num_rows % kO != 0)) return ARREAU_ERR_BAD_SHAPE;
@@ -880,21 +907,26 @@ static int convnext_mlp_f16_launch(const void* y_img, const void* w_img, const f
   const long long tiles = (num_rows + kTileM - 1) / kTileM;
   const int grid = (int)(tiles < (long long)num_sms_tc() ? tiles : (long long)num_sms_tc());
   convnext_mlp_tc_kernel<<<grid, kThreads, mlp::kSmemBytes, (cudaStream_t)stream>>>(
-      (const uint8_t*)y_img, (const uint8_t*)w_img, b1, b2, layer_scale, (long long)num_rows, h, ori, pool_out);
+      (const uint8_t*)y_img, (const uint8_t*)w_img, b1, b2, layer_scale, (long long)num_rows, h, ori, pool_out, pool_wz,
+      pool_cols);
   CUDA_LAUNCH_CHECK();
   return ARREAU_OK;
 }
 
 extern "C" int arreau_convnext_mlp_f16(const void* y_img, const void* w_img, const float* b1, const float* b2,
                                         const float* layer_scale, int64_t num_rows, float* h, void* stream) {
-  return convnext_mlp_f16_launch(y_img, w_img, b1, b2, layer_scale, num_rows, h, nullptr, nullptr, stream);
+  return convnext_mlp_f16_launch(y_img, w_img, b1, b2, layer_scale, num_rows, h, nullptr, nullptr, nullptr, 0, stream);
 }
 
 extern "C" int arreau_convnext_mlp_f16_pooled(const void* y_img, const void* w_img, const float* b1, const float* b2,
                                                const float* layer_scale, int64_t num_rows, float* h, const float* ori,
-                                               float* pool_out, void* stream) {
-  if (num_rows > 0 && (!ori || !pool_out)) return ARREAU_ERR_NULL;
-  return convnext_mlp_f16_launch(y_img, w_img, b1, b2, layer_scale, num_rows, h, ori, pool_out, stream);
+                                               float* pool_out, const float* readout_v_k, int32_t num_states,
+                                               void* stream) {
+  if (num_rows > 0 && (!ori || !pool_out || !readout_v_k)) return ARREAU_ERR_NULL;
+  if (num_states <= 0) return ARREAU_ERR_BAD_SHAPE;
+  // the spare warps contract the vector-pooled parts with column Z of the entry's [C][Z+6] read-out matrix
+  return convnext_mlp_f16_launch(y_img, w_img, b1, b2, layer_scale, num_rows, h, ori, pool_out, readout_v_k + num_states,
+                                 num_states + 6, stream);
 }
 
 extern "C" int arreau_edge_kernels_f16(const double* dir, const double* dist, const double* lattice,

@@ -111,7 +111,7 @@ extern "C" int arreau_ponita_forward(const arreau_weights* w, const arreau_works
   const size_t pool_elems = (size_t)((N + 15) / 16) * 4 * kC * 16;   // one entry: [groups of 16 atoms][4][C][16]
   if (pool)
     ARREAU_TRY(arreau_node_embed_pooled(x, ws->onehot_types, Z, vec, w->w_embed_t, w->ori, N, w->num_scalar, w->num_vec,
-                                        ws->h, pool, stream));
+                                        ws->h, pool, w->readout_v, stream));
   else if (ws->onehot_types)
     ARREAU_TRY(arreau_node_embed_typed(x, ws->onehot_types, Z, vec, w->w_embed_t, w->ori, N, w->num_scalar, w->num_vec,
                                        ws->h, stream));
@@ -142,7 +142,7 @@ extern "C" int arreau_ponita_forward(const arreau_weights* w, const arreau_works
       ARREAU_TRY(arreau_convnext_mlp_f16_pooled(ws->y, (const uint8_t*)w->mlp_w_img + (size_t)l * 8 * 32768,
                                                  w->mlp_b1 + l * kW, w->mlp_b2 + l * kC, w->layer_scale + l * kC,
                                                  (int64_t)N * kO, ws->h, w->ori, pool + (size_t)(l + 1) * pool_elems,
-                                                 stream));
+                                                 w->readout_v + (size_t)(l + 1) * kC * (Z + 6), Z, stream));
     else if (fp16)
       ARREAU_TRY(arreau_convnext_mlp_f16(ws->y, (const uint8_t*)w->mlp_w_img + (size_t)l * 8 * 32768,
                                           w->mlp_b1 + l * kW, w->mlp_b2 + l * kC, w->layer_scale + l * kC,

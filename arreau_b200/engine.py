@@ -344,7 +344,8 @@ class DenoiseEngine:
         if pooled:
             add("node_embed", lambda: _lib.call("arreau_node_embed_pooled", self.x.data_ptr(), self.types.data_ptr(), Z,
                                                 self.vec.data_ptr(), w["w_embed_t"].data_ptr(), w["ori"].data_ptr(),
-                                                self.N, self.F, 4, self.h.data_ptr(), self.pool[0].data_ptr(), self.stream))
+                                                self.N, self.F, 4, self.h.data_ptr(), self.pool[0].data_ptr(),
+                                                w["readout_v"][0].data_ptr(), self.stream))
         else:
             add("node_embed", lambda: _lib.call("arreau_node_embed_typed", self.x.data_ptr(), self.types.data_ptr(), Z,
                                                 self.vec.data_ptr(), w["w_embed_t"].data_ptr(), w["ori"].data_ptr(),
@@ -382,7 +383,7 @@ class DenoiseEngine:
                     "arreau_convnext_mlp_f16_pooled", self.y.data_ptr(), w["mlp_w_img"].data_ptr() + l * 8 * 32768,
                     w["mlp_b1"][l].data_ptr(), w["mlp_b2"][l].data_ptr(),
                     w["layer_scale"][l].data_ptr(), self.N * NUM_ORI, self.h.data_ptr(), w["ori"].data_ptr(),
-                    self.pool[l + 1].data_ptr(), self.stream))
+                    self.pool[l + 1].data_ptr(), w["readout_v"][l + 1].data_ptr(), Z, self.stream))
             elif fp16:
                 add("convnext_mlp", lambda l=l: _lib.call(
                     "arreau_convnext_mlp_f16", self.y.data_ptr(), w["mlp_w_img"].data_ptr() + l * 8 * 32768,

@@ -202,23 +202,28 @@ int arreau_convnext_mlp_f16(const void* y_img, const void* w_img, const float* b
                              const float* layer_scale, int64_t num_rows, float* h, void* stream);
 
 /* Pooled read-out path of the fp16 tensor path (K7 fused into K2 / K6; ponita.py:105-117, to_from_sphere.py:10-14).
- * The read-out Linear commutes with the orientation pooling, so only pooled features are needed.  One pool ENTRY is
- * f32 [ceil(N/16)][4][C][16]: for each group of 16 atoms and channel c the 16 atoms' values of the four parts
- *   part 0 = mean_o x[b,o,c],   part 1+d = (1/O) sum_o ori[o][d] x[b,o,c].
- * pool is [L+1] entries: entry 0 pools the embedding output, entry k = 1..L pools the residual UPDATE of interaction
- * layer k (the feature after layer l is the sum of entries 0..l).
+ * The read-out Linear commutes with the orientation pooling, so only pooled features are needed, and the vector
+ * channel only meets ONE weight row (row Z), so its contraction over the channels is done by the producer.
+ * One pool ENTRY has a stride of ceil(N/16)*4*C*16 floats and holds
+ *   [ceil(N/16)][C][16]       for each group of 16 atoms and channel c the 16 atoms' values of mean_o x[b,o,c],
+ *   [ceil(N/16)*16][8]        per atom, element 2 d + half (d = 0..2; half = the producer's two channel halves):
+ *                             sum_{c in half} V_k[c][Z] * (1/O) sum_o ori[o][d] x[b,o,c]
+ * (the rest of the stride is unused).  pool is [L+1] entries: entry 0 pools the embedding output, entry k = 1..L pools
+ * the residual UPDATE of interaction layer k (the feature after layer l is the sum of entries 0..l).
+ * readout_v[L+1][C][Z+6], readout_bias[Z+6]: the per-entry sums of the read-out weights combined on the host
+ * (arreau_b200/weights.py: pooled_readout_weights); readout_v_k = readout_v + k*C*(Z+6) is entry k's matrix.
  * arreau_node_embed_pooled: K2 that also writes entry 0 (types may be NULL).
  * arreau_convnext_mlp_f16_pooled: K6 whose two spare warps pool the residual update staged in shared memory into
  *   pool_out (one entry); h itself is updated as by arreau_convnext_mlp_f16.
  * arreau_readout_pooled: acc[N,Z+6] (column layout of arreau_readout_accumulate, already divided by L) =
- *   sum_k readout_v[k] pool[k] + readout_bias, with readout_v[L+1][C][Z+6], readout_bias[Z+6] the per-entry sums of
- *   the read-out weights combined on the host (arreau_b200/weights.py: pooled_readout_weights); entries = L+1. */
+ *   sum_k readout_v[k] pool[k] + readout_bias (TF32 tensor-core products with the 3xTF32 split: fp32 accuracy);
+ *   entries = L+1. */
 int arreau_node_embed_pooled(const float* x, const int64_t* types, int32_t num_states, const float* vec,
                              const float* w_embed_t, const float* ori, int32_t num_atoms_total, int32_t num_scalar,
-                             int32_t num_vec, float* h, float* pool, void* stream);
+                             int32_t num_vec, float* h, float* pool, const float* readout_v_0, void* stream);
 int arreau_convnext_mlp_f16_pooled(const void* y_img, const void* w_img, const float* b1, const float* b2,
                                     const float* layer_scale, int64_t num_rows, float* h, const float* ori,
-                                    float* pool_out, void* stream);
+                                    float* pool_out, const float* readout_v_k, int32_t num_states, void* stream);
 int arreau_readout_pooled(const float* pool, const float* readout_v, const float* readout_bias,
                           int32_t num_atoms_total, int32_t num_states, int32_t entries, float* acc, void* stream);
 
