@@ -113,6 +113,7 @@ constexpr int kWStages = 3;
 constexpr int kTilesBytes = (2 + 2 + kWStages) * kTileBytes;
 constexpr int kSmemBytes = 232448;    // everything (tiles, bias, barriers) is carved from the dynamic window
 constexpr int kChunksPerTile = 8;     // W1_0, W1_1, W2_0, W1_2, W2_1, W1_3, W2_2, W2_3
+constexpr uint32_t kHCol = 384;       // TMEM: D1[2] = [0,256), D2 = [256,384), hidden-slice operand H[2] = [384,512) (64 columns each)
 
 struct Bars {
   uint64_t a_full[2], a_empty[2], w_full[kWStages], w_empty[kWStages];
@@ -180,7 +181,7 @@ convnext_mlp_tc_kernel(const uint8_t* __restrict__ y_img, const uint8_t* __restr
     // ---------------- MMA issuer: the whole warp runs the loop uniformly, one elected lane issues
     // (see tc_common.cuh: a divergent single thread pays ~50 cycles per MMA for operand moves) ----------------
     const uint32_t el = elect_one();
-    const uint32_t a_lo0 = umma_desc_lo(smem_u32(A0)), h_lo0 = umma_desc_lo(smem_u32(H0)), w_lo0 = umma_desc_lo(smem_u32(W));
+    const uint32_t a_lo0 = umma_desc_lo(smem_u32(A0)), w_lo0 = umma_desc_lo(smem_u32(W));
     const uint32_t wfull = smem_u32(&bars.w_full[0]), wempty = smem_u32(&bars.w_empty[0]);
     constexpr uint32_t kSlabLo = 16384 >> 4, kTileLo = kTileBytes >> 4;
     uint32_t ws = 0, wpar = 0;
@@ -220,7 +221,14 @@ convnext_mlp_tc_kernel(const uint8_t* __restrict__ y_img, const uint8_t* __restr
         mbar_wait(&bars.h_full[b], use & 1);
         if (j == 0) mbar_wait(&bars.d2_empty, (it & 1) ^ 1);
         tc_fence_after();
-        mma_tile(tmem + 256, h_lo0 + b * kTileLo, j > 0 ? 1u : 0u);
+        {
+          // the hidden slice is the A operand straight out of tensor memory (64 columns of packed fp16 per buffer)
+          const uint32_t w_lo = w_lo0 + ws * kTileLo, a_t = tmem + kHCol + b * 64;
+          umma_slab_ts_e<4>(tmem + 256, a_t, w_lo, kIdesc128, el, j > 0 ? 1u : 0u);
+          umma_slab_ts_e<4>(tmem + 256, a_t + 32, w_lo + kSlabLo, kIdesc128, el, 1u);
+          umma_commit_e(wempty + 8 * ws, el);
+          if (++ws == (uint32_t)kWStages) { ws = 0; wpar ^= 1; }
+        }
         umma_commit_e(smem_u32(&bars.h_empty[b]), el);
         if (j == 3) umma_commit_e(smem_u32(&bars.d2_full), el);
         TC_STAMP(6 + j);
@@ -249,27 +257,16 @@ convnext_mlp_tc_kernel(const uint8_t* __restrict__ y_img, const uint8_t* __restr
         tmem_ld32(tmem + lane_addr + b * 128 + cgi * 32, v);
         uint4 pk[4];
         gelu_pack32(v, s_b1 + j * 128 + cgi * 32, pk);
-        if (j < 2 && it > 0) {
-          // H[j] doubled as the staging area of the previous tile's residual reduce (rows 64j .. 64j+63): its bulk
-          // reduce must have finished reading shared memory before the buffer is rewritten
-          if (is_issuer) {
-            if (j == 0) asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");
-            else asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
-          }
-          // with pooling the pool warps (barriers 3 / 4) must also be done reading this half of the staged update
-          if (!pool_out) asm volatile("bar.sync 1, %0;" ::"n"(kEpiThreads) : "memory");
-          else if (j == 0) asm volatile("bar.sync 3, %0;" ::"n"(kEpiThreads + 64) : "memory");
-          else asm volatile("bar.sync 4, %0;" ::"n"(kEpiThreads + 64) : "memory");
-        }
         {
-          // hidden unit k = cgi*32 .. +31 of this 128-slice -> slab cgi>>1, chunks (cgi&1)*4 .. +3
-          uint8_t* hrow = H0 + b * kTileBytes + (cgi >> 1) * 16384 + m * kRowBytes;
+          // hidden unit k = cgi*32 .. +31 of this 128-slice -> 16 columns of packed pairs in the TMEM operand H[b]
+          const uint32_t* pr = reinterpret_cast<const uint32_t*>(pk);
+          uint32_t regs[16];
 #pragma unroll
-          for (int cc = 0; cc < 4; ++cc)
-            *reinterpret_cast<uint4*>(hrow + ((((cgi & 1) * 4 + cc) ^ (m & 7)) << 4)) = pk[cc];
+          for (int i = 0; i < 16; ++i) regs[i] = pr[i];
+          tmem_st16(tmem + lane_addr + kHCol + b * 64 + cgi * 16, regs);
+          tmem_wait_st();
         }
         tc_fence_before();
-        fence_proxy_async();
         __syncwarp();
         if (lane == 0) {
           mbar_arrive(&bars.d1_empty[b]);
@@ -292,6 +289,17 @@ convnext_mlp_tc_kernel(const uint8_t* __restrict__ y_img, const uint8_t* __restr
         tc_fence_before();
         __syncwarp();
         if (lane == 0) mbar_arrive(&bars.d2_empty);       // accumulators are in registers: release D2 early
+        if (it > 0) {
+          // the staging area still holds the previous tile's update: its bulk reduce must have finished reading shared
+          // memory, and with pooling the pool warps (barriers 3 / 4, one per half) must be done with it too
+          if (is_issuer) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+          if (!pool_out) {
+            asm volatile("bar.sync 1, %0;" ::"n"(kEpiThreads) : "memory");
+          } else {
+            asm volatile("bar.sync 3, %0;" ::"n"(kEpiThreads + 64) : "memory");
+            asm volatile("bar.sync 4, %0;" ::"n"(kEpiThreads + 64) : "memory");
+          }
+        }
         const int c0 = cgi * 32;
         float4 d[8];
 #pragma unroll

@@ -217,6 +217,26 @@ __device__ __forceinline__ void umma_slab_e(uint32_t tmem_d, uint32_t a_lo, uint
 #pragma unroll
   for (int k = 1; k < KSTEPS; ++k) umma_f16_e(tmem_d, a_lo + 2 * k, b_lo + 2 * k, idesc, elected, 1u);
 }
+// A operand from tensor memory (row m in lane m, the K values packed two fp16 per 32-bit column, 8 columns per
+// UMMA_K = 16 step), B from shared memory: D (+)= A[tmem] . B^T
+__device__ __forceinline__ void umma_f16_ts_e(uint32_t tmem_d, uint32_t a_tmem, uint32_t b_lo, uint32_t idesc, uint32_t elected,
+                                              uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p, e;\n\t.reg .b64 db;\n\t"
+      "mov.b64 db, {%2, %4};\n\t"
+      "setp.ne.u32 e, %5, 0;\n\t"
+      "setp.ne.u32 p, %6, 0;\n\t"
+      "@e tcgen05.mma.cta_group::1.kind::f16 [%0], [%1], db, %3, p;\n\t}"
+      ::"r"(tmem_d), "r"(a_tmem), "r"(b_lo), "r"(idesc), "r"(kDescHiSw128), "r"(elected), "r"(accumulate)
+      : "memory");
+}
+template <int KSTEPS>
+__device__ __forceinline__ void umma_slab_ts_e(uint32_t tmem_d, uint32_t a_tmem, uint32_t b_lo, uint32_t idesc, uint32_t elected,
+                                               uint32_t accumulate_first) {
+  umma_f16_ts_e(tmem_d, a_tmem, b_lo, idesc, elected, accumulate_first);
+#pragma unroll
+  for (int k = 1; k < KSTEPS; ++k) umma_f16_ts_e(tmem_d, a_tmem + 8 * k, b_lo + 2 * k, idesc, elected, 1u);
+}
 __device__ __forceinline__ void umma_commit_e(uint32_t bar_addr, uint32_t elected) {
   asm volatile(
       "{\n\t.reg .pred e;\n\tsetp.ne.u32 e, %1, 0;\n\t"
