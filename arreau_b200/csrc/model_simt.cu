@@ -1153,37 +1153,27 @@ constexpr int kPoolCols = 96;
 constexpr int kPoolWarps = 8;
 // One pool entry = [groups][C][16 atoms] of the orientation mean, then [groups * 16 atoms][8] partial contractions of
 // the vector-pooled parts with the score row: element 2 d + half (d = 0..2; the producer's two channel halves).
-// Tensor cores: the [16 atoms x C] block of a group is the A operand of mma.sync.m16n8k8 TF32 products against
-// V_k[C][96] (12 n-tiles), with the 3xTF32 split (a_lo b_hi + a_hi b_lo + a_hi b_hi, fp32 accumulation) so that the
-// result keeps fp32 accuracy (the read-outs feed the D3PM argmax and the coordinate update directly).  V_k sits in
-// shared memory in fp32 (row stride 104 floats: conflict-free B fragments) and is split on the fly.  One persistent
-// CTA per SM, one warp per 16-atom group; the group's 8 KB block arrives through a per-warp cp.async double buffer
-// (the next group's block is in flight while this one is multiplied); acc is updated in place, entry by entry, in a
-// fixed order (deterministic).  Measured: 0.26 ms at C2, bound by the legacy mma.sync TF32 rate (8.8 M instructions,
-// ~33 cycles each per SM sub-partition, about 70 TFLOP/s) -- a tcgen05 kind::tf32 version is the next step.
-constexpr int kRpV = 104;
+// One persistent CTA per SM; per entry k the 48 KB matrix V_k sits in shared memory; a warp owns a group of 16 atoms:
+// lane = output columns (lane, lane + 32, lane + 64), 16 atoms x 3 columns accumulated as packed FFMA2 over atom pairs
+// (fp32 throughout: the read-outs feed the D3PM argmax and the coordinate update directly); the group's 8 KB block
+// arrives through a per-warp cp.async double buffer (the next group's block is in flight while this one is
+// multiplied); lanes 0..15 add the producers' score partials of one atom each; acc is updated in place, entry by entry,
+// in a fixed order (deterministic).  (A mma.sync TF32 version with the 3xTF32 split measured 0.26 ms against this
+// kernel's FFMA2: the legacy tensor path delivers ~70 TFLOP/s of TF32 on this part, a third of that after the split.)
 constexpr int kRpBlockFloats = kC * kPoolAtoms;                                 // 2048 floats = 8 KB
-constexpr int kRpSmem = (kC * kRpV + kPoolWarps * 2 * kRpBlockFloats) * (int)sizeof(float);
-
-__device__ __forceinline__ uint32_t tf32_rna(float x) {
-  uint32_t r;
-  asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(x));
-  return r;
-}
-__device__ __forceinline__ void mma1688_tf32(float (&d)[4], const uint32_t (&a)[4], uint32_t b0, uint32_t b1) {
-  asm volatile("mma.sync.aligned.m16n8k8.row.col.f32.tf32.tf32.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
-               : "+f"(d[0]), "+f"(d[1]), "+f"(d[2]), "+f"(d[3])
-               : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
-}
+constexpr int kRpSmem = (kC * kPoolCols + kPoolWarps * 2 * kRpBlockFloats) * (int)sizeof(float);
 
 __global__ void __launch_bounds__(kPoolWarps * 32, 1)
 readout_pooled_kernel(const float* __restrict__ pool, size_t entry_stride, const float* __restrict__ v,
                       const float* __restrict__ bias, int N, int Z, int entries, float* __restrict__ acc) {
   extern __shared__ __align__(16) float rp_sm[];
-  float* const vs = rp_sm;                                                       // [kC][kRpV]
-  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, g = lane >> 2, t = lane & 3;
-  float* const pb = rp_sm + kC * kRpV + warp * 2 * kRpBlockFloats;               // this warp's [2][C][16 atoms]
+  float* const vs = rp_sm;                                                       // [kC][kPoolCols]
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  float* const pb = rp_sm + kC * kPoolCols + warp * 2 * kRpBlockFloats;          // this warp's [2][C][16 atoms]
   const int groups = (N + kPoolAtoms - 1) / kPoolAtoms;
+  // columns Z..Z+2 (the score vector) come from the producers' partials, not from this product
+  const int col2 = lane + 64;
+  const bool skip2 = col2 >= Z && col2 < Z + 3;
   auto load_block = [&](const float* gsrc, int buf) {                            // 8 KB, 16 bytes per lane and copy
     float* dst = pb + buf * kRpBlockFloats;
 #pragma unroll
@@ -1192,15 +1182,27 @@ readout_pooled_kernel(const float* __restrict__ pool, size_t entry_stride, const
   };
   for (int k = 0; k < entries; ++k) {
     __syncthreads();                                                             // the previous matrix is no longer read
-    for (int i = tid; i < kC * kPoolCols; i += kPoolWarps * 32) {
-      const int c = i / kPoolCols, n = i - c * kPoolCols;
-      vs[c * kRpV + n] = __ldg(v + (size_t)k * kC * kPoolCols + i);
-    }
+    for (int i = tid; i < kC * kPoolCols / 4; i += kPoolWarps * 32)
+      reinterpret_cast<float4*>(vs)[i] = __ldg(reinterpret_cast<const float4*>(v + (size_t)k * kC * kPoolCols) + i);
     __syncthreads();
     const float* entry = pool + (size_t)k * entry_stride;
     const float* partials = entry + (size_t)groups * kRpBlockFloats;
     const int g0 = blockIdx.x * kPoolWarps + warp, gstep = gridDim.x * kPoolWarps;
     if (g0 < groups) load_block(entry + (size_t)g0 * kRpBlockFloats, 0);
+    auto load_acc = [&](int base, float2 (&x)[3][kPoolAtoms / 2]) {              // running sums of a group (bias at k = 0)
+#pragma unroll
+      for (int j = 0; j < 3; ++j) {
+        const bool skip = j == 2 && skip2;
+        const float bb = k == 0 ? bias[lane + 32 * j] : 0.f;
+#pragma unroll
+        for (int a = 0; a < kPoolAtoms / 2; ++a) {
+          const int a0 = base + 2 * a;
+          x[j][a].x = k == 0 ? bb : ((a0 < N && !skip) ? acc[(size_t)a0 * kPoolCols + lane + 32 * j] : 0.f);
+          x[j][a].y = k == 0 ? bb : ((a0 + 1 < N && !skip) ? acc[(size_t)(a0 + 1) * kPoolCols + lane + 32 * j] : 0.f);
+        }
+      }
+    };
+    float2 rn[3][kPoolAtoms / 2];
     int it = 0;
     for (int grp = g0; grp < groups; grp += gstep, ++it) {
       const int b0 = grp * kPoolAtoms;
@@ -1211,20 +1213,16 @@ readout_pooled_kernel(const float* __restrict__ pool, size_t entry_stride, const
         cp_async_wait<0>();
       }
       __syncwarp();
-      const bool r0 = b0 + g < N, r1 = b0 + g + 8 < N;
-      float d[kPoolCols / 8][4];
+      float2 r[3][kPoolAtoms / 2];
+      if (it == 0) load_acc(b0, r);
+      else {
 #pragma unroll
-      for (int nt = 0; nt < kPoolCols / 8; ++nt) {
-        const int col = nt * 8 + 2 * t;
-        if (k == 0) {
-          d[nt][0] = d[nt][2] = bias[col];
-          d[nt][1] = d[nt][3] = bias[col + 1];
-        } else {
-          const float2 x0 = r0 ? *reinterpret_cast<const float2*>(acc + (size_t)(b0 + g) * kPoolCols + col) : make_float2(0.f, 0.f);
-          const float2 x1 = r1 ? *reinterpret_cast<const float2*>(acc + (size_t)(b0 + g + 8) * kPoolCols + col) : make_float2(0.f, 0.f);
-          d[nt][0] = x0.x; d[nt][1] = x0.y; d[nt][2] = x1.x; d[nt][3] = x1.y;
-        }
+        for (int j = 0; j < 3; ++j)
+#pragma unroll
+          for (int a = 0; a < kPoolAtoms / 2; ++a) r[j][a] = rn[j][a];
       }
+      // the next group's running sums are fetched now, under this group's products
+      if (grp + gstep < groups) load_acc(b0 + gstep * kPoolAtoms, rn);
       // score vector (columns Z..Z+2): lanes 0..15 own one atom each and add the producers' partial contractions
       float sc[3] = {0.f, 0.f, 0.f};
       const bool sv = lane < kPoolAtoms && b0 + lane < N;
@@ -1237,52 +1235,33 @@ readout_pooled_kernel(const float* __restrict__ pool, size_t entry_stride, const
         sc[2] = (k == 0 ? bias[Z + 2] : prev[2]) + (s1.x + s1.y);
       }
       const float* p0 = pb + (it & 1) * kRpBlockFloats;
+      const float* w = vs + lane;
 #pragma unroll 2
-      for (int ks = 0; ks < kC / 8; ++ks) {
-        uint32_t ahi[4], alo[4];
+      for (int c = 0; c < kC; ++c) {
+        const float w0 = w[c * kPoolCols], w1 = w[c * kPoolCols + 32], w2 = w[c * kPoolCols + 64];
+        const float2 w0d = make_float2(w0, w0), w1d = make_float2(w1, w1), w2d = make_float2(w2, w2);
 #pragma unroll
-        for (int i = 0; i < 4; ++i) {
-          const float a = p0[(ks * 8 + t + 4 * (i >> 1)) * kPoolAtoms + g + 8 * (i & 1)];
-          ahi[i] = tf32_rna(a);
-          alo[i] = tf32_rna(a - __uint_as_float(ahi[i]));
-        }
-        const float* vrow = vs + (ks * 8 + t) * kRpV + g;
-        // six n-tiles at a time, term by term: the three products into one accumulator are six independent
-        // instructions apart, so the warp does not wait on the tensor pipe's latency
-#pragma unroll
-        for (int nh = 0; nh < 2; ++nh) {
-          uint32_t bh[6][2], bl[6][2];
-#pragma unroll
-          for (int j = 0; j < 6; ++j) {
-            const float w0 = vrow[(nh * 6 + j) * 8], w1 = vrow[4 * kRpV + (nh * 6 + j) * 8];
-            bh[j][0] = tf32_rna(w0); bh[j][1] = tf32_rna(w1);
-            bl[j][0] = tf32_rna(w0 - __uint_as_float(bh[j][0])); bl[j][1] = tf32_rna(w1 - __uint_as_float(bh[j][1]));
-          }
-#pragma unroll
-          for (int j = 0; j < 6; ++j) mma1688_tf32(d[nh * 6 + j], alo, bh[j][0], bh[j][1]);
-#pragma unroll
-          for (int j = 0; j < 6; ++j) mma1688_tf32(d[nh * 6 + j], ahi, bl[j][0], bl[j][1]);
-#pragma unroll
-          for (int j = 0; j < 6; ++j) mma1688_tf32(d[nh * 6 + j], ahi, bh[j][0], bh[j][1]);
+        for (int q4 = 0; q4 < kPoolAtoms / 4; ++q4) {
+          const float4 pa = *reinterpret_cast<const float4*>(p0 + c * kPoolAtoms + 4 * q4);
+          const float2 pa0 = make_float2(pa.x, pa.y), pa1 = make_float2(pa.z, pa.w);
+          r[0][2 * q4] = __ffma2_rn(w0d, pa0, r[0][2 * q4]);
+          r[0][2 * q4 + 1] = __ffma2_rn(w0d, pa1, r[0][2 * q4 + 1]);
+          r[1][2 * q4] = __ffma2_rn(w1d, pa0, r[1][2 * q4]);
+          r[1][2 * q4 + 1] = __ffma2_rn(w1d, pa1, r[1][2 * q4 + 1]);
+          r[2][2 * q4] = __ffma2_rn(w2d, pa0, r[2][2 * q4]);
+          r[2][2 * q4 + 1] = __ffma2_rn(w2d, pa1, r[2][2 * q4 + 1]);
         }
       }
       __syncwarp();                                                              // the buffer is refilled by the next iteration
 #pragma unroll
-      for (int nt = 0; nt < kPoolCols / 8; ++nt) {
-        const int col = nt * 8 + 2 * t;
-        // columns Z..Z+2 belong to the score side
-        const bool k0 = col < Z || col >= Z + 3, k1 = col + 1 < Z || col + 1 >= Z + 3;
-        if (r0) {
-          float* o = acc + (size_t)(b0 + g) * kPoolCols + col;
-          if (k0) o[0] = d[nt][0];
-          if (k1) o[1] = d[nt][1];
+      for (int j = 0; j < 3; ++j)
+#pragma unroll
+        for (int a = 0; a < kPoolAtoms / 2; ++a) {
+          const int a0 = b0 + 2 * a;
+          const bool skip = j == 2 && skip2;
+          if (a0 < N && !skip) acc[(size_t)a0 * kPoolCols + lane + 32 * j] = r[j][a].x;
+          if (a0 + 1 < N && !skip) acc[(size_t)(a0 + 1) * kPoolCols + lane + 32 * j] = r[j][a].y;
         }
-        if (r1) {
-          float* o = acc + (size_t)(b0 + g + 8) * kPoolCols + col;
-          if (k0) o[0] = d[nt][2];
-          if (k1) o[1] = d[nt][3];
-        }
-      }
       if (sv) {
         float* o = acc + (size_t)(b0 + lane) * kPoolCols + Z;
         o[0] = sc[0]; o[1] = sc[1]; o[2] = sc[2];

@@ -216,8 +216,7 @@ int arreau_convnext_mlp_f16(const void* y_img, const void* w_img, const float* b
  * arreau_convnext_mlp_f16_pooled: K6 whose two spare warps pool the residual update staged in shared memory into
  *   pool_out (one entry); h itself is updated as by arreau_convnext_mlp_f16.
  * arreau_readout_pooled: acc[N,Z+6] (column layout of arreau_readout_accumulate, already divided by L) =
- *   sum_k readout_v[k] pool[k] + readout_bias (TF32 tensor-core products with the 3xTF32 split: fp32 accuracy);
- *   entries = L+1. */
+ *   sum_k readout_v[k] pool[k] + readout_bias (fp32); entries = L+1. */
 int arreau_node_embed_pooled(const float* x, const int64_t* types, int32_t num_states, const float* vec,
                              const float* w_embed_t, const float* ori, int32_t num_atoms_total, int32_t num_scalar,
                              int32_t num_vec, float* h, float* pool, const float* readout_v_0, void* stream);
