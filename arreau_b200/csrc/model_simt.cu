@@ -710,7 +710,41 @@ message_fiber_norm_fused_kernel(const __half* __restrict__ kern, const float* __
         float4 s0 = make_float4(0.f, 0.f, 0.f, 0.f), s1 = s0;
         const int koff0 = (((lane >> 1) ^ o0) << 3) | ((lane & 1) << 2);
         const int koff1 = (((lane >> 1) ^ (o0 + 1)) << 3) | ((lane & 1) << 2);
-        for (int e = e0; e < e1; e += 8) {
+        int e = e0;
+        if (e1 - e0 >= 8) {
+          // full first chunk (every atom under the neighbour cap): the 8 slab rows are 4 KB apart from one base pointer
+          // (immediate offsets), the source rows one wide multiply each; no clamps, no per-edge predicates
+          const __half* k0 = kern + ((size_t)e0 * kO + o0) * kC + koff0;
+          const __half* k1 = kern + ((size_t)e0 * kO + o0 + 1) * kC + koff1;
+          const float* hb = h + (size_t)o0 * kC + lane * 4;
+          uint2 kv0[8], kv1[8];
+          float4 hv0[8], hv1[8];
+#pragma unroll
+          for (int u = 0; u < 8; ++u) {
+            asm volatile("ld.global.L1::no_allocate.v2.u32 {%0, %1}, [%2];" : "=r"(kv0[u].x), "=r"(kv0[u].y) : "l"(k0 + (size_t)u * kO * kC));
+            asm volatile("ld.global.L1::no_allocate.v2.u32 {%0, %1}, [%2];" : "=r"(kv1[u].x), "=r"(kv1[u].y) : "l"(k1 + (size_t)u * kO * kC));
+            const float* hrow = hb + (size_t)(unsigned)sj0[u] * (kO * kC);
+            hv0[u] = *reinterpret_cast<const float4*>(hrow);
+            hv1[u] = *reinterpret_cast<const float4*>(hrow + kC);
+          }
+#pragma unroll
+          for (int u = 0; u < 8; ++u) {
+            const float2 a0 = __half22float2(*reinterpret_cast<const __half2*>(&kv0[u].x));
+            const float2 a1 = __half22float2(*reinterpret_cast<const __half2*>(&kv0[u].y));
+            s0.x = fmaf(a0.x, hv0[u].x, s0.x);
+            s0.y = fmaf(a0.y, hv0[u].y, s0.y);
+            s0.z = fmaf(a1.x, hv0[u].z, s0.z);
+            s0.w = fmaf(a1.y, hv0[u].w, s0.w);
+            const float2 b0 = __half22float2(*reinterpret_cast<const __half2*>(&kv1[u].x));
+            const float2 b1 = __half22float2(*reinterpret_cast<const __half2*>(&kv1[u].y));
+            s1.x = fmaf(b0.x, hv1[u].x, s1.x);
+            s1.y = fmaf(b0.y, hv1[u].y, s1.y);
+            s1.z = fmaf(b1.x, hv1[u].z, s1.z);
+            s1.w = fmaf(b1.y, hv1[u].w, s1.w);
+          }
+          e = e0 + 8;
+        }
+        for (; e < e1; e += 8) {
           uint2 kv0[8], kv1[8];
           float4 hv0[8], hv1[8];
 #pragma unroll
