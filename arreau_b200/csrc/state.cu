@@ -199,6 +199,10 @@ d3pm_reverse_kernel(const int64_t* types, const float* __restrict__ logits,
   const double scale = (t != 1) ? 1.0 : (double)0.2f;
   double best = -INFINITY;
   int best_d = 0x7fffffff;
+  // q_one_step_transposed[t-1, x_t, d] = Q[d, x_t] only takes two values per atom: their logs are evaluated once
+  // (same log on the same doubles as the per-element form: identical bits)
+  const double f1_hit = (xt != mask) ? onestep_keep : 1.0, f1_miss = (xt != mask) ? 0.0 : onestep_to_mask;
+  const double lf1_hit = log(f1_hit + kD3pmEps), lf1_miss = log(f1_miss + kD3pmEps);
 #pragma unroll
   for (int r = 0; r < kPer; ++r) {
     const int d = lane + 32 * r;
@@ -207,13 +211,11 @@ d3pm_reverse_kernel(const int64_t* types, const float* __restrict__ logits,
     if (t == 1) {
       lp = lg[r];
     } else {
-      double f1;   // q_one_step_transposed[t-1, x_t, d] = Q[d, x_t]
-      if (xt != mask) f1 = (d == xt) ? onestep_keep : 0.0;
-      else f1 = (d == mask) ? 1.0 : onestep_to_mask;
+      const bool hit = (xt != mask) ? (d == xt) : (d == mask);
       double f2;   // sum_c softmax_c * Qbar[c, d]
       if (d != mask) f2 = p[r] * qa;
       else f2 = sum_nomask * qb + p_mask;
-      lp = log(f1 + kD3pmEps) + log(f2 + kD3pmEps);
+      lp = (hit ? lf1_hit : lf1_miss) + log(f2 + kD3pmEps);
     }
     double noise = u[(size_t)b * Z + d];
     noise = fmin(fmax(noise, kD3pmEps), 1.0);
