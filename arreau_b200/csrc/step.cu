@@ -133,6 +133,17 @@ extern "C" int arreau_ponita_forward(const arreau_weights* w, const arreau_works
   for (int l = 0; l < kL; ++l) {
     const void* kern = fp16 ? (const void*)((const uint16_t*)ws->kernels + (size_t)l * layer_elems)
                             : (const void*)((const float*)ws->kernels + (size_t)l * layer_elems);
+    // long rows (uncapped graphs, E/N ~ 30..90): the fused kernel's one-warp-per-atom gather serialises a row's
+    // edges 8 at a time; the CTA-per-atom gather + separate tensor-core fiber conv is faster there (C2 uncapped:
+    // 22.3 ms of message pass per step fused against ~15 ms for the pair)
+    const bool long_rows = fp16 && w->fiber_frag && ws->edge_capacity > 16LL * N;
+    if (long_rows) {
+      const void* frag = (const uint8_t*)w->fiber_frag + (size_t)l * kC * 32 * 16;
+      ARREAU_TRY(arreau_message_gather(kern, 1, ws->h, row_ptr, src, N, 1, ws->x1, stream));
+      ARREAU_TRY(arreau_fiber_norm(ws->x1, 1, w->fiber_kernel + (size_t)l * kO * kO * kC, frag, w->conv_bias + l * kC,
+                                   w->ln_w + l * kC, w->ln_b + l * kC, N, ws->y, 1,
+                                   ws->x2_debug ? ws->x2_debug + l * node_elems : nullptr, stream));
+    } else
     ARREAU_TRY(arreau_message_fiber_norm(kern, fp16, ws->h, row_ptr, src, w->fiber_kernel + (size_t)l * kO * kO * kC,
                                          w->fiber_frag ? (const uint8_t*)w->fiber_frag + (size_t)l * kC * 32 * 16 : nullptr,
                                          w->conv_bias + l * kC, w->ln_w + l * kC, w->ln_b + l * kC, N, ws->y, fp16,

@@ -364,7 +364,17 @@ class DenoiseEngine:
                 w["w1m_t"].data_ptr(), w["w2_t"].data_ptr(), w["b2"].data_ptr(), w["wk_t"].data_ptr(),
                 self.radius, self.kernels.data_ptr(), self.stream))
         for l in range(LAYERS):
-            if fp16:      # one fused launch (the message sums stay in shared memory)
+            if fp16 and self.edge_capacity > 16 * self.N:
+                # long rows (uncapped graphs): the step runs the CTA-per-atom gather + tensor-core fiber conv pair
+                # (csrc/step.cu); both launches are booked under the fused kernel's label
+                add("message_fiber_norm", lambda l=l: _lib.call(
+                    "arreau_message_gather", self.kernels[l].data_ptr(), 1, self.h.data_ptr(),
+                    self.row_ptr.data_ptr(), self.src.data_ptr(), self.N, 1, self.x1.data_ptr(), self.stream))
+                add("message_fiber_norm", lambda l=l: _lib.call(
+                    "arreau_fiber_norm", self.x1.data_ptr(), 1, w["fiber_kernel"][l].data_ptr(),
+                    w["fiber_frag"].data_ptr() + l * HIDDEN * 32 * 16, w["conv_bias"][l].data_ptr(),
+                    w["ln_w"][l].data_ptr(), w["ln_b"][l].data_ptr(), self.N, self.y.data_ptr(), 1, None, self.stream))
+            elif fp16:    # one fused launch (the message sums stay in shared memory)
                 add("message_fiber_norm", lambda l=l: _lib.call(
                     "arreau_message_fiber_norm_fused", self.kernels[l].data_ptr(), self.h.data_ptr(),
                     self.row_ptr.data_ptr(), self.src.data_ptr(), w["fiber_frag"].data_ptr() + l * HIDDEN * 32 * 16,
