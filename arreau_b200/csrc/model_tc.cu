@@ -162,20 +162,37 @@ convnext_mlp_tc_kernel(const uint8_t* __restrict__ y_img, const uint8_t* __restr
   const uint32_t tmem = tmem_base_s;
 
   if (warp == 0 && lane == 0) {
-    // ---------------- producer ----------------
+    // ---------------- producer: y tiles and 32 KB weight chunks in the order the MMA warp consumes them.  The first
+    // two GEMM1 slices of a tile are issued under the previous tile's tail (see the MMA warp), so per tile the chunk
+    // order is W2_0 W1_2 W2_1 W1_3 W2_2 [W1_0 of the next tile] W2_3 [W1_1 of the next tile] ----------------
     uint32_t chunk = 0;
-    int it = 0;
-    for (long long tile = blockIdx.x; tile < tiles; tile += gridDim.x, ++it) {
-      const int ab = it & 1;
-      mbar_wait(&bars.a_empty[ab], ((it >> 1) & 1) ^ 1);
+    auto push = [&](int c) {                       // c = chunk index in w_img (W1_0 W1_1 W2_0 W1_2 W2_1 W1_3 W2_2 W2_3)
+      const int ws = chunk % kWStages;
+      mbar_wait(&bars.w_empty[ws], ((chunk / kWStages) & 1) ^ 1);
+      mbar_expect_tx(&bars.w_full[ws], kTileBytes);
+      bulk_g2s(W + ws * kTileBytes, w_img + (size_t)c * kTileBytes, kTileBytes, &bars.w_full[ws]);
+      ++chunk;
+    };
+    auto load_y = [&](long long tile, int ti) {
+      const int ab = ti & 1;
+      mbar_wait(&bars.a_empty[ab], ((ti >> 1) & 1) ^ 1);
       mbar_expect_tx(&bars.a_full[ab], kTileBytes);
       bulk_g2s(A0 + ab * kTileBytes, y_img + (size_t)tile * kTileBytes, kTileBytes, &bars.a_full[ab]);
-      for (int c = 0; c < kChunksPerTile; ++c, ++chunk) {
-        const int ws = chunk % kWStages;
-        mbar_wait(&bars.w_empty[ws], ((chunk / kWStages) & 1) ^ 1);
-        mbar_expect_tx(&bars.w_full[ws], kTileBytes);
-        bulk_g2s(W + ws * kTileBytes, w_img + (size_t)c * kTileBytes, kTileBytes, &bars.w_full[ws]);
+    };
+    if ((long long)blockIdx.x < tiles) {
+      load_y(blockIdx.x, 0);
+      push(0); push(1);
+    }
+    int it = 0;
+    for (long long tile = blockIdx.x; tile < tiles; tile += gridDim.x, ++it) {
+      const bool has_next = tile + gridDim.x < tiles;
+      push(2); push(3); push(4); push(5); push(6);
+      if (has_next) {
+        load_y(tile + gridDim.x, it + 1);
+        push(0);
       }
+      push(7);
+      if (has_next) push(1);
     }
   } else if (warp == 1) {
     // ---------------- MMA issuer: the whole warp runs the loop uniformly, one elected lane issues
@@ -188,52 +205,55 @@ convnext_mlp_tc_kernel(const uint8_t* __restrict__ y_img, const uint8_t* __restr
     int it = 0;
     long long* prof = (blockIdx.x == 0 && el) ? g_tc_prof : nullptr;
     constexpr int prof_role = 0;
-    for (long long tile = blockIdx.x; tile < tiles; tile += gridDim.x, ++it) {
-      const int ab = it & 1;
-      TC_STAMP(0);
-      mbar_wait(&bars.a_full[ab], (it >> 1) & 1);
+    // one 32 KB weight tile (two K slabs): D (+)= X[:, 0:64] . W[0]^T + X[:, 64:128] . W[1]^T, then release it
+    auto mma_tile = [&](uint32_t d, uint32_t x_lo, uint32_t accumulate) {
+      const uint32_t w_lo = w_lo0 + ws * kTileLo;
+      umma_slab_e<4>(d, x_lo, w_lo, kIdesc128, el, accumulate);
+      umma_slab_e<4>(d, x_lo + kSlabLo, w_lo + kSlabLo, kIdesc128, el, 1u);
+      umma_commit_e(wempty + 8 * ws, el);
+      if (++ws == (uint32_t)kWStages) { ws = 0; wpar ^= 1; }
+    };
+    auto gemm1 = [&](int ti, int j) {        // tile number ti of this CTA: D1[j&1] = y_tile . W1_j^T
+      const int b = j & 1, ab = ti & 1;
+      const uint32_t use = (uint32_t)ti * 2 + (j >> 1);
+      if (j == 0) mbar_wait(&bars.a_full[ab], (ti >> 1) & 1);
+      mbar_wait_addr(wfull + 8 * ws, wpar);
+      mbar_wait(&bars.d1_empty[b], (use & 1) ^ 1);
       tc_fence_after();
-      TC_STAMP(1);
-      const uint32_t a_lo = a_lo0 + ab * kTileLo;
-      // one 32 KB weight tile (two K slabs): D (+)= X[:, 0:64] . W[0]^T + X[:, 64:128] . W[1]^T, then release it
-      auto mma_tile = [&](uint32_t d, uint32_t x_lo, uint32_t accumulate) {
-        const uint32_t w_lo = w_lo0 + ws * kTileLo;
-        umma_slab_e<4>(d, x_lo, w_lo, kIdesc128, el, accumulate);
-        umma_slab_e<4>(d, x_lo + kSlabLo, w_lo + kSlabLo, kIdesc128, el, 1u);
+      mma_tile(tmem + b * 128, a_lo0 + ab * kTileLo, 0u);
+      umma_commit_e(smem_u32(&bars.d1_full[b]), el);
+      if (j == 3) umma_commit_e(smem_u32(&bars.a_empty[ab]), el);
+      TC_STAMP(2 + j);
+    };
+    auto gemm2 = [&](int ti, int j) {        // D2 (+)= H[j&1] . W2_j^T
+      const int b = j & 1;
+      const uint32_t use = (uint32_t)ti * 2 + (j >> 1);
+      mbar_wait_addr(wfull + 8 * ws, wpar);
+      mbar_wait(&bars.h_full[b], use & 1);
+      if (j == 0) mbar_wait(&bars.d2_empty, (ti & 1) ^ 1);
+      tc_fence_after();
+      {
+        // the hidden slice is the A operand straight out of tensor memory (64 columns of packed fp16 per buffer)
+        const uint32_t w_lo = w_lo0 + ws * kTileLo, a_t = tmem + kHCol + b * 64;
+        umma_slab_ts_e<4>(tmem + 256, a_t, w_lo, kIdesc128, el, j > 0 ? 1u : 0u);
+        umma_slab_ts_e<4>(tmem + 256, a_t + 32, w_lo + kSlabLo, kIdesc128, el, 1u);
         umma_commit_e(wempty + 8 * ws, el);
         if (++ws == (uint32_t)kWStages) { ws = 0; wpar ^= 1; }
-      };
-      auto gemm1 = [&](int j) {        // D1[j&1] = y_tile . W1_j^T
-        const int b = j & 1;
-        const uint32_t use = (uint32_t)it * 2 + (j >> 1);
-        mbar_wait_addr(wfull + 8 * ws, wpar);
-        mbar_wait(&bars.d1_empty[b], (use & 1) ^ 1);
-        tc_fence_after();
-        mma_tile(tmem + b * 128, a_lo, 0u);
-        umma_commit_e(smem_u32(&bars.d1_full[b]), el);
-        if (j == 3) umma_commit_e(smem_u32(&bars.a_empty[ab]), el);
-        TC_STAMP(2 + j);
-      };
-      auto gemm2 = [&](int j) {        // D2 (+)= H[j&1] . W2_j^T
-        const int b = j & 1;
-        const uint32_t use = (uint32_t)it * 2 + (j >> 1);
-        mbar_wait_addr(wfull + 8 * ws, wpar);
-        mbar_wait(&bars.h_full[b], use & 1);
-        if (j == 0) mbar_wait(&bars.d2_empty, (it & 1) ^ 1);
-        tc_fence_after();
-        {
-          // the hidden slice is the A operand straight out of tensor memory (64 columns of packed fp16 per buffer)
-          const uint32_t w_lo = w_lo0 + ws * kTileLo, a_t = tmem + kHCol + b * 64;
-          umma_slab_ts_e<4>(tmem + 256, a_t, w_lo, kIdesc128, el, j > 0 ? 1u : 0u);
-          umma_slab_ts_e<4>(tmem + 256, a_t + 32, w_lo + kSlabLo, kIdesc128, el, 1u);
-          umma_commit_e(wempty + 8 * ws, el);
-          if (++ws == (uint32_t)kWStages) { ws = 0; wpar ^= 1; }
-        }
-        umma_commit_e(smem_u32(&bars.h_empty[b]), el);
-        if (j == 3) umma_commit_e(smem_u32(&bars.d2_full), el);
-        TC_STAMP(6 + j);
-      };
-      gemm1(0); gemm1(1); gemm2(0); gemm1(2); gemm2(1); gemm1(3); gemm2(2); gemm2(3);
+      }
+      umma_commit_e(smem_u32(&bars.h_empty[b]), el);
+      if (j == 3) umma_commit_e(smem_u32(&bars.d2_full), el);
+      TC_STAMP(6 + j);
+    };
+    // Issue order: the first two GEMM1 slices of tile i+1 go in around the last GEMM2 of tile i, so the epilogue warps
+    // find slice 0 of the next tile ready while that last GEMM2 runs instead of waiting for it
+    if ((long long)blockIdx.x < tiles) { gemm1(0, 0); gemm1(0, 1); }
+    for (long long tile = blockIdx.x; tile < tiles; tile += gridDim.x, ++it) {
+      const bool has_next = tile + gridDim.x < tiles;
+      TC_STAMP(0);
+      gemm2(it, 0); gemm1(it, 2); gemm2(it, 1); gemm1(it, 3); gemm2(it, 2);
+      if (has_next) gemm1(it + 1, 0);
+      gemm2(it, 3);
+      if (has_next) gemm1(it + 1, 1);
     }
   } else if (warp >= kEpiWarp0) {
     // ---------------- epilogue: warp = (lane quarter q, column group cgi of 32 columns) ----------------
@@ -244,36 +264,46 @@ convnext_mlp_tc_kernel(const uint8_t* __restrict__ y_img, const uint8_t* __restr
     const bool is_issuer = threadIdx.x == kEpiWarp0 * 32;
     long long* prof = (blockIdx.x == 0 && is_issuer) ? g_tc_prof : nullptr;
     constexpr int prof_role = 1;
+    // GELU epilogue of hidden slice j of the CTA's tile number `ti`: D1[j & 1] -> + b1 -> GELU -> packed fp16 -> TMEM operand H[j & 1]
+    auto gelu_slice = [&](int ti, int j) {
+      const int b = j & 1;
+      const uint32_t use = (uint32_t)ti * 2 + (j >> 1);
+      mbar_wait(&bars.d1_full[b], use & 1);
+      mbar_wait(&bars.h_empty[b], (use & 1) ^ 1);
+      tc_fence_after();
+      float v[32];
+      tmem_ld32(tmem + lane_addr + b * 128 + cgi * 32, v);
+      uint4 pk[4];
+      gelu_pack32(v, s_b1 + j * 128 + cgi * 32, pk);
+      {
+        // hidden unit k = cgi*32 .. +31 of this 128-slice -> 16 columns of packed pairs in the TMEM operand H[b]
+        const uint32_t* pr = reinterpret_cast<const uint32_t*>(pk);
+        uint32_t regs[16];
+#pragma unroll
+        for (int i = 0; i < 16; ++i) regs[i] = pr[i];
+        tmem_st16(tmem + lane_addr + kHCol + b * 64 + cgi * 16, regs);
+        tmem_wait_st();
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) {
+        mbar_arrive(&bars.d1_empty[b]);
+        mbar_arrive(&bars.h_full[b]);
+      }
+    };
+    // this warp's 32 output channels: lane i keeps b2 and layer_scale of channel cgi*32 + i (broadcast by shuffles in the
+    // final epilogue: with 227 KB of shared memory there is no L1 left, every per-tile reload would be an L2 round trip)
+    const float my_b2 = __ldg(b2 + cgi * 32 + lane), my_ls = __ldg(layer_scale + cgi * 32 + lane);
+    if (blockIdx.x < tiles) gelu_slice(0, 0);
     for (long long tile = blockIdx.x; tile < tiles; tile += gridDim.x, ++it) {
       TC_STAMP(0);
-      for (int j = 0; j < 4; ++j) {
-        const int b = j & 1;
-        const uint32_t use = (uint32_t)it * 2 + (j >> 1);
-        mbar_wait(&bars.d1_full[b], use & 1);
-        mbar_wait(&bars.h_empty[b], (use & 1) ^ 1);
-        tc_fence_after();
+      // slice 0 of this tile was done ahead (below / above): it fills the wait for the previous tile's last GEMM
+      for (int j = 1; j < 4; ++j) {
         TC_STAMP(1 + 2 * j);
-        float v[32];
-        tmem_ld32(tmem + lane_addr + b * 128 + cgi * 32, v);
-        uint4 pk[4];
-        gelu_pack32(v, s_b1 + j * 128 + cgi * 32, pk);
-        {
-          // hidden unit k = cgi*32 .. +31 of this 128-slice -> 16 columns of packed pairs in the TMEM operand H[b]
-          const uint32_t* pr = reinterpret_cast<const uint32_t*>(pk);
-          uint32_t regs[16];
-#pragma unroll
-          for (int i = 0; i < 16; ++i) regs[i] = pr[i];
-          tmem_st16(tmem + lane_addr + kHCol + b * 64 + cgi * 16, regs);
-          tmem_wait_st();
-        }
-        tc_fence_before();
-        __syncwarp();
-        if (lane == 0) {
-          mbar_arrive(&bars.d1_empty[b]);
-          mbar_arrive(&bars.h_full[b]);
-        }
+        gelu_slice(it, j);
         TC_STAMP(2 + 2 * j);
       }
+      if (tile + gridDim.x < tiles) gelu_slice(it + 1, 0);
       TC_STAMP(9);
       mbar_wait(&bars.d2_full, it & 1);
       tc_fence_after();
@@ -300,14 +330,16 @@ convnext_mlp_tc_kernel(const uint8_t* __restrict__ y_img, const uint8_t* __restr
             asm volatile("bar.sync 4, %0;" ::"n"(kEpiThreads + 64) : "memory");
           }
         }
-        const int c0 = cgi * 32;
         float4 d[8];
 #pragma unroll
         for (int i = 0; i < 8; ++i) {
-          const float4 bb = __ldg(reinterpret_cast<const float4*>(b2 + c0 + 4 * i));
-          const float4 ls = __ldg(reinterpret_cast<const float4*>(layer_scale + c0 + 4 * i));
-          d[i] = make_float4(ls.x * (v[4 * i + 0] + bb.x), ls.y * (v[4 * i + 1] + bb.y), ls.z * (v[4 * i + 2] + bb.z),
-                             ls.w * (v[4 * i + 3] + bb.w));
+          float o4[4];
+#pragma unroll
+          for (int k = 0; k < 4; ++k) {
+            const float bb = __shfl_sync(0xffffffffu, my_b2, 4 * i + k), ls = __shfl_sync(0xffffffffu, my_ls, 4 * i + k);
+            o4[k] = ls * (v[4 * i + k] + bb);
+          }
+          d[i] = make_float4(o4[0], o4[1], o4[2], o4[3]);
         }
         // barrel-rotate the 8 chunks by r = lane & 7 so that register slot s holds chunk (s + r) & 7
         const int r = lane & 7;
