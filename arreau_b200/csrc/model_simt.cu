@@ -100,10 +100,14 @@ constexpr int kMaxVec = 8;
 // thread = (atom a of the CTA's 8, 4 channels): s = sum_f x[b,f] W[f, 4 cg..] once per atom, then the 16 orientations
 // only add the vector part (linearity) and store 16 bytes.  `types` (optional): the first Z features are a one-hot of
 // types[b] (diffusion_loss.py:140-150) -> one row lookup instead of Z multiply-adds with zeros.
+// kV > 0: the number of vector channels at compile time (4 in the diffusion model: no predicated-off slots)
+template <int kV>
 __global__ void __launch_bounds__(kEmbedNodes * 32)
 node_embed_kernel(const float* __restrict__ x, const float* __restrict__ vec, const float* __restrict__ w_t,
-                  const float* __restrict__ ori, const int64_t* __restrict__ types, int Z, int N, int F, int V,
+                  const float* __restrict__ ori, const int64_t* __restrict__ types, int Z, int N, int F, int V_rt,
                   float* __restrict__ h, float* __restrict__ pool, const float* __restrict__ pool_wz, int pool_z) {
+  const int V = kV > 0 ? kV : V_rt;
+  constexpr int kVecSlots = kV > 0 ? kV : kMaxVec;
   extern __shared__ float sm[];
   float* xs = sm;                                   // [kEmbedNodes][F]
   float* dots = sm + kEmbedNodes * F;               // [kEmbedNodes][V][kO]
@@ -117,6 +121,21 @@ node_embed_kernel(const float* __restrict__ x, const float* __restrict__ vec, co
     dots[idx] = p[0] * ori[3 * o] + p[1] * ori[3 * o + 1] + p[2] * ori[3 * o + 2];   // to_from_sphere.py:7-8
   }
   __syncthreads();
+  // pooled read-out features by linearity: sum_o w_o h[b,o,:] = (sum_o w_o) s + sum_v (sum_o w_o dots[b,v,o]) W_v for the
+  // four weightings w = 1, ori[:,0..2]; the orientation sums of the dots are formed once per atom here
+  float* dred = dots + kEmbedNodes * V * kO;        // [kEmbedNodes][V][4], then osum[4] = sum_o (1, ori[o][0..2])
+  if (pool) {
+    for (int idx = tid; idx < nb * V * 4 + 4; idx += kEmbedNodes * 32) {
+      const int q = idx & 3, bv = idx >> 2;          // bv = b * V + v, or nb * V for the weight sums themselves
+      float acc = 0.f;
+      for (int o = 0; o < kO; ++o) {
+        const float wgt = q == 0 ? 1.0f : ori[3 * o + q - 1];
+        acc += wgt * (bv < nb * V ? dots[bv * kO + o] : 1.0f);
+      }
+      dred[idx] = acc;
+    }
+    __syncthreads();
+  }
   float4 pq[4];
 #pragma unroll
   for (int q = 0; q < 4; ++q) pq[q] = make_float4(0.f, 0.f, 0.f, 0.f);
@@ -134,9 +153,9 @@ node_embed_kernel(const float* __restrict__ x, const float* __restrict__ vec, co
     const float xv = xr[f];
     s.x = fmaf(xv, w.x, s.x); s.y = fmaf(xv, w.y, s.y); s.z = fmaf(xv, w.z, s.z); s.w = fmaf(xv, w.w, s.w);
   }
-  float4 wv[kMaxVec];
+  float4 wv[kVecSlots];
 #pragma unroll
-  for (int v = 0; v < kMaxVec; ++v)
+  for (int v = 0; v < kVecSlots; ++v)
     wv[v] = v < V ? __ldg(reinterpret_cast<const float4*>(w_t + (size_t)(F + v) * kC + lane * 4)) : make_float4(0.f, 0.f, 0.f, 0.f);
   float* hp = h + (size_t)(b0 + a) * kO * kC + lane * 4;
   // optional orientation-pooled copy for the pooled read-out (part 0 = mean_o h, part 1+d = (1/O) sum_o ori[o][d] h)
@@ -144,20 +163,27 @@ node_embed_kernel(const float* __restrict__ x, const float* __restrict__ vec, co
   for (int o = 0; o < kO; ++o) {
     float4 r = s;
 #pragma unroll
-    for (int v = 0; v < kMaxVec; ++v)
+    for (int v = 0; v < kVecSlots; ++v)
       if (v < V) {
         const float dv = dots[(a * V + v) * kO + o];
         r.x = fmaf(dv, wv[v].x, r.x); r.y = fmaf(dv, wv[v].y, r.y); r.z = fmaf(dv, wv[v].z, r.z); r.w = fmaf(dv, wv[v].w, r.w);
       }
     *reinterpret_cast<float4*>(hp + o * kC) = r;
-    if (pool) {
-      pq[0].x += r.x; pq[0].y += r.y; pq[0].z += r.z; pq[0].w += r.w;
+  }
+  if (pool) {
+    const float* osum = dred + nb * V * 4;
 #pragma unroll
-      for (int d = 0; d < 3; ++d) {
-        const float od = __ldg(ori + 3 * o + d);
-        pq[1 + d].x = fmaf(od, r.x, pq[1 + d].x); pq[1 + d].y = fmaf(od, r.y, pq[1 + d].y);
-        pq[1 + d].z = fmaf(od, r.z, pq[1 + d].z); pq[1 + d].w = fmaf(od, r.w, pq[1 + d].w);
-      }
+    for (int q = 0; q < 4; ++q) {
+      const float ws = osum[q];
+      float4 acc = make_float4(ws * s.x, ws * s.y, ws * s.z, ws * s.w);
+#pragma unroll
+      for (int v = 0; v < kVecSlots; ++v)
+        if (v < V) {
+          const float dv = dred[(a * V + v) * 4 + q];
+          acc.x = fmaf(dv, wv[v].x, acc.x); acc.y = fmaf(dv, wv[v].y, acc.y);
+          acc.z = fmaf(dv, wv[v].z, acc.z); acc.w = fmaf(dv, wv[v].w, acc.w);
+        }
+      pq[q] = acc;
     }
   }
   }
@@ -1344,11 +1370,15 @@ static int node_embed_launch(const float* x, const float* vec, const float* w_em
   if (N == 0) return ARREAU_OK;
   if (!x || !vec || !w_embed_t || !ori || !h) return ARREAU_ERR_NULL;
   if (N < 0 || F <= 0 || V < 0 || V > kMaxVec || (types && (Z <= 0 || Z > F))) return ARREAU_ERR_BAD_SHAPE;
-  size_t smem = sizeof(float) * (size_t)kEmbedNodes * (F + V * kO);
+  size_t smem = sizeof(float) * ((size_t)kEmbedNodes * (F + V * kO) + (size_t)kEmbedNodes * V * 4 + 4);
   if (pool && smem < sizeof(float) * kEmbedNodes * kC) smem = sizeof(float) * kEmbedNodes * kC;
   if (smem > 48 * 1024) return ARREAU_ERR_UNSUPPORTED;
-  node_embed_kernel<<<(N + kEmbedNodes - 1) / kEmbedNodes, kEmbedNodes * 32, smem, (cudaStream_t)stream>>>(
-      x, vec, w_embed_t, ori, types, Z, N, F, V, h, pool, pool_wz, Z);
+  if (V == 4)
+    node_embed_kernel<4><<<(N + kEmbedNodes - 1) / kEmbedNodes, kEmbedNodes * 32, smem, (cudaStream_t)stream>>>(
+        x, vec, w_embed_t, ori, types, Z, N, F, V, h, pool, pool_wz, Z);
+  else
+    node_embed_kernel<0><<<(N + kEmbedNodes - 1) / kEmbedNodes, kEmbedNodes * 32, smem, (cudaStream_t)stream>>>(
+        x, vec, w_embed_t, ori, types, Z, N, F, V, h, pool, pool_wz, Z);
   CUDA_LAUNCH_CHECK();
   return ARREAU_OK;
 }
