@@ -107,7 +107,8 @@ extern "C" int arreau_ponita_forward(const arreau_weights* w, const arreau_works
   cudaStream_t s = (cudaStream_t)stream;
   // fp16 tensor path with a pool buffer: the read-outs run on orientation-pooled features that the embedding and the
   // MLP epilogues keep up to date, so h is never re-read for them (one pooled read-out launch instead of L passes)
-  float* const pool = (fp16 && w->readout_v && w->readout_bias) ? ws->pool : nullptr;
+  // (the pooled kernels are specialised on Z + 6 == 96 columns; other z_tables use the per-layer read-out)
+  float* const pool = (fp16 && w->readout_v && w->readout_bias && Z + 6 == 96) ? ws->pool : nullptr;
   const size_t pool_elems = (size_t)((N + 15) / 16) * 4 * kC * 16;   // one entry: [groups of 16 atoms][4][C][16]
   if (pool)
     ARREAU_TRY(arreau_node_embed_pooled(x, ws->onehot_types, Z, vec, w->w_embed_t, w->ori, N, w->num_scalar, w->num_vec,

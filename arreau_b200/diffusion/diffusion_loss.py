@@ -79,13 +79,24 @@ class DiffusionLoss(torch.nn.Module):
         net = getattr(model, "model", model)          # PONITA_DIFFUSION.model or a bare PonitaFiberBundle
         na = tuple(int(v) for v in torch.as_tensor(num_atoms).reshape(-1).tolist())
         key = (id(net), na, str(device), debug, self.precision)
+        # the engine reads a packed COPY of the weights: a training step / load_state_dict / callibrate in between
+        # bumps the version of the flat parameter buffer, and the copy is rebuilt (sample -> train ->
+        # sample must not sample from the pre-training weights)
+        version = (getattr(getattr(net, "flat", None), "version", 0), getattr(net, "_pack_epoch", 0))
+        stale = getattr(net, "_packed_version", None) != version
         if self._engine is None or self._engine_key != key:
-            packed = net._packed if getattr(net, "_packed", None) is not None and net._packed.device == torch.device(device) \
-                else net.pack(device)
+            packed = net._packed if getattr(net, "_packed", None) is not None and not stale \
+                and net._packed.device == torch.device(device) else net.pack(device)
+            net._packed_version = version
             fw = t_emb_weights.gaussian_fourier_proj_w if hasattr(t_emb_weights, "gaussian_fourier_proj_w") else t_emb_weights
             self._engine = DenoiseEngine(packed, self.tables, fw, na, self.cutoff, self.max_neighbors,
                                          precision=self.precision, debug=debug, device=device)
             self._engine_key = key
+        elif stale or self._engine.w is not net._packed:
+            if stale or net._packed is None:
+                net.pack(device)
+                net._packed_version = version
+            self._engine.w = net._packed
         return self._engine
 
     # -- training step (diffusion_loss.py:95-110,199-274) ---------------------------------------------

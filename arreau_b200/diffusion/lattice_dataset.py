@@ -112,8 +112,20 @@ def collate_crystals(items: Sequence[dict], device=None, pin: bool = True):
 
 def batches(dataset: CrystalDataset, batch_size: int, shuffle: bool = True, seed: int = 0, device=None, rank: int = 0,
             world: int = 1):
-    """Epoch iterator: shuffles, shards the batches over `world` ranks (DDP's DistributedSampler role) and collates."""
-    order = np.random.default_rng(seed).permutation(len(dataset)) if shuffle else np.arange(len(dataset))
-    starts = list(range(0, len(order), batch_size))[rank::world]
-    for s in starts:
-        yield collate_crystals([dataset[int(i)] for i in order[s:s + batch_size]], device=device)
+    """Epoch iterator: shuffles, shards the batches over `world` ranks (DDP's DistributedSampler role) and collates.
+    Every rank gets the SAME number of batches -- each training step carries a gradient all-reduce, so a rank that ran
+    out of batches early would leave its peers in a collective it never joins: like torch's DistributedSampler
+    (drop_last=False) the list of batches is padded to a multiple of `world` by wrapping around to the first ones."""
+    for b in batch_index_lists(len(dataset), batch_size, shuffle, seed, rank, world):
+        yield collate_crystals([dataset[int(i)] for i in b], device=device)
+
+
+def batch_index_lists(n: int, batch_size: int, shuffle: bool = True, seed: int = 0, rank: int = 0, world: int = 1):
+    """Dataset indices of this rank's batches for one epoch (see `batches`); identical length on every rank."""
+    if n == 0:
+        return []
+    order = np.random.default_rng(seed).permutation(n) if shuffle else np.arange(n)
+    all_batches = [order[s:s + batch_size] for s in range(0, n, batch_size)]
+    pad = (-len(all_batches)) % world
+    all_batches += [all_batches[i % len(all_batches)] for i in range(pad)]
+    return all_batches[rank::world]

@@ -78,8 +78,11 @@ class DenoiseEngine:
         self.logits, self.score, self.len0 = f32(N, Z), f32(N, 3), f32(G, 3)
         self.h, self.acc, self.x1 = f32(N, NUM_ORI, HIDDEN), f32(N, Z + 6), f32(N, NUM_ORI, HIDDEN)
         # orientation-pooled features per layer: the fp16 path's read-outs run on these (arreau_readout_pooled)
+        # (arreau_readout_pooled is specialised on Z + 6 == 96 output columns, i.e. the reference's 90 atom states;
+        # any other z_table takes the per-layer read-out arreau_readout_accumulate, Z <= 100)
         self.pool = (f32(LAYERS + 1, (N + 15) // 16, 4, HIDDEN, 16)
-                     if (self.precision == "fp16" and pooled_readout and "readout_v" in weights.t) else None)
+                     if (self.precision == "fp16" and pooled_readout and "readout_v" in weights.t and Z + 6 == 96)
+                     else None)
         if precision == "fp16":     # 128-row UMMA tile images (32 KB each), see arreau_message_fiber_norm
             self.y = torch.zeros(((N * NUM_ORI + 127) // 128) * 128 * HIDDEN, device=dev, dtype=torch.float16)
         else:

@@ -63,6 +63,9 @@ def main():
     ap.add_argument("--precision", default="fp16", choices=["fp32", "fp16"])
     ap.add_argument("--symbols", nargs="*", default=None, help="constant atomic symbols (use_constant_atomic_symbols)")
     ap.add_argument("--out", default=f"{OUT_DIR}/crystals.h5")
+    ap.add_argument("--ori_grid", default=None, help=".npy [16,3] (or .npz with key ori_grid): the orientation grid the "
+                    "model was trained with; a reference checkpoint does not carry it (quirk B2)")
+    ap.add_argument("--no_strict", action="store_true", help="tolerate model tensors missing from the checkpoint")
     args = ap.parse_args()
     from .lightning_wrappers.diffusion import PONITA_DIFFUSION
     local = int(os.environ.get("LOCAL_RANK", "0"))
@@ -70,7 +73,12 @@ def main():
     dev = torch.device("cuda", local)
     if int(os.environ.get("WORLD_SIZE", "1")) > 1:
         dist.init_process_group("nccl", device_id=dev)
-    model = PONITA_DIFFUSION.load_from_checkpoint(args.model_path, strict=False, precision=args.precision)
+    grid = None
+    if args.ori_grid:
+        g = np.load(args.ori_grid)
+        grid = g["ori_grid"] if hasattr(g, "files") else g
+    model = PONITA_DIFFUSION.load_from_checkpoint(args.model_path, ori_grid=grid, strict=not args.no_strict,
+                                                  precision=args.precision)
     res = generate_n_crystals(model, args.num_crystals, args.num_atoms, args.symbols, args.batch, device=dev,
                               out_path=args.out)
     if not dist.is_initialized() or dist.get_rank() == 0:

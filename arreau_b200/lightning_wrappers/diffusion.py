@@ -79,13 +79,17 @@ class PONITA_DIFFUSION(nn.Module):
 
     # ---- checkpoint ingestion --------------------------------------------------------------------------
     @classmethod
-    def load_from_checkpoint(cls, path, ori_grid=None, strict: bool = False, map_location="cpu", **kw):
+    def load_from_checkpoint(cls, path, ori_grid=None, strict: bool = True, map_location="cpu", **kw):
         """A Lightning .ckpt of the reference: {"state_dict": {model.*, t_emb.*, z_table_zs, diffusion_loss.* ...},
         "hyper_parameters": {"args": Namespace, "z_table": AtomicNumberTable}}.  The pickled z_table refers to the
         reference's module path; it is resolved to this package's class.  The orientation grid is NOT in a reference
         checkpoint (quirk B2: it is rebuilt randomly at construction): pass the grid the model was trained with via
         `ori_grid=` (a checkpoint written by `save_checkpoint` below carries it as `ori_grid`); without one the
-        deterministic Fibonacci grid is used and a warning is raised."""
+        deterministic Fibonacci grid is used and a warning is raised.  `strict` (default True): every `model.*` /
+        `t_emb.*` tensor of this module must be in the checkpoint with the same shape, otherwise KeyError -- the
+        reference passes strict=False to Lightning only to tolerate ITS extra keys (metrics, zero-width edge
+        read-outs), which are ignored here in either mode; a checkpoint that does not fit never samples from
+        random weights silently."""
         ckpt = load_checkpoint_file(path, map_location)
         hp = ckpt.get("hyper_parameters", {})
         args, z_table = hp["args"], hp["z_table"]
@@ -102,8 +106,15 @@ class PONITA_DIFFUSION(nn.Module):
         picked = {k: v for k, v in sd.items() if k in own and tuple(v.shape) == tuple(own[k].shape)}
         missing = [k for k in own if k not in picked and own[k].numel() > 0 and not k.endswith("callibrated")
                    and not k.startswith("diffusion_loss.")]
-        if strict and missing:
-            raise KeyError(f"checkpoint lacks {missing}")
+        if missing:
+            bad_shape = {k: (tuple(sd[k].shape), tuple(own[k].shape)) for k in missing if k in sd}
+            msg = f"checkpoint {path} lacks {len(missing)} tensors of the model: {missing[:8]}{' ...' if len(missing) > 8 else ''}"
+            if bad_shape:
+                msg += f"; shape mismatches (checkpoint, model): {bad_shape}"
+            if strict:
+                raise KeyError(msg)
+            import warnings
+            warnings.warn(msg + " -- they keep their random initialisation")
         m.load_state_dict(picked, strict=False)
         m.model._packed = None
         return m

@@ -17,7 +17,6 @@ import torch
 import torch.distributed as dist
 
 from .diffusion.lattice_dataset import CrystalDataset, batches
-from .diffusion.lattice_helpers import matrix_to_params
 from .distributed import allreduce_gradients, broadcast_parameters, reduce_loss_metric
 from .lightning_wrappers.diffusion import PONITA_DIFFUSION
 
@@ -47,17 +46,21 @@ def fit(model: PONITA_DIFFUSION, dataset: CrystalDataset, epochs: int, batch_siz
         total_loss = torch.zeros((), dtype=torch.float64, device=device)
         total_samples = torch.zeros((), dtype=torch.float64, device=device)
         for batch in batches(dataset, batch_size, shuffle=True, seed=seed + epoch, device=device, rank=rank, world=world):
+            loss = model.training_step(batch)          # the step's kernels have filled flat.grad
             if calibrate:
-                # the reference's first train-mode forward re-initialises kernel / fiber_kernel scales on its own
-                # batch (noised at a random t); here: the clean batch at the middle of the schedule
+                # ponita/nn/conv.py:122-123: the reference's FIRST train-mode forward -- the noised batch of the first
+                # training step at its random timesteps -- re-initialises the kernel / fiber_kernel scales from its own
+                # activations AFTER using the old weights, and that same forward's loss is then back-propagated: the
+                # first gradient belongs to the un-rescaled weights and is applied to the rescaled ones.  Same here:
+                # statistics from the step that has just run, rescale, then the optimizer step.  (Under DDP every
+                # reference rank rescales from its own shard and the replicas silently diverge; here rank 0's scales
+                # are broadcast -- the one deliberate deviation.)
                 te = model.diffusion_loss.train_engine_for(model.model, model.t_emb, batch.num_atoms, device)
-                lengths, angles = matrix_to_params(batch.L0.view(-1, 3, 3))
-                te.calibrate(batch.X0, batch.A0, lengths, angles, model.diffusion_loss.T // 2)
+                te.calibrate_from_last_forward()
                 broadcast_parameters(flat.data)
                 for layer in model.model.interaction_layers:
                     layer.conv.callibrated.fill_(True)
                 calibrate = False
-            loss = model.training_step(batch)          # the step's kernels have filled flat.grad
             allreduce_gradients(flat.grad)
             opt.step()
             total_loss += loss.detach().double()

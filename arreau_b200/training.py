@@ -36,6 +36,9 @@ class FlatParams:
         self.total = int(self.layout.total)
         self.data = torch.zeros(self.total, dtype=torch.float32, device=self.device)
         self.grad = torch.zeros(self.total, dtype=torch.float32, device=self.device)
+        # bumped by everything that changes `data` in place (optimizer step, load_state_dict, callibrate), so that
+        # cached kernel-layout copies of the weights (PonitaWeights of a sampling engine) know they are stale
+        self.version = 0
         R, FV, L, Cc, D, W = num_states + 4, num_scalar + num_vec, LAYERS, HIDDEN, BASIS, WIDEN * HIDDEN
         lay = self.layout
         self.specs = {   # name -> (offset, shape)
@@ -80,6 +83,7 @@ class FlatParams:
         for k, v in self.views().items():
             v.copy_(torch.as_tensor(np.asarray(sd[k].detach().cpu()) if isinstance(sd[k], torch.Tensor) else np.asarray(sd[k]),
                                     dtype=torch.float32).reshape(v.shape))
+        self.version += 1
 
     def state_dict(self) -> Dict[str, torch.Tensor]:
         return {k: v.clone() for k, v in self.views().items()}
@@ -114,6 +118,7 @@ class FusedAdam:
         p = self.p
         s = torch.cuda.current_stream(p.device).cuda_stream
         self.step_count += 1
+        p.version += 1
         _lib.call("arreau_moments", p.grad.data_ptr(), None, p.total, self.scratch.data_ptr(), self.moments.data_ptr(), s)
         _lib.call("arreau_adam_step", p.data.data_ptr(), p.grad.data_ptr(), self.exp_avg.data_ptr(),
                   self.exp_avg_sq.data_ptr(), self.mask.data_ptr(), p.total, self.lr, self.betas[0], self.betas[1],
@@ -247,16 +252,25 @@ class TrainEngine:
         return float(np.sqrt(max(q - s * s / n, 0.0) / (n - 1)))      # torch.std: unbiased
 
     def calibrate(self, frac, types, lengths, angles, t) -> None:
-        """The one-time re-initialisation of the reference's first train-mode forward: per layer,
-        kernel.weight *= std(x) / std(x1) and fiber_kernel.weight *= std(x1) / std(x2) with that forward's own
-        tensors (x2 before the bias).  The statistics are reduced on the device (arreau_moments)."""
+        """The one-time re-initialisation of the reference's first train-mode forward on a GIVEN state: runs
+        predict_scores at timestep(s) t, then `calibrate_from_last_forward`."""
         e = self.eng
         e.set_state(frac, types, lengths, angles)
         e.predict_scores(t)
+        self.calibrate_from_last_forward()
+
+    def calibrate_from_last_forward(self) -> None:
+        """conv.py:122-123,140-146 with the tensors of the forward that has just run (`predict` of a training step or
+        `calibrate`): per layer kernel.weight *= std(x) / std(x1) and fiber_kernel.weight *= std(x1) / std(x2), x2
+        before the bias, all three taken from that ONE forward with the weights as they were (the reference rescales
+        a layer's weights after the layer has produced its output, so later layers see un-rescaled activations).
+        The statistics are reduced on the device (arreau_moments)."""
+        e = self.eng
         v = self.p.views()
         for l in range(LAYERS):
             s_in, s_1 = self._std(e.h_debug[l]), self._std(e.x1_debug[l])
             s_2 = self._std(e.x2_debug[l], v[f"interaction_layers.{l}.conv.bias"])
             v[f"interaction_layers.{l}.conv.kernel.weight"].mul_(s_in / s_1)
             v[f"interaction_layers.{l}.conv.fiber_kernel.weight"].mul_(s_1 / s_2)
+        self.p.version += 1
         self.repack()

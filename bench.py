@@ -7,9 +7,12 @@ trajectory, and ms per denoise step).
 A "step" is one denoise step (graph + Ponita forward + VE/VP/D3PM update) of one batch of synthetic crystals;
 the N=1 workload is BASELINE.json configs[1] (C2: 1024 crystals x 40 atoms, 5 A cutoff, max_neighbors 8 as in the
 reference's Makefile:7).  value = crystals / (999 * step time): the whole-job trajectory throughput with the state
-resident in HBM.  e2e = the same through the public engine API with the step's state and noise copied from pinned
-host memory and the result read back, every step.  N>1: one process per GPU (torchrun), each rank owns its own
-batch of independent crystals (weak scaling, no data-path collective), time = max over ranks.
+resident in HBM, from --steps timed steps.  e2e = ONE WHOLE 999-step trajectory of the same batch through the public
+API a user calls (PONITA_DIFFUSION.sample, the mirror of lightning_wrappers/diffusion.py:220-253: host RNG draws of
+the initial state -> upload -> 999 x arreau_denoise_step -> SampleResult as numpy arrays on the host), everything
+inside the clock; e2e.step_api is the older per-step measurement (state + noise uploaded from pinned host memory and
+the result read back EVERY step).  N>1: one process per GPU (torchrun), each rank owns its own batch of independent
+crystals (weak scaling, no data-path collective), time = max over ranks.
 
 --impl reference times the reference's algorithm on the host cores (the oracle port; the reference itself is
 Python that needs /root/reference and cannot travel) on a bounded sample of the same workload.
@@ -160,6 +163,23 @@ def oracle_step_time(G_s: int, n: int, steps: int, warmup: int, cap: int, thread
         torch.set_default_dtype(prev)
 
 
+def build_public_model(dev, atoms_per_crystal: int, precision: str):
+    """The reference-facing module (arreau_b200.lightning_wrappers.diffusion.PONITA_DIFFUSION, constructor arguments of
+    main_diffusion.py:88-120 / Makefile:7) carrying the benchmark weights."""
+    import torch
+    from arreau_b200.lightning_wrappers.diffusion import PONITA_DIFFUSION
+    from arreau_b200.tools.atomic_number_table import AtomicNumberTable
+    a = argparse.Namespace(dataset="synthetic", lr=3e-4, weight_decay=0.0, epochs=1, warmup=0, layer_scale=1e-6,
+                           train_augm=False, hidden_dim=C, layers=L, radius=RADIUS, num_ori=O, basis_dim=D, degree=3,
+                           widening_factor=4, multiple_readouts=True, num_timesteps=T_STEPS, max_neighbors=8)
+    sd, ori, fw = load_weights(atoms_per_crystal)
+    m = PONITA_DIFFUSION(a, AtomicNumberTable(list(range(1, Z)) + [2001]), ori_grid=ori, precision=precision)
+    m.model.load_state_dict({k: torch.as_tensor(v) for k, v in sd.items()})
+    with torch.no_grad():
+        m.t_emb.gaussian_fourier_proj_w.copy_(torch.as_tensor(fw))
+    return m.to(dev)
+
+
 def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
@@ -172,7 +192,9 @@ def run_reference(args):
     line = {"impl": "reference", "metric": "crystals_per_sec_full_trajectory", "value": value, "unit": "crystals/s",
             "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": t_step * 1e3,
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-            "config": config_dict(args),
+            "config": dict(config_dict(args), cpu_sample=f"{G_s} of the {args.crystals} crystals per step (the reference "
+                           f"costs ~1.4 s per step at 64 x 40 atoms; crystals are independent, cost is linear in them)",
+                           cpu_sample_crystals=G_s),
             "cpu_baseline": {"value": value, "unit": "crystals/s", "cores": cores, "kind": "port", "sample": sample},
             "e2e": {"value": value, "unit": "crystals/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "note": "ms_per_step is for the bounded sample; crystals/s = sample crystals / (999 * step time)"}
@@ -293,8 +315,9 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--precision", default=os.environ.get("ARREAU_PRECISION", "fp16"), choices=["fp32", "fp16"],
-                    help="fp16: tcgen05 tensor-core path (fp16 operands, fp32 accumulate; tolerance 1e-2 stated in "
-                         "tests/test_gpu_tc.py, measured <= 2e-3); fp32: FFMA2 SIMT path (<= 1e-4, measured 2e-6)")
+                    help="fp16: tcgen05 tensor-core path (fp16 operands, fp32 accumulate; stated tolerance 4e-3 of "
+                         "max|ref| -- tests/conftest.py TOL_FP16_MODEL, measured 2e-4..2e-3); fp32: FFMA2 SIMT path "
+                         "(<= 1e-4, measured 2e-6)")
     ap.add_argument("--crystals", type=int, default=1024)
     ap.add_argument("--atoms", type=int, default=40)
     ap.add_argument("--cap", type=int, default=8)
@@ -308,6 +331,7 @@ def main():
                     help="time ONE WHOLE trajectory (every denoise step from the sampler init at t=T-1 down to t=1, "
                          "state re-initialised after the warm-up) instead of --steps steps; value = crystals / that time")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-e2e-trajectory", action="store_true", help="skip the whole-trajectory e2e leg (~7 s at C2)")
     ap.add_argument("--no-other-precision", action="store_true")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 0)
@@ -433,7 +457,46 @@ def main():
         tmax = torch.tensor([ems], device=dev)
         dist.all_reduce(tmax, op=dist.ReduceOp.MAX)
         ems = float(tmax.item())
-    e2e_value = world * G / ((T_STEPS - 1) * (ems / e2e_steps) * 1e-3)
+    e2e_step_value = world * G / ((T_STEPS - 1) * (ems / e2e_steps) * 1e-3)
+
+    # ---- end to end, the call a user makes: ONE whole trajectory through PONITA_DIFFUSION.sample -------
+    # (host RNG draws + upload of the initial state, 999 denoise steps with in-kernel Philox noise -- the default of
+    # generate_n_crystals --, result back on the host as the reference's SampleResult; capped graphs only: the
+    # reference sampler's ~1 A initial cells are all images without the cap)
+    e2e_traj = None
+    if args.cap > 0 and args.state == "sampler" and not args.no_e2e_trajectory:
+        model = build_public_model(dev, n, args.precision)
+        model.diffusion_loss.max_neighbors, model.diffusion_loss.cutoff = args.cap, args.radius
+        dl = model.diffusion_loss
+        model.model._packed = eng.w                       # same packed weights; the engine below is this topology's
+        model.model._packed_version = (0, 0)
+        dl._engine, dl._engine_key = eng, (id(model.model), tuple([n] * G), str(dev), False, args.precision)
+        np.random.seed(17 + rank)
+        torch.manual_seed(17 + rank)
+        barrier()
+        clocks2 = ClockSampler(local)
+        time.sleep(0.25)
+        clocks2.begin()
+        tw0 = time.perf_counter()
+        t0e, t1e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        t0e.record()
+        res = model.sample(num_atoms_per_sample=n, num_samples_in_batch=G, device=dev, device_noise=True, seed=31 + rank)
+        t1e.record()
+        torch.cuda.synchronize(dev)
+        wall = time.perf_counter() - tw0
+        clocks2.end()
+        tsec = max(t0e.elapsed_time(t1e) * 1e-3, wall)    # the host work before the first launch counts too
+        if world > 1:
+            tmax = torch.tensor([tsec], device=dev, dtype=torch.float64)
+            dist.all_reduce(tmax, op=dist.ReduceOp.MAX)
+            tsec = float(tmax.item())
+        assert res.frac_x.shape == (N, 3) and np.isfinite(res.frac_x).all() and np.isfinite(res.lattice).all()
+        up = N * 3 * 8 + N * 8 + G * 3 * 8 * 2 + G * 6 * 8                 # frac, types, lengths, angles, angle factors
+        down = N * 3 * 8 + N * 8 + G * 9 * 8                               # frac, types, lattice
+        e2e_traj = {"value": world * G / tsec, "seconds": tsec, "steps": T_STEPS - 1, "ms_per_step": tsec * 1e3 / (T_STEPS - 1),
+                    "h2d_bytes": up, "d2h_bytes": down, "clocks": clocks2.summary(),
+                    "final_edges_per_atom": eng.num_edges() / N,
+                    "api": "PONITA_DIFFUSION.sample(num_atoms_per_sample, num_samples_in_batch, device_noise=True)"}
 
     # ---- final gather of a trajectory's result (the only collective of the sampling path) -------------
     gather_ms = None
@@ -490,21 +553,32 @@ def main():
         # measured DRAM bytes per launch (dram__bytes_read.sum + dram__bytes_write.sum of one `ncu --set full`
         # capture of this workload, profiles/r1_traffic.json); only valid for the configuration it was captured on
         traffic = None
-        tpath = os.path.join(ROOT, "profiles", "r1_traffic.json")
-        if os.path.exists(tpath):
+        import glob
+        for tpath in sorted(glob.glob(os.path.join(ROOT, "profiles", "r*_traffic.json")), reverse=True):   # newest round first
             tj = json.load(open(tpath))
             if tj.get("workload") == [args.crystals, args.atoms, args.cap, args.radius, args.precision]:
                 traffic = tj["bytes_per_launch"].get(dom)
                 for kname, kv in kernels.items():
                     kv["traffic"] = tj["bytes_per_launch"].get(kname)
+                break
         roof = dict(kernels[dom]); roof.update({"kernel": dom, "traffic": traffic, "peak_source": peak_src,
                                                 "share_of_step": br[dom]["ms_per_step"] / sum(v["ms_per_step"] for v in br.values())})
         line = {"metric": "crystals_per_sec_full_trajectory", "value": value, "unit": "crystals/s", "n_gpus": world,
                 "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": ms_per_step, "higher_is_better": True,
                 "scaling": "weak", "vs_baseline": None, "dtype": "f32" if args.precision == "fp32" else "f16",
                 "data": "synthetic", "config": config_dict(args), "clocks": clk,
-                "e2e": {"value": e2e_value, "unit": "crystals/s", "ms_per_step": ems / e2e_steps,
-                        "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h},
+                "e2e": ({"value": e2e_traj["value"], "unit": "crystals/s", "ms_per_step": e2e_traj["ms_per_step"],
+                         "h2d_bytes_per_step": e2e_traj["h2d_bytes"] / (T_STEPS - 1),
+                         "d2h_bytes_per_step": e2e_traj["d2h_bytes"] / (T_STEPS - 1), "trajectory": e2e_traj,
+                         "what": "one whole 999-step trajectory through PONITA_DIFFUSION.sample: host draws + upload of the "
+                                 "initial state, every step, SampleResult back on the host; bytes are per trajectory / 999",
+                         "step_api": {"value": e2e_step_value, "ms_per_step": ems / e2e_steps, "h2d_bytes_per_step": h2d,
+                                      "d2h_bytes_per_step": d2h,
+                                      "what": "engine API, state + noise from pinned host memory and result read back EVERY step"}}
+                        if e2e_traj is not None else
+                        {"value": e2e_step_value, "unit": "crystals/s", "ms_per_step": ems / e2e_steps,
+                         "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
+                         "what": "engine API, state + noise from pinned host memory and result read back EVERY step"}),
                 "gpu_launches": int(launches), "roofline": roof, "kernels": kernels,
                 "breakdown_ms_per_step": {k: round(v["ms_per_step"], 4) for k, v in br.items()},
                 "edges_per_atom": {"first_timed_step": epa_first, "last_timed_step": epa_last, "breakdown": E / N},

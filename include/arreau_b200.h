@@ -54,6 +54,9 @@ int64_t arreau_launch_count(void);
 /* Pass 1.  pos[N,3] f64 cartesian, lattice[G,3,3] f64 rows a,b,c, atom_offset[G+1] i32 (prefix
  * sum of num_atoms), crystal_of_atom[N] i32.  radius_sq = radius*radius evaluated by the caller
  * in double (helpers:432).  cap = max_num_neighbors_threshold (<= 0 disables, helpers:469-472).
+ * LIMIT: cap <= 224 (the per-receiver selection buffer holds 256 candidates: cap + one 32-lane
+ * batch); a larger positive cap returns ARREAU_ERR_UNSUPPORTED from both passes -- run uncapped
+ * (cap <= 0) instead, which has no limit.  The reference's own configurations use 8 (Makefile:7).
  * Outputs: raw_count[N] i32 (bits 0..23: candidates with 1e-4 < d2 <= r2; bits 24..30: a scratch
  * hint for pass 2 -- the log-spaced distance bin that is known to contain the cap nearest; mask
  * with 0xFFFFFF to read the count), deg[N] i32 (= min(raw, cap) when cap > 0),

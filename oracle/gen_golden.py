@@ -32,12 +32,13 @@ T64 = lambda a: torch.as_tensor(np.asarray(a), dtype=torch.float64)  # noqa: E73
 I64 = lambda a: torch.as_tensor(np.asarray(a), dtype=torch.long)  # noqa: E731
 
 
-def build_reference_model(ref, T, radius, max_neighbors, seed=0):
+def build_reference_model(ref, T, radius, max_neighbors, seed=0, zs=None):
     """seed 0, construct, one train-mode forward (LazyLinear + callibrate, quirk B8),
     eval, re-draw layer_scale / conv.bias / LayerNorm affine (quirk B6), round to fp32."""
     torch.manual_seed(seed)
     args = ref_loader.default_args(T=T, radius=radius, max_neighbors=max_neighbors)
-    z_table = ref.AtomicNumberTable(list(range(1, Z)) + [2001])
+    z_table = ref.AtomicNumberTable((list(range(1, globals()["Z"])) if zs is None else list(zs)) + [2001])
+    Z = len(z_table)
     with torch.enable_grad():  # the orientation grid is built by 100 SGD steps (rotation.py:994-1006)
         m = ref.wrapper.PONITA_DIFFUSION(args, z_table)
     # calibration forward on realistic crystals
@@ -47,7 +48,7 @@ def build_reference_model(ref, T, radius, max_neighbors, seed=0):
                       batch=torch.repeat_interleave(torch.arange(cr.num_crystals), I64(cr.num_atoms)))
     t = torch.full((cr.total_atoms,), min(T - 1, 500), dtype=torch.long)
     with torch.no_grad():
-        m.diffusion_loss.predict_scores(T64(cr.frac), torch.nn.functional.one_hot(I64(cr.types), Z), t,
+        m.diffusion_loss.predict_scores(T64(cr.frac), torch.nn.functional.one_hot(I64(cr.types) % (Z - 1), Z), t,
                                         I64(cr.num_atoms), T64(cr.lengths), T64(cr.angles), m, batch, m.t_emb)
     m.eval()
     g = torch.Generator().manual_seed(seed + 1)
@@ -487,15 +488,135 @@ def gen_training(ref):
     print("train_c5small.npz done")
 
 
+@torch.no_grad()
+def gen_long_rows(ref):
+    """Live-reference goldens for receivers with MORE than 8 incoming edges: the message pass
+    beyond the first 8-edge chunk (cap 12), the uncapped C1 regime at r = 5 (E/N ~ 30) and a 2 x 200-atom supercell
+    batch at r = 7 uncapped (E/N ~ 75, the "dense image neighbour lists" of BASELINE configs[2]).  Same weights as
+    weights_seed0.npz (the window only depends on the radius).  Outputs come from the LIVE reference model on the
+    reference's own graph; per-layer intermediates from the restatement, pinned to the live outputs at 1e-12."""
+    T = 1000
+    w = np.load(os.path.join(GOLD, "weights_seed0.npz"))
+    sd = {k: torch.as_tensor(w[k], dtype=torch.float64) for k in w.files if k not in ("ori_grid", "fourier_w")}
+    ori, fw = T64(w["ori_grid"]), T64(w["fourier_w"])
+    tabs = R.DiffusionTables.build(T, Z)
+    out = {}
+    cases = [("c1_cap12", make_crystals(8, 6, 20, seed=21), 5.0, 12, 500),
+             ("c1_uncapped", make_crystals(8, 6, 20, seed=22), 5.0, 0, 500),
+             ("c3_uncapped", make_crystals(2, 200, None, seed=23), 7.0, 0, 300)]
+    for name, cr, radius, cap, timestep in cases:
+        m = build_reference_model(ref, T, radius, cap, seed=0)
+        load_state(m, sd)
+        m.model.transform.transforms[0].ori_grid_s2 = ori.clone()
+        m.t_emb.gaussian_fourier_proj_w.copy_(fw)
+        m.eval()
+        W = oracle_weights(sd, ori, radius)
+        dl = m.diffusion_loss
+        na = I64(cr.num_atoms)
+        G, N = cr.num_crystals, cr.total_atoms
+        lat0 = R.lattice_from_params(T64(cr.lengths), T64(cr.angles))
+        torch.manual_seed(3000 + len(out))
+        t_feat = torch.full((N, 1), timestep)
+        frac_t, _, _ = dl.pos_diffusion(T64(cr.frac), t_feat, lat0, na)       # the reference's own forward noising
+        types_t = dl.d3pm.get_xt(I64(cr.types), t_feat.squeeze())
+        lengths_t, _ = dl.lattice_diffusion(T64(cr.lengths), torch.full((G, 1), timestep))
+        angles = T64(cr.angles)
+        t = torch.full((N,), timestep)
+        batch_obj = ref.Batch(num_atoms=na, batch=torch.repeat_interleave(torch.arange(G), na))
+        with ref_loader.stable_sort():
+            r_score, r_logits, r_len0 = dl.predict_scores(frac_t, torch.nn.functional.one_hot(types_t, Z), t, na,
+                                                          lengths_t, angles, m, batch_obj, m.t_emb)
+        score, logits, len0, graph = R.predict_scores(W, tabs, fw, frac_t, torch.nn.functional.one_hot(types_t, Z), t,
+                                                      na, lengths_t, angles, radius, cap, return_graph=True)
+        for a, b in ((r_score, score), (r_logits, logits), (r_len0, len0)):
+            assert (a - b).abs().max().item() / a.abs().max().item() < 1e-11, name
+        ei, _, _, dist, direction = graph
+        deg = torch.bincount(ei[1], minlength=N)
+        lat = R.lattice_from_params(lengths_t, angles)
+        rep = lambda a: torch.repeat_interleave(a, na, dim=0)  # noqa: E731
+        x = torch.cat([torch.nn.functional.one_hot(types_t, Z), R.fourier_time_embedding(tabs.vp_betas[t].view(-1, 1), fw),
+                       rep(na).unsqueeze(-1), rep(lengths_t), rep(angles), rep((lengths_t / na.unsqueeze(-1)).abs())], dim=1)
+        vec = torch.cat([frac_t.unsqueeze(1), rep(lat)], dim=1)
+        bvec = torch.repeat_interleave(torch.arange(G), na)
+        o_logits, o_vec, o_len0, inter = R.ponita_forward(W, x, vec, ei, dist, direction, lat, bvec, G,
+                                                          out_dims=(Z, 1, 0, 3), return_intermediates=True)
+        assert (o_logits - r_logits).abs().max().item() / r_logits.abs().max().item() < 1e-11
+        # atoms whose intermediates are stored: the first 4, the last 4, and the 4 longest rows
+        sel = torch.unique(torch.cat([torch.arange(4), torch.arange(N - 4, N), torch.argsort(deg, descending=True)[:4]]))
+        p = name + "/"
+        out.update({p + "num_atoms": cr.num_atoms, p + "radius": np.float64(radius), p + "cap": np.int64(cap),
+                    p + "timestep": np.int64(timestep), p + "frac": frac_t.numpy(), p + "types": types_t.numpy(),
+                    p + "lengths": lengths_t.numpy(), p + "angles": angles.numpy(),
+                    p + "src": ei[0].numpy().astype(np.int32), p + "dst": ei[1].numpy().astype(np.int32),
+                    p + "score": r_score.numpy(), p + "logits": r_logits.numpy(), p + "len0": r_len0.numpy(),
+                    p + "sel": sel.numpy()})
+        for l in range(5):
+            out[p + f"x1_{l}"] = inter[f"x1_{l}"][sel].numpy().astype(np.float32)
+            out[p + f"x2_{l}"] = inter[f"x2_{l}"][sel].numpy().astype(np.float32)
+            out[p + f"h_{l}"] = inter[f"h_{l}"][sel].numpy().astype(np.float32)
+        print(f"  long rows {name}: N={N} E={ei.shape[1]} E/N={ei.shape[1] / N:.1f} max row {int(deg.max())} "
+              f"|score|max={r_score.abs().max():.3e}")
+    np.savez_compressed(os.path.join(GOLD, "forward_longrows.npz"), **out)
+    print("forward_longrows.npz done")
+
+
+def gen_checkpoint(ref):
+    """A Lightning-shaped .ckpt pickled from the LIVE reference classes: the state_dict of the
+    reference's own PONITA_DIFFUSION (fp32, the dtype a Lightning training run saves; `model.*`, `t_emb.*`,
+    `z_table_zs` and the `diffusion_loss.*` schedule buffers), hyper_parameters = {args: Namespace, z_table: the
+    reference's AtomicNumberTable instance} as save_hyperparameters() records them
+    (lightning_wrappers/diffusion.py:34).  The orientation grid is NOT inside (quirk B2): it travels in the
+    companion reference_model_io.npz together with one predict_scores input/output pair of the live model.
+    To keep the fixture small the model is a 20-element one (Z = 21 states: also the Z != 90 case of the fp16
+    read-out) with T = 100 (the pickled D3PM tables are T x Z x Z)."""
+    T, radius, cap = 100, 5.0, 8
+    zs = [1, 3, 6, 7, 8, 9, 11, 12, 13, 14, 15, 16, 17, 19, 20, 22, 26, 29, 30, 38]
+    m = build_reference_model(ref, T, radius, cap, seed=5, zs=zs)
+    Zc = len(zs) + 1
+    args = ref_loader.default_args(T=T, radius=radius, max_neighbors=cap)
+    z_table = ref.AtomicNumberTable(zs + [2001])
+    state = {k: (v.detach().float() if v.is_floating_point() else v.detach().clone()) for k, v in m.state_dict().items()}
+    ckpt = {"epoch": 0, "global_step": 0, "pytorch-lightning_version": "2.2.1", "state_dict": state, "loops": {},
+            "callbacks": {}, "optimizer_states": [], "lr_schedulers": [], "hparams_name": "kwargs",
+            "hyper_parameters": {"args": args, "z_table": z_table}}
+    path = os.path.join(GOLD, "reference_model.ckpt")
+    torch.save(ckpt, path)
+    print("reference_model.ckpt", os.path.getsize(path), "bytes,", len(state), "state_dict entries,",
+          type(z_table).__module__ + "." + type(z_table).__name__)
+    # one predict_scores call of the live model (weights are fp32-representable: build_reference_model rounds them)
+    cr = make_crystals(6, 3, 14, seed=51)
+    na = I64(cr.num_atoms)
+    G, N = cr.num_crystals, cr.total_atoms
+    types = I64(cr.types) % Zc
+    timestep = 40
+    t = torch.full((N,), timestep)
+    batch_obj = ref.Batch(num_atoms=na, batch=torch.repeat_interleave(torch.arange(G), na))
+    with torch.no_grad(), ref_loader.stable_sort():
+        score, logits, len0 = m.diffusion_loss.predict_scores(T64(cr.frac), torch.nn.functional.one_hot(types, Zc), t, na,
+                                                              T64(cr.lengths), T64(cr.angles), m, batch_obj, m.t_emb)
+    np.savez_compressed(os.path.join(GOLD, "reference_model_io.npz"),
+                        ori_grid=m.model.transform.transforms[0].ori_grid_s2.numpy().astype(np.float32),
+                        num_atoms=cr.num_atoms, frac=cr.frac, types=types.numpy(), lengths=cr.lengths, angles=cr.angles,
+                        timestep=np.int64(timestep), score=score.numpy(), logits=logits.numpy(), len0=len0.numpy(),
+                        zs=np.asarray(zs + [2001]))
+    print("reference_model_io.npz: N =", N, "|score|max", float(score.abs().max()))
+
+
 def main():
     os.makedirs(GOLD, exist_ok=True)
     ref = ref_loader.import_reference()
     if "--training-only" in sys.argv:
         return gen_training(ref)
+    if "--long-rows-only" in sys.argv:
+        return gen_long_rows(ref)
+    if "--checkpoint-only" in sys.argv:
+        return gen_checkpoint(ref)
     gen_kats(ref)
     gen_graph_cases(ref)
     gen_model_goldens(ref)
     gen_training(ref)
+    gen_long_rows(ref)
+    gen_checkpoint(ref)
 
 
 if __name__ == "__main__":

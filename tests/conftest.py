@@ -11,6 +11,16 @@ if ROOT not in sys.path:
 GOLD = os.path.join(ROOT, "tests", "golden")
 
 
+# ONE stated tolerance for the fp16 tensor-core path (BASELINE.json north_star: "any TF32/bf16 path given its own
+# stated tolerance"): model outputs (score, logits, lengths read-out) and per-layer activations within 4e-3 of
+# max|reference|, against the fp64 live-reference goldens / the oracle.  fp16 operands carry 11 significant bits
+# (2^-12 = 2.4e-4 per rounding), accumulation is fp32; measured on B200: 2e-4 .. 2e-3.  The same number is quoted
+# in DESIGN.md section 3 and bench.py --help.  The fp32 path's bar is north_star's 1e-4.
+TOL_FP16_MODEL = 4e-3
+TOL_FP16_KERNEL = 5e-3      # one GEMM-chain kernel (three chained fp16 GEMMs + two fp16 GELUs) against its fp32 twin
+TOL_FP32 = 1e-4
+
+
 def pytest_configure(config):
     config.addinivalue_line("markers", "gpu: needs a CUDA device (run on the B200 box)")
 

@@ -113,3 +113,94 @@ def test_staged_noise_equals_direct(device, gold, packed_weights, weights_npz):
 
     a, b = run(False), run(True)
     assert all(torch.equal(x, y) for x, y in zip(a, b))
+
+
+def test_sample_draws_the_reference_noise_stream(device, gold, weights_npz):
+    """DiffusionLoss.sample in its default host-noise mode draws numpy / torch CPU random numbers exactly as the
+    reference's sample() does (diffusion_loss.py:294-316, then per step randn_like(lengths), randn_like(frac),
+    rand((N, Z)): SURVEY 3.1): with the seeds of tests/golden/sample_T11.npz the initial angles and every step's three
+    noise tensors are BIT-IDENTICAL to what the reference consumed.  The free-running trajectory itself is chaotic in
+    the sampler's ~1 A initial cells (exactly tied periodic images flip on 1-ulp differences, see
+    oracle/gen_golden.py), so the end state is compared loosely; step-by-step parity is the teacher-forced test above."""
+    import argparse
+    from arreau_b200.diffusion.diffusion_loss import DiffusionLoss
+    from arreau_b200.ponita.models.ponita import PonitaFiberBundle
+    from arreau_b200.synthetic import calibrate_length_readout
+    s = gold("sample_T11.npz")
+    n_per, G = int(s["n_per"]), int(s["num_crystals"])
+    sd = calibrate_length_readout({k: weights_npz[k].astype(np.float64) for k in weights_npz.files
+                                   if k not in ("ori_grid", "fourier_w")}, n_per)
+    net = PonitaFiberBundle((164, 4), 128, 90, 3, 0, 0, 5, output_dim_vec=1, radius=5.0, num_ori=16, basis_dim=256, degree=3,
+                            widening_factor=4, layer_scale=1e-6, multiple_readouts=True, ori_grid=weights_npz["ori_grid"])
+    net.load_state_dict({k: torch.as_tensor(v) for k, v in sd.items()})
+    dl = DiffusionLoss(argparse.Namespace(radius=5.0, max_neighbors=8, num_timesteps=11), 90)
+    seen = []
+
+    def spy(timestep, eng):
+        seen.append((timestep, eng.z_len.cpu().numpy().copy(), eng.z_frac.cpu().numpy().copy(),
+                     eng.u_type.cpu().numpy().copy(), eng.frac.cpu().numpy().copy(), eng.lengths.cpu().numpy().copy()))
+
+    np.random.seed(77)
+    torch.manual_seed(77)
+    zt = list(range(1, 90)) + [2001]
+    res = dl.sample(model=net, z_table=zt, t_emb_weights=torch.as_tensor(weights_npz["fourier_w"]),
+                    num_atoms_per_sample=n_per, num_samples_in_batch=G, device=device, step_callback=spy)
+    assert [k[0] for k in seen] == list(reversed(range(1, 11)))
+    eng = dl._engine
+    assert np.array_equal(eng.angles.cpu().numpy(), s["angles"])            # numpy stream: sample_bravais_angles
+    for k, (_, zl, zf, uu, _, _) in enumerate(seen):
+        assert np.array_equal(zl, s["z_len"][k]), k                          # torch CPU stream, reference order
+        assert np.array_equal(zf, s["z_frac"][k]), k
+        assert np.array_equal(uu, s["u_type"][k]), k
+    # first step: same initial state (lengths0 / frac0 are the draws before the loop) -> step 1 output within fp32 error
+    assert _wrapped(seen[0][4], s["step_frac"][1]) < TOL_FP32 * max(1.0, np.abs(s["step_score"][0]).max())
+    assert rel_err(seen[0][5], s["step_lengths"][1]) < TOL_FP32
+    # end of the free-running trajectory: same crystals up to the chaos of the degenerate early cells
+    assert res.num_atoms.tolist() == s["num_atoms"].tolist() and res.frac_x.shape == s["frac_x"].shape
+    lat_err = rel_err(res.lattice, s["lattice"])
+    frac_dev = np.abs(res.frac_x - s["frac_x"]); frac_dev = np.minimum(frac_dev, 1 - frac_dev)
+    same_types = float((res.atomic_numbers == s["atomic_numbers"]).mean())
+    print(f"free-running sample vs reference: lattice rel {lat_err:.2e}, frac max {frac_dev.max():.2e} "
+          f"median {np.median(frac_dev):.2e}, types equal {same_types:.3f}")
+    assert lat_err < 5e-2 and np.median(frac_dev) < 1e-2 and same_types > 0.8
+
+
+def test_fp16_trajectory_tracks_fp32_trajectory(device, weights_npz):
+    """A WHOLE 999-step trajectory on the fp16 tensor path against the fp32 path (same Philox noise, same initial
+    state, 64 crystals x 40 atoms, calibrated length read-out): per-step rounding differences (~1e-3) and the
+    occasional Gumbel-argmax flip compound over 999 steps, so individual atoms decorrelate; what a sampler user
+    relies on are the trajectory's statistics: E/N trace, final cell lengths, final type histogram."""
+    from arreau_b200.engine import DenoiseEngine
+    from arreau_b200.synthetic import calibrate_length_readout
+    from arreau_b200.tables import build_tables
+    from arreau_b200.weights import PonitaWeights
+    G, n = 64, 40
+    sd = calibrate_length_readout({k: weights_npz[k] for k in weights_npz.files if k not in ("ori_grid", "fourier_w")}, n)
+    w = PonitaWeights(sd, weights_npz["ori_grid"], device=device)
+    rng = np.random.default_rng(3)
+    angles = np.stack([np.full(G, 90.0), rng.uniform(90, 180, G), np.full(G, 90.0)], 1)
+    lengths, frac = rng.standard_normal((G, 3)), rng.standard_normal((G * n, 3))
+    out = {}
+    for prec in ("fp32", "fp16"):
+        eng = DenoiseEngine(w, build_tables(1000, 90), weights_npz["fourier_w"], [n] * G, 5.0, 8, precision=prec, device=device)
+        eng.set_state(frac, np.full(G * n, 89), lengths, angles)
+        epa = []
+        for k, t in enumerate(reversed(range(1, 1000))):
+            eng.draw_noise(5, k)
+            eng.step(t)
+            if k % 10 == 0:
+                epa.append(eng.num_edges() / (G * n))
+        torch.cuda.synchronize()
+        out[prec] = dict(epa=np.asarray(epa), lengths=eng.lengths.cpu().numpy(), types=eng.types.cpu().numpy(),
+                         frac=eng.frac.cpu().numpy())
+        assert np.isfinite(out[prec]["lengths"]).all() and np.isfinite(out[prec]["frac"]).all()
+    a, b = out["fp32"], out["fp16"]
+    epa_dev = float(np.abs(a["epa"] - b["epa"]).max())
+    len_rel = float(np.abs(a["lengths"] - b["lengths"]).max() / np.abs(a["lengths"]).max())
+    ha, hb = np.bincount(a["types"], minlength=90) / a["types"].size, np.bincount(b["types"], minlength=90) / b["types"].size
+    tv = 0.5 * float(np.abs(ha - hb).sum())
+    same = float((a["types"] == b["types"]).mean())
+    print(f"fp16 vs fp32 trajectory: max |E/N diff| {epa_dev:.3f} (E/N {a['epa'].min():.2f}..{a['epa'].max():.2f}), "
+          f"final lengths rel diff {len_rel:.2e}, type histogram TV {tv:.3f}, identical types {same:.3f}")
+    assert a["epa"].min() > 1.0                       # the graph never empties (calibrated read-out, SURVEY B7)
+    assert epa_dev < 0.25 and len_rel < 2e-2 and tv < 0.1

@@ -1,16 +1,15 @@
-"""fp16 tensor-core path (tcgen05): its own stated tolerances (BASELINE.json north_star: "any TF32/bf16 path
-given its own stated tolerance").  fp16 operands carry 11 significant bits (2^-12 = 2.4e-4 relative rounding per
+"""fp16 tensor-core path (tcgen05): its own stated tolerance, ONE number for every test, DESIGN.md and bench.py --help
+(tests/conftest.py: TOL_FP16_MODEL = 4e-3 of max|ref| on model outputs; TOL_FP16_KERNEL = 5e-3 for one GEMM-chain
+kernel against its fp32 twin).  fp16 operands carry 11 significant bits (2^-12 = 2.4e-4 relative rounding per
 element), accumulation is fp32 in TMEM, the GELU epilogues use a packed-fp16 tanh form (max 2.7e-4 from the erf
 form); measured on B200: kernels 6e-4..1.5e-3, model outputs 2e-4..2e-3 of max|ref|."""
 import numpy as np
 import pytest
 import torch
 
-from conftest import rel_err
+from conftest import TOL_FP16_KERNEL, TOL_FP16_MODEL, rel_err
 
 pytestmark = pytest.mark.gpu
-TOL_FP16_KERNEL = 5e-3      # one GEMM-chain kernel against its fp32 twin, max|diff| / max|ref|
-TOL_FP16_MODEL = 1e-2       # score / logits / lengths of the whole forward against the fp64 reference
 
 
 def _rel(a, b):
@@ -87,8 +86,9 @@ def test_teacher_forced_step_f16(device, gold, packed_weights, weights_npz, time
     assert rel_err(eng.logits.cpu().numpy(), s[p + "logits"]) < TOL_FP16_MODEL
     assert rel_err(eng.len0.cpu().numpy(), s[p + "len0"]) < TOL_FP16_MODEL
     assert rel_err(eng.lengths.cpu().numpy(), s[p + "lengths_next"]) < TOL_FP16_MODEL
-    # the edge list is decided in fp64 before the network runs: identical on both precision paths
-    assert (eng.types.cpu().numpy() != s[p + "types_next"]).mean() <= 0.05
+    # the edge list is decided in fp64 before the network runs: identical on both precision paths.  Types: the Gumbel
+    # argmax flips only where the reference's own top-2 margin is within the logit error
+    assert (eng.types.cpu().numpy() != s[p + "types_next"]).mean() <= 0.02
 
 
 def test_c2_shape_f16_vs_fp32_and_properties(device, packed_weights, weights_npz):

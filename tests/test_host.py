@@ -282,3 +282,44 @@ def test_crystal_dataset_and_collate(tmp_path):
         for bb in batches(ds, 2, shuffle=True, seed=3, rank=rank, world=2):
             seen.append(int(bb.num_atoms.shape[0]))
     assert sum(seen) == 7
+
+
+def test_every_rank_gets_the_same_number_of_batches():
+    """each training step carries a gradient all-reduce, so the ranks must run the same number of
+    steps for ANY dataset size: the batch list is padded to a multiple of the world size by wrapping around (torch's
+    DistributedSampler, drop_last=False).  Before the fix 7 crystals / batch 3 / world 2 gave 2 and 1 batches."""
+    from arreau_b200.diffusion.lattice_dataset import batch_index_lists
+    for n, bs, world in [(7, 3, 2), (7, 2, 2), (10, 3, 4), (1, 4, 8), (270 * 5 + 1, 270, 8), (9, 3, 3), (0, 4, 2)]:
+        per_rank = [batch_index_lists(n, bs, True, 5, r, world) for r in range(world)]
+        counts = [len(p) for p in per_rank]
+        assert len(set(counts)) == 1, (n, bs, world, counts)
+        covered = set(int(i) for p in per_rank for b in p for i in b)
+        assert covered == set(range(n)), (n, bs, world)                      # nobody's crystals are dropped
+        assert sum(len(b) for p in per_rank for b in p) >= n
+        # the padding re-uses whole leading batches, at most world - 1 of them
+        assert sum(counts) - (n + bs - 1) // bs < world if n else counts == [0] * world
+
+
+def test_reference_pickled_checkpoint_loads_on_the_host(gold):
+    """tests/golden/reference_model.ckpt was pickled by the LIVE reference classes (oracle/gen_golden.py::gen_checkpoint):
+    hyper_parameters.z_table is a `diffusion.tools.atomic_number_table.AtomicNumberTable` in the pickle and resolves to
+    this package's class; every model / time-embedding tensor lands under the same name (no compute: CPU only)."""
+    import zipfile
+    from conftest import GOLD
+    from arreau_b200.lightning_wrappers.diffusion import PONITA_DIFFUSION, load_checkpoint_file
+    from arreau_b200.tools.atomic_number_table import AtomicNumberTable
+    path = GOLD + "/reference_model.ckpt"
+    with zipfile.ZipFile(path) as z:
+        pkl = z.read([n for n in z.namelist() if n.endswith("data.pkl")][0])
+    assert b"diffusion.tools.atomic_number_table" in pkl                     # the reference's own class path
+    ck = load_checkpoint_file(path)
+    assert isinstance(ck["hyper_parameters"]["z_table"], AtomicNumberTable)
+    io = gold("reference_model_io.npz")
+    m = PONITA_DIFFUSION.load_from_checkpoint(path, ori_grid=io["ori_grid"], strict=True)
+    own = m.state_dict()
+    n_model = 0
+    for k, v in ck["state_dict"].items():
+        if (k.startswith("model.") or k.startswith("t_emb.")) and k in own and v.numel():
+            assert torch.equal(own[k].float().cpu(), v.float()), k
+            n_model += v.numel()
+    assert n_model > 1_100_000 and m.diffusion_loss.num_atomic_states == 21 and m.diffusion_loss.T == 100
