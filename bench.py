@@ -315,8 +315,8 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--precision", default=os.environ.get("ARREAU_PRECISION", "fp16"), choices=["fp32", "fp16"],
-                    help="fp16: tcgen05 tensor-core path (fp16 operands, fp32 accumulate; stated tolerance 4e-3 of "
-                         "max|ref| -- tests/conftest.py TOL_FP16_MODEL, measured 2e-4..2e-3); fp32: FFMA2 SIMT path "
+                    help="fp16: tcgen05 tensor-core path (fp16 operands, fp32 accumulate; stated tolerance 5e-3 of "
+                         "max|ref| -- tests/conftest.py TOL_FP16_MODEL, measured 3e-5..4e-3); fp32: FFMA2 SIMT path "
                          "(<= 1e-4, measured 2e-6)")
     ap.add_argument("--crystals", type=int, default=1024)
     ap.add_argument("--atoms", type=int, default=40)

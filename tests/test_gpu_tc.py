@@ -1,5 +1,5 @@
 """fp16 tensor-core path (tcgen05): its own stated tolerance, ONE number for every test, DESIGN.md and bench.py --help
-(tests/conftest.py: TOL_FP16_MODEL = 4e-3 of max|ref| on model outputs; TOL_FP16_KERNEL = 5e-3 for one GEMM-chain
+(tests/conftest.py: TOL_FP16_MODEL = 5e-3 of max|ref| on model outputs; TOL_FP16_KERNEL = 5e-3 for one GEMM-chain
 kernel against its fp32 twin).  fp16 operands carry 11 significant bits (2^-12 = 2.4e-4 relative rounding per
 element), accumulation is fp32 in TMEM, the GELU epilogues use a packed-fp16 tanh form (max 2.7e-4 from the erf
 form); measured on B200: kernels 6e-4..1.5e-3, model outputs 2e-4..2e-3 of max|ref|."""
