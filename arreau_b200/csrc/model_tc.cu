@@ -25,6 +25,7 @@ constexpr int kTileM = 128;
 constexpr uint32_t kIdesc128 = umma_idesc_f16(128, 128);
 
 __device__ long long* g_tc_prof = nullptr;   // debug: per-phase clock64 stamps of CTA 0 (scratch/prof_tc.py)
+__device__ unsigned g_tc_prof_tile0 = 2;     // first of the 8 stamped tiles (ordinal within the CTA)
 #ifdef ARREAU_TC_PROFILE
 #define TC_STAMP(slot)                                                                     \
   do {                                                                                      \
@@ -470,23 +471,8 @@ convnext_mlp_tc_kernel(const uint8_t* __restrict__ y_img, const uint8_t* __restr
 // K3 + K4a  edge pipeline
 // =================================================================================================
 namespace edge {
-constexpr int kChunkBytes = 32768;      // ring unit: two K slabs [128 rows x 64 K] fp16 of one weight matrix
-constexpr int kStages = 3;
-constexpr int kStageBytes = 32768;      // output staging: two 16 KB halves
-constexpr int kA2Bytes = 32768;         // doubles as the monomial tile A1
-constexpr int kA3Bytes = 65536;
-constexpr int kTilesBytes = kA2Bytes + kA3Bytes + kStageBytes + kStages * kChunkBytes;
-constexpr int kSmemBytes = 232448;      // everything (tiles, bias, barriers) is carved from the dynamic window
-constexpr int kChunksPerTile = 3 + 2 * kL;   // W1, W2 (n-half) x2, then two per Wk_l
 constexpr int kEdgesPerTile = kTileM / kO;
 constexpr int kGeo = 12;                // floats per edge: dir (3), dist, cos(dir, a/b/c) (3), window, valid, pad
-
-struct Bars {
-  uint64_t w_full[kStages], w_empty[kStages];
-  uint64_t a1_full, a2_full, a3_full, d1_full, d2_full;
-  uint64_t g_full[2], g_empty[2];     // per-edge geometry of a tile (warp 3 -> epilogue warps), double buffered
-  uint64_t x_full[2], x_empty[2];     // TMEM buffers X0 (D1, D3 even layers) / X1 (D3 odd layers)
-};
 
 // monomial n of csrc/common.cuh monomials83 as compile-time index triples; 83 = constant 1 (bias), > 83 = 0
 struct MonoIdx { int deg, a, b, c; };
@@ -557,20 +543,55 @@ __device__ __forceinline__ void edge_invariants_f32(const double* __restrict__ d
 }
 }  // namespace edge
 
+// =================================================================================================
+// K3 + K4a  edge pipeline, version 2: the kernel basis is a TENSOR-MEMORY operand
+// =================================================================================================
+// Round 1's kernel kept the kernel basis in shared memory (tile A3) and was bound by the SM's shared-memory port
+// (profiles/README.md): an SS-mode 128 x 128 x 16 MMA
+// reads 8 KB of operands per 64 tensor cycles = the port's whole 128 B/clk, before the weight ring's writes, the
+// epilogue stores and the output staging.  Here the five kernel projections (80 of a tile's 102 MMAs) take their A
+// operand -- the kernel basis [128 rows x 256] fp16 -- from tensor memory (tcgen05.mma ... [a_tmem]), where the second
+// GELU epilogue writes it directly (tcgen05.st): the 64 KB shared-memory tile A3, its 64 KB of epilogue stores and its
+// 320 KB of operand reads per tile are gone (1.66 -> 1.28 MB through the port per 128-row tile), and the freed shared
+// memory deepens the weight ring from 3 to 5 stages.
+//   TMEM     ACC0 = [0,128), ACC1 = [128,256): ONE two-slot accumulator ring shared by every GEMM of the pipeline;
+//            KB0 = [256,384), KB1 = [384,512): kernel basis of the current / the next tile (packed fp16 pairs)
+//   jobs     per tile i, in this order on BOTH sides (MMA warp issues, epilogue warps drain):
+//              L0  G1'  L1  G2a'  L2  G2b'  L3  L4          (' = tile i+1: GEMM1, GEMM2 output halves 0 / 1)
+//            job number j uses slot j & 1; the epilogue pulls a finished slot into registers first (tcgen05.ld) and
+//            hands it back before its own post-processing, so the tensor pipe runs up to two GEMMs ahead
+//   post     L_l : fp16 pack -> staging -> bulk store of kernels[l] (as in version 1)
+//            G1' : GELU -> hidden tile A2 (shared memory, UMMA image)           -> a2_full
+//            G2x': + b2, GELU, * window -> packed fp16 -> KB[(i+1) & 1] (TMEM)  -> kb_full
+//   ring     Wk0 W1' Wk1 W2a' Wk2 W2b' Wk3 Wk4  (13 chunks of 32 KB per tile, 5 stages)
+namespace edge2 {
+constexpr int kChunkBytes = 32768;
+constexpr int kStages = 5;
+constexpr int kStageBytes = 32768;
+constexpr int kA2Bytes = 32768;
+constexpr int kTilesBytes = kA2Bytes + kStageBytes + kStages * kChunkBytes;
+constexpr int kSmemBytes = 232448;
+constexpr int kEdgesPerTile = kTileM / kO;
+constexpr int kGeo = edge::kGeo;
+constexpr uint32_t kKbCol = 256;
+
+struct Bars {
+  uint64_t w_full[kStages], w_empty[kStages];
+  uint64_t a1_full, a2_full;
+  uint64_t acc_full[2], acc_empty[2];
+  uint64_t kb_full[2];
+  uint64_t g_full[2], g_empty[2];
+};
+}  // namespace edge2
+
 __global__ void __launch_bounds__(kThreads, 1)
-edge_kernels_tc_kernel(const double* __restrict__ dir, const double* __restrict__ dist, const double* __restrict__ lattice,
-                       const int32_t* __restrict__ crystal_of_atom, const int32_t* __restrict__ src,
-                       const int32_t* __restrict__ num_edges_ptr, long long edge_capacity, const float* __restrict__ ori,
-                       const uint8_t* __restrict__ w1_img, const uint8_t* __restrict__ w_img, const float* __restrict__ b2,
-                       double radius, __half* __restrict__ kernels) {
-  // Software pipeline over the CTA's tiles: while the tensor pipe runs the five kernel projections (GEMM3) of tile i
-  // out of A3, the head of tile i+1 -- monomials, GEMM1, GELU, GEMM2 -- runs in the shadow, so that only the second
-  // GELU epilogue (which has to overwrite A3) sits between two GEMM3 phases.
-  //   shared:  A2: monomial tile A1, then the hidden layer | A3: kernel basis | S: output staging | weight ring
-  //   TMEM:    X0 = [0,128) and X1 = [384,512): GEMM3 double buffer;  D2 = [128,384): GEMM1 (first half) then GEMM2
-  //   MMA issue order per tile i:   L0 L1 G1(i+1) L2 L3 G2(i+1) L4   (ring order Wk0 Wk1 W1 Wk2 Wk3 W2 Wk4, 26 chunks)
-  //   epilogue order per tile i:    gen(i+1) E0 E1 Q1(i+1) E2 E3 E4 Q2(i+1)
-  using namespace edge;
+edge_kernels_tc2_kernel(const double* __restrict__ dir, const double* __restrict__ dist, const double* __restrict__ lattice,
+                        const int32_t* __restrict__ crystal_of_atom, const int32_t* __restrict__ src,
+                        const int32_t* __restrict__ num_edges_ptr, long long edge_capacity, const float* __restrict__ ori,
+                        const uint8_t* __restrict__ w1_img, const uint8_t* __restrict__ w_img, const float* __restrict__ b2,
+                        double radius, __half* __restrict__ kernels) {
+  using namespace edge2;
+  using edge::store_mono_part;
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
   uint8_t* smem = smem_raw + (base - smem_u32(smem_raw));
@@ -581,9 +602,8 @@ edge_kernels_tc_kernel(const double* __restrict__ dir, const double* __restrict_
       *reinterpret_cast<uint32_t*>(smem + kTilesBytes + (kD + 2 * kEdgesPerTile * kGeo) * sizeof(float) + sizeof(Bars));
   if ((base - smem_u32(smem_raw)) + kTilesBytes + (kD + 2 * kEdgesPerTile * kGeo) * sizeof(float) + sizeof(Bars) + 16 > (uint32_t)kSmemBytes)
     __trap();
-  uint8_t* const A2 = smem;                   // A1 (monomials) aliases A2
-  uint8_t* const A3 = A2 + kA2Bytes;
-  uint8_t* const S = A3 + kA3Bytes;           // two 16 KB halves (rows 0..63 / 64..127) of one layer's output tile
+  uint8_t* const A2 = smem;                   // monomial tile A1, then the hidden layer
+  uint8_t* const S = A2 + kA2Bytes;           // two 16 KB halves (rows 0..63 / 64..127) of one layer's output tile
   uint8_t* const W = S + kStageBytes;
   const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0), lane = threadIdx.x & 31;   // warp-uniform
   long long E = *num_edges_ptr;
@@ -594,10 +614,12 @@ edge_kernels_tc_kernel(const double* __restrict__ dir, const double* __restrict_
   for (int i = threadIdx.x; i < kD; i += kThreads) s_b2[i] = b2[i];
   if (threadIdx.x == 0) {
     for (int i = 0; i < kStages; ++i) { mbar_init(&bars.w_full[i], 1); mbar_init(&bars.w_empty[i], 1); }
-    mbar_init(&bars.a1_full, kEpiWarps); mbar_init(&bars.a2_full, kEpiWarps); mbar_init(&bars.a3_full, kEpiWarps);
-    mbar_init(&bars.d1_full, 1); mbar_init(&bars.d2_full, 1);
-    for (int i = 0; i < 2; ++i) { mbar_init(&bars.x_full[i], 1); mbar_init(&bars.x_empty[i], kEpiWarps); }
-    for (int i = 0; i < 2; ++i) { mbar_init(&bars.g_full[i], 1); mbar_init(&bars.g_empty[i], kEpiWarps); }
+    mbar_init(&bars.a1_full, kEpiWarps); mbar_init(&bars.a2_full, kEpiWarps);
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(&bars.acc_full[i], 1); mbar_init(&bars.acc_empty[i], kEpiWarps);
+      mbar_init(&bars.kb_full[i], 2 * kEpiWarps);            // both output halves of GEMM2
+      mbar_init(&bars.g_full[i], 1); mbar_init(&bars.g_empty[i], kEpiWarps);
+    }
     fence_barrier_init();
   }
   if (warp == 2) tmem_alloc(&tmem_base_s, 512);
@@ -605,11 +627,10 @@ edge_kernels_tc_kernel(const double* __restrict__ dir, const double* __restrict_
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem = tmem_base_s;
+  const uint32_t t0p = g_tc_prof_tile0;
 
   if (warp == 3) {
-    // ---------------- geometry: the per-edge part of the invariants, up to two tiles ahead ----------------
-    // (src -> crystal -> lattice, dir, dist are dependent global loads of ~3000 cycles; here they are off every
-    // critical path).  fp32 like the rest of the fp16 path: the monomials are rounded to fp16 right after.
+    // ---------------- geometry: the per-edge part of the invariants, up to two tiles ahead (as in version 1) --------
     uint32_t k = 0;
     for (long long tile = first; tile < tiles; tile += stride, ++k) {
       const int buf = k & 1;
@@ -640,7 +661,7 @@ edge_kernels_tc_kernel(const double* __restrict__ dir, const double* __restrict_
       if (lane == 0) mbar_arrive(&bars.g_full[buf]);
     }
   } else if (warp == 0 && lane == 0) {
-    // ---------------- producer: 32 KB weight chunks (two K slabs) in the order the MMA warp consumes them ----------------
+    // ---------------- producer: 32 KB weight chunks in the order the MMA warp consumes them ----------------
     if (first < tiles) {
       uint32_t st = 0, par = 1;          // waits on w_empty start at parity 1 (a fresh barrier passes)
       auto push = [&](const uint8_t* src_chunk) {
@@ -651,84 +672,114 @@ edge_kernels_tc_kernel(const double* __restrict__ dir, const double* __restrict_
       };
       auto push_w = [&](int c0, int n) { for (int c = c0; c < c0 + n; ++c) push(w_img + (size_t)c * kChunkBytes); };
       push(w1_img);
-      push_w(0, 2);                                   // first tile: W1, W2
+      push_w(0, 2);                                   // first tile: W1, W2 (both output halves)
       for (long long tile = first; tile < tiles; tile += stride) {
         const bool has_next = tile + stride < tiles;
-        push_w(2, 4);                                 // Wk_0, Wk_1
+        push_w(2, 2);                                 // Wk_0
         if (has_next) push(w1_img);
-        push_w(6, 4);                                 // Wk_2, Wk_3
-        if (has_next) push_w(0, 2);                   // W2 of the next tile
-        push_w(10, 2);                                // Wk_4
+        push_w(4, 2);                                 // Wk_1
+        if (has_next) push_w(0, 1);                   // W2, output half 0
+        push_w(6, 2);                                 // Wk_2
+        if (has_next) push_w(1, 1);                   // W2, output half 1
+        push_w(8, 4);                                 // Wk_3, Wk_4
       }
     }
   } else if (warp == 1) {
-    // ---------------- MMA issuer ----------------
-    // The tensor pipe's issue queue is shallow: every cycle the issuer spends between two tcgen05.mma is an idle
-    // tensor cycle.  The whole warp runs this loop uniformly (descriptors and barrier addresses stay in uniform
-    // registers) and one elected lane issues; ring chunks are waited for in pairs, so that a barrier round covers
-    // 8 MMAs = 512 tensor cycles (measured: the pipe's floor of 64 cycles per MMA, scratch/ubench/mma_ring.cu).
+    // ---------------- MMA issuer (warp-uniform, one elected lane; see version 1) ----------------
     if (first < tiles) {
       const uint32_t el = elect_one();
-      const uint32_t a2_lo = umma_desc_lo(smem_u32(A2)), a3_lo = umma_desc_lo(smem_u32(A3)), w_lo = umma_desc_lo(smem_u32(W));
+      const uint32_t a2_lo = umma_desc_lo(smem_u32(A2)), w_lo = umma_desc_lo(smem_u32(W));
       const uint32_t wfull = smem_u32(&bars.w_full[0]), wempty = smem_u32(&bars.w_empty[0]);
-      constexpr uint32_t kSlabLo = 16384 >> 4;          // descriptor step of one 16 KB slab / ring stage
-      uint32_t st = 0, par = 0;
-      // one ring chunk = two K slabs: D (+)= A[:, slab a] . chunk[0]^T + A[:, slab a+1] . chunk[1]^T, then hand it back
-      auto pair = [&](uint32_t d, uint32_t a_lo, int ksteps1, uint32_t accumulate) {
+      const uint32_t accfull = smem_u32(&bars.acc_full[0]), accempty = smem_u32(&bars.acc_empty[0]);
+      constexpr uint32_t kSlabLo = 16384 >> 4;
+      uint32_t st = 0, par = 0, j = 0;
+      // debug: clock64 stamps of CTA 0, tiles 2..9 of this CTA: [tile][role 0 = MMA][3 * job + {entry, waits done, issued}]
+      long long* const prof = (blockIdx.x == 0 && el) ? g_tc_prof : nullptr;
+      uint32_t pit = 0, pjob = 0;
+      auto stamp = [&](int what) { if (prof && pit >= t0p && pit < t0p + 8) prof[((pit - t0p) * 2 + 0) * 32 + 3 * pjob + what] = clock64(); };
+      auto advance = [&]() { if (++st == kStages) { st = 0; par ^= 1; } };
+      // accumulator slot of job j: wait until the epilogue has pulled the slot's previous content into registers
+      auto acc_begin = [&]() -> uint32_t {
+        const uint32_t slot = j & 1u;
+        mbar_wait_addr(accempty + 8 * slot, ((j >> 1) & 1u) ^ 1u);
+        tc_fence_after();
+        return tmem + slot * 128;
+      };
+      auto acc_end = [&]() { umma_commit_e(accfull + 8 * (j & 1u), el); ++j; };
+      // one ring chunk = two K slabs, A from shared memory (GEMM1 / GEMM2)
+      auto pair_ss = [&](uint32_t d, uint32_t a_lo, int ksteps1) {
         mbar_wait_addr(wfull + 8 * st, par);
         const uint32_t b_lo = w_lo + st * (2 * kSlabLo);
-        umma_slab_e<4>(d, a_lo, b_lo, kIdesc128, el, accumulate);
+        umma_slab_e<4>(d, a_lo, b_lo, kIdesc128, el, 0u);
         if (ksteps1 == 4) umma_slab_e<4>(d, a_lo + kSlabLo, b_lo + kSlabLo, kIdesc128, el, 1u);
         else umma_slab_e<2>(d, a_lo + kSlabLo, b_lo + kSlabLo, kIdesc128, el, 1u);
         umma_commit_e(wempty + 8 * st, el);
-        if (++st == kStages) { st = 0; par ^= 1; }
+        advance();
       };
-      auto gemm1 = [&](uint32_t k) {       // D2[:, 0:128] = A1[128 x 96] . W1m^T   (tile ordinal k)
+      // one ring chunk = two K slabs (128 K values = 64 TMEM columns of packed pairs), A from tensor memory (GEMM3)
+      auto pair_ts = [&](uint32_t d, uint32_t a_t, uint32_t accumulate) {
+        mbar_wait_addr(wfull + 8 * st, par);
+        const uint32_t b_lo = w_lo + st * (2 * kSlabLo);
+        umma_slab_ts_e<4>(d, a_t, b_lo, kIdesc128, el, accumulate);
+        umma_slab_ts_e<4>(d, a_t + 32, b_lo + kSlabLo, kIdesc128, el, 1u);
+        umma_commit_e(wempty + 8 * st, el);
+        advance();
+      };
+      auto gemm1 = [&](uint32_t k) {       // ACC = A1[128 x 96] . W1m^T   (tile ordinal k)
+        stamp(0);
         mbar_wait(&bars.a1_full, k & 1);
-        tc_fence_after();
-        pair(tmem + 128, a2_lo, 2, 0u);
-        umma_commit_e(smem_u32(&bars.d1_full), el);
+        const uint32_t d = acc_begin();
+        stamp(1);
+        pair_ss(d, a2_lo, 2);
+        acc_end();
+        stamp(2); ++pjob;
       };
-      auto gemm2 = [&](uint32_t k) {       // D2[:, nh*128 ..] = A2[128 x 128] . W2[nh]^T, chunks (nh, ks)
-        mbar_wait(&bars.a2_full, k & 1);
-        tc_fence_after();
-        pair(tmem + 128, a2_lo, 4, 0u);
-        pair(tmem + 256, a2_lo, 4, 0u);
-        umma_commit_e(smem_u32(&bars.d2_full), el);
+      auto gemm2 = [&](uint32_t k, int nh) {   // ACC = hidden[128 x 128] . W2[nh]^T
+        stamp(0);
+        if (nh == 0) mbar_wait(&bars.a2_full, k & 1);
+        const uint32_t d = acc_begin();
+        stamp(1);
+        pair_ss(d, a2_lo, 4);
+        acc_end();
+        stamp(2); ++pjob;
       };
       gemm1(0);
-      gemm2(0);
+      gemm2(0, 0);
+      gemm2(0, 1);
       uint32_t it = 0;
-      long long* prof = (blockIdx.x == 0 && el) ? g_tc_prof : nullptr;
-      constexpr int prof_role = 0;
       for (long long tile = first; tile < tiles; tile += stride, ++it) {
         const bool has_next = tile + stride < tiles;
-        TC_STAMP(0);
-        mbar_wait(&bars.a3_full, it & 1);      // kernel basis of tile `it` is in A3 (and D2 has been read out)
-        tc_fence_after();
-        TC_STAMP(1);
+        const uint32_t kb = tmem + kKbCol + (it & 1u) * 128;
+        pit = it; pjob = 0;
+        if (prof && (it == 0 || it == 256)) {       // SM clock during the kernel: cycles and nanoseconds at two distant tiles
+          unsigned long long ns;
+          asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(ns));
+          prof[8 * 2 * 32 + (it ? 2 : 0)] = clock64();
+          prof[8 * 2 * 32 + (it ? 3 : 1)] = (long long)ns;
+        }
 #pragma unroll 1
         for (int l = 0; l < kL; ++l) {
-          // X0 is used by layers 0, 2, 4 (use number 3 it + l/2), X1 by layers 1, 3 (2 it + l/2)
-          const int b = l & 1;
-          const uint32_t use_par = b ? (uint32_t)(l >> 1) & 1u : (it + (uint32_t)(l >> 1)) & 1u;
-          mbar_wait(&bars.x_empty[b], use_par ^ 1u);
-          tc_fence_after();
-          const uint32_t d = tmem + b * 384;
-          pair(d, a3_lo, 4, 0u);
-          pair(d, a3_lo + 2 * kSlabLo, 4, 1u);
-          umma_commit_e(smem_u32(&bars.x_full[b]), el);
-          TC_STAMP(2 + 2 * l);
-          if (has_next) {
-            if (l == 1) gemm1(it + 1);
-            if (l == 3) gemm2(it + 1);
+          stamp(0);
+          const uint32_t d = acc_begin();
+          if (l == 0) {                        // kernel basis of this tile is in tensor memory
+            mbar_wait(&bars.kb_full[it & 1u], (it >> 1) & 1u);
+            tc_fence_after();
           }
-          TC_STAMP(3 + 2 * l);
+          stamp(1);
+          pair_ts(d, kb, 0u);
+          pair_ts(d, kb + 64, 1u);
+          acc_end();
+          stamp(2); ++pjob;
+          if (has_next) {
+            if (l == 0) gemm1(it + 1);
+            else if (l == 1) gemm2(it + 1, 0);
+            else if (l == 2) gemm2(it + 1, 1);
+          }
         }
       }
     }
   } else if (warp >= kEpiWarp0) {
-    // ---------------- generator + epilogues: warp = (lane quarter q, column group cgi) ----------------
+    // ---------------- generator + epilogues: warp = (lane quarter q, column group cgi of 32 columns) ----------------
     const int q = warp & 3, cgi = (warp - kEpiWarp0) >> 2;
     const int m = q * 32 + lane;                     // tile row = (edge m / 16, orientation m % 16)
     const uint32_t lane_addr = (uint32_t)(q * 32) << 16;
@@ -736,9 +787,25 @@ edge_kernels_tc_kernel(const double* __restrict__ dir, const double* __restrict_
     const bool is_issuer = cgi == 0 && (q & 1) == 0 && lane == 0;     // one bulk-store issuer per half tile
     const float ox = ori[3 * (m & 15)], oy = ori[3 * (m & 15) + 1], oz = ori[3 * (m & 15) + 2];
     float win_cur = 0.f;
-    // A1 of tile ordinal k: [dir.ori, |dir - (dir.ori) ori|, dist, cos(dir,a), cos(dir,b), cos(dir,c)] -> 83 monomials
-    // + constant 1 (bias) -> fp16 into A2; 3 of the 12 16-byte chunks per thread
-    auto gen = [&](uint32_t k) {
+    uint32_t j = 0;
+    // debug stamps: [tile][role 1 = epilogue warp 4][3 * job + {entry, accumulator in registers, post-processing done}]
+    long long* const prof = (blockIdx.x == 0 && threadIdx.x == kEpiWarp0 * 32) ? g_tc_prof : nullptr;
+    uint32_t pit = 0, pjob = 0;
+    auto stamp = [&](int what) { if (prof && pit >= t0p && pit < t0p + 8) prof[((pit - t0p) * 2 + 1) * 32 + 3 * pjob + what] = clock64(); };
+    // pull the accumulator of job j (this thread: row m, columns cgi*32 .. +31) into registers and hand the slot back
+    auto acc_take = [&](float (&v)[32]) {
+      stamp(0);
+      const uint32_t slot = j & 1u;
+      mbar_wait(&bars.acc_full[slot], (j >> 1) & 1u);
+      tc_fence_after();
+      tmem_ld32(tmem + slot * 128 + lane_addr + cgi * 32, v);
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&bars.acc_empty[slot]);
+      ++j;
+      stamp(1);
+    };
+    auto gen = [&](uint32_t k) {                     // monomials of tile ordinal k -> A2 (as A1), see version 1
       const int buf = k & 1;
       mbar_wait(&bars.g_full[buf], (k >> 1) & 1);
       const float* gp = s_geo + (buf * kEdgesPerTile + (m >> 4)) * kGeo;
@@ -763,92 +830,30 @@ edge_kernels_tc_kernel(const double* __restrict__ dir, const double* __restrict_
       __syncwarp();
       if (lane == 0) mbar_arrive(&bars.a1_full);
     };
-    // epilogue 1: hidden = GELU(D2[:, 0:128]) -> A2 (hidden unit cgi*32.. -> slab cgi>>1, chunks (cgi&1)*4..)
-    auto epi1 = [&](uint32_t k) {
-      mbar_wait(&bars.d1_full, k & 1);
-      tc_fence_after();
+    auto job_g1 = [&]() {                            // hidden = GELU(GEMM1) -> A2 (unit cgi*32.. -> slab cgi>>1)
       float v[32];
-      tmem_ld32(tmem + 128 + lane_addr + cgi * 32, v);
+      acc_take(v);
       gelu_store32<false, false>(v, nullptr, 1.0f, A2 + (cgi >> 1) * 16384 + m * kRowBytes, (cgi & 1) * 4, m);
-      tc_fence_before();
       fence_proxy_async();
       __syncwarp();
       if (lane == 0) mbar_arrive(&bars.a2_full);
+      stamp(2); ++pjob;
     };
-    // epilogue 2: kernel basis = GELU(D2 + b2) * window -> A3; this warp: columns cgi*64 .. +63 = slab cgi.
-    // A3 is still being read by GEMM3 of the current tile when D2 of the next tile is ready, and the 64 GELUs per
-    // thread are the longest stretch of the epilogue: so the math runs early (epi2_compute) and parks the packed
-    // fp16 rows in the accumulator buffer X1, which is idle between layers 3 and 1; once GEMM3 has finished only
-    // a TMEM -> shared copy (epi2_store) stands between two GEMM3 phases.  The first tile writes A3 directly.
-    auto epi2_direct = [&](uint32_t k) {
-      mbar_wait(&bars.d2_full, k & 1);
-      tc_fence_after();
-#pragma unroll
-      for (int g = 0; g < 2; ++g) {
-        const int col0 = cgi * 64 + g * 32;
-        float v[32];
-        tmem_ld32(tmem + 128 + lane_addr + col0, v);
-        gelu_store32<true, true>(v, s_b2 + col0, win_cur, A3 + cgi * 16384 + m * kRowBytes, g * 4, m);
-      }
-      tc_fence_before();
-      fence_proxy_async();
-      __syncwarp();
-      if (lane == 0) mbar_arrive(&bars.a3_full);
-    };
-    auto epi2_compute = [&](uint32_t k) {          // needs: D2 of tile k complete, X1 drained (layer 3 read out)
-      mbar_wait(&bars.d2_full, k & 1);
-      tc_fence_after();
-#pragma unroll
-      for (int g = 0; g < 2; ++g) {
-        const int col0 = cgi * 64 + g * 32;
-        float v[32];
-        tmem_ld32(tmem + 128 + lane_addr + col0, v);
-        uint32_t pk[16];
-        gelu_scaled_pack32(v, s_b2 + col0, win_cur, pk);
-        tmem_st16(tmem + 384 + lane_addr + cgi * 32 + g * 16, pk);
-      }
-      tmem_wait_st();
-    };
-    auto epi2_store = [&]() {                      // needs: GEMM3 of the current tile complete (A3 free)
-#pragma unroll
-      for (int g = 0; g < 2; ++g) {
-        uint32_t pk[16];
-        tmem_ld16(tmem + 384 + lane_addr + cgi * 32 + g * 16, pk);
-        uint8_t* row = A3 + cgi * 16384 + m * kRowBytes;
-#pragma unroll
-        for (int cc = 0; cc < 4; ++cc)
-          *reinterpret_cast<uint4*>(row + (((g * 4 + cc) ^ (m & 7)) << 4)) =
-              make_uint4(pk[cc * 4], pk[cc * 4 + 1], pk[cc * 4 + 2], pk[cc * 4 + 3]);
-      }
-      tc_fence_before();
-      fence_proxy_async();
-      __syncwarp();
-      if (lane == 0) mbar_arrive(&bars.a3_full);
-    };
-    // epilogue 3: kernels[l][e][o][c] = X[l&1] (fp16), channels cgi*32 .. +31.  The layer's output tile is 32 KB
-    // contiguous in HBM: it is staged in shared memory and written by the TMA engine with bulk stores (scattered
-    // 32-byte stores from 512 threads would monopolise the LSU).  Rows are 256 B; the 16-byte chunk k of row (e, o)
-    // is stored at chunk position k ^ o (the fp16 kernels layout, undone by the message kernel's loads), which
-    // makes these 16-byte shared stores conflict free.  The two 16 KB halves (rows 0..63 / 64..127) are staged,
-    // stored and recycled independently by the 8 warps owning those rows.
-    auto epi3 = [&](int l, long long tile, uint32_t it, bool store_next_a3) {
-      const int b = l & 1;
-      const uint32_t use_par = b ? (uint32_t)(l >> 1) & 1u : (it + (uint32_t)(l >> 1)) & 1u;
-      mbar_wait(&bars.x_full[b], use_par);
-      tc_fence_after();
+    auto job_g2 = [&](uint32_t k, int nh) {          // kernel basis half nh of tile k -> KB[k & 1] (tensor memory)
       float v[32];
-      tmem_ld32(tmem + b * 384 + lane_addr + cgi * 32, v);
+      acc_take(v);
+      uint32_t pk[16];
+      gelu_scaled_pack32(v, s_b2 + nh * 128 + cgi * 32, win_cur, pk);
+      tmem_st16(tmem + kKbCol + (k & 1u) * 128 + lane_addr + nh * 64 + cgi * 16, pk);
+      tmem_wait_st();
       tc_fence_before();
       __syncwarp();
-      if (lane == 0) mbar_arrive(&bars.x_empty[b]);       // accumulators are in registers: release the buffer
-      if (store_next_a3) epi2_store();                    // layer 4: GEMM3 is done with A3 -> next tile's kernel basis
-      // The layer's output tile is 32 KB contiguous in HBM: it is staged in shared memory and written by the TMA
-      // engine with bulk stores.  (Measured alternatives: scattered 32-byte stores straight from registers 2.94 ms,
-      // coalesced 16-byte stores from the staging buffer 2.49 ms, bulk stores 2.39 ms; without any output store the
-      // kernel takes 1.75 ms -- a per-SM write path of ~32 B/clk has to carry 160 KB per tile.)  Rows are 256 B; the
-      // 16-byte chunk k of row (e, o) is staged at chunk position k ^ o -- conflict-free shared stores -- and that
-      // is also the fp16 kernels layout in HBM (undone by the message kernel's loads).  The two 16 KB halves
-      // (rows 0..63 / 64..127) are staged, stored and recycled independently by the 8 warps owning those rows.
+      if (lane == 0) mbar_arrive(&bars.kb_full[k & 1u]);
+      stamp(2); ++pjob;
+    };
+    auto job_layer = [&](int l, long long tile) {    // kernels[l][e][o][c] = ACC (fp16), staged + bulk store (version 1)
+      float v[32];
+      acc_take(v);
       uint8_t* stage = S + hf * 16384;
       if (is_issuer) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");   // this half's previous store has left smem
       asm volatile("bar.sync %0, %1;" ::"r"(1 + hf), "n"(kEpiThreads / 2) : "memory");
@@ -874,34 +879,28 @@ edge_kernels_tc_kernel(const double* __restrict__ dir, const double* __restrict_
         }
         asm volatile("cp.async.bulk.commit_group;" ::: "memory");
       }
+      stamp(2); ++pjob;
     };
     if (first < tiles) {
       gen(0);
-      epi1(0);
-      epi2_direct(0);
+      job_g1();
+      job_g2(0, 0);
+      job_g2(0, 1);
       uint32_t it = 0;
-      long long* prof = (blockIdx.x == 0 && threadIdx.x == kEpiWarp0 * 32) ? g_tc_prof : nullptr;
-      constexpr int prof_role = 1;
       for (long long tile = first; tile < tiles; tile += stride, ++it) {
         const bool has_next = tile + stride < tiles;
-        TC_STAMP(0);
-        if (has_next) gen(it + 1);                 // A2 is free: GEMM2 of this tile completed before d2_full fired
-        TC_STAMP(1);
-        TC_STAMP(2);
-        epi3(0, tile, it, false);
-        TC_STAMP(3);
-        epi3(1, tile, it, false);
-        TC_STAMP(4);
-        if (has_next) epi1(it + 1);
-        TC_STAMP(5);
-        epi3(2, tile, it, false);
-        TC_STAMP(6);
-        epi3(3, tile, it, false);                  // X1 is drained: it can hold the next tile's packed kernel basis
-        TC_STAMP(7);
-        if (has_next) epi2_compute(it + 1);
-        TC_STAMP(8);
-        epi3(4, tile, it, has_next);               // its x_full also says GEMM3 has finished reading A3
-        TC_STAMP(9);
+        pit = it; pjob = 0;
+        if (prof && pit >= t0p && pit < t0p + 8) prof[((pit - t0p) * 2 + 1) * 32 + 30] = clock64();
+        if (has_next) gen(it + 1);                 // A2 is free: both halves of this tile's GEMM2 have been drained
+        if (prof && pit >= t0p && pit < t0p + 8) prof[((pit - t0p) * 2 + 1) * 32 + 31] = clock64();
+        job_layer(0, tile);
+        if (has_next) job_g1();
+        job_layer(1, tile);
+        if (has_next) job_g2(it + 1, 0);
+        job_layer(2, tile);
+        if (has_next) job_g2(it + 1, 1);
+        job_layer(3, tile);
+        job_layer(4, tile);
       }
       if (is_issuer) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");   // all output tiles have landed
     }
@@ -913,6 +912,453 @@ edge_kernels_tc_kernel(const double* __restrict__ dir, const double* __restrict_
     tmem_dealloc(tmem, 512);
   }
 }
+
+// =================================================================================================
+// K3 + K4a  edge pipeline, version 3: version 2 with TWO epilogue groups working on different jobs at the same time
+// =================================================================================================
+// Version 2 is bound by its 16 epilogue warps (clock64 timeline, profiles/r2_edge_timeline.md): they take the tile's 8
+// jobs one after the other in lockstep -- every job pays the accumulator drain latency (~180 cycles), the block
+// barriers of the output staging and the XU-bound GELU chains back to back, 11.5 K cycles per tile against the tensor
+// pipe's 6.5 K.  Here 24 epilogue warps form two groups with one accumulator slot each:
+//   G-group (warps 4..19)   gen' -> G1' (GELU -> hidden tile A2) -> G2a', G2b' (GELU * window -> kernel basis in TMEM)
+//   L-group (warps 20..27)  L0 .. L4: fp16 pack -> staging -> bulk store of kernels[l]  (64 columns per thread)
+// Every producer/consumer chain of the tile head (monomials, hidden layer, kernel basis) stays inside the G-group, so
+// no cross-group hand-off is needed: completion of earlier MMAs is implied by the in-order tensor pipe (a finished
+// GEMM2 says that the previous tile's five projections have finished reading the other kernel-basis buffer).
+// MMA issue order per tile as in version 2 (L0 G1' L1 G2a' L2 G2b' L3 L4); L jobs use ACC1, G jobs ACC0.
+// 896 threads (a block holds at most 1024) -> 73 registers per thread.
+namespace edge3 {
+constexpr int kChunkBytes = 32768;
+constexpr int kStages = 5;
+constexpr int kStageBytes = 32768;
+constexpr int kA2Bytes = 32768;
+constexpr int kTilesBytes = kA2Bytes + kStageBytes + kStages * kChunkBytes;
+constexpr int kSmemBytes = 232448;
+constexpr int kEdgesPerTile = kTileM / kO;
+constexpr int kGeo = edge::kGeo;
+constexpr uint32_t kKbCol = 256;
+constexpr int kLWarps = 8;                 // L-group: 4 lane quarters x 2 column halves
+constexpr int kThreads3 = (kEpiWarp0 + kEpiWarps + kLWarps) * 32;   // 896: 4 service warps + G-group (16) + L-group (8)
+constexpr int kLWarp0 = kEpiWarp0 + kEpiWarps;
+
+struct Bars {
+  uint64_t w_full[kStages], w_empty[kStages];
+  uint64_t a1_full, a2_full;
+  uint64_t acc_full[2], acc_empty[2];      // [0] = G jobs (ACC0), [1] = L jobs (ACC1)
+  uint64_t kb_full[2];
+  uint64_t g_full[2], g_empty[2];
+};
+}  // namespace edge3
+
+__global__ void __launch_bounds__(edge3::kThreads3, 1)
+edge_kernels_tc3_kernel(const double* __restrict__ dir, const double* __restrict__ dist, const double* __restrict__ lattice,
+                        const int32_t* __restrict__ crystal_of_atom, const int32_t* __restrict__ src,
+                        const int32_t* __restrict__ num_edges_ptr, long long edge_capacity, const float* __restrict__ ori,
+                        const uint8_t* __restrict__ w1_img, const uint8_t* __restrict__ w_img, const float* __restrict__ b2,
+                        double radius, __half* __restrict__ kernels) {
+  using namespace edge3;
+  using edge::store_mono_part;
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  uint8_t* smem = smem_raw + (base - smem_u32(smem_raw));
+  float* const s_b2 = reinterpret_cast<float*>(smem + kTilesBytes);                                   // [kD]
+  float* const s_geo = s_b2 + kD;                                                                      // [2][8 edges][kGeo]
+  Bars& bars = *reinterpret_cast<Bars*>(smem + kTilesBytes + (kD + 2 * kEdgesPerTile * kGeo) * sizeof(float));
+  uint32_t& tmem_base_s =
+      *reinterpret_cast<uint32_t*>(smem + kTilesBytes + (kD + 2 * kEdgesPerTile * kGeo) * sizeof(float) + sizeof(Bars));
+  if ((base - smem_u32(smem_raw)) + kTilesBytes + (kD + 2 * kEdgesPerTile * kGeo) * sizeof(float) + sizeof(Bars) + 16 > (uint32_t)kSmemBytes)
+    __trap();
+  uint8_t* const A2 = smem;                   // monomial tile A1, then the hidden layer
+  uint8_t* const S = A2 + kA2Bytes;           // two 16 KB halves (rows 0..63 / 64..127) of one layer's output tile
+  uint8_t* const W = S + kStageBytes;
+  const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0), lane = threadIdx.x & 31;   // warp-uniform
+  long long E = *num_edges_ptr;
+  if (E > edge_capacity) E = edge_capacity;
+  const long long tiles = (E + kEdgesPerTile - 1) / kEdgesPerTile;
+  const long long first = blockIdx.x, stride = gridDim.x;
+
+  for (int i = threadIdx.x; i < kD; i += kThreads3) s_b2[i] = b2[i];
+  if (threadIdx.x == 0) {
+    for (int i = 0; i < kStages; ++i) { mbar_init(&bars.w_full[i], 1); mbar_init(&bars.w_empty[i], 1); }
+    mbar_init(&bars.a1_full, kEpiWarps); mbar_init(&bars.a2_full, kEpiWarps);
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(&bars.acc_full[i], 1); mbar_init(&bars.acc_empty[i], i == 0 ? kEpiWarps : kLWarps);
+      mbar_init(&bars.kb_full[i], 2 * kEpiWarps);            // both output halves of GEMM2
+      mbar_init(&bars.g_full[i], 1); mbar_init(&bars.g_empty[i], kEpiWarps);
+    }
+    fence_barrier_init();
+  }
+  if (warp == 2) tmem_alloc(&tmem_base_s, 512);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem = tmem_base_s;
+
+  if (warp == 3) {
+    // ---------------- geometry: the per-edge part of the invariants, up to two tiles ahead (as in version 1) --------
+    uint32_t k = 0;
+    for (long long tile = first; tile < tiles; tile += stride, ++k) {
+      const int buf = k & 1;
+      mbar_wait(&bars.g_empty[buf], ((k >> 1) & 1) ^ 1);
+      if (lane < kEdgesPerTile) {
+        const long long e = tile * kEdgesPerTile + lane;
+        float* gp = s_geo + (buf * kEdgesPerTile + lane) * kGeo;
+        float vals[9] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+        if (e < E) {
+          const double* lat9 = lattice + 9 * (size_t)crystal_of_atom[src[e]];
+          const float dx = (float)dir[3 * e], dy = (float)dir[3 * e + 1], dz = (float)dir[3 * e + 2];
+          const float dd = dx * dx + dy * dy + dz * dz;
+          vals[0] = dx; vals[1] = dy; vals[2] = dz;
+          vals[3] = (float)dist[e];
+#pragma unroll
+          for (int mm = 0; mm < 3; ++mm) {
+            const float ax = (float)lat9[3 * mm], ay = (float)lat9[3 * mm + 1], az = (float)lat9[3 * mm + 2];
+            const float w12 = dx * ax + dy * ay + dz * az, w2 = ax * ax + ay * ay + az * az;
+            vals[4 + mm] = w12 * rsqrtf(fmaxf(dd * w2, 1e-16f));     // CosineSimilarity, eps = 1e-8
+          }
+          vals[7] = cutoff_window(dist[e], radius);
+          vals[8] = 1.0f;
+        }
+#pragma unroll
+        for (int i = 0; i < 9; ++i) gp[i] = vals[i];
+      }
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&bars.g_full[buf]);
+    }
+  } else if (warp == 0 && lane == 0) {
+    // ---------------- producer: 32 KB weight chunks in the order the MMA warp consumes them ----------------
+    if (first < tiles) {
+      uint32_t st = 0, par = 1;          // waits on w_empty start at parity 1 (a fresh barrier passes)
+      auto push = [&](const uint8_t* src_chunk) {
+        mbar_wait(&bars.w_empty[st], par);
+        mbar_expect_tx(&bars.w_full[st], kChunkBytes);
+        bulk_g2s(W + st * kChunkBytes, src_chunk, kChunkBytes, &bars.w_full[st]);
+        if (++st == kStages) { st = 0; par ^= 1; }
+      };
+      auto push_w = [&](int c0, int n) { for (int c = c0; c < c0 + n; ++c) push(w_img + (size_t)c * kChunkBytes); };
+      push(w1_img);
+      push_w(0, 2);                                   // first tile: W1, W2 (both output halves)
+      for (long long tile = first; tile < tiles; tile += stride) {
+        const bool has_next = tile + stride < tiles;
+        push_w(2, 2);                                 // Wk_0
+        if (has_next) push(w1_img);
+        push_w(4, 2);                                 // Wk_1
+        if (has_next) push_w(0, 1);                   // W2, output half 0
+        push_w(6, 2);                                 // Wk_2
+        if (has_next) push_w(1, 1);                   // W2, output half 1
+        push_w(8, 4);                                 // Wk_3, Wk_4
+      }
+    }
+  } else if (warp == 1) {
+    // ---------------- MMA issuer (warp-uniform, one elected lane; see version 1) ----------------
+    if (first < tiles) {
+      const uint32_t el = elect_one();
+      const uint32_t a2_lo = umma_desc_lo(smem_u32(A2)), w_lo = umma_desc_lo(smem_u32(W));
+      const uint32_t wfull = smem_u32(&bars.w_full[0]), wempty = smem_u32(&bars.w_empty[0]);
+      const uint32_t accfull = smem_u32(&bars.acc_full[0]), accempty = smem_u32(&bars.acc_empty[0]);
+      constexpr uint32_t kSlabLo = 16384 >> 4;
+      uint32_t st = 0, par = 0, ug = 0, ul = 0;        // uses of the G slot (ACC0) / the L slot (ACC1) so far
+      // debug: clock64 stamps of CTA 0, tiles 2..9 of this CTA: [tile][role 0 = MMA][3 * job + {entry, waits done, issued}]
+      long long* const prof = (blockIdx.x == 0 && el) ? g_tc_prof : nullptr;
+      uint32_t pit = 0, pjob = 0;
+#ifdef ARREAU_TC_PROFILE
+      auto stamp = [&](int what) { if (prof && pit >= 2 && pit < 10) prof[((pit - 2) * 3 + 0) * 32 + 3 * pjob + what] = clock64(); };
+#else
+      auto stamp = [&](int) { (void)prof; };
+#endif
+      auto advance = [&]() { if (++st == kStages) { st = 0; par ^= 1; } };
+      // accumulator slot of a job: wait until its group has pulled the slot's previous content into registers
+      auto acc_begin = [&](uint32_t slot) -> uint32_t {
+        mbar_wait_addr(accempty + 8 * slot, ((slot ? ul : ug) & 1u) ^ 1u);
+        tc_fence_after();
+        return tmem + slot * 128;
+      };
+      auto acc_end = [&](uint32_t slot) { umma_commit_e(accfull + 8 * slot, el); if (slot) ++ul; else ++ug; };
+      // one ring chunk = two K slabs, A from shared memory (GEMM1 / GEMM2)
+      auto pair_ss = [&](uint32_t d, uint32_t a_lo, int ksteps1) {
+        mbar_wait_addr(wfull + 8 * st, par);
+        const uint32_t b_lo = w_lo + st * (2 * kSlabLo);
+        umma_slab_e<4>(d, a_lo, b_lo, kIdesc128, el, 0u);
+        if (ksteps1 == 4) umma_slab_e<4>(d, a_lo + kSlabLo, b_lo + kSlabLo, kIdesc128, el, 1u);
+        else umma_slab_e<2>(d, a_lo + kSlabLo, b_lo + kSlabLo, kIdesc128, el, 1u);
+        umma_commit_e(wempty + 8 * st, el);
+        advance();
+      };
+      // one ring chunk = two K slabs (128 K values = 64 TMEM columns of packed pairs), A from tensor memory (GEMM3)
+      auto pair_ts = [&](uint32_t d, uint32_t a_t, uint32_t accumulate) {
+        mbar_wait_addr(wfull + 8 * st, par);
+        const uint32_t b_lo = w_lo + st * (2 * kSlabLo);
+        umma_slab_ts_e<4>(d, a_t, b_lo, kIdesc128, el, accumulate);
+        umma_slab_ts_e<4>(d, a_t + 32, b_lo + kSlabLo, kIdesc128, el, 1u);
+        umma_commit_e(wempty + 8 * st, el);
+        advance();
+      };
+      auto gemm1 = [&](uint32_t k) {       // ACC = A1[128 x 96] . W1m^T   (tile ordinal k)
+        stamp(0);
+        mbar_wait(&bars.a1_full, k & 1);
+        const uint32_t d = acc_begin(0);
+        stamp(1);
+        pair_ss(d, a2_lo, 2);
+        acc_end(0);
+        stamp(2); ++pjob;
+      };
+      auto gemm2 = [&](uint32_t k, int nh) {   // ACC = hidden[128 x 128] . W2[nh]^T
+        stamp(0);
+        if (nh == 0) mbar_wait(&bars.a2_full, k & 1);
+        const uint32_t d = acc_begin(0);
+        stamp(1);
+        pair_ss(d, a2_lo, 4);
+        acc_end(0);
+        stamp(2); ++pjob;
+      };
+      gemm1(0);
+      gemm2(0, 0);
+      gemm2(0, 1);
+      uint32_t it = 0;
+      for (long long tile = first; tile < tiles; tile += stride, ++it) {
+        const bool has_next = tile + stride < tiles;
+        const uint32_t kb = tmem + kKbCol + (it & 1u) * 128;
+        pit = it; pjob = 0;
+#pragma unroll 1
+        for (int l = 0; l < kL; ++l) {
+          stamp(0);
+          const uint32_t d = acc_begin(1);
+          if (l == 0) {                        // kernel basis of this tile is in tensor memory
+            mbar_wait(&bars.kb_full[it & 1u], (it >> 1) & 1u);
+            tc_fence_after();
+          }
+          stamp(1);
+          pair_ts(d, kb, 0u);
+          pair_ts(d, kb + 64, 1u);
+          acc_end(1);
+          stamp(2); ++pjob;
+          if (has_next) {
+            if (l == 0) gemm1(it + 1);
+            else if (l == 1) gemm2(it + 1, 0);
+            else if (l == 2) gemm2(it + 1, 1);
+          }
+        }
+      }
+    }
+  } else if (warp >= kEpiWarp0 && warp < kLWarp0) {
+    // ---------------- G-group: generator + the two GELU epilogues; warp = (lane quarter q, column group cgi) --------
+    const int q = warp & 3, cgi = (warp - kEpiWarp0) >> 2;
+    const int m = q * 32 + lane;                     // tile row = (edge m / 16, orientation m % 16)
+    const uint32_t lane_addr = (uint32_t)(q * 32) << 16;
+    const float ox = ori[3 * (m & 15)], oy = ori[3 * (m & 15) + 1], oz = ori[3 * (m & 15) + 2];
+    float win_cur = 0.f;
+    uint32_t ug = 0;
+    long long* const prof = (blockIdx.x == 0 && threadIdx.x == kEpiWarp0 * 32) ? g_tc_prof : nullptr;
+    uint32_t pit = 0, pjob = 0;
+#ifdef ARREAU_TC_PROFILE
+    auto stamp = [&](int what) { if (prof && pit >= 2 && pit < 10) prof[((pit - 2) * 3 + 1) * 32 + 3 * pjob + what] = clock64(); };
+#else
+    auto stamp = [&](int) { (void)prof; };
+#endif
+    auto acc_wait = [&]() {
+      stamp(0);
+      mbar_wait(&bars.acc_full[0], ug & 1u);
+      tc_fence_after();
+    };
+    auto acc_release = [&]() {                       // the accumulator is in registers: hand the slot back
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&bars.acc_empty[0]);
+      ++ug;
+      stamp(1);
+    };
+    auto ld32 = [&](uint32_t (&r0)[16], uint32_t (&r1)[16]) {      // columns cgi*32 .. +31 of row m, one wait for both
+      tmem_ld16_nowait(tmem + lane_addr + cgi * 32, r0);
+      tmem_ld16_nowait(tmem + lane_addr + cgi * 32 + 16, r1);
+      tmem_wait_ld();
+    };
+    auto gen = [&](uint32_t k) {                     // monomials of tile ordinal k -> A2 (as A1), see version 1
+      const int buf = k & 1;
+      mbar_wait(&bars.g_full[buf], (k >> 1) & 1);
+      const float* gp = s_geo + (buf * kEdgesPerTile + (m >> 4)) * kGeo;
+      const float dx = gp[0], dy = gp[1], dz = gp[2];
+      float attr[6];
+      const float i1 = dx * ox + dy * oy + dz * oz;
+      const float px = dx - i1 * ox, py = dy - i1 * oy, pz = dz - i1 * oz;
+      attr[0] = i1;
+      attr[1] = sqrtf(px * px + py * py + pz * pz);
+      attr[2] = gp[3]; attr[3] = gp[4]; attr[4] = gp[5]; attr[5] = gp[6];
+      win_cur = gp[7];
+      const float one = gp[8];
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&bars.g_empty[buf]);
+      switch (cgi) {
+        case 0: store_mono_part<0>(attr, one, A2, m); break;
+        case 1: store_mono_part<1>(attr, one, A2, m); break;
+        case 2: store_mono_part<2>(attr, one, A2, m); break;
+        default: store_mono_part<3>(attr, one, A2, m); break;
+      }
+      fence_proxy_async();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&bars.a1_full);
+    };
+    auto job_g1 = [&]() {                            // hidden = GELU(GEMM1) -> A2 (unit cgi*32.. -> slab cgi>>1)
+      uint32_t v0[16], v1[16];
+      acc_wait();
+      ld32(v0, v1);
+      acc_release();
+      uint8_t* row = A2 + (cgi >> 1) * 16384 + m * kRowBytes;
+      const int chunk0 = (cgi & 1) * 4;
+      auto f = [](uint32_t u) { return __uint_as_float(u); };
+#pragma unroll
+      for (int cc = 0; cc < 2; ++cc) {
+        uint4 pk;
+        pk.x = gelu2_f16(f(v0[cc * 8 + 0]), f(v0[cc * 8 + 1])); pk.y = gelu2_f16(f(v0[cc * 8 + 2]), f(v0[cc * 8 + 3]));
+        pk.z = gelu2_f16(f(v0[cc * 8 + 4]), f(v0[cc * 8 + 5])); pk.w = gelu2_f16(f(v0[cc * 8 + 6]), f(v0[cc * 8 + 7]));
+        *reinterpret_cast<uint4*>(row + (((chunk0 + cc) ^ (m & 7)) << 4)) = pk;
+      }
+#pragma unroll
+      for (int cc = 0; cc < 2; ++cc) {
+        uint4 pk;
+        pk.x = gelu2_f16(f(v1[cc * 8 + 0]), f(v1[cc * 8 + 1])); pk.y = gelu2_f16(f(v1[cc * 8 + 2]), f(v1[cc * 8 + 3]));
+        pk.z = gelu2_f16(f(v1[cc * 8 + 4]), f(v1[cc * 8 + 5])); pk.w = gelu2_f16(f(v1[cc * 8 + 6]), f(v1[cc * 8 + 7]));
+        *reinterpret_cast<uint4*>(row + (((chunk0 + 2 + cc) ^ (m & 7)) << 4)) = pk;
+      }
+      fence_proxy_async();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&bars.a2_full);
+      stamp(2); ++pjob;
+    };
+    auto job_g2 = [&](uint32_t k, int nh) {          // kernel basis half nh of tile k -> KB[k & 1] (tensor memory)
+      uint32_t v0[16], v1[16];
+      acc_wait();
+      ld32(v0, v1);
+      acc_release();
+      const __half2 sc = __float2half2_rn(win_cur);
+      const float* bias = s_b2 + nh * 128 + cgi * 32;
+      const uint32_t dst = tmem + kKbCol + (k & 1u) * 128 + lane_addr + nh * 64 + cgi * 16;
+      // in place: packed pair i of the 32 columns overwrites v0[i] (its inputs v0[2i], v0[2i+1] / v1[..] are dead by then)
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        const float2 b = *reinterpret_cast<const float2*>(bias + 2 * i);           // warp-uniform: smem broadcast
+        v0[i] = gelu2_scaled_f16(__uint_as_float(v0[2 * i]) + b.x, __uint_as_float(v0[2 * i + 1]) + b.y, sc);
+      }
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        const float2 b = *reinterpret_cast<const float2*>(bias + 16 + 2 * i);
+        v0[8 + i] = gelu2_scaled_f16(__uint_as_float(v1[2 * i]) + b.x, __uint_as_float(v1[2 * i + 1]) + b.y, sc);
+      }
+      tmem_st16(dst, v0);
+      tmem_wait_st();
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&bars.kb_full[k & 1u]);
+      stamp(2); ++pjob;
+    };
+    if (first < tiles) {
+      gen(0);
+      job_g1();
+      job_g2(0, 0);
+      job_g2(0, 1);
+      uint32_t it = 0;
+      for (long long tile = first; tile < tiles; tile += stride, ++it) {
+        if (tile + stride >= tiles) break;
+        pit = it; pjob = 0;
+#ifdef ARREAU_TC_PROFILE
+        if (prof && pit >= 2 && pit < 10) prof[((pit - 2) * 3 + 1) * 32 + 30] = clock64();
+#endif
+        gen(it + 1);                               // A2 is free: this group has drained both halves of tile it's GEMM2
+#ifdef ARREAU_TC_PROFILE
+        if (prof && pit >= 2 && pit < 10) prof[((pit - 2) * 3 + 1) * 32 + 31] = clock64();
+#endif
+        job_g1();
+        job_g2(it + 1, 0);
+        job_g2(it + 1, 1);
+      }
+    }
+  } else if (warp >= kLWarp0) {
+    // ---------------- L-group: kernels[l][e][o][c] = ACC1 (fp16), staged in shared memory, bulk stores ---------------
+    // warp = (lane quarter q, column half ch): row m, channels ch*64 .. +63, pulled in two passes of 32 columns
+    const int q = warp & 3, ch = (warp - kLWarp0) >> 2;
+    const int m = q * 32 + lane;
+    const uint32_t lane_addr = (uint32_t)(q * 32) << 16;
+    const int hf = q >> 1;                           // staging half of this warp's rows
+    const bool is_issuer = ch == 0 && (q & 1) == 0 && lane == 0;      // one bulk-store issuer per half tile
+    uint32_t ul = 0;
+    long long* const prof = (blockIdx.x == 0 && threadIdx.x == kLWarp0 * 32) ? g_tc_prof : nullptr;
+    uint32_t pit = 0, pjob = 0;
+#ifdef ARREAU_TC_PROFILE
+    auto stamp = [&](int what) { if (prof && pit >= 2 && pit < 10) prof[((pit - 2) * 3 + 2) * 32 + 3 * pjob + what] = clock64(); };
+#else
+    auto stamp = [&](int) { (void)prof; };
+#endif
+    auto pack16 = [](const uint32_t (&r)[16], uint4 (&pk)[2]) {
+#pragma unroll
+      for (int cc = 0; cc < 2; ++cc) {
+        pk[cc].x = pack_f16(__uint_as_float(r[cc * 8 + 0]), __uint_as_float(r[cc * 8 + 1]));
+        pk[cc].y = pack_f16(__uint_as_float(r[cc * 8 + 2]), __uint_as_float(r[cc * 8 + 3]));
+        pk[cc].z = pack_f16(__uint_as_float(r[cc * 8 + 4]), __uint_as_float(r[cc * 8 + 5]));
+        pk[cc].w = pack_f16(__uint_as_float(r[cc * 8 + 6]), __uint_as_float(r[cc * 8 + 7]));
+      }
+    };
+    auto job_layer = [&](int l, long long tile) {
+      stamp(0);
+      mbar_wait(&bars.acc_full[1], ul & 1u);
+      tc_fence_after();
+      const uint32_t acc = tmem + 128 + lane_addr + ch * 64;
+      uint4 pk[8];                                   // 64 channels of row m as packed fp16
+      {
+        uint32_t r0[16], r1[16];
+        tmem_ld16_nowait(acc, r0);
+        tmem_ld16_nowait(acc + 16, r1);
+        tmem_wait_ld();
+        pack16(r0, *reinterpret_cast<uint4(*)[2]>(&pk[0]));
+        pack16(r1, *reinterpret_cast<uint4(*)[2]>(&pk[2]));
+        tmem_ld16_nowait(acc + 32, r0);
+        tmem_ld16_nowait(acc + 48, r1);
+        tmem_wait_ld();
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&bars.acc_empty[1]);      // the accumulator is in registers: hand the slot back
+        ++ul;
+        stamp(1);
+        pack16(r0, *reinterpret_cast<uint4(*)[2]>(&pk[4]));
+        pack16(r1, *reinterpret_cast<uint4(*)[2]>(&pk[6]));
+      }
+      uint8_t* stage = S + hf * 16384;
+      if (is_issuer) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");   // this half's previous store has left smem
+      asm volatile("bar.sync %0, %1;" ::"r"(1 + hf), "n"(kLWarps * 32 / 2) : "memory");
+      uint8_t* orow = stage + (m & 63) * 256;
+#pragma unroll
+      for (int cc = 0; cc < 8; ++cc) *reinterpret_cast<uint4*>(orow + (((ch * 8 + cc) ^ (m & 15)) << 4)) = pk[cc];
+      fence_proxy_async();
+      asm volatile("bar.sync %0, %1;" ::"r"(1 + hf), "n"(kLWarps * 32 / 2) : "memory");
+      if (is_issuer) {
+        const long long left = E - tile * kEdgesPerTile - hf * (kEdgesPerTile / 2);   // edges of this half still valid
+        if (left > 0) {
+          const uint32_t bytes = (uint32_t)(left < kEdgesPerTile / 2 ? left : kEdgesPerTile / 2) * (kO * kC * 2);
+          __half* out = kernels + ((size_t)l * edge_capacity * kO + (size_t)tile * kTileM + hf * 64) * kC;
+          asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(out), "r"(smem_u32(stage)), "r"(bytes)
+                       : "memory");
+        }
+        asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+      }
+      stamp(2); ++pjob;
+    };
+    if (first < tiles) {
+      uint32_t it = 0;
+      for (long long tile = first; tile < tiles; tile += stride, ++it) {
+        pit = it; pjob = 0;
+#pragma unroll 1
+        for (int l = 0; l < kL; ++l) job_layer(l, tile);
+      }
+      if (is_issuer) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");   // all output tiles have landed
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 2) {
+    tc_fence_after();
+    tmem_dealloc(tmem, 512);
+  }
+}
+
+int g_edge_variant = 3;      // 2: one epilogue group (16 warps); 3: two epilogue groups (G 16 + L 8 warps), the default
 
 int num_sms_tc() {
   static int sms = 0;
@@ -928,6 +1374,17 @@ int num_sms_tc() {
 }  // namespace
 
 // debug only (not part of the public ABI): clock64 stamps of CTA 0 of the edge kernel, [6 tiles][2 roles][16]
+// debug only: select the edge-kernel implementation for same-process A/B timing (scratch/ab_edge.py)
+extern "C" int arreau_debug_set_edge_variant(int v) {
+  if (v < 2 || v > 3) return ARREAU_ERR_BAD_SHAPE;
+  g_edge_variant = v;
+  return ARREAU_OK;
+}
+
+extern "C" int arreau_debug_set_tc_profile_tile0(unsigned t0) {
+  return (int)cudaMemcpyToSymbol(g_tc_prof_tile0, &t0, sizeof(t0));
+}
+
 extern "C" int arreau_debug_set_tc_profile(long long* buf) {
   return (int)cudaMemcpyToSymbol(g_tc_prof, &buf, sizeof(buf));
 }
@@ -978,17 +1435,29 @@ extern "C" int arreau_edge_kernels_f16(const double* dir, const double* dist, co
       !kernels_f16)
     return ARREAU_ERR_NULL;
   if (edge_capacity < 0) return ARREAU_ERR_BAD_SHAPE;
-  static bool attr_set = false;
-  if (!attr_set) {
-    cudaError_t e = cudaFuncSetAttribute(edge_kernels_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, edge::kSmemBytes);
-    if (e != cudaSuccess) return (int)e;
-    attr_set = true;
-  }
   const long long tiles = (edge_capacity + edge::kEdgesPerTile - 1) / edge::kEdgesPerTile;
   const int grid = (int)(tiles < (long long)num_sms_tc() ? tiles : (long long)num_sms_tc());
-  edge_kernels_tc_kernel<<<grid, kThreads, edge::kSmemBytes, (cudaStream_t)stream>>>(
-      dir, dist, lattice, crystal_of_atom, src, num_edges_ptr, (long long)edge_capacity, ori, (const uint8_t*)w1_img,
-      (const uint8_t*)w_img, b2, radius, (__half*)kernels_f16);
+  if (g_edge_variant == 3) {
+    static bool attr3_set = false;
+    if (!attr3_set) {
+      cudaError_t e = cudaFuncSetAttribute(edge_kernels_tc3_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, edge3::kSmemBytes);
+      if (e != cudaSuccess) return (int)e;
+      attr3_set = true;
+    }
+    edge_kernels_tc3_kernel<<<grid, edge3::kThreads3, edge3::kSmemBytes, (cudaStream_t)stream>>>(
+        dir, dist, lattice, crystal_of_atom, src, num_edges_ptr, (long long)edge_capacity, ori, (const uint8_t*)w1_img,
+        (const uint8_t*)w_img, b2, radius, (__half*)kernels_f16);
+  } else {
+    static bool attr2_set = false;
+    if (!attr2_set) {
+      cudaError_t e = cudaFuncSetAttribute(edge_kernels_tc2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, edge2::kSmemBytes);
+      if (e != cudaSuccess) return (int)e;
+      attr2_set = true;
+    }
+    edge_kernels_tc2_kernel<<<grid, kThreads, edge2::kSmemBytes, (cudaStream_t)stream>>>(
+        dir, dist, lattice, crystal_of_atom, src, num_edges_ptr, (long long)edge_capacity, ori, (const uint8_t*)w1_img,
+        (const uint8_t*)w_img, b2, radius, (__half*)kernels_f16);
+  }
   CUDA_LAUNCH_CHECK();
   return ARREAU_OK;
 }
