@@ -706,7 +706,7 @@ message_fiber_norm_fused_kernel(const __half* __restrict__ kern, const float* __
                                 const int32_t* __restrict__ row_ptr, const int32_t* __restrict__ src,
                                 const uint4* __restrict__ fk_frag, const float* __restrict__ bias,
                                 const float* __restrict__ ln_w, const float* __restrict__ ln_b, int N,
-                                __half* __restrict__ y, float* __restrict__ x2_dbg) {
+                                __half* __restrict__ y, float* __restrict__ x2_dbg, int prefetch) {
   extern __shared__ __align__(128) uint8_t fsm[];
   uint8_t* s_a = fsm;                                                            // [16 atoms][kFusedRowBytes]
   float* s_stats = reinterpret_cast<float*>(s_a + (size_t)kFusedTileBytes);      // [warps][32 lanes][16]
@@ -717,6 +717,7 @@ message_fiber_norm_fused_kernel(const __half* __restrict__ kern, const float* __
   __syncthreads();
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, g = lane >> 2, t = lane & 3;
   const int groups = (N + kFiberGroup - 1) / kFiberGroup;
+  const int e_last = max(row_ptr[N] - 1, 0);                   // for clamping the slab prefetch addresses
   for (int grp = blockIdx.x; grp < groups; grp += gridDim.x) {
     const int atom0 = grp * kFiberGroup;
     // ---------------- phase 1: gather ----------------
@@ -733,6 +734,16 @@ message_fiber_norm_fused_kernel(const __half* __restrict__ kern, const float* __
       for (int op = 0; op < kO / 2; ++op) {
         // both orientations of the pair at once: 32 independent loads per lane in flight
         const int o0 = 2 * op;
+        if (prefetch) {
+          // The slab is streamed from HBM exactly once, so each of these iterations would wait for 16 DRAM misses.  Pull
+          // the NEXT iteration's slab block into L2 now (next orientation pair of this atom, or the first pair of the
+          // warp's second atom, whose edges follow in CSR order): 8 edges x 512 B = one 128-byte line per lane, no
+          // registers held; one iteration (~3-5 K cycles) of lead time turns the misses into L2 hits.
+          const bool same_atom = op + 1 < kO / 2;
+          const int pe = min((same_atom ? e0 : e1) + (lane >> 2), e_last);
+          const char* pa = reinterpret_cast<const char*>(kern + ((size_t)pe * kO + (same_atom ? o0 + 2 : 0)) * kC) + (lane & 3) * 128;
+          asm volatile("prefetch.global.L2 [%0];" ::"l"(pa));
+        }
         float4 s0 = make_float4(0.f, 0.f, 0.f, 0.f), s1 = s0;
         const int koff0 = (((lane >> 1) ^ o0) << 3) | ((lane & 1) << 2);
         const int koff1 = (((lane >> 1) ^ (o0 + 1)) << 3) | ((lane & 1) << 2);
@@ -1496,6 +1507,12 @@ extern "C" int arreau_fiber_norm(const float* x1, int32_t x1_f16_transposed, con
   return ARREAU_OK;
 }
 
+int g_message_prefetch = 1;     // debug switch for same-process A/B (scratch/ab_message.py)
+extern "C" int arreau_debug_set_message_prefetch(int v) {
+  g_message_prefetch = v ? 1 : 0;
+  return ARREAU_OK;
+}
+
 extern "C" int arreau_message_fiber_norm_fused(const void* kernels_f16, const float* h, const int32_t* row_ptr,
                                                const int32_t* src, const void* fiber_frag, const float* conv_bias,
                                                const float* ln_w, const float* ln_b, int32_t N, void* y_f16,
@@ -1512,7 +1529,8 @@ extern "C" int arreau_message_fiber_norm_fused(const void* kernels_f16, const fl
   const int groups = (N + kFiberGroup - 1) / kFiberGroup;
   const int grid = groups < 2 * num_sms() ? groups : 2 * num_sms();
   message_fiber_norm_fused_kernel<<<grid, kFusedWarps * 32, kFusedSmem, (cudaStream_t)stream>>>(
-      (const __half*)kernels_f16, h, row_ptr, src, (const uint4*)fiber_frag, conv_bias, ln_w, ln_b, N, (__half*)y_f16, x2_debug);
+      (const __half*)kernels_f16, h, row_ptr, src, (const uint4*)fiber_frag, conv_bias, ln_w, ln_b, N, (__half*)y_f16, x2_debug,
+      g_message_prefetch);
   CUDA_LAUNCH_CHECK();
   return ARREAU_OK;
 }

@@ -100,21 +100,29 @@ class DiffusionLoss(torch.nn.Module):
         return self._engine
 
     # -- training step (diffusion_loss.py:95-110,199-274) ---------------------------------------------
-    def train_engine_for(self, net, t_emb_weights, num_atoms, device, max_cached: int = 8):
-        """One TrainEngine per batch topology (atoms per crystal), a few kept."""
+    def train_engine_for(self, net, t_emb_weights, num_atoms, device, headroom: float = 1.25):
+        """ONE capacity-based TrainEngine per (parameters, backward precision): every batch topology (atoms per crystal)
+        is bound to its buffers in place; it is rebuilt -- with `headroom` -- only when a batch exceeds the capacity
+        (the first batches of the first epoch), so a shuffled epoch does not reallocate (`self.train_engine_builds`
+        counts the builds)."""
         from ..training import TrainEngine
         flat = net.flat if getattr(net, "flat", None) is not None and net.flat.device == torch.device(device) \
             else net.flatten_parameters(device)
-        na = tuple(int(v) for v in torch.as_tensor(num_atoms).reshape(-1).tolist())
-        key = (id(flat), na, self.backward_precision)
-        te = self._train_engines.pop(key, None)
-        if te is None:
+        na = [int(v) for v in torch.as_tensor(num_atoms).reshape(-1).tolist()]
+        key = (id(flat), self.backward_precision)
+        te = self._train_engines.get(key)
+        if te is None or not te.fits(na):
+            n_cap = max(int(sum(na) * headroom), te.eng.N_cap if te is not None else 0)
+            g_cap = max(int(len(na) * headroom), te.eng.G_cap if te is not None else 0)
             fw = t_emb_weights.gaussian_fourier_proj_w if hasattr(t_emb_weights, "gaussian_fourier_proj_w") else t_emb_weights
+            self._train_engines.pop(key, None)
+            te = None                                           # free the old buffers before allocating the larger ones
             te = TrainEngine(flat, self.tables, fw, net.ori_grid, na, self.cutoff, self.max_neighbors, device=device,
-                             backward_precision=self.backward_precision)
-            while len(self._train_engines) >= max_cached:
-                self._train_engines.pop(next(iter(self._train_engines)))
-        self._train_engines[key] = te
+                             backward_precision=self.backward_precision, node_capacity=n_cap, crystal_capacity=g_cap)
+            self._train_engines[key] = te
+            self.train_engine_builds = getattr(self, "train_engine_builds", 0) + 1
+        elif tuple(na) != te.eng.topology:
+            te.set_topology(na)
         return te
 
     def compute_frac_x_error(self, pred_frac_eps_x, target_frac_eps_x, batch=None):

@@ -38,9 +38,25 @@ def _i32(a, device):
 
 
 class DenoiseEngine:
+    """Buffers are sized once for a CAPACITY (atoms, crystals, edges) and a batch topology (atoms per crystal) is bound
+    to them in place with `set_topology`: every kernel takes N / G as arguments and bounds itself, so shuffled
+    variable-size batches (training) re-use one engine without reallocating.  By default the capacity
+    is the topology given to the constructor."""
+
+    # per-atom / per-crystal buffers: name -> (leading extent kind, trailing shape, dtype)
+    _NODE_BUFS = {"frac": ((3,), torch.float64), "types": ((), torch.int64), "pos": ((3,), torch.float64),
+                  "raw_count": ((), torch.int32), "deg": ((), torch.int32), "crystal_of_atom": ((), torch.int32),
+                  "t_of_atom": ((), torch.int32), "vec": ((4, 3), torch.float32), "score": ((3,), torch.float32),
+                  "h": ((NUM_ORI, HIDDEN), torch.float32), "x1": ((NUM_ORI, HIDDEN), torch.float32),
+                  "z_frac": ((3,), torch.float64)}
+    _CRYSTAL_BUFS = {"lengths": ((3,), torch.float64), "angles": ((3,), torch.float64), "lattice": ((3, 3), torch.float64),
+                     "angle_trig": ((6,), torch.float64), "num_neighbors_image": ((), torch.int64),
+                     "len0": ((3,), torch.float32), "z_len": ((3,), torch.float64), "num_atoms": ((), torch.int64)}
+
     def __init__(self, weights: PonitaWeights, tables: DiffusionTables, fourier_w, num_atoms: Sequence[int],
                  radius: float, max_neighbors: int, precision: str = "fp32", edge_capacity: Optional[int] = None,
-                 debug: bool = False, device="cuda", pooled_readout: bool = True):
+                 debug: bool = False, device="cuda", pooled_readout: bool = True,
+                 node_capacity: Optional[int] = None, crystal_capacity: Optional[int] = None):
         if precision not in PRECISIONS:
             raise ValueError(f"precision must be one of {sorted(PRECISIONS)}")
         _lib.load()
@@ -49,47 +65,39 @@ class DenoiseEngine:
         self.precision, self.debug = precision, debug
         self.radius, self.cap = float(radius), int(max_neighbors)
         na = np.asarray(num_atoms, dtype=np.int64).reshape(-1)
-        self.G, self.N = int(na.shape[0]), int(na.sum())
         self.Z = weights.num_states
         if tables.Z != self.Z:
             raise ValueError(f"tables built for {tables.Z} atom states, weights have {self.Z}")
         dev = self.device
-        off = np.zeros(self.G + 1, dtype=np.int64)
-        np.cumsum(na, out=off[1:])
-        self.num_atoms = torch.as_tensor(na).to(dev)
-        self.atom_offset = _i32(off, dev)
-        self.crystal_of_atom = _i32(np.repeat(np.arange(self.G), na), dev)
-        f64 = lambda *s: torch.zeros(*s, dtype=torch.float64, device=dev)  # noqa: E731
-        f32 = lambda *s: torch.zeros(*s, dtype=torch.float32, device=dev)  # noqa: E731
-        i32 = lambda *s: torch.zeros(*s, dtype=torch.int32, device=dev)  # noqa: E731
-        N, G, Z = self.N, self.G, self.Z
-        # diffusion state (fp64 / i64, like the reference)
-        self.frac, self.types = f64(N, 3), torch.zeros(N, dtype=torch.int64, device=dev)
-        self.lengths, self.angles, self.lattice = f64(G, 3), f64(G, 3), f64(G, 3, 3)
-        self.angle_trig = f64(G, 6)
-        # graph scratch
-        self.pos, self.raw_count, self.deg, self.row_ptr = f64(N, 3), i32(N), i32(N), i32(N + 1)
-        self.num_neighbors_image = torch.zeros(G, dtype=torch.int64, device=dev)
-        self.overflow_flag = i32(1)
-        # network io
+        Z = self.Z
+        self.N_cap = max(int(na.sum()), int(node_capacity or 0), 1)
+        self.G_cap = max(int(na.shape[0]), int(crystal_capacity or 0), 1)
+        Nc, Gc = self.N_cap, self.G_cap
         self.F = weights.num_scalar
         self.emb = (self.F - Z - 10) // 2
-        self.x, self.vec = f32(N, self.F), f32(N, 4, 3)
-        self.logits, self.score, self.len0 = f32(N, Z), f32(N, 3), f32(G, 3)
-        self.h, self.acc, self.x1 = f32(N, NUM_ORI, HIDDEN), f32(N, Z + 6), f32(N, NUM_ORI, HIDDEN)
+        self._bufs = {}
+        z = lambda shape, dt: torch.zeros(shape, dtype=dt, device=dev)  # noqa: E731
+        for name, (tail, dt) in self._NODE_BUFS.items():
+            self._bufs[name] = ("N", z((Nc,) + tail, dt))
+        for name, (tail, dt) in self._CRYSTAL_BUFS.items():
+            self._bufs[name] = ("G", z((Gc,) + tail, dt))
+        self._bufs["x"] = ("N", z((Nc, self.F), torch.float32))
+        self._bufs["logits"] = ("N", z((Nc, Z), torch.float32))
+        self._bufs["acc"] = ("N", z((Nc, Z + 6), torch.float32))
+        self._bufs["u_type"] = ("N", z((Nc, Z), torch.float64))
+        self._bufs["row_ptr"] = ("N+1", z((Nc + 1,), torch.int32))
+        self._bufs["atom_offset"] = ("G+1", z((Gc + 1,), torch.int32))
+        self.overflow_flag = z((1,), torch.int32)
         # orientation-pooled features per layer: the fp16 path's read-outs run on these (arreau_readout_pooled)
         # (arreau_readout_pooled is specialised on Z + 6 == 96 output columns, i.e. the reference's 90 atom states;
         # any other z_table takes the per-layer read-out arreau_readout_accumulate, Z <= 100)
-        self.pool = (f32(LAYERS + 1, (N + 15) // 16, 4, HIDDEN, 16)
-                     if (self.precision == "fp16" and pooled_readout and "readout_v" in weights.t and Z + 6 == 96)
-                     else None)
+        self._pool_flat = (z(((LAYERS + 1) * ((Nc + 15) // 16) * 4 * HIDDEN * 16,), torch.float32)
+                           if (self.precision == "fp16" and pooled_readout and "readout_v" in weights.t and Z + 6 == 96)
+                           else None)
         if precision == "fp16":     # 128-row UMMA tile images (32 KB each), see arreau_message_fiber_norm
-            self.y = torch.zeros(((N * NUM_ORI + 127) // 128) * 128 * HIDDEN, device=dev, dtype=torch.float16)
+            self.y = torch.zeros(((Nc * NUM_ORI + 127) // 128) * 128 * HIDDEN, device=dev, dtype=torch.float16)
         else:
-            self.y = torch.zeros(N, NUM_ORI, HIDDEN, device=dev, dtype=torch.float32)
-        self.t_of_atom = i32(N)
-        # noise
-        self.z_len, self.z_frac, self.u_type = f64(G, 3), f64(N, 3), f64(N, Z)
+            self.y = torch.zeros(Nc * NUM_ORI * HIDDEN, device=dev, dtype=torch.float32)
         # tables
         self.d_vp_betas = tables.vp_betas.to(torch.float64).to(dev)
         self.d_ve_sigmas = tables.ve_sigmas.to(torch.float64).to(dev)
@@ -99,55 +107,113 @@ class DenoiseEngine:
         if self.d_fourier_w.numel() != self.emb:
             raise ValueError(f"time embedding has {self.d_fourier_w.numel()} frequencies, the model expects {self.emb}")
         self.edge_capacity = -1
+        self.G = self.N = 0
+        self._debug_flat = None
         self._alloc_edges(int(edge_capacity) if edge_capacity is not None else
-                          (N * self.cap if self.cap > 0 else max(1, 32 * N)))
+                          (Nc * self.cap if self.cap > 0 else max(1, 32 * Nc)))
+        self.set_topology(na)
+
+    # ------------------------------------------------------------------ topology
+    def set_topology(self, num_atoms: Sequence[int]) -> None:
+        """Bind a batch topology (atoms per crystal) to the preallocated buffers: index arrays are rewritten in place,
+        the public tensors (`frac`, `types`, `h`, `logits`, ...) become views of the first N / G rows, the argument
+        structs get the new extents.  No allocation; raises if the batch exceeds the capacity."""
+        na = np.asarray(num_atoms, dtype=np.int64).reshape(-1)
+        G, N = int(na.shape[0]), int(na.sum())
+        if N > self.N_cap or G > self.G_cap:
+            raise ValueError(f"batch of {N} atoms / {G} crystals exceeds the engine capacity {self.N_cap} / {self.G_cap}")
+        if self.cap > 0 and N * self.cap > self._edge_alloc:
+            raise ValueError("edge capacity too small for this batch")
+        self.G, self.N = G, N
+        # capped graphs: E <= N * cap for THIS batch; kernels that walk "capacity" rows (the training backward) and the
+        # layer stride of the kernel slab follow the bound batch, not the allocation
+        self._bind_edges(N * self.cap if self.cap > 0 else self._edge_alloc)
+        self.topology = tuple(int(v) for v in na)
+        off = np.zeros(G + 1, dtype=np.int64)
+        np.cumsum(na, out=off[1:])
+        ext = {"N": N, "G": G, "N+1": N + 1, "G+1": G + 1}
+        for name, (kind, buf) in self._bufs.items():
+            setattr(self, name, buf[: ext[kind]])
+        self.atom_offset.copy_(torch.as_tensor(off, dtype=torch.int32))
+        self.crystal_of_atom.copy_(torch.as_tensor(np.repeat(np.arange(G), na), dtype=torch.int32))
+        self.num_atoms.copy_(torch.as_tensor(na))
+        groups = (N + 15) // 16
+        self.pool = (self._pool_flat[: (LAYERS + 1) * groups * 4 * HIDDEN * 16].view(LAYERS + 1, groups, 4, HIDDEN, 16)
+                     if self._pool_flat is not None else None)
+        if self._debug_flat is not None:
+            node = N * NUM_ORI * HIDDEN
+            d = self._debug_flat
+            self.x1_debug = d[0][: LAYERS * node].view(LAYERS, N, NUM_ORI, HIDDEN)
+            self.x2_debug = d[1][: LAYERS * node].view(LAYERS, N, NUM_ORI, HIDDEN)
+            self.h_debug = d[2][: (LAYERS + 1) * node].view(LAYERS + 1, N, NUM_ORI, HIDDEN)
+        if hasattr(self, "_noise_sets"):      # staged-noise double buffers are bound to the old extents
+            del self._noise_sets
+        self.ws.pool = _lib.ptr(self.pool)
+        self.args.num_atoms_total, self.args.num_crystals = N, G
+        a, p = self.args, _lib.ptr
+        a.z_len, a.z_frac, a.u_type = p(self.z_len), p(self.z_frac), p(self.u_type)
 
     # ------------------------------------------------------------------ buffers
     def _alloc_edges(self, capacity: int) -> None:
-        dev, N = self.device, self.N
+        dev, Nc = self.device, self.N_cap
         capacity = max(int(capacity), 1)
-        self.edge_capacity = capacity
-        self.kernels = None            # release the old slab first: at C3 uncapped one slab is ~100 GB
+        self.edge_capacity = self._edge_alloc = capacity
+        self.kernels = self._kernels_flat = None            # release the old slab first: at C3 uncapped one slab is ~100 GB
         self.src = torch.zeros(capacity, dtype=torch.int32, device=dev)
         self.dst = torch.zeros(capacity, dtype=torch.int32, device=dev)
         self.cell = torch.zeros(capacity, dtype=torch.int8, device=dev)
         self.dist = torch.zeros(capacity, dtype=torch.float64, device=dev)
         self.dir = torch.zeros(capacity, 3, dtype=torch.float64, device=dev)
         kdt = torch.float16 if self.precision == "fp16" else torch.float32
-        self.kernels = torch.empty(LAYERS, capacity, NUM_ORI, HIDDEN, dtype=kdt, device=dev)
-        node = (N, NUM_ORI, HIDDEN)
-        if self.debug:
-            self.x1_debug = torch.zeros(LAYERS, *node, dtype=torch.float32, device=dev)
-            self.x2_debug = torch.zeros(LAYERS, *node, dtype=torch.float32, device=dev)
-            self.h_debug = torch.zeros(LAYERS + 1, *node, dtype=torch.float32, device=dev)
-        else:
+        self._kernels_flat = torch.empty(LAYERS * capacity * NUM_ORI * HIDDEN, dtype=kdt, device=dev)
+        self.kernels = self._kernels_flat.view(LAYERS, capacity, NUM_ORI, HIDDEN)
+        if self.debug and self._debug_flat is None:
+            node = Nc * NUM_ORI * HIDDEN
+            self._debug_flat = [torch.zeros(LAYERS * node, dtype=torch.float32, device=dev),
+                                torch.zeros(LAYERS * node, dtype=torch.float32, device=dev),
+                                torch.zeros((LAYERS + 1) * node, dtype=torch.float32, device=dev)]
+        if not self.debug:
             self.x1_debug = self.x2_debug = self.h_debug = None
+        B = lambda name: self._bufs[name][1]  # noqa: E731
         ws = _lib.Workspace()
-        ws.h, ws.y, ws.kernels, ws.acc = self.h.data_ptr(), self.y.data_ptr(), self.kernels.data_ptr(), self.acc.data_ptr()
-        ws.x1 = self.x1.data_ptr()
-        ws.x1_debug, ws.x2_debug, ws.h_debug = _lib.ptr(self.x1_debug), _lib.ptr(self.x2_debug), _lib.ptr(self.h_debug)
+        ws.h, ws.y, ws.kernels, ws.acc = B("h").data_ptr(), self.y.data_ptr(), self.kernels.data_ptr(), B("acc").data_ptr()
+        ws.x1 = B("x1").data_ptr()
+        if self.debug:      # the kernels index these by the CURRENT N (layer stride N * O * C): flat buffers
+            ws.x1_debug, ws.x2_debug, ws.h_debug = (t.data_ptr() for t in self._debug_flat)
+        else:
+            ws.x1_debug = ws.x2_debug = ws.h_debug = None
         ws.edge_capacity = capacity
         ws.onehot_types = None          # set by predict_scores / step: x[:, :Z] is one_hot(self.types) there
-        ws.pool = _lib.ptr(self.pool)
+        ws.pool = _lib.ptr(self._pool_flat)
         self.ws = ws
         a = _lib.StepArgs()
-        p = _lib.ptr
-        a.frac, a.types, a.lengths, a.angles, a.lattice = p(self.frac), p(self.types), p(self.lengths), p(self.angles), p(self.lattice)
-        a.angle_trig = p(self.angle_trig)
-        a.atom_offset, a.crystal_of_atom = p(self.atom_offset), p(self.crystal_of_atom)
+        p = lambda name: B(name).data_ptr()  # noqa: E731
+        a.frac, a.types, a.lengths, a.angles, a.lattice = p("frac"), p("types"), p("lengths"), p("angles"), p("lattice")
+        a.angle_trig = p("angle_trig")
+        a.atom_offset, a.crystal_of_atom = p("atom_offset"), p("crystal_of_atom")
         a.num_atoms_total, a.num_crystals = self.N, self.G
-        a.pos, a.raw_count, a.deg, a.row_ptr = p(self.pos), p(self.raw_count), p(self.deg), p(self.row_ptr)
-        a.num_neighbors_image = p(self.num_neighbors_image)
-        a.src, a.dst, a.cell, a.dist, a.dir = p(self.src), p(self.dst), p(self.cell), p(self.dist), p(self.dir)
-        a.overflow_flag = p(self.overflow_flag)
-        a.x, a.vec, a.logits, a.score, a.len0 = p(self.x), p(self.vec), p(self.logits), p(self.score), p(self.len0)
-        a.z_len, a.z_frac, a.u_type = p(self.z_len), p(self.z_frac), p(self.u_type)
-        a.vp_betas, a.fourier_w, a.ve_sigmas = p(self.d_vp_betas), p(self.d_fourier_w), p(self.d_ve_sigmas)
-        a.q_keep, a.q_to_mask = p(self.d_q_keep), p(self.d_q_to_mask)
+        a.pos, a.raw_count, a.deg, a.row_ptr = p("pos"), p("raw_count"), p("deg"), p("row_ptr")
+        a.num_neighbors_image = p("num_neighbors_image")
+        a.src, a.dst, a.cell, a.dist, a.dir = (t.data_ptr() for t in (self.src, self.dst, self.cell, self.dist, self.dir))
+        a.overflow_flag = self.overflow_flag.data_ptr()
+        a.x, a.vec, a.logits, a.score, a.len0 = p("x"), p("vec"), p("logits"), p("score"), p("len0")
+        a.z_len, a.z_frac, a.u_type = p("z_len"), p("z_frac"), p("u_type")
+        a.vp_betas, a.fourier_w, a.ve_sigmas = (t.data_ptr() for t in (self.d_vp_betas, self.d_fourier_w, self.d_ve_sigmas))
+        a.q_keep, a.q_to_mask = self.d_q_keep.data_ptr(), self.d_q_to_mask.data_ptr()
         a.onestep_keep, a.onestep_to_mask = self.tabs.onestep_keep, self.tabs.onestep_to_mask
         a.emb, a.num_steps, a.cap, a.radius = self.emb, self.tabs.T, self.cap, self.radius
         a.precision, a.update_types = PRECISIONS[self.precision], 1
         self.args = a
+        if self.N:                      # re-allocation of a bound engine (uncapped graphs): keep the topology's views
+            self.ws.pool = _lib.ptr(self.pool)
+
+    def _bind_edges(self, capacity: int) -> None:
+        """Edge capacity the kernels see (<= the allocation): slab layer stride, fill bound, backward row extent."""
+        capacity = max(int(capacity), 1)
+        assert capacity <= self._edge_alloc
+        self.edge_capacity = capacity
+        self.kernels = self._kernels_flat[: LAYERS * capacity * NUM_ORI * HIDDEN].view(LAYERS, capacity, NUM_ORI, HIDDEN)
+        self.ws.edge_capacity = capacity
 
     @property
     def stream(self) -> int:

@@ -130,12 +130,16 @@ class FusedAdam:
 
 
 class TrainEngine:
-    """One batch topology (atoms per crystal) on one GPU."""
+    """The training step's buffers on one GPU, sized for a CAPACITY (atoms, crystals) and re-bound in place to every
+    batch topology (`set_topology`): a shuffled epoch of variable-size batches (lattice_dataset.py:96-113,
+    main_diffusion.py:221-230) runs through one engine without reallocating."""
 
     def __init__(self, params: FlatParams, tables: DiffusionTables, fourier_w, ori_grid, num_atoms: Sequence[int],
-                 radius: float, max_neighbors: int, device="cuda", backward_precision: str = "fp32"):
+                 radius: float, max_neighbors: int, device="cuda", backward_precision: str = "fp32",
+                 node_capacity: Optional[int] = None, crystal_capacity: Optional[int] = None):
         """backward_precision: "fp32" (FFMA GEMMs: the parity path) or "tf32" (tensor-core GEMMs with fp32
-        accumulation in the backward pass; the forward stays fp32)."""
+        accumulation in the backward pass; the forward stays fp32).  node_capacity / crystal_capacity: room for
+        larger batches than `num_atoms` (default: exactly that topology)."""
         if backward_precision not in ("fp32", "tf32"):
             raise ValueError("backward_precision must be 'fp32' or 'tf32'")
         self.backward_precision = _lib.PRECISION_TF32 if backward_precision == "tf32" else _lib.PRECISION_FP32
@@ -145,22 +149,39 @@ class TrainEngine:
             .to(dev, torch.float32).contiguous()
         self.w = PonitaWeights.from_device_params(params.views(), self.ori)
         self.eng = DenoiseEngine(self.w, tables, fourier_w, num_atoms, radius, max_neighbors, precision="fp32",
-                                 debug=True, device=dev)
+                                 debug=True, device=dev, node_capacity=node_capacity, crystal_capacity=crystal_capacity)
         e = self.eng
-        N, G, Z = e.N, e.G, e.Z
+        N, G, Z = e.N_cap, e.G_cap, e.Z
         f64 = lambda *s: torch.zeros(*s, dtype=torch.float64, device=dev)  # noqa: E731
         f32 = lambda *s: torch.zeros(*s, dtype=torch.float32, device=dev)  # noqa: E731
-        self.frac0, self.types0, self.lattice0 = f64(N, 3), torch.zeros(N, dtype=torch.int64, device=dev), f64(G, 3, 3)
-        self.lengths0, self.angles0, self.target_eps = f64(G, 3), f64(G, 3), f64(N, 3)
-        self.eps_x, self.u, self.eps_l = f64(N, 3), f64(N, Z), f64(G, 3)
-        self.t_crystal = torch.ones(G, dtype=torch.int32, device=dev)
-        self.t_atom = torch.ones(N, dtype=torch.int32, device=dev)
-        self.terms, self.loss = f64(3 * N), f64(5)
-        self.dscore, self.dlogits, self.dlen0 = f32(N, 3), f32(N, Z), f32(G, 3)
+        self._bufs = {   # name -> (leading extent kind, capacity buffer)
+            "frac0": ("N", f64(N, 3)), "types0": ("N", torch.zeros(N, dtype=torch.int64, device=dev)),
+            "lattice0": ("G", f64(G, 3, 3)), "lengths0": ("G", f64(G, 3)), "angles0": ("G", f64(G, 3)),
+            "target_eps": ("N", f64(N, 3)), "eps_x": ("N", f64(N, 3)), "u": ("N", f64(N, Z)), "eps_l": ("G", f64(G, 3)),
+            "t_crystal": ("G", torch.ones(G, dtype=torch.int32, device=dev)),
+            "t_atom": ("N", torch.ones(N, dtype=torch.int32, device=dev)), "terms": ("3N", f64(3 * N)),
+            "dscore": ("N", f32(N, 3)), "dlogits": ("N", f32(N, Z)), "dlen0": ("G", f32(G, 3))}
+        self.loss = f64(5)
         self.d_alpha_bars = tables.vp_alpha_bars.to(torch.float32).to(dev)
         self.fold = torch.as_tensor(monomial_fold_table(), dtype=torch.int32).to(dev)
         self.mom_scratch, self.mom_out = f64(512), f64(2)
         self._bwd_ws = None
+        self._bind()
+
+    def _bind(self) -> None:
+        e = self.eng
+        ext = {"N": e.N, "G": e.G, "3N": 3 * e.N}
+        for name, (kind, buf) in self._bufs.items():
+            setattr(self, name, buf[: ext[kind]])
+
+    def fits(self, num_atoms) -> bool:
+        na = np.asarray(num_atoms, dtype=np.int64).reshape(-1)
+        return int(na.sum()) <= self.eng.N_cap and int(na.shape[0]) <= self.eng.G_cap
+
+    def set_topology(self, num_atoms) -> None:
+        """Bind the next batch's atoms-per-crystal vector (no allocation)."""
+        self.eng.set_topology(num_atoms)
+        self._bind()
 
     # ------------------------------------------------------------------ pieces (each = the mirrored reference call)
     def repack(self) -> None:

@@ -289,3 +289,66 @@ def test_tf32_backward_against_reference(device, gold, weights_npz):
     bad = {k: v for k, v in errs.items() if not v < 1e-2}
     assert not bad, bad
     print("tf32 backward worst gradient error", max(errs.values()))
+
+
+def test_capacity_engine_reuses_buffers_across_topologies(device, weights_npz):
+    """SURVEY 8f-4 / VERDICT r1 missing #2: shuffled variable-size batches run through ONE TrainEngine whose buffers are
+    re-bound in place (no reallocation), and a step on a re-bound engine is bit-identical to the same step on an
+    engine built for exactly that topology."""
+    from arreau_b200.diffusion.lattice_helpers import lattice_from_params
+    from arreau_b200.synthetic import make_training_batch
+    from arreau_b200.tables import build_tables
+    from arreau_b200.training import FlatParams, TrainEngine
+    sd = {k: weights_npz[k] for k in weights_npz.files if k not in ("ori_grid", "fourier_w")}
+    tabs = build_tables(1000, 90)
+    batches = [make_training_batch(g, seed=s) for g, s in ((14, 1), (9, 2), (16, 3), (5, 4))]
+    n_cap, g_cap = max(b.total_atoms for b in batches), max(b.num_crystals for b in batches)
+
+    def draws(cr, seed):
+        g = torch.Generator(device=device).manual_seed(seed)
+        G, N = cr.num_crystals, cr.total_atoms
+        lat0 = lattice_from_params(torch.as_tensor(cr.lengths).to(device), torch.as_tensor(cr.angles).to(device))
+        return (torch.as_tensor(cr.frac).to(device), torch.as_tensor(cr.types).to(device), lat0,
+                torch.randint(1, 1001, (G,), device=device, generator=g),
+                torch.randn(N, 3, device=device, dtype=torch.float64, generator=g),
+                torch.rand(N, 90, device=device, dtype=torch.float64, generator=g),
+                torch.randn(G, 3, device=device, dtype=torch.float64, generator=g))
+
+    p = FlatParams(164, 4, 90, device)
+    p.load_state_dict(sd)
+    shared = TrainEngine(p, tabs, weights_npz["fourier_w"], weights_npz["ori_grid"], batches[0].num_atoms, 5.0, 8,
+                         device=device, node_capacity=n_cap, crystal_capacity=g_cap)
+    ptrs = {k: v[1].data_ptr() for k, v in shared.eng._bufs.items()}
+    kernels_ptr = shared.eng.kernels.data_ptr()
+    for i, cr in enumerate(batches):
+        shared.set_topology(cr.num_atoms)
+        loss_s, grad_s = shared.loss_and_grads(*draws(cr, 10 + i))
+        loss_s, grad_s = loss_s.clone(), grad_s.clone()
+        exact = TrainEngine(p, tabs, weights_npz["fourier_w"], weights_npz["ori_grid"], cr.num_atoms, 5.0, 8, device=device)
+        loss_e, grad_e = exact.loss_and_grads(*draws(cr, 10 + i))
+        assert torch.equal(loss_s, loss_e) and torch.equal(grad_s, grad_e), i
+        assert float(grad_s.abs().max()) > 0
+    assert {k: v[1].data_ptr() for k, v in shared.eng._bufs.items()} == ptrs and shared.eng.kernels.data_ptr() == kernels_ptr
+    with pytest.raises(ValueError, match="capacity"):
+        shared.set_topology([n_cap + 1])
+
+
+def test_shuffled_epoch_builds_one_engine(device, weights_npz, tmp_path):
+    """arreau_b200.train.fit over a shuffled dataset of ragged crystals: DiffusionLoss keeps ONE capacity-based
+    TrainEngine (grown at most a couple of times while the first batches arrive), not one per batch topology."""
+    from arreau_b200.diffusion.lattice_dataset import CrystalDataset, save_dataset_npz
+    from arreau_b200.lightning_wrappers.diffusion import PONITA_DIFFUSION
+    from arreau_b200.synthetic import make_crystals
+    from arreau_b200.train import default_args, fit
+    cr = make_crystals(40, 1, 12, seed=19)
+    off = np.concatenate([[0], np.cumsum(cr.num_atoms)])
+    zs = [cr.types[off[i]:off[i + 1]] % 7 + 1 for i in range(40)]
+    frac = [cr.frac[off[i]:off[i + 1]] for i in range(40)]
+    lat = np.stack([np.diag(cr.lengths[i]) for i in range(40)])
+    ds = CrystalDataset([save_dataset_npz(str(tmp_path / "ragged"), zs, lat, frac)])
+    torch.manual_seed(0)
+    model = PONITA_DIFFUSION(default_args(lr=1e-3, epochs=3, warmup=0), ds.z_table)
+    hist = fit(model, ds, epochs=3, batch_size=7, device=device, backward_precision="tf32", log=lambda *_: None)
+    assert len(hist) == 3 and all(np.isfinite(hist))
+    dl = model.diffusion_loss
+    assert len(dl._train_engines) == 1 and dl.train_engine_builds <= 3, dl.train_engine_builds     # 18 steps, <= 3 builds
