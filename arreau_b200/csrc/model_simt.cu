@@ -720,6 +720,9 @@ message_fiber_norm_fused_kernel(const __half* __restrict__ kern, const float* __
   const int e_last = max(row_ptr[N] - 1, 0);                   // for clamping the slab prefetch addresses
   for (int grp = blockIdx.x; grp < groups; grp += gridDim.x) {
     const int atom0 = grp * kFiberGroup;
+    // first edge of this warp's first atom in the CTA's NEXT tile (slab prefetch across the tile boundary)
+    const int next_node = (grp + (int)gridDim.x) * kFiberGroup + warp * 2;
+    const int next_e0 = next_node < N ? __ldg(row_ptr + next_node) : e_last;
     // ---------------- phase 1: gather ----------------
 #pragma unroll 1
     for (int rep = 0; rep < 2; ++rep) {
@@ -736,12 +739,14 @@ message_fiber_norm_fused_kernel(const __half* __restrict__ kern, const float* __
         const int o0 = 2 * op;
         if (prefetch) {
           // The slab is streamed from HBM exactly once, so each of these iterations would wait for 16 DRAM misses.  Pull
-          // the NEXT iteration's slab block into L2 now (next orientation pair of this atom, or the first pair of the
-          // warp's second atom, whose edges follow in CSR order): 8 edges x 512 B = one 128-byte line per lane, no
-          // registers held; one iteration (~3-5 K cycles) of lead time turns the misses into L2 hits.
-          const bool same_atom = op + 1 < kO / 2;
-          const int pe = min((same_atom ? e0 : e1) + (lane >> 2), e_last);
-          const char* pa = reinterpret_cast<const char*>(kern + ((size_t)pe * kO + (same_atom ? o0 + 2 : 0)) * kC) + (lane & 3) * 128;
+          // the slab block of the iteration `prefetch` steps ahead into L2 now (a later orientation pair of this atom,
+          // the warp's second atom -- its edges follow in CSR order --, or the warp's first atom of the CTA's next
+          // tile): 8 edges x 512 B = one 128-byte line per lane, no registers held; the lead time turns the misses
+          // into L2 hits (445 -> 405 us per launch at C2 with one step of lead).
+          const int kk = rep * (kO / 2) + op + prefetch;            // iteration index within the tile (16 per warp)
+          const int pe0 = kk >= kO ? next_e0 : ((kk >> 3) == rep ? e0 : e1);
+          const int pe = min(pe0 + (lane >> 2), e_last);
+          const char* pa = reinterpret_cast<const char*>(kern + ((size_t)pe * kO + 2 * (kk & 7)) * kC) + (lane & 3) * 128;
           asm volatile("prefetch.global.L2 [%0];" ::"l"(pa));
         }
         float4 s0 = make_float4(0.f, 0.f, 0.f, 0.f), s1 = s0;
@@ -1509,7 +1514,7 @@ extern "C" int arreau_fiber_norm(const float* x1, int32_t x1_f16_transposed, con
 
 int g_message_prefetch = 1;     // debug switch for same-process A/B (scratch/ab_message.py)
 extern "C" int arreau_debug_set_message_prefetch(int v) {
-  g_message_prefetch = v ? 1 : 0;
+  g_message_prefetch = v < 0 ? 0 : (v > 4 ? 4 : v);     // 0 = off, k = slab prefetch k iterations ahead
   return ARREAU_OK;
 }
 

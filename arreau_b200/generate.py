@@ -10,6 +10,7 @@ from __future__ import annotations
 
 import argparse
 import os
+import time
 from typing import Optional
 
 import numpy as np
@@ -26,18 +27,22 @@ OUT_DIR = "out"
 def generate_n_crystals(model, num_crystals: int, num_atoms_per_sample: int,
                         use_constant_atomic_symbols: Optional[list] = None, num_crystals_per_batch: int = 1024,
                         device="cuda", device_noise: bool = True, seed: int = 0, out_path: Optional[str] = None,
-                        group=None) -> SampleResult:
+                        group=None, timings: Optional[dict] = None) -> SampleResult:
     """main_diffusion_generate.py:52-94.  With torch.distributed initialised the crystals are sharded over the ranks;
-    every rank returns the full gathered result and rank 0 writes `out_path`."""
+    every rank returns the full gathered result and rank 0 writes `out_path`.  `timings` (optional dict) receives this
+    rank's wall-clock seconds per phase: `sample` (list, one per batch), `gather`, `write`."""
     rank = dist.get_rank(group) if dist.is_initialized() else 0
     world = dist.get_world_size(group) if dist.is_initialized() else 1
     lo, hi = shard_range(num_crystals, rank, world)
     parts = []
+    t_batches = []
     for b0 in range(lo, hi, num_crystals_per_batch):
         nb = min(num_crystals_per_batch, hi - b0)
+        t0 = time.perf_counter()
         parts.append(model.sample(num_atoms_per_sample=num_atoms_per_sample, num_samples_in_batch=nb,
                                   use_constant_atomic_symbols=use_constant_atomic_symbols, device=device,
                                   device_noise=device_noise, seed=seed + b0))
+        t_batches.append(time.perf_counter() - t0)      # sample() ends with the device->host copy of the result
     n_local = hi - lo
     if parts:
         local = SampleResult(frac_x=np.concatenate([p.frac_x for p in parts]),
@@ -48,9 +53,13 @@ def generate_n_crystals(model, num_crystals: int, num_atoms_per_sample: int,
     else:
         local = SampleResult(frac_x=np.zeros((0, 3)), atomic_numbers=np.zeros(0, dtype=np.int64), lattice=np.zeros((0, 3, 3)),
                              num_atoms=np.zeros(0, dtype=np.int64), idx_start=np.zeros(0, dtype=np.int64))
+    t0 = time.perf_counter()
     result = gather_sample_results(local, group=group, device=torch.device(device) if world > 1 else None)
+    t1 = time.perf_counter()
     if out_path and rank == 0:
         save_sample_results_to_hdf5(result, out_path)
+    if timings is not None:
+        timings.update(sample=t_batches, gather=t1 - t0, write=time.perf_counter() - t1)
     return result
 
 

@@ -34,15 +34,15 @@ def run(l, y):
 
 
 ys = {}
-for v in (0, 1):
+for v in (0, 1, 2, 3):
     lib.arreau_debug_set_message_prefetch(v)
     ys[v] = torch.zeros_like(eng.y)
     run(2, ys[v])
 torch.cuda.synchronize()
-print("bitwise equal:", torch.equal(ys[0].view(torch.int16), ys[1].view(torch.int16)), "E/N", eng.num_edges() / eng.N)
-times = {0: [], 1: []}
+print("bitwise equal:", all(torch.equal(ys[0].view(torch.int16), ys[v].view(torch.int16)) for v in (1, 2, 3)), "E/N", eng.num_edges() / eng.N)
+times = {0: [], 1: [], 2: [], 3: []}
 for rep in range(7):
-    for v in (0, 1):
+    for v in (0, 1, 2, 3):
         lib.arreau_debug_set_message_prefetch(v)
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record()
@@ -55,7 +55,7 @@ for rep in range(7):
             times[v].append(e0.elapsed_time(e1) * 1e3 / 20)
 E, N = eng.num_edges(), eng.N
 nbytes = E * 16 * 128 * 2 + 4 * N * 16 * 128 + 12 * E + 2 * N * 16 * 128
-for v in (0, 1):
+for v in (0, 1, 2, 3):
     t = float(np.median(times[v]))
     print(f"prefetch={v}: {t:.1f} us per launch, {nbytes / t / 1e3:.0f} GB/s algorithmic; all {np.round(times[v], 1).tolist()}")
 lib.arreau_debug_set_message_prefetch(1)

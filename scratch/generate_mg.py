@@ -33,7 +33,9 @@ torch.cuda.synchronize()
 if world > 1:
     dist.barrier()
 t0 = time.perf_counter()
-res = generate_n_crystals(m, total, n, None, num_crystals_per_batch=1024, device=dev, out_path="gpurun_out/crystals_mg.h5")
+tm = {}
+res = generate_n_crystals(m, total, n, None, num_crystals_per_batch=1024, device=dev, out_path="gpurun_out/crystals_mg.h5",
+                          timings=tm)
 torch.cuda.synchronize()
 if world > 1:
     dist.barrier()
@@ -41,9 +43,11 @@ dt = time.perf_counter() - t0
 if local == 0:
     ok = bool(res.num_atoms.shape[0] == total and np.isfinite(res.frac_x).all() and np.isfinite(res.lattice).all()
               and (res.frac_x >= 0).all() and (res.frac_x < 1).all())
-    print(json.dumps({"workload": "C4 slice: generate_n_crystals, T=1000, 40 atoms, cap 8, fp16 tensor path",
+    print(json.dumps({"workload": "C4: generate_n_crystals, T=1000, 40 atoms, cap 8, fp16 tensor path",
                       "n_gpus": world, "crystals": total, "crystals_per_gpu": per_gpu, "seconds": dt,
                       "crystals_per_sec": total / dt, "gathered_ok": ok, "atoms": int(res.frac_x.shape[0]),
+                      "rank0_seconds": {"sample_batches": [round(x, 3) for x in tm["sample"]], "gather": round(tm["gather"], 4),
+                                        "write_file": round(tm["write"], 4)},
                       "unique_types": int(np.unique(res.atomic_numbers).size)}))
     for f in ("gpurun_out/crystals_mg.h5", "gpurun_out/crystals_mg.npz"):
         if os.path.exists(f):
