@@ -18,6 +18,7 @@
 // The forward pass of a training step is the ordinary fp32 forward (arreau_ponita_forward) run with its
 // per-layer buffers kept (h, x1, x2 of every layer and the per-layer spatial kernels).
 #include "common.cuh"
+#include "tc_common.cuh"
 
 namespace {
 
@@ -266,6 +267,206 @@ sgemm_tf32_kernel(const float* __restrict__ A, long long lda, const float* __res
     }
 }
 
+// ================================================================================================
+// tcgen05 variant of the same GEMM (ARREAU_PRECISION_TF32 on sm_100a): kind::tf32 UMMA, fp32 accumulation in TMEM.
+//   * one 128 x 128 output tile per CTA (grid as above), K in slabs of 32 (one 128-byte swizzle row of fp32);
+//   * operands go global -> registers -> shared memory (rounded to TF32 with cvt.rna on the way, as the mma.sync
+//     version did) straight into the layout the UMMA descriptor reads, WITHOUT transposing:
+//       K-contiguous storage  X[x][k]  -> canonical K-major  SWIZZLE_128B tile: row x = 128 B, 8-row groups 1 KB apart
+//       MN-contiguous storage X[k][x]  -> canonical MN-major tile in the one layout tcgen05 accepts for 32-bit MN-major
+//                                         operands, SWIZZLE_128B_BASE32B: atom = 32 x-elements (128 B) x 4 k, the 32-byte
+//                                         chunk c of k-row j at chunk position c ^ j; 4 atoms along x (LBO = 512 B),
+//                                         8 along k (SBO = 2 KB); a_major / b_major = 1
+//     so the weight-gradient GEMMs (both operands row-major over the reduced rows) need no transposed copies either;
+//   * 3-stage ring of 32 KB stages, all 8 warps load (next slab's global loads in flight under the current slab's
+//     stores and the barrier), warp 0 issues the slab's four 128x128x8 MMAs warp-uniformly with one elected lane and
+//     commits the stage's "empty" barrier; two CTAs per SM overlap one's loads with the other's MMAs;
+//   * epilogue: tcgen05.ld, then alpha / bias / accumulate or the split-K partial tile as in the kernels above.
+// Requirements as above (K % 4, pitches % 4, 16-byte aligned pointers); M, N arbitrary (zero-filled tiles), N % 4 == 0.
+// ================================================================================================
+namespace tcg {
+constexpr int kStages = 3;
+constexpr int kSlab = 32;                        // K per stage: one 128-byte row of fp32
+constexpr int kOperandBytes = 128 * 128;         // 128 (M or N) x 32 K x 4 B
+constexpr int kStageBytes = 2 * kOperandBytes;
+constexpr int kSmemBytes = kStages * kStageBytes + 1024 + 128;
+__host__ __device__ constexpr uint32_t idesc_tf32(bool a_mn, bool b_mn) {
+  // c_format F32 (bit 4), a_format / b_format TF32 = 2 (bits 7.., 10..), a_major / b_major (bits 15, 16: 1 = MN-major),
+  // N >> 3 at bit 17, M >> 4 at bit 24
+  return (1u << 4) | (2u << 7) | (2u << 10) | ((a_mn ? 1u : 0u) << 15) | ((b_mn ? 1u : 0u) << 16) |
+         ((uint32_t)(128 >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
+}
+__device__ __forceinline__ void umma_tf32_e(uint32_t tmem_d, uint32_t a_lo, uint32_t a_hi, uint32_t b_lo, uint32_t b_hi,
+                                            uint32_t idesc, uint32_t elected, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p, e;\n\t.reg .b64 da, db;\n\t"
+      "mov.b64 da, {%1, %2};\n\tmov.b64 db, {%3, %4};\n\t"
+      "setp.ne.u32 e, %6, 0;\n\t"
+      "setp.ne.u32 p, %7, 0;\n\t"
+      "@e tcgen05.mma.cta_group::1.kind::tf32 [%0], da, db, %5, p;\n\t}"
+      ::"r"(tmem_d), "r"(a_lo), "r"(a_hi), "r"(b_lo), "r"(b_hi), "r"(idesc), "r"(elected), "r"(accumulate)
+      : "memory");
+}
+}  // namespace tcg
+
+int g_tc_mn_lbo = 512, g_tc_mn_sbo = 2048;       // MN-major descriptor strides (bytes); debug-settable
+
+template <bool KCONTIG>
+__device__ __forceinline__ void tc_fetch(const float* __restrict__ X, long long ld, int x0, int xext, long long k0,
+                                         long long kend, int tid, float4 (&r)[4]) {
+#pragma unroll
+  for (int u = 0; u < 4; ++u) {
+    const int v = tid + u * kGT;
+    r[u] = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (KCONTIG) {                       // X[x][k]: v -> row x = v >> 3, 16-byte chunk (4 k) = v & 7
+      const int x = x0 + (v >> 3);
+      const long long k = k0 + (v & 7) * 4;
+      if (x < xext && k < kend) r[u] = __ldg(reinterpret_cast<const float4*>(X + (long long)x * ld + k));
+    } else {                             // X[k][x]: v -> k = v >> 5, 4 x-elements = v & 31
+      const long long k = k0 + (v >> 5);
+      const int x = x0 + (v & 31) * 4;
+      if (k < kend && x < xext) r[u] = __ldg(reinterpret_cast<const float4*>(X + k * ld + x));
+    }
+  }
+}
+
+template <bool KCONTIG>
+__device__ __forceinline__ void tc_stage(uint8_t* __restrict__ tile, int tid, const float4 (&r)[4]) {
+#pragma unroll
+  for (int u = 0; u < 4; ++u) {
+    const int v = tid + u * kGT;
+    const float4 q = make_float4(to_tf32(r[u].x), to_tf32(r[u].y), to_tf32(r[u].z), to_tf32(r[u].w));
+    uint32_t off;
+    if (KCONTIG) {
+      const int row = v >> 3, chunk = v & 7;
+      off = (uint32_t)(row * 128 + ((chunk ^ (row & 7)) << 4));
+    } else {
+      const int kk = v >> 5, x4 = v & 31, j = kk & 3;
+      off = (uint32_t)((kk >> 2) * 2048 + (x4 >> 3) * 512 + j * 128 + (((((x4 & 7) >> 1) ^ j) << 5) | ((x4 & 1) << 4)));
+    }
+    *reinterpret_cast<float4*>(tile + off) = q;
+  }
+}
+
+template <bool AK, bool BK>
+__global__ void __launch_bounds__(kGT, 2)
+sgemm_tc_kernel(const float* __restrict__ A, long long lda, const float* __restrict__ B, long long ldb, float* __restrict__ C,
+                long long ldc, int M, int N, long long K, long long k_per_split, float alpha,
+                const float* __restrict__ bias, int accumulate, float* __restrict__ partial, int mn_lbo, int mn_sbo) {
+  using namespace tc;
+  extern __shared__ __align__(1024) uint8_t gsm_raw[];
+  const uint32_t base = (smem_u32(gsm_raw) + 1023u) & ~1023u;
+  uint8_t* const sm = gsm_raw + (base - smem_u32(gsm_raw));
+  uint64_t* const bar_empty = reinterpret_cast<uint64_t*>(sm + tcg::kStages * tcg::kStageBytes);   // [kStages]
+  uint64_t* const bar_done = bar_empty + tcg::kStages;
+  uint32_t* const tmem_slot = reinterpret_cast<uint32_t*>(bar_done + 1);
+  const int tid = threadIdx.x, warp = __shfl_sync(0xffffffffu, tid >> 5, 0), lane = tid & 31;
+  const int m0 = blockIdx.y * kBM, n0 = blockIdx.x * kBN;
+  const long long kbeg = (long long)blockIdx.z * k_per_split;
+  const long long kend = (kbeg + k_per_split < K) ? kbeg + k_per_split : K;
+  const int nslabs = kbeg < kend ? (int)((kend - kbeg + tcg::kSlab - 1) / tcg::kSlab) : 0;
+  if (tid == 0) {
+    for (int i = 0; i < tcg::kStages; ++i) mbar_init(&bar_empty[i], 1);
+    mbar_init(bar_done, 1);
+    fence_barrier_init();
+  }
+  if (warp == 1) tmem_alloc(tmem_slot, 128);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem = *tmem_slot;
+
+  const uint32_t el = warp == 0 ? elect_one() : 0u;
+  constexpr uint32_t kIdesc = tcg::idesc_tf32(!AK, !BK);
+  // descriptor words: K-major: LBO unused (1), SBO = 1 KB (8-row groups), SWIZZLE_128B; MN-major: LBO = stride between the
+  // 32-element atoms along M/N, SBO = stride between the 4-k atoms, SWIZZLE_128B_BASE32B; version 1
+  const uint32_t hi_k = (uint32_t)(1024 >> 4) | (1u << 14) | (2u << 29);
+  const uint32_t hi_mn = (uint32_t)(mn_sbo >> 4) | (1u << 14) | (1u << 29);      // layout type 1 = SWIZZLE_128B_BASE32B
+  const uint32_t a_hi = AK ? hi_k : hi_mn, b_hi = BK ? hi_k : hi_mn;
+  const uint32_t a_lbo = AK ? (1u << 16) : ((uint32_t)(mn_lbo >> 4) << 16), b_lbo = BK ? (1u << 16) : ((uint32_t)(mn_lbo >> 4) << 16);
+  constexpr uint32_t a_kstep = AK ? 2u : (4096u >> 4), b_kstep = BK ? 2u : (4096u >> 4);   // +8 K per MMA
+
+  float4 ra[4], rb[4];
+  if (nslabs > 0) {
+    tc_fetch<AK>(A, lda, m0, M, kbeg, kend, tid, ra);
+    tc_fetch<BK>(B, ldb, n0, N, kbeg, kend, tid, rb);
+  }
+  for (int s = 0; s < nslabs; ++s) {
+    const int stage = s % tcg::kStages;
+    if (s >= tcg::kStages) mbar_wait(&bar_empty[stage], (uint32_t)((s / tcg::kStages - 1) & 1));   // its MMAs have read it
+    uint8_t* const ta = sm + stage * tcg::kStageBytes;
+    uint8_t* const tb = ta + tcg::kOperandBytes;
+    tc_stage<AK>(ta, tid, ra);
+    tc_stage<BK>(tb, tid, rb);
+    fence_proxy_async();                        // generic-proxy stores -> visible to the UMMA operand reads
+    if (s + 1 < nslabs) {                       // next slab's loads fly under the barrier and the MMA issue
+      const long long k0 = kbeg + (long long)(s + 1) * tcg::kSlab;
+      tc_fetch<AK>(A, lda, m0, M, k0, kend, tid, ra);
+      tc_fetch<BK>(B, ldb, n0, N, k0, kend, tid, rb);
+    }
+    __syncthreads();
+    if (warp == 0) {
+      tc_fence_after();
+      const uint32_t a_lo = ((smem_u32(ta) & 0x3FFFFu) >> 4) | a_lbo, b_lo = ((smem_u32(tb) & 0x3FFFFu) >> 4) | b_lbo;
+#pragma unroll
+      for (int ki = 0; ki < 4; ++ki)
+        tcg::umma_tf32_e(tmem, a_lo + ki * a_kstep, a_hi, b_lo + ki * b_kstep, b_hi, kIdesc, el, (s > 0 || ki > 0) ? 1u : 0u);
+      umma_commit_e(smem_u32(&bar_empty[stage]), el);
+      if (s + 1 == nslabs) umma_commit_e(smem_u32(bar_done), el);
+    }
+  }
+  // ---- epilogue: warp = (lane quarter q: rows 32 q .. +31, column half: 64 columns) ----
+  const int q = warp & 3, half = warp >> 2;
+  const int m = m0 + q * 32 + lane;
+  const bool split = gridDim.z > 1;
+  float* out = split ? partial + (size_t)blockIdx.z * M * N : C;
+  const long long ldo = split ? (long long)N : ldc;
+  if (nslabs > 0) {
+    mbar_wait(bar_done, 0);
+    tc_fence_after();
+  }
+#pragma unroll
+  for (int part = 0; part < 4; ++part) {
+    uint32_t r[16];
+    if (nslabs > 0) {
+      tmem_ld16(tmem + ((uint32_t)(q * 32) << 16) + half * 64 + part * 16, r);
+    } else {
+#pragma unroll
+      for (int i = 0; i < 16; ++i) r[i] = 0u;
+    }
+    if (m < M) {
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const int n = n0 + half * 64 + part * 16 + j * 4;
+        if (n >= N) continue;
+        float4 v = make_float4(__uint_as_float(r[4 * j]), __uint_as_float(r[4 * j + 1]), __uint_as_float(r[4 * j + 2]),
+                               __uint_as_float(r[4 * j + 3]));
+        float* p = out + (long long)m * ldo + n;
+        if (!split) {
+          v.x *= alpha; v.y *= alpha; v.z *= alpha; v.w *= alpha;
+          if (bias) {
+            const float4 bb = *reinterpret_cast<const float4*>(bias + n);
+            v.x += bb.x; v.y += bb.y; v.z += bb.z; v.w += bb.w;
+          }
+          if (accumulate) {
+            const float4 c = *reinterpret_cast<const float4*>(p);
+            v.x += c.x; v.y += c.y; v.z += c.z; v.w += c.w;
+          }
+        }
+        *reinterpret_cast<float4*>(p) = v;
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc(tmem, 128);
+  }
+}
+
+int g_tf32_legacy = 0;       // debug: 1 = the mma.sync TF32 kernel instead of the tcgen05 one (same-process A/B)
+
 // second stage of every split reduction: out[i] (=|+=) alpha * sum_s partial[s][i] (fixed order)
 __global__ void reduce_partials_kernel(const float* __restrict__ partial, int splits, long long n, long long ldo, int ncols,
                                        float alpha, int accumulate, float* __restrict__ out) {
@@ -300,11 +501,21 @@ int gemm(const Gemm& g, const float* A, long long lda, const float* B, long long
     while (splits > 1 && (size_t)splits * M * N > g.partial_floats) --splits;
   }
   long long kps = (K + splits - 1) / splits;
-  kps = (kps + kBK - 1) / kBK * kBK;
+  kps = (kps + 31) / 32 * 32;             // whole K slabs of both the SIMT (16) and the tcgen05 (32) kernels
   splits = (int)((K + kps - 1) / kps);
   if (splits < 1) splits = 1;
   dim3 grid((N + kBN - 1) / kBN, (M + kBM - 1) / kBM, splits);
-  if (g.tf32)
+  if (g.tf32 && !g_tf32_legacy) {
+    static bool attr_set = false;       // one flag per template instance
+    if (!attr_set) {
+      cudaError_t e = cudaFuncSetAttribute(sgemm_tc_kernel<AK, BK>, cudaFuncAttributeMaxDynamicSharedMemorySize, tcg::kSmemBytes);
+      if (e != cudaSuccess) return (int)e;
+      attr_set = true;
+    }
+    sgemm_tc_kernel<AK, BK><<<grid, kGT, tcg::kSmemBytes, g.s>>>(A, lda, B, ldb, C, ldc, M, N, K, kps, alpha,
+                                                                   splits == 1 ? bias : nullptr, accumulate ? 1 : 0,
+                                                                   g.partial, g_tc_mn_lbo, g_tc_mn_sbo);
+  } else if (g.tf32)
     sgemm_tf32_kernel<AK, BK><<<grid, kGT, 0, g.s>>>(A, lda, B, ldb, C, ldc, M, N, K, kps, alpha,
                                                      splits == 1 ? bias : nullptr, accumulate ? 1 : 0, g.partial);
   else
@@ -841,6 +1052,14 @@ extern "C" int arreau_moments(const float* x, const float* sub_cols, int64_t n, 
   CUDA_LAUNCH_CHECK();
   moments_finish_kernel<<<1, 32, 0, (cudaStream_t)stream>>>(scratch, blocks, out);
   CUDA_LAUNCH_CHECK();
+  return ARREAU_OK;
+}
+
+// debug only (not part of the public ABI): TF32 GEMM implementation switch and MN-major descriptor strides
+extern "C" int arreau_debug_set_tf32_gemm(int legacy, int mn_lbo, int mn_sbo) {
+  g_tf32_legacy = legacy ? 1 : 0;
+  if (mn_lbo > 0) g_tc_mn_lbo = mn_lbo;
+  if (mn_sbo > 0) g_tc_mn_sbo = mn_sbo;
   return ARREAU_OK;
 }
 
