@@ -52,6 +52,99 @@ __device__ __forceinline__ double lane_d2(const double* __restrict__ pj, const d
   return __dadd_rn(__dadd_rn(__dmul_rn(dx, dx), __dmul_rn(dy, dy)), __dmul_rn(dz, dz));
 }
 
+// Image culling.  A candidate (j, cell c) can only be in range if, along every lattice axis a, the fractional
+// displacement f_j[a] + c[a] - f_i[a] is at most r * |b_a| in magnitude (b_a = the reciprocal vector of axis a: the
+// projection of a Cartesian vector of length <= r on b_a cannot exceed that).  With [lo, hi] the fractional bounding box
+// of the crystal's atoms, a whole image cell is therefore skipped when its shifted box misses that window on one axis
+// (a conservative, slightly widened test: the exact fp64 distance test below still decides every surviving candidate,
+// so the edge list is unchanged).  The A surviving images of a receiver are dealt to the lanes in ascending cell
+// order, floor(32 / A) senders at a time, which keeps the reference's (j, cell) candidate order and cuts the walk from
+// n to n / floor(32 / A) iterations: A is ~7 of 27 in a 15 A cell at r = 7 A, ~9 in a 9 A cell at r = 5 A, and 27 in the
+// ~1 A cells of the sampler's first steps.  Used for crystals of at least kCullMinAtoms atoms (measured at 40 atoms per
+// crystal: the box pass costs more than the shorter walk saves, 0.35 vs 0.27 ms per step).  The culled walk is a SEPARATE
+// template instantiation of both kernels (its per-lane (image, sender) bookkeeping costs ~20 registers, which slowed the
+// plain walk of small cells when both lived in one kernel, scratch/attic/README.md); the launchers pick it when the
+// batch averages >= kCullMinAtoms atoms per crystal (C3: 200-atom supercells, 1.28 -> 0.82 ms per step at 15 A cells).
+constexpr int kCullMinAtoms = 64;
+struct LaneImage {
+  int img;      // this lane's image cell (0..26)
+  int jj;       // this lane's sender within a batch of q
+  int q;        // senders per iteration
+  bool live;
+};
+template <bool kCull>
+__device__ __forceinline__ LaneImage active_images(const double* __restrict__ lat, const double* __restrict__ pos, int start,
+                                                   int n, double pix, double piy, double piz, double r2, int lane) {
+  if constexpr (!kCull) {      // the plain walk: lane = image cell, one sender per iteration (compile-time constants)
+    LaneImage li;
+    li.img = lane < 27 ? lane : 0;
+    li.jj = 0;
+    li.q = 1;
+    li.live = lane < 27;
+    return li;
+  }
+  const double ax = lat[0], ay = lat[1], az = lat[2], bx = lat[3], by = lat[4], bz = lat[5], cx = lat[6], cy = lat[7], cz = lat[8];
+  // reciprocal vectors (rows): f[a] = pos . rec[a]
+  double rec[3][3] = {{by * cz - bz * cy, bz * cx - bx * cz, bx * cy - by * cx},
+                      {cy * az - cz * ay, cz * ax - cx * az, cx * ay - cy * ax},
+                      {ay * bz - az * by, az * bx - ax * bz, ax * by - ay * bx}};
+  const double det = ax * rec[0][0] + ay * rec[0][1] + az * rec[0][2];
+  unsigned mask = 0x07ffffffu;
+  // small crystals: the box pass below (n / 32 iterations plus the reductions) costs as much as the walk it could save
+  if (n >= kCullMinAtoms && isfinite(det) && fabs(det) > 1e-200) {
+    const double inv = 1.0 / det, r = sqrt(r2);
+    double tol[3], lo[3], hi[3], fi[3];
+#pragma unroll
+    for (int a = 0; a < 3; ++a) {
+#pragma unroll
+      for (int d = 0; d < 3; ++d) rec[a][d] *= inv;
+      tol[a] = r * sqrt(rec[a][0] * rec[a][0] + rec[a][1] * rec[a][1] + rec[a][2] * rec[a][2]) * (1.0 + 1e-6) + 1e-9;
+      fi[a] = pix * rec[a][0] + piy * rec[a][1] + piz * rec[a][2];
+      lo[a] = INFINITY;
+      hi[a] = -INFINITY;
+    }
+    for (int j = lane; j < n; j += 32) {
+      const double* pj = pos + 3 * (size_t)(start + j);
+      const double x = pj[0], y = pj[1], z = pj[2];
+#pragma unroll
+      for (int a = 0; a < 3; ++a) {
+        const double f = x * rec[a][0] + y * rec[a][1] + z * rec[a][2];
+        lo[a] = fmin(lo[a], f);
+        hi[a] = fmax(hi[a], f);
+      }
+    }
+#pragma unroll
+    for (int a = 0; a < 3; ++a)
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) {
+        lo[a] = fmin(lo[a], __shfl_xor_sync(0xffffffffu, lo[a], o));
+        hi[a] = fmax(hi[a], __shfl_xor_sync(0xffffffffu, hi[a], o));
+      }
+    bool ok = lane < 27;
+    if (ok) {
+      int c[3];
+      cell_of(lane, c[0], c[1], c[2]);
+      bool sane = true, in = true;
+#pragma unroll
+      for (int a = 0; a < 3; ++a) {
+        const double w = tol[a] + 1e-6 * (fabs(lo[a]) + fabs(hi[a]) + fabs(fi[a]));     // rounding of the projections
+        sane = sane && isfinite(w);
+        in = in && (lo[a] + c[a] - fi[a] <= w) && (hi[a] + c[a] - fi[a] >= -w);
+      }
+      ok = in || !sane;                                                                 // degenerate cell: keep every image
+    }
+    mask = __ballot_sync(0xffffffffu, ok) & 0x07ffffffu;
+    mask |= 1u << 13;                                                                   // the home cell always stays
+  }
+  LaneImage li;
+  const int A = __popc(mask);
+  li.q = 32 / A;
+  li.jj = lane / A;
+  li.live = lane < li.q * A;
+  li.img = li.live ? (int)__fns(mask, 0, lane - li.jj * A + 1) : 0;
+  return li;
+}
+
 // Log-spaced distance bins (4 per octave of d2, from the self-edge threshold 1e-4 up): monotone in d2, so "all
 // candidates in bins <= b" is a superset of the cap nearest as soon as those bins hold >= cap candidates.  The count
 // pass histograms the in-range candidates per receiver and leaves that bin in the top byte of raw_count; the fill pass
@@ -68,6 +161,7 @@ __device__ __forceinline__ bool cand_pass(double d2, double r2, int remove_self)
   return (d2 <= r2) && (!remove_self || d2 > 0.0001);   // helpers:432-436
 }
 
+template <bool kCull>
 __global__ void __launch_bounds__(kWarpsPerBlock * 32)
 graph_count_kernel(const double* __restrict__ pos, const double* __restrict__ lattice,
                    const int32_t* __restrict__ atom_offset, const int32_t* __restrict__ crystal_of_atom,
@@ -82,17 +176,19 @@ graph_count_kernel(const double* __restrict__ pos, const double* __restrict__ la
   for (int b = 0; b < kBins / 32; ++b) hist[b * 32 + lane] = 0;
   const int g = crystal_of_atom[i];
   const int start = atom_offset[g], n = atom_offset[g + 1] - start;
-  double off[3];
-  lane_offset(lattice + 9 * (size_t)g, lane, off);
   const double pix = pos[3 * (size_t)i], piy = pos[3 * (size_t)i + 1], piz = pos[3 * (size_t)i + 2];
+  const LaneImage li = active_images<kCull>(lattice + 9 * (size_t)g, pos, start, n, pix, piy, piz, r2, lane);
+  double off[3];
+  lane_offset(lattice + 9 * (size_t)g, li.img, off);
   __syncwarp();
   int cnt = 0;
-  const bool live = lane < 27;
   const bool want_hist = cap > 0;
-  for (int j = 0; j < n; ++j) {
+  for (int j0 = 0; j0 < n; j0 += li.q) {
+    const int j = j0 + li.jj;
+    const bool valid = li.live && j < n;
     double dx, dy, dz;
-    const double d2 = lane_d2(pos + 3 * (size_t)(start + j), off, pix, piy, piz, dx, dy, dz);
-    if (live && cand_pass(d2, r2, remove_self)) {
+    const double d2 = lane_d2(pos + 3 * (size_t)(start + (valid ? j : 0)), off, pix, piy, piz, dx, dy, dz);
+    if (valid && cand_pass(d2, r2, remove_self)) {
       ++cnt;
       if (want_hist) atomicAdd(&hist[dist_bin(d2)], 1);
     }
@@ -228,6 +324,7 @@ __device__ __forceinline__ int select_topk(double* sd2, int* sc, unsigned* smask
   return out;
 }
 
+template <bool kCull>
 __global__ void __launch_bounds__(kWarpsPerBlock * 32)
 graph_fill_kernel(const double* __restrict__ pos, const double* __restrict__ lattice,
                   const int32_t* __restrict__ atom_offset, const int32_t* __restrict__ crystal_of_atom, int N,
@@ -244,11 +341,11 @@ graph_fill_kernel(const double* __restrict__ pos, const double* __restrict__ lat
   if (i >= N) return;
   const int g = crystal_of_atom[i];
   const int start = atom_offset[g], n = atom_offset[g + 1] - start;
-  double off[3];
-  lane_offset(lattice + 9 * (size_t)g, lane, off);
   const double pix = pos[3 * (size_t)i], piy = pos[3 * (size_t)i + 1], piz = pos[3 * (size_t)i + 2];
+  const LaneImage li = active_images<kCull>(lattice + 9 * (size_t)g, pos, start, n, pix, piy, piz, r2, lane);
+  double off[3];
+  lane_offset(lattice + 9 * (size_t)g, li.img, off);
   const long long base = row_ptr[i];
-  const bool live = lane < 27;
   const int rc = raw_count[i];
   const bool select = cap > 0 && (rc & kCountMask) > cap;
   const int bin_max = rc >> 24;          // graph_count: the cap nearest all lie in distance bins <= bin_max
@@ -281,12 +378,14 @@ graph_fill_kernel(const double* __restrict__ pos, const double* __restrict__ lat
 
   if (!select) {
     int written = 0;
-    for (int j = 0; j < n; ++j) {
+    for (int j0 = 0; j0 < n; j0 += li.q) {
+      const int j = j0 + li.jj;
+      const bool valid = li.live && j < n;
       double dx, dy, dz;
-      const double d2 = lane_d2(pos + 3 * (size_t)(start + j), off, pix, piy, piz, dx, dy, dz);
-      const bool ok = live && cand_pass(d2, r2, remove_self);
+      const double d2 = lane_d2(pos + 3 * (size_t)(start + (valid ? j : 0)), off, pix, piy, piz, dx, dy, dz);
+      const bool ok = valid && cand_pass(d2, r2, remove_self);
       const unsigned bal = __ballot_sync(0xffffffffu, ok);
-      if (ok) emit(base + written + __popc(bal & ((1u << lane) - 1u)), 27 * j + lane, d2, dx, dy, dz);
+      if (ok) emit(base + written + __popc(bal & ((1u << lane) - 1u)), 27 * j + li.img, d2, dx, dy, dz);
       written += __popc(bal);
     }
     return;
@@ -303,7 +402,7 @@ graph_fill_kernel(const double* __restrict__ pos, const double* __restrict__ lat
   int thr_c = 0x7fffffff;
   // compact as soon as cap + 64 candidates are buffered: the selection pass is O(m^2 / 32) per lane
   const int sel_limit = min(kSelBuf, ((cap + 31) / 32) * 32 + 64);
-  for (int j = 0; j < n; ++j) {
+  for (int j0 = 0; j0 < n; j0 += li.q) {
     if (m + 32 > sel_limit) {
       m = select_topk(sd2, sc, s_mask[warp], m, cap, lane);
       // threshold = the largest kept key
@@ -320,10 +419,12 @@ graph_fill_kernel(const double* __restrict__ pos, const double* __restrict__ lat
       thr_d2 = kd;
       thr_c = kc;
     }
-    const int c = 27 * j + lane;
+    const int j = j0 + li.jj;
+    const bool valid = li.live && j < n;
+    const int c = 27 * j + li.img;
     double dx, dy, dz;
-    const double d2 = lane_d2(pos + 3 * (size_t)(start + j), off, pix, piy, piz, dx, dy, dz);
-    const bool ok = live && cand_pass(d2, r2, remove_self) && dist_bin(d2) <= bin_max &&
+    const double d2 = lane_d2(pos + 3 * (size_t)(start + (valid ? j : 0)), off, pix, piy, piz, dx, dy, dz);
+    const bool ok = valid && cand_pass(d2, r2, remove_self) && dist_bin(d2) <= bin_max &&
                     (d2 < thr_d2 || (d2 == thr_d2 && c < thr_c));
     const unsigned bal = __ballot_sync(0xffffffffu, ok);
     if (ok) {
@@ -363,9 +464,14 @@ extern "C" int arreau_graph_count(const double* pos, const double* lattice, cons
   }
   if (N == 0) return ARREAU_OK;
   const int blocks = (N + kWarpsPerBlock - 1) / kWarpsPerBlock;
-  graph_count_kernel<<<blocks, kWarpsPerBlock * 32, 0, s>>>(pos, lattice, atom_offset, crystal_of_atom, N,
-                                                             radius_sq, cap, remove_self_edges, raw_count, deg,
-                                                             (unsigned long long*)num_neighbors_image);
+  if ((long long)N >= (long long)kCullMinAtoms * G)      // large cells on average: the image-culling walk
+    graph_count_kernel<true><<<blocks, kWarpsPerBlock * 32, 0, s>>>(pos, lattice, atom_offset, crystal_of_atom, N, radius_sq,
+                                                                    cap, remove_self_edges, raw_count, deg,
+                                                                    (unsigned long long*)num_neighbors_image);
+  else
+    graph_count_kernel<false><<<blocks, kWarpsPerBlock * 32, 0, s>>>(pos, lattice, atom_offset, crystal_of_atom, N, radius_sq,
+                                                                     cap, remove_self_edges, raw_count, deg,
+                                                                     (unsigned long long*)num_neighbors_image);
   CUDA_LAUNCH_CHECK();
   return ARREAU_OK;
 }
@@ -390,10 +496,14 @@ extern "C" int arreau_graph_fill(const double* pos, const double* lattice, const
   if (N < 0 || G < 0 || edge_capacity < 0) return ARREAU_ERR_BAD_SHAPE;
   if (cap > kMaxCap) return ARREAU_ERR_UNSUPPORTED;
   const int blocks = (N + kWarpsPerBlock - 1) / kWarpsPerBlock;
-  graph_fill_kernel<<<blocks, kWarpsPerBlock * 32, 0, (cudaStream_t)stream>>>(
-      pos, lattice, atom_offset, crystal_of_atom, N, radius_sq, cap, remove_self_edges, raw_count, row_ptr,
-      (long long)edge_capacity, src, dst, cell, dist, dir, (long long*)edge_index_i64, cell_offsets,
-      overflow_flag);
+  if ((long long)N >= (long long)kCullMinAtoms * G)
+    graph_fill_kernel<true><<<blocks, kWarpsPerBlock * 32, 0, (cudaStream_t)stream>>>(
+        pos, lattice, atom_offset, crystal_of_atom, N, radius_sq, cap, remove_self_edges, raw_count, row_ptr,
+        (long long)edge_capacity, src, dst, cell, dist, dir, (long long*)edge_index_i64, cell_offsets, overflow_flag);
+  else
+    graph_fill_kernel<false><<<blocks, kWarpsPerBlock * 32, 0, (cudaStream_t)stream>>>(
+        pos, lattice, atom_offset, crystal_of_atom, N, radius_sq, cap, remove_self_edges, raw_count, row_ptr,
+        (long long)edge_capacity, src, dst, cell, dist, dir, (long long*)edge_index_i64, cell_offsets, overflow_flag);
   CUDA_LAUNCH_CHECK();
   return ARREAU_OK;
 }
