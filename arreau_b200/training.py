@@ -147,7 +147,7 @@ class TrainEngine:
         self.device = dev = torch.device(device)
         self.ori = (ori_grid.detach() if isinstance(ori_grid, torch.Tensor) else torch.as_tensor(np.asarray(ori_grid))) \
             .to(dev, torch.float32).contiguous()
-        self.w = PonitaWeights.from_device_params(params.views(), self.ori)
+        self.w = PonitaWeights.from_flat(params, self.ori)
         self.eng = DenoiseEngine(self.w, tables, fourier_w, num_atoms, radius, max_neighbors, precision="fp32",
                                  debug=True, device=dev, node_capacity=node_capacity, crystal_capacity=crystal_capacity)
         e = self.eng
@@ -186,7 +186,7 @@ class TrainEngine:
     # ------------------------------------------------------------------ pieces (each = the mirrored reference call)
     def repack(self) -> None:
         """Kernel layouts of the current flat parameters (after an optimizer step)."""
-        self.w = PonitaWeights.from_device_params(self.p.views(), self.ori)
+        self.w = PonitaWeights.from_flat(self.p, self.ori)
         self.eng.w = self.w
 
     def set_batch(self, frac0, types0, lattice0, timestep, eps_x, u, eps_l) -> None:

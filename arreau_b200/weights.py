@@ -212,5 +212,53 @@ class PonitaWeights:
         self.c.num_scalar, self.c.num_vec, self.c.num_states = self.num_scalar, self.num_vec, self.num_states
         return self
 
+    @classmethod
+    def from_flat(cls, flat, ori_grid: torch.Tensor) -> "PonitaWeights":
+        """Kernel layouts of the fp32 path straight from the training step's flat parameter buffer (training.py
+        FlatParams, arreau_train_layout_t order): tensors whose kernel layout equals the reference's own layout are
+        VIEWS of the flat buffer (no copy, so they are current after every optimizer step by construction), the six
+        transposed matrices are one strided copy each, plus the monomial fold and the fiber-kernel precompute --
+        ~10 launches per step instead of the ~60 small stack / transpose kernels of from_device_params."""
+        self = cls.__new__(cls)
+        dev = flat.data.device
+        self.device = dev
+        L, lay, buf = LAYERS, flat.layout, flat.data
+        R, FV = flat.num_states + 4, flat.num_scalar + flat.num_vec
+
+        def view(off, *shape):
+            n = int(np.prod(shape))
+            return buf[off:off + n].view(*shape)
+
+        w1, b1 = view(lay.basis_w1, HIDDEN, 258), view(lay.basis_b1, HIDDEN)
+        fold = getattr(flat, "_fold_table", None)
+        if fold is None:
+            fold = flat._fold_table = torch.as_tensor(monomial_fold_table(), dtype=torch.int32).to(dev)
+        w1m_t = torch.empty(MONO_PAD, HIDDEN, dtype=torch.float32, device=dev)
+        stream = torch.cuda.current_stream(dev).cuda_stream
+        _lib.call("arreau_fold_basis_w1", w1.data_ptr(), b1.data_ptr(), fold.data_ptr(), w1m_t.data_ptr(), stream)
+        self.num_readout, self.num_states, self.num_vec, self.num_scalar = R, flat.num_states, flat.num_vec, flat.num_scalar
+        wk = view(lay.conv_kernel_w, L, HIDDEN, BASIS)
+        self.t = dict(
+            ori=ori_grid.to(dev, torch.float32).contiguous(), w_embed_t=view(lay.embed_w, HIDDEN, FV).t().contiguous(),
+            w1m_t=w1m_t, w2_t=view(lay.basis_w2, BASIS, HIDDEN).t().contiguous(), b2=view(lay.basis_b2, BASIS),
+            wk_t=wk.permute(2, 0, 1).reshape(BASIS, L * HIDDEN).contiguous(),
+            conv_bias=view(lay.conv_bias, L, HIDDEN), ln_w=view(lay.norm_w, L, HIDDEN), ln_b=view(lay.norm_b, L, HIDDEN),
+            mlp_w1_t=view(lay.lin1_w, L, WIDEN * HIDDEN, HIDDEN).transpose(1, 2).contiguous(),
+            mlp_b1=view(lay.lin1_b, L, WIDEN * HIDDEN),
+            mlp_w2_t=view(lay.lin2_w, L, HIDDEN, WIDEN * HIDDEN).transpose(1, 2).contiguous(),
+            mlp_b2=view(lay.lin2_b, L, HIDDEN), layer_scale=view(lay.layer_scale, L, HIDDEN),
+            wr_t=view(lay.readout_w, L, R, HIDDEN).transpose(1, 2).contiguous(), br=view(lay.readout_b, L, R),
+            fiber_kernel=torch.empty(L, NUM_ORI, NUM_ORI, HIDDEN, dtype=torch.float32, device=dev))
+        keep = [view(lay.fiber_w1, HIDDEN, 3), view(lay.fiber_b1, HIDDEN), view(lay.fiber_w2, BASIS, HIDDEN),
+                view(lay.fiber_b2, BASIS), view(lay.conv_fiber_w, L, HIDDEN, BASIS)]
+        _lib.call("arreau_fiber_kernel_precompute", self.t["ori"].data_ptr(), *[k.data_ptr() for k in keep],
+                  self.t["fiber_kernel"].data_ptr(), stream)
+        self.c = _lib.Weights()
+        for name, _ in _lib.Weights._fields_:
+            if name in self.t:
+                setattr(self.c, name, self.t[name].data_ptr())
+        self.c.num_scalar, self.c.num_vec, self.c.num_states = self.num_scalar, self.num_vec, self.num_states
+        return self
+
     def ref(self):
         return C.byref(self.c)
