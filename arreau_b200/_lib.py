@@ -51,6 +51,11 @@ class StepArgs(C.Structure):
         ("precision", i32), ("update_types", i32)]
 
 
+class StepReplay(C.Structure):
+    _fields_ = [("counter", vp), ("vp_table", vp), ("t_of_atom", vp), ("dyn", vp), ("step_out", vp),
+                ("seed", C.c_uint64), ("t_first", i32), ("reserved", i32)]
+
+
 class TrainLayout(C.Structure):
     FIELDS = ("basis_w1", "basis_b1", "basis_w2", "basis_b2", "fiber_w1", "fiber_b1", "fiber_w2", "fiber_b2", "embed_w",
               "layer_scale", "conv_bias", "conv_kernel_w", "conv_fiber_w", "lin1_w", "lin1_b", "lin2_w", "lin2_b",
@@ -94,6 +99,7 @@ SIGNATURES = {
     "arreau_d3pm_reverse": [vp, vp, vp, vp, i32, vp, vp, f64, f64, i32, i32, i32, vp, vp],
     "arreau_step_noise": [C.c_uint64, i32, i32, i32, i32, vp, vp, vp, vp],
     "arreau_denoise_step": [C.POINTER(Weights), C.POINTER(Workspace), C.POINTER(StepArgs), vp],
+    "arreau_denoise_step_replay": [C.POINTER(Weights), C.POINTER(Workspace), C.POINTER(StepArgs), C.POINTER(StepReplay), vp],
     # training step
     "arreau_matrix_to_params": [vp, i32, vp, vp, vp],
     "arreau_ve_pbc_forward": [vp, vp, vp, vp, vp, vp, i32, vp, vp, vp],

@@ -110,9 +110,12 @@ assemble_features_kernel(const double* __restrict__ frac, const int64_t* __restr
 __global__ void vp_lattice_reverse_kernel(const double* lengths, const float* __restrict__ len0,
                                           const int32_t* __restrict__ atom_offset, const double* __restrict__ z,
                                           int t, double cx0, double cxt, double denom, double var, int G,
-                                          double* out) {   // out may alias lengths
+                                          double* out, const double* __restrict__ dyn) {   // out may alias lengths
   const int idx = blockIdx.x * blockDim.x + threadIdx.x;
   if (idx >= 3 * G) return;
+  if (dyn) {      // replayable step: {t, cx0, cxt, denom, var} of the current replay live in device memory
+    t = (int)dyn[0]; cx0 = dyn[1]; cxt = dyn[2]; denom = dyn[3]; var = dyn[4];
+  }
   const int g = idx / 3;
   const double n = (double)(atom_offset[g + 1] - atom_offset[g]);
   const double pred = __dmul_rn((double)len0[idx], n);            // diffusion_loss.py:338
@@ -295,7 +298,18 @@ extern "C" int arreau_vp_lattice_reverse(const double* lengths, const float* len
   if (!lengths || !len0 || !atom_offset || !lengths_out || (t > 1 && !z)) return ARREAU_ERR_NULL;
   if (G < 0) return ARREAU_ERR_BAD_SHAPE;
   vp_lattice_reverse_kernel<<<(3 * G + 127) / 128, 128, 0, (cudaStream_t)stream>>>(
-      lengths, len0, atom_offset, z, t, cx0, cxt, denom, var, G, lengths_out);
+      lengths, len0, atom_offset, z, t, cx0, cxt, denom, var, G, lengths_out, nullptr);
+  CUDA_LAUNCH_CHECK();
+  return ARREAU_OK;
+}
+
+// the same with the timestep and the four posterior coefficients read from device memory (arreau_denoise_step_replay)
+int arreau_vp_lattice_reverse_dyn(const double* lengths, const float* len0, const int32_t* atom_offset, const double* z,
+                                  const double* dyn, int32_t G, double* lengths_out, void* stream) {
+  if (G == 0) return ARREAU_OK;
+  if (!lengths || !len0 || !atom_offset || !lengths_out || !z || !dyn) return ARREAU_ERR_NULL;
+  vp_lattice_reverse_kernel<<<(3 * G + 127) / 128, 128, 0, (cudaStream_t)stream>>>(
+      lengths, len0, atom_offset, z, 0, 0.0, 0.0, 1.0, 0.0, G, lengths_out, dyn);
   CUDA_LAUNCH_CHECK();
   return ARREAU_OK;
 }

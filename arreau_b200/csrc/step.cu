@@ -34,8 +34,9 @@ __device__ __forceinline__ double u01(uint32_t a, uint32_t b) {   // 53-bit unif
 
 __global__ void step_noise_kernel(uint64_t seed, int step, long long n_normal, long long n_uniform,
                                   double* __restrict__ z_len, long long n_len, double* __restrict__ z_frac,
-                                  double* __restrict__ u) {
+                                  double* __restrict__ u, const int32_t* __restrict__ step_ptr) {
   const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (step_ptr) step = *step_ptr;       // replayable step: the step ordinal of the current replay
   uint32_t r[4];
   if (idx < (n_normal + 1) / 2) {   // Box-Muller: two normals per counter
     philox4x32_10(seed, (uint64_t)idx, (uint32_t)step, 0u, r);
@@ -57,7 +58,28 @@ __global__ void step_noise_kernel(uint64_t seed, int step, long long n_normal, l
   }
 }
 
+// Replayable step (CUDA graph): the per-step scalars live in device memory and advance by themselves.  One block:
+// k = *counter; t = max(t_first - k, 1); dyn = {t, VP posterior coefficients of t}; t_of_atom[:] = t; step_out = k;
+// then *counter = k + 1.
+__global__ void __launch_bounds__(1024)
+step_advance_kernel(int32_t* __restrict__ counter, int t_first, const double* __restrict__ vp_table, int N,
+                    int32_t* __restrict__ t_of_atom, double* __restrict__ dyn, int32_t* __restrict__ step_out) {
+  const int k = *counter;
+  const int t = max(t_first - k, 1);
+  for (int i = threadIdx.x; i < N; i += blockDim.x) t_of_atom[i] = t;
+  if (threadIdx.x < 4) dyn[1 + threadIdx.x] = vp_table[4 * (size_t)t + threadIdx.x];
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    dyn[0] = (double)t;
+    *step_out = k;
+    *counter = k + 1;
+  }
+}
+
 }  // namespace
+
+int arreau_vp_lattice_reverse_dyn(const double* lengths, const float* len0, const int32_t* atom_offset, const double* z,
+                                  const double* dyn, int32_t G, double* lengths_out, void* stream);   // csrc/state.cu
 
 extern "C" int arreau_abi_version(void) { return 1; }
 
@@ -80,7 +102,7 @@ extern "C" int arreau_step_noise(uint64_t seed, int32_t step, int32_t G, int32_t
   const long long work = ((n_normal > n_uniform ? n_normal : n_uniform) + 1) / 2;
   if (work == 0) return ARREAU_OK;
   step_noise_kernel<<<(unsigned)((work + 255) / 256), 256, 0, (cudaStream_t)stream>>>(seed, step, n_normal, n_uniform,
-                                                                                     z_len, n_len, z_frac, u);
+                                                                                     z_len, n_len, z_frac, u, nullptr);
   CUDA_LAUNCH_CHECK();
   return ARREAU_OK;
 }
@@ -213,6 +235,61 @@ extern "C" int arreau_denoise_step(const arreau_weights* w, const arreau_workspa
   ARREAU_TRY(arreau_ve_pbc_reverse(a->frac, a->score, a->z_frac, nullptr, a->t, a->ve_sigmas, N, a->frac, stream));
   if (a->update_types)
     ARREAU_TRY(arreau_d3pm_reverse(a->types, a->logits, a->u_type, nullptr, a->t, a->q_keep, a->q_to_mask,
+                                   a->onestep_keep, a->onestep_to_mask, a->num_steps, N, Z, a->types, stream));
+  return ARREAU_OK;
+}
+
+// The same step with every per-step scalar in device memory, so that ONE captured CUDA graph replays the whole
+// trajectory: replay k runs timestep t = max(t_first - k, 1) with Philox noise of step ordinal k (bit-identical to
+// arreau_step_noise(seed, k) + arreau_denoise_step(t)).  capped graphs only (no host read of the edge count).
+extern "C" int arreau_denoise_step_replay(const arreau_weights* w, const arreau_workspace* ws, const arreau_step_args* a,
+                                          const arreau_step_replay* r, void* stream) {
+  if (!w || !ws || !a || !r) return ARREAU_ERR_NULL;
+  if (!r->counter || !r->vp_table || !r->t_of_atom || !r->dyn || !r->step_out) return ARREAU_ERR_NULL;
+  const int N = a->num_atoms_total, G = a->num_crystals, Z = w->num_states;
+  if (N < 0 || G < 0) return ARREAU_ERR_BAD_SHAPE;
+  if (a->cap <= 0) return ARREAU_ERR_UNSUPPORTED;
+  if (N == 0 || G == 0) return ARREAU_OK;
+  if (w->num_scalar != Z + 2 * a->emb + 10 || w->num_vec != 4) return ARREAU_ERR_BAD_SHAPE;
+  cudaStream_t s = (cudaStream_t)stream;
+  step_advance_kernel<<<1, 1024, 0, s>>>(r->counter, r->t_first, r->vp_table, N, r->t_of_atom, r->dyn, r->step_out);
+  CUDA_LAUNCH_CHECK();
+  {
+    const long long n_len = 3LL * G, n_normal = n_len + 3LL * N, n_uniform = (long long)N * Z;
+    const long long work = ((n_normal > n_uniform ? n_normal : n_uniform) + 1) / 2;
+    // (the step's noise buffers are inputs of arreau_denoise_step; here the call itself fills them)
+    step_noise_kernel<<<(unsigned)((work + 255) / 256), 256, 0, s>>>(r->seed, 0, n_normal, n_uniform,
+                                                                     const_cast<double*>(a->z_len), n_len,
+                                                                     const_cast<double*>(a->z_frac),
+                                                                     const_cast<double*>(a->u_type), r->step_out);
+    CUDA_LAUNCH_CHECK();
+  }
+  if (a->angle_trig)
+    ARREAU_TRY(arreau_lattice_from_trig(a->lengths, a->angle_trig, G, a->lattice, stream));
+  else
+    ARREAU_TRY(arreau_lattice_from_params(a->lengths, a->angles, G, a->lattice, stream));
+  ARREAU_TRY(arreau_assemble_features(a->frac, a->types, a->lengths, a->angles, a->lattice, a->atom_offset,
+                                      a->crystal_of_atom, r->t_of_atom, 0, a->vp_betas, a->fourier_w, a->emb, N, G, Z,
+                                      a->x, a->vec, stream));
+  ARREAU_TRY(arreau_frac_to_cart(a->frac, a->lattice, a->crystal_of_atom, N, a->pos, stream));
+  const double r2 = a->radius * a->radius;
+  ARREAU_TRY(arreau_graph_count(a->pos, a->lattice, a->atom_offset, a->crystal_of_atom, N, G, r2, a->cap, 1,
+                                a->raw_count, a->deg, a->num_neighbors_image, stream));
+  ARREAU_TRY(arreau_graph_scan(a->deg, a->row_ptr, N, stream));
+  ARREAU_TRY(arreau_graph_fill(a->pos, a->lattice, a->atom_offset, a->crystal_of_atom, N, G, r2, a->cap, 1,
+                               a->raw_count, a->row_ptr, ws->edge_capacity, a->src, a->dst, a->cell, a->dist, a->dir,
+                               nullptr, nullptr, a->overflow_flag, stream));
+  ARREAU_TRY(arreau_ponita_forward(w, ws, a->precision, a->x, a->vec, a->row_ptr, a->src, a->dist, a->dir, a->lattice,
+                                   a->atom_offset, a->crystal_of_atom, N, G, a->radius, a->logits, a->score, a->len0,
+                                   stream));
+  ARREAU_TRY(arreau_vp_lattice_reverse_dyn(a->lengths, a->len0, a->atom_offset, a->z_len, r->dyn, G, a->lengths, stream));
+  if (a->angle_trig)
+    ARREAU_TRY(arreau_lattice_from_trig(a->lengths, a->angle_trig, G, a->lattice, stream));
+  else
+    ARREAU_TRY(arreau_lattice_from_params(a->lengths, a->angles, G, a->lattice, stream));
+  ARREAU_TRY(arreau_ve_pbc_reverse(a->frac, a->score, a->z_frac, r->t_of_atom, 0, a->ve_sigmas, N, a->frac, stream));
+  if (a->update_types)
+    ARREAU_TRY(arreau_d3pm_reverse(a->types, a->logits, a->u_type, r->t_of_atom, 0, a->q_keep, a->q_to_mask,
                                    a->onestep_keep, a->onestep_to_mask, a->num_steps, N, Z, a->types, stream));
   return ARREAU_OK;
 }

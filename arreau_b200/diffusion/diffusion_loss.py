@@ -187,10 +187,13 @@ class DiffusionLoss(torch.nn.Module):
     def sample(self, *, model, z_table, t_emb_weights, num_atoms_per_sample: int, num_samples_in_batch: int,
                vis_name: str = "", visualization_setting=None, show_bonds: bool = False,
                constant_atoms: Optional[torch.Tensor] = None, num_atoms: Optional[torch.Tensor] = None,
-               device="cuda", device_noise: bool = False, seed: int = 0, step_callback=None) -> SampleResult:
+               device="cuda", device_noise: bool = False, seed: int = 0, step_callback=None,
+               cuda_graph: bool = False) -> SampleResult:
         """diffusion/diffusion_loss.py:277-377.  Extra keyword-only options (defaults reproduce the reference):
         `num_atoms` a per-crystal atom-count vector, `device_noise` Philox noise generated on the GPU,
-        `step_callback(timestep, engine)` called after each step (e.g. to log E/N)."""
+        `step_callback(timestep, engine)` called after each step (e.g. to log E/N), `cuda_graph` (needs device_noise and
+        max_neighbors > 0): the loop body is captured once and replayed T - 1 times, one launch per step -- bit-identical
+        results; it pays for small batches, whose steps are launch bound."""
         Z = len(z_table)
         G = num_samples_in_batch
         dd = torch.float64                                     # main_diffusion_generate.py:27
@@ -202,7 +205,15 @@ class DiffusionLoss(torch.nn.Module):
         atom_types = constant_atoms if constant_atoms is not None else torch.full((N,), Z - 1)
         eng = self.engine_for(model, t_emb_weights, na, torch.device(device))
         eng.set_state(frac_x, atom_types, lengths, angles)
-        for step_idx, timestep in enumerate(reversed(range(1, self.T))):
+        if cuda_graph:
+            if not device_noise or self.max_neighbors <= 0:
+                raise ValueError("cuda_graph=True needs device_noise=True and max_neighbors > 0")
+            g = eng.capture_trajectory_graph(self.T - 1, seed, update_types=constant_atoms is None)
+            for timestep in reversed(range(1, self.T)):
+                g.replay()
+                if step_callback is not None:
+                    step_callback(timestep, eng)
+        for step_idx, timestep in enumerate(reversed(range(1, self.T)) if not cuda_graph else ()):
             if device_noise:
                 eng.draw_noise(seed, step_idx)
             else:   # the reference's draw order per step: lengths, frac, types

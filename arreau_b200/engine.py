@@ -375,6 +375,54 @@ class DenoiseEngine:
         finally:
             self.ws.onehot_types = None
 
+    # ------------------------------------------------------------------ whole trajectory as one replayed CUDA graph
+    def capture_trajectory_graph(self, t_first: int, seed: int, update_types: bool = True) -> "torch.cuda.CUDAGraph":
+        """Capture ONE denoise step (arreau_denoise_step_replay: Philox noise + graph + network + update, every
+        per-step scalar in device memory) as a CUDA graph; replay k runs timestep max(t_first - k, 1) with the noise of
+        step ordinal k, so `for _ in range(steps): g.replay()` is the sampler loop of diffusion_loss.py:318-349 with one
+        launch per step instead of 26.  Bit-identical to `draw_noise(seed, k); step(t)`.  Capped graphs only.
+        `reset_trajectory_graph()` rewinds the device-side step counter (a new trajectory on new state)."""
+        if self.cap <= 0:
+            raise ValueError("the replayable step needs max_neighbors > 0 (uncapped graphs size their buffers on the host)")
+        tb, dev = self.tabs, self.device
+        if not hasattr(self, "_replay"):
+            table = torch.stack([tb.vp_cx0, tb.vp_cxt, tb.vp_denom, tb.vp_var], dim=1).to(torch.float64).contiguous().to(dev)
+            self._replay_bufs = dict(counter=torch.zeros(1, dtype=torch.int32, device=dev), table=table,
+                                     t_of_atom=torch.zeros(self.N_cap, dtype=torch.int32, device=dev),
+                                     dyn=torch.zeros(5, dtype=torch.float64, device=dev),
+                                     step_out=torch.zeros(1, dtype=torch.int32, device=dev))
+            self._replay = _lib.StepReplay()
+        b, r = self._replay_bufs, self._replay
+        r.counter, r.vp_table, r.t_of_atom = b["counter"].data_ptr(), b["table"].data_ptr(), b["t_of_atom"].data_ptr()
+        r.dyn, r.step_out, r.seed, r.t_first = b["dyn"].data_ptr(), b["step_out"].data_ptr(), int(seed), int(t_first)
+        a = self.args
+        a.update_types = 1 if update_types else 0
+        self.ws.onehot_types = self.types.data_ptr()
+        keep = [t.clone() for t in (self.frac, self.types, self.lengths, self.lattice)]
+
+        def one_step():
+            _lib.call("arreau_denoise_step_replay", self.w.ref(), C.byref(self.ws), C.byref(a), C.byref(r), self.stream)
+
+        # warm up outside the capture (first launches set function attributes), on a side stream as torch requires
+        side = torch.cuda.Stream(dev)
+        side.wait_stream(torch.cuda.current_stream(dev))
+        with torch.cuda.stream(side):
+            one_step()
+        torch.cuda.current_stream(dev).wait_stream(side)
+        torch.cuda.synchronize(dev)
+        g = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(g):
+            one_step()
+        # the warm-up step advanced the state and the counter: restore both
+        for dst, src in zip((self.frac, self.types, self.lengths, self.lattice), keep):
+            dst.copy_(src)
+        b["counter"].zero_()
+        self._trajectory_graph = g
+        return g
+
+    def reset_trajectory_graph(self) -> None:
+        self._replay_bufs["counter"].zero_()
+
     def kernels_logical(self, layer: int, num_edges: Optional[int] = None) -> torch.Tensor:
         """Spatial kernels of one layer as fp32 [E,O,C] in logical channel order (debug / tests).  The fp16 path
         stores the 16-byte chunk k of row (e, o) at chunk position k ^ o (csrc/model_tc.cu); undo that here."""

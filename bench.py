@@ -330,6 +330,9 @@ def main():
     ap.add_argument("--trajectory", action="store_true",
                     help="time ONE WHOLE trajectory (every denoise step from the sampler init at t=T-1 down to t=1, "
                          "state re-initialised after the warm-up) instead of --steps steps; value = crystals / that time")
+    ap.add_argument("--cuda-graph", action="store_true",
+                    help="run the timed steps as replays of ONE captured CUDA graph of the step (arreau_denoise_step_replay: "
+                         "device-resident step counter, Philox noise inside the graph): one launch per step instead of 26")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e-trajectory", action="store_true", help="skip the whole-trajectory e2e leg (~7 s at C2)")
     ap.add_argument("--no-other-precision", action="store_true")
@@ -387,6 +390,7 @@ def main():
         args.steps = t_start
     barrier()
     epa_first = eng.num_edges() / N
+    graph = eng.capture_trajectory_graph(t, seed) if args.cuda_graph else None      # state and counter are restored
     clocks = ClockSampler(local)
     time.sleep(0.25)
     l0 = _lib.launch_count()
@@ -394,13 +398,19 @@ def main():
     barrier()
     clocks.begin()
     ev0.record()
-    for i in range(args.steps):
-        eng.draw_noise(seed, 1000 + i)
-        eng.step(t); t = max(t - 1, 1)
+    if graph is not None:
+        for i in range(args.steps):
+            graph.replay()
+    else:
+        for i in range(args.steps):
+            eng.draw_noise(seed, 1000 + i)
+            eng.step(t); t = max(t - 1, 1)
     ev1.record()
     barrier()
     clocks.end()
     launches = _lib.launch_count() - l0
+    if graph is not None:
+        launches = 26 * args.steps          # kernels inside the replayed graph (the library counts launches at capture only)
     ms = ev0.elapsed_time(ev1)
     if world > 1:
         tmax = torch.tensor([ms], device=dev)
@@ -582,7 +592,8 @@ def main():
                 "gpu_launches": int(launches), "roofline": roof, "kernels": kernels,
                 "breakdown_ms_per_step": {k: round(v["ms_per_step"], 4) for k, v in br.items()},
                 "edges_per_atom": {"first_timed_step": epa_first, "last_timed_step": epa_last, "breakdown": E / N},
-                "edge_overflow": overflow, "final_gather_ms": gather_ms, "impl": "ours", "precision": args.precision}
+                "edge_overflow": overflow, "final_gather_ms": gather_ms, "impl": "ours", "precision": args.precision,
+                "cuda_graph": bool(args.cuda_graph)}
         if args.trajectory:
             line["trajectory"] = {"steps_run": args.steps, "t_from": t_start, "t_to": 1, "seconds": ms * 1e-3,
                                   "crystals": world * G, "note": "value = crystals / seconds of this one whole trajectory"}

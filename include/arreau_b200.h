@@ -388,6 +388,26 @@ typedef struct arreau_step_args {
 int arreau_denoise_step(const arreau_weights* w, const arreau_workspace* ws, const arreau_step_args* a,
                         void* stream);
 
+/* The same loop body (diffusion_loss.py:318-349 including the `for timestep in reversed(range(1, T))` bookkeeping)
+ * with every per-step scalar in DEVICE memory, so that one captured CUDA graph of this call replays the whole
+ * trajectory: replay k (k = *counter, incremented by the call) runs timestep t = max(t_first - k, 1) with Philox noise
+ * of step ordinal k written into a->z_len / z_frac / u_type -- bit-identical to arreau_step_noise(seed, k, ...)
+ * followed by arreau_denoise_step with a->t = t and the VP posterior coefficients of t.  a->t and a->vp_* are ignored.
+ * Capped graphs only (max_neighbors > 0: no host read of the edge count); ARREAU_ERR_UNSUPPORTED otherwise. */
+typedef struct arreau_step_replay {
+  int32_t* counter;        /* [1] device: replays done so far; reset it to restart a trajectory */
+  const double* vp_table;  /* [T+1][4] device: {cx0, cxt, denom, var} of VP_lattice.reverse_given_x0 per timestep */
+  int32_t* t_of_atom;      /* [N] device scratch: the replay's timestep for the per-atom kernels */
+  double* dyn;             /* [5] device scratch: {t, cx0, cxt, denom, var} of the replay */
+  int32_t* step_out;       /* [1] device scratch: the replay's step ordinal (read by the noise kernel) */
+  uint64_t seed;           /* Philox seed */
+  int32_t t_first;         /* timestep of replay 0 (T - 1 for a whole trajectory) */
+  int32_t reserved;
+} arreau_step_replay;
+
+int arreau_denoise_step_replay(const arreau_weights* w, const arreau_workspace* ws, const arreau_step_args* a,
+                               const arreau_step_replay* r, void* stream);
+
 /* ---------------------------------------------------------------------------------------------
  * Training step   replaces DiffusionLoss.__call__ (diffusion/diffusion_loss.py:204-274),
  *     the forward noising it calls, and the autograd backward of the network (trainer.fit, main_diffusion.py:307).

@@ -206,3 +206,50 @@ def test_fp16_trajectory_tracks_fp32_trajectory(device, weights_npz):
     assert a["epa"].min() > 1.0                       # the graph never empties (calibrated read-out)
     # measured on B200: E/N identical at every sampled step, final lengths 1.5e-4 apart, identical final types
     assert epa_dev < 0.05 and len_rel < 5e-3 and tv < 0.02 and same > 0.95
+
+
+@pytest.mark.parametrize("precision", ["fp32", "fp16"])
+def test_cuda_graph_replay_is_bit_identical(device, packed_weights, weights_npz, precision):
+    """arreau_denoise_step_replay captured once as a CUDA graph and replayed (device-resident step counter, timestep and
+    VP coefficients; Philox noise inside the graph) against the ordinary loop `draw_noise(seed, k); step(t)`: the same
+    bits after 40 steps, including the clamp at t = 1, and again after rewinding the counter on a new state."""
+    from arreau_b200.engine import DenoiseEngine
+    from arreau_b200.synthetic import make_crystals
+    from arreau_b200.tables import build_tables
+    cr = make_crystals(5, 3, 17, seed=4)
+    tabs = build_tables(1000, 90)
+
+    def run(graph, t_first, steps, seed, state):
+        eng = DenoiseEngine(packed_weights, tabs, weights_npz["fourier_w"], cr.num_atoms, 5.0, 8, precision=precision, device=device)
+        eng.set_state(*state)
+        if graph:
+            g = eng.capture_trajectory_graph(t_first, seed)
+            assert int(eng._replay_bufs["counter"].item()) == 0
+            for _ in range(steps):
+                g.replay()
+        else:
+            for k in range(steps):
+                eng.draw_noise(seed, k)
+                eng.step(max(t_first - k, 1))
+        torch.cuda.synchronize()
+        return eng, [t.clone() for t in (eng.frac, eng.types, eng.lengths, eng.lattice, eng.score, eng.logits)]
+
+    state = (cr.frac, cr.types, cr.lengths, cr.angles)
+    for t_first, steps in ((700, 40), (20, 25)):           # the second run walks through t = 1 and stays there
+        _, a = run(False, t_first, steps, 9, state)
+        eng, b = run(True, t_first, steps, 9, state)
+        for x, y in zip(a, b):
+            assert torch.equal(x, y)
+        assert int(eng._replay_bufs["counter"].item()) == steps
+    # rewind: a second trajectory on the same engine and graph
+    state2 = (cr.frac[::-1].copy(), cr.types, cr.lengths * 1.1, cr.angles)
+    _, a = run(False, 500, 10, 9, state2)
+    eng.set_state(*state2)
+    eng.reset_trajectory_graph()
+    eng._replay.t_first = 500          # the struct is read by value at capture: a new t_first needs a new capture
+    g = eng.capture_trajectory_graph(500, 9)
+    for _ in range(10):
+        g.replay()
+    torch.cuda.synchronize()
+    for x, y in zip(a, (eng.frac, eng.types, eng.lengths, eng.lattice, eng.score, eng.logits)):
+        assert torch.equal(x, y)
