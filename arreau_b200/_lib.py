@@ -56,6 +56,13 @@ class StepReplay(C.Structure):
                 ("seed", C.c_uint64), ("t_first", i32), ("reserved", i32)]
 
 
+class WorkspaceSizes(C.Structure):
+    FIELDS = ("h", "y", "kernels", "acc", "x1", "debug_per_layer", "pool", "x", "vec", "logits", "score", "len0", "pos",
+              "raw_count", "deg", "row_ptr", "num_neighbors_image", "src", "dst", "cell", "dist", "dir", "z_len", "z_frac",
+              "u_type")
+    _fields_ = [(n, i64) for n in FIELDS]
+
+
 class TrainLayout(C.Structure):
     FIELDS = ("basis_w1", "basis_b1", "basis_w2", "basis_b2", "fiber_w1", "fiber_b1", "fiber_w2", "fiber_b2", "embed_w",
               "layer_scale", "conv_bias", "conv_kernel_w", "conv_fiber_w", "lin1_w", "lin1_b", "lin2_w", "lin2_b",
@@ -68,6 +75,7 @@ SIGNATURES = {
     "arreau_abi_version": [],
     "arreau_model_dims": [C.POINTER(C.c_int)] * 5,
     "arreau_launch_count": [],
+    "arreau_workspace_bytes": [i32, i32, i64, i32, i32, i32, C.POINTER(WorkspaceSizes)],
     "arreau_graph_count": [vp, vp, vp, vp, i32, i32, f64, i32, i32, vp, vp, vp, vp],
     "arreau_graph_scan": [vp, vp, i32, vp],
     "arreau_graph_fill": [vp, vp, vp, vp, i32, i32, f64, i32, i32, vp, vp, i64, vp, vp, vp, vp, vp, vp, vp, vp, vp],

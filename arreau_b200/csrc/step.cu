@@ -94,6 +94,27 @@ extern "C" int arreau_model_dims(int* num_ori, int* hidden, int* basis, int* wid
 
 extern "C" int64_t arreau_launch_count(void) { return (int64_t)g_arreau_launches; }
 
+extern "C" int arreau_workspace_bytes(int32_t N, int32_t G, int64_t edge_capacity, int32_t precision, int32_t F, int32_t Z,
+                                      arreau_workspace_sizes* o) {
+  if (!o) return ARREAU_ERR_NULL;
+  if (N < 0 || G < 0 || edge_capacity < 0 || F <= 0 || Z <= 0) return ARREAU_ERR_BAD_SHAPE;
+  if (precision != ARREAU_PRECISION_FP32 && precision != ARREAU_PRECISION_FP16) return ARREAU_ERR_UNSUPPORTED;
+  const bool fp16 = precision == ARREAU_PRECISION_FP16;
+  const int64_t node = (int64_t)N * kO * kC, n = N, g = G, e = edge_capacity;
+  o->h = node * 4;
+  o->y = fp16 ? ((n * kO + 127) / 128) * 128 * kC * 2 : node * 4;            // fp16: 128-row UMMA tile images
+  o->kernels = (int64_t)kL * e * kO * kC * (fp16 ? 2 : 4);
+  o->acc = n * (Z + 6) * 4;
+  o->x1 = node * 4;
+  o->debug_per_layer = node * 4;
+  o->pool = (fp16 && Z + 6 == 96) ? (int64_t)(kL + 1) * ((n + 15) / 16) * 4 * kC * 16 * 4 : 0;
+  o->x = n * F * 4; o->vec = n * 12 * 4; o->logits = n * Z * 4; o->score = n * 3 * 4; o->len0 = g * 3 * 4;
+  o->pos = n * 3 * 8; o->raw_count = n * 4; o->deg = n * 4; o->row_ptr = (n + 1) * 4; o->num_neighbors_image = g * 8;
+  o->src = e * 4; o->dst = e * 4; o->cell = e; o->dist = e * 8; o->dir = e * 3 * 8;
+  o->z_len = g * 3 * 8; o->z_frac = n * 3 * 8; o->u_type = n * Z * 8;
+  return ARREAU_OK;
+}
+
 extern "C" int arreau_step_noise(uint64_t seed, int32_t step, int32_t G, int32_t N, int32_t Z, double* z_len,
                                  double* z_frac, double* u, void* stream) {
   if (!z_len || !z_frac || !u) return ARREAU_ERR_NULL;

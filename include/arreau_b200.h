@@ -291,6 +291,19 @@ typedef struct arreau_workspace {
   float* pool;      /* NULL, or [L+1] pool entries (see arreau_readout_pooled) -> the fp16 path uses the pooled read-out */
 } arreau_workspace;
 
+/* Bytes of every buffer of arreau_workspace (and of the graph / step scratch of arreau_step_args) for N atoms, G
+ * crystals, an edge capacity and a precision: what a caller allocates before arreau_ponita_forward /
+ * arreau_denoise_step / arreau_denoise_step_replay (the caller owns all memory; nothing is allocated inside). */
+typedef struct arreau_workspace_sizes {
+  int64_t h, y, kernels, acc, x1, debug_per_layer, pool;          /* arreau_workspace (debug: x1/x2 take L, h L+1 layers) */
+  int64_t x, vec, logits, score, len0;                            /* network io                                     */
+  int64_t pos, raw_count, deg, row_ptr, num_neighbors_image;      /* graph scratch                                  */
+  int64_t src, dst, cell, dist, dir;                              /* edge arrays                                    */
+  int64_t z_len, z_frac, u_type;                                  /* noise                                          */
+} arreau_workspace_sizes;
+int arreau_workspace_bytes(int32_t num_atoms_total, int32_t num_crystals, int64_t edge_capacity, int32_t precision,
+                           int32_t num_scalar, int32_t num_states, arreau_workspace_sizes* out);
+
 /* PonitaFiberBundle.forward (ponita/models/ponita.py:88-123) on a prebuilt graph: x[N,F], vec[N,V,3] f32;
  * row_ptr[N+1], src[E] (receiver-sorted CSR), dist[E], dir[E,3] f64, lattice[G,3,3] f64.
  * Outputs logits[N,Z], score[N,3], len0[G,3] f32. */

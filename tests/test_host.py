@@ -57,7 +57,8 @@ def test_struct_layouts_match_header():
     """ctypes mirrors of the three argument structs have the field order of the header."""
     from arreau_b200 import _lib
     text = open(HEADER).read()
-    for cname, cls in (("arreau_weights", _lib.Weights), ("arreau_workspace", _lib.Workspace), ("arreau_step_args", _lib.StepArgs)):
+    for cname, cls in (("arreau_weights", _lib.Weights), ("arreau_workspace", _lib.Workspace), ("arreau_step_args", _lib.StepArgs),
+                       ("arreau_step_replay", _lib.StepReplay), ("arreau_workspace_sizes", _lib.WorkspaceSizes)):
         body = text[text.index("typedef struct " + cname):]
         body = body[:body.index("} " + cname)]
         body = re.sub(r"/\*.*?\*/", "", body, flags=re.S)
@@ -323,3 +324,27 @@ def test_reference_pickled_checkpoint_loads_on_the_host(gold):
             assert torch.equal(own[k].float().cpu(), v.float()), k
             n_model += v.numel()
     assert n_model > 1_100_000 and m.diffusion_loss.num_atomic_states == 21 and m.diffusion_loss.T == 100
+
+
+def test_workspace_bytes_query():
+    """arreau_workspace_bytes (the caller sizes and owns every buffer) against the sizes the engine allocates,
+    for both precision paths (host-only: no kernel is launched)."""
+    from arreau_b200 import _lib
+    lib = _lib.load()
+    N, G, cap, F, Z = 1000, 37, 8, 164, 90
+    for prec, kbytes in ((_lib.PRECISION_FP32, 4), (_lib.PRECISION_FP16, 2)):
+        o = _lib.WorkspaceSizes()
+        assert lib.arreau_workspace_bytes(N, G, N * cap, prec, F, Z, C.byref(o)) == 0
+        node = N * 16 * 128
+        assert o.h == node * 4 and o.x1 == node * 4 and o.debug_per_layer == node * 4
+        assert o.kernels == 5 * N * cap * 16 * 128 * kbytes
+        assert o.y == (node * 4 if kbytes == 4 else ((N * 16 + 127) // 128) * 128 * 128 * 2)
+        assert o.acc == N * 96 * 4 and o.pool == (0 if kbytes == 4 else 6 * ((N + 15) // 16) * 4 * 128 * 16 * 4)
+        assert (o.x, o.vec, o.logits, o.score, o.len0) == (N * F * 4, N * 48, N * Z * 4, N * 12, G * 12)
+        assert (o.pos, o.raw_count, o.deg, o.row_ptr, o.num_neighbors_image) == (N * 24, N * 4, N * 4, (N + 1) * 4, G * 8)
+        assert (o.src, o.dst, o.cell, o.dist, o.dir) == (N * cap * 4, N * cap * 4, N * cap, N * cap * 8, N * cap * 24)
+        assert (o.z_len, o.z_frac, o.u_type) == (G * 24, N * 24, N * Z * 8)
+    o = _lib.WorkspaceSizes()
+    assert lib.arreau_workspace_bytes(10, 2, 80, _lib.PRECISION_FP16, 95, 21, C.byref(o)) == 0 and o.pool == 0   # Z != 90
+    assert lib.arreau_workspace_bytes(-1, 2, 80, 0, 164, 90, C.byref(o)) == -1
+    assert lib.arreau_workspace_bytes(10, 2, 80, 2, 164, 90, C.byref(o)) == -2
