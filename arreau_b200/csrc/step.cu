@@ -117,11 +117,11 @@ extern "C" int arreau_workspace_bytes(int32_t N, int32_t G, int64_t edge_capacit
 
 extern "C" int arreau_step_noise(uint64_t seed, int32_t step, int32_t G, int32_t N, int32_t Z, double* z_len,
                                  double* z_frac, double* u, void* stream) {
-  if (!z_len || !z_frac || !u) return ARREAU_ERR_NULL;
   if (G < 0 || N < 0 || Z <= 0) return ARREAU_ERR_BAD_SHAPE;
   const long long n_len = 3LL * G, n_normal = n_len + 3LL * N, n_uniform = (long long)N * Z;
   const long long work = ((n_normal > n_uniform ? n_normal : n_uniform) + 1) / 2;
-  if (work == 0) return ARREAU_OK;
+  if (work == 0) return ARREAU_OK;          // an empty batch is a no-op (its buffers may be NULL)
+  if (!z_len || !z_frac || !u) return ARREAU_ERR_NULL;
   step_noise_kernel<<<(unsigned)((work + 255) / 256), 256, 0, (cudaStream_t)stream>>>(seed, step, n_normal, n_uniform,
                                                                                      z_len, n_len, z_frac, u, nullptr);
   CUDA_LAUNCH_CHECK();

@@ -91,3 +91,45 @@ def test_c3_uncapped_step_against_chunked_oracle(device, packed_weights, weights
     """Dense image neighbour lists: 16 x 200 atoms, 7 A, uncapped (E/N ~ 75-150 -> the fp16 path's long-row message
     pass); oracle on the first and the last crystal."""
     _check(device, packed_weights, weights_npz, 16, 200, 7.0, 0, 300, precision, slice_crystals=1, seed=13)
+
+
+@pytest.mark.parametrize("precision", ["fp32", "fp16"])
+def test_largest_dataset_cell_against_oracle(device, packed_weights, weights_npz, precision):
+    """The dataset's largest cell (236 atoms, exploration/largest_system_in_dataset.py:34): 3 such crystals, 5 A, cap 8 --
+    the image-culling graph instantiation, a tile count that is not a multiple of anything -- every crystal against
+    the oracle."""
+    _check(device, packed_weights, weights_npz, 3, 236, 5.0, 8, 400, precision, slice_crystals=1, seed=14)
+
+
+def test_empty_batch_and_empty_graph(device, packed_weights, weights_npz):
+    """Degenerate inputs: a batch without crystals is a no-op on every entry point; a batch whose atoms have no neighbour
+    at all (one atom per 1000 A^3 cell, nothing within the cutoff, so E = 0) still runs the whole step and agrees with
+    the oracle (the network then sees only the embedding)."""
+    from arreau_b200.engine import DenoiseEngine
+    from arreau_b200.tables import build_tables
+    tabs = build_tables(T, Z)
+    for prec in ("fp32", "fp16"):
+        eng = DenoiseEngine(packed_weights, tabs, weights_npz["fourier_w"], [], 5.0, 8, precision=prec, device=device)
+        assert eng.N == 0 and eng.G == 0
+        eng.set_state(np.zeros((0, 3)), np.zeros(0, dtype=np.int64), np.zeros((0, 3)), np.zeros((0, 3)))
+        eng.draw_noise(1, 0)
+        eng.step(500)
+        torch.cuda.synchronize()
+        assert eng.frac.shape == (0, 3) and eng.num_edges() == 0
+    na = [1, 1, 1]
+    rng = np.random.default_rng(2)
+    frac, types = rng.random((3, 3)), rng.integers(0, 89, 3)
+    lengths, angles = np.full((3, 3), 10.0) + rng.random((3, 3)), np.full((3, 3), np.pi / 2) + 0.05 * rng.standard_normal((3, 3))
+    for prec, tol in (("fp32", TOL_FP32), ("fp16", TOL_FP16_MODEL)):
+        eng = DenoiseEngine(packed_weights, tabs, weights_npz["fourier_w"], na, 5.0, 8, precision=prec, device=device)
+        eng.set_state(frac, types, lengths, angles)
+        eng.draw_noise(3, 0)
+        z_len, z_frac, u = eng.z_len.cpu().numpy(), eng.z_frac.cpu().numpy(), eng.u_type.cpu().numpy()
+        eng.step(500)
+        torch.cuda.synchronize()
+        assert eng.num_edges() == 0
+        ref = _oracle_slice(weights_npz, 5.0, 8, frac, types, lengths, angles, na, 500, z_len, z_frac, u)
+        assert rel_err(eng.score.cpu().numpy(), ref[4].numpy()) < tol
+        assert rel_err(eng.logits.cpu().numpy(), ref[5].numpy()) < tol
+        assert rel_err(eng.lengths.cpu().numpy(), ref[2].numpy()) < tol
+        assert np.array_equal(eng.types.cpu().numpy(), ref[1].numpy())
