@@ -118,7 +118,9 @@ SIGNATURES = {
     "arreau_train_layout": [i32, i32, i32, C.POINTER(TrainLayout)],
     "arreau_ponita_backward_workspace_bytes": [i32, i64, i32, i32],
     "arreau_ponita_backward": [vp, C.POINTER(TrainLayout), C.POINTER(Weights), C.POINTER(Workspace), vp, vp, vp, vp, vp,
-                               vp, vp, vp, vp, vp, vp, i32, i32, f64, vp, vp, vp, vp, i64, vp, i32, vp],
+                               vp, vp, vp, vp, vp, vp, i32, i32, f64, vp, vp, vp, vp, i64, vp, i32, i32, vp],
+    "arreau_ponita_forward_train": [vp, C.POINTER(TrainLayout), C.POINTER(Weights), C.POINTER(Workspace), vp, vp, vp, vp, vp,
+                                    vp, vp, vp, vp, vp, i32, i32, f64, vp, i64, i32, vp, vp, vp, vp],
     "arreau_sgemm": [i32, i32, vp, i64, vp, i64, vp, i64, i32, i32, i64, C.c_float, vp, i32, vp, i64, vp],
     "arreau_fold_basis_w1": [vp, vp, vp, vp, vp],
     "arreau_moments": [vp, vp, i64, vp, vp, vp],

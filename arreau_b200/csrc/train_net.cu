@@ -983,6 +983,7 @@ struct BwdBuffers {
   // fiber chain (256 rows)
   float *frow, *fz1, *fa1, *fz2, *fkb, *dfk, *dfkb, *fda1, *fw16, *fdw16;
   float *w1m, *dw1m, *partial, *small;   // small: [128 x 512] scratch for narrow outputs
+  float* zs;                             // [L][Rn][W]: ConvNext hidden pre-activations kept by arreau_ponita_forward_train
   size_t total;
 };
 
@@ -1003,6 +1004,7 @@ BwdBuffers carve(float* base, long long N, long long Ecap, int xl_pitch) {
   b.w1m = c.take(kC * 128); b.dw1m = c.take(kC * 128);
   b.partial = c.take(kPartialFloats);
   b.small = c.take((size_t)128 * 512);
+  b.zs = c.take((size_t)kL * Rn * kW);
   b.total = c.used;
   return b;
 }
@@ -1012,6 +1014,41 @@ BwdBuffers carve(float* base, long long N, long long Ecap, int xl_pitch) {
 // ================================================================================================
 // C ABI
 // ================================================================================================
+// h[r][c] += ls[c] * m[r][c]   (convnext.py:31-32: layer_scale * x + input)
+__global__ void residual_add_kernel(const float* __restrict__ m, const float* __restrict__ ls, long long n4,
+                                    float* __restrict__ h) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n4) return;
+  const float4 mv = reinterpret_cast<const float4*>(m)[i];
+  const float4 sc = *reinterpret_cast<const float4*>(ls + (int)((i * 4) % kC));
+  float4 hv = reinterpret_cast<float4*>(h)[i];
+  hv.x = fmaf(sc.x, mv.x, hv.x); hv.y = fmaf(sc.y, mv.y, hv.y); hv.z = fmaf(sc.z, mv.z, hv.z); hv.w = fmaf(sc.w, mv.w, hv.w);
+  reinterpret_cast<float4*>(h)[i] = hv;
+}
+
+// Edge chain forward: monomials -> z1 -> a1 = gelu(z1) -> z2 -> kb = gelu(z2) * window, every matrix kept in the
+// workspace for the backward (geometry/invariants.py:10-31, embedding.py:10-14, ponita.py:65,94, windowing.py:21-29).
+static int edge_chain_forward(const Gemm& g, const BwdBuffers& b, const float* P, const arreau_train_layout_t* lay,
+                              const arreau_weights* w, const int32_t* fold_table, const int32_t* src, const double* dist,
+                              const double* dir, const double* lattice, const int32_t* crystal_of_atom,
+                              const int32_t* num_edges_ptr, long long Ecap, double radius) {
+  cudaStream_t s = g.s;
+  const long long Re = Ecap * kO;
+  fold_w1_kernel<<<kC, 128, 0, s>>>(P + lay->basis_w1, P + lay->basis_b1, fold_table, 258, b.w1m);
+  CUDA_LAUNCH_CHECK();
+  if (Re <= 0) return ARREAU_OK;
+  edge_mono_kernel<<<blocks_for(Re, 128), 128, 0, s>>>(dir, dist, lattice, crystal_of_atom, src, num_edges_ptr, Ecap, w->ori,
+                                                       radius, b.mono, b.win);
+  CUDA_LAUNCH_CHECK();
+  TRY((gemm<true, true>(g, b.mono, 128, b.w1m, 128, b.z1, kC, (int)Re, kC, kMonoPad, 1.f, nullptr, false)));
+  gelu_fwd_kernel<<<blocks_for(Re * kC / 4, 256), 256, 0, s>>>(b.z1, Re * kC, kC, nullptr, 1, b.a1);
+  CUDA_LAUNCH_CHECK();
+  TRY((gemm<true, true>(g, b.a1, kC, P + lay->basis_w2, kC, b.z2, kD, (int)Re, kD, kC, 1.f, P + lay->basis_b2, false)));
+  gelu_fwd_kernel<<<blocks_for(Re * kD / 4, 256), 256, 0, s>>>(b.z2, Re * kD, kD, b.win, kO, b.kb);
+  CUDA_LAUNCH_CHECK();
+  return ARREAU_OK;
+}
+
 extern "C" int arreau_train_layout(int32_t num_scalar, int32_t num_vec, int32_t num_states, arreau_train_layout_t* lay) {
   if (!lay) return ARREAU_ERR_NULL;
   if (num_scalar <= 0 || num_vec < 0 || num_states <= 0) return ARREAU_ERR_BAD_SHAPE;
@@ -1085,7 +1122,7 @@ extern "C" int arreau_ponita_backward(const float* params, const arreau_train_la
                                       const int32_t* atom_offset, const int32_t* crystal_of_atom, int32_t N, int32_t G,
                                       double radius, const float* dlogits, const float* dscore, const float* dlen0,
                                       float* workspace, int64_t workspace_bytes, float* grads, int32_t precision,
-                                      void* stream) {
+                                      int32_t forward_kept, void* stream) {
   if (!params || !lay || !w || !ws || !fold_table || !grads || !workspace) return ARREAU_ERR_NULL;
   if (N < 0 || G < 0) return ARREAU_ERR_BAD_SHAPE;
   if (N == 0) return ARREAU_OK;
@@ -1133,19 +1170,11 @@ extern "C" int arreau_ponita_backward(const float* params, const arreau_train_la
                                                         1.0f / (float)(kL * kO), b.dr);
   CUDA_LAUNCH_CHECK();
 
-  // ---- 1. recompute the edge chain: monomials -> z1 -> a1 -> z2 -> kernel basis kb ------------------------
-  fold_w1_kernel<<<kC, 128, 0, s>>>(P + lay->basis_w1, P + lay->basis_b1, fold_table, 258, b.w1m);
-  CUDA_LAUNCH_CHECK();
-  if (Re > 0) {
-    edge_mono_kernel<<<blocks_for(Re, 128), 128, 0, s>>>(dir, dist, lattice, crystal_of_atom, src, num_edges_ptr, Ecap,
-                                                         w->ori, radius, b.mono, b.win);
-    CUDA_LAUNCH_CHECK();
-    TRY((gemm<true, true>(g, b.mono, 128, b.w1m, 128, b.z1, kC, (int)Re, kC, kMonoPad, 1.f, nullptr, false)));
-    TRY(gelu_f(b.z1, Re, kC, nullptr, 1, b.a1));
-    TRY((gemm<true, true>(g, b.a1, kC, P + lay->basis_w2, kC, b.z2, kD, (int)Re, kD, kC, 1.f, P + lay->basis_b2, false)));
-    TRY(gelu_f(b.z2, Re, kD, b.win, kO, b.kb));
-    TRY(zero(b.dkb, Re * kD));
-  }
+  // ---- 1. the edge chain: monomials -> z1 -> a1 -> z2 -> kernel basis kb ---------------------------------
+  // (kept in the workspace by arreau_ponita_forward_train; recomputed here after the plain fp32 forward)
+  if (!forward_kept)
+    TRY(edge_chain_forward(g, b, P, lay, w, fold_table, src, dist, dir, lattice, crystal_of_atom, num_edges_ptr, Ecap, radius));
+  if (Re > 0) TRY(zero(b.dkb, Re * kD));
   // fiber chain forward (ponita.py:66,95): rows (o,p)
   const int Rf = kO * kO;
   fiber_rows_kernel<<<1, 256, 0, s>>>(w->ori, b.frow);
@@ -1189,8 +1218,11 @@ extern "C" int arreau_ponita_backward(const float* params, const arreau_train_la
     // ConvNext MLP recompute (convnext.py:25-32): y = LN(x2), z = y W1^T + b1, a = gelu(z), m = a W2^T + b2
     ln_fwd_kernel<<<blocks_for(Rn * 32, 256), 256, 0, s>>>(x2, P + lay->norm_w + l * kC, P + lay->norm_b + l * kC, Rn, b.y);
     CUDA_LAUNCH_CHECK();
-    TRY((gemm<true, true>(g, b.y, kC, W1, kC, b.z, kW, (int)Rn, kW, kC, 1.f, P + lay->lin1_b + l * kW, false)));
-    TRY(gelu_f(b.z, Rn, kW, nullptr, 1, b.a));
+    // z: kept per layer by arreau_ponita_forward_train, else recomputed
+    const float* zl = forward_kept ? b.zs + (size_t)l * Rn * kW : b.z;
+    if (!forward_kept)
+      TRY((gemm<true, true>(g, b.y, kC, W1, kC, b.z, kW, (int)Rn, kW, kC, 1.f, P + lay->lin1_b + l * kW, false)));
+    TRY(gelu_f(zl, Rn, kW, nullptr, 1, b.a));
     TRY((gemm<true, true>(g, b.a, kW, W2, kW, b.m, kC, (int)Rn, kC, kW, 1.f, P + lay->lin2_b + l * kC, false)));
     // h_out = h_in + ls * m
     TRY(colsum(g, b.dh, b.m, Rn, kC, kC, Gd + lay->layer_scale + l * kC, false));
@@ -1199,7 +1231,7 @@ extern "C" int arreau_ponita_backward(const float* params, const arreau_train_la
     TRY(colsum(g, b.m, nullptr, Rn, kC, kC, Gd + lay->lin2_b + l * kC, false));
     TRY((gemm<false, false>(g, b.m, kC, b.a, kW, Gd + lay->lin2_w + (size_t)l * kC * kW, kW, kC, kW, Rn, 1.f, nullptr, false)));
     TRY((gemm<true, false>(g, b.m, kC, W2, kW, b.da, kW, (int)Rn, kW, kC, 1.f, nullptr, false)));
-    TRY(gelu_b(b.z, b.da, Rn, kW, nullptr, 1, b.da));                                                  // b.da = dz
+    TRY(gelu_b(zl, b.da, Rn, kW, nullptr, 1, b.da));                                                   // b.da = dz
     TRY(colsum(g, b.da, nullptr, Rn, kW, kW, Gd + lay->lin1_b + l * kW, false));
     TRY((gemm<false, false>(g, b.da, kW, b.y, kC, Gd + lay->lin1_w + (size_t)l * kW * kC, kC, kW, kC, Rn, 1.f, nullptr, false)));
     TRY((gemm<true, false>(g, b.da, kW, W1, kC, b.dy, kC, (int)Rn, kC, kW, 1.f, nullptr, false)));
@@ -1279,5 +1311,78 @@ extern "C" int arreau_ponita_backward(const float* params, const arreau_train_la
   TRY((gemm<false, false>(g, b.fda1, kC, b.frow, 16, b.fdw16, 16, kC, 16, Rf, 1.f, nullptr, false)));
   unpack_fiber_w1_grad_kernel<<<1, kC, 0, s>>>(b.fdw16, Gd + lay->fiber_w1, Gd + lay->fiber_b1);
   CUDA_LAUNCH_CHECK();
+  return ARREAU_OK;
+}
+
+// Training forward with every dense contraction on the generic GEMM (tcgen05 kind::tf32 under ARREAU_PRECISION_TF32) and
+// its activations KEPT for arreau_ponita_backward(forward_kept = 1): the edge chain (mono, z1, a1, z2, kb) and the
+// ConvNext hidden pre-activations of every layer stay in `workspace`, h / x1 / x2 of every layer and the per-layer
+// spatial kernels in `ws` as after arreau_ponita_forward with the debug buffers set.  Same mathematics as
+// arreau_ponita_forward (ponita/models/ponita.py:88-123); the message pass, fiber conv + LayerNorm, embedding and
+// read-outs are the fp32 kernels of that function.
+extern "C" int arreau_ponita_forward_train(const float* params, const arreau_train_layout_t* lay, const arreau_weights* w,
+                                           const arreau_workspace* ws, const int32_t* fold_table, const float* x,
+                                           const float* vec, const int32_t* row_ptr, const int32_t* src, const double* dist,
+                                           const double* dir, const double* lattice, const int32_t* atom_offset,
+                                           const int32_t* crystal_of_atom, int32_t N, int32_t G, double radius,
+                                           float* workspace, int64_t workspace_bytes, int32_t precision, float* logits,
+                                           float* score, float* len0, void* stream) {
+  if (!params || !lay || !w || !ws || !fold_table || !workspace) return ARREAU_ERR_NULL;
+  if (N < 0 || G < 0) return ARREAU_ERR_BAD_SHAPE;
+  if (N == 0) return ARREAU_OK;
+  if (!ws->h || !ws->y || !ws->acc || !ws->h_debug || !ws->x1_debug || !ws->x2_debug || !ws->kernels || !x || !vec ||
+      !row_ptr || !src || !dist || !dir || !lattice || !atom_offset || !crystal_of_atom || !logits || !score || !len0)
+    return ARREAU_ERR_NULL;
+  if (precision != ARREAU_PRECISION_FP32 && precision != ARREAU_PRECISION_TF32) return ARREAU_ERR_UNSUPPORTED;
+  const int Z = w->num_states, F = w->num_scalar, V = w->num_vec, FV = F + V;
+  const int xl_pitch = ((FV + 127) / 128) * 128;
+  const long long Ecap = ws->edge_capacity;
+  BwdBuffers b = carve(workspace, N, Ecap, xl_pitch);
+  if ((int64_t)(b.total * sizeof(float)) > workspace_bytes) return ARREAU_ERR_WORKSPACE;
+  cudaStream_t s = (cudaStream_t)stream;
+  Gemm g{s, b.partial, kPartialFloats, sm_count()};
+  g.tf32 = precision == ARREAU_PRECISION_TF32;
+  const long long Re = Ecap * kO, Rn = (long long)N * kO;
+  const size_t node_elems = (size_t)N * kO * kC, layer_kernel_elems = (size_t)Ecap * kO * kC;
+  const float* P = params;
+  // embedding (ponita.py:98)
+  if (ws->onehot_types)
+    TRY(arreau_node_embed_typed(x, ws->onehot_types, Z, vec, w->w_embed_t, w->ori, N, F, V, ws->h, stream));
+  else
+    TRY(arreau_node_embed(x, vec, w->w_embed_t, w->ori, N, F, V, ws->h, stream));
+  {
+    cudaError_t e = cudaMemcpyAsync(ws->h_debug, ws->h, node_elems * sizeof(float), cudaMemcpyDeviceToDevice, s);
+    if (e != cudaSuccess) return (int)e;
+  }
+  // edge chain and the five kernel projections kernels[l] = kb Wk_l^T (conv.py:110)
+  TRY(edge_chain_forward(g, b, P, lay, w, fold_table, src, dist, dir, lattice, crystal_of_atom, row_ptr + N, Ecap, radius));
+  for (int l = 0; l < kL && Re > 0; ++l)
+    TRY((gemm<true, true>(g, b.kb, kD, P + lay->conv_kernel_w + (size_t)l * kC * kD, kD,
+                          (float*)ws->kernels + (size_t)l * layer_kernel_elems, kC, (int)Re, kC, kD, 1.f, nullptr, false)));
+  for (int l = 0; l < kL; ++l) {
+    const float* kern = (const float*)ws->kernels + (size_t)l * layer_kernel_elems;
+    // message pass + fiber conv + bias + LayerNorm (conv.py:111-133, convnext.py:25): y = LN(x2)
+    TRY(arreau_message_fiber_norm(kern, 0, ws->h, row_ptr, src, w->fiber_kernel + (size_t)l * kO * kO * kC, nullptr,
+                                  w->conv_bias + l * kC, w->ln_w + l * kC, w->ln_b + l * kC, N, ws->y, 0,
+                                  ws->x1_debug + l * node_elems, ws->x2_debug + l * node_elems, stream));
+    // ConvNext MLP (convnext.py:26-32): z = y W1^T + b1 (kept), a = gelu(z), m = a W2^T + b2, h += ls * m
+    float* zl = b.zs + (size_t)l * Rn * kW;
+    TRY((gemm<true, true>(g, (const float*)ws->y, kC, P + lay->lin1_w + (size_t)l * kW * kC, kC, zl, kW, (int)Rn, kW, kC, 1.f,
+                          P + lay->lin1_b + l * kW, false)));
+    gelu_fwd_kernel<<<blocks_for(Rn * kW / 4, 256), 256, 0, s>>>(zl, Rn * kW, kW, nullptr, 1, b.a);
+    CUDA_LAUNCH_CHECK();
+    TRY((gemm<true, true>(g, b.a, kW, P + lay->lin2_w + (size_t)l * kC * kW, kW, b.m, kC, (int)Rn, kC, kW, 1.f,
+                          P + lay->lin2_b + l * kC, false)));
+    residual_add_kernel<<<blocks_for(Rn * kC / 4, 256), 256, 0, s>>>(b.m, P + lay->layer_scale + l * kC, Rn * kC / 4, ws->h);
+    CUDA_LAUNCH_CHECK();
+    {
+      cudaError_t e = cudaMemcpyAsync(ws->h_debug + (size_t)(l + 1) * node_elems, ws->h, node_elems * sizeof(float),
+                                      cudaMemcpyDeviceToDevice, s);
+      if (e != cudaSuccess) return (int)e;
+    }
+    TRY(arreau_readout_accumulate(ws->h, w->wr_t + (size_t)l * kC * (Z + 4), w->br + l * (Z + 4), w->ori, N, Z, l == 0,
+                                  ws->acc, stream));
+  }
+  TRY(arreau_readout_finalize(ws->acc, atom_offset, N, G, Z, kL, logits, score, len0, stream));
   return ARREAU_OK;
 }

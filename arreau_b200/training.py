@@ -215,13 +215,36 @@ class TrainEngine:
                   self.d_alpha_bars.data_ptr(), e.G, e.lengths.data_ptr(), s)
         e.angles.copy_(self.angles0)
 
+    def _workspace(self) -> torch.Tensor:
+        e = self.eng
+        need = int(_lib.load().arreau_ponita_backward_workspace_bytes(e.N, e.edge_capacity, e.F, 4))
+        if need < 0:
+            _lib.check(need, "arreau_ponita_backward_workspace_bytes")
+        if self._bwd_ws is None or self._bwd_ws.numel() * 4 < need:
+            self._bwd_ws = None
+            self._bwd_ws = torch.empty((need + 3) // 4, dtype=torch.float32, device=self.device)
+        return self._bwd_ws
+
     def predict(self) -> None:
-        """DiffusionLoss.predict_scores (diffusion_loss.py:112-197) on the noised batch; per-layer buffers kept."""
+        """DiffusionLoss.predict_scores (diffusion_loss.py:112-197) on the noised batch; per-layer buffers kept.
+        backward_precision "tf32": the forward's dense contractions run on the tcgen05 TF32 GEMM as well and keep their
+        activations for the backward (arreau_ponita_forward_train); "fp32": the plain fp32 forward (the parity path),
+        the backward recomputes what it needs."""
         e = self.eng
         e.prepare_inputs(self.t_atom, from_trig=False)
         e._ensure_capacity()
         e.build_graph()
-        e.forward()
+        self._forward_kept = 0
+        if self.backward_precision == _lib.PRECISION_TF32:
+            ws = self._workspace()
+            _lib.call("arreau_ponita_forward_train", self.p.data.data_ptr(), C.byref(self.p.layout), self.w.ref(), C.byref(e.ws),
+                      self.fold.data_ptr(), e.x.data_ptr(), e.vec.data_ptr(), e.row_ptr.data_ptr(), e.src.data_ptr(),
+                      e.dist.data_ptr(), e.dir.data_ptr(), e.lattice.data_ptr(), e.atom_offset.data_ptr(),
+                      e.crystal_of_atom.data_ptr(), e.N, e.G, e.radius, ws.data_ptr(), ws.numel() * 4, self.backward_precision,
+                      e.logits.data_ptr(), e.score.data_ptr(), e.len0.data_ptr(), e.stream)
+            self._forward_kept = 1
+        else:
+            e.forward()
 
     def compute_loss(self) -> torch.Tensor:
         e, tb = self.eng, self.tabs
@@ -239,17 +262,13 @@ class TrainEngine:
         dlogits = self.dlogits if dlogits is None else dlogits
         dscore = self.dscore if dscore is None else dscore
         dlen0 = self.dlen0 if dlen0 is None else dlen0
-        need = int(_lib.load().arreau_ponita_backward_workspace_bytes(e.N, e.edge_capacity, e.F, 4))
-        if need < 0:
-            _lib.check(need, "arreau_ponita_backward_workspace_bytes")
-        if self._bwd_ws is None or self._bwd_ws.numel() * 4 < need:
-            self._bwd_ws = torch.empty((need + 3) // 4, dtype=torch.float32, device=self.device)
+        self._workspace()
         _lib.call("arreau_ponita_backward", self.p.data.data_ptr(), C.byref(self.p.layout), self.w.ref(), C.byref(e.ws),
                   self.fold.data_ptr(), e.x.data_ptr(), e.vec.data_ptr(), e.row_ptr.data_ptr(), e.src.data_ptr(),
                   e.dst.data_ptr(), e.dist.data_ptr(), e.dir.data_ptr(), e.lattice.data_ptr(), e.atom_offset.data_ptr(),
                   e.crystal_of_atom.data_ptr(), e.N, e.G, e.radius, dlogits.data_ptr(), dscore.data_ptr(),
                   dlen0.data_ptr(), self._bwd_ws.data_ptr(), self._bwd_ws.numel() * 4, self.p.grad.data_ptr(),
-                  self.backward_precision, e.stream)
+                  self.backward_precision, int(getattr(self, "_forward_kept", 0)), e.stream)
         return self.p.grad
 
     # ------------------------------------------------------------------ the step

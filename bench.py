@@ -294,7 +294,7 @@ def run_train(args):
         print(json.dumps({"metric": "train_crystals_per_sec", "value": world * G / (ms * 1e-3), "unit": "crystals/s",
                           "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": ms,
                           "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-                          "dtype": "f32" if bwd_prec == "fp32" else "f32 forward, tf32 backward GEMMs",
+                          "dtype": "f32" if bwd_prec == "fp32" else "tf32 GEMMs (tcgen05, fp32 accumulate) in forward and backward; fp32 elsewhere",
                           "data": "synthetic", "impl": "ours",
                           "config": {"workload": f"C5: training step (score-matching + D3PM + lattice loss), {G} crystals "
                                                  f"/ {N} atoms / {E} edges per GPU, max_neighbors {args.cap}, "

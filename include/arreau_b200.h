@@ -479,15 +479,31 @@ int64_t arreau_ponita_backward_workspace_bytes(int32_t num_atoms_total, int64_t 
  * outputs (ws->h_debug, x1_debug, x2_debug, kernels must hold that pass; fp32 path).  fold_table[258] i32: monomial
  * index of each PolynomialFeatures(3) column.  Deterministic: split reductions with a fixed-order second stage and a
  * sender-side gather for the transposed message pass, no atomics.  precision: ARREAU_PRECISION_FP32 (FFMA GEMMs,
- * the parity path) or ARREAU_PRECISION_TF32 (every GEMM of the backward on mma.sync TF32 tensor cores with fp32
- * accumulation: operands rounded to 10 mantissa bits, gradients within ~1e-3 of the fp32 path). */
+ * the parity path) or ARREAU_PRECISION_TF32 (every GEMM of the backward on tcgen05 kind::tf32 tensor cores with fp32
+ * accumulation in TMEM: operands rounded to 10 mantissa bits, gradients within ~1e-3 of the fp32 path).
+ * forward_kept: 0 after arreau_ponita_forward (the edge chain and the ConvNext hidden layers are recomputed here),
+ * 1 after arreau_ponita_forward_train on the same `workspace` (they are read from it). */
 int arreau_ponita_backward(const float* params, const arreau_train_layout_t* layout, const arreau_weights* w,
                            const arreau_workspace* ws, const int32_t* fold_table, const float* x, const float* vec,
                            const int32_t* row_ptr, const int32_t* src, const int32_t* dst, const double* dist,
                            const double* dir, const double* lattice, const int32_t* atom_offset,
                            const int32_t* crystal_of_atom, int32_t num_atoms_total, int32_t num_crystals, double radius,
                            const float* dlogits, const float* dscore, const float* dlen0, float* workspace,
-                           int64_t workspace_bytes, float* grads, int32_t precision, void* stream);
+                           int64_t workspace_bytes, float* grads, int32_t precision, int32_t forward_kept, void* stream);
+
+/* The training forward with every dense contraction on the same generic GEMM as the backward (tcgen05 kind::tf32 under
+ * ARREAU_PRECISION_TF32: the edge chain monomials -> basis MLP -> kernel basis, the five kernel projections and the
+ * ConvNext MLP of every layer) and its activations KEPT in `workspace` (same layout and size as
+ * arreau_ponita_backward's), so that arreau_ponita_backward(..., forward_kept = 1) does not recompute them.  Message
+ * pass, fiber conv + LayerNorm, embedding and read-outs are the fp32 kernels of arreau_ponita_forward; ws must carry the
+ * debug buffers (h / x1 / x2 of every layer) and fp32 `kernels`.  Mathematics: ponita/models/ponita.py:88-123. */
+int arreau_ponita_forward_train(const float* params, const arreau_train_layout_t* layout, const arreau_weights* w,
+                                const arreau_workspace* ws, const int32_t* fold_table, const float* x, const float* vec,
+                                const int32_t* row_ptr, const int32_t* src, const double* dist, const double* dir,
+                                const double* lattice, const int32_t* atom_offset, const int32_t* crystal_of_atom,
+                                int32_t num_atoms_total, int32_t num_crystals, double radius, float* workspace,
+                                int64_t workspace_bytes, int32_t precision, float* logits, float* score, float* len0,
+                                void* stream);
 
 /* The fp32 GEMM the backward pass is built from: C[M,N] (=|+=) alpha * A * B (+ bias[n]).  a_k_contiguous: A is stored
  * [M][K] (else [K][M]); b_k_contiguous: B is stored [N][K] (else [K][N]).  Long reductions (K) are split over CTAs
