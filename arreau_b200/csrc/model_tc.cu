@@ -1,15 +1,19 @@
 // tcgen05 (fp16 operands, fp32 accumulation in TMEM) variants of the two GEMM-shaped kernels of the step.
 //
-//   convnext_mlp_tc_kernel   K6   h += layer_scale * (W2 gelu(W1 y + b1) + b2)          convnext.py:26-32
-//   edge_kernels_tc_kernel   K3+K4a invariants -> monomials -> basis MLP -> window -> 5 kernel projections
+//   convnext_mlp_tc_kernel    K6     h += layer_scale * (W2 gelu(W1 y + b1) + b2)          convnext.py:26-32
+//   edge_kernels_tc3_kernel   K3+K4a invariants -> monomials -> basis MLP -> window -> 5 kernel projections
+//   (edge_kernels_tc2_kernel: the same pipeline with ONE epilogue group and run-time clock64 stamps, kept for A/B timing
+//    and for the timeline in profiles/)
 //
-// Both are persistent (one CTA per SM, 128-row tiles) and warp specialised (640 threads):
+// All are persistent (one CTA per SM, 128-row tiles) and warp specialised:
 //   warp 0   producer: cp.async.bulk (TMA engine) of pre-swizzled weight / activation tiles into an mbarrier ring
-//   warp 1   MMA issuer: one thread issues tcgen05.mma (M = 128, N = 128, K = 16) and tcgen05.commit
-//   warp 2   TMEM allocation / release
-//   warps 4..19  epilogue (16 warps: 4 per TMEM lane quarter, each a quarter of the columns): tcgen05.ld ->
-//                bias / GELU / window in registers -> fp16 operand tile of the next GEMM written back to shared
-//                memory in the UMMA layout (the intermediate never leaves the SM), or the final result to HBM.
+//   warp 1   MMA issuer: the warp runs the issue loop uniformly, one elected lane issues tcgen05.mma (M = 128, N = 128,
+//            K = 16) and tcgen05.commit; the hidden slice (MLP) and the kernel basis (edge) are TENSOR-MEMORY operands
+//   warp 2   TMEM allocation / release (MLP: also half of the read-out pooling); warp 3: geometry (edge) / pooling (MLP)
+//   warps 4.. epilogue: tcgen05.ld -> bias / GELU / window in registers -> fp16 operand of the next GEMM written back to
+//            shared memory in the UMMA layout or to tensor memory (tcgen05.st) -- the intermediates never leave the SM --
+//            or the final result to HBM through the TMA engine (bulk stores / bulk reduce-add).  MLP: 16 warps (640
+//            threads); edge: a G-group of 16 warps and an L-group of 8 warps working on different jobs (896 threads).
 #include "common.cuh"
 #include "tc_common.cuh"
 
