@@ -330,6 +330,23 @@ __device__ __forceinline__ void tc_fetch(const float* __restrict__ X, long long 
   }
 }
 
+// L2 prefetch of one operand's slab (128 lines of 128 B) by 128 threads (t = 0..127): the register-staged loaders keep
+// only ONE slab in flight per CTA, so without it every slab of a streamed operand costs a full DRAM round trip
+// (measured 5.6 K cycles per slab on the step's skinny shapes); prefetched two slabs ahead the loads hit L2.
+template <bool KCONTIG>
+__device__ __forceinline__ void tc_prefetch(const float* __restrict__ X, long long ld, int x0, int xext, long long k0,
+                                            long long kend, int t) {
+  const float* p = nullptr;
+  if (KCONTIG) {                       // X[x][k]: one line = the 32 k of row x0 + t
+    if (x0 + t < xext && k0 < kend) p = X + (long long)(x0 + t) * ld + k0;
+  } else {                             // X[k][x]: 4 lines per k row
+    const long long k = k0 + (t >> 2);
+    const int x = x0 + (t & 3) * 32;
+    if (k < kend && x < xext) p = X + k * ld + x;
+  }
+  if (p) asm volatile("prefetch.global.L2 [%0];" ::"l"(p));
+}
+
 template <bool KCONTIG>
 __device__ __forceinline__ void tc_stage(uint8_t* __restrict__ tile, int tid, const float4 (&r)[4]) {
 #pragma unroll
@@ -387,11 +404,23 @@ sgemm_tc_kernel(const float* __restrict__ A, long long lda, const float* __restr
   constexpr uint32_t a_kstep = AK ? 2u : (4096u >> 4), b_kstep = BK ? 2u : (4096u >> 4);   // +8 K per MMA
 
   float4 ra[4], rb[4];
+  constexpr int kPrefetchAhead = 3;            // slabs of L2 prefetch lead
   if (nslabs > 0) {
     tc_fetch<AK>(A, lda, m0, M, kbeg, kend, tid, ra);
     tc_fetch<BK>(B, ldb, n0, N, kbeg, kend, tid, rb);
+#pragma unroll
+    for (int a = 1; a < kPrefetchAhead; ++a) {
+      const long long kp = kbeg + (long long)a * tcg::kSlab;
+      if (tid < 128) tc_prefetch<AK>(A, lda, m0, M, kp, kend, tid);
+      else tc_prefetch<BK>(B, ldb, n0, N, kp, kend, tid - 128);
+    }
   }
   for (int s = 0; s < nslabs; ++s) {
+    {
+      const long long kp = kbeg + (long long)(s + kPrefetchAhead) * tcg::kSlab;
+      if (tid < 128) tc_prefetch<AK>(A, lda, m0, M, kp, kend, tid);
+      else tc_prefetch<BK>(B, ldb, n0, N, kp, kend, tid - 128);
+    }
     const int stage = s % tcg::kStages;
     if (s >= tcg::kStages) mbar_wait(&bar_empty[stage], (uint32_t)((s / tcg::kStages - 1) & 1));   // its MMAs have read it
     uint8_t* const ta = sm + stage * tcg::kStageBytes;
@@ -415,46 +444,54 @@ sgemm_tc_kernel(const float* __restrict__ A, long long lda, const float* __restr
       if (s + 1 == nslabs) umma_commit_e(smem_u32(bar_done), el);
     }
   }
-  // ---- epilogue: warp = (lane quarter q: rows 32 q .. +31, column half: 64 columns) ----
+  // ---- epilogue: TMEM -> registers -> shared memory (row pitch 132 floats: conflict-free 16-byte stores of 32 rows) ->
+  // coalesced 512-byte row segments to global (a thread owns ONE row of the accumulator, so writing it out directly
+  // would touch 32 different rows per store instruction) ----
   const int q = warp & 3, half = warp >> 2;
-  const int m = m0 + q * 32 + lane;
   const bool split = gridDim.z > 1;
   float* out = split ? partial + (size_t)blockIdx.z * M * N : C;
   const long long ldo = split ? (long long)N : ldc;
+  constexpr int kPitch = 132;
+  float* const stage = reinterpret_cast<float*>(sm);          // 128 x 132 floats = 66 KB of the (now idle) ring
   if (nslabs > 0) {
-    mbar_wait(bar_done, 0);
+    mbar_wait(bar_done, 0);                                    // every MMA has completed: accumulators final, ring idle
     tc_fence_after();
   }
+  {
+    float* srow = stage + (q * 32 + lane) * kPitch + half * 64;
 #pragma unroll
-  for (int part = 0; part < 4; ++part) {
-    uint32_t r[16];
-    if (nslabs > 0) {
-      tmem_ld16(tmem + ((uint32_t)(q * 32) << 16) + half * 64 + part * 16, r);
-    } else {
+    for (int part = 0; part < 4; ++part) {
+      uint32_t r[16];
+      if (nslabs > 0) {
+        tmem_ld16(tmem + ((uint32_t)(q * 32) << 16) + half * 64 + part * 16, r);
+      } else {
 #pragma unroll
-      for (int i = 0; i < 16; ++i) r[i] = 0u;
-    }
-    if (m < M) {
-#pragma unroll
-      for (int j = 0; j < 4; ++j) {
-        const int n = n0 + half * 64 + part * 16 + j * 4;
-        if (n >= N) continue;
-        float4 v = make_float4(__uint_as_float(r[4 * j]), __uint_as_float(r[4 * j + 1]), __uint_as_float(r[4 * j + 2]),
-                               __uint_as_float(r[4 * j + 3]));
-        float* p = out + (long long)m * ldo + n;
-        if (!split) {
-          v.x *= alpha; v.y *= alpha; v.z *= alpha; v.w *= alpha;
-          if (bias) {
-            const float4 bb = *reinterpret_cast<const float4*>(bias + n);
-            v.x += bb.x; v.y += bb.y; v.z += bb.z; v.w += bb.w;
-          }
-          if (accumulate) {
-            const float4 c = *reinterpret_cast<const float4*>(p);
-            v.x += c.x; v.y += c.y; v.z += c.z; v.w += c.w;
-          }
-        }
-        *reinterpret_cast<float4*>(p) = v;
+        for (int i = 0; i < 16; ++i) r[i] = 0u;
       }
+#pragma unroll
+      for (int j = 0; j < 4; ++j)
+        *reinterpret_cast<uint4*>(srow + part * 16 + j * 4) = make_uint4(r[4 * j], r[4 * j + 1], r[4 * j + 2], r[4 * j + 3]);
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  {
+    const int n = n0 + lane * 4;
+    float4 bb = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (!split && bias && n < N) bb = *reinterpret_cast<const float4*>(bias + n);
+    for (int r = warp; r < kBM; r += kGT / 32) {
+      const int m = m0 + r;
+      if (m >= M || n >= N) continue;
+      float4 v = *reinterpret_cast<const float4*>(stage + r * kPitch + lane * 4);
+      float* p = out + (long long)m * ldo + n;
+      if (!split) {
+        v.x = fmaf(v.x, alpha, bb.x); v.y = fmaf(v.y, alpha, bb.y); v.z = fmaf(v.z, alpha, bb.z); v.w = fmaf(v.w, alpha, bb.w);
+        if (accumulate) {
+          const float4 c = *reinterpret_cast<const float4*>(p);
+          v.x += c.x; v.y += c.y; v.z += c.z; v.w += c.w;
+        }
+      }
+      *reinterpret_cast<float4*>(p) = v;
     }
   }
   tc_fence_before();
@@ -536,39 +573,56 @@ int gemm(const Gemm& g, const float* A, long long lda, const float* B, long long
 // column sums over rows (bias / scale gradients): out[c] (=|+=) sum_r X[r][c] (* Y[r][c])
 // two stages, fixed order.  ncols % 128 == 0.
 // ================================================================================================
-constexpr int kColSplits = 128;
+constexpr int kColSplits = 1184;    // 8 blocks of 256 threads per SM
 
 template <bool PROD>
-__global__ void __launch_bounds__(128)
+__global__ void __launch_bounds__(256)
 colsum_kernel(const float* __restrict__ X, const float* __restrict__ Y, long long rows, int ncols, long long ld,
               float* __restrict__ partial) {
-  const int c = blockIdx.x * 128 + threadIdx.x;
-  const long long per = (rows + gridDim.y - 1) / gridDim.y;
-  const long long r0 = (long long)blockIdx.y * per, r1 = (r0 + per < rows) ? r0 + per : rows;
-  float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f;
-  long long r = r0;
-  for (; r + 4 <= r1; r += 4) {
-    float a0 = X[(r + 0) * ld + c], a1 = X[(r + 1) * ld + c], a2 = X[(r + 2) * ld + c], a3 = X[(r + 3) * ld + c];
+  // block = 256 threads = (256 / (ncols / 4)) row lanes x (ncols / 4) float4 columns; blockIdx.x = row split.  Each
+  // thread keeps 4 independent 16-byte loads in flight; the row lanes are combined in shared memory in a fixed order.
+  __shared__ float4 red[256];
+  const int c4n = ncols >> 2, lanes = 256 / c4n;
+  const int c4 = threadIdx.x % c4n, rl = threadIdx.x / c4n;
+  const long long per = (rows + gridDim.x - 1) / gridDim.x;
+  const long long r0 = (long long)blockIdx.x * per, r1 = (r0 + per < rows) ? r0 + per : rows;
+  float4 s0 = make_float4(0.f, 0.f, 0.f, 0.f), s1 = s0, s2 = s0, s3 = s0;
+  auto ld4 = [&](long long r) {
+    float4 a = __ldg(reinterpret_cast<const float4*>(X + r * ld) + c4);
     if (PROD) {
-      a0 *= Y[(r + 0) * ld + c]; a1 *= Y[(r + 1) * ld + c]; a2 *= Y[(r + 2) * ld + c]; a3 *= Y[(r + 3) * ld + c];
+      const float4 y = __ldg(reinterpret_cast<const float4*>(Y + r * ld) + c4);
+      a.x *= y.x; a.y *= y.y; a.z *= y.z; a.w *= y.w;
     }
-    s0 += a0; s1 += a1; s2 += a2; s3 += a3;
+    return a;
+  };
+  auto acc = [](float4& s, const float4& a) { s.x += a.x; s.y += a.y; s.z += a.z; s.w += a.w; };
+  long long r = r0 + rl;
+  for (; r + 3LL * lanes < r1; r += 4LL * lanes) {
+    const float4 a0 = ld4(r), a1 = ld4(r + lanes), a2 = ld4(r + 2LL * lanes), a3 = ld4(r + 3LL * lanes);
+    acc(s0, a0); acc(s1, a1); acc(s2, a2); acc(s3, a3);
   }
-  for (; r < r1; ++r) s0 += PROD ? X[r * ld + c] * Y[r * ld + c] : X[r * ld + c];
-  partial[(size_t)blockIdx.y * ncols + c] = (s0 + s1) + (s2 + s3);
+  for (; r < r1; r += lanes) acc(s0, ld4(r));
+  acc(s0, s1); acc(s2, s3); acc(s0, s2);
+  red[threadIdx.x] = s0;
+  __syncthreads();
+  if (rl == 0) {
+    for (int k = 1; k < lanes; ++k) acc(s0, red[k * c4n + c4]);          // fixed order: deterministic
+    reinterpret_cast<float4*>(partial + (size_t)blockIdx.x * ncols)[c4] = s0;
+  }
 }
 
 int colsum(const Gemm& g, const float* X, const float* Y, long long rows, int ncols, long long ld, float* out,
            bool accumulate) {
-  if (ncols % 128 != 0 || (size_t)kColSplits * ncols > g.partial_floats) return ARREAU_ERR_UNSUPPORTED;
+  if (ncols % 128 != 0 || ncols > 1024 || ld % 4 != 0) return ARREAU_ERR_UNSUPPORTED;
   if (rows <= 0) return ARREAU_OK;
-  int splits = (int)((rows + 63) / 64);
+  // enough row splits to put ~2 blocks on every SM, at least 64 rows each, bounded by the split scratch
+  long long splits = (rows + 63) / 64;
   if (splits > kColSplits) splits = kColSplits;
-  dim3 grid(ncols / 128, splits);
-  if (Y) colsum_kernel<true><<<grid, 128, 0, g.s>>>(X, Y, rows, ncols, ld, g.partial);
-  else colsum_kernel<false><<<grid, 128, 0, g.s>>>(X, nullptr, rows, ncols, ld, g.partial);
+  while (splits > 1 && (size_t)splits * ncols > g.partial_floats) --splits;
+  if (Y) colsum_kernel<true><<<(unsigned)splits, 256, 0, g.s>>>(X, Y, rows, ncols, ld, g.partial);
+  else colsum_kernel<false><<<(unsigned)splits, 256, 0, g.s>>>(X, nullptr, rows, ncols, ld, g.partial);
   CUDA_LAUNCH_CHECK();
-  reduce_partials_kernel<<<(ncols + 255) / 256, 256, 0, g.s>>>(g.partial, splits, ncols, ncols, ncols, 1.0f,
+  reduce_partials_kernel<<<(ncols + 255) / 256, 256, 0, g.s>>>(g.partial, (int)splits, ncols, ncols, ncols, 1.0f,
                                                                accumulate ? 1 : 0, out);
   CUDA_LAUNCH_CHECK();
   return ARREAU_OK;
