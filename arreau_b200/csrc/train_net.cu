@@ -504,16 +504,27 @@ sgemm_tc_kernel(const float* __restrict__ A, long long lda, const float* __restr
 
 int g_tf32_legacy = 0;       // debug: 1 = the mma.sync TF32 kernel instead of the tcgen05 one (same-process A/B)
 
-// second stage of every split reduction: out[i] (=|+=) alpha * sum_s partial[s][i] (fixed order)
-__global__ void reduce_partials_kernel(const float* __restrict__ partial, int splits, long long n, long long ldo, int ncols,
-                                       float alpha, int accumulate, float* __restrict__ out) {
-  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= n) return;
+// second stage of every split reduction: out[i] (=|+=) alpha * sum_s partial[s][i] in a FIXED order (deterministic):
+// a block covers 32 consecutive outputs with 8 split lanes; lane j adds the splits j, j + 8, ... in order (coalesced
+// 128-byte reads, chains 8x shorter than one thread per output), then the 8 lane sums are added in lane order.
+__global__ void __launch_bounds__(256)
+reduce_partials_kernel(const float* __restrict__ partial, int splits, long long n, long long ldo, int ncols,
+                       float alpha, int accumulate, float* __restrict__ out) {
+  __shared__ float red[8][32];
+  const int o = threadIdx.x & 31, sl = threadIdx.x >> 5;
+  const long long i = (long long)blockIdx.x * 32 + o;
   float s = 0.f;
-  for (int k = 0; k < splits; ++k) s += partial[(size_t)k * n + i];
-  s *= alpha;
-  float* p = out + (i / ncols) * ldo + (i % ncols);
-  *p = accumulate ? *p + s : s;
+  if (i < n)
+    for (int k = sl; k < splits; k += 8) s += partial[(size_t)k * n + i];
+  red[sl][o] = s;
+  __syncthreads();
+  if (sl == 0 && i < n) {
+#pragma unroll
+    for (int k = 1; k < 8; ++k) s += red[k][o];
+    s *= alpha;
+    float* p = out + (i / ncols) * ldo + (i % ncols);
+    *p = accumulate ? *p + s : s;
+  }
 }
 
 struct Gemm {
@@ -562,7 +573,7 @@ int gemm(const Gemm& g, const float* A, long long lda, const float* B, long long
   if (splits > 1) {
     if (bias) return ARREAU_ERR_UNSUPPORTED;
     const long long n = (long long)M * N;
-    reduce_partials_kernel<<<(unsigned)((n + 255) / 256), 256, 0, g.s>>>(g.partial, splits, n, ldc, N, alpha,
+    reduce_partials_kernel<<<(unsigned)((n + 31) / 32), 256, 0, g.s>>>(g.partial, splits, n, ldc, N, alpha,
                                                                          accumulate ? 1 : 0, C);
     CUDA_LAUNCH_CHECK();
   }
@@ -573,7 +584,7 @@ int gemm(const Gemm& g, const float* A, long long lda, const float* B, long long
 // column sums over rows (bias / scale gradients): out[c] (=|+=) sum_r X[r][c] (* Y[r][c])
 // two stages, fixed order.  ncols % 128 == 0.
 // ================================================================================================
-constexpr int kColSplits = 1184;    // 8 blocks of 256 threads per SM
+constexpr int kColSplits = 592;     // 4 blocks of 256 threads per SM
 
 template <bool PROD>
 __global__ void __launch_bounds__(256)
@@ -622,7 +633,7 @@ int colsum(const Gemm& g, const float* X, const float* Y, long long rows, int nc
   if (Y) colsum_kernel<true><<<(unsigned)splits, 256, 0, g.s>>>(X, Y, rows, ncols, ld, g.partial);
   else colsum_kernel<false><<<(unsigned)splits, 256, 0, g.s>>>(X, nullptr, rows, ncols, ld, g.partial);
   CUDA_LAUNCH_CHECK();
-  reduce_partials_kernel<<<(ncols + 255) / 256, 256, 0, g.s>>>(g.partial, (int)splits, ncols, ncols, ncols, 1.0f,
+  reduce_partials_kernel<<<(ncols + 31) / 32, 256, 0, g.s>>>(g.partial, (int)splits, ncols, ncols, ncols, 1.0f,
                                                                accumulate ? 1 : 0, out);
   CUDA_LAUNCH_CHECK();
   return ARREAU_OK;
@@ -1228,7 +1239,6 @@ extern "C" int arreau_ponita_backward(const float* params, const arreau_train_la
   // (kept in the workspace by arreau_ponita_forward_train; recomputed here after the plain fp32 forward)
   if (!forward_kept)
     TRY(edge_chain_forward(g, b, P, lay, w, fold_table, src, dist, dir, lattice, crystal_of_atom, num_edges_ptr, Ecap, radius));
-  if (Re > 0) TRY(zero(b.dkb, Re * kD));
   // fiber chain forward (ponita.py:66,95): rows (o,p)
   const int Rf = kO * kO;
   fiber_rows_kernel<<<1, 256, 0, s>>>(w->ori, b.frow);
@@ -1295,7 +1305,7 @@ extern "C" int arreau_ponita_backward(const float* params, const arreau_train_la
       if (blocks > kLnBlocks) blocks = kLnBlocks;
       ln_bwd_kernel<<<blocks, kLnWarps * 32, 0, s>>>(x2, b.dy, P + lay->norm_w + l * kC, Rn, b.dx2, b.partial);
       CUDA_LAUNCH_CHECK();
-      reduce_partials_kernel<<<(3 * kC + 255) / 256, 256, 0, s>>>(b.partial, blocks, 3 * kC, 3 * kC, 3 * kC, 1.f, 0, b.small);
+      reduce_partials_kernel<<<(3 * kC + 31) / 32, 256, 0, s>>>(b.partial, blocks, 3 * kC, 3 * kC, 3 * kC, 1.f, 0, b.small);
       CUDA_LAUNCH_CHECK();
       // b.small[0..383] = [dgamma | dbeta | dbias]
       cudaError_t e = cudaMemcpyAsync(Gd + lay->norm_w + l * kC, b.small, sizeof(float) * kC, cudaMemcpyDeviceToDevice, s);
@@ -1313,7 +1323,7 @@ extern "C" int arreau_ponita_backward(const float* params, const arreau_train_la
       fiber_bwd_dfk_kernel<<<fb, 1024, 0, s>>>(x1, b.dx2, N, b.partial);
       CUDA_LAUNCH_CHECK();
       float* dfk = b.dfk + (size_t)l * Rf * kC;
-      reduce_partials_kernel<<<blocks_for((long long)Rf * kC, 256), 256, 0, s>>>(b.partial, fb, (long long)Rf * kC, Rf * kC,
+      reduce_partials_kernel<<<blocks_for((long long)Rf * kC, 32), 256, 0, s>>>(b.partial, fb, (long long)Rf * kC, Rf * kC,
                                                                                Rf * kC, 1.0f / kO, 0, dfk);
       CUDA_LAUNCH_CHECK();
       // fiber_kernel = fkb Wf^T: dWf[C,D] = dfk^T fkb ; dfkb += dfk Wf
@@ -1328,7 +1338,8 @@ extern "C" int arreau_ponita_backward(const float* params, const arreau_train_la
       CUDA_LAUNCH_CHECK();
       // kernel = kb Wk^T: dWk[C,D] = dkern^T kb ; dkb += dkern Wk
       TRY((gemm<false, false>(g, b.dkern, kC, b.kb, kD, Gd + lay->conv_kernel_w + (size_t)l * kC * kD, kD, kC, kD, Re, 1.f, nullptr, false)));
-      TRY((gemm<true, false>(g, b.dkern, kC, Wk, kD, b.dkb, kD, (int)Re, kD, kC, 1.f, nullptr, true)));
+      // dkb accumulates over the layers: the first layer visited (l = L - 1) overwrites, which saves zeroing 4 Re D bytes
+      TRY((gemm<true, false>(g, b.dkern, kC, Wk, kD, b.dkb, kD, (int)Re, kD, kC, 1.f, nullptr, l != kL - 1)));
     }
   }
 
