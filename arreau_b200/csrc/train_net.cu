@@ -33,9 +33,62 @@ namespace {
 // ================================================================================================
 constexpr int kBM = 128, kBN = 128, kBK = 16, kSP = 132, kGT = 256;
 
+// One GEMM launch.  Every matrix is addressed through a ROW PITCH (ld*) over its strided index and a BLOCK STRIDE (*_cblk)
+// over 128-element blocks of its contiguous index: element i of the contiguous index lives at (i >> 7) * cblk + (i & 127).
+// cblk = 128 is the ordinary dense matrix; another value strings together equally shaped slabs that are 128 wide each --
+// the per-layer [rows][128] kernel / kernel-gradient slabs of the five layers act as ONE [rows][640] (or [640][rows]) operand
+// or output, so the five per-layer products of conv.py:110 (and their two transposes in the backward) are one launch each
+// and the shared operand is streamed from HBM once instead of five times.
+// Epilogue (unsplit launches only), in this order:  v = alpha * acc + bias[n];  v *= gelu'(gz[m][n]) * rowscale[m >> 4]  (gz);
+// v += C (accumulate);  C = v;  C2 = gelu(v) * rowscale[m >> 4]  (C2: the activation next to its pre-activation, so that no
+// separate element-wise pass re-reads the matrix).
+struct GemmArgs {
+  const float* A; long long lda, a_cblk;
+  const float* B; long long ldb, b_cblk;
+  float* C; long long ldc, c_cblk;
+  int M, N; long long K, k_per_split;
+  float alpha; const float* bias; int accumulate;
+  float* partial;
+  float* C2;
+  const float* gz; long long gz_ld;
+  const float* rowscale;
+  int mn_lbo, mn_sbo;
+};
+
+__device__ __forceinline__ long long blk_off(long long i, long long cblk) { return (i >> 7) * cblk + (i & 127); }
+
+__device__ __forceinline__ float gelu_grad(float x) {
+  // d/dx [0.5 x (1 + erf(x / sqrt 2))] = 0.5 (1 + erf(x / sqrt 2)) + x exp(-x^2 / 2) / sqrt(2 pi)
+  return 0.5f * (1.0f + erff(x * 0.70710678118654752440f)) + x * expf(-0.5f * x * x) * 0.39894228040143267794f;
+}
+
+// the four accumulators (m, n .. n + 3) of a tile on their way out (n % 4 == 0, n < N)
+__device__ __forceinline__ void gemm_store4(const GemmArgs& g, bool split, int m, int n, float4 v) {
+  if (split) {
+    *reinterpret_cast<float4*>(g.partial + ((size_t)blockIdx.z * g.M + m) * g.N + n) = v;
+    return;
+  }
+  float4 bb = make_float4(0.f, 0.f, 0.f, 0.f);
+  if (g.bias) bb = *reinterpret_cast<const float4*>(g.bias + n);
+  v.x = fmaf(v.x, g.alpha, bb.x); v.y = fmaf(v.y, g.alpha, bb.y); v.z = fmaf(v.z, g.alpha, bb.z); v.w = fmaf(v.w, g.alpha, bb.w);
+  const float rs = g.rowscale ? g.rowscale[m >> 4] : 1.0f;
+  if (g.gz) {
+    const float4 z = *reinterpret_cast<const float4*>(g.gz + (long long)m * g.gz_ld + n);
+    v.x *= gelu_grad(z.x) * rs; v.y *= gelu_grad(z.y) * rs; v.z *= gelu_grad(z.z) * rs; v.w *= gelu_grad(z.w) * rs;
+  }
+  const long long off = (long long)m * g.ldc + blk_off(n, g.c_cblk);
+  if (g.accumulate) {
+    const float4 c = *reinterpret_cast<const float4*>(g.C + off);
+    v.x += c.x; v.y += c.y; v.z += c.z; v.w += c.w;
+  }
+  *reinterpret_cast<float4*>(g.C + off) = v;
+  if (g.C2)
+    *reinterpret_cast<float4*>(g.C2 + off) = make_float4(gelu_erf(v.x) * rs, gelu_erf(v.y) * rs, gelu_erf(v.z) * rs, gelu_erf(v.w) * rs);
+}
+
 template <bool KCONTIG>
-__device__ __forceinline__ void tile_fetch(const float* __restrict__ X, long long ld, int x0, int xext, long long k0,
-                                           long long kend, int tid, float4 (&r)[2]) {
+__device__ __forceinline__ void tile_fetch(const float* __restrict__ X, long long ld, long long cblk, int x0, int xext,
+                                           long long k0, long long kend, int tid, float4 (&r)[2]) {
   // KCONTIG: X[x][k]: float4 v -> x = v >> 2, k = (v & 3) * 4 ; else X[k][x]: v -> k = v >> 5, x = (v & 31) * 4
 #pragma unroll
   for (int u = 0; u < 2; ++u) {
@@ -44,11 +97,11 @@ __device__ __forceinline__ void tile_fetch(const float* __restrict__ X, long lon
     if (KCONTIG) {
       const int x = x0 + (v >> 2);
       const long long k = k0 + (v & 3) * 4;
-      if (x < xext && k < kend) r[u] = __ldg(reinterpret_cast<const float4*>(X + (long long)x * ld + k));
+      if (x < xext && k < kend) r[u] = __ldg(reinterpret_cast<const float4*>(X + (long long)x * ld + blk_off(k, cblk)));
     } else {
       const long long k = k0 + (v >> 5);
       const int x = x0 + (v & 31) * 4;
-      if (k < kend && x < xext) r[u] = __ldg(reinterpret_cast<const float4*>(X + k * ld + x));
+      if (k < kend && x < xext) r[u] = __ldg(reinterpret_cast<const float4*>(X + k * ld + blk_off(x, cblk)));
     }
   }
 }
@@ -59,37 +112,35 @@ __device__ __forceinline__ float to_tf32(float x) {
   return __uint_as_float(r);
 }
 
-template <bool KCONTIG, int PITCH = kSP, bool TF32 = false>
+template <bool KCONTIG>
 __device__ __forceinline__ void tile_stage(float* __restrict__ S, int tid, const float4 (&r)[2]) {
 #pragma unroll
   for (int u = 0; u < 2; ++u) {
     const int v = tid + u * kGT;
-    float4 q = r[u];
-    if (TF32) q = make_float4(to_tf32(q.x), to_tf32(q.y), to_tf32(q.z), to_tf32(q.w));
+    const float4 q = r[u];
     if (KCONTIG) {
       const int x = v >> 2, k = (v & 3) * 4;
-      S[(k + 0) * PITCH + x] = q.x;
-      S[(k + 1) * PITCH + x] = q.y;
-      S[(k + 2) * PITCH + x] = q.z;
-      S[(k + 3) * PITCH + x] = q.w;
+      S[(k + 0) * kSP + x] = q.x;
+      S[(k + 1) * kSP + x] = q.y;
+      S[(k + 2) * kSP + x] = q.z;
+      S[(k + 3) * kSP + x] = q.w;
     } else {
       const int k = v >> 5, x = (v & 31) * 4;
-      *reinterpret_cast<float4*>(S + k * PITCH + x) = q;
+      *reinterpret_cast<float4*>(S + k * kSP + x) = q;
     }
   }
 }
 
 template <bool AK, bool BK>
 __global__ void __launch_bounds__(kGT)
-sgemm_kernel(const float* __restrict__ A, long long lda, const float* __restrict__ B, long long ldb, float* __restrict__ C,
-             long long ldc, int M, int N, long long K, long long k_per_split, float alpha,
-             const float* __restrict__ bias, int accumulate, float* __restrict__ partial) {
+sgemm_kernel(const __grid_constant__ GemmArgs g) {
   __shared__ __align__(16) float As[2][kBK * kSP];
   __shared__ __align__(16) float Bs[2][kBK * kSP];
   const int tid = threadIdx.x, ty = tid >> 4, tx = tid & 15;
   const int m0 = blockIdx.y * kBM, n0 = blockIdx.x * kBN;
-  const long long kbeg = (long long)blockIdx.z * k_per_split;
-  const long long kend = (kbeg + k_per_split < K) ? kbeg + k_per_split : K;
+  const int M = g.M, N = g.N;
+  const long long kbeg = (long long)blockIdx.z * g.k_per_split;
+  const long long kend = (kbeg + g.k_per_split < g.K) ? kbeg + g.k_per_split : g.K;
   float2 acc[8][4];
 #pragma unroll
   for (int i = 0; i < 8; ++i)
@@ -97,8 +148,8 @@ sgemm_kernel(const float* __restrict__ A, long long lda, const float* __restrict
     for (int j = 0; j < 4; ++j) acc[i][j] = make_float2(0.f, 0.f);
   float4 ra[2], rb[2];
   if (kbeg < kend) {
-    tile_fetch<AK>(A, lda, m0, M, kbeg, kend, tid, ra);
-    tile_fetch<BK>(B, ldb, n0, N, kbeg, kend, tid, rb);
+    tile_fetch<AK>(g.A, g.lda, g.a_cblk, m0, M, kbeg, kend, tid, ra);
+    tile_fetch<BK>(g.B, g.ldb, g.b_cblk, n0, N, kbeg, kend, tid, rb);
     tile_stage<AK>(As[0], tid, ra);
     tile_stage<BK>(Bs[0], tid, rb);
   }
@@ -107,8 +158,8 @@ sgemm_kernel(const float* __restrict__ A, long long lda, const float* __restrict
   for (long long k0 = kbeg; k0 < kend; k0 += kBK) {
     const bool more = k0 + kBK < kend;
     if (more) {
-      tile_fetch<AK>(A, lda, m0, M, k0 + kBK, kend, tid, ra);
-      tile_fetch<BK>(B, ldb, n0, N, k0 + kBK, kend, tid, rb);
+      tile_fetch<AK>(g.A, g.lda, g.a_cblk, m0, M, k0 + kBK, kend, tid, ra);
+      tile_fetch<BK>(g.B, g.ldb, g.b_cblk, n0, N, k0 + kBK, kend, tid, rb);
     }
     const float* a = As[buf];
     const float* b = Bs[buf];
@@ -136,8 +187,6 @@ sgemm_kernel(const float* __restrict__ A, long long lda, const float* __restrict
     buf ^= 1;
   }
   const bool split = gridDim.z > 1;
-  float* out = split ? partial + (size_t)blockIdx.z * M * N : C;
-  const long long ldo = split ? (long long)N : ldc;
 #pragma unroll
   for (int i = 0; i < 8; ++i) {
     const int m = m0 + ((i < 4) ? (ty * 4 + i) : (64 + ty * 4 + i - 4));
@@ -146,125 +195,10 @@ sgemm_kernel(const float* __restrict__ A, long long lda, const float* __restrict
     for (int half = 0; half < 2; ++half) {
       const int n = n0 + half * 64 + tx * 4;
       if (n >= N) continue;
-      float4 v = make_float4(acc[i][half * 2].x, acc[i][half * 2].y, acc[i][half * 2 + 1].x, acc[i][half * 2 + 1].y);
-      float* p = out + (long long)m * ldo + n;
-      if (!split) {
-        v.x *= alpha; v.y *= alpha; v.z *= alpha; v.w *= alpha;
-        if (bias) {
-          const float4 bb = *reinterpret_cast<const float4*>(bias + n);
-          v.x += bb.x; v.y += bb.y; v.z += bb.z; v.w += bb.w;
-        }
-        if (accumulate) {
-          const float4 c = *reinterpret_cast<const float4*>(p);
-          v.x += c.x; v.y += c.y; v.z += c.z; v.w += c.w;
-        }
-      }
-      *reinterpret_cast<float4*>(p) = v;
+      gemm_store4(g, split, m, n,
+                  make_float4(acc[i][half * 2].x, acc[i][half * 2].y, acc[i][half * 2 + 1].x, acc[i][half * 2 + 1].y));
     }
   }
-}
-
-// TF32 variant of the same GEMM (ARREAU_PRECISION_TF32): identical tiling and operand staging (values rounded to
-// TF32 with cvt.rna on their way into shared memory), the inner product on mma.sync.m16n8k8 with fp32 accumulation.
-// 8 warps = 2 (M) x 4 (N); a warp owns a 64 x 32 block = 4 x 4 mma tiles.  Shared pitch 136: fragment loads
-// (address = k * 136 + column) hit 32 distinct banks.
-constexpr int kTP = 136;
-
-template <bool AK, bool BK>
-__global__ void __launch_bounds__(kGT)
-sgemm_tf32_kernel(const float* __restrict__ A, long long lda, const float* __restrict__ B, long long ldb, float* __restrict__ C,
-                  long long ldc, int M, int N, long long K, long long k_per_split, float alpha,
-                  const float* __restrict__ bias, int accumulate, float* __restrict__ partial) {
-  __shared__ __align__(16) float As[2][kBK * kTP];
-  __shared__ __align__(16) float Bs[2][kBK * kTP];
-  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31, g = lane >> 2, t = lane & 3;
-  const int wm = (warp & 1) * 64, wn = (warp >> 1) * 32;
-  const int m0 = blockIdx.y * kBM, n0 = blockIdx.x * kBN;
-  const long long kbeg = (long long)blockIdx.z * k_per_split;
-  const long long kend = (kbeg + k_per_split < K) ? kbeg + k_per_split : K;
-  float acc[4][4][4];
-#pragma unroll
-  for (int i = 0; i < 4; ++i)
-#pragma unroll
-    for (int j = 0; j < 4; ++j)
-#pragma unroll
-      for (int q = 0; q < 4; ++q) acc[i][j][q] = 0.f;
-  float4 ra[2], rb[2];
-  if (kbeg < kend) {
-    tile_fetch<AK>(A, lda, m0, M, kbeg, kend, tid, ra);
-    tile_fetch<BK>(B, ldb, n0, N, kbeg, kend, tid, rb);
-    tile_stage<AK, kTP, true>(As[0], tid, ra);
-    tile_stage<BK, kTP, true>(Bs[0], tid, rb);
-  }
-  __syncthreads();
-  int buf = 0;
-  for (long long k0 = kbeg; k0 < kend; k0 += kBK) {
-    const bool more = k0 + kBK < kend;
-    if (more) {
-      tile_fetch<AK>(A, lda, m0, M, k0 + kBK, kend, tid, ra);
-      tile_fetch<BK>(B, ldb, n0, N, k0 + kBK, kend, tid, rb);
-    }
-    const float* a = As[buf];
-    const float* b = Bs[buf];
-#pragma unroll
-    for (int ks = 0; ks < kBK; ks += 8) {
-      uint32_t af[4][4], bf[4][2];
-#pragma unroll
-      for (int i = 0; i < 4; ++i) {
-        const float* p = a + (ks + t) * kTP + wm + i * 16 + g;
-        af[i][0] = __float_as_uint(p[0]);
-        af[i][1] = __float_as_uint(p[8]);
-        af[i][2] = __float_as_uint(p[4 * kTP]);
-        af[i][3] = __float_as_uint(p[4 * kTP + 8]);
-      }
-#pragma unroll
-      for (int j = 0; j < 4; ++j) {
-        const float* p = b + (ks + t) * kTP + wn + j * 8 + g;
-        bf[j][0] = __float_as_uint(p[0]);
-        bf[j][1] = __float_as_uint(p[4 * kTP]);
-      }
-#pragma unroll
-      for (int i = 0; i < 4; ++i)
-#pragma unroll
-        for (int j = 0; j < 4; ++j)
-          asm volatile(
-              "mma.sync.aligned.m16n8k8.row.col.f32.tf32.tf32.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
-              : "+f"(acc[i][j][0]), "+f"(acc[i][j][1]), "+f"(acc[i][j][2]), "+f"(acc[i][j][3])
-              : "r"(af[i][0]), "r"(af[i][1]), "r"(af[i][2]), "r"(af[i][3]), "r"(bf[j][0]), "r"(bf[j][1]));
-    }
-    if (more) {
-      tile_stage<AK, kTP, true>(As[buf ^ 1], tid, ra);
-      tile_stage<BK, kTP, true>(Bs[buf ^ 1], tid, rb);
-    }
-    __syncthreads();
-    buf ^= 1;
-  }
-  const bool split = gridDim.z > 1;
-  float* out = split ? partial + (size_t)blockIdx.z * M * N : C;
-  const long long ldo = split ? (long long)N : ldc;
-#pragma unroll
-  for (int i = 0; i < 4; ++i)
-#pragma unroll
-    for (int hrow = 0; hrow < 2; ++hrow) {
-      const int m = m0 + wm + i * 16 + g + hrow * 8;
-      if (m >= M) continue;
-#pragma unroll
-      for (int j = 0; j < 4; ++j) {
-        const int n = n0 + wn + j * 8 + 2 * t;
-        if (n >= N) continue;
-        float2 v = make_float2(acc[i][j][hrow * 2], acc[i][j][hrow * 2 + 1]);
-        float* p = out + (long long)m * ldo + n;
-        if (!split) {
-          v.x *= alpha; v.y *= alpha;
-          if (bias) { v.x += bias[n]; v.y += bias[n + 1]; }
-          if (accumulate) {
-            const float2 c = *reinterpret_cast<const float2*>(p);
-            v.x += c.x; v.y += c.y;
-          }
-        }
-        *reinterpret_cast<float2*>(p) = v;
-      }
-    }
 }
 
 // ================================================================================================
@@ -312,8 +246,8 @@ __device__ __forceinline__ void umma_tf32_e(uint32_t tmem_d, uint32_t a_lo, uint
 int g_tc_mn_lbo = 512, g_tc_mn_sbo = 2048;       // MN-major descriptor strides (bytes); debug-settable
 
 template <bool KCONTIG>
-__device__ __forceinline__ void tc_fetch(const float* __restrict__ X, long long ld, int x0, int xext, long long k0,
-                                         long long kend, int tid, float4 (&r)[4]) {
+__device__ __forceinline__ void tc_fetch(const float* __restrict__ X, long long ld, long long cblk, int x0, int xext,
+                                         long long k0, long long kend, int tid, float4 (&r)[4]) {
 #pragma unroll
   for (int u = 0; u < 4; ++u) {
     const int v = tid + u * kGT;
@@ -321,11 +255,11 @@ __device__ __forceinline__ void tc_fetch(const float* __restrict__ X, long long 
     if (KCONTIG) {                       // X[x][k]: v -> row x = v >> 3, 16-byte chunk (4 k) = v & 7
       const int x = x0 + (v >> 3);
       const long long k = k0 + (v & 7) * 4;
-      if (x < xext && k < kend) r[u] = __ldg(reinterpret_cast<const float4*>(X + (long long)x * ld + k));
+      if (x < xext && k < kend) r[u] = __ldg(reinterpret_cast<const float4*>(X + (long long)x * ld + blk_off(k, cblk)));
     } else {                             // X[k][x]: v -> k = v >> 5, 4 x-elements = v & 31
       const long long k = k0 + (v >> 5);
       const int x = x0 + (v & 31) * 4;
-      if (k < kend && x < xext) r[u] = __ldg(reinterpret_cast<const float4*>(X + k * ld + x));
+      if (k < kend && x < xext) r[u] = __ldg(reinterpret_cast<const float4*>(X + k * ld + blk_off(x, cblk)));
     }
   }
 }
@@ -334,15 +268,15 @@ __device__ __forceinline__ void tc_fetch(const float* __restrict__ X, long long 
 // only ONE slab in flight per CTA, so without it every slab of a streamed operand costs a full DRAM round trip
 // (measured 5.6 K cycles per slab on the step's skinny shapes); prefetched two slabs ahead the loads hit L2.
 template <bool KCONTIG>
-__device__ __forceinline__ void tc_prefetch(const float* __restrict__ X, long long ld, int x0, int xext, long long k0,
-                                            long long kend, int t) {
+__device__ __forceinline__ void tc_prefetch(const float* __restrict__ X, long long ld, long long cblk, int x0, int xext,
+                                            long long k0, long long kend, int t) {
   const float* p = nullptr;
   if (KCONTIG) {                       // X[x][k]: one line = the 32 k of row x0 + t
-    if (x0 + t < xext && k0 < kend) p = X + (long long)(x0 + t) * ld + k0;
+    if (x0 + t < xext && k0 < kend) p = X + (long long)(x0 + t) * ld + blk_off(k0, cblk);
   } else {                             // X[k][x]: 4 lines per k row
     const long long k = k0 + (t >> 2);
     const int x = x0 + (t & 3) * 32;
-    if (k < kend && x < xext) p = X + k * ld + x;
+    if (k < kend && x < xext) p = X + k * ld + blk_off(x, cblk);
   }
   if (p) asm volatile("prefetch.global.L2 [%0];" ::"l"(p));
 }
@@ -367,10 +301,12 @@ __device__ __forceinline__ void tc_stage(uint8_t* __restrict__ tile, int tid, co
 
 template <bool AK, bool BK>
 __global__ void __launch_bounds__(kGT, 2)
-sgemm_tc_kernel(const float* __restrict__ A, long long lda, const float* __restrict__ B, long long ldb, float* __restrict__ C,
-                long long ldc, int M, int N, long long K, long long k_per_split, float alpha,
-                const float* __restrict__ bias, int accumulate, float* __restrict__ partial, int mn_lbo, int mn_sbo) {
+sgemm_tc_kernel(const __grid_constant__ GemmArgs g) {
   using namespace tc;
+  const float* __restrict__ A = g.A;
+  const float* __restrict__ B = g.B;
+  const long long lda = g.lda, ldb = g.ldb, K = g.K, k_per_split = g.k_per_split;
+  const int M = g.M, N = g.N, mn_lbo = g.mn_lbo, mn_sbo = g.mn_sbo;
   extern __shared__ __align__(1024) uint8_t gsm_raw[];
   const uint32_t base = (smem_u32(gsm_raw) + 1023u) & ~1023u;
   uint8_t* const sm = gsm_raw + (base - smem_u32(gsm_raw));
@@ -406,20 +342,20 @@ sgemm_tc_kernel(const float* __restrict__ A, long long lda, const float* __restr
   float4 ra[4], rb[4];
   constexpr int kPrefetchAhead = 3;            // slabs of L2 prefetch lead
   if (nslabs > 0) {
-    tc_fetch<AK>(A, lda, m0, M, kbeg, kend, tid, ra);
-    tc_fetch<BK>(B, ldb, n0, N, kbeg, kend, tid, rb);
+    tc_fetch<AK>(A, lda, g.a_cblk, m0, M, kbeg, kend, tid, ra);
+    tc_fetch<BK>(B, ldb, g.b_cblk, n0, N, kbeg, kend, tid, rb);
 #pragma unroll
     for (int a = 1; a < kPrefetchAhead; ++a) {
       const long long kp = kbeg + (long long)a * tcg::kSlab;
-      if (tid < 128) tc_prefetch<AK>(A, lda, m0, M, kp, kend, tid);
-      else tc_prefetch<BK>(B, ldb, n0, N, kp, kend, tid - 128);
+      if (tid < 128) tc_prefetch<AK>(A, lda, g.a_cblk, m0, M, kp, kend, tid);
+      else tc_prefetch<BK>(B, ldb, g.b_cblk, n0, N, kp, kend, tid - 128);
     }
   }
   for (int s = 0; s < nslabs; ++s) {
     {
       const long long kp = kbeg + (long long)(s + kPrefetchAhead) * tcg::kSlab;
-      if (tid < 128) tc_prefetch<AK>(A, lda, m0, M, kp, kend, tid);
-      else tc_prefetch<BK>(B, ldb, n0, N, kp, kend, tid - 128);
+      if (tid < 128) tc_prefetch<AK>(A, lda, g.a_cblk, m0, M, kp, kend, tid);
+      else tc_prefetch<BK>(B, ldb, g.b_cblk, n0, N, kp, kend, tid - 128);
     }
     const int stage = s % tcg::kStages;
     if (s >= tcg::kStages) mbar_wait(&bar_empty[stage], (uint32_t)((s / tcg::kStages - 1) & 1));   // its MMAs have read it
@@ -430,8 +366,8 @@ sgemm_tc_kernel(const float* __restrict__ A, long long lda, const float* __restr
     fence_proxy_async();                        // generic-proxy stores -> visible to the UMMA operand reads
     if (s + 1 < nslabs) {                       // next slab's loads fly under the barrier and the MMA issue
       const long long k0 = kbeg + (long long)(s + 1) * tcg::kSlab;
-      tc_fetch<AK>(A, lda, m0, M, k0, kend, tid, ra);
-      tc_fetch<BK>(B, ldb, n0, N, k0, kend, tid, rb);
+      tc_fetch<AK>(A, lda, g.a_cblk, m0, M, k0, kend, tid, ra);
+      tc_fetch<BK>(B, ldb, g.b_cblk, n0, N, k0, kend, tid, rb);
     }
     __syncthreads();
     if (warp == 0) {
@@ -449,8 +385,6 @@ sgemm_tc_kernel(const float* __restrict__ A, long long lda, const float* __restr
   // would touch 32 different rows per store instruction) ----
   const int q = warp & 3, half = warp >> 2;
   const bool split = gridDim.z > 1;
-  float* out = split ? partial + (size_t)blockIdx.z * M * N : C;
-  const long long ldo = split ? (long long)N : ldc;
   constexpr int kPitch = 132;
   float* const stage = reinterpret_cast<float*>(sm);          // 128 x 132 floats = 66 KB of the (now idle) ring
   if (nslabs > 0) {
@@ -477,21 +411,10 @@ sgemm_tc_kernel(const float* __restrict__ A, long long lda, const float* __restr
   __syncthreads();
   {
     const int n = n0 + lane * 4;
-    float4 bb = make_float4(0.f, 0.f, 0.f, 0.f);
-    if (!split && bias && n < N) bb = *reinterpret_cast<const float4*>(bias + n);
     for (int r = warp; r < kBM; r += kGT / 32) {
       const int m = m0 + r;
       if (m >= M || n >= N) continue;
-      float4 v = *reinterpret_cast<const float4*>(stage + r * kPitch + lane * 4);
-      float* p = out + (long long)m * ldo + n;
-      if (!split) {
-        v.x = fmaf(v.x, alpha, bb.x); v.y = fmaf(v.y, alpha, bb.y); v.z = fmaf(v.z, alpha, bb.z); v.w = fmaf(v.w, alpha, bb.w);
-        if (accumulate) {
-          const float4 c = *reinterpret_cast<const float4*>(p);
-          v.x += c.x; v.y += c.y; v.z += c.z; v.w += c.w;
-        }
-      }
-      *reinterpret_cast<float4*>(p) = v;
+      gemm_store4(g, split, m, n, *reinterpret_cast<const float4*>(stage + r * kPitch + lane * 4));
     }
   }
   tc_fence_before();
@@ -501,8 +424,6 @@ sgemm_tc_kernel(const float* __restrict__ A, long long lda, const float* __restr
     tmem_dealloc(tmem, 128);
   }
 }
-
-int g_tf32_legacy = 0;       // debug: 1 = the mma.sync TF32 kernel instead of the tcgen05 one (same-process A/B)
 
 // second stage of every split reduction: out[i] (=|+=) alpha * sum_s partial[s][i] in a FIXED order (deterministic):
 // a block covers 32 consecutive outputs with 8 split lanes; lane j adds the splits j, j + 8, ... in order (coalesced
@@ -535,14 +456,24 @@ struct Gemm {
   bool tf32 = false;       // tensor-core TF32 products (fp32 accumulation) instead of fp32 FFMA
 };
 
-// op: C[M,N] (=|+=) alpha A B (+bias).  Returns ARREAU_* / cudaError.
+// what a launch may add to the plain product (see GemmArgs)
+struct GemmOpt {
+  long long a_cblk = 128, b_cblk = 128, c_cblk = 128;
+  float* gelu_out = nullptr;            // C2 = gelu(C) * rowscale
+  const float* gz = nullptr;            // C = (alpha A B + bias) * gelu'(gz) * rowscale
+  long long gz_ld = 0;
+  const float* rowscale = nullptr;      // per 16 rows of C (the cutoff window of an edge)
+};
+
+// op: C[M,N] (=|+=) alpha A B (+bias), epilogue options in `o`.  Returns ARREAU_* / cudaError.
 template <bool AK, bool BK>
 int gemm(const Gemm& g, const float* A, long long lda, const float* B, long long ldb, float* C, long long ldc, int M,
-         int N, long long K, float alpha, const float* bias, bool accumulate) {
+         int N, long long K, float alpha, const float* bias, bool accumulate, const GemmOpt& o = GemmOpt()) {
   if (M <= 0 || N <= 0) return ARREAU_OK;
   const int tiles = ((M + kBM - 1) / kBM) * ((N + kBN - 1) / kBN);
+  const bool plain_out = !bias && !o.gelu_out && !o.gz && o.c_cblk == 128;   // what the split second stage can finish
   int splits = 1;
-  if (K > 4096 && tiles < g.sms) {      // reduction-dominated (weight gradients): split the rows
+  if (K > 4096 && tiles < g.sms && plain_out) {      // reduction-dominated (weight gradients): split the rows
     splits = (2 * g.sms + tiles - 1) / tiles;
     const long long max_by_k = (K + 511) / 512;
     if (splits > max_by_k) splits = (int)max_by_k;
@@ -553,25 +484,21 @@ int gemm(const Gemm& g, const float* A, long long lda, const float* B, long long
   splits = (int)((K + kps - 1) / kps);
   if (splits < 1) splits = 1;
   dim3 grid((N + kBN - 1) / kBN, (M + kBM - 1) / kBM, splits);
-  if (g.tf32 && !g_tf32_legacy) {
+  GemmArgs a{A, lda, o.a_cblk, B, ldb, o.b_cblk, C, ldc, o.c_cblk, M, N, K, kps, alpha, bias, accumulate ? 1 : 0,
+             g.partial, o.gelu_out, o.gz, o.gz_ld, o.rowscale, g_tc_mn_lbo, g_tc_mn_sbo};
+  if (g.tf32) {
     static bool attr_set = false;       // one flag per template instance
     if (!attr_set) {
       cudaError_t e = cudaFuncSetAttribute(sgemm_tc_kernel<AK, BK>, cudaFuncAttributeMaxDynamicSharedMemorySize, tcg::kSmemBytes);
       if (e != cudaSuccess) return (int)e;
       attr_set = true;
     }
-    sgemm_tc_kernel<AK, BK><<<grid, kGT, tcg::kSmemBytes, g.s>>>(A, lda, B, ldb, C, ldc, M, N, K, kps, alpha,
-                                                                   splits == 1 ? bias : nullptr, accumulate ? 1 : 0,
-                                                                   g.partial, g_tc_mn_lbo, g_tc_mn_sbo);
-  } else if (g.tf32)
-    sgemm_tf32_kernel<AK, BK><<<grid, kGT, 0, g.s>>>(A, lda, B, ldb, C, ldc, M, N, K, kps, alpha,
-                                                     splits == 1 ? bias : nullptr, accumulate ? 1 : 0, g.partial);
-  else
-    sgemm_kernel<AK, BK><<<grid, kGT, 0, g.s>>>(A, lda, B, ldb, C, ldc, M, N, K, kps, alpha, splits == 1 ? bias : nullptr,
-                                                accumulate ? 1 : 0, g.partial);
+    sgemm_tc_kernel<AK, BK><<<grid, kGT, tcg::kSmemBytes, g.s>>>(a);
+  } else {
+    sgemm_kernel<AK, BK><<<grid, kGT, 0, g.s>>>(a);
+  }
   CUDA_LAUNCH_CHECK();
   if (splits > 1) {
-    if (bias) return ARREAU_ERR_UNSUPPORTED;
     const long long n = (long long)M * N;
     reduce_partials_kernel<<<(unsigned)((n + 31) / 32), 256, 0, g.s>>>(g.partial, splits, n, ldc, N, alpha,
                                                                          accumulate ? 1 : 0, C);
@@ -642,11 +569,6 @@ int colsum(const Gemm& g, const float* X, const float* Y, long long rows, int nc
 // ================================================================================================
 // elementwise / rowwise kernels
 // ================================================================================================
-__device__ __forceinline__ float gelu_grad(float x) {
-  // d/dx [0.5 x (1 + erf(x / sqrt 2))] = 0.5 (1 + erf(x / sqrt 2)) + x exp(-x^2 / 2) / sqrt(2 pi)
-  return 0.5f * (1.0f + erff(x * 0.70710678118654752440f)) + x * expf(-0.5f * x * x) * 0.39894228040143267794f;
-}
-
 // a = gelu(z) [* rowscale[r / rows_per_scale]]
 __global__ void gelu_fwd_kernel(const float* __restrict__ z, long long n, int ncols, const float* __restrict__ rowscale,
                                 int rows_per_scale, float* __restrict__ a) {
@@ -686,29 +608,43 @@ __global__ void fill_kernel(float* __restrict__ p, long long n, float v) {
 
 // ---- edge rows: invariants -> 83 monomials (+ constant 1, zero padding to 128) and the cutoff window ----------
 // (geometry/invariants.py:17-22, transforms/invariants.py:81-87, embedding.py:10-14, windowing.py:21-29)
+// A block takes 64 (edge, orientation) rows: one thread per row forms its monomials in shared memory, then the whole block
+// writes the 64 x 128 tile with coalesced 16-byte stores (one thread per row writing its own 512-byte row straight to
+// global memory took 242 us for the C5 batch's 146 MB; this form is HBM-bound).
+constexpr int kMonoRows = 64;
 __global__ void __launch_bounds__(128)
 edge_mono_kernel(const double* __restrict__ dir, const double* __restrict__ dist, const double* __restrict__ lattice,
                  const int32_t* __restrict__ crystal_of_atom, const int32_t* __restrict__ src,
                  const int32_t* __restrict__ num_edges_ptr, long long edge_capacity, const float* __restrict__ ori,
                  double radius, float* __restrict__ mono, float* __restrict__ win) {
-  const long long row = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  __shared__ float tile[kMonoRows][129];
+  const long long row0 = (long long)blockIdx.x * kMonoRows, total = edge_capacity * kO;
   long long E = *num_edges_ptr;
   if (E > edge_capacity) E = edge_capacity;
-  if (row >= edge_capacity * kO) return;
-  const long long e = row >> 4;
-  const int o = (int)(row & (kO - 1));
-  float* out = mono + row * 128;
-  if (e >= E) {
-    for (int k = 0; k < 128; ++k) out[k] = 0.f;
-    if (o == 0) win[e] = 0.f;
-    return;
+  const int t = threadIdx.x;
+  if (t < kMonoRows && row0 + t < total) {
+    const long long row = row0 + t, e = row >> 4;
+    const int o = (int)(row & (kO - 1));
+    float* out = tile[t];
+    if (e >= E) {
+      for (int k = 0; k <= kMono; ++k) out[k] = 0.f;
+      if (o == 0) win[e] = 0.f;
+    } else {
+      float attr[6];
+      edge_invariants(dir + 3 * e, dist[e], lattice + 9 * (size_t)crystal_of_atom[src[e]], ori + 3 * o, attr);
+      monomials83(attr, out, 1);
+      out[kMono] = 1.0f;
+      if (o == 0) win[e] = cutoff_window(dist[e], radius);
+    }
   }
-  float attr[6];
-  edge_invariants(dir + 3 * e, dist[e], lattice + 9 * (size_t)crystal_of_atom[src[e]], ori + 3 * o, attr);
-  monomials83(attr, out, 1);
-  out[kMono] = 1.0f;
-  for (int k = kMono + 1; k < 128; ++k) out[k] = 0.f;
-  if (o == 0) win[e] = cutoff_window(dist[e], radius);
+  __syncthreads();
+  for (int i = t; i < kMonoRows * 32; i += 128) {
+    const int r = i >> 5, c = (i & 31) * 4;
+    if (row0 + r >= total) break;
+    float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (c <= kMono) v = make_float4(tile[r][c], tile[r][c + 1], tile[r][c + 2], tile[r][c + 3]);   // kMono + 1 = 84 = 21 * 4
+    *reinterpret_cast<float4*>(mono + (row0 + r) * 128 + c) = v;
+  }
 }
 
 // ---- LayerNorm over C = 128 channels, one warp per row (convnext.py:25) -------------------------------------
@@ -1036,19 +972,21 @@ struct Carver {
   }
 };
 
-constexpr size_t kPartialFloats = (size_t)4 << 20;   // 16 MB of split scratch
+constexpr size_t kPartialFloats = (size_t)8 << 20;   // 32 MB of split scratch
 constexpr int kDfkBlocks = 64;
 constexpr int kLnBlocks = 296;
 
 struct BwdBuffers {
   // edge rows (Re = edge_capacity * O)
-  float *mono, *z1, *a1, *z2, *kb, *dkb, *dkern, *da1, *win;
+  float *mono, *z1, *a1, *z2, *kb, *dkb, *dkern, *da1, *win;   // dkern: [L][Re][C], the gradient slabs of every layer
   // node rows (Rn = N * O)
-  float *dh, *dr, *y, *z, *a, *m, *da, *dy, *dx2, *dx1, *xl;
+  float *dh, *dr, *y, *z, *a, *m, *dm, *da, *dy, *dx2, *dx1, *xl;
   // fiber chain (256 rows)
   float *frow, *fz1, *fa1, *fz2, *fkb, *dfk, *dfkb, *fda1, *fw16, *fdw16;
   float *w1m, *dw1m, *partial, *small;   // small: [128 x 512] scratch for narrow outputs
-  float* zs;                             // [L][Rn][W]: ConvNext hidden pre-activations kept by arreau_ponita_forward_train
+  // kept by arreau_ponita_forward_train, one slab per layer: LayerNorm output y [Rn][C], ConvNext hidden pre-activation
+  // z [Rn][W], its GELU a [Rn][W], the MLP output m [Rn][C]
+  float *ys, *zs, *as, *ms;
   size_t total;
 };
 
@@ -1057,10 +995,10 @@ BwdBuffers carve(float* base, long long N, long long Ecap, int xl_pitch) {
   BwdBuffers b;
   const size_t Re = (size_t)Ecap * kO, Rn = (size_t)N * kO;
   b.mono = c.take(Re * 128); b.z1 = c.take(Re * kC); b.a1 = c.take(Re * kC); b.z2 = c.take(Re * kD);
-  b.kb = c.take(Re * kD); b.dkb = c.take(Re * kD); b.dkern = c.take(Re * kC); b.da1 = c.take(Re * kC);
+  b.kb = c.take(Re * kD); b.dkb = c.take(Re * kD); b.dkern = c.take((size_t)kL * Re * kC); b.da1 = c.take(Re * kC);
   b.win = c.take((size_t)Ecap);
   b.dh = c.take(Rn * kC); b.dr = c.take(Rn * 128); b.y = c.take(Rn * kC); b.z = c.take(Rn * kW); b.a = c.take(Rn * kW);
-  b.m = c.take(Rn * kC); b.da = c.take(Rn * kW); b.dy = c.take(Rn * kC); b.dx2 = c.take(Rn * kC);
+  b.m = c.take(Rn * kC); b.dm = c.take(Rn * kC); b.da = c.take(Rn * kW); b.dy = c.take(Rn * kC); b.dx2 = c.take(Rn * kC);
   b.dx1 = c.take(Rn * kC); b.xl = c.take(Rn * xl_pitch);
   const size_t Rf = kO * kO;
   b.frow = c.take(Rf * 16); b.fz1 = c.take(Rf * kC); b.fa1 = c.take(Rf * kC); b.fz2 = c.take(Rf * kD);
@@ -1069,7 +1007,8 @@ BwdBuffers carve(float* base, long long N, long long Ecap, int xl_pitch) {
   b.w1m = c.take(kC * 128); b.dw1m = c.take(kC * 128);
   b.partial = c.take(kPartialFloats);
   b.small = c.take((size_t)128 * 512);
-  b.zs = c.take((size_t)kL * Rn * kW);
+  b.ys = c.take((size_t)kL * Rn * kC); b.zs = c.take((size_t)kL * Rn * kW); b.as = c.take((size_t)kL * Rn * kW);
+  b.ms = c.take((size_t)kL * Rn * kC);
   b.total = c.used;
   return b;
 }
@@ -1093,6 +1032,7 @@ __global__ void residual_add_kernel(const float* __restrict__ m, const float* __
 
 // Edge chain forward: monomials -> z1 -> a1 = gelu(z1) -> z2 -> kb = gelu(z2) * window, every matrix kept in the
 // workspace for the backward (geometry/invariants.py:10-31, embedding.py:10-14, ponita.py:65,94, windowing.py:21-29).
+// The activations leave the GEMMs' epilogues next to their pre-activations (no element-wise pass in between).
 static int edge_chain_forward(const Gemm& g, const BwdBuffers& b, const float* P, const arreau_train_layout_t* lay,
                               const arreau_weights* w, const int32_t* fold_table, const int32_t* src, const double* dist,
                               const double* dir, const double* lattice, const int32_t* crystal_of_atom,
@@ -1102,15 +1042,41 @@ static int edge_chain_forward(const Gemm& g, const BwdBuffers& b, const float* P
   fold_w1_kernel<<<kC, 128, 0, s>>>(P + lay->basis_w1, P + lay->basis_b1, fold_table, 258, b.w1m);
   CUDA_LAUNCH_CHECK();
   if (Re <= 0) return ARREAU_OK;
-  edge_mono_kernel<<<blocks_for(Re, 128), 128, 0, s>>>(dir, dist, lattice, crystal_of_atom, src, num_edges_ptr, Ecap, w->ori,
-                                                       radius, b.mono, b.win);
+  edge_mono_kernel<<<blocks_for(Re, kMonoRows), 128, 0, s>>>(dir, dist, lattice, crystal_of_atom, src, num_edges_ptr, Ecap,
+                                                             w->ori, radius, b.mono, b.win);
   CUDA_LAUNCH_CHECK();
-  TRY((gemm<true, true>(g, b.mono, 128, b.w1m, 128, b.z1, kC, (int)Re, kC, kMonoPad, 1.f, nullptr, false)));
-  gelu_fwd_kernel<<<blocks_for(Re * kC / 4, 256), 256, 0, s>>>(b.z1, Re * kC, kC, nullptr, 1, b.a1);
+  GemmOpt o1;
+  o1.gelu_out = b.a1;
+  TRY((gemm<true, true>(g, b.mono, 128, b.w1m, 128, b.z1, kC, (int)Re, kC, kMonoPad, 1.f, nullptr, false, o1)));
+  GemmOpt o2;
+  o2.gelu_out = b.kb;
+  o2.rowscale = b.win;
+  TRY((gemm<true, true>(g, b.a1, kC, P + lay->basis_w2, kC, b.z2, kD, (int)Re, kD, kC, 1.f, P + lay->basis_b2, false, o2)));
+  return ARREAU_OK;
+}
+
+// Fiber chain forward (geometry/invariants.py:23, ponita.py:66,95): rows (o, p) -> [fa, fa^2, fa^3, 1] -> fz1 -> fa1 -> fz2 ->
+// fkb, kept for the backward; with `fiber_kernel` the five fiber kernels fkb Wf_l^T (conv.py:113) as ONE product whose
+// output columns are the per-layer [O*O][C] slabs.
+static int fiber_chain_forward(const Gemm& g, const BwdBuffers& b, const float* P, const arreau_train_layout_t* lay,
+                               const float* ori, float* fiber_kernel) {
+  cudaStream_t s = g.s;
+  const int Rf = kO * kO;
+  fiber_rows_kernel<<<1, 256, 0, s>>>(ori, b.frow);
   CUDA_LAUNCH_CHECK();
-  TRY((gemm<true, true>(g, b.a1, kC, P + lay->basis_w2, kC, b.z2, kD, (int)Re, kD, kC, 1.f, P + lay->basis_b2, false)));
-  gelu_fwd_kernel<<<blocks_for(Re * kD / 4, 256), 256, 0, s>>>(b.z2, Re * kD, kD, b.win, kO, b.kb);
+  pack_fiber_w1_kernel<<<kC, 16, 0, s>>>(P + lay->fiber_w1, P + lay->fiber_b1, b.fw16);
   CUDA_LAUNCH_CHECK();
+  GemmOpt o1;
+  o1.gelu_out = b.fa1;
+  TRY((gemm<true, true>(g, b.frow, 16, b.fw16, 16, b.fz1, kC, Rf, kC, 16, 1.f, nullptr, false, o1)));
+  GemmOpt o2;
+  o2.gelu_out = b.fkb;
+  TRY((gemm<true, true>(g, b.fa1, kC, P + lay->fiber_w2, kC, b.fz2, kD, Rf, kD, kC, 1.f, P + lay->fiber_b2, false, o2)));
+  if (fiber_kernel) {
+    GemmOpt o3;
+    o3.c_cblk = (long long)Rf * kC;
+    TRY((gemm<true, true>(g, b.fkb, kD, P + lay->conv_fiber_w, kD, fiber_kernel, kC, Rf, kL * kC, kD, 1.f, nullptr, false, o3)));
+  }
   return ARREAU_OK;
 }
 
@@ -1159,7 +1125,7 @@ extern "C" int arreau_moments(const float* x, const float* sub_cols, int64_t n, 
 
 // debug only (not part of the public ABI): TF32 GEMM implementation switch and MN-major descriptor strides
 extern "C" int arreau_debug_set_tf32_gemm(int legacy, int mn_lbo, int mn_sbo) {
-  g_tf32_legacy = legacy ? 1 : 0;
+  (void)legacy;                          // the mma.sync TF32 kernel this used to select is gone
   if (mn_lbo > 0) g_tc_mn_lbo = mn_lbo;
   if (mn_sbo > 0) g_tc_mn_sbo = mn_sbo;
   return ARREAU_OK;
@@ -1235,20 +1201,13 @@ extern "C" int arreau_ponita_backward(const float* params, const arreau_train_la
                                                         1.0f / (float)(kL * kO), b.dr);
   CUDA_LAUNCH_CHECK();
 
-  // ---- 1. the edge chain: monomials -> z1 -> a1 -> z2 -> kernel basis kb ---------------------------------
+  // ---- 1. the edge chain (monomials -> z1 -> a1 -> z2 -> kernel basis kb) and the fiber chain ------------
   // (kept in the workspace by arreau_ponita_forward_train; recomputed here after the plain fp32 forward)
-  if (!forward_kept)
-    TRY(edge_chain_forward(g, b, P, lay, w, fold_table, src, dist, dir, lattice, crystal_of_atom, num_edges_ptr, Ecap, radius));
-  // fiber chain forward (ponita.py:66,95): rows (o,p)
   const int Rf = kO * kO;
-  fiber_rows_kernel<<<1, 256, 0, s>>>(w->ori, b.frow);
-  CUDA_LAUNCH_CHECK();
-  pack_fiber_w1_kernel<<<kC, 16, 0, s>>>(P + lay->fiber_w1, P + lay->fiber_b1, b.fw16);
-  CUDA_LAUNCH_CHECK();
-  TRY((gemm<true, true>(g, b.frow, 16, b.fw16, 16, b.fz1, kC, Rf, kC, 16, 1.f, nullptr, false)));
-  TRY(gelu_f(b.fz1, Rf, kC, nullptr, 1, b.fa1));
-  TRY((gemm<true, true>(g, b.fa1, kC, P + lay->fiber_w2, kC, b.fz2, kD, Rf, kD, kC, 1.f, P + lay->fiber_b2, false)));
-  TRY(gelu_f(b.fz2, Rf, kD, nullptr, 1, b.fkb));
+  if (!forward_kept) {
+    TRY(edge_chain_forward(g, b, P, lay, w, fold_table, src, dist, dir, lattice, crystal_of_atom, num_edges_ptr, Ecap, radius));
+    TRY(fiber_chain_forward(g, b, P, lay, w->ori, nullptr));
+  }
   TRY(zero(b.dfkb, (long long)Rf * kD));
 
   // ---- 2. layers, last to first -------------------------------------------------------------------------
@@ -1261,7 +1220,6 @@ extern "C" int arreau_ponita_backward(const float* params, const arreau_train_la
     const float* Wr = P + lay->readout_w + (size_t)l * R * kC;
     const float* W1 = P + lay->lin1_w + (size_t)l * kW * kC;
     const float* W2 = P + lay->lin2_w + (size_t)l * kC * kW;
-    const float* Wk = P + lay->conv_kernel_w + (size_t)l * kC * kD;
     const float* Wf = P + lay->conv_fiber_w + (size_t)l * kC * kD;
     const float* ls = P + lay->layer_scale + l * kC;
     // read-out l: r = h_out Wr^T + br   (ponita.py:105)
@@ -1272,32 +1230,37 @@ extern "C" int arreau_ponita_backward(const float* params, const arreau_train_la
                                       cudaMemcpyDeviceToDevice, s);
       if (e != cudaSuccess) return (int)e;
     }
-    TRY(colsum(g, b.dr, nullptr, Rn, 128, 128, b.small, false));
-    {
-      cudaError_t e = cudaMemcpyAsync(Gd + lay->readout_b + (size_t)l * R, b.small, sizeof(float) * R, cudaMemcpyDeviceToDevice, s);
-      if (e != cudaSuccess) return (int)e;
-    }
     //   dh += dr Wr      (K = R rows of Wr; dr columns beyond R are zero, so K = R rounded down to the stored rows)
     TRY((gemm<true, false>(g, b.dr, 128, Wr, kC, b.dh, kC, (int)Rn, kC, R, 1.f, nullptr, true)));
-    // ConvNext MLP recompute (convnext.py:25-32): y = LN(x2), z = y W1^T + b1, a = gelu(z), m = a W2^T + b2
-    ln_fwd_kernel<<<blocks_for(Rn * 32, 256), 256, 0, s>>>(x2, P + lay->norm_w + l * kC, P + lay->norm_b + l * kC, Rn, b.y);
-    CUDA_LAUNCH_CHECK();
-    // z: kept per layer by arreau_ponita_forward_train, else recomputed
-    const float* zl = forward_kept ? b.zs + (size_t)l * Rn * kW : b.z;
-    if (!forward_kept)
-      TRY((gemm<true, true>(g, b.y, kC, W1, kC, b.z, kW, (int)Rn, kW, kC, 1.f, P + lay->lin1_b + l * kW, false)));
-    TRY(gelu_f(zl, Rn, kW, nullptr, 1, b.a));
-    TRY((gemm<true, true>(g, b.a, kW, W2, kW, b.m, kC, (int)Rn, kC, kW, 1.f, P + lay->lin2_b + l * kC, false)));
+    // ConvNext MLP (convnext.py:25-32): y = LN(x2), z = y W1^T + b1, a = gelu(z), m = a W2^T + b2 -- kept per layer by
+    // arreau_ponita_forward_train, else recomputed
+    const float *yl, *zl, *al, *ml;
+    if (forward_kept) {
+      yl = b.ys + (size_t)l * Rn * kC; zl = b.zs + (size_t)l * Rn * kW; al = b.as + (size_t)l * Rn * kW;
+      ml = b.ms + (size_t)l * Rn * kC;
+    } else {
+      ln_fwd_kernel<<<blocks_for(Rn * 32, 256), 256, 0, s>>>(x2, P + lay->norm_w + l * kC, P + lay->norm_b + l * kC, Rn, b.y);
+      CUDA_LAUNCH_CHECK();
+      GemmOpt oz;
+      oz.gelu_out = b.a;
+      TRY((gemm<true, true>(g, b.y, kC, W1, kC, b.z, kW, (int)Rn, kW, kC, 1.f, P + lay->lin1_b + l * kW, false, oz)));
+      TRY((gemm<true, true>(g, b.a, kW, W2, kW, b.m, kC, (int)Rn, kC, kW, 1.f, P + lay->lin2_b + l * kC, false)));
+      yl = b.y; zl = b.z; al = b.a; ml = b.m;
+    }
     // h_out = h_in + ls * m
-    TRY(colsum(g, b.dh, b.m, Rn, kC, kC, Gd + lay->layer_scale + l * kC, false));
-    scale_cols_kernel<<<blocks_for(Rn * kC / 4, 256), 256, 0, s>>>(b.dh, ls, Rn * kC, b.m);            // b.m = dm
+    TRY(colsum(g, b.dh, ml, Rn, kC, kC, Gd + lay->layer_scale + l * kC, false));
+    scale_cols_kernel<<<blocks_for(Rn * kC / 4, 256), 256, 0, s>>>(b.dh, ls, Rn * kC, b.dm);
     CUDA_LAUNCH_CHECK();
-    TRY(colsum(g, b.m, nullptr, Rn, kC, kC, Gd + lay->lin2_b + l * kC, false));
-    TRY((gemm<false, false>(g, b.m, kC, b.a, kW, Gd + lay->lin2_w + (size_t)l * kC * kW, kW, kC, kW, Rn, 1.f, nullptr, false)));
-    TRY((gemm<true, false>(g, b.m, kC, W2, kW, b.da, kW, (int)Rn, kW, kC, 1.f, nullptr, false)));
-    TRY(gelu_b(zl, b.da, Rn, kW, nullptr, 1, b.da));                                                   // b.da = dz
+    TRY(colsum(g, b.dm, nullptr, Rn, kC, kC, Gd + lay->lin2_b + l * kC, false));
+    TRY((gemm<false, false>(g, b.dm, kC, al, kW, Gd + lay->lin2_w + (size_t)l * kC * kW, kW, kC, kW, Rn, 1.f, nullptr, false)));
+    {   // dz = (dm W2) * gelu'(z) in the product's epilogue
+      GemmOpt od;
+      od.gz = zl;
+      od.gz_ld = kW;
+      TRY((gemm<true, false>(g, b.dm, kC, W2, kW, b.da, kW, (int)Rn, kW, kC, 1.f, nullptr, false, od)));
+    }
     TRY(colsum(g, b.da, nullptr, Rn, kW, kW, Gd + lay->lin1_b + l * kW, false));
-    TRY((gemm<false, false>(g, b.da, kW, b.y, kC, Gd + lay->lin1_w + (size_t)l * kW * kC, kC, kW, kC, Rn, 1.f, nullptr, false)));
+    TRY((gemm<false, false>(g, b.da, kW, yl, kC, Gd + lay->lin1_w + (size_t)l * kW * kC, kC, kW, kC, Rn, 1.f, nullptr, false)));
     TRY((gemm<true, false>(g, b.da, kW, W1, kC, b.dy, kC, (int)Rn, kC, kW, 1.f, nullptr, false)));
     // LayerNorm backward + conv bias gradient
     {
@@ -1326,21 +1289,31 @@ extern "C" int arreau_ponita_backward(const float* params, const arreau_train_la
       reduce_partials_kernel<<<blocks_for((long long)Rf * kC, 32), 256, 0, s>>>(b.partial, fb, (long long)Rf * kC, Rf * kC,
                                                                                Rf * kC, 1.0f / kO, 0, dfk);
       CUDA_LAUNCH_CHECK();
-      // fiber_kernel = fkb Wf^T: dWf[C,D] = dfk^T fkb ; dfkb += dfk Wf
-      TRY((gemm<false, false>(g, dfk, kC, b.fkb, kD, Gd + lay->conv_fiber_w + (size_t)l * kC * kD, kD, kC, kD, Rf, 1.f, nullptr, false)));
-      TRY((gemm<true, false>(g, dfk, kC, Wf, kD, b.dfkb, kD, Rf, kD, kC, 1.f, nullptr, true)));
     }
-    // message pass backward
+    // message pass backward: this layer's slab of the kernel gradient, and dh
     if (Re > 0) {
-      message_bwd_dkern_kernel<<<blocks_for(Re * kC / 4, 256), 256, 0, s>>>(b.dx1, h_in, src, dst, num_edges_ptr, Ecap, b.dkern);
+      message_bwd_dkern_kernel<<<blocks_for(Re * kC / 4, 256), 256, 0, s>>>(b.dx1, h_in, src, dst, num_edges_ptr, Ecap,
+                                                                            b.dkern + (size_t)l * Re * kC);
       CUDA_LAUNCH_CHECK();
       message_bwd_dh_kernel<<<N, 256, 0, s>>>(kern, b.dx1, row_ptr, src, dst, atom_offset, crystal_of_atom, Ecap, b.dh);
       CUDA_LAUNCH_CHECK();
-      // kernel = kb Wk^T: dWk[C,D] = dkern^T kb ; dkb += dkern Wk
-      TRY((gemm<false, false>(g, b.dkern, kC, b.kb, kD, Gd + lay->conv_kernel_w + (size_t)l * kC * kD, kD, kC, kD, Re, 1.f, nullptr, false)));
-      // dkb accumulates over the layers: the first layer visited (l = L - 1) overwrites, which saves zeroing 4 Re D bytes
-      TRY((gemm<true, false>(g, b.dkern, kC, Wk, kD, b.dkb, kD, (int)Re, kD, kC, 1.f, nullptr, l != kL - 1)));
     }
+  }
+  // read-out bias: the same dr for every layer -> one column sum, copied to the five slots
+  TRY(colsum(g, b.dr, nullptr, Rn, 128, 128, b.small, false));
+  for (int l = 0; l < kL; ++l) {
+    cudaError_t e = cudaMemcpyAsync(Gd + lay->readout_b + (size_t)l * R, b.small, sizeof(float) * R, cudaMemcpyDeviceToDevice, s);
+    if (e != cudaSuccess) return (int)e;
+  }
+  // the five layers' kernel projections at once (conv.py:110,113: kernel_l = kb Wk_l^T, fiber_kernel_l = fkb Wf_l^T):
+  // the gradient slabs [L][rows][C] are ONE operand [rows][L*C] (block stride = one slab), the weights [L][C][D] one
+  // [L*C][D] matrix, so kb / the slabs are streamed once instead of five times and dkb needs no accumulation passes
+  {
+    GemmOpt of;
+    of.a_cblk = (long long)Rf * kC;
+    //   dWf[L*C, D] = dfk^T fkb ; dfkb = dfk Wf
+    TRY((gemm<false, false>(g, b.dfk, kC, b.fkb, kD, Gd + lay->conv_fiber_w, kD, kL * kC, kD, Rf, 1.f, nullptr, false, of)));
+    TRY((gemm<true, false>(g, b.dfk, kC, P + lay->conv_fiber_w, kD, b.dfkb, kD, Rf, kD, kL * kC, 1.f, nullptr, false, of)));
   }
 
   // ---- 3. node embedding: h0 = x_lift We^T  (ponita.py:98) ------------------------------------------------
@@ -1357,11 +1330,22 @@ extern "C" int arreau_ponita_backward(const float* params, const arreau_train_la
 
   // ---- 4. edge chain backward ------------------------------------------------------------------------------
   if (Re > 0) {
-    TRY(gelu_b(b.z2, b.dkb, Re, kD, b.win, kO, b.dkb));                                              // b.dkb = dz2
+    GemmOpt ok;
+    ok.a_cblk = Re * kC;
+    //   dWk[L*C, D] = dkern^T kb
+    TRY((gemm<false, false>(g, b.dkern, kC, b.kb, kD, Gd + lay->conv_kernel_w, kD, kL * kC, kD, Re, 1.f, nullptr, false, ok)));
+    //   dz2 = (dkern Wk) * gelu'(z2) * window        (b.dkb = dz2)
+    ok.gz = b.z2;
+    ok.gz_ld = kD;
+    ok.rowscale = b.win;
+    TRY((gemm<true, false>(g, b.dkern, kC, P + lay->conv_kernel_w, kD, b.dkb, kD, (int)Re, kD, kL * kC, 1.f, nullptr, false, ok)));
     TRY(colsum(g, b.dkb, nullptr, Re, kD, kD, Gd + lay->basis_b2, false));
     TRY((gemm<false, false>(g, b.dkb, kD, b.a1, kC, Gd + lay->basis_w2, kC, kD, kC, Re, 1.f, nullptr, false)));
-    TRY((gemm<true, false>(g, b.dkb, kD, P + lay->basis_w2, kC, b.da1, kC, (int)Re, kC, kD, 1.f, nullptr, false)));
-    TRY(gelu_b(b.z1, b.da1, Re, kC, nullptr, 1, b.da1));                                             // b.da1 = dz1
+    //   dz1 = (dz2 W2) * gelu'(z1)                   (b.da1 = dz1)
+    GemmOpt o1;
+    o1.gz = b.z1;
+    o1.gz_ld = kC;
+    TRY((gemm<true, false>(g, b.dkb, kD, P + lay->basis_w2, kC, b.da1, kC, (int)Re, kC, kD, 1.f, nullptr, false, o1)));
     TRY((gemm<false, false>(g, b.da1, kC, b.mono, 128, b.dw1m, 128, kC, kMonoPad, Re, 1.f, nullptr, false)));
     unfold_w1_grad_kernel<<<kC, 128, 0, s>>>(b.dw1m, fold_table, 258, Gd + lay->basis_w1, Gd + lay->basis_b1);
     CUDA_LAUNCH_CHECK();
@@ -1371,8 +1355,12 @@ extern "C" int arreau_ponita_backward(const float* params, const arreau_train_la
   TRY(gelu_b(b.fz2, b.dfkb, Rf, kD, nullptr, 1, b.dfkb));
   TRY(colsum(g, b.dfkb, nullptr, Rf, kD, kD, Gd + lay->fiber_b2, false));
   TRY((gemm<false, false>(g, b.dfkb, kD, b.fa1, kC, Gd + lay->fiber_w2, kC, kD, kC, Rf, 1.f, nullptr, false)));
-  TRY((gemm<true, false>(g, b.dfkb, kD, P + lay->fiber_w2, kC, b.fda1, kC, Rf, kC, kD, 1.f, nullptr, false)));
-  TRY(gelu_b(b.fz1, b.fda1, Rf, kC, nullptr, 1, b.fda1));
+  {
+    GemmOpt o1;
+    o1.gz = b.fz1;
+    o1.gz_ld = kC;
+    TRY((gemm<true, false>(g, b.dfkb, kD, P + lay->fiber_w2, kC, b.fda1, kC, Rf, kC, kD, 1.f, nullptr, false, o1)));
+  }
   TRY((gemm<false, false>(g, b.fda1, kC, b.frow, 16, b.fdw16, 16, kC, 16, Rf, 1.f, nullptr, false)));
   unpack_fiber_w1_grad_kernel<<<1, kC, 0, s>>>(b.fdw16, Gd + lay->fiber_w1, Gd + lay->fiber_b1);
   CUDA_LAUNCH_CHECK();
@@ -1419,26 +1407,35 @@ extern "C" int arreau_ponita_forward_train(const float* params, const arreau_tra
     cudaError_t e = cudaMemcpyAsync(ws->h_debug, ws->h, node_elems * sizeof(float), cudaMemcpyDeviceToDevice, s);
     if (e != cudaSuccess) return (int)e;
   }
-  // edge chain and the five kernel projections kernels[l] = kb Wk_l^T (conv.py:110)
+  // edge chain and the five kernel projections kernels[l] = kb Wk_l^T (conv.py:110) as ONE product: the weights [L][C][D]
+  // are one [L*C][D] matrix and the output columns are the per-layer [Re][C] slabs, so kb is streamed once
   TRY(edge_chain_forward(g, b, P, lay, w, fold_table, src, dist, dir, lattice, crystal_of_atom, row_ptr + N, Ecap, radius));
-  for (int l = 0; l < kL && Re > 0; ++l)
-    TRY((gemm<true, true>(g, b.kb, kD, P + lay->conv_kernel_w + (size_t)l * kC * kD, kD,
-                          (float*)ws->kernels + (size_t)l * layer_kernel_elems, kC, (int)Re, kC, kD, 1.f, nullptr, false)));
+  if (Re > 0) {
+    GemmOpt ok;
+    ok.c_cblk = (long long)layer_kernel_elems;
+    TRY((gemm<true, true>(g, b.kb, kD, P + lay->conv_kernel_w, kD, (float*)ws->kernels, kC, (int)Re, kL * kC, kD, 1.f, nullptr,
+                          false, ok)));
+  }
+  // fiber chain, kept for the backward (the fiber kernels themselves come packed in `w`)
+  TRY(fiber_chain_forward(g, b, P, lay, w->ori, nullptr));
   for (int l = 0; l < kL; ++l) {
     const float* kern = (const float*)ws->kernels + (size_t)l * layer_kernel_elems;
-    // message pass + fiber conv + bias + LayerNorm (conv.py:111-133, convnext.py:25): y = LN(x2)
-    TRY(arreau_message_fiber_norm(kern, 0, ws->h, row_ptr, src, w->fiber_kernel + (size_t)l * kO * kO * kC, nullptr,
-                                  w->conv_bias + l * kC, w->ln_w + l * kC, w->ln_b + l * kC, N, ws->y, 0,
-                                  ws->x1_debug + l * node_elems, ws->x2_debug + l * node_elems, stream));
-    // ConvNext MLP (convnext.py:26-32): z = y W1^T + b1 (kept), a = gelu(z), m = a W2^T + b2, h += ls * m
+    float* yl = b.ys + (size_t)l * Rn * kC;
     float* zl = b.zs + (size_t)l * Rn * kW;
-    TRY((gemm<true, true>(g, (const float*)ws->y, kC, P + lay->lin1_w + (size_t)l * kW * kC, kC, zl, kW, (int)Rn, kW, kC, 1.f,
-                          P + lay->lin1_b + l * kW, false)));
-    gelu_fwd_kernel<<<blocks_for(Rn * kW / 4, 256), 256, 0, s>>>(zl, Rn * kW, kW, nullptr, 1, b.a);
-    CUDA_LAUNCH_CHECK();
-    TRY((gemm<true, true>(g, b.a, kW, P + lay->lin2_w + (size_t)l * kC * kW, kW, b.m, kC, (int)Rn, kC, kW, 1.f,
+    float* al = b.as + (size_t)l * Rn * kW;
+    float* ml = b.ms + (size_t)l * Rn * kC;
+    // message pass + fiber conv + bias + LayerNorm (conv.py:111-133, convnext.py:25): y = LN(x2), kept
+    TRY(arreau_message_fiber_norm(kern, 0, ws->h, row_ptr, src, w->fiber_kernel + (size_t)l * kO * kO * kC, nullptr,
+                                  w->conv_bias + l * kC, w->ln_w + l * kC, w->ln_b + l * kC, N, yl, 0,
+                                  ws->x1_debug + l * node_elems, ws->x2_debug + l * node_elems, stream));
+    // ConvNext MLP (convnext.py:26-32): z = y W1^T + b1, a = gelu(z) (same epilogue), m = a W2^T + b2, all kept; h += ls * m
+    GemmOpt oz;
+    oz.gelu_out = al;
+    TRY((gemm<true, true>(g, yl, kC, P + lay->lin1_w + (size_t)l * kW * kC, kC, zl, kW, (int)Rn, kW, kC, 1.f,
+                          P + lay->lin1_b + l * kW, false, oz)));
+    TRY((gemm<true, true>(g, al, kW, P + lay->lin2_w + (size_t)l * kC * kW, kW, ml, kC, (int)Rn, kC, kW, 1.f,
                           P + lay->lin2_b + l * kC, false)));
-    residual_add_kernel<<<blocks_for(Rn * kC / 4, 256), 256, 0, s>>>(b.m, P + lay->layer_scale + l * kC, Rn * kC / 4, ws->h);
+    residual_add_kernel<<<blocks_for(Rn * kC / 4, 256), 256, 0, s>>>(ml, P + lay->layer_scale + l * kC, Rn * kC / 4, ws->h);
     CUDA_LAUNCH_CHECK();
     {
       cudaError_t e = cudaMemcpyAsync(ws->h_debug + (size_t)(l + 1) * node_elems, ws->h, node_elems * sizeof(float),
