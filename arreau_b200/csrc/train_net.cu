@@ -17,6 +17,8 @@
 //
 // The forward pass of a training step is the ordinary fp32 forward (arreau_ponita_forward) run with its
 // per-layer buffers kept (h, x1, x2 of every layer and the per-layer spatial kernels).
+#include <cuda.h>          // CUtensorMap and its enums only: cuTensorMapEncodeTiled is reached through the runtime
+
 #include "common.cuh"
 #include "tc_common.cuh"
 
@@ -53,6 +55,8 @@ struct GemmArgs {
   const float* gz; long long gz_ld;
   const float* rowscale;
   int mn_lbo, mn_sbo;
+  int splits;                 // K splits (the persistent kernel's grid is not the tile grid)
+  long long* prof;            // debug: per-CTA phase clocks of the persistent kernel ([grid][16]), or null
 };
 
 __device__ __forceinline__ long long blk_off(long long i, long long cblk) { return (i >> 7) * cblk + (i & 127); }
@@ -63,9 +67,9 @@ __device__ __forceinline__ float gelu_grad(float x) {
 }
 
 // the four accumulators (m, n .. n + 3) of a tile on their way out (n % 4 == 0, n < N)
-__device__ __forceinline__ void gemm_store4(const GemmArgs& g, bool split, int m, int n, float4 v) {
+__device__ __forceinline__ void gemm_store4(const GemmArgs& g, bool split, int z, int m, int n, float4 v) {
   if (split) {
-    *reinterpret_cast<float4*>(g.partial + ((size_t)blockIdx.z * g.M + m) * g.N + n) = v;
+    *reinterpret_cast<float4*>(g.partial + ((size_t)z * g.M + m) * g.N + n) = v;
     return;
   }
   float4 bb = make_float4(0.f, 0.f, 0.f, 0.f);
@@ -195,7 +199,7 @@ sgemm_kernel(const __grid_constant__ GemmArgs g) {
     for (int half = 0; half < 2; ++half) {
       const int n = n0 + half * 64 + tx * 4;
       if (n >= N) continue;
-      gemm_store4(g, split, m, n,
+      gemm_store4(g, split, (int)blockIdx.z, m, n,
                   make_float4(acc[i][half * 2].x, acc[i][half * 2].y, acc[i][half * 2 + 1].x, acc[i][half * 2 + 1].y));
     }
   }
@@ -414,7 +418,7 @@ sgemm_tc_kernel(const __grid_constant__ GemmArgs g) {
     for (int r = warp; r < kBM; r += kGT / 32) {
       const int m = m0 + r;
       if (m >= M || n >= N) continue;
-      gemm_store4(g, split, m, n, *reinterpret_cast<const float4*>(stage + r * kPitch + lane * 4));
+      gemm_store4(g, split, (int)blockIdx.z, m, n, *reinterpret_cast<const float4*>(stage + r * kPitch + lane * 4));
     }
   }
   tc_fence_before();
@@ -424,6 +428,312 @@ sgemm_tc_kernel(const __grid_constant__ GemmArgs g) {
     tmem_dealloc(tmem, 128);
   }
 }
+
+// ================================================================================================
+// The same product as a PERSISTENT, WARP-SPECIALISED kernel fed by the TMA engine (the default of ARREAU_PRECISION_TF32).
+// The step's products are skinny (285 k rows x 128 .. 640 columns, K = 128 .. 640) and HBM-bound; with one tile per CTA and
+// every warp loading, then multiplying, then storing, each CTA is a serial chain of memory round trips (2 .. 3 TB/s), and a
+// persistent kernel whose warps copy with cp.async is bound by the SM's load/store pipe instead (1.4 K cycles of issue per
+// 32 KB slab + 0.9 K for rounding it in place: profiles/r2_gemm_cpasync_phases.txt).  Here one CTA per SM walks over the work
+// items (m tile, n tile, K split; n fastest, so that the SMs working side by side share the rows of A in L2):
+//   warp 0      producer: one thread issues two cp.async.bulk.tensor loads per slab (tensor maps built per launch on the
+//               host, data type TFLOAT32: the TMA engine rounds fp32 -> TF32 on the way, so no thread touches the operands),
+//               hardware swizzle straight into the UMMA tile images, up to kStages slabs in flight across tile boundaries:
+//                 K-contiguous storage  X[x][k]: box 32 k x 128 rows, SWIZZLE_128B           -> K-major tile (as above)
+//                 MN-contiguous storage X[k][x]: box 32 x * 32 k * 4 atoms, SWIZZLE_128B_ATOM_32B -> MN-major tile with the
+//                 atoms 4 KB apart (LBO) and the 4-k groups 512 B apart (SBO);
+//               block-strided operands (GemmArgs) get one more tensor dimension;
+//   warp 1      MMA issue: four 128x128x8 kind::tf32 MMAs per slab, tcgen05.commit -> empty[stage]; the accumulator is
+//               double-buffered in tensor memory (2 x 128 columns), commit -> tmem_full[buffer] after a tile's last slab;
+//   warps 2-9   epilogue: warp w owns TMEM lanes 32 (w % 4) and 64 columns: tcgen05.ld in 32-column chunks through a private
+//               shared-memory staging tile, so that the global stores (and the loads of the fused epilogue, GemmArgs) are
+//               whole 128-byte row segments; the buffer is released (tmem_empty) after the last tcgen05.ld.
+// So the loads of tile i + 1, the MMAs of tile i and the stores of tile i - 1 overlap.
+// ================================================================================================
+namespace wsg {
+constexpr int kStages = 5;
+constexpr int kMmaWarp = 1;
+constexpr int kThreads = 10 * 32;
+constexpr int kStagePitch = 36;                  // floats: 32 columns + 4 (conflict-free 16-byte rows)
+constexpr int kStagingBytes = 8 * 32 * kStagePitch * 4;
+constexpr int kSmemBytes = kStages * tcg::kStageBytes + kStagingBytes + 256 + 1024;
+constexpr int kMnLbo = 4096, kMnSbo = 512;       // MN-major tile image written by the TMA box (see above)
+}  // namespace wsg
+
+__device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap* m, uint32_t bar, int c0, int c1) {
+  asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+               ::"r"(dst), "l"(m), "r"(bar), "r"(c0), "r"(c1) : "memory");
+}
+__device__ __forceinline__ void tma_load_3d(uint32_t dst, const CUtensorMap* m, uint32_t bar, int c0, int c1, int c2) {
+  asm volatile("cp.async.bulk.tensor.3d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];"
+               ::"r"(dst), "l"(m), "r"(bar), "r"(c0), "r"(c1), "r"(c2) : "memory");
+}
+__device__ __forceinline__ void tma_load_4d(uint32_t dst, const CUtensorMap* m, uint32_t bar, int c0, int c1, int c2, int c3) {
+  asm volatile("cp.async.bulk.tensor.4d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2];"
+               ::"r"(dst), "l"(m), "r"(bar), "r"(c0), "r"(c1), "r"(c2), "r"(c3) : "memory");
+}
+// one 128 x 32 operand slab: x0 = first row / column of the tile, k = first K index (a multiple of 32)
+template <bool KCONTIG>
+__device__ __forceinline__ void tma_slab(uint32_t dst, const CUtensorMap* m, uint32_t bar, bool blocked, int x0, long long k) {
+  if (KCONTIG) {
+    if (!blocked) tma_load_2d(dst, m, bar, (int)k, x0);
+    else tma_load_3d(dst, m, bar, (int)(k & 127), x0, (int)(k >> 7));
+  } else {
+    if (!blocked) tma_load_3d(dst, m, bar, 0, (int)k, x0 >> 5);
+    else tma_load_4d(dst, m, bar, 0, (int)k, 0, x0 >> 7);
+  }
+}
+
+// a work item of the persistent kernel (shared by the three roles)
+struct WsItem {
+  int m0, n0, z, nslabs;
+  long long kbeg, kend;
+};
+__device__ __forceinline__ WsItem ws_item(const GemmArgs& g, int item, int ntn, int ntm) {
+  WsItem w;
+  const int nt = item % ntn, r = item / ntn;
+  w.n0 = nt * kBN;
+  w.m0 = (r % ntm) * kBM;
+  w.z = r / ntm;
+  w.kbeg = (long long)w.z * g.k_per_split;
+  w.kend = (w.kbeg + g.k_per_split < g.K) ? w.kbeg + g.k_per_split : g.K;
+  w.nslabs = w.kbeg < w.kend ? (int)((w.kend - w.kbeg + tcg::kSlab - 1) / tcg::kSlab) : 0;
+  return w;
+}
+
+long long* g_ws_prof = nullptr;   // debug: see GemmArgs::prof
+
+template <bool AK, bool BK>
+__global__ void __launch_bounds__(wsg::kThreads, 1)
+sgemm_tma_kernel(const __grid_constant__ GemmArgs g, const __grid_constant__ CUtensorMap map_a,
+                 const __grid_constant__ CUtensorMap map_b) {
+  using namespace tc;
+  extern __shared__ __align__(1024) uint8_t gsm_raw[];
+  const uint32_t base = (smem_u32(gsm_raw) + 1023u) & ~1023u;
+  uint8_t* const sm = gsm_raw + (base - smem_u32(gsm_raw));
+  float* const staging = reinterpret_cast<float*>(sm + wsg::kStages * tcg::kStageBytes);
+  uint64_t* const bar_full = reinterpret_cast<uint64_t*>(sm + wsg::kStages * tcg::kStageBytes + wsg::kStagingBytes);
+  uint64_t* const bar_empty = bar_full + wsg::kStages;
+  uint64_t* const bar_tfull = bar_empty + wsg::kStages;     // [2]
+  uint64_t* const bar_tempty = bar_tfull + 2;               // [2]
+  uint32_t* const tmem_slot = reinterpret_cast<uint32_t*>(bar_tempty + 2);
+  const int tid = threadIdx.x, warp = __shfl_sync(0xffffffffu, tid >> 5, 0), lane = tid & 31;
+  const int ntn = (g.N + kBN - 1) / kBN, ntm = (g.M + kBM - 1) / kBM;
+  const int items = ntn * ntm * g.splits;
+  if (tid == 0) {
+    for (int i = 0; i < wsg::kStages; ++i) {
+      mbar_init(&bar_full[i], 1);
+      mbar_init(&bar_empty[i], 1);
+    }
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(&bar_tfull[i], 1);
+      mbar_init(&bar_tempty[i], 8);
+    }
+    fence_barrier_init();
+  }
+  if (warp == wsg::kMmaWarp) tmem_alloc(tmem_slot, 256);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem = *tmem_slot;
+  long long pf[3] = {0, 0, 0}, t0 = clock64(), t1;
+#define WS_PROF(i) { t1 = clock64(); pf[i] += t1 - t0; t0 = t1; }
+
+  if (warp == 0) {
+    // ---------------- producer ----------------
+    if (lane == 0) {
+      const bool a_blocked = g.a_cblk != 128, b_blocked = g.b_cblk != 128;
+      uint32_t slab = 0;
+      for (int item = blockIdx.x; item < items; item += gridDim.x) {
+        const WsItem w = ws_item(g, item, ntn, ntm);
+        for (int s = 0; s < w.nslabs; ++s, ++slab) {
+          const uint32_t st = slab % wsg::kStages;
+          WS_PROF(1)
+          if (slab >= (uint32_t)wsg::kStages) mbar_wait(&bar_empty[st], ((slab / wsg::kStages) - 1) & 1);
+          WS_PROF(0)
+          const uint32_t ta = base + st * tcg::kStageBytes, bar = smem_u32(&bar_full[st]);
+          const long long k = w.kbeg + (long long)s * tcg::kSlab;
+          mbar_expect_tx(&bar_full[st], tcg::kStageBytes);
+          tma_slab<AK>(ta, &map_a, bar, a_blocked, w.m0, k);
+          tma_slab<BK>(ta + tcg::kOperandBytes, &map_b, bar, b_blocked, w.n0, k);
+        }
+      }
+      WS_PROF(1)
+      if (g.prof) {
+        long long* o = g.prof + (size_t)blockIdx.x * 16;
+        o[0] = pf[0]; o[1] = pf[1]; o[2] = slab;
+      }
+    }
+  } else if (warp == wsg::kMmaWarp) {
+    // ---------------- MMA issue ----------------
+    const uint32_t el = elect_one();
+    constexpr uint32_t kIdesc = tcg::idesc_tf32(!AK, !BK);
+    const uint32_t hi_k = (uint32_t)(1024 >> 4) | (1u << 14) | (2u << 29);
+    const uint32_t hi_mn = (uint32_t)(wsg::kMnSbo >> 4) | (1u << 14) | (1u << 29);   // layout type 1 = SWIZZLE_128B_BASE32B
+    const uint32_t a_hi = AK ? hi_k : hi_mn, b_hi = BK ? hi_k : hi_mn;
+    const uint32_t a_lbo = AK ? (1u << 16) : ((uint32_t)(wsg::kMnLbo >> 4) << 16), b_lbo = BK ? (1u << 16) : ((uint32_t)(wsg::kMnLbo >> 4) << 16);
+    constexpr uint32_t a_kstep = AK ? 2u : (uint32_t)(2 * wsg::kMnSbo >> 4), b_kstep = BK ? 2u : (uint32_t)(2 * wsg::kMnSbo >> 4);   // +8 K per MMA
+    uint32_t slab = 0, tile = 0;
+    for (int item = blockIdx.x; item < items; item += gridDim.x) {
+      const WsItem w = ws_item(g, item, ntn, ntm);
+      if (w.nslabs == 0) continue;
+      const uint32_t buf = tile & 1;
+      WS_PROF(2)
+      if (tile >= 2) mbar_wait(&bar_tempty[buf], ((tile >> 1) - 1) & 1);       // the epilogue has read this buffer
+      WS_PROF(0)
+      tc_fence_after();
+      for (int s = 0; s < w.nslabs; ++s, ++slab) {
+        const uint32_t st = slab % wsg::kStages;
+        WS_PROF(2)
+        mbar_wait(&bar_full[st], (slab / wsg::kStages) & 1);
+        WS_PROF(1)
+        tc_fence_after();
+        const uint32_t ta = base + st * tcg::kStageBytes, tb = ta + tcg::kOperandBytes;
+        const uint32_t a_lo = ((ta & 0x3FFFFu) >> 4) | a_lbo, b_lo = ((tb & 0x3FFFFu) >> 4) | b_lbo;
+#pragma unroll
+        for (int ki = 0; ki < 4; ++ki)
+          tcg::umma_tf32_e(tmem + buf * 128, a_lo + ki * a_kstep, a_hi, b_lo + ki * b_kstep, b_hi, kIdesc, el,
+                           (s > 0 || ki > 0) ? 1u : 0u);
+        umma_commit_e(smem_u32(&bar_empty[st]), el);
+      }
+      umma_commit_e(smem_u32(&bar_tfull[buf]), el);
+      ++tile;
+    }
+    if (g.prof && lane == 0) {
+      long long* o = g.prof + (size_t)blockIdx.x * 16;
+      o[3] = pf[0]; o[4] = pf[1]; o[5] = pf[2];
+    }
+  } else {
+    // ---------------- epilogue ----------------
+    const int ew = warp - wsg::kMmaWarp - 1;           // 0..7
+    const int q = warp & 3, half = ew >> 2;            // TMEM lane quarter of this warp (warp % 4), column half
+    float* const st = staging + ew * 32 * wsg::kStagePitch;
+    const bool split = g.splits > 1;
+    uint32_t tile = 0;
+    for (int item = blockIdx.x; item < items; item += gridDim.x) {
+      const WsItem w = ws_item(g, item, ntn, ntm);
+      const uint32_t buf = tile & 1;
+      WS_PROF(1)
+      if (w.nslabs > 0) {
+        mbar_wait(&bar_tfull[buf], (tile >> 1) & 1);
+        tc_fence_after();
+      }
+      WS_PROF(0)
+#pragma unroll
+      for (int chunk = 0; chunk < 2; ++chunk) {
+        uint32_t r[2][16];
+        if (w.nslabs > 0) {
+          const uint32_t ta = tmem + ((uint32_t)(q * 32) << 16) + buf * 128 + half * 64 + chunk * 32;
+          tmem_ld16_nowait(ta, r[0]);
+          tmem_ld16_nowait(ta + 16, r[1]);
+          tmem_wait_ld();
+          if (chunk == 1) {
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&bar_tempty[buf]);     // the MMAs of the tile after next may overwrite it
+          }
+        } else {
+#pragma unroll
+          for (int i = 0; i < 16; ++i) r[0][i] = r[1][i] = 0u;
+        }
+        float* srow = st + lane * wsg::kStagePitch;
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          const uint32_t* rr = r[j >> 2] + (j & 3) * 4;
+          *reinterpret_cast<uint4*>(srow + j * 4) = make_uint4(rr[0], rr[1], rr[2], rr[3]);
+        }
+        __syncwarp();
+        const int n = w.n0 + half * 64 + chunk * 32 + (lane & 7) * 4;
+#pragma unroll
+        for (int it = 0; it < 8; ++it) {
+          const int row = it * 4 + (lane >> 3);
+          const int m = w.m0 + q * 32 + row;
+          if (m < g.M && n < g.N)
+            gemm_store4(g, split, w.z, m, n, *reinterpret_cast<const float4*>(st + row * wsg::kStagePitch + (lane & 7) * 4));
+        }
+        __syncwarp();
+      }
+      if (w.nslabs > 0) ++tile;
+    }
+    WS_PROF(1)
+    if (g.prof && ew == 0 && lane == 0) {
+      long long* o = g.prof + (size_t)blockIdx.x * 16;
+      o[6] = pf[0]; o[7] = pf[1];
+    }
+  }
+#undef WS_PROF
+  tc_fence_before();
+  __syncthreads();
+  if (warp == wsg::kMmaWarp) {
+    tc_fence_after();
+    tmem_dealloc(tmem, 256);
+  }
+}
+
+// ---- tensor maps (host) ----------------------------------------------------------------------------------
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                  const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+EncodeTiledFn encode_tiled_fn() {
+  static EncodeTiledFn fn = nullptr;
+  static bool tried = false;
+  if (!tried) {
+    tried = true;
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess &&
+        q == cudaDriverEntryPointSuccess)
+      fn = (EncodeTiledFn)p;
+  }
+  return fn;
+}
+
+// Tensor map of one operand for tma_slab (extent xext along M / N, K along the reduction); false = this operand cannot
+// be described (the caller takes the one-tile kernel).
+template <bool KCONTIG>
+bool make_operand_map(CUtensorMap* m, const float* X, long long ld, long long cblk, int xext, long long K) {
+  EncodeTiledFn enc = encode_tiled_fn();
+  if (!enc || K < 32 || xext < 1 || (ld & 3) || (cblk & 3) || ((uintptr_t)X & 15)) return false;
+  cuuint64_t dims[4], strides[3];
+  cuuint32_t box[4], estr[4] = {1, 1, 1, 1};
+  cuuint32_t rank;
+  CUtensorMapSwizzle sw;
+  const bool blocked = cblk != 128;
+  if (KCONTIG) {                       // X[x][k]
+    sw = CU_TENSOR_MAP_SWIZZLE_128B;
+    if (!blocked) {
+      rank = 2;
+      dims[0] = (cuuint64_t)K; dims[1] = (cuuint64_t)xext;
+      strides[0] = (cuuint64_t)ld * 4;
+      box[0] = 32; box[1] = 128;
+    } else {
+      if (K & 127) return false;
+      rank = 3;
+      dims[0] = 128; dims[1] = (cuuint64_t)xext; dims[2] = (cuuint64_t)(K >> 7);
+      strides[0] = (cuuint64_t)ld * 4; strides[1] = (cuuint64_t)cblk * 4;
+      box[0] = 32; box[1] = 128; box[2] = 1;
+    }
+  } else {                             // X[k][x]
+    sw = CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B;
+    if (!blocked) {
+      if (xext & 31) return false;
+      rank = 3;
+      dims[0] = 32; dims[1] = (cuuint64_t)K; dims[2] = (cuuint64_t)(xext >> 5);
+      strides[0] = (cuuint64_t)ld * 4; strides[1] = 128;
+      box[0] = 32; box[1] = 32; box[2] = 4;
+    } else {
+      if (xext & 127) return false;
+      rank = 4;
+      dims[0] = 32; dims[1] = (cuuint64_t)K; dims[2] = 4; dims[3] = (cuuint64_t)(xext >> 7);
+      strides[0] = (cuuint64_t)ld * 4; strides[1] = 128; strides[2] = (cuuint64_t)cblk * 4;
+      box[0] = 32; box[1] = 32; box[2] = 4; box[3] = 1;
+    }
+  }
+  return enc(m, CU_TENSOR_MAP_DATA_TYPE_TFLOAT32, rank, const_cast<float*>(X), dims, strides, box, estr,
+             CU_TENSOR_MAP_INTERLEAVE_NONE, sw, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
+}
+
+int g_tc_one_tile = 0;       // debug: 1 = sgemm_tc_kernel (one tile per CTA) instead of the persistent kernel (same-process A/B)
 
 // second stage of every split reduction: out[i] (=|+=) alpha * sum_s partial[s][i] in a FIXED order (deterministic):
 // a block covers 32 consecutive outputs with 8 split lanes; lane j adds the splits j, j + 8, ... in order (coalesced
@@ -472,9 +782,25 @@ int gemm(const Gemm& g, const float* A, long long lda, const float* B, long long
   if (M <= 0 || N <= 0) return ARREAU_OK;
   const int tiles = ((M + kBM - 1) / kBM) * ((N + kBN - 1) / kBN);
   const bool plain_out = !bias && !o.gelu_out && !o.gz && o.c_cblk == 128;   // what the split second stage can finish
+  // tensor maps of the operands for the TMA-fed persistent kernel; an operand it cannot describe -> one tile per CTA
+  alignas(64) CUtensorMap map_a, map_b;
+  const bool use_tma = g.tf32 && !g_tc_one_tile && make_operand_map<AK>(&map_a, A, lda, o.a_cblk, M, K) &&
+                       make_operand_map<BK>(&map_b, B, ldb, o.b_cblk, N, K);
   int splits = 1;
   if (K > 4096 && tiles < g.sms && plain_out) {      // reduction-dominated (weight gradients): split the rows
     splits = (2 * g.sms + tiles - 1) / tiles;
+    if (use_tma) {
+      // persistent kernel: items = tiles * splits should fill whole rounds of the SMs; the fewest splits that do
+      // (within 3 %) keep the partial traffic and the second stage small
+      double best = 0.0;
+      for (int r = 1; r <= 4; ++r) {
+        const int sp = r * g.sms / tiles;
+        if (sp < 1) continue;
+        const long long it = (long long)sp * tiles;
+        const double util = (double)it / (double)(((it + g.sms - 1) / g.sms) * g.sms);
+        if (util > best + 0.03) { best = util; splits = sp; }
+      }
+    }
     const long long max_by_k = (K + 511) / 512;
     if (splits > max_by_k) splits = (int)max_by_k;
     while (splits > 1 && (size_t)splits * M * N > g.partial_floats) --splits;
@@ -485,8 +811,17 @@ int gemm(const Gemm& g, const float* A, long long lda, const float* B, long long
   if (splits < 1) splits = 1;
   dim3 grid((N + kBN - 1) / kBN, (M + kBM - 1) / kBM, splits);
   GemmArgs a{A, lda, o.a_cblk, B, ldb, o.b_cblk, C, ldc, o.c_cblk, M, N, K, kps, alpha, bias, accumulate ? 1 : 0,
-             g.partial, o.gelu_out, o.gz, o.gz_ld, o.rowscale, g_tc_mn_lbo, g_tc_mn_sbo};
-  if (g.tf32) {
+             g.partial, o.gelu_out, o.gz, o.gz_ld, o.rowscale, g_tc_mn_lbo, g_tc_mn_sbo, splits, g_ws_prof};
+  if (use_tma) {
+    static bool attr_set = false;       // one flag per template instance
+    if (!attr_set) {
+      cudaError_t e = cudaFuncSetAttribute(sgemm_tma_kernel<AK, BK>, cudaFuncAttributeMaxDynamicSharedMemorySize, wsg::kSmemBytes);
+      if (e != cudaSuccess) return (int)e;
+      attr_set = true;
+    }
+    const long long items = (long long)tiles * splits;
+    sgemm_tma_kernel<AK, BK><<<(unsigned)(items < g.sms ? items : g.sms), wsg::kThreads, wsg::kSmemBytes, g.s>>>(a, map_a, map_b);
+  } else if (g.tf32) {
     static bool attr_set = false;       // one flag per template instance
     if (!attr_set) {
       cudaError_t e = cudaFuncSetAttribute(sgemm_tc_kernel<AK, BK>, cudaFuncAttributeMaxDynamicSharedMemorySize, tcg::kSmemBytes);
@@ -1124,8 +1459,13 @@ extern "C" int arreau_moments(const float* x, const float* sub_cols, int64_t n, 
 }
 
 // debug only (not part of the public ABI): TF32 GEMM implementation switch and MN-major descriptor strides
+extern "C" int arreau_debug_set_gemm_prof(long long* prof) {
+  g_ws_prof = prof;
+  return ARREAU_OK;
+}
+
 extern "C" int arreau_debug_set_tf32_gemm(int legacy, int mn_lbo, int mn_sbo) {
-  (void)legacy;                          // the mma.sync TF32 kernel this used to select is gone
+  g_tc_one_tile = legacy ? 1 : 0;        // 1 = the one-tile-per-CTA tcgen05 kernel instead of the persistent TMA-fed one
   if (mn_lbo > 0) g_tc_mn_lbo = mn_lbo;
   if (mn_sbo > 0) g_tc_mn_sbo = mn_sbo;
   return ARREAU_OK;
