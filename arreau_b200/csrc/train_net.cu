@@ -66,7 +66,34 @@ __device__ __forceinline__ float gelu_grad(float x) {
   return 0.5f * (1.0f + erff(x * 0.70710678118654752440f)) + x * expf(-0.5f * x * x) * 0.39894228040143267794f;
 }
 
+// GELU and its derivative for the TF32 kernels' epilogues, where the exact erff / expf pair (~60 instructions per value)
+// made the fused epilogues the bound of the HBM-bound products: Phi(x) = 1/2 erfc(-x / sqrt 2) from the Abramowitz-Stegun
+// 7.1.26 rational form (absolute error 1.5e-7, no cancellation on the negative side) and ONE ex2.approx shared by Phi and
+// the density: exp(-x^2 / 2) is both erfc's factor and sqrt(2 pi) phi(x).
+__device__ __forceinline__ void gelu_parts_fast(float x, float& cdf, float& e) {
+  const float a = fabsf(x) * 0.70710678118654752440f;
+  const float t = __fdividef(1.0f, fmaf(0.3275911f, a, 1.0f));
+  e = __expf(-a * a);
+  const float h = 0.5f * e * t * fmaf(t, fmaf(t, fmaf(t, fmaf(t, 1.061405429f, -1.453152027f), 1.421413741f), -0.284496736f), 0.254829592f);
+  cdf = x < 0.f ? h : 1.0f - h;
+}
+template <bool FAST>
+__device__ __forceinline__ float gelu_fwd_t(float x) {
+  if (!FAST) return gelu_erf(x);
+  float cdf, e;
+  gelu_parts_fast(x, cdf, e);
+  return x * cdf;
+}
+template <bool FAST>
+__device__ __forceinline__ float gelu_grad_t(float x) {
+  if (!FAST) return gelu_grad(x);
+  float cdf, e;
+  gelu_parts_fast(x, cdf, e);
+  return fmaf(x * 0.39894228040143267794f, e, cdf);
+}
+
 // the four accumulators (m, n .. n + 3) of a tile on their way out (n % 4 == 0, n < N)
+template <bool FAST = false>
 __device__ __forceinline__ void gemm_store4(const GemmArgs& g, bool split, int z, int m, int n, float4 v) {
   if (split) {
     *reinterpret_cast<float4*>(g.partial + ((size_t)z * g.M + m) * g.N + n) = v;
@@ -78,7 +105,8 @@ __device__ __forceinline__ void gemm_store4(const GemmArgs& g, bool split, int z
   const float rs = g.rowscale ? g.rowscale[m >> 4] : 1.0f;
   if (g.gz) {
     const float4 z = *reinterpret_cast<const float4*>(g.gz + (long long)m * g.gz_ld + n);
-    v.x *= gelu_grad(z.x) * rs; v.y *= gelu_grad(z.y) * rs; v.z *= gelu_grad(z.z) * rs; v.w *= gelu_grad(z.w) * rs;
+    v.x *= gelu_grad_t<FAST>(z.x) * rs; v.y *= gelu_grad_t<FAST>(z.y) * rs;
+    v.z *= gelu_grad_t<FAST>(z.z) * rs; v.w *= gelu_grad_t<FAST>(z.w) * rs;
   }
   const long long off = (long long)m * g.ldc + blk_off(n, g.c_cblk);
   if (g.accumulate) {
@@ -87,7 +115,8 @@ __device__ __forceinline__ void gemm_store4(const GemmArgs& g, bool split, int z
   }
   *reinterpret_cast<float4*>(g.C + off) = v;
   if (g.C2)
-    *reinterpret_cast<float4*>(g.C2 + off) = make_float4(gelu_erf(v.x) * rs, gelu_erf(v.y) * rs, gelu_erf(v.z) * rs, gelu_erf(v.w) * rs);
+    *reinterpret_cast<float4*>(g.C2 + off) = make_float4(gelu_fwd_t<FAST>(v.x) * rs, gelu_fwd_t<FAST>(v.y) * rs,
+                                                         gelu_fwd_t<FAST>(v.z) * rs, gelu_fwd_t<FAST>(v.w) * rs);
 }
 
 template <bool KCONTIG>
@@ -445,17 +474,18 @@ sgemm_tc_kernel(const __grid_constant__ GemmArgs g) {
 //               block-strided operands (GemmArgs) get one more tensor dimension;
 //   warp 1      MMA issue: four 128x128x8 kind::tf32 MMAs per slab, tcgen05.commit -> empty[stage]; the accumulator is
 //               double-buffered in tensor memory (2 x 128 columns), commit -> tmem_full[buffer] after a tile's last slab;
-//   warps 2-9   epilogue: warp w owns TMEM lanes 32 (w % 4) and 64 columns: tcgen05.ld in 32-column chunks through a private
-//               shared-memory staging tile, so that the global stores (and the loads of the fused epilogue, GemmArgs) are
-//               whole 128-byte row segments; the buffer is released (tmem_empty) after the last tcgen05.ld.
+//   warps 2-17  epilogue: warp w owns TMEM lanes 32 (w % 4) and 32 columns: tcgen05.ld, release of the buffer (tmem_empty),
+//               then through a private shared-memory staging tile, so that the global stores (and the loads of the fused
+//               epilogue, GemmArgs) are whole 128-byte row segments; GELU / GELU' in the fast form above.
 // So the loads of tile i + 1, the MMAs of tile i and the stores of tile i - 1 overlap.
 // ================================================================================================
 namespace wsg {
-constexpr int kStages = 5;
+constexpr int kStages = 4;
 constexpr int kMmaWarp = 1;
-constexpr int kThreads = 10 * 32;
+constexpr int kEpiWarps = 16;
+constexpr int kThreads = (2 + kEpiWarps) * 32;
 constexpr int kStagePitch = 36;                  // floats: 32 columns + 4 (conflict-free 16-byte rows)
-constexpr int kStagingBytes = 8 * 32 * kStagePitch * 4;
+constexpr int kStagingBytes = kEpiWarps * 32 * kStagePitch * 4;
 constexpr int kSmemBytes = kStages * tcg::kStageBytes + kStagingBytes + 256 + 1024;
 constexpr int kMnLbo = 4096, kMnSbo = 512;       // MN-major tile image written by the TMA box (see above)
 }  // namespace wsg
@@ -527,7 +557,7 @@ sgemm_tma_kernel(const __grid_constant__ GemmArgs g, const __grid_constant__ CUt
     }
     for (int i = 0; i < 2; ++i) {
       mbar_init(&bar_tfull[i], 1);
-      mbar_init(&bar_tempty[i], 8);
+      mbar_init(&bar_tempty[i], wsg::kEpiWarps);
     }
     fence_barrier_init();
   }
@@ -605,8 +635,8 @@ sgemm_tma_kernel(const __grid_constant__ GemmArgs g, const __grid_constant__ CUt
     }
   } else {
     // ---------------- epilogue ----------------
-    const int ew = warp - wsg::kMmaWarp - 1;           // 0..7
-    const int q = warp & 3, half = ew >> 2;            // TMEM lane quarter of this warp (warp % 4), column half
+    const int ew = warp - wsg::kMmaWarp - 1;           // 0..15
+    const int q = warp & 3, cq = ew >> 2;              // TMEM lane quarter of this warp (warp % 4), column quarter
     float* const st = staging + ew * 32 * wsg::kStagePitch;
     const bool split = g.splits > 1;
     uint32_t tile = 0;
@@ -619,19 +649,16 @@ sgemm_tma_kernel(const __grid_constant__ GemmArgs g, const __grid_constant__ CUt
         tc_fence_after();
       }
       WS_PROF(0)
-#pragma unroll
-      for (int chunk = 0; chunk < 2; ++chunk) {
+      {
         uint32_t r[2][16];
         if (w.nslabs > 0) {
-          const uint32_t ta = tmem + ((uint32_t)(q * 32) << 16) + buf * 128 + half * 64 + chunk * 32;
+          const uint32_t ta = tmem + ((uint32_t)(q * 32) << 16) + buf * 128 + cq * 32;
           tmem_ld16_nowait(ta, r[0]);
           tmem_ld16_nowait(ta + 16, r[1]);
           tmem_wait_ld();
-          if (chunk == 1) {
-            tc_fence_before();
-            __syncwarp();
-            if (lane == 0) mbar_arrive(&bar_tempty[buf]);     // the MMAs of the tile after next may overwrite it
-          }
+          tc_fence_before();
+          __syncwarp();
+          if (lane == 0) mbar_arrive(&bar_tempty[buf]);     // the MMAs of the tile after next may overwrite it
         } else {
 #pragma unroll
           for (int i = 0; i < 16; ++i) r[0][i] = r[1][i] = 0u;
@@ -643,13 +670,13 @@ sgemm_tma_kernel(const __grid_constant__ GemmArgs g, const __grid_constant__ CUt
           *reinterpret_cast<uint4*>(srow + j * 4) = make_uint4(rr[0], rr[1], rr[2], rr[3]);
         }
         __syncwarp();
-        const int n = w.n0 + half * 64 + chunk * 32 + (lane & 7) * 4;
+        const int n = w.n0 + cq * 32 + (lane & 7) * 4;
 #pragma unroll
         for (int it = 0; it < 8; ++it) {
           const int row = it * 4 + (lane >> 3);
           const int m = w.m0 + q * 32 + row;
           if (m < g.M && n < g.N)
-            gemm_store4(g, split, w.z, m, n, *reinterpret_cast<const float4*>(st + row * wsg::kStagePitch + (lane & 7) * 4));
+            gemm_store4<true>(g, split, w.z, m, n, *reinterpret_cast<const float4*>(st + row * wsg::kStagePitch + (lane & 7) * 4));
         }
         __syncwarp();
       }
