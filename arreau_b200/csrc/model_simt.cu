@@ -242,18 +242,31 @@ fiber_kernel_kernel(const float* __restrict__ ori, const float* __restrict__ w1,
                     (double)ori[3 * o + 2] * ori[3 * p + 2];
   if (t < kC) h1[t] = gelu_erf_d(w1[3 * t] * fa + w1[3 * t + 1] * (fa * fa) + w1[3 * t + 2] * (fa * fa * fa) + b1[t]);
   __syncthreads();
-  {
-    double s = b2[t];
-    for (int c = 0; c < kC; ++c) s += (double)w2[(size_t)t * kC + c] * h1[c];
-    fkb[t] = gelu_erf_d(s);
+  // a warp per output, lanes over the reduced index (coalesced weight rows, shuffle tree): one thread per output walking
+  // a 1 KB-strided row of 256 fp64 products took 213 us per call, once per training step
+  const int warp = t >> 5, lane = t & 31;
+  auto warp_sum = [](double s) {
+#pragma unroll
+    for (int off = 16; off > 0; off >>= 1) s += __shfl_xor_sync(0xffffffffu, s, off);
+    return s;
+  };
+  for (int d = warp; d < kD; d += kD / 32) {
+    const float* w = w2 + (size_t)d * kC;
+    double s = 0.0;
+#pragma unroll
+    for (int c = lane; c < kC; c += 32) s += (double)w[c] * h1[c];
+    s = warp_sum(s);
+    if (lane == 0) fkb[d] = gelu_erf_d(s + (double)b2[d]);
   }
   __syncthreads();
-  for (int idx = t; idx < kL * kC; idx += kD) {
+  for (int idx = warp; idx < kL * kC; idx += kD / 32) {
     const int l = idx / kC, c = idx % kC;
     const float* w = wf + ((size_t)l * kC + c) * kD;
     double s = 0.0;
-    for (int d = 0; d < kD; ++d) s += (double)w[d] * fkb[d];
-    fk[(((size_t)l * kO + o) * kO + p) * kC + c] = (float)s;
+#pragma unroll
+    for (int d = lane; d < kD; d += 32) s += (double)w[d] * fkb[d];
+    s = warp_sum(s);
+    if (lane == 0) fk[(((size_t)l * kO + o) * kO + p) * kC + c] = (float)s;
   }
 }
 

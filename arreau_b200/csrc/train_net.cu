@@ -94,7 +94,8 @@ __device__ __forceinline__ float gelu_grad_t(float x) {
 
 // the four accumulators (m, n .. n + 3) of a tile on their way out (n % 4 == 0, n < N)
 template <bool FAST = false>
-__device__ __forceinline__ void gemm_store4(const GemmArgs& g, bool split, int z, int m, int n, float4 v) {
+__device__ __forceinline__ void gemm_store4(const GemmArgs& g, bool split, int z, int m, int n, float4 v,
+                                            const float4* gz_loaded = nullptr) {
   if (split) {
     *reinterpret_cast<float4*>(g.partial + ((size_t)z * g.M + m) * g.N + n) = v;
     return;
@@ -104,7 +105,7 @@ __device__ __forceinline__ void gemm_store4(const GemmArgs& g, bool split, int z
   v.x = fmaf(v.x, g.alpha, bb.x); v.y = fmaf(v.y, g.alpha, bb.y); v.z = fmaf(v.z, g.alpha, bb.z); v.w = fmaf(v.w, g.alpha, bb.w);
   const float rs = g.rowscale ? g.rowscale[m >> 4] : 1.0f;
   if (g.gz) {
-    const float4 z = *reinterpret_cast<const float4*>(g.gz + (long long)m * g.gz_ld + n);
+    const float4 z = gz_loaded ? *gz_loaded : *reinterpret_cast<const float4*>(g.gz + (long long)m * g.gz_ld + n);
     v.x *= gelu_grad_t<FAST>(z.x) * rs; v.y *= gelu_grad_t<FAST>(z.y) * rs;
     v.z *= gelu_grad_t<FAST>(z.z) * rs; v.w *= gelu_grad_t<FAST>(z.w) * rs;
   }
@@ -643,6 +644,17 @@ sgemm_tma_kernel(const __grid_constant__ GemmArgs g, const __grid_constant__ CUt
     for (int item = blockIdx.x; item < items; item += gridDim.x) {
       const WsItem w = ws_item(g, item, ntn, ntm);
       const uint32_t buf = tile & 1;
+      const int n = w.n0 + cq * 32 + (lane & 7) * 4;
+      // the pre-activations of a fused GELU' do not depend on the product: fetched before the wait for the accumulator
+      float4 gzv[8];
+      if (g.gz && !split) {
+#pragma unroll
+        for (int it = 0; it < 8; ++it) {
+          const int m = w.m0 + q * 32 + it * 4 + (lane >> 3);
+          gzv[it] = (m < g.M && n < g.N) ? __ldg(reinterpret_cast<const float4*>(g.gz + (long long)m * g.gz_ld + n))
+                                         : make_float4(0.f, 0.f, 0.f, 0.f);
+        }
+      }
       WS_PROF(1)
       if (w.nslabs > 0) {
         mbar_wait(&bar_tfull[buf], (tile >> 1) & 1);
@@ -670,13 +682,13 @@ sgemm_tma_kernel(const __grid_constant__ GemmArgs g, const __grid_constant__ CUt
           *reinterpret_cast<uint4*>(srow + j * 4) = make_uint4(rr[0], rr[1], rr[2], rr[3]);
         }
         __syncwarp();
-        const int n = w.n0 + cq * 32 + (lane & 7) * 4;
 #pragma unroll
         for (int it = 0; it < 8; ++it) {
           const int row = it * 4 + (lane >> 3);
           const int m = w.m0 + q * 32 + row;
           if (m < g.M && n < g.N)
-            gemm_store4<true>(g, split, w.z, m, n, *reinterpret_cast<const float4*>(st + row * wsg::kStagePitch + (lane & 7) * 4));
+            gemm_store4<true>(g, split, w.z, m, n, *reinterpret_cast<const float4*>(st + row * wsg::kStagePitch + (lane & 7) * 4),
+                              &gzv[it]);
         }
         __syncwarp();
       }
