@@ -43,7 +43,8 @@ constexpr int kBM = 128, kBN = 128, kBK = 16, kSP = 132, kGT = 256;
 // and the shared operand is streamed from HBM once instead of five times.
 // Epilogue (unsplit launches only), in this order:  v = alpha * acc + bias[n];  v *= gelu'(gz[m][n]) * rowscale[m >> 4]  (gz);
 // v += C (accumulate);  C = v;  C2 = gelu(v) * rowscale[m >> 4]  (C2: the activation next to its pre-activation, so that no
-// separate element-wise pass re-reads the matrix).
+// separate element-wise pass re-reads the matrix), or, with res_in:  C2 = res_in + res_scale[n] * v  (the residual update
+// of the ConvNext block next to the kept MLP output).
 struct GemmArgs {
   const float* A; long long lda, a_cblk;
   const float* B; long long ldb, b_cblk;
@@ -54,6 +55,7 @@ struct GemmArgs {
   float* C2;
   const float* gz; long long gz_ld;
   const float* rowscale;
+  const float* res_in; const float* res_scale;   // C2 = res_in[m][n] + res_scale[n] * v (pitch ldc) instead of the GELU
   int mn_lbo, mn_sbo;
   int splits;                 // K splits (the persistent kernel's grid is not the tile grid)
   long long* prof;            // debug: per-CTA phase clocks of the persistent kernel ([grid][16]), or null
@@ -115,7 +117,10 @@ __device__ __forceinline__ void gemm_store4(const GemmArgs& g, bool split, int z
     v.x += c.x; v.y += c.y; v.z += c.z; v.w += c.w;
   }
   *reinterpret_cast<float4*>(g.C + off) = v;
-  if (g.C2)
+  if (g.res_in) {
+    const float4 r = *reinterpret_cast<const float4*>(g.res_in + off), sc = *reinterpret_cast<const float4*>(g.res_scale + n);
+    *reinterpret_cast<float4*>(g.C2 + off) = make_float4(fmaf(sc.x, v.x, r.x), fmaf(sc.y, v.y, r.y), fmaf(sc.z, v.z, r.z), fmaf(sc.w, v.w, r.w));
+  } else if (g.C2)
     *reinterpret_cast<float4*>(g.C2 + off) = make_float4(gelu_fwd_t<FAST>(v.x) * rs, gelu_fwd_t<FAST>(v.y) * rs,
                                                          gelu_fwd_t<FAST>(v.z) * rs, gelu_fwd_t<FAST>(v.w) * rs);
 }
@@ -775,26 +780,37 @@ bool make_operand_map(CUtensorMap* m, const float* X, long long ld, long long cb
 int g_tc_one_tile = 0;       // debug: 1 = sgemm_tc_kernel (one tile per CTA) instead of the persistent kernel (same-process A/B)
 
 // second stage of every split reduction: out[i] (=|+=) alpha * sum_s partial[s][i] in a FIXED order (deterministic):
-// a block covers 32 consecutive outputs with 8 split lanes; lane j adds the splits j, j + 8, ... in order (coalesced
-// 128-byte reads, chains 8x shorter than one thread per output), then the 8 lane sums are added in lane order.
-__global__ void __launch_bounds__(256)
+// a block covers 32 consecutive outputs with LANES split lanes; lane j adds the splits j, j + LANES, ... in order (coalesced
+// 128-byte reads), then the lane sums are added in lane order.  LANES = 32 for the long split lists of the column sums
+// (a few outputs, hundreds of splits: a latency chain), 8 for the short ones of the split products.
+template <int LANES>
+__global__ void __launch_bounds__(32 * LANES)
 reduce_partials_kernel(const float* __restrict__ partial, int splits, long long n, long long ldo, int ncols,
                        float alpha, int accumulate, float* __restrict__ out) {
-  __shared__ float red[8][32];
+  __shared__ float red[LANES][32];
   const int o = threadIdx.x & 31, sl = threadIdx.x >> 5;
   const long long i = (long long)blockIdx.x * 32 + o;
   float s = 0.f;
-  if (i < n)
-    for (int k = sl; k < splits; k += 8) s += partial[(size_t)k * n + i];
+  if (i < n) {
+#pragma unroll 4
+    for (int k = sl; k < splits; k += LANES) s += partial[(size_t)k * n + i];
+  }
   red[sl][o] = s;
   __syncthreads();
   if (sl == 0 && i < n) {
 #pragma unroll
-    for (int k = 1; k < 8; ++k) s += red[k][o];
+    for (int k = 1; k < LANES; ++k) s += red[k][o];
     s *= alpha;
     float* p = out + (i / ncols) * ldo + (i % ncols);
     *p = accumulate ? *p + s : s;
   }
+}
+
+void reduce_partials(cudaStream_t s, const float* partial, int splits, long long n, long long ldo, int ncols, float alpha,
+                     int accumulate, float* out) {
+  const unsigned blocks = (unsigned)((n + 31) / 32);
+  if (splits > 64) reduce_partials_kernel<32><<<blocks, 1024, 0, s>>>(partial, splits, n, ldo, ncols, alpha, accumulate, out);
+  else reduce_partials_kernel<8><<<blocks, 256, 0, s>>>(partial, splits, n, ldo, ncols, alpha, accumulate, out);
 }
 
 struct Gemm {
@@ -812,6 +828,8 @@ struct GemmOpt {
   const float* gz = nullptr;            // C = (alpha A B + bias) * gelu'(gz) * rowscale
   long long gz_ld = 0;
   const float* rowscale = nullptr;      // per 16 rows of C (the cutoff window of an edge)
+  const float* res_in = nullptr;        // with res_scale and gelu_out: gelu_out = res_in + res_scale[n] * C (residual update)
+  const float* res_scale = nullptr;
 };
 
 // op: C[M,N] (=|+=) alpha A B (+bias), epilogue options in `o`.  Returns ARREAU_* / cudaError.
@@ -850,7 +868,7 @@ int gemm(const Gemm& g, const float* A, long long lda, const float* B, long long
   if (splits < 1) splits = 1;
   dim3 grid((N + kBN - 1) / kBN, (M + kBM - 1) / kBM, splits);
   GemmArgs a{A, lda, o.a_cblk, B, ldb, o.b_cblk, C, ldc, o.c_cblk, M, N, K, kps, alpha, bias, accumulate ? 1 : 0,
-             g.partial, o.gelu_out, o.gz, o.gz_ld, o.rowscale, g_tc_mn_lbo, g_tc_mn_sbo, splits, g_ws_prof};
+             g.partial, o.gelu_out, o.gz, o.gz_ld, o.rowscale, o.res_in, o.res_scale, g_tc_mn_lbo, g_tc_mn_sbo, splits, g_ws_prof};
   if (use_tma) {
     static bool attr_set = false;       // one flag per template instance
     if (!attr_set) {
@@ -874,8 +892,7 @@ int gemm(const Gemm& g, const float* A, long long lda, const float* B, long long
   CUDA_LAUNCH_CHECK();
   if (splits > 1) {
     const long long n = (long long)M * N;
-    reduce_partials_kernel<<<(unsigned)((n + 31) / 32), 256, 0, g.s>>>(g.partial, splits, n, ldc, N, alpha,
-                                                                         accumulate ? 1 : 0, C);
+    reduce_partials(g.s, g.partial, splits, n, ldc, N, alpha, accumulate ? 1 : 0, C);
     CUDA_LAUNCH_CHECK();
   }
   return ARREAU_OK;
@@ -934,8 +951,7 @@ int colsum(const Gemm& g, const float* X, const float* Y, long long rows, int nc
   if (Y) colsum_kernel<true><<<(unsigned)splits, 256, 0, g.s>>>(X, Y, rows, ncols, ld, g.partial);
   else colsum_kernel<false><<<(unsigned)splits, 256, 0, g.s>>>(X, nullptr, rows, ncols, ld, g.partial);
   CUDA_LAUNCH_CHECK();
-  reduce_partials_kernel<<<(ncols + 31) / 32, 256, 0, g.s>>>(g.partial, (int)splits, ncols, ncols, ncols, 1.0f,
-                                                               accumulate ? 1 : 0, out);
+  reduce_partials(g.s, g.partial, (int)splits, ncols, ncols, ncols, 1.0f, accumulate ? 1 : 0, out);
   CUDA_LAUNCH_CHECK();
   return ARREAU_OK;
 }
@@ -1078,21 +1094,29 @@ ln_bwd_kernel(const float* __restrict__ x2, const float* __restrict__ dy, const 
 }
 
 // ---- fiber conv backward (conv.py:115): x2[b,p,c] = (1/O) sum_o x1[b,o,c] fk[o,p,c] ------------------------
-// dx1[b,o,c] = (1/O) sum_p dx2[b,p,c] fk[o,p,c]; thread = (atom, channel)
+// dx1[b,o,c] = (1/O) sum_p dx2[b,p,c] fk[o,p,c]; block = two atoms, thread = channel (every fiber-kernel value read from
+// L1 serves both atoms; N / 2 independent blocks instead of 2 per SM looping over their atoms)
 __global__ void __launch_bounds__(kC)
 fiber_bwd_dx1_kernel(const float* __restrict__ dx2, const float* __restrict__ fk, int N, float* __restrict__ dx1) {
   const int c = threadIdx.x;
-  for (int b = blockIdx.x; b < N; b += gridDim.x) {
-    float d[kO];
+  const int b0 = 2 * blockIdx.x, b1 = b0 + 1 < N ? b0 + 1 : b0;
+  float d0[kO], d1[kO];
 #pragma unroll
-    for (int p = 0; p < kO; ++p) d[p] = dx2[((size_t)b * kO + p) * kC + c];
+  for (int p = 0; p < kO; ++p) {
+    d0[p] = dx2[((size_t)b0 * kO + p) * kC + c];
+    d1[p] = dx2[((size_t)b1 * kO + p) * kC + c];
+  }
 #pragma unroll 4
-    for (int o = 0; o < kO; ++o) {
-      float s = 0.f;
+  for (int o = 0; o < kO; ++o) {
+    float s0 = 0.f, s1 = 0.f;
 #pragma unroll
-      for (int p = 0; p < kO; ++p) s = fmaf(d[p], __ldg(fk + ((size_t)o * kO + p) * kC + c), s);
-      dx1[((size_t)b * kO + o) * kC + c] = s * (1.0f / kO);
+    for (int p = 0; p < kO; ++p) {
+      const float f = __ldg(fk + ((size_t)o * kO + p) * kC + c);
+      s0 = fmaf(d0[p], f, s0);
+      s1 = fmaf(d1[p], f, s1);
     }
+    dx1[((size_t)b0 * kO + o) * kC + c] = s0 * (1.0f / kO);
+    if (b1 != b0) dx1[((size_t)b1 * kO + o) * kC + c] = s1 * (1.0f / kO);
   }
 }
 
@@ -1347,7 +1371,7 @@ struct Carver {
 };
 
 constexpr size_t kPartialFloats = (size_t)8 << 20;   // 32 MB of split scratch
-constexpr int kDfkBlocks = 64;
+constexpr int kDfkBlocks = 148;
 constexpr int kLnBlocks = 296;
 
 struct BwdBuffers {
@@ -1647,7 +1671,7 @@ extern "C" int arreau_ponita_backward(const float* params, const arreau_train_la
       if (blocks > kLnBlocks) blocks = kLnBlocks;
       ln_bwd_kernel<<<blocks, kLnWarps * 32, 0, s>>>(x2, b.dy, P + lay->norm_w + l * kC, Rn, b.dx2, b.partial);
       CUDA_LAUNCH_CHECK();
-      reduce_partials_kernel<<<(3 * kC + 31) / 32, 256, 0, s>>>(b.partial, blocks, 3 * kC, 3 * kC, 3 * kC, 1.f, 0, b.small);
+      reduce_partials(s, b.partial, blocks, 3 * kC, 3 * kC, 3 * kC, 1.f, 0, b.small);
       CUDA_LAUNCH_CHECK();
       // b.small[0..383] = [dgamma | dbeta | dbias]
       cudaError_t e = cudaMemcpyAsync(Gd + lay->norm_w + l * kC, b.small, sizeof(float) * kC, cudaMemcpyDeviceToDevice, s);
@@ -1658,15 +1682,13 @@ extern "C" int arreau_ponita_backward(const float* params, const arreau_train_la
     // fiber conv backward
     const float* fk = w->fiber_kernel + (size_t)l * kO * kO * kC;
     {
-      int blocks = N < 2 * g.sms ? N : 2 * g.sms;
-      fiber_bwd_dx1_kernel<<<blocks, kC, 0, s>>>(b.dx2, fk, N, b.dx1);
+      fiber_bwd_dx1_kernel<<<(N + 1) / 2, kC, 0, s>>>(b.dx2, fk, N, b.dx1);
       CUDA_LAUNCH_CHECK();
       int fb = N < kDfkBlocks ? N : kDfkBlocks;
       fiber_bwd_dfk_kernel<<<fb, 1024, 0, s>>>(x1, b.dx2, N, b.partial);
       CUDA_LAUNCH_CHECK();
       float* dfk = b.dfk + (size_t)l * Rf * kC;
-      reduce_partials_kernel<<<blocks_for((long long)Rf * kC, 32), 256, 0, s>>>(b.partial, fb, (long long)Rf * kC, Rf * kC,
-                                                                               Rf * kC, 1.0f / kO, 0, dfk);
+      reduce_partials(s, b.partial, fb, (long long)Rf * kC, Rf * kC, Rf * kC, 1.0f / kO, 0, dfk);
       CUDA_LAUNCH_CHECK();
     }
     // message pass backward: this layer's slab of the kernel gradient, and dh
@@ -1777,15 +1799,12 @@ extern "C" int arreau_ponita_forward_train(const float* params, const arreau_tra
   const long long Re = Ecap * kO, Rn = (long long)N * kO;
   const size_t node_elems = (size_t)N * kO * kC, layer_kernel_elems = (size_t)Ecap * kO * kC;
   const float* P = params;
-  // embedding (ponita.py:98)
+  // embedding (ponita.py:98); the features of layer l live in slab l of h_debug (what the backward reads): no copies
+  float* const hs = ws->h_debug;
   if (ws->onehot_types)
-    TRY(arreau_node_embed_typed(x, ws->onehot_types, Z, vec, w->w_embed_t, w->ori, N, F, V, ws->h, stream));
+    TRY(arreau_node_embed_typed(x, ws->onehot_types, Z, vec, w->w_embed_t, w->ori, N, F, V, hs, stream));
   else
-    TRY(arreau_node_embed(x, vec, w->w_embed_t, w->ori, N, F, V, ws->h, stream));
-  {
-    cudaError_t e = cudaMemcpyAsync(ws->h_debug, ws->h, node_elems * sizeof(float), cudaMemcpyDeviceToDevice, s);
-    if (e != cudaSuccess) return (int)e;
-  }
+    TRY(arreau_node_embed(x, vec, w->w_embed_t, w->ori, N, F, V, hs, stream));
   // edge chain and the five kernel projections kernels[l] = kb Wk_l^T (conv.py:110) as ONE product: the weights [L][C][D]
   // are one [L*C][D] matrix and the output columns are the per-layer [Re][C] slabs, so kb is streamed once
   TRY(edge_chain_forward(g, b, P, lay, w, fold_table, src, dist, dir, lattice, crystal_of_atom, row_ptr + N, Ecap, radius));
@@ -1804,24 +1823,24 @@ extern "C" int arreau_ponita_forward_train(const float* params, const arreau_tra
     float* al = b.as + (size_t)l * Rn * kW;
     float* ml = b.ms + (size_t)l * Rn * kC;
     // message pass + fiber conv + bias + LayerNorm (conv.py:111-133, convnext.py:25): y = LN(x2), kept
-    TRY(arreau_message_fiber_norm(kern, 0, ws->h, row_ptr, src, w->fiber_kernel + (size_t)l * kO * kO * kC, nullptr,
+    const float* h_in = hs + (size_t)l * node_elems;
+    float* h_out = hs + (size_t)(l + 1) * node_elems;
+    TRY(arreau_message_fiber_norm(kern, 0, h_in, row_ptr, src, w->fiber_kernel + (size_t)l * kO * kO * kC, nullptr,
                                   w->conv_bias + l * kC, w->ln_w + l * kC, w->ln_b + l * kC, N, yl, 0,
                                   ws->x1_debug + l * node_elems, ws->x2_debug + l * node_elems, stream));
-    // ConvNext MLP (convnext.py:26-32): z = y W1^T + b1, a = gelu(z) (same epilogue), m = a W2^T + b2, all kept; h += ls * m
+    // ConvNext MLP (convnext.py:26-32): z = y W1^T + b1, a = gelu(z) (same epilogue), m = a W2^T + b2, all kept;
+    // h_out = h_in + ls * m in the second product's epilogue
     GemmOpt oz;
     oz.gelu_out = al;
     TRY((gemm<true, true>(g, yl, kC, P + lay->lin1_w + (size_t)l * kW * kC, kC, zl, kW, (int)Rn, kW, kC, 1.f,
                           P + lay->lin1_b + l * kW, false, oz)));
+    GemmOpt om;
+    om.gelu_out = h_out;
+    om.res_in = h_in;
+    om.res_scale = P + lay->layer_scale + l * kC;
     TRY((gemm<true, true>(g, al, kW, P + lay->lin2_w + (size_t)l * kC * kW, kW, ml, kC, (int)Rn, kC, kW, 1.f,
-                          P + lay->lin2_b + l * kC, false)));
-    residual_add_kernel<<<blocks_for(Rn * kC / 4, 256), 256, 0, s>>>(ml, P + lay->layer_scale + l * kC, Rn * kC / 4, ws->h);
-    CUDA_LAUNCH_CHECK();
-    {
-      cudaError_t e = cudaMemcpyAsync(ws->h_debug + (size_t)(l + 1) * node_elems, ws->h, node_elems * sizeof(float),
-                                      cudaMemcpyDeviceToDevice, s);
-      if (e != cudaSuccess) return (int)e;
-    }
-    TRY(arreau_readout_accumulate(ws->h, w->wr_t + (size_t)l * kC * (Z + 4), w->br + l * (Z + 4), w->ori, N, Z, l == 0,
+                          P + lay->lin2_b + l * kC, false, om)));
+    TRY(arreau_readout_accumulate(h_out, w->wr_t + (size_t)l * kC * (Z + 4), w->br + l * (Z + 4), w->ori, N, Z, l == 0,
                                   ws->acc, stream));
   }
   TRY(arreau_readout_finalize(ws->acc, atom_offset, N, G, Z, kL, logits, score, len0, stream));
