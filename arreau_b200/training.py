@@ -196,7 +196,8 @@ class TrainEngine:
         self.types0.copy_(torch.as_tensor(types0).reshape(e.N), non_blocking=True)
         self.lattice0.copy_(torch.as_tensor(lattice0).reshape(e.G, 3, 3), non_blocking=True)
         self.t_crystal.copy_(torch.as_tensor(timestep).reshape(e.G).to(torch.int32), non_blocking=True)
-        self.t_atom.copy_(torch.repeat_interleave(self.t_crystal, e.num_atoms.to(self.device)))
+        # one gather through the engine's atom -> crystal map (repeat_interleave would upload the counts and synchronise)
+        torch.index_select(self.t_crystal, 0, e.crystal_of_atom[: e.N], out=self.t_atom)
         self.eps_x.copy_(torch.as_tensor(eps_x).reshape(e.N, 3), non_blocking=True)
         self.u.copy_(torch.as_tensor(u).reshape(e.N, e.Z), non_blocking=True)
         self.eps_l.copy_(torch.as_tensor(eps_l).reshape(e.G, 3), non_blocking=True)
