@@ -34,7 +34,9 @@ def _engine(device, weights_npz, num_atoms, sd=None, backward_precision="fp32"):
 
 @pytest.mark.parametrize("tf32", [0, 1])
 @pytest.mark.parametrize("M,N,K,ak,bk,acc", [(300, 128, 96, 1, 1, 0), (128, 256, 20000, 0, 0, 0), (1000, 512, 128, 1, 0, 1),
-                                             (128, 16, 256, 0, 0, 0), (77, 128, 94, 1, 0, 1), (512, 128, 5000, 0, 0, 1)])
+                                             (128, 16, 256, 0, 0, 0), (77, 128, 94, 1, 0, 1), (512, 128, 5000, 0, 0, 1),
+                                             (640, 256, 50000, 0, 0, 0), (4000, 640, 256, 1, 1, 0), (2100, 256, 640, 1, 0, 0),
+                                             (96, 64, 1000, 0, 1, 0)])
 def test_sgemm_against_torch(device, M, N, K, ak, bk, acc, tf32):
     """The generic GEMM of the backward pass (fp32 FFMA, and its TF32 tensor-core variant: operands rounded to 10
     mantissa bits -> 2e-3 of max|ref|) against a torch fp64 matmul of the same operands."""
@@ -60,6 +62,23 @@ def test_sgemm_against_torch(device, M, N, K, ak, bk, acc, tf32):
               torch.cuda.current_stream().cuda_stream)
     tol = 2e-3 if tf32 else 2e-6 * max(1.0, np.sqrt(K) / 16)
     assert rel_err(Cm.cpu().numpy(), ref.cpu().numpy()) < tol
+
+
+def test_sgemm_tma_operands_round_to_nearest(device):
+    """The TMA-fed TF32 GEMM reads its operands through TFLOAT32 tensor maps: the TMA engine must ROUND fp32 to TF32
+    (1 + 0.75 * 2^-10 -> 1 + 2^-10), not truncate (-> 1), in all four operand orders -- truncation would bias every
+    product of the chain by ~1e-3 in the same direction."""
+    from arreau_b200 import _lib
+    M, N, K = 128, 128, 64
+    partial = torch.empty(1 << 20, device=device)
+    for ak in (1, 0):
+        for bk in (1, 0):
+            A = torch.full((M, K) if ak else (K, M), 1.0 + 0.75 * 2.0 ** -10, device=device)
+            B = torch.ones((N, K) if bk else (K, N), device=device)
+            Cm = torch.zeros(M, N, device=device)
+            _lib.call("arreau_sgemm", ak | 2, bk, A.data_ptr(), A.stride(0), B.data_ptr(), B.stride(0), Cm.data_ptr(), N, M, N, K,
+                      C.c_float(1.0), None, 0, partial.data_ptr(), partial.numel(), torch.cuda.current_stream().cuda_stream)
+            assert torch.all(Cm == K * (1.0 + 2.0 ** -10)), (ak, bk, float(Cm[0, 0]) / K)
 
 
 @pytest.mark.parametrize("case", [0, 1])
