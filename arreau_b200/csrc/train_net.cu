@@ -1770,8 +1770,9 @@ extern "C" int arreau_ponita_backward(const float* params, const arreau_train_la
 
 // Training forward with every dense contraction on the generic GEMM (tcgen05 kind::tf32 under ARREAU_PRECISION_TF32) and
 // its activations KEPT for arreau_ponita_backward(forward_kept = 1): the edge chain (mono, z1, a1, z2, kb) and the
-// ConvNext hidden pre-activations of every layer stay in `workspace`, h / x1 / x2 of every layer and the per-layer
-// spatial kernels in `ws` as after arreau_ponita_forward with the debug buffers set.  Same mathematics as
+// LayerNorm output, hidden pre-activation, hidden activation and MLP output of every ConvNext block stay in `workspace`,
+// h / x1 / x2 of every layer (h written straight into its kept slab) and the per-layer spatial kernels in `ws` as after
+// arreau_ponita_forward with the debug buffers set.  Same mathematics as
 // arreau_ponita_forward (ponita/models/ponita.py:88-123); the message pass, fiber conv + LayerNorm, embedding and
 // read-outs are the fp32 kernels of that function.
 extern "C" int arreau_ponita_forward_train(const float* params, const arreau_train_layout_t* lay, const arreau_weights* w,

@@ -480,7 +480,8 @@ int64_t arreau_ponita_backward_workspace_bytes(int32_t num_atoms_total, int64_t 
  * index of each PolynomialFeatures(3) column.  Deterministic: split reductions with a fixed-order second stage and a
  * sender-side gather for the transposed message pass, no atomics.  precision: ARREAU_PRECISION_FP32 (FFMA GEMMs,
  * the parity path) or ARREAU_PRECISION_TF32 (every GEMM of the backward on tcgen05 kind::tf32 tensor cores with fp32
- * accumulation in TMEM: operands rounded to 10 mantissa bits, gradients within ~1e-3 of the fp32 path).
+ * accumulation in TMEM, operands fetched through TFLOAT32 tensor maps -- the TMA engine rounds them to 10 mantissa bits --
+ * gradients within ~1e-3 of the fp32 path).
  * forward_kept: 0 after arreau_ponita_forward (the edge chain and the ConvNext hidden layers are recomputed here),
  * 1 after arreau_ponita_forward_train on the same `workspace` (they are read from it). */
 int arreau_ponita_backward(const float* params, const arreau_train_layout_t* layout, const arreau_weights* w,
@@ -496,7 +497,8 @@ int arreau_ponita_backward(const float* params, const arreau_train_layout_t* lay
  * ConvNext MLP of every layer) and its activations KEPT in `workspace` (same layout and size as
  * arreau_ponita_backward's), so that arreau_ponita_backward(..., forward_kept = 1) does not recompute them.  Message
  * pass, fiber conv + LayerNorm, embedding and read-outs are the fp32 kernels of arreau_ponita_forward; ws must carry the
- * debug buffers (h / x1 / x2 of every layer) and fp32 `kernels`.  Mathematics: ponita/models/ponita.py:88-123. */
+ * debug buffers (h / x1 / x2 of every layer) and fp32 `kernels`.  The node features of layer l are written straight into
+ * slab l of ws->h_debug (ws->h itself is not touched).  Mathematics: ponita/models/ponita.py:88-123. */
 int arreau_ponita_forward_train(const float* params, const arreau_train_layout_t* layout, const arreau_weights* w,
                                 const arreau_workspace* ws, const int32_t* fold_table, const float* x, const float* vec,
                                 const int32_t* row_ptr, const int32_t* src, const double* dist, const double* dir,
