@@ -58,6 +58,7 @@ struct GemmArgs {
   const float* res_in; const float* res_scale;   // C2 = res_in[m][n] + res_scale[n] * v (pitch ldc) instead of the GELU
   int mn_lbo, mn_sbo;
   int splits;                 // K splits (the persistent kernel's grid is not the tile grid)
+  float* colsum_part;         // persistent kernel: per-CTA column sums of C, [grid / ntn * 4][N] (see GemmOpt::colsum_out), or null
   long long* prof;            // debug: per-CTA phase clocks of the persistent kernel ([grid][16]), or null
 };
 
@@ -96,11 +97,11 @@ __device__ __forceinline__ float gelu_grad_t(float x) {
 
 // the four accumulators (m, n .. n + 3) of a tile on their way out (n % 4 == 0, n < N)
 template <bool FAST = false>
-__device__ __forceinline__ void gemm_store4(const GemmArgs& g, bool split, int z, int m, int n, float4 v,
-                                            const float4* gz_loaded = nullptr) {
+__device__ __forceinline__ float4 gemm_store4(const GemmArgs& g, bool split, int z, int m, int n, float4 v,
+                                              const float4* gz_loaded = nullptr) {
   if (split) {
     *reinterpret_cast<float4*>(g.partial + ((size_t)z * g.M + m) * g.N + n) = v;
-    return;
+    return v;
   }
   float4 bb = make_float4(0.f, 0.f, 0.f, 0.f);
   if (g.bias) bb = *reinterpret_cast<const float4*>(g.bias + n);
@@ -123,6 +124,7 @@ __device__ __forceinline__ void gemm_store4(const GemmArgs& g, bool split, int z
   } else if (g.C2)
     *reinterpret_cast<float4*>(g.C2 + off) = make_float4(gelu_fwd_t<FAST>(v.x) * rs, gelu_fwd_t<FAST>(v.y) * rs,
                                                          gelu_fwd_t<FAST>(v.z) * rs, gelu_fwd_t<FAST>(v.w) * rs);
+  return v;      // what went to C
 }
 
 template <bool KCONTIG>
@@ -646,6 +648,9 @@ sgemm_tma_kernel(const __grid_constant__ GemmArgs g, const __grid_constant__ CUt
     float* const st = staging + ew * 32 * wsg::kStagePitch;
     const bool split = g.splits > 1;
     uint32_t tile = 0;
+    // fused column sums of C (bias gradients): this warp's rows of every tile of the CTA, four columns per lane (the host
+    // launches this mode only when every item of a CTA has the same n tile: gridDim.x % ntn == 0)
+    float4 cs = make_float4(0.f, 0.f, 0.f, 0.f);
     for (int item = blockIdx.x; item < items; item += gridDim.x) {
       const WsItem w = ws_item(g, item, ntn, ntm);
       const uint32_t buf = tile & 1;
@@ -691,13 +696,28 @@ sgemm_tma_kernel(const __grid_constant__ GemmArgs g, const __grid_constant__ CUt
         for (int it = 0; it < 8; ++it) {
           const int row = it * 4 + (lane >> 3);
           const int m = w.m0 + q * 32 + row;
-          if (m < g.M && n < g.N)
-            gemm_store4<true>(g, split, w.z, m, n, *reinterpret_cast<const float4*>(st + row * wsg::kStagePitch + (lane & 7) * 4),
-                              &gzv[it]);
+          if (m < g.M && n < g.N) {
+            const float4 v = gemm_store4<true>(g, split, w.z, m, n,
+                                               *reinterpret_cast<const float4*>(st + row * wsg::kStagePitch + (lane & 7) * 4), &gzv[it]);
+            cs.x += v.x; cs.y += v.y; cs.z += v.z; cs.w += v.w;
+          }
         }
         __syncwarp();
       }
       if (w.nslabs > 0) ++tile;
+    }
+    if (g.colsum_part) {
+      // the four row groups of a lane's columns (lanes l, l + 8, l + 16, l + 24), in a fixed order
+#pragma unroll
+      for (int off = 8; off < 32; off <<= 1) {
+        cs.x += __shfl_xor_sync(0xffffffffu, cs.x, off);
+        cs.y += __shfl_xor_sync(0xffffffffu, cs.y, off);
+        cs.z += __shfl_xor_sync(0xffffffffu, cs.z, off);
+        cs.w += __shfl_xor_sync(0xffffffffu, cs.w, off);
+      }
+      const int n = (int)(blockIdx.x % ntn) * kBN + cq * 32 + lane * 4;
+      if (lane < 8 && n < g.N)
+        *reinterpret_cast<float4*>(g.colsum_part + ((size_t)(blockIdx.x / ntn) * 4 + q) * g.N + n) = cs;
     }
     WS_PROF(1)
     if (g.prof && ew == 0 && lane == 0) {
@@ -830,7 +850,11 @@ struct GemmOpt {
   const float* rowscale = nullptr;      // per 16 rows of C (the cutoff window of an edge)
   const float* res_in = nullptr;        // with res_scale and gelu_out: gelu_out = res_in + res_scale[n] * C (residual update)
   const float* res_scale = nullptr;
+  float* colsum_out = nullptr;          // out[n] = sum_m C[m][n] (a bias gradient) from the epilogue's own values when the
+                                        // TMA kernel runs unsplit with one n tile per CTA; a separate column-sum pass otherwise
 };
+
+int colsum(const Gemm& g, const float* X, const float* Y, long long rows, int ncols, long long ld, float* out, bool accumulate);
 
 // op: C[M,N] (=|+=) alpha A B (+bias), epilogue options in `o`.  Returns ARREAU_* / cudaError.
 template <bool AK, bool BK>
@@ -838,7 +862,7 @@ int gemm(const Gemm& g, const float* A, long long lda, const float* B, long long
          int N, long long K, float alpha, const float* bias, bool accumulate, const GemmOpt& o = GemmOpt()) {
   if (M <= 0 || N <= 0) return ARREAU_OK;
   const int tiles = ((M + kBM - 1) / kBM) * ((N + kBN - 1) / kBN);
-  const bool plain_out = !bias && !o.gelu_out && !o.gz && o.c_cblk == 128;   // what the split second stage can finish
+  const bool plain_out = !bias && !o.gelu_out && !o.gz && o.c_cblk == 128 && !o.colsum_out;   // what the split second stage can finish
   // tensor maps of the operands for the TMA-fed persistent kernel; an operand it cannot describe -> one tile per CTA
   alignas(64) CUtensorMap map_a, map_b;
   const bool use_tma = g.tf32 && !g_tc_one_tile && make_operand_map<AK>(&map_a, A, lda, o.a_cblk, M, K) &&
@@ -867,8 +891,13 @@ int gemm(const Gemm& g, const float* A, long long lda, const float* B, long long
   splits = (int)((K + kps - 1) / kps);
   if (splits < 1) splits = 1;
   dim3 grid((N + kBN - 1) / kBN, (M + kBM - 1) / kBM, splits);
+  const int ntn = (N + kBN - 1) / kBN;
+  const int ws_grid = (long long)tiles * splits < g.sms ? tiles * splits : g.sms;
+  const bool fuse_colsum = o.colsum_out && use_tma && splits == 1 && ws_grid % ntn == 0 && o.c_cblk == 128 &&
+                           (size_t)(ws_grid / ntn) * 4 * N <= g.partial_floats;
   GemmArgs a{A, lda, o.a_cblk, B, ldb, o.b_cblk, C, ldc, o.c_cblk, M, N, K, kps, alpha, bias, accumulate ? 1 : 0,
-             g.partial, o.gelu_out, o.gz, o.gz_ld, o.rowscale, o.res_in, o.res_scale, g_tc_mn_lbo, g_tc_mn_sbo, splits, g_ws_prof};
+             g.partial, o.gelu_out, o.gz, o.gz_ld, o.rowscale, o.res_in, o.res_scale, g_tc_mn_lbo, g_tc_mn_sbo, splits,
+             fuse_colsum ? g.partial : nullptr, g_ws_prof};
   if (use_tma) {
     static bool attr_set = false;       // one flag per template instance
     if (!attr_set) {
@@ -876,8 +905,7 @@ int gemm(const Gemm& g, const float* A, long long lda, const float* B, long long
       if (e != cudaSuccess) return (int)e;
       attr_set = true;
     }
-    const long long items = (long long)tiles * splits;
-    sgemm_tma_kernel<AK, BK><<<(unsigned)(items < g.sms ? items : g.sms), wsg::kThreads, wsg::kSmemBytes, g.s>>>(a, map_a, map_b);
+    sgemm_tma_kernel<AK, BK><<<(unsigned)ws_grid, wsg::kThreads, wsg::kSmemBytes, g.s>>>(a, map_a, map_b);
   } else if (g.tf32) {
     static bool attr_set = false;       // one flag per template instance
     if (!attr_set) {
@@ -894,6 +922,12 @@ int gemm(const Gemm& g, const float* A, long long lda, const float* B, long long
     const long long n = (long long)M * N;
     reduce_partials(g.s, g.partial, splits, n, ldc, N, alpha, accumulate ? 1 : 0, C);
     CUDA_LAUNCH_CHECK();
+  }
+  if (fuse_colsum) {
+    reduce_partials(g.s, g.partial, ws_grid / ntn * 4, N, N, N, 1.0f, 0, o.colsum_out);
+    CUDA_LAUNCH_CHECK();
+  } else if (o.colsum_out) {
+    return colsum(g, C, nullptr, M, N, ldc, o.colsum_out, false);
   }
   return ARREAU_OK;
 }
@@ -989,6 +1023,40 @@ __global__ void scale_cols_kernel(const float* __restrict__ x, const float* __re
   const float4 v = *reinterpret_cast<const float4*>(x + i);
   const float4 s = *reinterpret_cast<const float4*>(colscale + (i & (kC - 1)));
   *reinterpret_cast<float4*>(out + i) = make_float4(v.x * s.x, v.y * s.y, v.z * s.z, v.w * s.w);
+}
+
+// Backward of the residual update h_out = h_in + ls * m (convnext.py:31-32) in one pass over dh and m:
+//   dm = dh * ls (written), partial[block] = [ sum_r dh * m  (d layer_scale) | sum_r dm  (d lin2 bias) ]
+// block = 256 threads = 8 row lanes x 32 float4 columns, blockIdx.x = row split; fixed-order combination (deterministic).
+__global__ void __launch_bounds__(256)
+ls_bwd_kernel(const float* __restrict__ dh, const float* __restrict__ m, const float* __restrict__ ls, long long rows,
+              float* __restrict__ dm, float* __restrict__ partial) {
+  __shared__ float4 red[2][256];
+  const int c4 = threadIdx.x & 31, rl = threadIdx.x >> 5;
+  const long long per = (rows + gridDim.x - 1) / gridDim.x;
+  const long long r0 = (long long)blockIdx.x * per, r1 = (r0 + per < rows) ? r0 + per : rows;
+  const float4 sc = reinterpret_cast<const float4*>(ls)[c4];
+  float4 s1 = make_float4(0.f, 0.f, 0.f, 0.f), s2 = s1;
+#pragma unroll 4
+  for (long long r = r0 + rl; r < r1; r += 8) {
+    const float4 g = __ldg(reinterpret_cast<const float4*>(dh + r * kC) + c4);
+    const float4 mv = __ldg(reinterpret_cast<const float4*>(m + r * kC) + c4);
+    const float4 d = make_float4(g.x * sc.x, g.y * sc.y, g.z * sc.z, g.w * sc.w);
+    reinterpret_cast<float4*>(dm + r * kC)[c4] = d;
+    s1.x = fmaf(g.x, mv.x, s1.x); s1.y = fmaf(g.y, mv.y, s1.y); s1.z = fmaf(g.z, mv.z, s1.z); s1.w = fmaf(g.w, mv.w, s1.w);
+    s2.x += d.x; s2.y += d.y; s2.z += d.z; s2.w += d.w;
+  }
+  red[0][threadIdx.x] = s1;
+  red[1][threadIdx.x] = s2;
+  __syncthreads();
+  if (rl < 2) {                              // row lane 0 finishes the first sum, row lane 1 the second
+    float4 a = red[rl][c4];
+    for (int k = 1; k < 8; ++k) {
+      const float4 v = red[rl][k * 32 + c4];
+      a.x += v.x; a.y += v.y; a.z += v.z; a.w += v.w;
+    }
+    reinterpret_cast<float4*>(partial + (size_t)blockIdx.x * 2 * kC + rl * kC)[c4] = a;
+  }
 }
 
 __global__ void fill_kernel(float* __restrict__ p, long long n, float v) {
@@ -1381,7 +1449,7 @@ struct BwdBuffers {
   float *dh, *dr, *y, *z, *a, *m, *dm, *da, *dy, *dx2, *dx1, *xl;
   // fiber chain (256 rows)
   float *frow, *fz1, *fa1, *fz2, *fkb, *dfk, *dfkb, *fda1, *fw16, *fdw16;
-  float *w1m, *dw1m, *partial, *small;   // small: [128 x 512] scratch for narrow outputs
+  float *w1m, *dw1m, *partial, *small;   // small: [128 x 640] scratch for narrow outputs
   // kept by arreau_ponita_forward_train, one slab per layer: LayerNorm output y [Rn][C], ConvNext hidden pre-activation
   // z [Rn][W], its GELU a [Rn][W], the MLP output m [Rn][C]
   float *ys, *zs, *as, *ms;
@@ -1404,7 +1472,7 @@ BwdBuffers carve(float* base, long long N, long long Ecap, int xl_pitch) {
   b.fw16 = c.take(kC * 16); b.fdw16 = c.take(kC * 16);
   b.w1m = c.take(kC * 128); b.dw1m = c.take(kC * 128);
   b.partial = c.take(kPartialFloats);
-  b.small = c.take((size_t)128 * 512);
+  b.small = c.take((size_t)128 * kL * kC);
   b.ys = c.take((size_t)kL * Rn * kC); b.zs = c.take((size_t)kL * Rn * kW); b.as = c.take((size_t)kL * Rn * kW);
   b.ms = c.take((size_t)kL * Rn * kC);
   b.total = c.used;
@@ -1615,7 +1683,6 @@ extern "C" int arreau_ponita_backward(const float* params, const arreau_train_la
 
   // ---- 2. layers, last to first -------------------------------------------------------------------------
   for (int l = kL - 1; l >= 0; --l) {
-    const float* h_out = ws->h_debug + (size_t)(l + 1) * node_elems;
     const float* h_in = ws->h_debug + (size_t)l * node_elems;
     const float* x1 = ws->x1_debug + (size_t)l * node_elems;
     const float* x2 = ws->x2_debug + (size_t)l * node_elems;
@@ -1625,14 +1692,7 @@ extern "C" int arreau_ponita_backward(const float* params, const arreau_train_la
     const float* W2 = P + lay->lin2_w + (size_t)l * kC * kW;
     const float* Wf = P + lay->conv_fiber_w + (size_t)l * kC * kD;
     const float* ls = P + lay->layer_scale + l * kC;
-    // read-out l: r = h_out Wr^T + br   (ponita.py:105)
-    //   dWr[R,C] = dr^T h_out   (dr is 128 wide, only the first R rows of the product are parameters)
-    TRY((gemm<false, false>(g, b.dr, 128, h_out, kC, b.small, kC, 128, kC, Rn, 1.f, nullptr, false)));
-    {
-      cudaError_t e = cudaMemcpyAsync(Gd + lay->readout_w + (size_t)l * R * kC, b.small, sizeof(float) * R * kC,
-                                      cudaMemcpyDeviceToDevice, s);
-      if (e != cudaSuccess) return (int)e;
-    }
+    // read-out l: r = h_out Wr^T + br   (ponita.py:105); dWr of all layers after the loop
     //   dh += dr Wr      (K = R rows of Wr; dr columns beyond R are zero, so K = R rounded down to the stored rows)
     TRY((gemm<true, false>(g, b.dr, 128, Wr, kC, b.dh, kC, (int)Rn, kC, R, 1.f, nullptr, true)));
     // ConvNext MLP (convnext.py:25-32): y = LN(x2), z = y W1^T + b1, a = gelu(z), m = a W2^T + b2 -- kept per layer by
@@ -1651,18 +1711,23 @@ extern "C" int arreau_ponita_backward(const float* params, const arreau_train_la
       yl = b.y; zl = b.z; al = b.a; ml = b.m;
     }
     // h_out = h_in + ls * m
-    TRY(colsum(g, b.dh, ml, Rn, kC, kC, Gd + lay->layer_scale + l * kC, false));
-    scale_cols_kernel<<<blocks_for(Rn * kC / 4, 256), 256, 0, s>>>(b.dh, ls, Rn * kC, b.dm);
-    CUDA_LAUNCH_CHECK();
-    TRY(colsum(g, b.dm, nullptr, Rn, kC, kC, Gd + lay->lin2_b + l * kC, false));
+    {   // dm = dh * ls, d layer_scale = column sums of dh * m, d lin2 bias = column sums of dm: one pass
+      long long sp = (Rn + 63) / 64;
+      if (sp > kColSplits) sp = kColSplits;
+      ls_bwd_kernel<<<(unsigned)sp, 256, 0, s>>>(b.dh, ml, ls, Rn, b.dm, b.partial);
+      CUDA_LAUNCH_CHECK();
+      // rows of the second stage's output: [d layer_scale | d lin2 bias] of this layer, lin2_b - layer_scale floats apart
+      reduce_partials(s, b.partial, (int)sp, 2 * kC, lay->lin2_b - lay->layer_scale, kC, 1.0f, 0, Gd + lay->layer_scale + l * kC);
+      CUDA_LAUNCH_CHECK();
+    }
     TRY((gemm<false, false>(g, b.dm, kC, al, kW, Gd + lay->lin2_w + (size_t)l * kC * kW, kW, kC, kW, Rn, 1.f, nullptr, false)));
     {   // dz = (dm W2) * gelu'(z) in the product's epilogue
       GemmOpt od;
       od.gz = zl;
       od.gz_ld = kW;
+      od.colsum_out = Gd + lay->lin1_b + l * kW;          // db1 = column sums of dz, from the same epilogue
       TRY((gemm<true, false>(g, b.dm, kC, W2, kW, b.da, kW, (int)Rn, kW, kC, 1.f, nullptr, false, od)));
     }
-    TRY(colsum(g, b.da, nullptr, Rn, kW, kW, Gd + lay->lin1_b + l * kW, false));
     TRY((gemm<false, false>(g, b.da, kW, yl, kC, Gd + lay->lin1_w + (size_t)l * kW * kC, kC, kW, kC, Rn, 1.f, nullptr, false)));
     TRY((gemm<true, false>(g, b.da, kW, W1, kC, b.dy, kC, (int)Rn, kC, kW, 1.f, nullptr, false)));
     // LayerNorm backward + conv bias gradient
@@ -1698,6 +1763,18 @@ extern "C" int arreau_ponita_backward(const float* params, const arreau_train_la
       CUDA_LAUNCH_CHECK();
       message_bwd_dh_kernel<<<N, 256, 0, s>>>(kern, b.dx1, row_ptr, src, dst, atom_offset, crystal_of_atom, Ecap, b.dh);
       CUDA_LAUNCH_CHECK();
+    }
+  }
+  // read-out weights: dWr_l[R,C] = dr^T h_l for the five layers as ONE product over the kept feature slabs (block-strided
+  // operand [Rn][L*C]); dr is 128 wide, only the first R rows of each 128-column block are parameters
+  {
+    GemmOpt orw;
+    orw.b_cblk = (long long)node_elems;
+    TRY((gemm<false, false>(g, b.dr, 128, ws->h_debug + node_elems, kC, b.small, kL * kC, 128, kL * kC, Rn, 1.f, nullptr, false, orw)));
+    for (int l = 0; l < kL; ++l) {
+      cudaError_t e = cudaMemcpy2DAsync(Gd + lay->readout_w + (size_t)l * R * kC, sizeof(float) * kC, b.small + l * kC,
+                                        sizeof(float) * kL * kC, sizeof(float) * kC, R, cudaMemcpyDeviceToDevice, s);
+      if (e != cudaSuccess) return (int)e;
     }
   }
   // read-out bias: the same dr for every layer -> one column sum, copied to the five slots
@@ -1739,8 +1816,8 @@ extern "C" int arreau_ponita_backward(const float* params, const arreau_train_la
     ok.gz = b.z2;
     ok.gz_ld = kD;
     ok.rowscale = b.win;
+    ok.colsum_out = Gd + lay->basis_b2;                   // db2 = column sums of dz2, from the same epilogue
     TRY((gemm<true, false>(g, b.dkern, kC, P + lay->conv_kernel_w, kD, b.dkb, kD, (int)Re, kD, kL * kC, 1.f, nullptr, false, ok)));
-    TRY(colsum(g, b.dkb, nullptr, Re, kD, kD, Gd + lay->basis_b2, false));
     TRY((gemm<false, false>(g, b.dkb, kD, b.a1, kC, Gd + lay->basis_w2, kC, kD, kC, Re, 1.f, nullptr, false)));
     //   dz1 = (dz2 W2) * gelu'(z1)                   (b.da1 = dz1)
     GemmOpt o1;
