@@ -250,23 +250,36 @@ fiber_kernel_kernel(const float* __restrict__ ori, const float* __restrict__ w1,
     for (int off = 16; off > 0; off >>= 1) s += __shfl_xor_sync(0xffffffffu, s, off);
     return s;
   };
-  for (int d = warp; d < kD; d += kD / 32) {
-    const float* w = w2 + (size_t)d * kC;
-    double s = 0.0;
+  // four outputs per pass: their weight rows are loaded together (one memory round trip per pass, not per output)
+  for (int d0 = warp * 4; d0 < kD; d0 += kD / 8) {
+    double s[4] = {0.0, 0.0, 0.0, 0.0};
 #pragma unroll
-    for (int c = lane; c < kC; c += 32) s += (double)w[c] * h1[c];
-    s = warp_sum(s);
-    if (lane == 0) fkb[d] = gelu_erf_d(s + (double)b2[d]);
+    for (int u = 0; u < 4; ++u) {
+      const float* w = w2 + (size_t)(d0 + u) * kC;
+#pragma unroll
+      for (int c = lane; c < kC; c += 32) s[u] += (double)w[c] * h1[c];
+    }
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      const double t4 = warp_sum(s[u]);
+      if (lane == 0) fkb[d0 + u] = gelu_erf_d(t4 + (double)b2[d0 + u]);
+    }
   }
   __syncthreads();
-  for (int idx = warp; idx < kL * kC; idx += kD / 32) {
-    const int l = idx / kC, c = idx % kC;
-    const float* w = wf + ((size_t)l * kC + c) * kD;
-    double s = 0.0;
+  for (int i0 = warp * 4; i0 < kL * kC; i0 += kD / 8) {
+    double s[4] = {0.0, 0.0, 0.0, 0.0};
 #pragma unroll
-    for (int d = lane; d < kD; d += 32) s += (double)w[d] * fkb[d];
-    s = warp_sum(s);
-    if (lane == 0) fk[(((size_t)l * kO + o) * kO + p) * kC + c] = (float)s;
+    for (int u = 0; u < 4; ++u) {
+      const float* w = wf + (size_t)(i0 + u) * kD;         // row (l, c) = i0 + u of wf[L][C][D]
+#pragma unroll
+      for (int d = lane; d < kD; d += 32) s[u] += (double)w[d] * fkb[d];
+    }
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      const double t4 = warp_sum(s[u]);
+      const int l = (i0 + u) / kC, c = (i0 + u) % kC;
+      if (lane == 0) fk[(((size_t)l * kO + o) * kO + p) * kC + c] = (float)t4;
+    }
   }
 }
 

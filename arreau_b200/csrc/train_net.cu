@@ -1015,16 +1015,6 @@ __global__ void gelu_bwd_kernel(const float* __restrict__ z, const float* da, lo
                                                    d.z * gelu_grad(v.z) * sc, d.w * gelu_grad(v.w) * sc);
 }
 
-// out[r][c] = x[r][c] * colscale[c]     (ncols == kC)
-__global__ void scale_cols_kernel(const float* __restrict__ x, const float* __restrict__ colscale, long long n,
-                                  float* __restrict__ out) {
-  const long long i = ((long long)blockIdx.x * blockDim.x + threadIdx.x) * 4;
-  if (i >= n) return;
-  const float4 v = *reinterpret_cast<const float4*>(x + i);
-  const float4 s = *reinterpret_cast<const float4*>(colscale + (i & (kC - 1)));
-  *reinterpret_cast<float4*>(out + i) = make_float4(v.x * s.x, v.y * s.y, v.z * s.z, v.w * s.w);
-}
-
 // Backward of the residual update h_out = h_in + ls * m (convnext.py:31-32) in one pass over dh and m:
 //   dm = dh * ls (written), partial[block] = [ sum_r dh * m  (d layer_scale) | sum_r dm  (d lin2 bias) ]
 // block = 256 threads = 8 row lanes x 32 float4 columns, blockIdx.x = row split; fixed-order combination (deterministic).
@@ -1215,41 +1205,37 @@ fiber_bwd_dfk_kernel(const float* __restrict__ x1, const float* __restrict__ dx2
 }
 
 // ---- message pass backward (conv.py:131-133 + PyG add aggregation) -------------------------------------------
-// dkern[e,o,c] = dx1[dst_e,o,c] * h[src_e,o,c]
-__global__ void __launch_bounds__(256)
-message_bwd_dkern_kernel(const float* __restrict__ dx1, const float* __restrict__ h, const int32_t* __restrict__ src,
-                         const int32_t* __restrict__ dst, const int32_t* __restrict__ num_edges_ptr,
-                         long long edge_capacity, float* __restrict__ dkern) {
-  const long long i = ((long long)blockIdx.x * blockDim.x + threadIdx.x) * 4;
-  long long E = *num_edges_ptr;
-  if (E > edge_capacity) E = edge_capacity;
-  if (i >= edge_capacity * kO * kC) return;
-  const long long e = i / (kO * kC);
-  const int oc = (int)(i % (kO * kC));
-  float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
-  if (e < E) {
-    const float4 a = *reinterpret_cast<const float4*>(dx1 + (size_t)dst[e] * kO * kC + oc);
-    const float4 b = *reinterpret_cast<const float4*>(h + (size_t)src[e] * kO * kC + oc);
-    v = make_float4(a.x * b.x, a.y * b.y, a.z * b.z, a.w * b.w);
-  }
-  *reinterpret_cast<float4*>(dkern + i) = v;
-}
-
 // dh[j,o,c] += sum_{e: src_e = j} kern[e,o,c] * dx1[dst_e,o,c]   (edges of j's crystal scanned in edge order:
-// deterministic, no atomics).  One block per sender atom; thread owns 8 of the 2048 (o,c) entries.
+// deterministic, no atomics) and, in the same pass over j's outgoing edges, their rows of the kernel gradient
+// dkern[e,o,c] = dx1[dst_e,o,c] * h[j,o,c] (every edge has exactly one sender, so every row is written exactly once and
+// dx1[dst_e] is fetched once for both).  One block per sender atom; a thread owns 8 of the 2048 (o,c) entries.  The blocks
+// beyond the atoms zero the rows of the unused edge capacity (the weight-gradient product reduces over all of it).
+constexpr int kDkernTailBlocks = 32;
 __global__ void __launch_bounds__(256)
-message_bwd_dh_kernel(const float* __restrict__ kern, const float* __restrict__ dx1, const int32_t* __restrict__ row_ptr,
-                      const int32_t* __restrict__ src, const int32_t* __restrict__ dst,
-                      const int32_t* __restrict__ atom_offset, const int32_t* __restrict__ crystal_of_atom,
-                      long long edge_capacity, float* __restrict__ dh) {
+message_bwd_kernel(const float* __restrict__ kern, const float* __restrict__ dx1, const float* __restrict__ h,
+                   const int32_t* __restrict__ row_ptr, const int32_t* __restrict__ src, const int32_t* __restrict__ dst,
+                   const int32_t* __restrict__ atom_offset, const int32_t* __restrict__ crystal_of_atom,
+                   const int32_t* __restrict__ num_edges_ptr, long long edge_capacity, int N, float* __restrict__ dh,
+                   float* __restrict__ dkern) {
   __shared__ int s_list[256];
   __shared__ int s_wcount[8];
-  const int j = blockIdx.x, tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  if ((int)blockIdx.x >= N) {
+    long long E = *num_edges_ptr;
+    if (E > edge_capacity) E = edge_capacity;
+    const long long lo = E * (kO * kC / 4), hi = edge_capacity * (kO * kC / 4);
+    for (long long i = lo + (long long)(blockIdx.x - N) * 256 + tid; i < hi; i += (long long)kDkernTailBlocks * 256)
+      reinterpret_cast<float4*>(dkern)[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+    return;
+  }
+  const int j = blockIdx.x;
   const int g = crystal_of_atom[j];
   long long e_lo = row_ptr[atom_offset[g]], e_hi = row_ptr[atom_offset[g + 1]];
   if (e_hi > edge_capacity) e_hi = edge_capacity;
   float4 acc0 = make_float4(0.f, 0.f, 0.f, 0.f), acc1 = acc0;
   const int i0 = tid * 4, i1 = 1024 + tid * 4;
+  const float4 h0 = *reinterpret_cast<const float4*>(h + (size_t)j * kO * kC + i0);
+  const float4 h1 = *reinterpret_cast<const float4*>(h + (size_t)j * kO * kC + i1);
   for (long long base = e_lo; base < e_hi; base += 256) {
     const long long e = base + tid;
     const bool match = e < e_hi && src[e] == j;
@@ -1264,6 +1250,7 @@ message_bwd_dh_kernel(const float* __restrict__ kern, const float* __restrict__ 
     }
     if (match) s_list[off + __popc(bal & ((1u << lane) - 1u))] = (int)(e - base);
     __syncthreads();
+#pragma unroll 2
     for (int m = 0; m < total; ++m) {
       const long long ee = base + s_list[m];
       const size_t ko = (size_t)ee * kO * kC, xo = (size_t)dst[ee] * kO * kC;
@@ -1273,6 +1260,8 @@ message_bwd_dh_kernel(const float* __restrict__ kern, const float* __restrict__ 
       acc0.z = fmaf(k0.z, d0.z, acc0.z); acc0.w = fmaf(k0.w, d0.w, acc0.w);
       acc1.x = fmaf(k1.x, d1.x, acc1.x); acc1.y = fmaf(k1.y, d1.y, acc1.y);
       acc1.z = fmaf(k1.z, d1.z, acc1.z); acc1.w = fmaf(k1.w, d1.w, acc1.w);
+      *reinterpret_cast<float4*>(dkern + ko + i0) = make_float4(d0.x * h0.x, d0.y * h0.y, d0.z * h0.z, d0.w * h0.w);
+      *reinterpret_cast<float4*>(dkern + ko + i1) = make_float4(d1.x * h1.x, d1.y * h1.y, d1.z * h1.z, d1.w * h1.w);
     }
     __syncthreads();
   }
@@ -1758,10 +1747,8 @@ extern "C" int arreau_ponita_backward(const float* params, const arreau_train_la
     }
     // message pass backward: this layer's slab of the kernel gradient, and dh
     if (Re > 0) {
-      message_bwd_dkern_kernel<<<blocks_for(Re * kC / 4, 256), 256, 0, s>>>(b.dx1, h_in, src, dst, num_edges_ptr, Ecap,
-                                                                            b.dkern + (size_t)l * Re * kC);
-      CUDA_LAUNCH_CHECK();
-      message_bwd_dh_kernel<<<N, 256, 0, s>>>(kern, b.dx1, row_ptr, src, dst, atom_offset, crystal_of_atom, Ecap, b.dh);
+      message_bwd_kernel<<<N + kDkernTailBlocks, 256, 0, s>>>(kern, b.dx1, h_in, row_ptr, src, dst, atom_offset, crystal_of_atom,
+                                                            num_edges_ptr, Ecap, N, b.dh, b.dkern + (size_t)l * Re * kC);
       CUDA_LAUNCH_CHECK();
     }
   }
