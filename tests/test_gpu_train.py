@@ -81,6 +81,30 @@ def test_sgemm_tma_operands_round_to_nearest(device):
             assert torch.all(Cm == K * (1.0 + 2.0 ** -10)), (ak, bk, float(Cm[0, 0]) / K)
 
 
+@pytest.mark.parametrize("M,N,K,ak,bk", [(77, 132, 96, 1, 0), (300, 128, 200, 1, 1), (640, 256, 9000, 0, 0), (130, 96, 5000, 0, 1)])
+def test_sgemm_tf32_stays_in_bounds_and_is_deterministic(device, M, N, K, ak, bk):
+    """Ragged tiles of the TF32 GEMM (TMA zero fill of the operands, predicated epilogue, split second stage): nothing is
+    written outside C[M, N] inside a larger allocation (compute-sanitizer is closed on this pool), and two runs agree bit
+    for bit."""
+    from arreau_b200 import _lib
+    g = torch.Generator(device="cpu").manual_seed(7 * M + N + K)
+    A = torch.randn((M, K) if ak else (K, M), generator=g).to(device)
+    B = torch.randn((N, K) if bk else (K, N), generator=g).to(device)
+    ldc, pad = N + 4, 5
+    partial = torch.empty(4 << 20, device=device)
+    outs = []
+    for _ in range(2):
+        Cm = torch.full((M + pad, ldc), -7.25, device=device)
+        _lib.call("arreau_sgemm", ak | 2, bk, A.data_ptr(), A.stride(0), B.data_ptr(), B.stride(0), Cm.data_ptr(), ldc, M, N, K,
+                  C.c_float(1.0), None, 0, partial.data_ptr(), partial.numel(), torch.cuda.current_stream().cuda_stream)
+        torch.cuda.synchronize()
+        assert torch.all(Cm[M:] == -7.25) and torch.all(Cm[:, N:] == -7.25)
+        outs.append(Cm[:M, :N].clone())
+    assert torch.equal(outs[0], outs[1])
+    ref = (A.double() if ak else A.double().T) @ (B.double().T if bk else B.double())
+    assert rel_err(outs[0].cpu().numpy(), ref.cpu().numpy()) < 2e-3
+
+
 @pytest.mark.parametrize("case", [0, 1])
 def test_noising_matches_reference(device, gold, weights_npz, case):
     c = _case(gold("train_c5small.npz"), case)
