@@ -81,7 +81,7 @@ def test_sgemm_tma_operands_round_to_nearest(device):
             assert torch.all(Cm == K * (1.0 + 2.0 ** -10)), (ak, bk, float(Cm[0, 0]) / K)
 
 
-@pytest.mark.parametrize("M,N,K,ak,bk", [(77, 132, 96, 1, 0), (300, 128, 200, 1, 1), (640, 256, 9000, 0, 0), (130, 96, 5000, 0, 1)])
+@pytest.mark.parametrize("M,N,K,ak,bk", [(77, 132, 96, 1, 0), (300, 128, 200, 1, 1), (640, 256, 9000, 0, 0), (132, 96, 5000, 0, 1)])
 def test_sgemm_tf32_stays_in_bounds_and_is_deterministic(device, M, N, K, ak, bk):
     """Ragged tiles of the TF32 GEMM (TMA zero fill of the operands, predicated epilogue, split second stage): nothing is
     written outside C[M, N] inside a larger allocation (compute-sanitizer is closed on this pool), and two runs agree bit
