@@ -262,9 +262,11 @@ fiber_kernel_kernel(const float* __restrict__ ori, const float* __restrict__ w1,
 #pragma unroll
     for (int u = 0; u < 4; ++u) {
       const double t4 = warp_sum(s[u]);
-      if (lane == 0) fkb[d0 + u] = gelu_erf_d(t4 + (double)b2[d0 + u]);
+      if (lane == 0) fkb[d0 + u] = t4 + (double)b2[d0 + u];
     }
   }
+  __syncthreads();
+  fkb[t] = gelu_erf_d(fkb[t]);           // one fp64 erf per thread (kD threads), not 32 in a row on lane 0 of each warp
   __syncthreads();
   for (int i0 = warp * 4; i0 < kL * kC; i0 += kD / 8) {
     double s[4] = {0.0, 0.0, 0.0, 0.0};

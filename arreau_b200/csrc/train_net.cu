@@ -1152,29 +1152,34 @@ ln_bwd_kernel(const float* __restrict__ x2, const float* __restrict__ dy, const 
 }
 
 // ---- fiber conv backward (conv.py:115): x2[b,p,c] = (1/O) sum_o x1[b,o,c] fk[o,p,c] ------------------------
-// dx1[b,o,c] = (1/O) sum_p dx2[b,p,c] fk[o,p,c]; block = two atoms, thread = channel (every fiber-kernel value read from
-// L1 serves both atoms; N / 2 independent blocks instead of 2 per SM looping over their atoms)
+// dx1[b,o,c] = (1/O) sum_p dx2[b,p,c] fk[o,p,c]; block = kDx1Atoms atoms, thread = channel (every fiber-kernel value read
+// from L1 serves all of them; N / kDx1Atoms independent blocks instead of 2 per SM looping over their atoms)
+constexpr int kDx1Atoms = 4;
 __global__ void __launch_bounds__(kC)
 fiber_bwd_dx1_kernel(const float* __restrict__ dx2, const float* __restrict__ fk, int N, float* __restrict__ dx1) {
   const int c = threadIdx.x;
-  const int b0 = 2 * blockIdx.x, b1 = b0 + 1 < N ? b0 + 1 : b0;
-  float d0[kO], d1[kO];
+  const int b0 = kDx1Atoms * blockIdx.x;
+  float d[kDx1Atoms][kO];
 #pragma unroll
-  for (int p = 0; p < kO; ++p) {
-    d0[p] = dx2[((size_t)b0 * kO + p) * kC + c];
-    d1[p] = dx2[((size_t)b1 * kO + p) * kC + c];
+  for (int a = 0; a < kDx1Atoms; ++a) {
+    const int b = b0 + a < N ? b0 + a : N - 1;
+#pragma unroll
+    for (int p = 0; p < kO; ++p) d[a][p] = dx2[((size_t)b * kO + p) * kC + c];
   }
-#pragma unroll 4
+#pragma unroll 2
   for (int o = 0; o < kO; ++o) {
-    float s0 = 0.f, s1 = 0.f;
+    float s[kDx1Atoms];
+#pragma unroll
+    for (int a = 0; a < kDx1Atoms; ++a) s[a] = 0.f;
 #pragma unroll
     for (int p = 0; p < kO; ++p) {
       const float f = __ldg(fk + ((size_t)o * kO + p) * kC + c);
-      s0 = fmaf(d0[p], f, s0);
-      s1 = fmaf(d1[p], f, s1);
+#pragma unroll
+      for (int a = 0; a < kDx1Atoms; ++a) s[a] = fmaf(d[a][p], f, s[a]);
     }
-    dx1[((size_t)b0 * kO + o) * kC + c] = s0 * (1.0f / kO);
-    if (b1 != b0) dx1[((size_t)b1 * kO + o) * kC + c] = s1 * (1.0f / kO);
+#pragma unroll
+    for (int a = 0; a < kDx1Atoms; ++a)
+      if (b0 + a < N) dx1[((size_t)(b0 + a) * kO + o) * kC + c] = s[a] * (1.0f / kO);
   }
 }
 
@@ -1387,10 +1392,18 @@ moments_kernel(const float* __restrict__ x, const float* __restrict__ sub_cols, 
     partial[2 * blockIdx.x + 1] = tq;
   }
 }
+// one warp: lane l adds the blocks l, l + 32, ... in order, then a fixed shuffle tree (deterministic; one thread walking all
+// the partials was a 16 us chain of dependent loads once per training step)
 __global__ void moments_finish_kernel(const double* __restrict__ partial, int blocks, double* __restrict__ out) {
-  if (threadIdx.x == 0 && blockIdx.x == 0) {
-    double s = 0.0, q = 0.0;
-    for (int k = 0; k < blocks; ++k) { s += partial[2 * k]; q += partial[2 * k + 1]; }
+  if (blockIdx.x != 0 || threadIdx.x >= 32) return;
+  double s = 0.0, q = 0.0;
+  for (int k = threadIdx.x; k < blocks; k += 32) { s += partial[2 * k]; q += partial[2 * k + 1]; }
+#pragma unroll
+  for (int off = 16; off > 0; off >>= 1) {
+    s += __shfl_xor_sync(0xffffffffu, s, off);
+    q += __shfl_xor_sync(0xffffffffu, q, off);
+  }
+  if (threadIdx.x == 0) {
     out[0] = s;
     out[1] = q;
   }
@@ -1736,7 +1749,7 @@ extern "C" int arreau_ponita_backward(const float* params, const arreau_train_la
     // fiber conv backward
     const float* fk = w->fiber_kernel + (size_t)l * kO * kO * kC;
     {
-      fiber_bwd_dx1_kernel<<<(N + 1) / 2, kC, 0, s>>>(b.dx2, fk, N, b.dx1);
+      fiber_bwd_dx1_kernel<<<(N + kDx1Atoms - 1) / kDx1Atoms, kC, 0, s>>>(b.dx2, fk, N, b.dx1);
       CUDA_LAUNCH_CHECK();
       int fb = N < kDfkBlocks ? N : kDfkBlocks;
       fiber_bwd_dfk_kernel<<<fb, 1024, 0, s>>>(x1, b.dx2, N, b.partial);
