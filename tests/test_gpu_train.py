@@ -206,8 +206,11 @@ def test_calibrate_matches_reference(device, gold, weights_npz):
             assert rel_err(v[k[6:]].cpu().numpy(), c[k]) < 1e-4, k
 
 
-def test_larger_batch_against_oracle(device, weights_npz):
-    """A C5-shaped batch (48 crystals, 1..40 atoms): loss and gradients against the oracle's autograd."""
+@pytest.mark.parametrize("precision", ["fp32", "tf32"])
+def test_larger_batch_against_oracle(device, weights_npz, precision):
+    """A C5-shaped batch (48 crystals, 1..40 atoms): loss and gradients against the oracle's autograd -- the fp32 parity
+    path (loss 1e-4, gradients 2e-3 of max|ref| per tensor) and the TF32 path of `train.fit` / `bench.py --workload train`
+    (TMA-fed tcgen05 GEMMs in forward and backward; stated tolerance: loss 1e-3, gradients 4e-3; measured 1.4e-4 / 8.8e-4)."""
     from arreau_b200.synthetic import make_crystals
     from oracle import restatement as R, training as TR
     cr = make_crystals(48, 1, 40, seed=77)
@@ -223,12 +226,15 @@ def test_larger_batch_against_oracle(device, weights_npz):
         loss, grads, parts = TR.training_grads(W, tabs, torch.as_tensor(weights_npz["fourier_w"], dtype=torch.float64),
                                                torch.as_tensor(cr.frac), torch.as_tensor(cr.types), L0,
                                                torch.as_tensor(cr.num_atoms), timestep, eps_x, u, eps_l, 5.0, 8)
-    te = _engine(device, weights_npz, cr.num_atoms)
+    te = _engine(device, weights_npz, cr.num_atoms, backward_precision=precision)
     got, _ = te.loss_and_grads(cr.frac, cr.types, L0.numpy(), timestep.numpy(), eps_x.numpy(), u.numpy(), eps_l.numpy())
-    assert abs(got[0].item() - loss.item()) <= 1e-4 * abs(loss.item())
+    loss_tol, grad_tol = (1e-4, 2e-3) if precision == "fp32" else (1e-3, 4e-3)
+    assert abs(got[0].item() - loss.item()) <= loss_tol * abs(loss.item())
     gv = te.p.grad_views()
-    bad = {k: rel_err(gv[k].cpu().numpy(), grads[k].numpy()) for k in grads}
-    bad = {k: v for k, v in bad.items() if not v < 2e-3}
+    errs = {k: rel_err(gv[k].cpu().numpy(), grads[k].numpy()) for k in grads}
+    print(f"{precision}: loss rel err {abs(got[0].item() - loss.item()) / abs(loss.item()):.2e}, worst gradient error "
+          f"{max(errs.values()):.2e} ({max(errs, key=errs.get)})")
+    bad = {k: v for k, v in errs.items() if not v < grad_tol}
     assert not bad, bad
 
 
@@ -320,18 +326,19 @@ def test_training_reduces_loss_on_a_fixed_batch(device, gold, weights_npz):
 
 
 def test_tf32_backward_against_reference(device, gold, weights_npz):
-    """ARREAU_PRECISION_TF32: every GEMM of the backward pass on TF32 tensor cores (fp32 accumulation).  Stated
-    tolerance: 1e-2 of max|ref| per parameter tensor against the reference's fp64 gradients (measured ~1e-3);
-    the loss itself comes from the fp32 forward and is unchanged."""
+    """ARREAU_PRECISION_TF32: every dense contraction of the training forward and backward on the TMA-fed tcgen05 TF32
+    GEMM (operands rounded to 10 mantissa bits by the TMA engine, fp32 accumulation).  Stated tolerance of this path
+    against the live reference's fp64 loss and gradients (golden fixture): loss 1e-3 (measured 1e-4), every parameter
+    gradient 4e-3 of max|ref| per tensor (measured 1.1e-3)."""
     c = _case(gold("train_c5small.npz"), 0)
     te = _engine(device, weights_npz, c["num_atoms"], backward_precision="tf32")
     loss, _ = te.loss_and_grads(c["frac0"], c["types0"], c["lattice0"], c["timestep"], c["eps_x"], c["u"], c["eps_l"])
-    assert abs(loss[0].item() - float(c["loss"])) <= 1e-4 * abs(float(c["loss"]))
+    assert abs(loss[0].item() - float(c["loss"])) <= 1e-3 * abs(float(c["loss"]))
     gv = te.p.grad_views()
     errs = {k: rel_err(g.cpu().numpy(), c["grad/" + k]) for k, g in gv.items()}
-    bad = {k: v for k, v in errs.items() if not v < 1e-2}
+    print("tf32 loss rel err", abs(loss[0].item() - float(c["loss"])) / abs(float(c["loss"])), "worst gradient error", max(errs.values()))
+    bad = {k: v for k, v in errs.items() if not v < 4e-3}
     assert not bad, bad
-    print("tf32 backward worst gradient error", max(errs.values()))
 
 
 def test_capacity_engine_reuses_buffers_across_topologies(device, weights_npz):
