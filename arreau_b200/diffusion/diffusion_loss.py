@@ -74,6 +74,19 @@ class DiffusionLoss(torch.nn.Module):
         self.backward_precision = "fp32"      # "tf32": tensor-core GEMMs in the backward pass (training.py)
         self.coord_loss_weight = self.atom_type_loss_weight = self.lattice_loss_weight = 1
 
+    @staticmethod
+    def _same_device(have, want) -> bool:
+        """torch.device("cuda") names the current device: it must compare equal to the "cuda:0" a tensor reports."""
+        have, want = torch.device(have), torch.device(want)
+        if have.type != want.type:
+            return False
+        if have.type != "cuda" or have.index == want.index:
+            return True
+        if have.index is not None and want.index is not None:
+            return False
+        cur = torch.cuda.current_device()
+        return (cur if have.index is None else have.index) == (cur if want.index is None else want.index)
+
     # -- engine cache: one per (model weights, topology) --------------------------------------------
     def engine_for(self, model, t_emb_weights, num_atoms, device, debug=False) -> DenoiseEngine:
         net = getattr(model, "model", model)          # PONITA_DIFFUSION.model or a bare PonitaFiberBundle
@@ -86,7 +99,7 @@ class DiffusionLoss(torch.nn.Module):
         stale = getattr(net, "_packed_version", None) != version
         if self._engine is None or self._engine_key != key:
             packed = net._packed if getattr(net, "_packed", None) is not None and not stale \
-                and net._packed.device == torch.device(device) else net.pack(device)
+                and self._same_device(net._packed.device, device) else net.pack(device)
             net._packed_version = version
             fw = t_emb_weights.gaussian_fourier_proj_w if hasattr(t_emb_weights, "gaussian_fourier_proj_w") else t_emb_weights
             self._engine = DenoiseEngine(packed, self.tables, fw, na, self.cutoff, self.max_neighbors,
@@ -106,7 +119,7 @@ class DiffusionLoss(torch.nn.Module):
         (the first batches of the first epoch), so a shuffled epoch does not reallocate (`self.train_engine_builds`
         counts the builds)."""
         from ..training import TrainEngine
-        flat = net.flat if getattr(net, "flat", None) is not None and net.flat.device == torch.device(device) \
+        flat = net.flat if getattr(net, "flat", None) is not None and self._same_device(net.flat.device, device) \
             else net.flatten_parameters(device)
         na = [int(v) for v in torch.as_tensor(num_atoms).reshape(-1).tolist()]
         key = (id(flat), self.backward_precision)

@@ -383,9 +383,14 @@ def test_capacity_engine_reuses_buffers_across_topologies(device, weights_npz):
         shared.set_topology([n_cap + 1])
 
 
-def test_shuffled_epoch_builds_one_engine(device, weights_npz, tmp_path):
+@pytest.mark.parametrize("unindexed", [False, True])
+def test_shuffled_epoch_builds_one_engine(device, weights_npz, tmp_path, unindexed):
     """arreau_b200.train.fit over a shuffled dataset of ragged crystals: DiffusionLoss keeps ONE capacity-based
-    TrainEngine (grown at most a couple of times while the first batches arrive), not one per batch topology."""
+    TrainEngine (grown at most a couple of times while the first batches arrive), not one per batch topology -- also when
+    the caller names the device torch.device("cuda") while the tensors report "cuda:0" (the flat parameter buffer used to
+    be re-created, and `callibrate` read an engine that had never run)."""
+    if unindexed:
+        device = torch.device("cuda")
     from arreau_b200.diffusion.lattice_dataset import CrystalDataset, save_dataset_npz
     from arreau_b200.lightning_wrappers.diffusion import PONITA_DIFFUSION
     from arreau_b200.synthetic import make_crystals

@@ -348,3 +348,12 @@ def test_workspace_bytes_query():
     assert lib.arreau_workspace_bytes(10, 2, 80, _lib.PRECISION_FP16, 95, 21, C.byref(o)) == 0 and o.pool == 0   # Z != 90
     assert lib.arreau_workspace_bytes(-1, 2, 80, 0, 164, 90, C.byref(o)) == -1
     assert lib.arreau_workspace_bytes(10, 2, 80, 2, 164, 90, C.byref(o)) == -2
+
+
+def test_device_names_compare_like_torch_places_tensors():
+    """DiffusionLoss caches engines per parameter buffer and device: "cuda" (the current device) and "cuda:N" must not be
+    taken for different places (it would re-flatten the parameters under the optimizer)."""
+    from arreau_b200.diffusion.diffusion_loss import DiffusionLoss
+    same = DiffusionLoss._same_device
+    assert same("cpu", torch.device("cpu")) and not same("cpu", "cuda") and not same("cuda:0", "cpu")
+    assert same("cuda:1", torch.device("cuda", 1)) and not same("cuda:0", "cuda:1")
