@@ -173,7 +173,8 @@ class DiffusionLoss(torch.nn.Module):
         else:
             eps_x, u, eps_l = noise
         net = getattr(model, "model", model)
-        te = self.train_engine_for(net, t_emb_weights, num_atoms, dev)
+        # the batch topology from the host copy when the collate left one (no device -> host read per step)
+        te = self.train_engine_for(net, t_emb_weights, getattr(batch, "num_atoms_cpu", num_atoms), dev)
         te.loss_and_grads(frac_x_0, atom_type_0, lattice_0, timestep, eps_x, u, eps_l)
         self.last_loss_parts = te.loss
         names = [n for n, p in net.named_parameters() if p.numel() > 0]

@@ -81,6 +81,33 @@ class CrystalDataset(torch.utils.data.Dataset):
         self.z_table = AtomicNumberTable(sorted(zs))
         self.cutoff = cutoff
         self._index = {z: i for i, z in enumerate(self.z_table.zs)}
+        # flat copy of the whole set for the epoch iterator (`collate_indices`): one gather per field instead of a Python
+        # loop over the atoms of every crystal of every batch
+        na = np.asarray([len(np.asarray(c.atomic_numbers).reshape(-1)) for c in self.configs], dtype=np.int64)
+        self._na = na
+        self._off = np.concatenate([[0], np.cumsum(na)]).astype(np.int64)
+        if len(self.configs):
+            lut = np.full(max(zs) + 1, -1, dtype=np.int64)
+            for z, i in self._index.items():
+                lut[z] = i
+            self._A0 = lut[np.concatenate([np.asarray(c.atomic_numbers).reshape(-1).astype(np.int64) for c in self.configs])]
+            self._X0 = np.concatenate([np.asarray(c.X0, dtype=np.float64).reshape(-1, 3) for c in self.configs])
+            self._L0 = np.stack([np.asarray(c.L0, dtype=np.float64) for c in self.configs])
+
+    def collate_indices(self, indices, device=None, pin: bool = True):
+        """`collate_crystals([self[i] for i in indices])` as vectorised gathers over the flat copy (same fields, same values)."""
+        b = np.asarray(indices, dtype=np.int64).reshape(-1)
+        na = self._na[b]
+        total = int(na.sum())
+        # positions of the selected crystals' atoms in the flat arrays: start of each crystal repeated, plus a running index
+        starts = self._off[b]
+        within = np.arange(total, dtype=np.int64) - np.repeat(np.cumsum(na) - na, na)
+        idx = np.repeat(starts, na) + within
+        X0, A0 = self._X0[idx], self._A0[idx]
+        L0m = self._L0[b]
+        batch = np.repeat(np.arange(len(b)), na)
+        pos = np.einsum("bi,bij->bj", X0, L0m[batch])
+        return _to_namespace(dict(X0=X0, A0=A0, L0=L0m.reshape(-1, 3), num_atoms=na, batch=batch, pos=pos), device, pin)
 
     def __len__(self):
         return len(self.configs)
@@ -100,13 +127,19 @@ def collate_crystals(items: Sequence[dict], device=None, pin: bool = True):
     L0 = np.concatenate([it["L0"] for it in items]).astype(np.float64)              # [3G,3] like PyG's cat of [3,3]
     batch = np.repeat(np.arange(len(items)), na)
     pos = np.einsum("bi,bij->bj", X0, L0.reshape(-1, 3, 3)[batch])
-    fields = dict(X0=X0, A0=A0, L0=L0, num_atoms=na, batch=batch, pos=pos)
+    return _to_namespace(dict(X0=X0, A0=A0, L0=L0, num_atoms=na, batch=batch, pos=pos), device, pin)
+
+
+def _to_namespace(fields: dict, device, pin: bool):
     out = {}
     for k, v in fields.items():
-        t = torch.from_numpy(v)
+        t = torch.from_numpy(np.ascontiguousarray(v))
         if device is not None and torch.device(device).type == "cuda":
             t = (t.pin_memory() if pin else t).to(device, non_blocking=True)
         out[k] = t
+    # the atoms-per-crystal vector stays available on the host: the engines bind the batch topology from it without a
+    # device -> host read (which would synchronise every training step)
+    out["num_atoms_cpu"] = np.asarray(fields["num_atoms"], dtype=np.int64).copy()
     return argparse.Namespace(**out)
 
 
@@ -117,7 +150,10 @@ def batches(dataset: CrystalDataset, batch_size: int, shuffle: bool = True, seed
     out of batches early would leave its peers in a collective it never joins: like torch's DistributedSampler
     (drop_last=False) the list of batches is padded to a multiple of `world` by wrapping around to the first ones."""
     for b in batch_index_lists(len(dataset), batch_size, shuffle, seed, rank, world):
-        yield collate_crystals([dataset[int(i)] for i in b], device=device)
+        if hasattr(dataset, "collate_indices"):
+            yield dataset.collate_indices(b, device=device)
+        else:
+            yield collate_crystals([dataset[int(i)] for i in b], device=device)
 
 
 def batch_index_lists(n: int, batch_size: int, shuffle: bool = True, seed: int = 0, rank: int = 0, world: int = 1):

@@ -134,9 +134,13 @@ class DenoiseEngine:
         ext = {"N": N, "G": G, "N+1": N + 1, "G+1": G + 1}
         for name, (kind, buf) in self._bufs.items():
             setattr(self, name, buf[: ext[kind]])
-        self.atom_offset.copy_(torch.as_tensor(off, dtype=torch.int32))
-        self.crystal_of_atom.copy_(torch.as_tensor(np.repeat(np.arange(G), na), dtype=torch.int32))
-        self.num_atoms.copy_(torch.as_tensor(na))
+        # pinned staging + non_blocking: a plain copy_ from pageable memory synchronises the stream, i.e. a training loop
+        # that binds a new topology every step would drain the GPU before enqueueing the next step (the caching host
+        # allocator keeps a staging block alive until its copy has run)
+        stage = (lambda a: torch.as_tensor(a).pin_memory()) if self.device.type == "cuda" else torch.as_tensor
+        self.atom_offset.copy_(stage(off.astype(np.int32)), non_blocking=True)
+        self.crystal_of_atom.copy_(stage(np.repeat(np.arange(G), na).astype(np.int32)), non_blocking=True)
+        self.num_atoms.copy_(stage(na), non_blocking=True)
         groups = (N + 15) // 16
         self.pool = (self._pool_flat[: (LAYERS + 1) * groups * 4 * HIDDEN * 16].view(LAYERS + 1, groups, 4, HIDDEN, 16)
                      if self._pool_flat is not None else None)

@@ -55,7 +55,7 @@ def fit(model: PONITA_DIFFUSION, dataset: CrystalDataset, epochs: int, batch_siz
                 # statistics from the step that has just run, rescale, then the optimizer step.  (Under DDP every
                 # reference rank rescales from its own shard and the replicas silently diverge; here rank 0's scales
                 # are broadcast -- the one deliberate deviation.)
-                te = model.diffusion_loss.train_engine_for(model.model, model.t_emb, batch.num_atoms, device)
+                te = model.diffusion_loss.train_engine_for(model.model, model.t_emb, getattr(batch, "num_atoms_cpu", batch.num_atoms), device)
                 te.calibrate_from_last_forward()
                 broadcast_parameters(flat.data)
                 for layer in model.model.interaction_layers:
