@@ -185,9 +185,12 @@ def test_loss_gradients_wrt_outputs_against_oracle(device, gold, weights_npz):
     assert rel_err(te.dlen0.cpu().numpy(), gn.numpy()) < 1e-6
 
 
-def test_backward_is_deterministic(device, gold, weights_npz):
+@pytest.mark.parametrize("precision", ["fp32", "tf32"])
+def test_backward_is_deterministic(device, gold, weights_npz, precision):
+    """Two runs of the whole step give bit-identical losses and gradients on both precision paths: fixed-order split
+    reductions, per-CTA column sums in a static item order, no atomics."""
     c = _case(gold("train_c5small.npz"), 1)
-    te = _engine(device, weights_npz, c["num_atoms"])
+    te = _engine(device, weights_npz, c["num_atoms"], backward_precision=precision)
     args = (c["frac0"], c["types0"], c["lattice0"], c["timestep"], c["eps_x"], c["u"], c["eps_l"])
     te.loss_and_grads(*args)
     g0, l0 = te.p.grad.clone(), te.loss.clone()
