@@ -357,3 +357,24 @@ def test_device_names_compare_like_torch_places_tensors():
     same = DiffusionLoss._same_device
     assert same("cpu", torch.device("cpu")) and not same("cpu", "cuda") and not same("cuda:0", "cpu")
     assert same("cuda:1", torch.device("cuda", 1)) and not same("cuda:0", "cuda:1")
+
+
+def test_vectorised_collate_matches_the_per_item_collate(tmp_path):
+    """CrystalDataset.collate_indices (what the epoch iterator uses: gathers over a flat copy of the set) returns the
+    same batch as collate_crystals over the items, repeated and out-of-order indices included, plus the host copy of the
+    atoms-per-crystal vector the engines bind the topology from."""
+    from arreau_b200.diffusion.lattice_dataset import CrystalDataset, batches, collate_crystals, save_dataset_npz
+    rng = np.random.default_rng(3)
+    n = 23
+    na = rng.integers(1, 9, size=n)
+    zs = [rng.integers(1, 20, size=k) for k in na]
+    frac = [rng.random((k, 3)) for k in na]
+    lat = rng.random((n, 3, 3)) + np.eye(3) * 3
+    ds = CrystalDataset([save_dataset_npz(str(tmp_path / "d"), zs, lat, frac)])
+    idx = [5, 0, 22, 7, 7, 3]
+    a, b = collate_crystals([ds[i] for i in idx]), ds.collate_indices(idx)
+    for k in ("X0", "A0", "L0", "num_atoms", "batch", "pos"):
+        assert torch.equal(getattr(a, k), getattr(b, k)), k
+    assert np.array_equal(b.num_atoms_cpu, na[idx]) and np.array_equal(a.num_atoms_cpu, na[idx])
+    seen = np.concatenate([x.num_atoms_cpu for x in batches(ds, 5, shuffle=True, seed=2)])
+    assert sorted(seen.tolist()) == sorted(na.tolist())
