@@ -1,4 +1,5 @@
-// Backward pass of the Ponita fiber-bundle network (training step) in fp32, sm_100a.
+// Training step of the Ponita fiber-bundle network on sm_100a: the hand-derived backward pass
+// and, in TF32 mode, the training forward that keeps what the backward needs.
 //
 // The reference obtains parameter gradients with torch autograd through
 //   ponita/models/ponita.py:88-155, ponita/nn/conv.py:105-133, ponita/nn/convnext.py:20-33,
@@ -6,17 +7,24 @@
 // (inputs carry no gradient: positions, lattice and the graph are data).  Here the same derivatives are
 // written out by hand as a fixed sequence of kernels on one stream:
 //
-//   * every dense contraction (recomputed activations, input gradients, weight gradients) goes through ONE
-//     tiled fp32 SIMT GEMM (sgemm_kernel: 128x128x16 tiles, packed FFMA2, register-staged double buffering)
-//     that reads either operand in either storage order, so that the parameters and their gradients stay in
-//     the reference's own state_dict layouts ([out, in] row-major) with no transposed copies;
+//   * every dense contraction (kept or recomputed activations, input gradients, weight gradients) goes through ONE
+//     generic GEMM that reads either operand in either storage order, so that the parameters and their gradients stay
+//     in the reference's own state_dict layouts ([out, in] row-major) with no transposed copies.  Three kernels behind it:
+//       sgemm_kernel      fp32 SIMT (128x128x16 tiles, packed FFMA2): ARREAU_PRECISION_FP32, the parity path;
+//       sgemm_tma_kernel  ARREAU_PRECISION_TF32: persistent, warp-specialised tcgen05 kind::tf32 kernel fed by TMA tensor
+//                         maps, double-buffered TMEM accumulators, fused epilogues (bias, GELU, GELU', residual, column
+//                         sums) -- see the comment above it;
+//       sgemm_tc_kernel   the same product one tile per CTA with register-staged operands: fallback for operands a
+//                         tensor map cannot describe (K < 32, ragged contiguous extents);
 //   * weight gradients reduce over the rows (edges x orientations, or atoms x orientations): split-K with
 //     per-split partial tiles and a fixed-order second stage -- no atomics, bit-reproducible run to run;
 //   * the message pass is transposed with a sender-side gather in edge order (deterministic) instead of
-//     scatter atomics.
+//     scatter atomics; the same pass writes the sender's rows of the kernel gradient.
 //
-// The forward pass of a training step is the ordinary fp32 forward (arreau_ponita_forward) run with its
-// per-layer buffers kept (h, x1, x2 of every layer and the per-layer spatial kernels).
+// The forward pass of a training step is either the ordinary fp32 forward (arreau_ponita_forward) run with its per-layer
+// buffers kept (h, x1, x2 of every layer and the per-layer spatial kernels; the backward then recomputes the rest), or
+// arreau_ponita_forward_train below (TF32 mode): the same mathematics with its dense contractions on the generic GEMM
+// and every activation the backward reads kept in the backward's workspace.
 #include <cuda.h>          // CUtensorMap and its enums only: cuTensorMapEncodeTiled is reached through the runtime
 
 #include "common.cuh"
